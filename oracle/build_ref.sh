@@ -1,0 +1,57 @@
+#!/bin/bash
+#  TEST INFRASTRUCTURE (oracle/) -- not part of the shipped product.
+#
+#  Compiles the UNMODIFIED reference `meryl` (marbl/meryl + meryl-utility) from
+#  the sources where they lie under $REF (default /root/reference) into
+#  oracle/_ref/meryl.  Nothing is copied into this repository: objects, the
+#  generated version.H and the binary all go under oracle/_ref/ (git-ignored).
+#
+#  The reference's own build system is not used (it needs htslib's external
+#  libraries); instead the count/print/statistics/union path is compiled from
+#  its own source files with g++, with the BAM/CRAM reader replaced by
+#  oracle/hts_stub.C.
+#
+#  usage: oracle/build_ref.sh [-f]     (no-op when $REF is absent: the GPU
+#                                       box uses the prebuilt oracle/_ref/meryl)
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${REF:-/root/reference}"
+OUT="$HERE/_ref"
+SRC="$REF/src"
+
+if [ ! -d "$SRC/meryl" ]; then
+  echo "build_ref: $SRC not present; keeping prebuilt $OUT/meryl" >&2
+  exit 0
+fi
+if [ -x "$OUT/meryl" ] && [ "$1" != "-f" ]; then
+  exit 0
+fi
+
+mkdir -p "$OUT/obj" "$OUT/gen"
+( cd /tmp && perl "$SRC/utility/src/version.pl" meryl release v1.4.2 "$OUT/gen/version.H" > /dev/null )
+
+CXX="${REF_CXX:-/usr/bin/g++}"   #  not $CXX: this image exports a wrapper without libgomp
+FLAGS="-std=c++2a -fopenmp -pthread -O3 -DNOBACKTRACE -mxsave -w \
+  -I$OUT/gen -I$SRC -I$SRC/meryl -I$SRC/utility/src -I$SRC/utility/src/sequence"
+
+FILES=""
+for d in bits datastructures files kmers-v1 math system; do
+  FILES="$FILES $(ls $SRC/utility/src/$d/*.C)"
+done
+FILES="$FILES $SRC/utility/src/sequence/dnaSeq-v1.C $SRC/utility/src/sequence/bufSeqFile-v1.C $SRC/utility/src/sequence/sequence-v1.C"
+FILES="$FILES $(ls $SRC/meryl/*.C) $HERE/hts_stub.C"
+
+pids=()
+objs=""
+n=0
+for f in $FILES; do
+  o="$OUT/obj/$(echo "$f" | sed -e 's#/#_#g' -e 's#\.C$#.o#')"
+  objs="$objs $o"
+  $CXX $FLAGS -c "$f" -o "$o" &
+  n=$((n+1))
+  if [ $((n % $(nproc))) -eq 0 ]; then wait; fi
+done
+wait
+$CXX -fopenmp -pthread -O3 -o "$OUT/meryl" $objs -lm
+rm -rf "$OUT/obj"
+echo "build_ref: built $OUT/meryl" >&2
