@@ -1,0 +1,170 @@
+/*
+ *  meryl_b200.h -- C ABI of the B200-native `meryl count` path.
+ *
+ *  The reference (marbl/meryl) has no plugin/FFI interface; the count path sits
+ *  behind two seams and this header mirrors both:
+ *
+ *   process seam     argv word grammar + db directory
+ *                      src/meryl/merylCommandBuilder.C:188-326 (options), :333-435 (operations),
+ *                      :441-563 (output / inputs)          ->  mb_count_files(), and the
+ *                      `meryl-b200` CLI built on it (csrc/cli.cpp)
+ *
+ *   in-process seam  merylOperation::configureCounting()       src/meryl/merylOp-count.C:300-403
+ *                                                          ->  mb_plan()
+ *                    merylOperation::countThreads(wPrefix, nPrefix, wData, wDataMask)
+ *                                                              src/meryl/merylOp.H:210-213,
+ *                                                              src/meryl/merylOp-countThreads.C:385-474
+ *                                                          ->  mb_create() / mb_count() / mb_destroy()
+ *                    merylInput::loadBases(char*, max, &len, &endOfSequence)
+ *                                                              src/meryl/merylInput.H:67-70, merylInput.C:246-271
+ *                                                          ->  mb_add_bases()  (push form of the same pull)
+ *                    bufSeqFile::open / loadBases               src/utility/src/sequence/bufSeqFile-v1.C:54-104, :554-595
+ *                                                          ->  mb_add_file(), mb_add_file_bytes()
+ *                    merylBlockWriter::addBlock / finish, ~merylFileWriter
+ *                                                              src/utility/src/kmers-v1/kmers-writer-block.C:101-218,
+ *                                                              src/utility/src/kmers-v1/kmers-writer.C:118-291
+ *                                                          ->  mb_write_db(), mb_get_image()
+ *
+ *  Conventions: plain pointers and sizes only; every function returns 0 on
+ *  success or a negative MB_E* code and never calls exit(); mb_last_error()
+ *  gives the thread-local message.  A context is bound to one CUDA device and
+ *  must be driven from one host thread at a time.  There is NO CPU fallback:
+ *  without a usable CUDA device mb_create() fails with MB_ENODEVICE.
+ */
+#ifndef MERYL_B200_H
+#define MERYL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK          0
+#define MB_EINVAL     -1     /*  bad argument (k out of range, NULL, ...)                                  */
+#define MB_ENODEVICE  -2     /*  no usable CUDA device / CUDA runtime error                                */
+#define MB_ENOMEM     -3     /*  input does not fit the device workspace                                   */
+#define MB_EIO        -4     /*  cannot read input / write output                                          */
+#define MB_EFORMAT    -5     /*  input is not FASTA/FASTQ (bufSeqFile::open would reject it)               */
+#define MB_ESTATE     -6     /*  call out of order (e.g. mb_write_db before mb_count)                      */
+#define MB_ECOMM      -7     /*  NCCL error                                                                */
+
+/*  merylOp: opCount / opCountForward / opCountReverse  (src/meryl/merylOp.H)  */
+#define MB_MODE_CANONICAL 0
+#define MB_MODE_FORWARD   1
+#define MB_MODE_REVERSE   2
+
+typedef struct mb_ctx mb_ctx;
+
+typedef struct mb_config {
+  uint32_t k;               /*  mer size, 3..64                     (k=)                                    */
+  uint32_t mode;            /*  MB_MODE_*                           (count / count-forward / count-reverse) */
+  uint32_t wPrefix;         /*  prefix bits of the db, from mb_plan (wPrefix of countThreads)               */
+  int32_t  device;          /*  CUDA device ordinal; -1 = current device                                    */
+  uint64_t workspaceBytes;  /*  device arena size; 0 = all free memory minus a margin                       */
+  uint32_t rank;            /*  multi-GPU: this process' rank   (0 when worldSize <= 1)                     */
+  uint32_t worldSize;       /*  multi-GPU: number of ranks (one per GPU); 0 or 1 = single GPU               */
+  uint32_t flags;           /*  MB_FLAG_*                                                                   */
+  uint32_t reserved;
+} mb_config;
+
+#define MB_FLAG_KEEP_COUNTED   1u   /*  keep (distinct k-mer, count) arrays on the host for mb_get_counted (tests)  */
+#define MB_FLAG_NO_IMAGES      2u   /*  do not copy the encoded db to the host (kernel-only benchmarking)           */
+
+typedef struct mb_stats {
+  uint64_t nBases;          /*  positions in the packed store (bases + record breaks)     */
+  uint64_t nKmers;          /*  k-mer instances counted (this rank's share when sharded)  */
+  uint64_t nDistinct;
+  uint64_t nUnique;
+  uint64_t nTotal;          /*  sum of stored counts (== nKmers unless a count wrapped)   */
+  uint64_t dbBytes;         /*  bytes of the 129 images owned by this rank                */
+  uint32_t nPasses;         /*  prefix-range passes used                                  */
+  uint32_t nLaunches;       /*  CUDA kernels launched by mb_count (+ ingest)              */
+  uint64_t h2dBytes;        /*  host->device bytes moved                                  */
+  uint64_t d2hBytes;        /*  device->host bytes moved                                  */
+  /*  device time (CUDA events on the launching stream), milliseconds, summed over passes  */
+  float    msPack;          /*  K1  ASCII -> 2-bit + validity                              */
+  float    msHistogram;     /*  K2a prefix-bin histogram pre-pass                          */
+  float    msExtract;       /*  K2/K3 canonical extraction + prefix scatter                */
+  float    msSortHist;      /*  K4a digit histograms                                       */
+  float    msSort;          /*  K4  onesweep scatter passes                                */
+  float    msCount;         /*  K5  run-length count + value histogram                     */
+  float    msEncode;        /*  K6  block layout + bit scatter                             */
+  float    msExchange;      /*  multi-GPU all-to-all                                       */
+  float    msTotal;         /*  whole mb_count()                                           */
+  uint32_t sortPasses;      /*  onesweep digit passes per key                              */
+  uint32_t keyBytes;        /*  8 (k<=32) or 16                                            */
+  uint64_t sortLaunchKeys;  /*  sum over onesweep launches of keys moved                   */
+} mb_stats;
+
+/*  Thread-local message of the last failing call on this thread.  */
+const char *mb_last_error(void);
+
+/*  == configureCounting: simple-vs-complex decision and findBestPrefixSize
+ *  (src/meryl/merylOp-count.C:119-227, :300-403; simple-mode prefix: merylOp-countSimple.C:196-199).
+ *  nEstimate is what the reference calls _expNumKmers (n= or the sum of input file sizes);
+ *  memBytes is memory= in bytes.  Outputs may be NULL.  */
+int mb_plan(uint32_t k, uint64_t nEstimate, uint64_t memBytes,
+            uint32_t *wPrefix, int *simpleMode, uint64_t *memUsed, uint32_t *nBatches);
+
+/*  _expNumKmers guess for one input file name: src/meryl/merylOp-count.C:410-433.  */
+uint64_t mb_estimate_kmers_in_file(const char *path);
+
+int  mb_create(const mb_config *cfg, mb_ctx **ctx);
+void mb_destroy(mb_ctx *ctx);
+
+/*  Input.  All forms append to the same logical base stream ("record . record . ...",
+ *  src/meryl/merylOp-countThreads.C:139-231); they may be mixed and called repeatedly.  */
+int mb_add_bases(mb_ctx *ctx, const char *bases, uint64_t len, int endOfSequence);  /*  host memory   */
+int mb_add_bases_device(mb_ctx *ctx, const char *dBases, uint64_t len);             /*  device memory, work-buffer format ('.' = break)  */
+int mb_add_file(mb_ctx *ctx, const char *path);                                     /*  FASTA/FASTQ, optionally .gz/.bz2/.xz via popen like the reference  */
+int mb_add_file_bytes(mb_ctx *ctx, const uint8_t *data, uint64_t len);              /*  a FASTA/FASTQ file image in host memory  */
+
+/*  Multi-GPU (one process per GPU).  Rank 0 calls mb_comm_unique_id, the caller broadcasts the
+ *  128 bytes (torch.distributed / MPI / files), every rank calls mb_comm_init before mb_count.  */
+int mb_comm_unique_id(uint8_t id[128]);
+int mb_comm_init(mb_ctx *ctx, const uint8_t id[128]);
+
+/*  Count everything added so far.  After this the encoded db (this rank's files) is in host memory.  */
+int mb_count(mb_ctx *ctx);
+
+/*  Images: which = 0..63 -> 0xFFFFFF.merylData, 64..127 -> 0xFFFFFF.merylIndex, 128 -> merylIndex.
+ *  Pointers stay valid until mb_destroy.  Files not owned by this rank have len 0.  */
+int mb_get_image(mb_ctx *ctx, uint32_t which, const uint8_t **ptr, uint64_t *len);
+
+/*  Writes the files owned by this rank into outDir (created if needed); rank 0 also writes merylIndex.  */
+int mb_write_db(mb_ctx *ctx, const char *outDir);
+
+int mb_get_stats(mb_ctx *ctx, mb_stats *st);
+
+/*  With MB_FLAG_KEEP_COUNTED: the sorted distinct k-mers (hi word only for k > 32) and their counts.  */
+int mb_get_counted(mb_ctx *ctx, const uint64_t **kmerLo, const uint64_t **kmerHi, const uint32_t **count, uint64_t *n);
+
+/*  Value histogram of the master index: ascending values and their occurrences (this rank's share).  */
+int mb_get_histogram(mb_ctx *ctx, const uint64_t **values, const uint64_t **occurrences, uint64_t *n);
+/*  Multi-GPU: rank 0 receives the other ranks' histograms/statistics (gathered by the caller) before writing merylIndex.  */
+int mb_merge_histogram(mb_ctx *ctx, const uint64_t *values, const uint64_t *occurrences, uint64_t n);
+
+/*  One-shot: `meryl k=K [n=N] [memory=GB] count* <paths> output <outDir>` on one GPU.  */
+int mb_count_files(const mb_config *cfg, const char **paths, uint32_t nPaths, const char *outDir, mb_stats *st);
+
+/* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
+
+/*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the
+ *  scatter is unordered), so this returns them sorted ascending.  kmerHi may be NULL for k <= 32.  */
+int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *bases, uint64_t len,
+                          uint64_t *kmerLo, uint64_t *kmerHi, uint64_t cap, uint64_t *n);
+/*  K4 alone: sort `n` keys of `bits` significant bits (keys[] in/out; hi may be NULL).  */
+int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits);
+/*  K6 alone: encode one block like merylFileWriter::writeBlockToFile.  out must hold cap bytes.  */
+int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix, uint64_t n,
+                        const uint64_t *sufLo, const uint64_t *sufHi, const uint32_t *values,
+                        uint8_t *out, uint64_t cap, uint64_t *outLen);
+/*  P1/P2 alone (host parser): file image -> base stream in work-buffer format.  */
+int mb_dbg_parse(const uint8_t *data, uint64_t len, char *out, uint64_t cap, uint64_t *outLen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,248 @@
+"""meryl_b200 -- host-side Python mirror of the B200 `meryl count` path.
+
+The product is the C-ABI shared library ``libmeryl_b200.so`` (built in tree by
+``meryl_b200/csrc/Makefile``; ABI in ``include/meryl_b200.h``) and the
+``meryl-b200`` command line tool.  This module only binds that ABI with ctypes so
+that tests, ``bench.py`` and Python callers can drive it; it contains no compute
+and no fallback: if the library or a CUDA device is missing, calls raise.
+
+The reference has no Python surface; names follow its command words
+(``count``, ``count-forward``, ``count-reverse``, ``k=``, ``n=``, ``memory=``,
+``output``; src/meryl/merylCommandBuilder.C:188-326, :346-348, :441-461).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmeryl_b200.so")
+CLI_PATH = os.path.join(_HERE, "meryl-b200")
+
+MODE_CANONICAL, MODE_FORWARD, MODE_REVERSE = 0, 1, 2
+_MODES = {"count": MODE_CANONICAL, "count-forward": MODE_FORWARD, "count-reverse": MODE_REVERSE}
+
+FLAG_KEEP_COUNTED = 1
+FLAG_NO_IMAGES = 2
+
+
+class MerylB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("meryl_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("k", ctypes.c_uint32), ("mode", ctypes.c_uint32), ("wPrefix", ctypes.c_uint32),
+                ("device", ctypes.c_int32), ("workspaceBytes", ctypes.c_uint64),
+                ("rank", ctypes.c_uint32), ("worldSize", ctypes.c_uint32),
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("nBases", ctypes.c_uint64), ("nKmers", ctypes.c_uint64), ("nDistinct", ctypes.c_uint64),
+                ("nUnique", ctypes.c_uint64), ("nTotal", ctypes.c_uint64), ("dbBytes", ctypes.c_uint64),
+                ("nPasses", ctypes.c_uint32), ("nLaunches", ctypes.c_uint32),
+                ("h2dBytes", ctypes.c_uint64), ("d2hBytes", ctypes.c_uint64),
+                ("msPack", ctypes.c_float), ("msHistogram", ctypes.c_float), ("msExtract", ctypes.c_float),
+                ("msSortHist", ctypes.c_float), ("msSort", ctypes.c_float), ("msCount", ctypes.c_float),
+                ("msEncode", ctypes.c_float), ("msExchange", ctypes.c_float), ("msTotal", ctypes.c_float),
+                ("sortPasses", ctypes.c_uint32), ("keyBytes", ctypes.c_uint32), ("sortLaunchKeys", ctypes.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """The C-ABI library; raises if it has not been built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MerylB200Error(-2, "%s not built; run `make -C meryl_b200/csrc` (no CPU fallback exists)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        u8p, u32p, u64p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)
+        L.mb_last_error.restype = ctypes.c_char_p
+        L.mb_plan.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64, u32p, ctypes.POINTER(ctypes.c_int), u64p, u32p]
+        L.mb_estimate_kmers_in_file.argtypes = [ctypes.c_char_p]
+        L.mb_estimate_kmers_in_file.restype = ctypes.c_uint64
+        L.mb_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(ctypes.c_void_p)]
+        L.mb_destroy.argtypes = [ctypes.c_void_p]
+        L.mb_destroy.restype = None
+        L.mb_add_bases.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
+        L.mb_add_bases_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.mb_add_file.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.mb_add_file_bytes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.mb_comm_unique_id.argtypes = [ctypes.c_void_p]
+        L.mb_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.mb_count.argtypes = [ctypes.c_void_p]
+        L.mb_get_image.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), u64p]
+        L.mb_write_db.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.mb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+        L.mb_get_counted.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.POINTER(ctypes.c_void_p), u64p]
+        L.mb_get_histogram.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), u64p]
+        L.mb_merge_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.mb_count_files.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32,
+                                     ctypes.c_char_p, ctypes.POINTER(Stats)]
+        L.mb_dbg_extract_sorted.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, u64p]
+        L.mb_dbg_sort.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
+        L.mb_dbg_encode_block.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_uint64, u64p]
+        L.mb_dbg_parse.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, u64p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MerylB200Error(rc, (lib().mb_last_error() or b"").decode(errors="replace"))
+
+
+@dataclass
+class Plan:
+    w_prefix: int
+    simple: bool
+    mem_used: int
+    n_batches: int
+
+
+def plan(k: int, n_estimate: int, memory_bytes: int) -> Plan:
+    """== configureCounting (src/meryl/merylOp-count.C:300-403): the prefix width the reference picks."""
+    wp, simple = ctypes.c_uint32(0), ctypes.c_int(0)
+    used, nb = ctypes.c_uint64(0), ctypes.c_uint32(0)
+    _check(lib().mb_plan(k, n_estimate, memory_bytes, ctypes.byref(wp), ctypes.byref(simple), ctypes.byref(used), ctypes.byref(nb)))
+    return Plan(wp.value, bool(simple.value), used.value, nb.value)
+
+
+def estimate_kmers_in_file(path: str) -> int:
+    return lib().mb_estimate_kmers_in_file(os.fsencode(path))
+
+
+class Counter:
+    """One counting job on one GPU (== one merylOperation::countThreads call)."""
+
+    def __init__(self, k: int, w_prefix: int, operation: str = "count", device: int = -1,
+                 workspace_bytes: int = 0, flags: int = 0, rank: int = 0, world_size: int = 1):
+        if operation not in _MODES:
+            raise ValueError("operation must be one of %s" % sorted(_MODES))
+        self.k, self.w_prefix = k, w_prefix
+        cfg = _Config(k, _MODES[operation], w_prefix, device, workspace_bytes, rank, world_size, flags, 0)
+        self._h = ctypes.c_void_p()
+        _check(lib().mb_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().mb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- input (merylInput::loadBases seam) ----
+    def add_bases(self, bases: bytes, end_of_sequence: bool = True) -> None:
+        _check(lib().mb_add_bases(self._h, bases, len(bases), int(end_of_sequence)))
+
+    def add_bases_ptr(self, ptr: int, n: int, end_of_sequence: bool = True) -> None:
+        _check(lib().mb_add_bases(self._h, ctypes.c_void_p(ptr), n, int(end_of_sequence)))
+
+    def add_bases_device(self, dev_ptr: int, n: int) -> None:
+        _check(lib().mb_add_bases_device(self._h, ctypes.c_void_p(dev_ptr), n))
+
+    def add_file(self, path: str) -> None:
+        _check(lib().mb_add_file(self._h, os.fsencode(path)))
+
+    def add_file_bytes(self, data: bytes) -> None:
+        _check(lib().mb_add_file_bytes(self._h, data, len(data)))
+
+    def add_file_bytes_ptr(self, ptr: int, n: int) -> None:
+        _check(lib().mb_add_file_bytes(self._h, ctypes.c_void_p(ptr), n))
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _check(lib().mb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes) -> None:
+        _check(lib().mb_comm_init(self._h, unique_id))
+
+    # ---- run / results ----
+    def count(self) -> None:
+        _check(lib().mb_count(self._h))
+
+    def write_db(self, out_dir: str) -> None:
+        _check(lib().mb_write_db(self._h, os.fsencode(out_dir)))
+
+    def image(self, which: int) -> bytes:
+        p, n = ctypes.c_void_p(), ctypes.c_uint64(0)
+        _check(lib().mb_get_image(self._h, which, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p, n.value) if n.value else b""
+
+    def stats(self) -> Stats:
+        st = Stats()
+        _check(lib().mb_get_stats(self._h, ctypes.byref(st)))
+        return st
+
+    def counted(self):
+        """(lo, hi, count) numpy arrays of the distinct k-mers (needs FLAG_KEEP_COUNTED)."""
+        import numpy as np
+        lo, hi, cnt, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64(0)
+        _check(lib().mb_get_counted(self._h, ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(cnt), ctypes.byref(n)))
+        m = n.value
+
+        def arr(p, t):
+            if not m or not p.value:
+                return np.zeros(m, dtype=t)
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(np.ctypeslib.as_ctypes_type(t))), shape=(m,)).copy()
+        return arr(lo, np.uint64), arr(hi, np.uint64), arr(cnt, np.uint32)
+
+    def histogram(self):
+        import numpy as np
+        v, o, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64(0)
+        _check(lib().mb_get_histogram(self._h, ctypes.byref(v), ctypes.byref(o), ctypes.byref(n)))
+        m = n.value
+        if not m:
+            return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+        f = lambda p: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), shape=(m,)).copy()
+        return f(v), f(o)
+
+    def merge_histogram(self, values, occurrences) -> None:
+        import numpy as np
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        occurrences = np.ascontiguousarray(occurrences, dtype=np.uint64)
+        _check(lib().mb_merge_histogram(self._h, values.ctypes.data, occurrences.ctypes.data, len(values)))
+
+
+def count(inputs, output: str, k: int, operation: str = "count", memory_gb: float | None = None,
+          n: int | None = None, device: int = -1) -> Stats:
+    """`meryl k=K [n=N] [memory=GB] count <inputs> output <output>` on one GPU."""
+    inputs = [inputs] if isinstance(inputs, (str, os.PathLike)) else list(inputs)
+    if n is None or n == 0:
+        n = sum(estimate_kmers_in_file(os.fspath(p)) for p in inputs)
+    if memory_gb is None:
+        memory_bytes = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    else:
+        memory_bytes = int(memory_gb * 1024 * 1024 * 1024)
+    pl = plan(k, n, memory_bytes)
+    with Counter(k, pl.w_prefix, operation, device) as c:
+        for p in inputs:
+            c.add_file(os.fspath(p))
+        c.count()
+        c.write_db(os.fspath(output))
+        return c.stats()

@@ -1,0 +1,123 @@
+//  meryl-b200: the `meryl count` command line on a B200.
+//
+//  Keeps the count-relevant subset of the reference's word grammar
+//  (src/meryl/merylCommandBuilder.C:188-326 options, :346-348 operations, :441-461 output,
+//  :538-549 sequence inputs; usage text src/meryl/meryl.C:96-171):
+//
+//      meryl-b200 [-V|-Q|-P|-C] [k=K] [n=N] [memory=GB] [threads=T]
+//                 count|count-forward|count-reverse <seq files...> output <db.meryl>
+//
+//  Words are order-free like the reference's.  Errors are a message on stderr and exit(1)
+//  (missing k: merylOp-count.C:311-312; missing output: :314-315).  Any other operation (union-sum,
+//  print, statistics, ...) is not part of this tool: if $MERYL_REFERENCE names the reference
+//  binary the whole command line is handed to it unchanged, otherwise it is an error.
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <string>
+#include <vector>
+
+#include "../../include/meryl_b200.h"
+
+static uint64_t physicalMemory(void) {          //  getMaxMemoryAllowed(), src/utility/src/system/system-v1.C:216-238
+  uint64_t m = (uint64_t)sysconf(_SC_PHYS_PAGES) * (uint64_t)sysconf(_SC_PAGESIZE);
+  const char *cpu = getenv("SLURM_JOB_CPUS_PER_NODE"), *env = getenv("SLURM_MEM_PER_CPU");
+  if (env && cpu) { uint64_t v = strtoull(cpu, 0, 10) * strtoull(env, 0, 10) * 1024 * 1024; if (v < m) m = v; }
+  if ((env = getenv("SLURM_MEM_PER_NODE"))) { uint64_t v = strtoull(env, 0, 10) * 1024 * 1024; if (v < m) m = v; }
+  if ((env = getenv("PBS_RESC_MEM")))       { uint64_t v = strtoull(env, 0, 10); if (v < m) m = v; }
+  return m ? m : UINT64_MAX;
+}
+
+static bool isCountWord(const char *w, uint32_t *mode) {
+  if (!strcmp(w, "count"))         { *mode = MB_MODE_CANONICAL; return true; }
+  if (!strcmp(w, "count-forward")) { *mode = MB_MODE_FORWARD;   return true; }
+  if (!strcmp(w, "count-reverse")) { *mode = MB_MODE_REVERSE;   return true; }
+  return false;
+}
+
+int main(int argc, char **argv) {
+  uint32_t k = 0, mode = 0;
+  uint64_t nExpected = 0, memBytes = physicalMemory();
+  bool haveOp = false, onlyConfig = false, quiet = false;
+  const char *outDir = nullptr;
+  std::vector<const char *> inputs;
+
+  for (int i = 1; i < argc; i++) {
+    const char *w = argv[i];
+    if      (!strncmp(w, "-V", 2))            { }
+    else if (!strcmp(w, "-Q"))                { quiet = true; }
+    else if (!strcmp(w, "-P"))                { }
+    else if (!strcmp(w, "-C"))                { onlyConfig = true; }
+    else if (!strncmp(w, "k=", 2))            { k = (uint32_t)strtoul(w + 2, 0, 10); }
+    else if (!strncmp(w, "n=", 2))            { nExpected = strtoull(w + 2, 0, 10); }
+    else if (!strncmp(w, "memory=", 7))       { memBytes = (uint64_t)(strtod(w + 7, 0) * 1024 * 1024 * 1024); }
+    else if (!strncmp(w, "threads=", 8))      { }                         //  no CPU worker threads to size
+    else if (isCountWord(w, &mode))           { haveOp = true; }
+    else if (!strcmp(w, "output")) {
+      if (i + 1 >= argc) { fprintf(stderr, "ERROR: 'output' needs a database name.\n"); return 1; }
+      outDir = argv[++i];
+    }
+    else if (!strcmp(w, "[") || !strcmp(w, "]")) { }
+    else if (access(w, R_OK) == 0 || !strcmp(w, "-")) { inputs.push_back(w); }
+    else {
+      //  not a count command line: the reference handles everything else
+      const char *ref = getenv("MERYL_REFERENCE");
+      if (ref) { execv(ref, argv); perror("execv"); return 1; }
+      fprintf(stderr, "ERROR: word '%s' is not part of `meryl count` (operation, option or readable input file).\n", w);
+      fprintf(stderr, "       meryl-b200 implements count, count-forward and count-reverse; set MERYL_REFERENCE=<path to meryl>\n");
+      fprintf(stderr, "       to have every other command line passed to the reference binary.\n");
+      return 1;
+    }
+  }
+
+  if (!haveOp) {
+    const char *ref = getenv("MERYL_REFERENCE");
+    if (ref) { execv(ref, argv); perror("execv"); return 1; }
+    fprintf(stderr, "usage: %s [k=K] [n=N] [memory=GB] count|count-forward|count-reverse <sequence files> output <db.meryl>\n", argv[0]);
+    return 1;
+  }
+  if (k == 0)                    { fprintf(stderr, "ERROR: Kmer size not supplied with modifier k=<kmer-size>.\n"); return 1; }
+  if (!outDir && !onlyConfig)    { fprintf(stderr, "ERROR: No output specified for count operation.\n"); return 1; }
+  if (inputs.empty())            { fprintf(stderr, "ERROR: No sequence inputs for count operation.\n"); return 1; }
+
+  if (nExpected == 0)
+    for (const char *p : inputs) nExpected += mb_estimate_kmers_in_file(p);
+
+  uint32_t wPrefix = 0, nBatches = 0;  int simple = 0;  uint64_t memUsed = 0;
+  if (mb_plan(k, nExpected, memBytes, &wPrefix, &simple, &memUsed, &nBatches) != MB_OK) {
+    fprintf(stderr, "ERROR: %s\n", mb_last_error());
+    return 1;
+  }
+  if (!quiet) {
+    fprintf(stderr, "\nCounting %llu (estimated) %s %u-mers from %zu input file%s.\n", (unsigned long long)nExpected,
+            mode == MB_MODE_CANONICAL ? "canonical" : mode == MB_MODE_FORWARD ? "forward" : "reverse",
+            k, inputs.size(), inputs.size() == 1 ? "" : "s");
+    //  This line is parsed by Canu (merylOp-count.C:398-401); keep its shape.
+    fprintf(stderr, "Configured %s mode for %.3f GB memory per batch, and up to %u batch%s.\n",
+            simple ? "simple" : "complex", (memUsed < memBytes ? memUsed : memBytes) / 1024.0 / 1024.0 / 1024.0,
+            nBatches, nBatches == 1 ? "" : "es");
+    fprintf(stderr, "Database prefix width %u bits (%u file bits + %u block bits), suffix %u bits.\n\n", wPrefix, 6, wPrefix - 6, 2 * k - wPrefix);
+  }
+  if (onlyConfig) return 0;
+
+  mb_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.k = k;  cfg.mode = mode;  cfg.wPrefix = wPrefix;  cfg.device = -1;
+
+  mb_stats st;
+  if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), outDir, &st) != MB_OK) {
+    fprintf(stderr, "ERROR: %s\n", mb_last_error());
+    return 1;
+  }
+  if (!quiet) {
+    fprintf(stderr, "Counted %llu %u-mers (%llu distinct, %llu unique) in %u pass%s, %.1f ms on the device.\n",
+            (unsigned long long)st.nKmers, k, (unsigned long long)st.nDistinct, (unsigned long long)st.nUnique,
+            st.nPasses, st.nPasses == 1 ? "" : "es", st.msTotal);
+    fprintf(stderr, "  histogram %.2f  extract %.2f  sort %.2f+%.2f  count %.2f  encode %.2f ms;  db %llu bytes\n",
+            st.msHistogram, st.msExtract, st.msSortHist, st.msSort, st.msCount, st.msEncode, (unsigned long long)st.dbBytes);
+    fprintf(stderr, "\nFinished counting.\n");
+  }
+  return 0;
+}

@@ -1,0 +1,81 @@
+//  Shared host-side declarations for the B200 `meryl count` engine.
+#pragma once
+
+#include <stdint.h>
+#include <stddef.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+
+#include "../../include/meryl_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int       u32;
+
+//  Thread-local error string behind mb_last_error().
+int  mb_fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+void mb_clear_error(void);
+
+#define MB_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return mb_fail(MB_ENODEVICE, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define MB_TRY(call)  do { int r_ = (call); if (r_ != MB_OK) return r_; } while (0)
+
+//  Bin (pass-planning / partition) granularity: the top binBits bits of the k-mer.
+//  Always block aligned because binBits <= wPrefix.
+static inline u32 mb_bin_bits(u32 wPrefix) { return wPrefix < 10 ? wPrefix : 10; }
+
+//  ---- planner (planner.cpp) ---------------------------------------------------------------
+struct MbPlan {
+  u32  wPrefix;
+  int  simple;
+  u64  memUsed;
+  u32  nBatches;
+};
+int mb_plan_impl(u32 k, u64 nEstimate, u64 memBytes, MbPlan *out);
+
+//  ---- host FASTA/FASTQ parser (parser.cpp) --------------------------------------------------
+//  Byte-level state machine equivalent to bufSeqFile::open + loadBases + the '.' record breaks of
+//  the reference's work-buffer builder.  Emits the base stream through a sink callback.
+class SeqParser {
+public:
+  typedef int (*Sink)(void *arg, const char *bases, size_t n);   //  appends to the logical base stream
+  SeqParser(Sink sink, void *arg) : _sink(sink), _arg(arg) {}
+
+  //  Feed consecutive pieces of ONE file; call finish() at its end.
+  int  feed(const uint8_t *d, size_t n);
+  int  finish(void);
+
+  //  Format check on the first bytes of a file (needs >= 1001 bytes or the whole file).
+  static bool sniff(const uint8_t *d, size_t n);
+
+private:
+  int  emit(const uint8_t *p, size_t n) { return n ? _sink(_arg, (const char *)p, n) : 0; }
+  int  brk(void)                        { static const char dot = '.'; return _sink(_arg, &dot, 1); }
+
+  enum State { A, P1, P1CR, P2, P2CR, Q, H, HCR, L, W, G };
+  State  _st = A;
+  Sink   _sink;
+  void  *_arg;
+};
+
+//  ---- db assembly on the host (dbwriter.cpp) ------------------------------------------------
+struct MbHistogram {                      //  value -> occurrences, plus the master-index totals
+  std::vector<u64> values, occ;           //  ascending by value
+  u64 nUnique = 0, nDistinct = 0, nTotal = 0;
+};
+
+struct MbDbImages {
+  std::vector<uint8_t> data[64];
+  std::vector<uint8_t> index[64];
+  std::vector<uint8_t> master;
+  bool owned[64];                         //  files this rank owns
+};
+
+void mb_build_master_index(u32 k, u32 wPrefix, const MbHistogram &h, std::vector<uint8_t> &out);
+int  mb_write_db_dir(const MbDbImages &db, const char *dir, bool writeMaster);
+void mb_file_name(char *out, size_t cap, const char *dir, u32 file, bool isIndex);

@@ -1,0 +1,224 @@
+//  K5: run-length count of the sorted k-mers, and the count-value histogram.
+//
+//  Replaces the counting half of merylCountArray::countSingleKmers
+//  (src/meryl/merylCountArray.C:334-360: one pass over the sorted suffixes, a new (kmer, count)
+//  entry at every change) and merylHistogram::addValue (src/utility/src/kmers-v1/kmers-histogram.H:41-55).
+//
+//  count_kernel: single pass, chained-scan (decoupled look-back) stream compaction.  A tile of
+//  256 x ITEMS keys marks run heads with warp ballots (key != predecessor), scans them, obtains
+//  its exclusive distinct-count from the look-back chain, then writes each head's key to
+//  keys[out] IN PLACE and its index to runStart[out].  In place is safe: compaction only moves
+//  data towards lower indexes, a tile publishes its aggregate only after its own keys are in
+//  registers, and a tile writes only after it has read every earlier aggregate.
+//  count_j = runStart[j+1] - runStart[j]  (truncated to 32 bits like the reference's kmvalu).
+//
+//  HBM bytes per key instance: W read + (W + 8) * D/N written.  Bound: HBM bandwidth.
+
+#include "kernels.cuh"
+
+namespace {
+
+const int CNT_THREADS = 256;
+const int CNT_WARPS   = CNT_THREADS / 32;
+
+template <int KW> struct CountShape;
+template <> struct CountShape<1> { static const int ITEMS = 16; };
+template <> struct CountShape<2> { static const int ITEMS = 8;  };
+
+template <int KW>
+__global__ void __launch_bounds__(CNT_THREADS)
+count_kernel(typename KeyT<KW>::type *keys, u64 nKeys, u64 *__restrict__ runStart, u64 *__restrict__ numDistinct,
+             u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
+  typedef typename KeyT<KW>::type Key;
+  const int ITEMS = CountShape<KW>::ITEMS;
+  const int TILE  = CNT_THREADS * ITEMS;
+
+  __shared__ u32 warpTot[CNT_WARPS];
+  __shared__ u64 sTile, sExcl;
+
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+  const u64 tile  = sTile;
+  const u64 begin = tile * TILE;
+  const u64 left  = nKeys - begin;
+  const u32 n     = left > (u64)TILE ? (u32)TILE : (u32)left;
+
+  //  warp-striped load; head flags by comparing with the predecessor in index order
+  Key key[ITEMS];
+  u32 heads = 0;                                             //  bit i: my item i starts a run
+  const u32 wbase = warp * 32 * ITEMS;
+  Key carry;                                                 //  last key of the previous row (lane 31's)
+  {
+    const u64 g = begin + wbase;
+    if (lane == 0 && g > 0 && wbase < n) carry = keys[g - 1];
+  }
+  u32 before[ITEMS];                                         //  heads in this warp before my item i
+  u32 wrun = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const u32 j = wbase + i * 32 + lane;
+    const bool in = j < n;
+    if (in) key[i] = keys[begin + j];
+    //  predecessor: lane-1's key of this row, or the carry for lane 0
+    Key prev;
+    if (KW == 1) {
+      u64 up = __shfl_up_sync(0xffffffffu, key_lo(key[i]), 1);
+      *(u64 *)&prev = up;
+    } else {
+      u64 upl = __shfl_up_sync(0xffffffffu, key_lo(key[i]), 1);
+      u64 uph = __shfl_up_sync(0xffffffffu, key_hi(key[i]), 1);
+      ((u64 *)&prev)[0] = upl;  ((u64 *)&prev)[1] = uph;
+    }
+    if (lane == 0) prev = carry;
+    const bool first = (begin + j == 0);
+    const bool head  = in && (first || !key_eq(key[i], prev));
+    const u32  b     = __ballot_sync(0xffffffffu, head);
+    before[i] = wrun + __popc(b & ((1u << lane) - 1));
+    wrun += __popc(b);
+    if (head) heads |= 1u << i;
+    //  carry for the next row = this row's lane 31
+    if (KW == 1) {
+      u64 c = __shfl_sync(0xffffffffu, key_lo(key[i]), 31);
+      *(u64 *)&carry = c;
+    } else {
+      u64 cl = __shfl_sync(0xffffffffu, key_lo(key[i]), 31);
+      u64 ch = __shfl_sync(0xffffffffu, key_hi(key[i]), 31);
+      ((u64 *)&carry)[0] = cl;  ((u64 *)&carry)[1] = ch;
+    }
+  }
+
+  if (lane == 0) warpTot[warp] = wrun;
+  __syncthreads();                                           //  every key of the tile is in registers now
+
+  u32 wOff = 0, tileTot = 0;
+#pragma unroll
+  for (int w = 0; w < CNT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) wOff += c; tileTot += c; }
+
+  //  look back (one thread)
+  if (t == 0) {
+    u64 excl = 0;
+    if (tile == 0) {
+      st_volatile_u64(status + tile, MB_ST_INC | tileTot);
+    } else {
+      st_volatile_u64(status + tile, MB_ST_AGG | tileTot);
+      u64 j = tile - 1;
+      for (;;) {
+        const u64 v = ld_volatile_u64(status + j);
+        if ((v >> 62) == 0) continue;
+        excl += v & MB_ST_MASK;
+        if ((v >> 62) == 2) break;
+        j--;
+      }
+      st_volatile_u64(status + tile, MB_ST_INC | (excl + tileTot));
+    }
+    sExcl = excl;
+    if (begin + n == nKeys) {                                //  last tile: totals and the sentinel
+      *numDistinct = excl + tileTot;
+      runStart[excl + tileTot] = nKeys;
+    }
+  }
+  __syncthreads();
+
+  const u64 outBase = sExcl + wOff;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    if (heads & (1u << i)) {
+      const u64 o = outBase + before[i];
+      keys[o]     = key[i];
+      runStart[o] = begin + wbase + i * 32 + lane;
+    }
+  }
+}
+
+//  ---- value histogram --------------------------------------------------------------------------
+
+const int VH_THREADS = 256;
+const int VH_SMEM    = 1024;
+
+__global__ void __launch_bounds__(VH_THREADS)
+value_hist_kernel(const u64 *__restrict__ runStart, const u64 *__restrict__ numDistinct,
+                  u64 *__restrict__ histSmall, u32 *__restrict__ histBig, u64 *__restrict__ histBigN, u64 histBigCap,
+                  u64 *__restrict__ totals) {
+  __shared__ u32 sh[VH_SMEM];
+  __shared__ u64 sTot[3];
+  const u32 t = threadIdx.x;
+  for (u32 i = t; i < VH_SMEM; i += VH_THREADS) sh[i] = 0;
+  if (t < 3) sTot[t] = 0;
+  __syncthreads();
+
+  const u64 D = *numDistinct;
+  u64 uniq = 0, dist = 0, tot = 0;
+  for (u64 j = (u64)blockIdx.x * VH_THREADS + t; j < D; j += (u64)gridDim.x * VH_THREADS) {
+    const u32 c = (u32)(runStart[j + 1] - runStart[j]);      //  kmvalu is 32 bits and wraps (merylCountArray.C:357)
+    if (c == 0) continue;                                    //  addValue ignores zero
+    uniq += (c == 1);
+    dist += 1;
+    tot  += c;
+    if (c < VH_SMEM)             atomicAdd(&sh[c], 1u);
+    else if (c < MB_HIST_SMALL)  atomicAdd((unsigned long long *)&histSmall[c], 1ull);
+    else {
+      const u64 slot = atomicAdd((unsigned long long *)histBigN, 1ull);
+      if (slot < histBigCap) histBig[slot] = c;
+    }
+  }
+
+  //  block reduction of the three totals
+  for (int o = 16; o > 0; o >>= 1) {
+    uniq += __shfl_down_sync(0xffffffffu, uniq, o);
+    dist += __shfl_down_sync(0xffffffffu, dist, o);
+    tot  += __shfl_down_sync(0xffffffffu, tot,  o);
+  }
+  if ((t & 31) == 0) {
+    atomicAdd((unsigned long long *)&sTot[0], (unsigned long long)uniq);
+    atomicAdd((unsigned long long *)&sTot[1], (unsigned long long)dist);
+    atomicAdd((unsigned long long *)&sTot[2], (unsigned long long)tot);
+  }
+  __syncthreads();
+  if (t < 3 && sTot[t]) atomicAdd((unsigned long long *)&totals[t], (unsigned long long)sTot[t]);
+  for (u32 i = t; i < VH_SMEM; i += VH_THREADS)
+    if (sh[i]) atomicAdd((unsigned long long *)&histSmall[i], (unsigned long long)sh[i]);
+}
+
+}  //  namespace
+
+
+static u64 count_tiles(u32 keyWords, u64 nKeys) {
+  const u64 tile = CNT_THREADS * (keyWords == 1 ? CountShape<1>::ITEMS : CountShape<2>::ITEMS);
+  return (nKeys + tile - 1) / tile;
+}
+
+//  workspace: [tile counter: 1 u64 (padded to 2)][status: nTiles u64]
+size_t mb_count_workspace_bytes(u64 nKeys) {
+  return (2 + count_tiles(1, nKeys) + count_tiles(2, nKeys)) * sizeof(u64);
+}
+
+cudaError_t mb_launch_count(u32 keyWords, void *dKeys, u64 nKeys, u64 *dRunStart, u64 *dNumDistinct,
+                            void *dWorkspace, cudaStream_t s) {
+  cudaError_t e;
+  if (nKeys == 0) {
+    if ((e = cudaMemsetAsync(dNumDistinct, 0, sizeof(u64), s)) != cudaSuccess) return e;
+    return cudaMemsetAsync(dRunStart, 0, sizeof(u64), s);
+  }
+  const u64 nTiles = count_tiles(keyWords, nKeys);
+  if ((e = cudaMemsetAsync(dWorkspace, 0, (2 + nTiles) * sizeof(u64), s)) != cudaSuccess) return e;
+  u64 *counter = (u64 *)dWorkspace, *status = counter + 2;
+  if (keyWords == 1) count_kernel<1><<<(unsigned)nTiles, CNT_THREADS, 0, s>>>((u64 *)dKeys, nKeys, dRunStart, dNumDistinct, status, counter);
+  else               count_kernel<2><<<(unsigned)nTiles, CNT_THREADS, 0, s>>>((ulonglong2 *)dKeys, nKeys, dRunStart, dNumDistinct, status, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t mb_launch_value_histogram(const u64 *dRunStart, const u64 *dNumDistinct, u64 nMaxDistinct,
+                                      u64 *dHistSmall, u32 *dHistBig, u64 *dHistBigN, u64 histBigCap,
+                                      u64 *dTotals, cudaStream_t s) {
+  if (nMaxDistinct == 0) return cudaSuccess;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 grid = (nMaxDistinct + VH_THREADS - 1) / VH_THREADS;
+  const u64 cap = (u64)sms * 8;
+  if (grid > cap) grid = cap;
+  value_hist_kernel<<<(unsigned)grid, VH_THREADS, 0, s>>>(dRunStart, dNumDistinct, dHistSmall, dHistBig, dHistBigN, histBigCap, dTotals);
+  return cudaGetLastError();
+}

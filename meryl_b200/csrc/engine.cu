@@ -1,0 +1,752 @@
+//  Host orchestration of the device-resident `meryl count` (the role of
+//  merylOperation::countThreads, src/meryl/merylOp-countThreads.C:385-474, and of the
+//  merylBlockWriter it drives).
+//
+//  One context == one GPU.  All device memory is one arena, carved by the host:
+//
+//    [ packed read store | zero pad ][ control block ][ value histogram ] ... pass buffers ...  [ ingest staging x2 ]
+//
+//  Ingest (mb_add_*): the base stream is collected in pinned host buffers, copied to the device and
+//  packed (K1) into the store, asynchronously, while the host keeps parsing.
+//  Count (mb_count):
+//    1. K2a bin histogram over the store -> exact number of k-mers per prefix bin (top 10 bits);
+//    2. passes: consecutive bin ranges whose k-mers fit the key buffers.  A prefix is never split
+//       between passes, so no merge step exists and counts equal the reference's single batch;
+//    3. per pass: K2/K3 extract+scatter -> K4 segmented radix sort -> K5 run-length count ->
+//       value histogram -> K6 encode -> device-to-host copy of the encoded blocks and index entries.
+//  The host only appends the encoded bytes to the 64 file images and builds the master index.
+
+#include <algorithm>
+#include <map>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+#include <fcntl.h>
+
+#include "common.h"
+#include "kernels.cuh"
+#include "engine.h"
+
+namespace {
+
+const size_t kAlign      = 256;
+const size_t kStageBytes = (size_t)64 << 20;        //  ingest staging buffer (multiple of 32)
+
+inline size_t alignUp(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+struct EventTimer {                                  //  device time of a stream section
+  cudaEvent_t a = nullptr, b = nullptr;
+  void init()                         { cudaEventCreate(&a); cudaEventCreate(&b); }
+  void destroy()                      { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+  void start(cudaStream_t s)          { cudaEventRecord(a, s); }
+  void stop (cudaStream_t s)          { cudaEventRecord(b, s); }
+  float ms()                          { float m = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&m, a, b); return m; }
+};
+
+}  //  namespace
+
+
+struct mb_ctx {
+  mb_config   cfg;
+  int         device     = 0;
+  u32         keyWords   = 1;
+  u32         binBits    = 10;
+  cudaStream_t stream    = nullptr;
+
+  uint8_t    *arena      = nullptr;
+  size_t      arenaBytes = 0;
+
+  //  store
+  u64         nRecords   = 0;                        //  records filled so far
+  size_t      storeLimit = 0;                        //  bytes the store may grow to during ingest
+
+  //  ingest staging
+  char       *hStage[2]  = { nullptr, nullptr };
+  uint8_t    *dStage[2]  = { nullptr, nullptr };
+  cudaEvent_t evH2D[2]   = { nullptr, nullptr };     //  hStage[i] has been copied
+  size_t      fill       = 0;
+  int         cur        = 0;
+  bool        inRecord   = false;                    //  bases since the last '.'
+
+  //  results
+  bool        counted    = false;
+  MbDbImages  db;
+  MbHistogram hist;
+  mb_stats    st;
+  std::vector<u64> cLo, cHi;                         //  MB_FLAG_KEEP_COUNTED
+  std::vector<u32> cCnt;
+  std::vector<u64> sortedLo, sortedHi;               //  debug: all k-mers, sorted (stopAfterSort)
+  bool        stopAfterSort = false;
+
+  MbComm     *comm       = nullptr;                  //  multi-GPU (exchange.cu)
+};
+
+
+//  ------------------------------------------------------------------------------------------
+//  creation / destruction
+//  ------------------------------------------------------------------------------------------
+
+extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
+  mb_clear_error();
+  if (!cfg || !out)                       return mb_fail(MB_EINVAL, "mb_create: NULL argument");
+  if (cfg->k < 3 || cfg->k > 64)          return mb_fail(MB_EINVAL, "mb_create: k=%u outside 3..64", cfg->k);
+  if (cfg->mode > MB_MODE_REVERSE)        return mb_fail(MB_EINVAL, "mb_create: bad mode %u", cfg->mode);
+  if (cfg->wPrefix < 6 || cfg->wPrefix > 2 * cfg->k || cfg->wPrefix > 40)
+    return mb_fail(MB_EINVAL, "mb_create: wPrefix=%u unusable for k=%u (need 6..min(2k,40))", cfg->wPrefix, cfg->k);
+
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return mb_fail(MB_ENODEVICE, "mb_create: no CUDA device (this library has no CPU path)");
+
+  mb_ctx *c = new mb_ctx();
+  c->cfg = *cfg;
+  if (cfg->device >= 0) { c->device = cfg->device; MB_CUDA(cudaSetDevice(c->device)); }
+  else                  { MB_CUDA(cudaGetDevice(&c->device)); }
+
+  cudaDeviceProp prop;
+  MB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10) {
+    const int dev = c->device;
+    delete c;
+    return mb_fail(MB_ENODEVICE, "mb_create: device %d is sm_%d%d; this build is sm_100a only", dev, prop.major, prop.minor);
+  }
+
+  c->keyWords = cfg->k <= 32 ? 1 : 2;
+  c->binBits  = mb_bin_bits(cfg->wPrefix);
+  memset(&c->st, 0, sizeof(c->st));
+  c->st.keyBytes = 8 * c->keyWords;
+  for (u32 f = 0; f < 64; f++) c->db.owned[f] = true;
+
+  MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+  size_t want = cfg->workspaceBytes;
+  if (want == 0) want = freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2;
+  if (want > freeB) want = freeB;
+  want = want / kAlign * kAlign;
+  if (want < ((size_t)256 << 20)) { delete c; return mb_fail(MB_ENOMEM, "mb_create: only %zu bytes of device memory free", freeB); }
+  if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
+    delete c;
+    return mb_fail(MB_ENOMEM, "mb_create: cannot allocate a %zu byte device arena", want);
+  }
+  c->arenaBytes = want;
+
+  for (int i = 0; i < 2; i++) {
+    MB_CUDA(cudaMallocHost((void **)&c->hStage[i], kStageBytes));
+    c->dStage[i] = c->arena + c->arenaBytes - (size_t)(i + 1) * kStageBytes;
+    MB_CUDA(cudaEventCreateWithFlags(&c->evH2D[i], cudaEventDisableTiming));
+  }
+  c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
+
+  *out = c;
+  return MB_OK;
+}
+
+
+extern "C" void mb_destroy(mb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm) mb_comm_destroy(c->comm);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; i++) {
+    if (c->hStage[i]) cudaFreeHost(c->hStage[i]);
+    if (c->evH2D[i])  cudaEventDestroy(c->evH2D[i]);
+  }
+  if (c->arena)  cudaFree(c->arena);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+
+//  ------------------------------------------------------------------------------------------
+//  ingest
+//  ------------------------------------------------------------------------------------------
+
+static int storeReserve(mb_ctx *c, u64 moreRecords) {
+  const size_t need = (size_t)(c->nRecords + moreRecords + MB_STORE_PAD_RECORDS) * MB_STORE_REC_WORDS * 4;
+  if (need > c->storeLimit)
+    return mb_fail(MB_ENOMEM, "input too large for one device: the packed read store needs %zu bytes, %zu available "
+                              "(shard the input over more GPUs)", need, c->storeLimit);
+  return MB_OK;
+}
+
+//  Ship the filled part of the current pinned buffer: H2D, then K1 into the store.
+static int flushStage(mb_ctx *c) {
+  if (c->fill == 0) return MB_OK;
+  const int    i = c->cur;
+  const size_t n = c->fill;
+  const u64 recs = (n + 31) / 32;
+  MB_TRY(storeReserve(c, recs));
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_CUDA(cudaMemcpyAsync(c->dStage[i], c->hStage[i], n, cudaMemcpyHostToDevice, c->stream));
+  MB_CUDA(cudaEventRecord(c->evH2D[i], c->stream));
+  MB_CUDA(mb_launch_pack(c->dStage[i], n, (u32 *)c->arena, c->nRecords, c->stream));
+  c->st.nLaunches++;
+  c->st.h2dBytes += n;
+  c->nRecords    += recs;
+  c->fill = 0;
+  c->cur ^= 1;
+  MB_CUDA(cudaEventSynchronize(c->evH2D[c->cur]));      //  the other pinned buffer must have left the host
+  return MB_OK;
+}
+
+static int appendHost(mb_ctx *c, const char *p, size_t n) {
+  while (n) {
+    size_t room = kStageBytes - c->fill;
+    if (room == 0) { MB_TRY(flushStage(c)); room = kStageBytes; }
+    const size_t m = n < room ? n : room;
+    memcpy(c->hStage[c->cur] + c->fill, p, m);
+    c->fill += m;  p += m;  n -= m;
+  }
+  return MB_OK;
+}
+
+static int parserSink(void *arg, const char *bases, size_t n) {
+  mb_ctx *c = (mb_ctx *)arg;
+  c->inRecord = !(n == 1 && bases[0] == '.');
+  return appendHost(c, bases, n);
+}
+
+extern "C" int mb_add_bases(mb_ctx *c, const char *bases, uint64_t len, int endOfSequence) {
+  mb_clear_error();
+  if (!c || (!bases && len))  return mb_fail(MB_EINVAL, "mb_add_bases: NULL argument");
+  if (c->counted)             return mb_fail(MB_ESTATE, "mb_add_bases: already counted");
+  MB_TRY(appendHost(c, bases, len));
+  if (len) c->inRecord = true;
+  if (endOfSequence) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
+  return MB_OK;
+}
+
+extern "C" int mb_add_bases_device(mb_ctx *c, const char *dBases, uint64_t len) {
+  mb_clear_error();
+  if (!c || (!dBases && len))  return mb_fail(MB_EINVAL, "mb_add_bases_device: NULL argument");
+  if (c->counted)              return mb_fail(MB_ESTATE, "mb_add_bases_device: already counted");
+  if (((uintptr_t)dBases & 15) != 0) return mb_fail(MB_EINVAL, "mb_add_bases_device: pointer must be 16-byte aligned");
+  //  A device chunk holds whole records: the stream is padded to a record boundary before and after.
+  if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
+  MB_TRY(flushStage(c));
+  const u64 recs = (len + 31) / 32;
+  MB_TRY(storeReserve(c, recs));
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_CUDA(mb_launch_pack((const uint8_t *)dBases, len, (u32 *)c->arena, c->nRecords, c->stream));
+  MB_CUDA(cudaStreamSynchronize(c->stream));            //  the caller may reuse dBases when we return
+  c->st.nLaunches++;
+  c->nRecords += recs;
+  return MB_OK;
+}
+
+extern "C" int mb_add_file_bytes(mb_ctx *c, const uint8_t *data, uint64_t len) {
+  mb_clear_error();
+  if (!c || (!data && len))  return mb_fail(MB_EINVAL, "mb_add_file_bytes: NULL argument");
+  if (c->counted)            return mb_fail(MB_ESTATE, "mb_add_file_bytes: already counted");
+  if (!SeqParser::sniff(data, len < 65536 ? len : 65536))
+    return mb_fail(MB_EFORMAT, "input is not FASTA or FASTQ");
+  SeqParser ps(parserSink, c);
+  MB_TRY(ps.feed(data, len));
+  return ps.finish();
+}
+
+extern "C" int mb_add_file(mb_ctx *c, const char *path) {
+  mb_clear_error();
+  if (!c || !path)  return mb_fail(MB_EINVAL, "mb_add_file: NULL argument");
+  if (c->counted)   return mb_fail(MB_ESTATE, "mb_add_file: already counted");
+
+  //  Compressed inputs go through the same external tools the reference uses
+  //  (compressedFileReader, src/utility/src/files/compressed-v1-reading.C:90-116).
+  const size_t L = strlen(path);
+  const char *tool = nullptr;
+  if      (L > 3 && !strcmp(path + L - 3, ".gz"))   tool = "gzip -dc";
+  else if (L > 4 && !strcmp(path + L - 4, ".bz2"))  tool = "bzip2 -dc";
+  else if (L > 3 && !strcmp(path + L - 3, ".xz"))   tool = "xz -dc";
+  else if (L > 4 && !strcmp(path + L - 4, ".zst"))  tool = "zstd -dc";
+
+  FILE *f = nullptr;
+  if (tool) {
+    if (access(path, R_OK) != 0) return mb_fail(MB_EIO, "cannot read '%s'", path);
+    std::string cmd = std::string(tool) + " '" + path + "'";
+    f = popen(cmd.c_str(), "r");
+  } else if (!strcmp(path, "-")) {
+    f = stdin;
+  } else {
+    f = fopen(path, "rb");
+  }
+  if (!f) return mb_fail(MB_EIO, "cannot open '%s'", path);
+
+  const size_t CH = (size_t)16 << 20;
+  std::vector<uint8_t> buf(CH);
+  SeqParser ps(parserSink, c);
+  bool first = true;
+  int  rc = MB_OK;
+  for (;;) {
+    const size_t n = fread(buf.data(), 1, CH, f);
+    if (first) {
+      first = false;
+      if (!SeqParser::sniff(buf.data(), n < 65536 ? n : 65536)) { rc = mb_fail(MB_EFORMAT, "'%s' is not FASTA or FASTQ", path); break; }
+    }
+    if (n == 0) break;
+    if ((rc = ps.feed(buf.data(), n)) != MB_OK) break;
+    if (n < CH) break;
+  }
+  if (tool) pclose(f); else if (f != stdin) fclose(f);
+  if (rc != MB_OK) return rc;
+  return ps.finish();
+}
+
+
+//  ------------------------------------------------------------------------------------------
+//  counting
+//  ------------------------------------------------------------------------------------------
+
+namespace {
+
+struct Carver {                                       //  bump allocator over a region of the arena
+  uint8_t *base; size_t size, off = 0;
+  Carver(uint8_t *b, size_t s) : base(b), size(s) {}
+  void *take(size_t bytes) {
+    const size_t o = alignUp(off);
+    if (o + bytes > size) return nullptr;
+    off = o + bytes;
+    return base + o;
+  }
+  size_t left() const { const size_t o = alignUp(off); return o >= size ? 0 : size - o; }
+};
+
+struct Control {                                      //  small device-side tables, one block in the arena
+  u64 binCount [MB_MAX_BINS];
+  u64 binStart [MB_MAX_BINS + 1];
+  u64 binCursor[MB_MAX_BINS];
+  u64 segStart [MB_MAX_BINS + 1];
+  u64 segTile  [MB_MAX_BINS + 1];
+  u64 fileBase [64];
+  u64 numDistinct;
+  u64 encTotals[4];
+  u64 histTotals[3];
+  u64 histBigN;
+};
+
+struct Pass { u32 binLo, binHi; u64 nKeys; };
+
+}  //  namespace
+
+
+static int runCount(mb_ctx *c) {
+  const mb_config &cfg = c->cfg;
+  const u32 k = cfg.k, wP = cfg.wPrefix, W = 8 * c->keyWords;
+  const u32 wS = 2 * k - wP;
+  const u32 binBits = c->binBits, nBins = 1u << binBits;
+  const u32 blockBits = wP - 6;
+  const u64 blocksPerBin  = (u64)1 << (wP - binBits);
+  const u64 blocksPerFile = (u64)1 << blockBits;
+  cudaStream_t s = c->stream;
+
+  MB_CUDA(cudaSetDevice(c->device));
+
+  EventTimer tAll, tStage;
+  tAll.init(); tStage.init();
+  tAll.start(s);
+
+  //  ---- finish the ingest ------------------------------------------------------------------
+  if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
+  MB_TRY(flushStage(c));
+  MB_TRY(storeReserve(c, 0));
+  const size_t storeBytes = (size_t)c->nRecords * MB_STORE_REC_WORDS * 4;
+  const size_t padBytes   = (size_t)MB_STORE_PAD_RECORDS * MB_STORE_REC_WORDS * 4;
+  MB_CUDA(cudaMemsetAsync(c->arena + storeBytes, 0, padBytes, s));
+  c->st.nBases = c->nRecords * 32;
+
+  //  the staging buffers at the top of the arena are free from here on
+  Carver top(c->arena + alignUp(storeBytes + padBytes), c->arenaBytes - alignUp(storeBytes + padBytes));
+
+  Control *dCtl = (Control *)top.take(sizeof(Control));
+  u64 *dHistSmall = (u64 *)top.take((size_t)MB_HIST_SMALL * sizeof(u64));
+  if (!dCtl || !dHistSmall) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
+  MB_CUDA(cudaMemsetAsync(dCtl, 0, sizeof(Control), s));
+  MB_CUDA(cudaMemsetAsync(dHistSmall, 0, (size_t)MB_HIST_SMALL * sizeof(u64), s));
+
+  //  ---- K2a: k-mers per prefix bin ---------------------------------------------------------
+  MbExtractParams xp;
+  xp.store = (const u32 *)c->arena;  xp.nPositions = c->nRecords * 32;
+  xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;
+
+  tStage.start(s);
+  MB_CUDA(mb_launch_bin_histogram(xp, dCtl->binCount, s));
+  tStage.stop(s);
+  c->st.nLaunches++;
+  std::vector<u64> binCount(nBins);
+  MB_CUDA(cudaMemcpyAsync(binCount.data(), dCtl->binCount, nBins * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  c->st.msHistogram += tStage.ms();
+  c->st.d2hBytes += nBins * sizeof(u64);
+
+  u64 nKmers = 0;
+  for (u32 b = 0; b < nBins; b++) nKmers += binCount[b];
+  c->st.nKmers = nKmers;
+
+  const u64 histBigCap = nKmers / MB_HIST_SMALL + 1024;
+  u32 *dHistBig = (u32 *)top.take(histBigCap * sizeof(u32));
+  if (!dHistBig) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
+
+  //  ---- plan the passes --------------------------------------------------------------------
+  const size_t R = top.left();
+  const u64 nBlocksTotal = (u64)1 << wP;
+  size_t encBytes = std::max<size_t>(std::max<size_t>((size_t)512 << 20, R / 6), (size_t)nBlocksTotal * 200);
+  if (encBytes > R / 2) encBytes = R / 2;
+  const u32 tileKeys = mb_sort_tile_keys(c->keyWords);
+  //  per key: two key buffers + tile status; fixed: ragged tiles and tables of every bin
+  const double perKey = 2.0 * W + (double)MB_RADIX * 8 / tileKeys + 16.0 / tileKeys;
+  const size_t fixed  = (size_t)nBins * (MB_RADIX * 8 + 16 * MB_RADIX * 8) + ((size_t)8 << 20);
+  if (R < encBytes + fixed + ((size_t)64 << 20)) return mb_fail(MB_ENOMEM, "device arena too small: %zu bytes left after the read store", R);
+  u64 capKeys = (u64)((double)(R - encBytes - fixed) / perKey);
+  capKeys = capKeys / 4096 * 4096;
+
+  std::vector<Pass> passes;
+  {
+    Pass cur = { 0, 0, 0 };
+    for (u32 b = 0; b < nBins; b++) {
+      if (binCount[b] > capKeys)
+        return mb_fail(MB_ENOMEM, "prefix bin %u holds %llu k-mers, more than the %llu that fit the device at once "
+                                  "(spill-and-merge is not implemented; use more GPUs)", b, (u64)binCount[b], (u64)capKeys);
+      if (cur.nKeys + binCount[b] > capKeys) { cur.binHi = b; passes.push_back(cur); cur.binLo = b; cur.nKeys = 0; }
+      cur.nKeys += binCount[b];
+    }
+    cur.binHi = nBins;
+    passes.push_back(cur);
+  }
+  c->st.nPasses = (u32)passes.size();
+
+  MbSortPlan plan;
+  mb_sort_plan(2 * k - binBits, &plan);
+  c->st.sortPasses = plan.nPasses;
+
+  //  host images
+  for (u32 f = 0; f < 64; f++) { c->db.data[f].clear(); c->db.index[f].clear(); }
+  std::vector<u64> fileBase(64, 0);
+
+  std::vector<u64> segStart(MB_MAX_BINS + 1), segTile(MB_MAX_BINS + 1), binStart(MB_MAX_BINS + 1);
+  EventTimer tSortHist;  tSortHist.init();
+  cudaEvent_t evAfterHist;  MB_CUDA(cudaEventCreate(&evAfterHist));
+
+  for (size_t pi = 0; pi < passes.size(); pi++) {
+    const Pass &P = passes[pi];
+    const u32 nSegs = P.binHi - P.binLo;
+    const u64 n = P.nKeys;
+
+    //  ---- carve this pass ------------------------------------------------------------------
+    Carver pc((uint8_t *)top.base + alignUp(top.off), top.left());
+    void *bufA = pc.take((size_t)W * n + 64);
+    void *bufB = pc.take((size_t)W * n + 64);
+    u64 nTiles = 0;
+    std::fill(binStart.begin(), binStart.end(), 0);
+    {
+      u64 at = 0;
+      for (u32 b = 0; b < nBins; b++) {
+        binStart[b] = at;
+        if (b >= P.binLo && b < P.binHi) {
+          segStart[b - P.binLo] = at;
+          segTile [b - P.binLo] = nTiles;
+          at     += binCount[b];
+          nTiles += (binCount[b] + tileKeys - 1) / tileKeys;
+        }
+      }
+      binStart[nBins] = at;
+      segStart[nSegs] = at;
+      segTile [nSegs] = nTiles;
+    }
+    const size_t sortWs = std::max(mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses), mb_count_workspace_bytes(n));
+    void *ws = pc.take(sortWs);
+    if (!bufA || !bufB || !ws) return mb_fail(MB_ENOMEM, "internal: pass %zu does not fit the arena", pi);
+
+    Carver ec((uint8_t *)pc.base + alignUp(pc.off), pc.left());       //  encode region: everything that is left
+
+    MB_CUDA(cudaMemcpyAsync(dCtl->binStart, binStart.data(), (nBins + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaMemcpyAsync(dCtl->segStart, segStart.data(), (nSegs + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaMemcpyAsync(dCtl->segTile,  segTile.data(),  (nSegs + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaMemcpyAsync(dCtl->fileBase, fileBase.data(), 64 * sizeof(u64), cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaMemsetAsync(dCtl->binCursor, 0, sizeof(dCtl->binCursor), s));
+    c->st.h2dBytes += (nBins + 1 + 2 * (nSegs + 1) + 64) * sizeof(u64);
+
+    //  ---- K2/K3 ------------------------------------------------------------------------------
+    xp.binLo = P.binLo;  xp.binHi = P.binHi;
+    tStage.start(s);
+    if (n) { MB_CUDA(mb_launch_extract(xp, bufA, dCtl->binStart, dCtl->binCursor, s)); c->st.nLaunches++; }
+    tStage.stop(s);
+    MB_CUDA(cudaStreamSynchronize(s));
+    c->st.msExtract += tStage.ms();
+
+    //  ---- multi-GPU: route k-mers to their owners (exchange.cu) -------------------------------
+    //  (single GPU: nothing)
+
+    //  ---- K4 ---------------------------------------------------------------------------------
+    int inB = 0;  u32 nl = 0;
+    tSortHist.start(s);
+    MB_CUDA(mb_launch_sort(c->keyWords, bufA, bufB, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inB, &nl, s, evAfterHist));
+    tStage.stop(s);                                   //  reuse: [evAfterHist, tStage.b] = sweep passes
+    MB_CUDA(cudaStreamSynchronize(s));
+    { float m = 0;  cudaEventElapsedTime(&m, tSortHist.a, evAfterHist);  c->st.msSortHist += m;
+      m = 0;        cudaEventElapsedTime(&m, evAfterHist, tStage.b);     c->st.msSort     += m; }
+    c->st.nLaunches += nl;
+    if (n) c->st.sortLaunchKeys += n * plan.nPasses;
+    void *sorted = inB ? bufB : bufA;
+    void *other  = inB ? bufA : bufB;
+
+    if (c->stopAfterSort) {                           //  debug: hand back the sorted instances
+      const size_t at = c->sortedLo.size();
+      c->sortedLo.resize(at + n);
+      if (c->keyWords == 2) c->sortedHi.resize(at + n);
+      if (n) {
+        if (c->keyWords == 1) {
+          MB_CUDA(cudaMemcpy(c->sortedLo.data() + at, sorted, n * 8, cudaMemcpyDeviceToHost));
+        } else {
+          std::vector<u64> tmp(2 * n);
+          MB_CUDA(cudaMemcpy(tmp.data(), sorted, n * 16, cudaMemcpyDeviceToHost));
+          for (u64 i = 0; i < n; i++) { c->sortedLo[at + i] = tmp[2 * i]; c->sortedHi[at + i] = tmp[2 * i + 1]; }
+        }
+      }
+      continue;
+    }
+
+    //  ---- K5 ---------------------------------------------------------------------------------
+    u64 *runStart = (u64 *)other;
+    tStage.start(s);
+    MB_CUDA(mb_launch_count(c->keyWords, sorted, n, runStart, &dCtl->numDistinct, ws, s));
+    u64 D = 0;
+    MB_CUDA(cudaMemcpyAsync(&D, &dCtl->numDistinct, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(mb_launch_value_histogram(runStart, &dCtl->numDistinct, n, dHistSmall, dHistBig, &dCtl->histBigN, histBigCap, dCtl->histTotals, s));
+    tStage.stop(s);
+    MB_CUDA(cudaStreamSynchronize(s));
+    c->st.msCount += tStage.ms();
+    c->st.nLaunches += n ? 2 : 0;
+    c->st.d2hBytes += 8;
+
+    if (cfg.flags & MB_FLAG_KEEP_COUNTED) {
+      const size_t at = c->cLo.size();
+      c->cLo.resize(at + D);  c->cCnt.resize(at + D);
+      if (c->keyWords == 2) c->cHi.resize(at + D);
+      std::vector<u64> rs(D + 1);
+      if (D) {
+        MB_CUDA(cudaMemcpy(rs.data(), runStart, (D + 1) * 8, cudaMemcpyDeviceToHost));
+        if (c->keyWords == 1) {
+          MB_CUDA(cudaMemcpy(c->cLo.data() + at, sorted, D * 8, cudaMemcpyDeviceToHost));
+        } else {
+          std::vector<u64> tmp(2 * D);
+          MB_CUDA(cudaMemcpy(tmp.data(), sorted, D * 16, cudaMemcpyDeviceToHost));
+          for (u64 i = 0; i < D; i++) { c->cLo[at + i] = tmp[2 * i]; c->cHi[at + i] = tmp[2 * i + 1]; }
+        }
+        for (u64 i = 0; i < D; i++) c->cCnt[at + i] = (u32)(rs[i + 1] - rs[i]);
+      }
+    }
+
+    //  ---- K6 ---------------------------------------------------------------------------------
+    MbEncodeParams ep;
+    ep.keys = sorted;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = c->keyWords;
+    ep.k = k;  ep.wPrefix = wP;
+    ep.blockLo = (u64)P.binLo * blocksPerBin;
+    ep.nBlocks = (u64)nSegs * blocksPerBin;
+
+    MbBlockMeta *dMeta = (MbBlockMeta *)ec.take(ep.nBlocks * sizeof(MbBlockMeta));
+    void *dScanTmp     = ec.take(mb_encode_scan_tmp_bytes(ep.nBlocks));
+    if (!dMeta || !dScanTmp) return mb_fail(MB_ENOMEM, "device arena too small for the block table of pass %zu (%llu blocks)", pi, (u64)ep.nBlocks);
+
+    tStage.start(s);
+    MB_CUDA(mb_launch_encode_layout(ep, dMeta, dCtl->encTotals, dScanTmp, s));
+    c->st.nLaunches += 4;
+
+    //  chunk boundaries: first block of every file touched by this pass
+    const u32 fileLo = (u32)(ep.blockLo >> blockBits), fileHi = (u32)((ep.blockLo + ep.nBlocks - 1) >> blockBits);
+    const u32 nf = fileHi - fileLo + 1;
+    std::vector<MbBlockMeta> fm(nf + 1);
+    std::vector<u64> fblk(nf + 1);
+    for (u32 i = 0; i < nf; i++) {
+      const u64 fb = (u64)(fileLo + i) << blockBits;
+      fblk[i] = fb > ep.blockLo ? fb - ep.blockLo : 0;
+    }
+    fblk[nf] = ep.nBlocks;
+    for (u32 i = 0; i < nf; i++)
+      MB_CUDA(cudaMemcpyAsync(&fm[i], dMeta + fblk[i], sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
+    u64 encTotals[4];
+    MB_CUDA(cudaMemcpyAsync(encTotals, dCtl->encTotals, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    fm[nf].outByte = encTotals[0];  fm[nf].subFirst = (u32)encTotals[1];
+    c->st.d2hBytes += nf * sizeof(MbBlockMeta) + sizeof(encTotals);
+
+    //  greedy groups of whole files that fit what is left of the arena
+    size_t encLeft = ec.left();
+    u32 fi = 0;
+    while (fi < nf) {
+      u32 fj = fi;
+      while (fj < nf) {
+        const size_t bytes = fm[fj + 1].outByte - fm[fi].outByte;
+        const size_t subs  = (size_t)(fm[fj + 1].subFirst - fm[fi].subFirst);
+        const size_t idx   = (size_t)(fblk[fj + 1] - fblk[fi]) * 24;
+        const size_t tot   = alignUp(bytes) + alignUp(subs * 4) + alignUp(idx) + 3 * kAlign;
+        if (tot > encLeft) break;
+        fj++;
+      }
+      if (fj == fi)
+        return mb_fail(MB_ENOMEM, "encoded data file %u of pass %zu (%llu bytes) does not fit the %zu bytes left on the device",
+                       fileLo + fi, pi, (u64)(fm[fi + 1].outByte - fm[fi].outByte), encLeft);
+
+      MbEncodeChunk ch;
+      ch.chunkFirst = fblk[fi];  ch.chunkCount = fblk[fj] - fblk[fi];
+      ch.chunkByte0 = fm[fi].outByte;  ch.chunkSub0 = fm[fi].subFirst;
+      const size_t bytes = fm[fj].outByte - fm[fi].outByte;
+      const size_t subs  = (size_t)(fm[fj].subFirst - fm[fi].subFirst);
+
+      Carver cc((uint8_t *)ec.base + alignUp(ec.off), ec.left());
+      uint8_t *dOut  = (uint8_t *)cc.take(bytes);
+      u32     *dSub  = (u32 *)cc.take(subs * 4);
+      u64     *dIdx  = (u64 *)cc.take(ch.chunkCount * 24);
+      if (!dOut || !dSub || !dIdx) return mb_fail(MB_ENOMEM, "internal: encode chunk does not fit");
+
+      MB_CUDA(cudaMemsetAsync(dOut, 0, bytes, s));
+      MB_CUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl->encTotals, dSub, dOut, dIdx, dCtl->fileBase, s));
+      c->st.nLaunches += D ? 2 : 1;
+
+      if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
+        for (u32 f = fi; f < fj; f++) {
+          const u32 file = fileLo + f;
+          const size_t fb = fm[f + 1].outByte - fm[f].outByte;
+          const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
+          std::vector<uint8_t> &dv = c->db.data[file], &iv = c->db.index[file];
+          const size_t d0 = dv.size(), i0 = iv.size();
+          dv.resize(d0 + fb);  iv.resize(i0 + ib);
+          MB_CUDA(cudaMemcpyAsync(dv.data() + d0, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
+          MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
+          c->st.d2hBytes += fb + ib;
+        }
+      }
+      MB_CUDA(cudaStreamSynchronize(s));
+      for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
+      fi = fj;
+    }
+    tStage.stop(s);
+    MB_CUDA(cudaStreamSynchronize(s));
+    c->st.msEncode += tStage.ms();
+  }
+
+  cudaEventDestroy(evAfterHist);
+  tSortHist.destroy();
+
+  if (!c->stopAfterSort) {
+    //  ---- value histogram -> host ------------------------------------------------------------
+    std::vector<u64> hs(MB_HIST_SMALL);
+    u64 totals[3], bigN = 0;
+    MB_CUDA(cudaMemcpyAsync(hs.data(), dHistSmall, (size_t)MB_HIST_SMALL * 8, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaMemcpyAsync(totals, dCtl->histTotals, sizeof(totals), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaMemcpyAsync(&bigN, &dCtl->histBigN, 8, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    if (bigN > histBigCap) return mb_fail(MB_ENOMEM, "internal: value histogram overflow list too small");
+    std::vector<u32> big(bigN);
+    if (bigN) MB_CUDA(cudaMemcpy(big.data(), dHistBig, bigN * 4, cudaMemcpyDeviceToHost));
+    c->st.d2hBytes += (size_t)MB_HIST_SMALL * 8 + bigN * 4;
+
+    std::map<u64, u64> bigMap;
+    for (u64 i = 0; i < bigN; i++) bigMap[big[i]]++;
+    c->hist.values.clear();  c->hist.occ.clear();
+    for (u64 v = 1; v < MB_HIST_SMALL; v++) if (hs[v]) { c->hist.values.push_back(v); c->hist.occ.push_back(hs[v]); }
+    for (auto &kv : bigMap) { c->hist.values.push_back(kv.first); c->hist.occ.push_back(kv.second); }
+    c->hist.nUnique = totals[0];  c->hist.nDistinct = totals[1];  c->hist.nTotal = totals[2];
+    c->st.nUnique = totals[0];  c->st.nDistinct = totals[1];  c->st.nTotal = totals[2];
+
+    mb_build_master_index(k, wP, c->hist, c->db.master);
+    c->st.dbBytes = c->db.master.size();
+    for (u32 f = 0; f < 64; f++) c->st.dbBytes += c->db.data[f].size() + c->db.index[f].size();
+  }
+
+  tAll.stop(s);
+  c->st.msTotal = tAll.ms();
+  tAll.destroy();  tStage.destroy();
+  (void)wS;  (void)blocksPerFile;
+  c->counted = true;
+  return MB_OK;
+}
+
+
+extern "C" int mb_count(mb_ctx *c) {
+  mb_clear_error();
+  if (!c)          return mb_fail(MB_EINVAL, "mb_count: NULL context");
+  if (c->counted)  return mb_fail(MB_ESTATE, "mb_count: already counted");
+  return runCount(c);
+}
+
+
+//  ------------------------------------------------------------------------------------------
+//  results
+//  ------------------------------------------------------------------------------------------
+
+extern "C" int mb_get_image(mb_ctx *c, uint32_t which, const uint8_t **ptr, uint64_t *len) {
+  mb_clear_error();
+  if (!c || !ptr || !len || which > 128)  return mb_fail(MB_EINVAL, "mb_get_image: bad argument");
+  if (!c->counted)                        return mb_fail(MB_ESTATE, "mb_get_image: call mb_count first");
+  const std::vector<uint8_t> &v = which < 64 ? c->db.data[which] : which < 128 ? c->db.index[which - 64] : c->db.master;
+  *ptr = v.data();
+  *len = v.size();
+  return MB_OK;
+}
+
+extern "C" int mb_write_db(mb_ctx *c, const char *outDir) {
+  mb_clear_error();
+  if (!c || !outDir)  return mb_fail(MB_EINVAL, "mb_write_db: NULL argument");
+  if (!c->counted)    return mb_fail(MB_ESTATE, "mb_write_db: call mb_count first");
+  if (c->cfg.flags & MB_FLAG_NO_IMAGES) return mb_fail(MB_ESTATE, "mb_write_db: context was created with MB_FLAG_NO_IMAGES");
+  return mb_write_db_dir(c->db, outDir, c->cfg.rank == 0);
+}
+
+extern "C" int mb_get_stats(mb_ctx *c, mb_stats *st) {
+  mb_clear_error();
+  if (!c || !st) return mb_fail(MB_EINVAL, "mb_get_stats: NULL argument");
+  *st = c->st;
+  return MB_OK;
+}
+
+extern "C" int mb_get_counted(mb_ctx *c, const uint64_t **lo, const uint64_t **hi, const uint32_t **cnt, uint64_t *n) {
+  mb_clear_error();
+  if (!c || !lo || !cnt || !n)  return mb_fail(MB_EINVAL, "mb_get_counted: NULL argument");
+  if (!c->counted || !(c->cfg.flags & MB_FLAG_KEEP_COUNTED)) return mb_fail(MB_ESTATE, "mb_get_counted: count with MB_FLAG_KEEP_COUNTED first");
+  *lo = (const uint64_t *)c->cLo.data();
+  if (hi) *hi = c->keyWords == 2 ? (const uint64_t *)c->cHi.data() : nullptr;
+  *cnt = c->cCnt.data();
+  *n = c->cLo.size();
+  return MB_OK;
+}
+
+extern "C" int mb_get_histogram(mb_ctx *c, const uint64_t **values, const uint64_t **occ, uint64_t *n) {
+  mb_clear_error();
+  if (!c || !values || !occ || !n)  return mb_fail(MB_EINVAL, "mb_get_histogram: NULL argument");
+  if (!c->counted)                  return mb_fail(MB_ESTATE, "mb_get_histogram: call mb_count first");
+  *values = (const uint64_t *)c->hist.values.data();
+  *occ    = (const uint64_t *)c->hist.occ.data();
+  *n      = c->hist.values.size();
+  return MB_OK;
+}
+
+extern "C" int mb_merge_histogram(mb_ctx *c, const uint64_t *values, const uint64_t *occ, uint64_t n) {
+  mb_clear_error();
+  if (!c || (n && (!values || !occ)))  return mb_fail(MB_EINVAL, "mb_merge_histogram: NULL argument");
+  if (!c->counted)                     return mb_fail(MB_ESTATE, "mb_merge_histogram: call mb_count first");
+  std::map<u64, u64> m;
+  for (size_t i = 0; i < c->hist.values.size(); i++) m[c->hist.values[i]] += c->hist.occ[i];
+  for (u64 i = 0; i < n; i++) {
+    m[values[i]] += occ[i];
+    if (values[i] == 1) c->hist.nUnique += occ[i];
+    c->hist.nDistinct += occ[i];
+    c->hist.nTotal    += values[i] * occ[i];
+  }
+  c->hist.values.clear();  c->hist.occ.clear();
+  for (auto &kv : m) { c->hist.values.push_back(kv.first); c->hist.occ.push_back(kv.second); }
+  mb_build_master_index(c->cfg.k, c->cfg.wPrefix, c->hist, c->db.master);
+  return MB_OK;
+}
+
+
+//  engine-internal accessors for the debug entry points and the exchange layer
+void mb_ctx_set_stop_after_sort(mb_ctx *c)                               { c->stopAfterSort = true; }
+const std::vector<u64> &mb_ctx_sorted_lo(mb_ctx *c)                      { return c->sortedLo; }
+const std::vector<u64> &mb_ctx_sorted_hi(mb_ctx *c)                      { return c->sortedHi; }
+MbDbImages &mb_ctx_images(mb_ctx *c)                                     { return c->db; }
+void mb_ctx_set_comm(mb_ctx *c, MbComm *m)                               { c->comm = m; }
+MbComm *mb_ctx_comm(mb_ctx *c)                                           { return c->comm; }
+cudaStream_t mb_ctx_stream(mb_ctx *c)                                    { return c->stream; }
+int mb_ctx_device(mb_ctx *c)                                             { return c->device; }
+const mb_config &mb_ctx_config(mb_ctx *c)                                { return c->cfg; }

@@ -1,0 +1,300 @@
+//  K2 / K3: canonical k-mer extraction from the packed read store, fused with the prefix scatter.
+//
+//  Replaces the reference's hot loop #1:
+//    kmerIterator::nextMer        src/utility/src/kmers-v1/kmers-iterator.H:63-87   (k valid bases in a row)
+//    kmerTiny::addR / addL        src/utility/src/kmers-v1/kmers-tiny.H:86-87       (forward / reverse-complement)
+//    insertKmers                  src/meryl/merylOp-countThreads.C:236-280          (canonical = min(f, r); prefix | suffix)
+//    merylCountArray::add         src/meryl/merylCountArray.C:491-728               (append to the prefix bucket)
+//
+//  B200 formulation.  There is no rolling state: position p of the store starts a k-mer iff the k
+//  validity bits from p are all set, and its forward value is a 2k-bit window of the packed
+//  stream; the reverse complement is a bit reversal of that window.  A persistent CTA walks tiles
+//  of 32*THREADS positions; each tile's store records (12 B per 32 positions, plus a 4-record
+//  halo for the k-1 overhang) are brought into shared memory by one TMA bulk copy
+//  (cp.async.bulk + mbarrier), double buffered so the next tile streams in under the current
+//  tile's integer work.  Per thread: 32 consecutive positions.
+//    1. validity of all 32 windows at once by log-step erosion of the validity bits;
+//    2. cheap pre-filter: the prefix bin of the canonical k-mer is min(top bits of f, top bits of
+//       r) and needs only the first and last binBits/2 bases -> keep-mask of this pass's bins;
+//    3. full k-mer only for kept positions, rank within (tile, bin) by a shared-memory atomic;
+//    4. one global atomic per (tile, bin) reserves the run in the bin's segment, keys are stored.
+//  The same kernel in COUNT_ONLY form is the histogram pre-pass (K2a) that sizes the segments.
+//
+//  Work: integer/bit ops, ~16 per position for the pre-filter + ~40 per kept k-mer; HBM traffic
+//  0.375 B per position read + 8 (16) B per kept k-mer written -- compute bound, not HBM bound.
+
+#include "kernels.cuh"
+
+namespace {
+
+//  ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ------------------------------------------
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init(void) {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
+  u32 ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async(void) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+//  ---- bit helpers ---------------------------------------------------------------------------
+
+//  The 192-bit window of a thread: positions 0..95 relative to its first position, 2 bits each,
+//  position j in bits [191-2j, 190-2j] of (w0:w1:w2).
+struct Window { u64 w0, w1, w2; };
+
+//  nbits (1..64) bits of the window ending just before bit offset `end` (nbits <= end <= 192).
+__device__ __forceinline__ u64 bits_ending_at(const Window &w, u32 end, u32 nbits) {
+  u64 x;
+  if (end <= 64)        x = w.w0 >> (64 - end);
+  else if (end < 128)   x = (w.w0 << (end - 64)) | (w.w1 >> (128 - end));
+  else if (end == 128)  x = w.w1;
+  else if (end < 192)   x = (w.w1 << (end - 128)) | (w.w2 >> (192 - end));
+  else                  x = w.w2;
+  return nbits >= 64 ? x : (x & (((u64)1 << nbits) - 1));
+}
+
+//  Reverse complement of an n-base value held in the low 2n bits (n <= 32).
+__device__ __forceinline__ u64 revcomp64(u64 x, u32 n) {
+  u64 y = __brevll(x) >> (64 - 2 * n);
+  y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+  const u64 m = (n == 32) ? ~0ull : (((u64)1 << (2 * n)) - 1);
+  return y ^ (0xaaaaaaaaaaaaaaaaull & m);
+}
+
+//  128-bit variant for 33 <= n <= 64: value (hi:lo) in the low 2n bits.
+__device__ __forceinline__ void revcomp128(u64 hi, u64 lo, u32 n, u64 &rhi, u64 &rlo) {
+  u64 a = __brevll(lo), b = __brevll(hi);            //  reversed 128 bits = (a:b)
+  a = ((a >> 1) & 0x5555555555555555ull) | ((a & 0x5555555555555555ull) << 1);
+  b = ((b >> 1) & 0x5555555555555555ull) | ((b & 0x5555555555555555ull) << 1);
+  const u32 sh = 128 - 2 * n;                        //  0..62
+  if (sh == 0) { rhi = a; rlo = b; }
+  else         { rhi = a >> sh;  rlo = (b >> sh) | (a << (64 - sh)); }
+  const u64 mh = (n == 64) ? ~0ull : (((u64)1 << (2 * n - 64)) - 1);
+  rhi ^= 0xaaaaaaaaaaaaaaaaull & mh;
+  rlo ^= 0xaaaaaaaaaaaaaaaaull;
+}
+
+template <int KW> struct ExtractShape;
+template <> struct ExtractShape<1> { static const int THREADS = 256; };
+template <> struct ExtractShape<2> { static const int THREADS = 128; };
+
+template <int KW>
+struct ExtractSmem {
+  static const int    THREADS   = ExtractShape<KW>::THREADS;
+  static const int    TILE_POS  = THREADS * 32;
+  static const int    REC_U32   = (THREADS + 4) * MB_STORE_REC_WORDS;       //  records incl. halo
+  static const int    REC_BYTES = REC_U32 * 4;                              //  multiple of 16
+  static const size_t OFF_BAR   = 0;
+  static const size_t OFF_REC0  = 128;
+  static const size_t OFF_REC1  = OFF_REC0 + ((REC_BYTES + 127) / 128) * 128;
+  static const size_t OFF_CNT   = OFF_REC1 + ((REC_BYTES + 127) / 128) * 128;
+  static const size_t OFF_GBASE = OFF_CNT + MB_MAX_BINS * sizeof(u32);
+  static const size_t OFF_STASH = OFF_GBASE + MB_MAX_BINS * sizeof(u64);
+  static const size_t OFF_RANK  = OFF_STASH + (size_t)TILE_POS * sizeof(typename KeyT<KW>::type);
+  static const size_t SCATTER_BYTES = OFF_RANK + (size_t)TILE_POS * sizeof(unsigned short);
+  static const size_t COUNT_BYTES   = OFF_GBASE;
+};
+
+//  Validity of the 32 windows of length k that start at this thread's positions.
+//  m0..m2: validity bits of positions 0..95 (bit 31-j of m_i is position 32i+j).
+__device__ __forceinline__ u32 windows_valid(u32 m0, u32 m1, u32 m2, u32 k) {
+  u64 hi = ((u64)m0 << 32) | m1, lo = (u64)m2 << 32;                        //  position q at bit 127-q
+  u32 run = 1;
+  while (run < k) {
+    const u32 s = min(run, k - run);                                        //  1..32
+    const u64 shi = (hi << s) | (lo >> (64 - s)), slo = lo << s;
+    hi &= shi;  lo &= slo;
+    run += s;
+  }
+  return (u32)(hi >> 32);
+}
+
+//  Prefix bin of the counted k-mer that starts at thread-relative position q.
+__device__ __forceinline__ u32 kmer_bin(const Window &w, u32 q, u32 k, u32 mode, u32 binBits) {
+  const u32 half = binBits >> 1;
+  const u32 fTop = (u32)bits_ending_at(w, 2 * q + binBits, binBits);
+  const u32 tail = (u32)bits_ending_at(w, 2 * (q + k), binBits);
+  const u32 rTop = (u32)revcomp64(tail, half);
+  return (mode == MB_MODE_FORWARD) ? fTop : (mode == MB_MODE_REVERSE) ? rTop : min(fTop, rTop);
+}
+
+__device__ __forceinline__ u64 kmer_key(const Window &w, u32 q, u32 k, u32 mode, u64 *) {
+  const u64 f = bits_ending_at(w, 2 * (q + k), 2 * k);
+  if (mode == MB_MODE_FORWARD) return f;
+  const u64 r = revcomp64(f, k);
+  if (mode == MB_MODE_REVERSE) return r;
+  return f < r ? f : r;
+}
+
+__device__ __forceinline__ ulonglong2 kmer_key(const Window &w, u32 q, u32 k, u32 mode, ulonglong2 *) {
+  const u64 flo = bits_ending_at(w, 2 * (q + k), 64);
+  const u64 fhi = bits_ending_at(w, 2 * (q + k) - 64, 2 * k - 64);
+  u64 rhi, rlo;
+  revcomp128(fhi, flo, k, rhi, rlo);
+  bool useF = (mode == MB_MODE_FORWARD);
+  if (mode == MB_MODE_CANONICAL) useF = (fhi < rhi) || (fhi == rhi && flo < rlo);
+  return useF ? make_ulonglong2(flo, fhi) : make_ulonglong2(rlo, rhi);
+}
+
+template <int KW, bool COUNT_ONLY>
+__global__ void __launch_bounds__(ExtractShape<KW>::THREADS)
+extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
+               const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles) {
+  typedef typename KeyT<KW>::type Key;
+  typedef ExtractSmem<KW>         S;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  u64            *bar   = (u64 *)(smem + S::OFF_BAR);
+  u32            *rec[2] = { (u32 *)(smem + S::OFF_REC0), (u32 *)(smem + S::OFF_REC1) };
+  u32            *cnt   = (u32 *)(smem + S::OFF_CNT);
+  u64            *gbase = (u64 *)(smem + S::OFF_GBASE);
+  Key            *stash = (Key *)(smem + S::OFF_STASH);
+  unsigned short *rank  = (unsigned short *)(smem + S::OFF_RANK);
+
+  const u32 t = threadIdx.x;
+  const u32 nBins = 1u << p.binBits;
+
+  if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  for (u32 b = t; b < nBins; b += blockDim.x) cnt[b] = 0;
+  __syncthreads();
+
+  const unsigned char *storeBytes = (const unsigned char *)p.store;
+
+  u64 tile = blockIdx.x;
+  if (t == 0 && tile < nTiles) {
+    mbar_expect_tx(&bar[0], S::REC_BYTES);
+    tma_bulk_g2s(rec[0], storeBytes + tile * (u64)(S::THREADS * MB_STORE_REC_WORDS * 4), S::REC_BYTES, &bar[0]);
+  }
+
+  for (u32 it = 0; tile < nTiles; it++, tile += gridDim.x) {
+    const u32 buf = it & 1;
+
+    //  Prefetch the next tile into the other buffer (it was last read two iterations ago, and
+    //  every thread has passed a __syncthreads since).
+    const u64 next = tile + gridDim.x;
+    if (t == 0 && next < nTiles) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar[buf ^ 1], S::REC_BYTES);
+      tma_bulk_g2s(rec[buf ^ 1], storeBytes + next * (u64)(S::THREADS * MB_STORE_REC_WORDS * 4), S::REC_BYTES, &bar[buf ^ 1]);
+    }
+
+    while (!mbar_try_wait(&bar[buf], (it >> 1) & 1)) { }
+
+    const u32 *r = rec[buf] + t * MB_STORE_REC_WORDS;
+    Window w;
+    w.w0 = ((u64)r[0] << 32) | r[1];
+    w.w1 = ((u64)r[3] << 32) | r[4];
+    w.w2 = ((u64)r[6] << 32) | r[7];
+    u32 valid = windows_valid(r[2], r[5], r[8], p.k);
+
+    //  Positions at or beyond the end of the store never start a k-mer (their records are zero),
+    //  so no bound check is needed here.
+
+    //  Pre-filter: which of my valid windows fall into this pass's bins?
+    u32 keep = 0;
+    for (u32 v = valid; v; ) {
+      const u32 q   = __clz(v);                       //  position 0 is bit 31
+      v &= ~(0x80000000u >> q);
+      const u32 bin = kmer_bin(w, q, p.k, p.mode, p.binBits);
+      if (COUNT_ONLY) {
+        atomicAdd(&cnt[bin], 1u);
+      } else if (bin >= p.binLo && bin < p.binHi) {
+        keep |= 0x80000000u >> q;
+      }
+    }
+
+    if (!COUNT_ONLY) {
+      for (u32 v = keep; v; ) {
+        const u32 q = __clz(v);
+        v &= ~(0x80000000u >> q);
+        const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
+        const u32 bin = key_field(key, 2 * p.k - p.binBits, p.binBits);
+        stash[t * 32 + q] = key;
+        rank [t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin], 1u);
+      }
+      __syncthreads();
+
+      //  Reserve this tile's run in every bin segment it contributes to.
+      for (u32 b = p.binLo + t; b < p.binHi; b += blockDim.x) {
+        const u32 c = cnt[b];
+        if (c) {
+          gbase[b] = binStart[b] + atomicAdd((unsigned long long *)&binCursor[b], (unsigned long long)c);
+          cnt[b]   = 0;
+        }
+      }
+      __syncthreads();
+
+      for (u32 v = keep; v; ) {
+        const u32 q = __clz(v);
+        v &= ~(0x80000000u >> q);
+        const Key key = stash[t * 32 + q];
+        const u32 bin = key_field(key, 2 * p.k - p.binBits, p.binBits);
+        out[gbase[bin] + rank[t * 32 + q]] = key;
+      }
+    }
+    __syncthreads();                                  //  all reads of rec[buf] / gbase done
+  }
+
+  if (COUNT_ONLY) {
+    __syncthreads();
+    for (u32 b = t; b < nBins; b += blockDim.x)
+      if (cnt[b]) atomicAdd((unsigned long long *)&binCount[b], (unsigned long long)cnt[b]);
+  }
+}
+
+template <int KW, bool COUNT_ONLY>
+cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, u64 *binCount, cudaStream_t s) {
+  typedef ExtractSmem<KW> S;
+  const size_t smem = COUNT_ONLY ? S::COUNT_BYTES : S::SCATTER_BYTES;
+  auto kern = extract_kernel<KW, COUNT_ONLY>;
+
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+
+  int dev = 0, sms = 0, perSm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, S::THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (perSm < 1) perSm = 1;
+
+  const u64 nRecords = p.nPositions / 32;
+  const u64 nTiles   = (nRecords + S::THREADS - 1) / S::THREADS;
+  if (nTiles == 0) return cudaSuccess;
+  u64 grid = (u64)sms * perSm;                                   //  persistent: a multiple of the SM count
+  if (grid > nTiles) grid = nTiles;
+
+  kern<<<(unsigned)grid, S::THREADS, smem, s>>>(p, (typename KeyT<KW>::type *)out, binStart, binCursor, binCount, nTiles);
+  return cudaGetLastError();
+}
+
+}  //  namespace
+
+
+cudaError_t mb_launch_bin_histogram(const MbExtractParams &p, u64 *dBinCount, cudaStream_t s) {
+  return (p.k <= 32) ? launch<1, true>(p, nullptr, nullptr, nullptr, dBinCount, s)
+                     : launch<2, true>(p, nullptr, nullptr, nullptr, dBinCount, s);
+}
+
+cudaError_t mb_launch_extract(const MbExtractParams &p, void *dKeys, const u64 *dBinStart, u64 *dBinCursor, cudaStream_t s) {
+  return (p.k <= 32) ? launch<1, false>(p, dKeys, dBinStart, dBinCursor, nullptr, s)
+                     : launch<2, false>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
+}

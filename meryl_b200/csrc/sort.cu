@@ -1,0 +1,319 @@
+//  K4: segmented LSD radix sort of packed k-mers ("onesweep": one read + one write of every key
+//  per digit, decoupled look-back between tiles).
+//
+//  Replaces std::sort of each prefix bucket (merylCountArray::countSingleKmers,
+//  src/meryl/merylCountArray.C:324-330).  The reference sorts 2^wPrefix small buckets on the CPU;
+//  here one launch per digit sorts ALL prefix-bin segments of a pass at once: a segment is the
+//  run of keys sharing their top binBits bits (put there by the extraction scatter), and only the
+//  remaining 2k-binBits low bits are sorted, 8 (or fewer) bits per pass.
+//
+//   sort_hist_kernel    one read of the keys: per (segment, pass, digit) counts
+//   sort_scan_kernel    exclusive scan over digits -> first output index of every (segment, pass, digit)
+//   sort_sweep_kernel   per pass: tile = 256 threads x ITEMS keys.  Keys are ranked inside the tile
+//                       (warp match_any multisplit, stable), the tile publishes its digit counts,
+//                       looks back over the earlier tiles OF ITS SEGMENT for its exclusive prefix,
+//                       reorders the keys by digit in shared memory and writes digit runs to HBM.
+//
+//  Algorithmic HBM bytes per key: hist 1*W, each sweep pass 2*W (W = 8 or 16 bytes), plus the tile
+//  status traffic (2 KB per tile written, >= 2 KB read).  Bound: HBM bandwidth.
+
+#include "kernels.cuh"
+
+namespace {
+
+const int SORT_THREADS = 256;
+const int SORT_WARPS   = SORT_THREADS / 32;
+
+template <int KW> struct SortShape;
+template <> struct SortShape<1> { static const int ITEMS = 16; };
+template <> struct SortShape<2> { static const int ITEMS = 8;  };
+
+//  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:58] epoch (pass tag, 1..15)  [57:0] value
+#define ST_FLAG(v)    ((u32)((v) >> 62))
+#define ST_EPOCH(v)   ((u32)(((v) >> 58) & 15))
+#define ST_VALUE(v)   ((v) & ((1ull << 58) - 1))
+#define ST_MAKE(f, e, x)  (((u64)(f) << 62) | ((u64)(e) << 58) | (u64)(x))
+
+//  Largest s with tileStart[s] <= tile  (tileStart has nSegs+1 entries, non-decreasing).
+__device__ __forceinline__ u32 find_segment(const u64 *__restrict__ tileStart, u32 nSegs, u64 tile) {
+  u32 lo = 0, hi = nSegs;                    //  answer in [lo, hi)
+  while (hi - lo > 1) {
+    const u32 mid = (lo + hi) >> 1;
+    if (tileStart[mid] <= tile) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+struct SortPassTable { u32 nPasses; u32 shift[16]; u32 bits[16]; };
+
+//  ---- histogram ------------------------------------------------------------------------------
+
+const int HIST_TILES_PER_CTA = 16;
+
+template <int KW>
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
+                 const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
+                 SortPassTable pt, u64 *__restrict__ ghist) {
+  typedef typename KeyT<KW>::type Key;
+  const int TILE = SORT_THREADS * SortShape<KW>::ITEMS;
+  __shared__ u32 sh[16 * MB_RADIX];
+
+  const u32 t = threadIdx.x;
+  for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) sh[i] = 0;
+  __syncthreads();
+
+  const u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
+  u64 tileEnd = tile0 + HIST_TILES_PER_CTA;
+  if (tileEnd > nTiles) tileEnd = nTiles;
+
+  u32 seg = find_segment(segTile, nSegs, tile0);
+
+  for (u64 tile = tile0; tile < tileEnd; tile++) {
+    //  advance to the segment of this tile, flushing when it changes
+    u32 s = seg;
+    while (segTile[s + 1] <= tile) s++;
+    if (s != seg) {
+      __syncthreads();
+      for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) {
+        const u32 c = sh[i];
+        if (c) { atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * MB_RADIX + i], (unsigned long long)c); sh[i] = 0; }
+      }
+      __syncthreads();
+      seg = s;
+    }
+
+    const u64 begin = segStart[seg] + (tile - segTile[seg]) * TILE;
+    u64 n = segStart[seg + 1] - begin;
+    if (n > (u64)TILE) n = TILE;
+
+    for (u32 j = t; j < (u32)n; j += SORT_THREADS) {
+      const Key key = keys[begin + j];
+      for (u32 p = 0; p < pt.nPasses; p++)
+        atomicAdd(&sh[p * MB_RADIX + key_field(key, pt.shift[p], pt.bits[p])], 1u);
+    }
+  }
+
+  __syncthreads();
+  for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) {
+    const u32 c = sh[i];
+    if (c) atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * MB_RADIX + i], (unsigned long long)c);
+  }
+}
+
+//  ---- scan: counts -> first output index of each (segment, pass, digit) -------------------------
+
+__global__ void __launch_bounds__(MB_RADIX)
+sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 nPasses) {
+  __shared__ u64 warpSum[MB_RADIX / 32];
+  const u32 seg = blockIdx.x, pass = blockIdx.y, d = threadIdx.x;
+  u64 *h = ghist + ((u64)seg * nPasses + pass) * MB_RADIX;
+
+  const u64 c = h[d];
+  u64 incl = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u64 v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((d & 31) >= (u32)o) incl += v;
+  }
+  if ((d & 31) == 31) warpSum[d >> 5] = incl;
+  __syncthreads();
+  u64 base = 0;
+  for (u32 w = 0; w < (d >> 5); w++) base += warpSum[w];
+  h[d] = segStart[seg] + base + incl - c;
+}
+
+//  ---- one digit pass ---------------------------------------------------------------------------
+
+template <int KW>
+__global__ void __launch_bounds__(SORT_THREADS, (KW == 1 ? 3 : 3))
+sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+                  const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs,
+                  const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
+                  u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
+  typedef typename KeyT<KW>::type Key;
+  const int ITEMS = SortShape<KW>::ITEMS;
+  const int TILE  = SORT_THREADS * ITEMS;
+
+  __shared__ Key  stage[TILE];
+  __shared__ u32  wcnt[SORT_WARPS][MB_RADIX + 1];        //  [..][256] collects the padding of a ragged tile
+  __shared__ u32  binOff[MB_RADIX];
+  __shared__ u64  gofs[MB_RADIX];
+  __shared__ u32  warpTot[SORT_WARPS];
+  __shared__ u64  sTile;
+
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  for (u32 i = t; i < SORT_WARPS * (MB_RADIX + 1); i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+
+  const u64 tile  = sTile;
+  const u32 seg   = find_segment(segTile, nSegs, tile);
+  const u64 first = segTile[seg];
+  const u64 begin = segStart[seg] + (tile - first) * TILE;
+  u64 n64 = segStart[seg + 1] - begin;
+  const u32 n = n64 > (u64)TILE ? (u32)TILE : (u32)n64;
+
+  //  load (warp-striped: consecutive lanes, consecutive keys) and rank
+  //  dr[i]: digit in the low 16 bits (MB_RADIX for the padding of a ragged tile), rank within
+  //  (warp, digit) in the high 16 bits.
+  Key key[ITEMS];
+  u32 dr[ITEMS];
+  const u32 wbase = warp * 32 * ITEMS;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const u32 j = wbase + i * 32 + lane;
+    if (j < n) { key[i] = in[begin + j]; dr[i] = key_field(key[i], shift, bits); }
+    else       { dr[i] = MB_RADIX; }
+  }
+
+  const u32 ltMask = (1u << lane) - 1;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const u32 m      = __match_any_sync(0xffffffffu, dr[i]);
+    const u32 leader = __ffs(m) - 1;
+    u32 prior = 0;
+    if (lane == leader) prior = atomicAdd(&wcnt[warp][dr[i]], (u32)__popc(m));
+    prior  = __shfl_sync(0xffffffffu, prior, leader);
+    dr[i] |= (prior + __popc(m & ltMask)) << 16;
+  }
+  __syncthreads();
+
+  //  per digit: exclusive scan over the warps, tile total
+  u32 myCount = 0;
+  {
+    const u32 d = t;                                    //  SORT_THREADS == MB_RADIX
+    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) { const u32 c = wcnt[w][d]; wcnt[w][d] = run; run += c; }
+    myCount = run;
+  }
+
+  //  exclusive scan of the tile's digit counts -> position of each digit run in the stage buffer
+  u32 incl = myCount;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32)o) incl += v;
+  }
+  if (lane == 31) warpTot[warp] = incl;
+  __syncthreads();
+  {
+    u32 base = 0;
+    for (u32 w = 0; w < warp; w++) base += warpTot[w];
+    binOff[t] = base + incl - myCount;
+  }
+
+  //  publish, look back over the earlier tiles of this segment
+  {
+    const u32 d = t;
+    u64 *mine = status + tile * MB_RADIX + d;
+    u64 excl = 0;
+    if (tile == first) {
+      st_volatile_u64(mine, ST_MAKE(2, epoch, myCount));
+    } else {
+      st_volatile_u64(mine, ST_MAKE(1, epoch, myCount));
+      u64 j = tile - 1;
+      for (;;) {
+        const u64 v = ld_volatile_u64(status + j * MB_RADIX + d);
+        if (ST_FLAG(v) == 0 || ST_EPOCH(v) != epoch) continue;          //  not published yet
+        excl += ST_VALUE(v);
+        if (ST_FLAG(v) == 2) break;
+        j--;
+      }
+      st_volatile_u64(mine, ST_MAKE(2, epoch, excl + myCount));
+    }
+    gofs[d] = gbase[((u64)seg * nPasses + pass) * MB_RADIX + d] + excl - binOff[d];
+  }
+  __syncthreads();
+
+  //  reorder in shared memory
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    if ((dr[i] & 0xffff) < MB_RADIX)
+      stage[binOff[dr[i] & 0xffff] + wcnt[warp][dr[i] & 0xffff] + (dr[i] >> 16)] = key[i];
+  __syncthreads();
+
+  //  digit runs to HBM
+  for (u32 j = t; j < n; j += SORT_THREADS) {
+    const Key k = stage[j];
+    out[gofs[key_field(k, shift, bits)] + j] = k;
+  }
+}
+
+}  //  namespace
+
+
+void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
+  const u32 P = (sortBits + MB_RADIX_BITS - 1) / MB_RADIX_BITS;
+  plan->nPasses = P;
+  u32 shift = 0;
+  for (u32 p = 0; p < P; p++) {
+    const u32 b = sortBits / P + (p < sortBits % P ? 1 : 0);
+    plan->shift[p] = shift;
+    plan->bits[p]  = b;
+    shift += b;
+  }
+}
+
+u32 mb_sort_tile_keys(u32 keyWords) {
+  return SORT_THREADS * (keyWords == 1 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
+}
+
+//  workspace: [ghist: nSegs*nPasses*256 u64][tile counters: 16 u64][status: nTiles*256 u64]
+size_t mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses) {
+  return ((size_t)nSegs * nPasses * MB_RADIX + 16 + (size_t)nTiles * MB_RADIX) * sizeof(u64);
+}
+
+template <int KW>
+static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
+                             const u64 *dSegStart, const u64 *dSegTile, u32 nSegs, u64 nTiles,
+                             const MbSortPlan &plan, void *dWorkspace, size_t workspaceBytes,
+                             int *resultInB, u32 *nLaunches, cudaStream_t s, cudaEvent_t evAfterHist) {
+  typedef typename KeyT<KW>::type Key;
+  *resultInB = 0;
+  if (nLaunches) *nLaunches = 0;
+  if (nKeys == 0 || plan.nPasses == 0 || nTiles == 0) {
+    if (evAfterHist) cudaEventRecord(evAfterHist, s);
+    return cudaSuccess;
+  }
+  if (workspaceBytes < mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses)) return cudaErrorInvalidValue;
+
+  u64 *ghist   = (u64 *)dWorkspace;
+  u64 *counter = ghist + (size_t)nSegs * plan.nPasses * MB_RADIX;
+  u64 *status  = counter + 16;
+
+  cudaError_t e = cudaMemsetAsync(dWorkspace, 0, mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses), s);
+  if (e != cudaSuccess) return e;
+
+  SortPassTable pt;
+  pt.nPasses = plan.nPasses;
+  for (u32 p = 0; p < 16; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
+
+  const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
+  sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, ghist);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  sort_scan_kernel<<<dim3(nSegs, plan.nPasses), MB_RADIX, 0, s>>>(ghist, dSegStart, plan.nPasses);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (nLaunches) *nLaunches += 2;
+  if (evAfterHist) cudaEventRecord(evAfterHist, s);
+
+  Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
+  for (u32 p = 0; p < plan.nPasses; p++) {
+    sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, 0, s>>>(src, dst, dSegStart, dSegTile, nSegs, ghist, plan.nPasses, p,
+                                                                   plan.shift[p], plan.bits[p], status, counter + p, p + 1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (nLaunches) *nLaunches += 1;
+    Key *tmp = src; src = dst; dst = tmp;
+  }
+  *resultInB = (plan.nPasses & 1);
+  return cudaSuccess;
+}
+
+cudaError_t mb_launch_sort(u32 keyWords, void *dKeysA, void *dKeysB, u64 nKeys,
+                           const u64 *dSegStart, const u64 *dSegTile, u32 nSegs, u64 nTiles,
+                           const MbSortPlan &plan, void *dWorkspace, size_t workspaceBytes,
+                           int *resultInB, u32 *nLaunches, cudaStream_t s, cudaEvent_t evAfterHist) {
+  return keyWords == 1
+    ? sort_impl<1>(dKeysA, dKeysB, nKeys, dSegStart, dSegTile, nSegs, nTiles, plan, dWorkspace, workspaceBytes, resultInB, nLaunches, s, evAfterHist)
+    : sort_impl<2>(dKeysA, dKeysB, nKeys, dSegStart, dSegTile, nSegs, nTiles, plan, dWorkspace, workspaceBytes, resultInB, nLaunches, s, evAfterHist);
+}

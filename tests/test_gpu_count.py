@@ -1,0 +1,194 @@
+"""GPU parity tests of the whole `meryl count` path through the C ABI: FASTA/FASTQ bytes in,
+the 129-file db out, compared byte for byte with
+  - the committed golden dbs written by the unmodified reference binary (tests/golden/),
+  - the C oracle on seeded synthetic inputs (SURVEY.md 8(d) shapes, Appendix A.5 edge cases),
+  - the reference binary itself when oracle/_ref/meryl travelled to this box,
+and, at sizes the oracle cannot reach quickly, through size-independent properties."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+_OPS = {"count": "count", "count-forward": "count-forward", "count-reverse": "count-reverse"}
+
+
+def _words(words):
+    k = mem = None
+    op = "count"
+    for w in words:
+        if w.startswith("k="):
+            k = int(w[2:])
+        elif w.startswith("memory="):
+            mem = float(w[7:])
+        elif w in _OPS:
+            op = w
+    return k, mem, op
+
+
+def _gpu_db(tmp, paths, k, mem, op, n=None, name="gpu.meryl"):
+    out = os.path.join(tmp, name)
+    mb.count(paths, out, k, op, memory_gb=mem, n=n)
+    return out
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_golden_db_bit_exact(tmp_path, name):
+    inp, gold, words, _ = util.load_golden(name, str(tmp_path))
+    k, mem, op = _words(words)
+    out = _gpu_db(str(tmp_path), [inp], k, mem, op)
+    util.assert_same_db(gold, out)
+
+
+def test_cli_golden(tmp_path):
+    inp, gold, words, _ = util.load_golden("fastq_k31", str(tmp_path))
+    out = str(tmp_path / "cli.meryl")
+    p = subprocess.run([mb.CLI_PATH] + words + ["threads=4", inp, "output", out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Configured complex mode" in p.stderr
+    util.assert_same_db(gold, out)
+
+
+def _vs_oracle(tmp_path, files, k, op="count", memory="2"):
+    paths = []
+    for name, data in files.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        paths.append(str(p))
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=%d" % k, "memory=%s" % memory, op, *paths, "output", ora])
+    out = _gpu_db(str(tmp_path), paths, k, float(memory), op)
+    util.assert_same_db(ora, out)
+    return out
+
+
+def test_c1_config_10mb_fasta_k21(tmp_path):
+    """BASELINE.json configs[0]: k=21 count on 10 x 1 Mbp FASTA (seed 42), bit-exact db."""
+    out = _vs_oracle(tmp_path, {"c1.fa": synth.fasta_bytes(10, 1_000_000, 42)}, 21, memory="8")
+    if util.have_ref():
+        ref = str(tmp_path / "ref.meryl")
+        util.run_ref(["k=21", "threads=4", "memory=8", "count", str(tmp_path / "c1.fa"), "output", ref])
+        util.assert_same_db(ref, out)
+
+
+@pytest.mark.parametrize("k", [4, 6, 13, 14, 15, 16, 22, 31, 32, 33, 51, 64])
+def test_k_sweep(tmp_path, k):
+    _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 30_000, 100 + k)}, k)
+
+
+@pytest.mark.parametrize("op", ["count-forward", "count-reverse"])
+def test_forward_reverse(tmp_path, op):
+    _vs_oracle(tmp_path, {"a.fq": synth.reads_fastq_bytes(20_000, 2_000, 120, 0.01, 5)}, 21, op=op)
+
+
+def test_reads_with_errors_k21_and_k31(tmp_path):
+    data = synth.reads_fastq_bytes(100_000, 30_000, 150, 0.002, 9)
+    _vs_oracle(tmp_path, {"r.fq": data}, 21)
+    (tmp_path / "b").mkdir()
+    _vs_oracle(tmp_path / "b", {"r.fq": data}, 31)
+
+
+def test_multiple_inputs_and_formats(tmp_path):
+    _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(3, 20_000, 1),
+                          "b.fq": synth.reads_fastq_bytes(20_000, 1_000, 100, 0.01, 2),
+                          "c.fa": synth.fasta_bytes(1, 50_000, 3, width=60, eol=b"\r\n")}, 21)
+
+
+def test_low_complexity_big_counts(tmp_path):
+    rng = np.random.default_rng(5)
+    unit = synth.random_bases(3000, rng).tobytes()
+    recs = [b">r%d\n" % i + unit[: 200 + (1 + (i * 7) % 300) * 9] + b"\n" for i in range(400)]
+    recs.append(b">polyA\n" + b"A" * 100_000 + b"\n")
+    recs.append(b">polyAC\n" + b"AC" * 80_000 + b"\n")
+    _vs_oracle(tmp_path, {"rep.fa": b"".join(recs)}, 21)
+
+
+def test_no_kmers_at_all(tmp_path):
+    _vs_oracle(tmp_path, {"e.fa": b">only\nACGT\n"}, 21)
+
+
+def test_gz_input(tmp_path):
+    import gzip
+    data = synth.fasta_bytes(2, 20_000, 8)
+    plain = tmp_path / "a.fa"
+    plain.write_bytes(data)
+    gz = tmp_path / "b.fa.gz"
+    gz.write_bytes(gzip.compress(data))
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=21", "wprefix=10", "count", str(plain), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    with mb.Counter(21, 10) as c:
+        c.add_file(str(gz))
+        c.count()
+        c.write_db(out)
+    util.assert_same_db(ora, out)
+
+
+def test_add_bases_seam_equals_file_path(tmp_path):
+    """merylInput::loadBases seam: pushing base chunks == parsing the file."""
+    data = synth.reads_fastq_bytes(30_000, 4_000, 150, 0.01, 21)
+    stream = util.oracle_parse(data)
+    a, b = str(tmp_path / "a.meryl"), str(tmp_path / "b.meryl")
+    with mb.Counter(21, 10) as c:
+        c.add_file_bytes(data)
+        c.count()
+        c.write_db(a)
+    with mb.Counter(21, 10) as c:
+        for rec in stream.split(b"."):
+            if rec:
+                h = len(rec) // 2
+                c.add_bases(rec[:h], end_of_sequence=False)     # a record arrives in pieces
+                c.add_bases(rec[h:], end_of_sequence=True)
+        c.count()
+        c.write_db(b)
+    util.assert_same_db(a, b)
+
+
+def test_counted_arrays_and_histogram_properties():
+    """Size-independent checks on a larger input: sum of counts == instances, strictly ascending
+    distinct k-mers, histogram totals consistent with the master index statistics."""
+    nreads, readlen, k = 400_000, 150, 21
+    data = synth.reads_fastq_bytes(2_000_000, nreads, readlen, 0.001, 31)
+    with mb.Counter(k, 12, flags=mb.FLAG_KEEP_COUNTED) as c:
+        c.add_file_bytes(data)
+        c.count()
+        st = c.stats()
+        lo, hi, cnt = c.counted()
+        v, o = c.histogram()
+    assert st.nKmers == nreads * (readlen - k + 1)
+    assert int(cnt.sum(dtype=np.uint64)) == st.nKmers == st.nTotal
+    assert len(lo) == st.nDistinct and np.all(lo[1:] > lo[:-1])
+    assert int(o.sum()) == st.nDistinct and int((v * o).sum()) == st.nTotal
+    assert int(o[v == 1].sum()) == st.nUnique == int((cnt == 1).sum())
+    # canonical: no k-mer is larger than its reverse complement
+    sample = lo[:: max(1, len(lo) // 2000)]
+    for x in sample[:200]:
+        x = int(x)
+        rc = 0
+        for i in range(k):
+            rc |= (((x >> (2 * i)) & 3) ^ 2) << (2 * (k - 1 - i))
+        assert x <= rc
+
+
+def test_multi_pass_equals_single_pass(tmp_path):
+    """A small workspace forces several prefix-range passes; the db must not change."""
+    data = synth.reads_fastq_bytes(300_000, 120_000, 150, 0.002, 77)
+    a, b = str(tmp_path / "a.meryl"), str(tmp_path / "b.meryl")
+    with mb.Counter(21, 12) as c:
+        c.add_file_bytes(data)
+        c.count()
+        one = c.stats().nPasses
+        c.write_db(a)
+    with mb.Counter(21, 12, workspace_bytes=1 << 29) as c:
+        c.add_file_bytes(data)
+        c.count()
+        many = c.stats().nPasses
+        c.write_db(b)
+    assert one == 1 and many > 1, (one, many)
+    util.assert_same_db(a, b)

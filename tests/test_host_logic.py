@@ -1,0 +1,152 @@
+"""CPU-side tests of the product's host code (no GPU needed): the C ABI loads and exports what
+include/meryl_b200.h declares, the prefix-width planner agrees with the oracle (which is pinned to
+the reference), the FASTA/FASTQ parser emits the oracle's base stream, and device entry points
+fail loudly (no CPU fallback) when no GPU exists."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import synth
+
+ROOT = util.ROOT
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_product():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "meryl_b200", "csrc")], check=True)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "meryl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    L = ctypes.CDLL(mb.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mb.MerylB200Error) as e:
+        mb.Counter(21, 10)
+    assert e.value.code == -2
+    p = subprocess.run([mb.CLI_PATH, "k=21", "count", os.path.join(ROOT, "README.md"), "output", "/tmp/x.meryl"],
+                       capture_output=True, text=True)
+    assert p.returncode == 1
+
+
+@pytest.mark.parametrize("k", [3, 5, 6, 8, 13, 14, 15, 16, 17, 20, 21, 22, 31, 32, 33, 51, 64])
+def test_planner_matches_oracle(k):
+    rng = np.random.default_rng(k)
+    ns = [1, 1000, 10_125_060, 626_888_890, 86_670_000_000, 210_000_000_000] + [int(x) for x in 10 ** rng.uniform(3, 12, 12)]
+    mems = [1, 2, 8, 32, 180, 256, 1024] + [float(x) for x in rng.uniform(0.5, 2048, 6)]
+    L = util.oracle_lib()
+    for n in ns:
+        for m in mems:
+            mbytes = int(m * 1024 ** 3)
+            wp = ctypes.c_uint32(0)
+            used = ctypes.c_uint64(0)
+            nb = ctypes.c_uint32(0)
+            rc = L.ora_plan(k, n, mbytes, ctypes.byref(wp), ctypes.byref(used), ctypes.byref(nb))
+            if rc != 0:
+                with pytest.raises(mb.MerylB200Error):
+                    mb.plan(k, n, mbytes)
+                continue
+            p = mb.plan(k, n, mbytes)
+            assert (p.w_prefix, p.mem_used, p.n_batches) == (wp.value, used.value, nb.value), (k, n, m)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+@pytest.mark.parametrize("k,n,mem", [(21, 10_125_060, 8), (21, 210_000_000_000, 256), (31, 210_000_000_000, 512),
+                                     (51, 100_000_000_000, 1024), (16, 5_000_000, 1), (14, 100_000_000, 4)])
+def test_planner_matches_reference(k, n, mem):
+    assert mb.plan(k, n, int(mem * 1024 ** 3)).w_prefix == util.ref_wprefix(k, n, mem)
+
+
+def _collapse(s: bytes) -> bytes:
+    return re.sub(rb"\.+", b".", s)
+
+
+def _product_parse(data: bytes) -> bytes:
+    L = mb.lib()
+    n = ctypes.c_uint64(0)
+    buf = ctypes.create_string_buffer(len(data) + 64)
+    rc = L.mb_dbg_parse(data, len(data), buf, len(data) + 64, ctypes.byref(n))
+    if rc != 0:
+        raise mb.MerylB200Error(rc, L.mb_last_error().decode())
+    return buf.raw[: n.value]
+
+
+EDGE = [
+    b"",
+    b"\n\n",
+    b">only header",
+    b">h\nACGT",
+    b">h\nACGT\n",
+    b">h\r\nACGT\r\nTTTT\r\n>i\r\nGG\r\n",
+    b">h\rACGT\rTT\r>i\rGG",
+    b">a\n>b\nACGT\n",
+    b">a\n\n\n>b\n\nAC\n\nGT\n\n",
+    b">a\nAC GT\tTT\n",
+    b"@r1\nACGT\n+\nIIII\n@r2\nTTTT\n+r2\n@@@@\n",
+    b"@r1\nACGT\n+\n>>>>\n@r2\nTTTT\n+\n++++\n",
+    b"@r1\nACGT\n+\nIIII",
+    b"@r1\nACGT\n+\n",
+    b"@r1\nACGT\n+",
+    b"@r1\r\nACGT\r\n+\r\nIIII\r\n@r2\r\nGGGG\r\n+\r\nIIII\r\n",
+    b">x\nACGT+TT\nAA\n+AC\nGGGG\n>y\nCC\n",
+    b">x\nACGT\n+\nAAAA\nCCCC\n",
+    b">x\nAC>GT\n@T\n",
+    b"  \n>x desc\nNNNNACGTNNNN\n",
+]
+
+
+@pytest.mark.parametrize("i", range(len(EDGE)))
+def test_parser_edge_cases_match_oracle(i):
+    data = EDGE[i]
+    assert _collapse(_product_parse(data)) == _collapse(util.oracle_parse(data))
+
+
+def test_parser_fuzz_matches_oracle():
+    rng = np.random.default_rng(123)
+    alphabet = np.frombuffer(b"ACGTacgtN>@+\n\n\r \tIx", dtype=np.uint8)
+    for it in range(400):
+        n = int(rng.integers(1, 200))
+        body = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        data = (b">" if it % 2 else b">s\n") + body
+        assert _collapse(_product_parse(data)) == _collapse(util.oracle_parse(data)), data
+
+
+def test_parser_rejects_non_sequence_and_sam():
+    for data in [b"hello world\n", b"@HD\tVN:1.6\n@SQ\tSN:x\n", b"@r1\tfoo\nACGT\t0\n"]:
+        with pytest.raises(mb.MerylB200Error):
+            _product_parse(data)
+        with pytest.raises(ValueError):
+            util.oracle_parse(data)
+
+
+def test_parser_large_fastq_and_fasta():
+    for data in [synth.reads_fastq_bytes(10_000, 3_000, 150, 0.01, 5), synth.fasta_bytes(3, 100_000, 6),
+                 synth.fasta_bytes(2, 50_000, 7, width=70, eol=b"\r\n")]:
+        assert _collapse(_product_parse(data)) == _collapse(util.oracle_parse(data))
+
+
+def test_estimate_kmers_in_file(tmp_path):
+    p = tmp_path / "a.fa"
+    p.write_bytes(b">x\nACGT\n" * 100)
+    assert mb.estimate_kmers_in_file(str(p)) == 800
+    g = tmp_path / "a.fa.gz"
+    g.write_bytes(b"x" * 1000)
+    assert mb.estimate_kmers_in_file(str(g)) == 3000
+    b = tmp_path / "a.fa.bz2"
+    b.write_bytes(b"x" * 1001)
+    assert mb.estimate_kmers_in_file(str(b)) == int(1001 * 3.5)
