@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- `meryl count` throughput on B200 (BASELINE.json metric: k-mers/s end to end).
+
+Workload (config.workload): BASELINE.json configs[1] -- k=21 canonical count of synthetic 150 bp
+Illumina-shape reads (uniform-random 3 Gbp genome, both strands, 0.1 % substitutions),
+`--gbp` billion bases of them PER GPU (default 100 when it fits, otherwise the largest size that
+fits the device and the host, stated in config).  One step = one complete count of the workload.
+
+  value      whole-job k-mers/s with the input resident in HBM (the 2-bit packed read store) when the
+             timed region starts: prefix histogram -> extract+scatter -> radix sort -> run-length count
+             -> encode, all passes, encoded db left on the device.  CUDA events on the launching stream.
+  e2e        the same job through the C ABI from HOST memory: pinned host buffer of the reads' base
+             stream (the reference's work-buffer format at the merylInput::loadBases seam) -> H2D ->
+             pack -> count -> encoded db copied back to host images.  Wall clock around the calls.
+  roofline   the radix-sort sweep kernel: algorithmic bytes N * P * 2W over its summed device time,
+             against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the unmodified reference binary (oracle/_ref/meryl) on this box's host cores, timed on a
+             bounded prefix of the same reads written as a FASTQ file.
+
+`--impl reference` times only the reference binary (rank 0) and prints the same JSON shape.
+Multi-GPU (torchrun, one rank per GPU): the SAME total workload is split evenly over the ranks
+(strong scaling, as north_star asks: one stated base count at 1, 2, 4 and 8 GPUs); k-mers are routed to
+the GPU that owns their data file by one NCCL all-to-all per pass inside the library.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 21
+READ_LEN = 150
+GENOME_LEN = 3_000_000_000
+ERR = 0.001
+SEED = 2
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "meryl")
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def reference_arm(args, world, rank):
+    """The reference's own CPU implementation (oracle/_ref/meryl) on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    import torch
+    import meryl_b200 as mb
+    cores = os.cpu_count() or 1
+    if not os.access(REF_BIN, os.X_OK):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/meryl not built"}))
+        return
+    n_reads = int(args.ref_gbp * 1e9) // READ_LEN
+    rec = mb.synth_record_bytes(READ_LEN, 1)
+    tmp = tempfile.mkdtemp(prefix="merylref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fq = os.path.join(tmp, "sample.fq")
+    with open(fq, "wb") as fh:
+        chunk = 2_000_000
+        dev = torch.empty(chunk * rec, dtype=torch.uint8, device="cuda")
+        for first in range(0, n_reads, chunk):
+            m = min(chunk, n_reads - first)
+            mb.synth_reads_device(dev.data_ptr(), first, m, READ_LEN, GENOME_LEN, ERR, SEED, 1)
+            torch.cuda.synchronize()
+            fh.write(dev[: m * rec].cpu().numpy().tobytes())
+        del dev
+    n_kmers = n_reads * (READ_LEN - K + 1)
+    times = []
+    for it in range(args.warmup + args.steps):
+        out = os.path.join(tmp, "ref.meryl")
+        subprocess.run(["rm", "-rf", out])
+        t0 = time.perf_counter()
+        p = subprocess.run([REF_BIN, "k=%d" % K, "threads=%d" % cores, "memory=%d" % args.ref_memory_gb, "count", fq, "output", out],
+                           capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if p.returncode != 0:
+            print(json.dumps({"impl": "reference", "unavailable": "reference meryl failed: " + p.stderr[-200:].replace("\n", " ")}))
+            return
+        if it >= args.warmup:
+            times.append(dt)
+    subprocess.run(["rm", "-rf", tmp])
+    ms = 1000 * sum(times) / len(times)
+    val = n_kmers / (ms / 1000)
+    print(json.dumps({
+        "impl": "reference", "metric": "kmers_per_sec_end_to_end_meryl_count", "value": val, "unit": "k-mers/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "meryl count k=21, synthetic 150 bp FASTQ (3 Gbp random genome, 0.1% subst.), reference CPU binary on a %.2f Gbp prefix" % args.ref_gbp,
+                   "k": K, "read_len": READ_LEN, "sample_gbp": args.ref_gbp},
+        "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": cores, "kind": "reference",
+                         "sample": "first %d reads (%.2f Gbp) of the workload as a FASTQ file in /dev/shm, threads=%d memory=%d" % (n_reads, args.ref_gbp, cores, args.ref_memory_gb)},
+        "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gbp", type=float, default=0.0, help="billion bases of reads in total (0 = 100, reduced to what fits)")
+    ap.add_argument("--ref-gbp", type=float, default=1.5, help="size of the reference's bounded sample")
+    ap.add_argument("--ref-memory-gb", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    import torch.distributed as dist
+
+    if args.impl == "reference":
+        if rank == 0:
+            torch.cuda.set_device(0)
+        reference_arm(args, world, rank)
+        return
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import meryl_b200 as mb
+    from meryl_b200 import dist as mbd
+    import psutil
+
+    free_b, total_b = torch.cuda.mem_get_info()
+    host_free = psutil.virtual_memory().available
+
+    # ---- size the workload ---------------------------------------------------------------------
+    gbp = args.gbp if args.gbp > 0 else 100.0
+    total_reads = int(gbp * 1e9) // READ_LEN
+    rec0 = mb.synth_record_bytes(READ_LEN, 0)
+    # device: the packed store (12 B per 32 positions) must leave most of HBM to the key buffers
+    max_reads_dev = int(0.30 * free_b / (rec0 * 12 / 32)) * world
+    # host (e2e leg): every rank pins its share of the base stream and keeps its db images
+    max_reads_host = int(0.55 * host_free / rec0)
+    reduced = None
+    if total_reads > min(max_reads_dev, max_reads_host):
+        total_reads = min(max_reads_dev, max_reads_host)
+        reduced = "reduced to fit (device free %.0f GB, host free %.0f GB)" % (free_b / 1e9, host_free / 1e9)
+    if world > 1:                                   # every rank must agree on the size
+        t = torch.tensor([total_reads], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        total_reads = int(t.item())
+    total_kmers = total_reads * (READ_LEN - K + 1)
+    first_read, n_reads = mbd.shard_range(total_reads, rank, world)   # strong scaling: the same job, split
+
+    n_est = total_reads * mb.synth_record_bytes(READ_LEN, 1)          # what `meryl` would guess: the FASTQ size
+    pl = mb.plan(K, n_est, 1024 << 30)
+
+    def new_counter(flags):
+        c = mb.Counter(K, pl.w_prefix, "count", device=local, flags=flags, rank=rank, world_size=world)
+        if world > 1:
+            c.comm_init(mbd.broadcast_unique_id(mb.Counter.comm_unique_id, device="cuda"))
+        return c
+
+    chunk_reads = 4_000_000
+    dev_chunk = torch.empty(chunk_reads * rec0, dtype=torch.uint8, device="cuda")
+
+    def ingest_device(c):
+        for first in range(0, n_reads, chunk_reads):
+            m = min(chunk_reads, n_reads - first)
+            mb.synth_reads_device(dev_chunk.data_ptr(), first_read + first, m, READ_LEN, GENOME_LEN, ERR, SEED, 0)
+            torch.cuda.synchronize()
+            c.add_bases_device(dev_chunk.data_ptr(), m * rec0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident whole job ------------------------------------------------------
+    sampler = ClockSampler(local)
+    ms_steps, stats = [], None
+    for it in range(args.warmup + args.steps):
+        c = new_counter(mb.FLAG_NO_IMAGES)
+        try:
+            ingest_device(c)
+            barrier()
+            if it == args.warmup:
+                sampler.start()
+            c.count()
+            barrier()
+            st = c.stats()
+            counted = mbd.all_ranks_sum(st.nKmers, "cuda") if world > 1 else st.nKmers
+            assert counted == total_kmers, (counted, total_kmers)
+            if it >= args.warmup:
+                ms_steps.append(st.msTotal)
+                stats = st
+        finally:
+            c.close()
+    clocks = sampler.stop()
+    ms = sum(ms_steps) / len(ms_steps)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = total_kmers / (ms / 1000)
+
+    # roofline of the sort sweep kernel (rank-local)
+    peaks, peak_kind = _peaks()
+    sort_bytes = stats.sortLaunchKeys * 2 * stats.keyBytes
+    achieved = sort_bytes / (stats.msSort / 1000) / 1e9 if stats.msSort > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "sort_sweep_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": sort_bytes / max(1, stats.sortPasses * stats.nPasses),
+                "launches": stats.sortPasses * stats.nPasses}
+
+    # ---- e2e: host buffer -> C ABI -> host images ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(n_reads * rec0, dtype=torch.uint8, pin_memory=True)
+        for first in range(0, n_reads, chunk_reads):
+            m = min(chunk_reads, n_reads - first)
+            mb.synth_reads_device(dev_chunk.data_ptr(), first_read + first, m, READ_LEN, GENOME_LEN, ERR, SEED, 0)
+            host[first * rec0: (first + m) * rec0].copy_(dev_chunk[: m * rec0])
+        torch.cuda.synchronize()
+        e_steps, est = [], None
+        n_e2e = max(1, min(args.steps, 2)) + 1
+        for it in range(n_e2e):
+            barrier()
+            t0 = time.perf_counter()
+            c = new_counter(0)
+            try:
+                c.add_bases_ptr(host.data_ptr(), n_reads * rec0, end_of_sequence=True)
+                c.count()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                est = c.stats()
+            finally:
+                c.close()
+            barrier()
+            if it >= 1:
+                e_steps.append(dt)
+        dt = sum(e_steps) / len(e_steps)
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": total_kmers / dt, "unit": "k-mers/s", "h2d_bytes_per_step": int(est.h2dBytes),
+               "d2h_bytes_per_step": int(est.d2hBytes), "seconds_per_step": dt,
+               "input": "pinned host buffer of the base stream (1 B/base + '.' per read), output: 129 db images in host memory"}
+        del host
+    del dev_chunk
+
+    # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                              "--ref-gbp", str(args.ref_gbp), "--ref-memory-gb", str(args.ref_memory_gb)],
+                             capture_output=True, text=True, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
+        try:
+            cpu = json.loads(sub.stdout.strip().splitlines()[-1]).get("cpu_baseline")
+        except Exception:
+            cpu = {"value": None, "unit": "k-mers/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + sub.stderr[-200:]}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "kmers_per_sec_end_to_end_meryl_count", "value": value, "unit": "k-mers/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "meryl count k=21 canonical, %.2f Gbp of synthetic 150 bp reads (3 Gbp uniform-random genome, both strands, 0.1%% substitutions)%s"
+                                   % (total_reads * READ_LEN / 1e9, "; " + reduced if reduced else ""),
+                       "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix,
+                       "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
+                       "l2": "inputs (%.1f GB store, %.1f GB keys per pass on rank 0) far exceed the 126 MB L2" % (stats.nBases * 0.375 / 1e9, stats.nKmers * 8 / max(1, stats.nPasses) / 1e9),
+                       "parallelism": "reads split over %d GPU(s); 64 data files sharded by owner(f)=min(f,63-f) mod N, one NCCL all-to-all per pass" % world},
+            "stage_ms": {"histogram": stats.msHistogram, "extract": stats.msExtract, "sort_hist": stats.msSortHist,
+                         "sort": stats.msSort, "count": stats.msCount, "encode": stats.msEncode},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(stats.nLaunches),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,9 @@ int mb_add_file_bytes(mb_ctx *ctx, const uint8_t *data, uint64_t len);          
  *  128 bytes (torch.distributed / MPI / files), every rank calls mb_comm_init before mb_count.  */
 int mb_comm_unique_id(uint8_t id[128]);
 int mb_comm_init(mb_ctx *ctx, const uint8_t id[128]);
+/*  Which rank owns data file `file` (0..63): min(file, 63-file) mod worldSize -- pairs the heavy low
+ *  files with the light high ones (canonical k-mers are skewed), SURVEY.md section 8e.  */
+uint32_t mb_file_owner_of(uint32_t file, uint32_t worldSize);
 
 /*  Count everything added so far.  After this the encoded db (this rank's files) is in host memory.  */
 int mb_count(mb_ctx *ctx);
@@ -163,6 +166,15 @@ int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix, uint64_t 
                         uint8_t *out, uint64_t cap, uint64_t *outLen);
 /*  P1/P2 alone (host parser): file image -> base stream in work-buffer format.  */
 int mb_dbg_parse(const uint8_t *data, uint64_t len, char *out, uint64_t cap, uint64_t *outLen);
+
+/* ---- synthetic input for the benchmark and the tests (csrc/synth.cu) --------------------------- */
+
+/*  Seeded reads from a virtual uniform-random genome: start uniform, strand 50/50,
+ *  substitution rate err.  format 0: "<bases>." per read (work-buffer form); format 1: 4-line FASTQ
+ *  "@r%012llu\n<bases>\n+\n<I...>\n".  Writes nReads * mb_synth_record_bytes() bytes of device memory.  */
+uint64_t mb_synth_record_bytes(uint32_t readLen, uint32_t format);
+int      mb_synth_reads_device(void *dOut, uint64_t firstRead, uint64_t nReads, uint32_t readLen,
+                               uint64_t genomeLen, double err, uint64_t seed, uint32_t format, void *cudaStream);
 
 #ifdef __cplusplus
 }

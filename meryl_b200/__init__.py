@@ -78,6 +78,8 @@ def lib() -> ctypes.CDLL:
         L.mb_add_file_bytes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
         L.mb_comm_unique_id.argtypes = [ctypes.c_void_p]
         L.mb_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.mb_file_owner_of.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+        L.mb_file_owner_of.restype = ctypes.c_uint32
         L.mb_count.argtypes = [ctypes.c_void_p]
         L.mb_get_image.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), u64p]
         L.mb_write_db.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
@@ -95,6 +97,10 @@ def lib() -> ctypes.CDLL:
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_uint64, u64p]
         L.mb_dbg_parse.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, u64p]
+        L.mb_synth_record_bytes.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+        L.mb_synth_record_bytes.restype = ctypes.c_uint64
+        L.mb_synth_reads_device.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                            ctypes.c_uint64, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -227,6 +233,22 @@ class Counter:
         values = np.ascontiguousarray(values, dtype=np.uint64)
         occurrences = np.ascontiguousarray(occurrences, dtype=np.uint64)
         _check(lib().mb_merge_histogram(self._h, values.ctypes.data, occurrences.ctypes.data, len(values)))
+
+
+def file_owner(file: int, world_size: int) -> int:
+    """Rank that owns data file `file` (0..63) when the db is sharded over world_size GPUs."""
+    return lib().mb_file_owner_of(file, world_size)
+
+
+def synth_record_bytes(read_len: int, fmt: int) -> int:
+    return lib().mb_synth_record_bytes(read_len, fmt)
+
+
+def synth_reads_device(dev_ptr: int, first_read: int, n_reads: int, read_len: int, genome_len: int,
+                       err: float, seed: int, fmt: int, stream: int = 0) -> None:
+    """Fill device memory with seeded synthetic reads (fmt 0: "<bases>." records, fmt 1: FASTQ)."""
+    _check(lib().mb_synth_reads_device(ctypes.c_void_p(dev_ptr), first_read, n_reads, read_len, genome_len,
+                                       err, seed, fmt, ctypes.c_void_p(stream)))
 
 
 def count(inputs, output: str, k: int, operation: str = "count", memory_gb: float | None = None,

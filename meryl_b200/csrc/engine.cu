@@ -26,6 +26,7 @@
 #include "common.h"
 #include "kernels.cuh"
 #include "engine.h"
+#include "exchange.h"
 
 namespace {
 
@@ -319,13 +320,22 @@ struct Control {                                      //  small device-side tabl
   u64 segStart [MB_MAX_BINS + 1];
   u64 segTile  [MB_MAX_BINS + 1];
   u64 fileBase [64];
+  u64 fileCount[64];                                  //  multi-GPU: this rank's k-mers per file
+  u64 allFileCount[32 * 64];                          //  multi-GPU: every rank's
   u64 numDistinct;
   u64 encTotals[4];
   u64 histTotals[3];
   u64 histBigN;
 };
 
-struct Pass { u32 binLo, binHi; u64 nKeys; };
+//  One pass = one contiguous range of prefix bins, extracted, (exchanged,) sorted, counted, encoded.
+struct Pass {
+  u32 binLo = 0, binHi = 0;
+  u64 nLocal = 0;                                     //  keys this rank extracts
+  u64 nKeys  = 0;                                     //  keys this rank sorts (== nLocal on one GPU)
+  std::vector<u64> segCount;                          //  sort segments, in memory order
+  std::vector<std::pair<u64, u64>> encRanges;         //  (first block prefix, number of blocks) to encode
+};
 
 }  //  namespace
 
@@ -333,12 +343,17 @@ struct Pass { u32 binLo, binHi; u64 nKeys; };
 static int runCount(mb_ctx *c) {
   const mb_config &cfg = c->cfg;
   const u32 k = cfg.k, wP = cfg.wPrefix, W = 8 * c->keyWords;
-  const u32 wS = 2 * k - wP;
   const u32 binBits = c->binBits, nBins = 1u << binBits;
   const u32 blockBits = wP - 6;
   const u64 blocksPerBin  = (u64)1 << (wP - binBits);
   const u64 blocksPerFile = (u64)1 << blockBits;
+  const u32 binsPerFile   = 1u << (binBits - 6);
+  const u32 world = c->comm ? mb_comm_world(c->comm) : 1;
+  const u32 me    = c->comm ? mb_comm_rank(c->comm)  : 0;
   cudaStream_t s = c->stream;
+
+  if (cfg.worldSize > 1 && !c->comm)
+    return mb_fail(MB_ESTATE, "mb_count: context has worldSize %u but mb_comm_init was not called", cfg.worldSize);
 
   MB_CUDA(cudaSetDevice(c->device));
 
@@ -379,21 +394,40 @@ static int runCount(mb_ctx *c) {
   c->st.msHistogram += tStage.ms();
   c->st.d2hBytes += nBins * sizeof(u64);
 
-  u64 nKmers = 0;
-  for (u32 b = 0; b < nBins; b++) nKmers += binCount[b];
-  c->st.nKmers = nKmers;
+  u64 nLocalKmers = 0;
+  for (u32 b = 0; b < nBins; b++) nLocalKmers += binCount[b];
 
-  const u64 histBigCap = nKmers / MB_HIST_SMALL + 1024;
+  //  multi-GPU: everybody learns everybody's per-file counts
+  std::vector<u64> C((size_t)world * 64, 0);            //  C[r][f]
+  {
+    for (u32 b = 0; b < nBins; b++) C[(size_t)me * 64 + b / binsPerFile] += binCount[b];
+    if (world > 1) {
+      MB_CUDA(cudaMemcpyAsync(dCtl->fileCount, &C[(size_t)me * 64], 64 * sizeof(u64), cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 64, s));
+      MB_CUDA(cudaMemcpyAsync(C.data(), dCtl->allFileCount, (size_t)world * 64 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+      MB_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  std::vector<u64> fileTotal(64, 0);
+  for (u32 r = 0; r < world; r++) for (u32 f = 0; f < 64; f++) fileTotal[f] += C[(size_t)r * 64 + f];
+  u64 nMine = 0;                                        //  k-mers this rank will count
+  for (u32 f = 0; f < 64; f++) {
+    c->db.owned[f] = (mb_file_owner(f, world) == me);
+    if (c->db.owned[f]) nMine += fileTotal[f];
+  }
+  c->st.nKmers = nMine;
+
+  const u64 histBigCap = nMine / MB_HIST_SMALL + 1024;
   u32 *dHistBig = (u32 *)top.take(histBigCap * sizeof(u32));
   if (!dHistBig) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
 
   //  ---- plan the passes --------------------------------------------------------------------
   const size_t R = top.left();
   const u64 nBlocksTotal = (u64)1 << wP;
-  size_t encBytes = std::max<size_t>(std::max<size_t>((size_t)512 << 20, R / 6), (size_t)nBlocksTotal * 200);
+  size_t encBytes = std::max<size_t>(std::max<size_t>((size_t)512 << 20, R / 6), (size_t)nBlocksTotal * 200 / world);
   if (encBytes > R / 2) encBytes = R / 2;
   const u32 tileKeys = mb_sort_tile_keys(c->keyWords);
-  //  per key: two key buffers + tile status; fixed: ragged tiles and tables of every bin
+  //  per key: two key buffers + tile status; fixed: ragged tiles and tables of every segment
   const double perKey = 2.0 * W + (double)MB_RADIX * 8 / tileKeys + 16.0 / tileKeys;
   const size_t fixed  = (size_t)nBins * (MB_RADIX * 8 + 16 * MB_RADIX * 8) + ((size_t)8 << 20);
   if (R < encBytes + fixed + ((size_t)64 << 20)) return mb_fail(MB_ENOMEM, "device arena too small: %zu bytes left after the read store", R);
@@ -401,59 +435,113 @@ static int runCount(mb_ctx *c) {
   capKeys = capKeys / 4096 * 4096;
 
   std::vector<Pass> passes;
-  {
-    Pass cur = { 0, 0, 0 };
+  u32 sortBits;
+  if (world == 1) {
+    //  consecutive bins, as many as fit; segments = bins, sorted on the bits below the bin
+    sortBits = 2 * k - binBits;
+    Pass cur;
     for (u32 b = 0; b < nBins; b++) {
       if (binCount[b] > capKeys)
         return mb_fail(MB_ENOMEM, "prefix bin %u holds %llu k-mers, more than the %llu that fit the device at once "
                                   "(spill-and-merge is not implemented; use more GPUs)", b, (u64)binCount[b], (u64)capKeys);
-      if (cur.nKeys + binCount[b] > capKeys) { cur.binHi = b; passes.push_back(cur); cur.binLo = b; cur.nKeys = 0; }
+      if (cur.nKeys + binCount[b] > capKeys) {
+        cur.binHi = b;  passes.push_back(cur);
+        cur = Pass();  cur.binLo = b;
+      }
       cur.nKeys += binCount[b];
+      cur.segCount.push_back(binCount[b]);
     }
     cur.binHi = nBins;
     passes.push_back(cur);
+    for (Pass &P : passes) {
+      P.nLocal = P.nKeys;
+      P.encRanges.push_back(std::make_pair((u64)P.binLo * blocksPerBin, (u64)(P.binHi - P.binLo) * blocksPerBin));
+    }
+  } else {
+    //  slot j of every rank = files [j*world, (j+1)*world); a pass takes q consecutive slots.
+    //  Every rank must fit what it sends and what it receives, in every pass: pick the largest q.
+    sortBits = 2 * k - 6;
+    const u32 slots = 64 / world;
+    u32 q = 0;
+    for (u32 tryQ = slots; tryQ >= 1 && q == 0; tryQ--) {
+      if (slots % tryQ) continue;
+      bool ok = true;
+      for (u32 p0 = 0; p0 < slots && ok; p0 += tryQ)
+        for (u32 r = 0; r < world && ok; r++) {
+          u64 snd = 0, rcv = 0;
+          for (u32 f = p0 * world; f < (p0 + tryQ) * world; f++) {
+            snd += C[(size_t)r * 64 + f];
+            if (mb_file_owner(f, world) == r) rcv += fileTotal[f];
+          }
+          if (snd > capKeys || rcv > capKeys) ok = false;
+        }
+      if (ok) q = tryQ;
+    }
+    if (q == 0)
+      return mb_fail(MB_ENOMEM, "a single data file's k-mers do not fit one of the %u devices (capacity %llu keys); use more GPUs", world, (u64)capKeys);
+    for (u32 p0 = 0; p0 < slots; p0 += q) {
+      Pass P;
+      const u32 fLo = p0 * world, fHi = (p0 + q) * world;
+      P.binLo = fLo * binsPerFile;  P.binHi = fHi * binsPerFile;
+      for (u32 f = fLo; f < fHi; f++) {
+        P.nLocal += C[(size_t)me * 64 + f];
+        if (c->db.owned[f]) {
+          P.nKeys += fileTotal[f];
+          P.segCount.push_back(fileTotal[f]);
+          P.encRanges.push_back(std::make_pair((u64)f * blocksPerFile, blocksPerFile));
+        }
+      }
+      passes.push_back(P);
+    }
   }
   c->st.nPasses = (u32)passes.size();
 
   MbSortPlan plan;
-  mb_sort_plan(2 * k - binBits, &plan);
+  mb_sort_plan(sortBits, &plan);
   c->st.sortPasses = plan.nPasses;
 
   //  host images
   for (u32 f = 0; f < 64; f++) { c->db.data[f].clear(); c->db.index[f].clear(); }
   std::vector<u64> fileBase(64, 0);
 
-  std::vector<u64> segStart(MB_MAX_BINS + 1), segTile(MB_MAX_BINS + 1), binStart(MB_MAX_BINS + 1);
+  std::vector<u64> segStart, segTile, binStart(MB_MAX_BINS + 1);
   EventTimer tSortHist;  tSortHist.init();
   cudaEvent_t evAfterHist;  MB_CUDA(cudaEventCreate(&evAfterHist));
 
   for (size_t pi = 0; pi < passes.size(); pi++) {
     const Pass &P = passes[pi];
-    const u32 nSegs = P.binHi - P.binLo;
+    const u32 nSegs = (u32)P.segCount.size();
     const u64 n = P.nKeys;
+    const u64 bufKeys = std::max(P.nLocal, P.nKeys);
 
     //  ---- carve this pass ------------------------------------------------------------------
     Carver pc((uint8_t *)top.base + alignUp(top.off), top.left());
-    void *bufA = pc.take((size_t)W * n + 64);
-    void *bufB = pc.take((size_t)W * n + 64);
-    u64 nTiles = 0;
+    void *bufA = pc.take((size_t)W * bufKeys + 64);
+    void *bufB = pc.take((size_t)W * bufKeys + 64);
+
+    //  extraction layout: every bin of the pass is a contiguous run, bins ascending
     std::fill(binStart.begin(), binStart.end(), 0);
     {
       u64 at = 0;
       for (u32 b = 0; b < nBins; b++) {
         binStart[b] = at;
-        if (b >= P.binLo && b < P.binHi) {
-          segStart[b - P.binLo] = at;
-          segTile [b - P.binLo] = nTiles;
-          at     += binCount[b];
-          nTiles += (binCount[b] + tileKeys - 1) / tileKeys;
-        }
+        if (b >= P.binLo && b < P.binHi) at += binCount[b];
       }
       binStart[nBins] = at;
-      segStart[nSegs] = at;
-      segTile [nSegs] = nTiles;
     }
-    const size_t sortWs = std::max(mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses), mb_count_workspace_bytes(n));
+    //  sort layout
+    segStart.assign(nSegs + 1, 0);  segTile.assign(nSegs + 1, 0);
+    u64 nTiles = 0;
+    {
+      u64 at = 0;
+      for (u32 i = 0; i < nSegs; i++) {
+        segStart[i] = at;  segTile[i] = nTiles;
+        at += P.segCount[i];
+        nTiles += (P.segCount[i] + tileKeys - 1) / tileKeys;
+      }
+      segStart[nSegs] = at;  segTile[nSegs] = nTiles;
+    }
+    const size_t sortWs = std::max(mb_sort_workspace_bytes(nTiles, nSegs ? nSegs : 1, plan.nPasses), mb_count_workspace_bytes(n));
     void *ws = pc.take(sortWs);
     if (!bufA || !bufB || !ws) return mb_fail(MB_ENOMEM, "internal: pass %zu does not fit the arena", pi);
 
@@ -469,26 +557,37 @@ static int runCount(mb_ctx *c) {
     //  ---- K2/K3 ------------------------------------------------------------------------------
     xp.binLo = P.binLo;  xp.binHi = P.binHi;
     tStage.start(s);
-    if (n) { MB_CUDA(mb_launch_extract(xp, bufA, dCtl->binStart, dCtl->binCursor, s)); c->st.nLaunches++; }
+    if (P.nLocal) { MB_CUDA(mb_launch_extract(xp, bufA, dCtl->binStart, dCtl->binCursor, s)); c->st.nLaunches++; }
     tStage.stop(s);
     MB_CUDA(cudaStreamSynchronize(s));
     c->st.msExtract += tStage.ms();
 
-    //  ---- multi-GPU: route k-mers to their owners (exchange.cu) -------------------------------
-    //  (single GPU: nothing)
+    //  ---- multi-GPU: route k-mers to the owners of their files ----------------------------------
+    void *unsorted = bufA, *spare = bufB;
+    if (world > 1) {
+      const u32 fLo = P.binLo / binsPerFile, fHi = P.binHi / binsPerFile;
+      std::vector<u64> sendStart(fHi - fLo);
+      for (u32 f = fLo; f < fHi; f++) sendStart[f - fLo] = binStart[f * binsPerFile];
+      tStage.start(s);
+      MB_TRY(mb_comm_exchange_keys(c->comm, c->keyWords, bufA, bufB, fLo, fHi, sendStart.data(), C.data(), s));
+      tStage.stop(s);
+      MB_CUDA(cudaStreamSynchronize(s));
+      c->st.msExchange += tStage.ms();
+      unsorted = bufB;  spare = bufA;
+    }
 
     //  ---- K4 ---------------------------------------------------------------------------------
-    int inB = 0;  u32 nl = 0;
+    int inSpare = 0;  u32 nl = 0;
     tSortHist.start(s);
-    MB_CUDA(mb_launch_sort(c->keyWords, bufA, bufB, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inB, &nl, s, evAfterHist));
-    tStage.stop(s);                                   //  reuse: [evAfterHist, tStage.b] = sweep passes
+    MB_CUDA(mb_launch_sort(c->keyWords, unsorted, spare, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inSpare, &nl, s, evAfterHist));
+    tStage.stop(s);                                   //  [evAfterHist, tStage.b] = the sweep passes
     MB_CUDA(cudaStreamSynchronize(s));
     { float m = 0;  cudaEventElapsedTime(&m, tSortHist.a, evAfterHist);  c->st.msSortHist += m;
       m = 0;        cudaEventElapsedTime(&m, evAfterHist, tStage.b);     c->st.msSort     += m; }
     c->st.nLaunches += nl;
     if (n) c->st.sortLaunchKeys += n * plan.nPasses;
-    void *sorted = inB ? bufB : bufA;
-    void *other  = inB ? bufA : bufB;
+    void *sorted = inSpare ? spare : unsorted;
+    void *other  = inSpare ? unsorted : spare;
 
     if (c->stopAfterSort) {                           //  debug: hand back the sorted instances
       const size_t at = c->sortedLo.size();
@@ -537,88 +636,91 @@ static int runCount(mb_ctx *c) {
       }
     }
 
-    //  ---- K6 ---------------------------------------------------------------------------------
-    MbEncodeParams ep;
-    ep.keys = sorted;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = c->keyWords;
-    ep.k = k;  ep.wPrefix = wP;
-    ep.blockLo = (u64)P.binLo * blocksPerBin;
-    ep.nBlocks = (u64)nSegs * blocksPerBin;
-
-    MbBlockMeta *dMeta = (MbBlockMeta *)ec.take(ep.nBlocks * sizeof(MbBlockMeta));
-    void *dScanTmp     = ec.take(mb_encode_scan_tmp_bytes(ep.nBlocks));
-    if (!dMeta || !dScanTmp) return mb_fail(MB_ENOMEM, "device arena too small for the block table of pass %zu (%llu blocks)", pi, (u64)ep.nBlocks);
-
+    //  ---- K6: every block range of the pass ------------------------------------------------------
     tStage.start(s);
-    MB_CUDA(mb_launch_encode_layout(ep, dMeta, dCtl->encTotals, dScanTmp, s));
-    c->st.nLaunches += 4;
+    for (size_t ri = 0; ri < P.encRanges.size(); ri++) {
+      MbEncodeParams ep;
+      ep.keys = sorted;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = c->keyWords;
+      ep.k = k;  ep.wPrefix = wP;
+      ep.blockLo = P.encRanges[ri].first;
+      ep.nBlocks = P.encRanges[ri].second;
 
-    //  chunk boundaries: first block of every file touched by this pass
-    const u32 fileLo = (u32)(ep.blockLo >> blockBits), fileHi = (u32)((ep.blockLo + ep.nBlocks - 1) >> blockBits);
-    const u32 nf = fileHi - fileLo + 1;
-    std::vector<MbBlockMeta> fm(nf + 1);
-    std::vector<u64> fblk(nf + 1);
-    for (u32 i = 0; i < nf; i++) {
-      const u64 fb = (u64)(fileLo + i) << blockBits;
-      fblk[i] = fb > ep.blockLo ? fb - ep.blockLo : 0;
-    }
-    fblk[nf] = ep.nBlocks;
-    for (u32 i = 0; i < nf; i++)
-      MB_CUDA(cudaMemcpyAsync(&fm[i], dMeta + fblk[i], sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
-    u64 encTotals[4];
-    MB_CUDA(cudaMemcpyAsync(encTotals, dCtl->encTotals, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
-    MB_CUDA(cudaStreamSynchronize(s));
-    fm[nf].outByte = encTotals[0];  fm[nf].subFirst = (u32)encTotals[1];
-    c->st.d2hBytes += nf * sizeof(MbBlockMeta) + sizeof(encTotals);
+      Carver rc((uint8_t *)ec.base + alignUp(ec.off), ec.left());
+      MbBlockMeta *dMeta = (MbBlockMeta *)rc.take(ep.nBlocks * sizeof(MbBlockMeta));
+      void *dScanTmp     = rc.take(mb_encode_scan_tmp_bytes(ep.nBlocks));
+      if (!dMeta || !dScanTmp) return mb_fail(MB_ENOMEM, "device arena too small for the block table of pass %zu (%llu blocks)", pi, (u64)ep.nBlocks);
 
-    //  greedy groups of whole files that fit what is left of the arena
-    size_t encLeft = ec.left();
-    u32 fi = 0;
-    while (fi < nf) {
-      u32 fj = fi;
-      while (fj < nf) {
-        const size_t bytes = fm[fj + 1].outByte - fm[fi].outByte;
-        const size_t subs  = (size_t)(fm[fj + 1].subFirst - fm[fi].subFirst);
-        const size_t idx   = (size_t)(fblk[fj + 1] - fblk[fi]) * 24;
-        const size_t tot   = alignUp(bytes) + alignUp(subs * 4) + alignUp(idx) + 3 * kAlign;
-        if (tot > encLeft) break;
-        fj++;
+      MB_CUDA(mb_launch_encode_layout(ep, dMeta, dCtl->encTotals, dScanTmp, s));
+      c->st.nLaunches += 4;
+
+      //  chunk boundaries: first block of every file touched by this range
+      const u32 fileLo = (u32)(ep.blockLo >> blockBits), fileHi = (u32)((ep.blockLo + ep.nBlocks - 1) >> blockBits);
+      const u32 nf = fileHi - fileLo + 1;
+      std::vector<MbBlockMeta> fm(nf + 1);
+      std::vector<u64> fblk(nf + 1);
+      for (u32 i = 0; i < nf; i++) {
+        const u64 fb = (u64)(fileLo + i) << blockBits;
+        fblk[i] = fb > ep.blockLo ? fb - ep.blockLo : 0;
       }
-      if (fj == fi)
-        return mb_fail(MB_ENOMEM, "encoded data file %u of pass %zu (%llu bytes) does not fit the %zu bytes left on the device",
-                       fileLo + fi, pi, (u64)(fm[fi + 1].outByte - fm[fi].outByte), encLeft);
-
-      MbEncodeChunk ch;
-      ch.chunkFirst = fblk[fi];  ch.chunkCount = fblk[fj] - fblk[fi];
-      ch.chunkByte0 = fm[fi].outByte;  ch.chunkSub0 = fm[fi].subFirst;
-      const size_t bytes = fm[fj].outByte - fm[fi].outByte;
-      const size_t subs  = (size_t)(fm[fj].subFirst - fm[fi].subFirst);
-
-      Carver cc((uint8_t *)ec.base + alignUp(ec.off), ec.left());
-      uint8_t *dOut  = (uint8_t *)cc.take(bytes);
-      u32     *dSub  = (u32 *)cc.take(subs * 4);
-      u64     *dIdx  = (u64 *)cc.take(ch.chunkCount * 24);
-      if (!dOut || !dSub || !dIdx) return mb_fail(MB_ENOMEM, "internal: encode chunk does not fit");
-
-      MB_CUDA(cudaMemsetAsync(dOut, 0, bytes, s));
-      MB_CUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl->encTotals, dSub, dOut, dIdx, dCtl->fileBase, s));
-      c->st.nLaunches += D ? 2 : 1;
-
-      if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
-        for (u32 f = fi; f < fj; f++) {
-          const u32 file = fileLo + f;
-          const size_t fb = fm[f + 1].outByte - fm[f].outByte;
-          const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
-          std::vector<uint8_t> &dv = c->db.data[file], &iv = c->db.index[file];
-          const size_t d0 = dv.size(), i0 = iv.size();
-          dv.resize(d0 + fb);  iv.resize(i0 + ib);
-          MB_CUDA(cudaMemcpyAsync(dv.data() + d0, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
-          MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
-          c->st.d2hBytes += fb + ib;
-        }
-      }
+      fblk[nf] = ep.nBlocks;
+      for (u32 i = 0; i < nf; i++)
+        MB_CUDA(cudaMemcpyAsync(&fm[i], dMeta + fblk[i], sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
+      u64 encTotals[4];
+      MB_CUDA(cudaMemcpyAsync(encTotals, dCtl->encTotals, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
       MB_CUDA(cudaStreamSynchronize(s));
-      for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
-      fi = fj;
+      fm[nf].outByte = encTotals[0];  fm[nf].subFirst = (u32)encTotals[1];
+      c->st.d2hBytes += nf * sizeof(MbBlockMeta) + sizeof(encTotals);
+
+      //  greedy groups of whole files that fit what is left of the arena
+      const size_t encLeft = rc.left();
+      u32 fi = 0;
+      while (fi < nf) {
+        u32 fj = fi;
+        while (fj < nf) {
+          const size_t bytes = fm[fj + 1].outByte - fm[fi].outByte;
+          const size_t subs  = (size_t)(fm[fj + 1].subFirst - fm[fi].subFirst);
+          const size_t idx   = (size_t)(fblk[fj + 1] - fblk[fi]) * 24;
+          const size_t tot   = alignUp(bytes) + alignUp(subs * 4) + alignUp(idx) + 3 * kAlign;
+          if (tot > encLeft) break;
+          fj++;
+        }
+        if (fj == fi)
+          return mb_fail(MB_ENOMEM, "encoded data file %u of pass %zu (%llu bytes) does not fit the %zu bytes left on the device",
+                         fileLo + fi, pi, (u64)(fm[fi + 1].outByte - fm[fi].outByte), encLeft);
+
+        MbEncodeChunk ch;
+        ch.chunkFirst = fblk[fi];  ch.chunkCount = fblk[fj] - fblk[fi];
+        ch.chunkByte0 = fm[fi].outByte;  ch.chunkSub0 = fm[fi].subFirst;
+        const size_t bytes = fm[fj].outByte - fm[fi].outByte;
+        const size_t subs  = (size_t)(fm[fj].subFirst - fm[fi].subFirst);
+
+        Carver cc((uint8_t *)rc.base + alignUp(rc.off), rc.left());
+        uint8_t *dOut  = (uint8_t *)cc.take(bytes);
+        u32     *dSub  = (u32 *)cc.take(subs * 4);
+        u64     *dIdx  = (u64 *)cc.take(ch.chunkCount * 24);
+        if (!dOut || !dSub || !dIdx) return mb_fail(MB_ENOMEM, "internal: encode chunk does not fit");
+
+        MB_CUDA(cudaMemsetAsync(dOut, 0, bytes, s));
+        MB_CUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl->encTotals, dSub, dOut, dIdx, dCtl->fileBase, s));
+        c->st.nLaunches += D ? 2 : 1;
+
+        if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
+          for (u32 f = fi; f < fj; f++) {
+            const u32 file = fileLo + f;
+            const size_t fb = fm[f + 1].outByte - fm[f].outByte;
+            const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
+            std::vector<uint8_t> &dv = c->db.data[file], &iv = c->db.index[file];
+            const size_t d0 = dv.size(), i0 = iv.size();
+            dv.resize(d0 + fb);  iv.resize(i0 + ib);
+            MB_CUDA(cudaMemcpyAsync(dv.data() + d0, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
+            MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
+            c->st.d2hBytes += fb + ib;
+          }
+        }
+        MB_CUDA(cudaStreamSynchronize(s));
+        for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
+        fi = fj;
+      }
     }
     tStage.stop(s);
     MB_CUDA(cudaStreamSynchronize(s));
@@ -649,15 +751,52 @@ static int runCount(mb_ctx *c) {
     c->hist.nUnique = totals[0];  c->hist.nDistinct = totals[1];  c->hist.nTotal = totals[2];
     c->st.nUnique = totals[0];  c->st.nDistinct = totals[1];  c->st.nTotal = totals[2];
 
+    //  multi-GPU: rank 0 collects the other ranks' histograms for the master index
+    if (world > 1) {
+      const u64 myWords = 2 * (u64)c->hist.values.size();
+      std::vector<u64> cnt(world, 0);
+      Carver hc((uint8_t *)top.base + alignUp(top.off), top.left());
+      u64 *dCnt = (u64 *)hc.take(8 * (size_t)(world + 1));
+      if (!dCnt) return mb_fail(MB_ENOMEM, "internal: no room for the histogram exchange");
+      MB_CUDA(cudaMemcpyAsync(dCnt, &myWords, 8, cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCnt, dCnt + 1, 1, s));
+      MB_CUDA(cudaMemcpyAsync(cnt.data(), dCnt + 1, 8 * (size_t)world, cudaMemcpyDeviceToHost, s));
+      MB_CUDA(cudaStreamSynchronize(s));
+      u64 others = 0;
+      for (u32 r = 1; r < world; r++) others += cnt[r];
+      std::vector<u64> mine(myWords);
+      for (size_t i = 0; i < c->hist.values.size(); i++) { mine[2 * i] = c->hist.values[i]; mine[2 * i + 1] = c->hist.occ[i]; }
+      u64 *dSend = (u64 *)hc.take(8 * (size_t)(myWords + 1));
+      u64 *dRecv = (u64 *)hc.take(8 * (size_t)(others + 1));
+      if (!dSend || !dRecv) return mb_fail(MB_ENOMEM, "internal: no room for the histogram exchange");
+      if (myWords) MB_CUDA(cudaMemcpyAsync(dSend, mine.data(), 8 * (size_t)myWords, cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_gather_u64(c->comm, dSend, myWords, dRecv, cnt.data(), s));
+      MB_CUDA(cudaStreamSynchronize(s));
+      if (me == 0 && others) {
+        std::vector<u64> got(others);
+        MB_CUDA(cudaMemcpy(got.data(), dRecv, 8 * (size_t)others, cudaMemcpyDeviceToHost));
+        std::map<u64, u64> m;
+        for (size_t i = 0; i < c->hist.values.size(); i++) m[c->hist.values[i]] += c->hist.occ[i];
+        for (u64 i = 0; i < others; i += 2) {
+          m[got[i]] += got[i + 1];
+          if (got[i] == 1) c->hist.nUnique += got[i + 1];
+          c->hist.nDistinct += got[i + 1];
+          c->hist.nTotal    += got[i] * got[i + 1];
+        }
+        c->hist.values.clear();  c->hist.occ.clear();
+        for (auto &kv : m) { c->hist.values.push_back(kv.first); c->hist.occ.push_back(kv.second); }
+      }
+    }
+
     mb_build_master_index(k, wP, c->hist, c->db.master);
-    c->st.dbBytes = c->db.master.size();
+    c->st.dbBytes = (me == 0) ? c->db.master.size() : 0;
     for (u32 f = 0; f < 64; f++) c->st.dbBytes += c->db.data[f].size() + c->db.index[f].size();
   }
 
   tAll.stop(s);
   c->st.msTotal = tAll.ms();
   tAll.destroy();  tStage.destroy();
-  (void)wS;  (void)blocksPerFile;
+  (void)nLocalKmers;
   c->counted = true;
   return MB_OK;
 }

@@ -1,20 +1,171 @@
-//  Multi-GPU routing of extracted k-mers to the GPU that owns their data file (NCCL all-to-all).
-//  Placeholder until the single-GPU path is parity-green on hardware; see DESIGN.md (e).
+//  Multi-GPU: routing extracted k-mers to the GPU that owns their data file.
+//
+//  The reference has no distributed mode; the shard unit is its own output partition: the 64 data
+//  files (top 6 bits of the k-mer, `merylFileWriter::fileNumber`,
+//  src/utility/src/kmers-v1/kmers-writer.C:157-178).  Every file's blocks, index and bytes depend only
+//  on the k-mers with that prefix, so after ONE all-to-all of packed k-mers per pass each GPU sorts,
+//  counts and encodes its own files with no further communication.
+//
+//  Ownership: canonical k-mers are linearly skewed across files (file 0 holds ~2x the mean, file 63
+//  almost nothing), so file f is paired with 63-f and pairs are dealt round-robin:
+//      owner(f) = min(f, 63-f) mod worldSize.
+//  With that map the j-th owned file of every rank together form the contiguous file range
+//  [j*world, (j+1)*world), so a pass over "slots [a,b) of every rank" is a contiguous prefix range
+//  for the extraction kernel.
+//
+//  NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded when the
+//  caller is bench.py), so the library has no link-time dependency on it; the communicator is
+//  bootstrapped from a 128-byte unique id that the caller broadcasts with whatever it has
+//  (torch.distributed in bench.py).  One process per GPU.
+
+#include <dlfcn.h>
+#include <string.h>
+
 #include "common.h"
 #include "engine.h"
+#include "exchange.h"
 
-struct MbComm { int unused; };
+namespace {
 
-void mb_comm_destroy(MbComm *m) { delete m; }
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_p;
+enum { kNcclUint8 = 1, kNcclUint64 = 5 };                 //  ncclDataType_t values (nccl.h)
+
+struct NcclApi {
+  void *handle = nullptr;
+  int  (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  int  (*CommInitRank)(ncclComm_p *, int, ncclUniqueId_t, int) = nullptr;
+  int  (*CommDestroy)(ncclComm_p) = nullptr;
+  int  (*GroupStart)(void) = nullptr;
+  int  (*GroupEnd)(void) = nullptr;
+  int  (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int  (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int  (*AllGather)(const void *, void *, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+
+NcclApi g_nccl;
+
+int loadNccl(void) {
+  if (g_nccl.handle) return MB_OK;
+  const char *names[] = { "libnccl.so.2", "libnccl.so", nullptr };
+  void *h = nullptr;
+  for (int i = 0; names[i] && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return mb_fail(MB_ECOMM, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name) do { *(void **)&g_nccl.field = dlsym(h, name); if (!g_nccl.field) return mb_fail(MB_ECOMM, "libnccl lacks %s", name); } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId");    SYM(CommInitRank, "ncclCommInitRank");   SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GroupStart, "ncclGroupStart");      SYM(GroupEnd, "ncclGroupEnd");
+  SYM(Send, "ncclSend");                  SYM(Recv, "ncclRecv");                   SYM(AllGather, "ncclAllGather");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.handle = h;
+  return MB_OK;
+}
+
+#define MB_NCCL(call) do { int r_ = (call); if (r_ != 0) return mb_fail(MB_ECOMM, "%s:%d: %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); } while (0)
+
+}  //  namespace
+
+
+struct MbComm {
+  ncclComm_p comm = nullptr;
+  u32 rank = 0, world = 1;
+};
+
+void mb_comm_destroy(MbComm *m) {
+  if (!m) return;
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  delete m;
+}
+
+u32 mb_comm_rank(const MbComm *m)  { return m ? m->rank : 0; }
+u32 mb_comm_world(const MbComm *m) { return m ? m->world : 1; }
+
+u32 mb_file_owner(u32 file, u32 world) {
+  const u32 p = file < 63 - file ? file : 63 - file;
+  return p % world;
+}
+
+extern "C" uint32_t mb_file_owner_of(uint32_t file, uint32_t worldSize) {
+  return worldSize ? mb_file_owner(file & 63, worldSize) : 0;
+}
 
 extern "C" int mb_comm_unique_id(uint8_t id[128]) {
   mb_clear_error();
-  (void)id;
-  return mb_fail(MB_ECOMM, "multi-GPU exchange is not built yet");
+  if (!id) return mb_fail(MB_EINVAL, "mb_comm_unique_id: NULL argument");
+  MB_TRY(loadNccl());
+  ncclUniqueId_t u;
+  MB_NCCL(g_nccl.GetUniqueId(&u));
+  memcpy(id, u.internal, 128);
+  return MB_OK;
 }
 
 extern "C" int mb_comm_init(mb_ctx *ctx, const uint8_t id[128]) {
   mb_clear_error();
-  (void)ctx; (void)id;
-  return mb_fail(MB_ECOMM, "multi-GPU exchange is not built yet");
+  if (!ctx || !id) return mb_fail(MB_EINVAL, "mb_comm_init: NULL argument");
+  const mb_config &cfg = mb_ctx_config(ctx);
+  if (cfg.worldSize < 2) return mb_fail(MB_EINVAL, "mb_comm_init: context was created with worldSize %u", cfg.worldSize);
+  if (64 % cfg.worldSize != 0 || cfg.worldSize > 32) return mb_fail(MB_EINVAL, "mb_comm_init: worldSize %u must divide 64 and be <= 32", cfg.worldSize);
+  if (cfg.rank >= cfg.worldSize) return mb_fail(MB_EINVAL, "mb_comm_init: rank %u >= worldSize %u", cfg.rank, cfg.worldSize);
+  MB_TRY(loadNccl());
+  MB_CUDA(cudaSetDevice(mb_ctx_device(ctx)));
+  ncclUniqueId_t u;
+  memcpy(u.internal, id, 128);
+  MbComm *m = new MbComm();
+  m->rank = cfg.rank;  m->world = cfg.worldSize;
+  const int r = g_nccl.CommInitRank(&m->comm, (int)cfg.worldSize, u, (int)cfg.rank);
+  if (r != 0) { delete m; return mb_fail(MB_ECOMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+  mb_ctx_set_comm(ctx, m);
+  return MB_OK;
+}
+
+//  All-gather `n` u64 per rank (device pointers; dAll holds world*n).
+int mb_comm_allgather_u64(MbComm *m, const u64 *dMine, u64 *dAll, size_t n, cudaStream_t s) {
+  MB_NCCL(g_nccl.AllGather(dMine, dAll, n, kNcclUint64, m->comm, s));
+  return MB_OK;
+}
+
+//  The per-pass all-to-all.  `files` are the contiguous files [fileLo, fileHi) of this pass.
+//  sendBuf holds this rank's extracted keys grouped by file (sendStart[f - fileLo] in keys, counts
+//  C[me][f]); file f goes to owner(f).  recvBuf receives, for every file this rank owns (ascending),
+//  the chunks of ranks 0..world-1 back to back, so each owned file ends up as one contiguous segment.
+//  C is the [world][64] matrix of per-rank file counts (host).  keyWords u64 per key.
+int mb_comm_exchange_keys(MbComm *m, u32 keyWords, const void *sendBuf, void *recvBuf,
+                          u32 fileLo, u32 fileHi, const u64 *sendStart, const u64 *C, cudaStream_t s) {
+  const u32 me = m->rank, world = m->world;
+  const u64 *sb = (const u64 *)sendBuf;
+  u64       *rb = (u64 *)recvBuf;
+  MB_NCCL(g_nccl.GroupStart());
+  u64 recvAt = 0;
+  for (u32 f = fileLo; f < fileHi; f++) {
+    const u32 own = mb_file_owner(f, world);
+    const u64 mine = C[(size_t)me * 64 + f];
+    if (mine) MB_NCCL(g_nccl.Send(sb + sendStart[f - fileLo] * keyWords, mine * keyWords, kNcclUint64, (int)own, m->comm, s));
+    if (own == me) {
+      for (u32 src = 0; src < world; src++) {
+        const u64 c = C[(size_t)src * 64 + f];
+        if (c) MB_NCCL(g_nccl.Recv(rb + recvAt * keyWords, c * keyWords, kNcclUint64, (int)src, m->comm, s));
+        recvAt += c;
+      }
+    }
+  }
+  MB_NCCL(g_nccl.GroupEnd());
+  return MB_OK;
+}
+
+//  Gather variable-length u64 arrays on rank 0 (device staging provided by the caller):
+//  every rank sends `n` words from dSend; rank 0 receives rank r's words at dRecv + offsets[r].
+int mb_comm_gather_u64(MbComm *m, const u64 *dSend, u64 n, u64 *dRecv, const u64 *counts, cudaStream_t s) {
+  MB_NCCL(g_nccl.GroupStart());
+  if (m->rank != 0) {
+    if (n) MB_NCCL(g_nccl.Send(dSend, n, kNcclUint64, 0, m->comm, s));
+  } else {
+    u64 at = 0;
+    for (u32 r = 1; r < m->world; r++) {
+      if (counts[r]) MB_NCCL(g_nccl.Recv(dRecv + at, counts[r], kNcclUint64, (int)r, m->comm, s));
+      at += counts[r];
+    }
+  }
+  MB_NCCL(g_nccl.GroupEnd());
+  return MB_OK;
 }
