@@ -130,7 +130,7 @@ def reference_arm(args, world, rank):
         "impl": "reference", "metric": "kmers_per_sec_end_to_end_meryl_count", "value": val, "unit": "k-mers/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "meryl count k=21, synthetic 150 bp FASTQ (3 Gbp random genome, 0.1% subst.), reference CPU binary on a %.2f Gbp prefix" % args.ref_gbp,
+        "config": {"workload": "meryl count k=21, synthetic 150 bp FASTQ (3 Gbp random genome, 0.1%% subst.), reference CPU binary on a %.2f Gbp prefix" % args.ref_gbp,
                    "k": K, "read_len": READ_LEN, "sample_gbp": args.ref_gbp},
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": cores, "kind": "reference",
                          "sample": "first %d reads (%.2f Gbp) of the workload as a FASTQ file in /dev/shm, threads=%d memory=%d" % (n_reads, args.ref_gbp, cores, args.ref_memory_gb)},

@@ -209,12 +209,38 @@ static int parserSink(void *arg, const char *bases, size_t n) {
   return appendHost(c, bases, n);
 }
 
+//  Large buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+//  skip the staging memcpy: the DMA engine reads them in place, 64 MB at a time.
+static int appendPinnedDirect(mb_ctx *c, const char *&p, uint64_t &n) {
+  if (n < 4 * kStageBytes || c->inRecord) return MB_OK;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return MB_OK; }
+  if (at.type != cudaMemoryTypeHost) return MB_OK;
+  MB_TRY(flushStage(c));                                 //  stream is at a record boundary: padding is harmless
+  MB_CUDA(cudaSetDevice(c->device));
+  int i = 0;
+  while (n >= kStageBytes) {
+    const u64 recs = kStageBytes / 32;
+    MB_TRY(storeReserve(c, recs));
+    MB_CUDA(cudaMemcpyAsync(c->dStage[i], p, kStageBytes, cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(mb_launch_pack(c->dStage[i], kStageBytes, (u32 *)c->arena, c->nRecords, c->stream));
+    c->st.nLaunches++;
+    c->st.h2dBytes += kStageBytes;
+    c->nRecords    += recs;
+    p += kStageBytes;  n -= kStageBytes;  i ^= 1;
+  }
+  MB_CUDA(cudaStreamSynchronize(c->stream));             //  the caller may touch its buffer when we return
+  c->inRecord = (p[-1] != '.');
+  return MB_OK;
+}
+
 extern "C" int mb_add_bases(mb_ctx *c, const char *bases, uint64_t len, int endOfSequence) {
   mb_clear_error();
   if (!c || (!bases && len))  return mb_fail(MB_EINVAL, "mb_add_bases: NULL argument");
   if (c->counted)             return mb_fail(MB_ESTATE, "mb_add_bases: already counted");
+  MB_TRY(appendPinnedDirect(c, bases, len));
   MB_TRY(appendHost(c, bases, len));
-  if (len) c->inRecord = true;
+  if (len) c->inRecord = (bases[len - 1] != '.');
   if (endOfSequence) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
   return MB_OK;
 }

@@ -28,11 +28,11 @@ template <int KW> struct SortShape;
 template <> struct SortShape<1> { static const int ITEMS = 16; };
 template <> struct SortShape<2> { static const int ITEMS = 8;  };
 
-//  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:58] epoch (pass tag, 1..15)  [57:0] value
+//  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:57] epoch (pass tag, 1..16)  [56:0] value
 #define ST_FLAG(v)    ((u32)((v) >> 62))
-#define ST_EPOCH(v)   ((u32)(((v) >> 58) & 15))
-#define ST_VALUE(v)   ((v) & ((1ull << 58) - 1))
-#define ST_MAKE(f, e, x)  (((u64)(f) << 62) | ((u64)(e) << 58) | (u64)(x))
+#define ST_EPOCH(v)   ((u32)(((v) >> 57) & 31))
+#define ST_VALUE(v)   ((v) & ((1ull << 57) - 1))
+#define ST_MAKE(f, e, x)  (((u64)(f) << 62) | ((u64)(e) << 57) | (u64)(x))
 
 //  Largest s with tileStart[s] <= tile  (tileStart has nSegs+1 entries, non-decreasing).
 __device__ __forceinline__ u32 find_segment(const u64 *__restrict__ tileStart, u32 nSegs, u64 tile) {
