@@ -16,8 +16,10 @@
 //    1. validity of all 32 windows at once by log-step erosion of the validity bits;
 //    2. cheap pre-filter: the prefix bin of the canonical k-mer is min(top bits of f, top bits of
 //       r) and needs only the first and last binBits/2 bases -> keep-mask of this pass's bins;
-//    3. full k-mer only for kept positions, rank within (tile, bin) by a shared-memory atomic;
-//    4. one global atomic per (tile, bin) reserves the run in the bin's segment, keys are stored.
+//    3. kept positions take their rank within (tile, bin) by a shared-memory atomic; one global
+//       atomic per (tile, bin) reserves the run in the bin's segment;
+//    4. the full k-mer is computed only for kept positions and stored straight from registers
+//       (nothing is staged in shared memory: ~35 KB per CTA, 6 CTAs per SM).
 //  The same kernel in COUNT_ONLY form is the histogram pre-pass (K2a) that sizes the segments.
 //
 //  Work: integer/bit ops, ~16 per position for the pre-filter + ~40 per kept k-mer; HBM traffic
@@ -107,8 +109,7 @@ struct ExtractSmem {
   static const size_t OFF_REC1  = OFF_REC0 + ((REC_BYTES + 127) / 128) * 128;
   static const size_t OFF_CNT   = OFF_REC1 + ((REC_BYTES + 127) / 128) * 128;
   static const size_t OFF_GBASE = OFF_CNT + MB_MAX_BINS * sizeof(u32);
-  static const size_t OFF_STASH = OFF_GBASE + MB_MAX_BINS * sizeof(u64);
-  static const size_t OFF_RANK  = OFF_STASH + (size_t)TILE_POS * sizeof(typename KeyT<KW>::type);
+  static const size_t OFF_RANK  = OFF_GBASE + MB_MAX_BINS * sizeof(u64);
   static const size_t SCATTER_BYTES = OFF_RANK + (size_t)TILE_POS * sizeof(unsigned short);
   static const size_t COUNT_BYTES   = OFF_GBASE;
 };
@@ -166,7 +167,6 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
   u32            *rec[2] = { (u32 *)(smem + S::OFF_REC0), (u32 *)(smem + S::OFF_REC1) };
   u32            *cnt   = (u32 *)(smem + S::OFF_CNT);
   u64            *gbase = (u64 *)(smem + S::OFF_GBASE);
-  Key            *stash = (Key *)(smem + S::OFF_STASH);
   unsigned short *rank  = (unsigned short *)(smem + S::OFF_RANK);
 
   const u32 t = threadIdx.x;
@@ -208,7 +208,8 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
     //  Positions at or beyond the end of the store never start a k-mer (their records are zero),
     //  so no bound check is needed here.
 
-    //  Pre-filter: which of my valid windows fall into this pass's bins?
+    //  Pre-filter: which of my valid windows fall into this pass's bins?  The bin needs only the
+    //  first and last binBits/2 bases; kept positions take their rank inside (tile, bin) right away.
     u32 keep = 0;
     for (u32 v = valid; v; ) {
       const u32 q   = __clz(v);                       //  position 0 is bit 31
@@ -218,18 +219,11 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
         atomicAdd(&cnt[bin], 1u);
       } else if (bin >= p.binLo && bin < p.binHi) {
         keep |= 0x80000000u >> q;
+        rank[t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin], 1u);
       }
     }
 
     if (!COUNT_ONLY) {
-      for (u32 v = keep; v; ) {
-        const u32 q = __clz(v);
-        v &= ~(0x80000000u >> q);
-        const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
-        const u32 bin = key_field(key, 2 * p.k - p.binBits, p.binBits);
-        stash[t * 32 + q] = key;
-        rank [t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin], 1u);
-      }
       __syncthreads();
 
       //  Reserve this tile's run in every bin segment it contributes to.
@@ -242,10 +236,11 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
       }
       __syncthreads();
 
+      //  Full k-mer only for the kept positions, straight from the window registers to HBM.
       for (u32 v = keep; v; ) {
         const u32 q = __clz(v);
         v &= ~(0x80000000u >> q);
-        const Key key = stash[t * 32 + q];
+        const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
         const u32 bin = key_field(key, 2 * p.k - p.binBits, p.binBits);
         out[gbase[bin] + rank[t * 32 + q]] = key;
       }

@@ -122,12 +122,35 @@ sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 
   h[d] = segStart[seg] + base + incl - c;
 }
 
+//  ---- tile descriptors: one 16-byte record per tile, so a sweep CTA starts with ONE dependent load --
+
+struct __align__(16) TileInfo {
+  u64 begin;
+  u32 n;
+  u32 seg;                                   //  bit 31: first tile of its segment
+};
+
+__global__ void __launch_bounds__(256)
+sort_tiles_kernel(const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
+                  u32 tileKeys, TileInfo *__restrict__ info) {
+  const u64 tile = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= nTiles) return;
+  const u32 seg   = find_segment(segTile, nSegs, tile);
+  const u64 first = segTile[seg];
+  const u64 begin = segStart[seg] + (tile - first) * tileKeys;
+  u64 n = segStart[seg + 1] - begin;
+  if (n > tileKeys) n = tileKeys;
+  TileInfo t;
+  t.begin = begin;  t.n = (u32)n;  t.seg = seg | (tile == first ? 0x80000000u : 0u);
+  info[tile] = t;
+}
+
 //  ---- one digit pass ---------------------------------------------------------------------------
 
 template <int KW>
-__global__ void __launch_bounds__(SORT_THREADS, (KW == 1 ? 3 : 3))
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
-                  const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs,
+                  const TileInfo *__restrict__ info,
                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
   typedef typename KeyT<KW>::type Key;
@@ -147,12 +170,12 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   for (u32 i = t; i < SORT_WARPS * (MB_RADIX + 1); i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
   __syncthreads();
 
-  const u64 tile  = sTile;
-  const u32 seg   = find_segment(segTile, nSegs, tile);
-  const u64 first = segTile[seg];
-  const u64 begin = segStart[seg] + (tile - first) * TILE;
-  u64 n64 = segStart[seg + 1] - begin;
-  const u32 n = n64 > (u64)TILE ? (u32)TILE : (u32)n64;
+  const u64 tile = sTile;
+  const TileInfo ti = info[tile];
+  const u64  begin   = ti.begin;
+  const u32  n       = ti.n;
+  const u32  seg     = ti.seg & 0x7fffffffu;
+  const bool isFirst = (ti.seg >> 31) != 0;
 
   //  load (warp-striped: consecutive lanes, consecutive keys) and rank
   //  dr[i]: digit in the low 16 bits (MB_RADIX for the padding of a ragged tile), rank within
@@ -202,35 +225,44 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     for (u32 w = 0; w < warp; w++) base += warpTot[w];
     binOff[t] = base + incl - myCount;
   }
+  __syncthreads();
 
-  //  publish, look back over the earlier tiles of this segment
+  //  reorder in shared memory (needs only tile-local offsets; frees the key registers before the wait)
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    if ((dr[i] & 0xffff) < MB_RADIX)
+      stage[binOff[dr[i] & 0xffff] + wcnt[warp][dr[i] & 0xffff] + (dr[i] >> 16)] = key[i];
+
+  //  publish, look back over the earlier tiles of this segment.  The walk is batched: LB status
+  //  words are requested at once so a walk of d tiles costs ~d/LB L2 round trips, not d.
   {
+    const int LB = 4;
     const u32 d = t;
     u64 *mine = status + tile * MB_RADIX + d;
     u64 excl = 0;
-    if (tile == first) {
+    if (isFirst) {
       st_volatile_u64(mine, ST_MAKE(2, epoch, myCount));
     } else {
       st_volatile_u64(mine, ST_MAKE(1, epoch, myCount));
-      u64 j = tile - 1;
-      for (;;) {
-        const u64 v = ld_volatile_u64(status + j * MB_RADIX + d);
-        if (ST_FLAG(v) == 0 || ST_EPOCH(v) != epoch) continue;          //  not published yet
-        excl += ST_VALUE(v);
-        if (ST_FLAG(v) == 2) break;
-        j--;
+      const u64 *p = status + (tile - 1) * MB_RADIX + d;            //  predecessor; the segment's first tile ends the walk
+      bool done = false;
+      while (!done) {
+        u64 v[LB];
+#pragma unroll
+        for (int b = 0; b < LB; b++) v[b] = ld_volatile_u64(p - (size_t)b * MB_RADIX);   //  may read before the segment: ignored below
+#pragma unroll
+        for (int b = 0; b < LB; b++) {
+          if (done) break;
+          if (ST_FLAG(v[b]) == 0 || ST_EPOCH(v[b]) != epoch) break;                      //  not published yet: poll again from here
+          excl += ST_VALUE(v[b]);
+          p -= MB_RADIX;
+          if (ST_FLAG(v[b]) == 2) done = true;
+        }
       }
       st_volatile_u64(mine, ST_MAKE(2, epoch, excl + myCount));
     }
     gofs[d] = gbase[((u64)seg * nPasses + pass) * MB_RADIX + d] + excl - binOff[d];
   }
-  __syncthreads();
-
-  //  reorder in shared memory
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++)
-    if ((dr[i] & 0xffff) < MB_RADIX)
-      stage[binOff[dr[i] & 0xffff] + wcnt[warp][dr[i] & 0xffff] + (dr[i] >> 16)] = key[i];
   __syncthreads();
 
   //  digit runs to HBM
@@ -259,9 +291,12 @@ u32 mb_sort_tile_keys(u32 keyWords) {
   return SORT_THREADS * (keyWords == 1 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
 }
 
-//  workspace: [ghist: nSegs*nPasses*256 u64][tile counters: 16 u64][status: nTiles*256 u64]
+//  workspace: [ghist: nSegs*nPasses*256 u64][tile counters: 16 u64][guard: 4*256 u64][status: nTiles*256 u64][tile info: nTiles*16 B]
+//  (the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
+static const size_t kStatusGuard = 4 * MB_RADIX;
+
 size_t mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses) {
-  return ((size_t)nSegs * nPasses * MB_RADIX + 16 + (size_t)nTiles * MB_RADIX) * sizeof(u64);
+  return ((size_t)nSegs * nPasses * MB_RADIX + 16 + kStatusGuard + (size_t)nTiles * MB_RADIX) * sizeof(u64) + (size_t)nTiles * sizeof(TileInfo) + 64;
 }
 
 template <int KW>
@@ -276,30 +311,36 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     if (evAfterHist) cudaEventRecord(evAfterHist, s);
     return cudaSuccess;
   }
+  if (plan.nPasses > 16) return cudaErrorInvalidValue;
   if (workspaceBytes < mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses)) return cudaErrorInvalidValue;
 
   u64 *ghist   = (u64 *)dWorkspace;
   u64 *counter = ghist + (size_t)nSegs * plan.nPasses * MB_RADIX;
-  u64 *status  = counter + 16;
+  u64 *status  = counter + 16 + kStatusGuard;
+  TileInfo *info = (TileInfo *)(((uintptr_t)(status + (size_t)nTiles * MB_RADIX) + 15) & ~(uintptr_t)15);
 
-  cudaError_t e = cudaMemsetAsync(dWorkspace, 0, mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses), s);
+  const size_t zeroBytes = (size_t)((uint8_t *)(status + (size_t)nTiles * MB_RADIX) - (uint8_t *)dWorkspace);
+  cudaError_t e = cudaMemsetAsync(dWorkspace, 0, zeroBytes, s);
   if (e != cudaSuccess) return e;
 
   SortPassTable pt;
   pt.nPasses = plan.nPasses;
   for (u32 p = 0; p < 16; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
 
+  const u32 tileKeys = SORT_THREADS * SortShape<KW>::ITEMS;
+  sort_tiles_kernel<<<(unsigned)((nTiles + 255) / 256), 256, 0, s>>>(dSegStart, dSegTile, nSegs, nTiles, tileKeys, info);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
   sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, ghist);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   sort_scan_kernel<<<dim3(nSegs, plan.nPasses), MB_RADIX, 0, s>>>(ghist, dSegStart, plan.nPasses);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (nLaunches) *nLaunches += 2;
+  if (nLaunches) *nLaunches += 3;
   if (evAfterHist) cudaEventRecord(evAfterHist, s);
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
   for (u32 p = 0; p < plan.nPasses; p++) {
-    sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, 0, s>>>(src, dst, dSegStart, dSegTile, nSegs, ghist, plan.nPasses, p,
+    sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, 0, s>>>(src, dst, info, ghist, plan.nPasses, p,
                                                                    plan.shift[p], plan.bits[p], status, counter + p, p + 1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;

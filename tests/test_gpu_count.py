@@ -192,3 +192,60 @@ def test_multi_pass_equals_single_pass(tmp_path):
         c.write_db(b)
     assert one == 1 and many > 1, (one, many)
     util.assert_same_db(a, b)
+
+
+def test_device_generator_and_device_ingest_match_oracle(tmp_path):
+    """bench.py's input path: reads generated on the device (csrc/synth.cu) and ingested from device
+    memory must give the same db as the oracle run on the same reads written as a FASTQ file."""
+    import torch
+    n_reads, L, G, err, seed = 30_000, 150, 500_000, 0.004, 11
+    rec0, rec1 = mb.synth_record_bytes(L, 0), mb.synth_record_bytes(L, 1)
+    assert (rec0, rec1) == (151, 319)
+    d0 = torch.empty(n_reads * rec0, dtype=torch.uint8, device="cuda")
+    d1 = torch.empty(n_reads * rec1, dtype=torch.uint8, device="cuda")
+    mb.synth_reads_device(d0.data_ptr(), 5, n_reads, L, G, err, seed, 0)
+    mb.synth_reads_device(d1.data_ptr(), 5, n_reads, L, G, err, seed, 1)
+    torch.cuda.synchronize()
+    fq = d1.cpu().numpy().tobytes()
+    stream = d0.cpu().numpy().tobytes()
+    assert fq.startswith(b"@r000000000005\n") and fq.count(b"\n") == 4 * n_reads
+    assert util.oracle_parse(fq).replace(b"..", b".") == stream + b"."[:0] or util.oracle_parse(fq).rstrip(b".") == stream.rstrip(b".")
+    p = tmp_path / "s.fq"
+    p.write_bytes(fq)
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=21", "wprefix=12", "count", str(p), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    with mb.Counter(21, 12) as c:
+        half = (n_reads // 2) * rec0
+        c.add_bases_device(d0.data_ptr(), half)                       # two device chunks of whole records
+        c.add_bases_device(d0.data_ptr() + half, n_reads * rec0 - half) if half % 16 == 0 else c.add_bases(stream[half:], True)
+        c.count()
+        c.write_db(out)
+    util.assert_same_db(ora, out)
+
+
+def test_pinned_host_ingest_fast_path(tmp_path):
+    """mb_add_bases on a large page-locked buffer takes the in-place DMA path (64 MB pieces that cut
+    records anywhere); the db must equal the one from the ordinary staged path."""
+    import torch
+    n_reads, L = 2_000_000, 150                                       # 302 MB of base stream: > 4 staging buffers
+    rec0 = mb.synth_record_bytes(L, 0)
+    d0 = torch.empty(n_reads * rec0, dtype=torch.uint8, device="cuda")
+    mb.synth_reads_device(d0.data_ptr(), 0, n_reads, L, 3_000_000, 0.001, 4, 0)
+    host = torch.empty(n_reads * rec0, dtype=torch.uint8, pin_memory=True)
+    host.copy_(d0)
+    torch.cuda.synchronize()
+    a, b = str(tmp_path / "a.meryl"), str(tmp_path / "b.meryl")
+    with mb.Counter(21, 14) as c:
+        c.add_bases_ptr(host.data_ptr(), n_reads * rec0, True)        # pinned: direct
+        c.count()
+        sa = c.stats()
+        c.write_db(a)
+    pageable = host.numpy().tobytes()
+    with mb.Counter(21, 14) as c:
+        c.add_bases(pageable, True)                                   # pageable: staged
+        c.count()
+        sb = c.stats()
+        c.write_db(b)
+    assert sa.nKmers == sb.nKmers == n_reads * (L - 21 + 1)
+    util.assert_same_db(a, b)
