@@ -129,6 +129,12 @@ int mb_comm_init(mb_ctx *ctx, const uint8_t id[128]);
  *  files with the light high ones (canonical k-mers are skewed), SURVEY.md section 8e.  */
 uint32_t mb_file_owner_of(uint32_t file, uint32_t worldSize);
 
+/*  Optional: host memory (ideally page-locked) that receives the 64 data-file images, appended in file
+ *  order; mb_get_image(0..63) then points into it.  Without it the library allocates the images itself.
+ *  MB_ENOMEM from mb_count if it is too small (the db of N k-mers of which D are distinct needs about
+ *  D * (2k - wPrefix + 36) / 8 + 2^wPrefix * 104 bytes).  */
+int mb_set_output_buffer(mb_ctx *ctx, void *hostBuf, uint64_t bytes);
+
 /*  Count everything added so far.  After this the encoded db (this rank's files) is in host memory.  */
 int mb_count(mb_ctx *ctx);
 
@@ -160,6 +166,8 @@ int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *bases, uint64_t
                           uint64_t *kmerLo, uint64_t *kmerHi, uint64_t cap, uint64_t *n);
 /*  K4 alone: sort `n` keys of `bits` significant bits (keys[] in/out; hi may be NULL).  */
 int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits);
+/*  Debug: per-phase clock sums of the sort sweep kernel (enable=1 starts collecting; out may be NULL).  */
+int mb_dbg_sort_profile(uint64_t out[8], int enable);
 /*  K6 alone: encode one block like merylFileWriter::writeBlockToFile.  out must hold cap bytes.  */
 int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix, uint64_t n,
                         const uint64_t *sufLo, const uint64_t *sufHi, const uint32_t *values,

@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
         L.mb_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mb_file_owner_of.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         L.mb_file_owner_of.restype = ctypes.c_uint32
+        L.mb_set_output_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
         L.mb_count.argtypes = [ctypes.c_void_p]
         L.mb_get_image.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), u64p]
         L.mb_write_db.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
@@ -189,6 +190,10 @@ class Counter:
         _check(lib().mb_comm_init(self._h, unique_id))
 
     # ---- run / results ----
+    def set_output_buffer(self, host_ptr: int, n_bytes: int) -> None:
+        """Caller-owned (ideally pinned) host memory for the 64 data-file images."""
+        _check(lib().mb_set_output_buffer(self._h, ctypes.c_void_p(host_ptr), n_bytes))
+
     def count(self) -> None:
         _check(lib().mb_count(self._h))
 

@@ -70,7 +70,11 @@ struct MbHistogram {                      //  value -> occurrences, plus the mas
 };
 
 struct MbDbImages {
-  std::vector<uint8_t> data[64];
+  //  A data file image lives either in its own vector or, when the caller supplied an output
+  //  buffer (mb_set_output_buffer), as a contiguous slice of that buffer.
+  std::vector<uint8_t> dataVec[64];
+  const uint8_t       *dataPtr[64] = { nullptr };
+  size_t               dataLen[64] = { 0 };
   std::vector<uint8_t> index[64];
   std::vector<uint8_t> master;
   bool owned[64];                         //  files this rank owns

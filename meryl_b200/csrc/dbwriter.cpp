@@ -91,10 +91,10 @@ void mb_file_name(char *out, size_t cap, const char *dir, u32 file, bool isIndex
 }
 
 
-static int writeWhole(const char *path, const std::vector<uint8_t> &b) {
+static int writeWhole(const char *path, const uint8_t *p, size_t n) {
   FILE *f = fopen(path, "wb");
   if (!f) return mb_fail(MB_EIO, "cannot create '%s': %s", path, strerror(errno));
-  if (!b.empty() && fwrite(b.data(), 1, b.size(), f) != b.size()) {
+  if (n && fwrite(p, 1, n, f) != n) {
     fclose(f);
     return mb_fail(MB_EIO, "short write to '%s': %s", path, strerror(errno));
   }
@@ -110,13 +110,13 @@ int mb_write_db_dir(const MbDbImages &db, const char *dir, bool writeMaster) {
   for (u32 f = 0; f < 64; f++) {
     if (!db.owned[f]) continue;
     mb_file_name(path, sizeof(path), dir, f, false);
-    MB_TRY(writeWhole(path, db.data[f]));
+    MB_TRY(writeWhole(path, db.dataPtr[f], db.dataLen[f]));
     mb_file_name(path, sizeof(path), dir, f, true);
-    MB_TRY(writeWhole(path, db.index[f]));
+    MB_TRY(writeWhole(path, db.index[f].data(), db.index[f].size()));
   }
   if (writeMaster) {
     snprintf(path, sizeof(path), "%s/merylIndex", dir);
-    MB_TRY(writeWhole(path, db.master));
+    MB_TRY(writeWhole(path, db.master.data(), db.master.size()));
   }
   return MB_OK;
 }

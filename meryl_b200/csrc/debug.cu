@@ -63,6 +63,28 @@ extern "C" int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *base
   return rc;
 }
 
+void mb_sort_set_profile_buffer(u64 *dProf);
+
+//  Debug: turn the sweep kernel's phase timing on (returns 0) and read/reset it.
+//  out[0] = tiles, out[1..6] = summed clocks of: tile id, load+rank, scan+reorder, own look-back,
+//  wait for the CTA's look-back, copy-out.
+static u64 *g_dProf = nullptr;
+extern "C" int mb_dbg_sort_profile(uint64_t out[8], int enable) {
+  mb_clear_error();
+  if (enable && !g_dProf) {
+    MB_CUDA(cudaMalloc((void **)&g_dProf, 8 * sizeof(u64)));
+    MB_CUDA(cudaMemset(g_dProf, 0, 8 * sizeof(u64)));
+    mb_sort_set_profile_buffer(g_dProf);
+  }
+  if (g_dProf && out) {
+    MB_CUDA(cudaDeviceSynchronize());
+    MB_CUDA(cudaMemcpy(out, g_dProf, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
+    MB_CUDA(cudaMemset(g_dProf, 0, 8 * sizeof(u64)));
+  }
+  if (!enable && g_dProf) { mb_sort_set_profile_buffer(nullptr); cudaFree(g_dProf); g_dProf = nullptr; }
+  return MB_OK;
+}
+
 extern "C" int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits) {
   mb_clear_error();
   if (!lo && n) return mb_fail(MB_EINVAL, "mb_dbg_sort: NULL argument");

@@ -79,6 +79,9 @@ struct mb_ctx {
   std::vector<u64> sortedLo, sortedHi;               //  debug: all k-mers, sorted (stopAfterSort)
   bool        stopAfterSort = false;
 
+  uint8_t    *outBuf     = nullptr;                  //  caller-supplied host buffer for the data images
+  size_t      outCap     = 0, outUsed = 0;
+
   MbComm     *comm       = nullptr;                  //  multi-GPU (exchange.cu)
 };
 
@@ -527,7 +530,8 @@ static int runCount(mb_ctx *c) {
   c->st.sortPasses = plan.nPasses;
 
   //  host images
-  for (u32 f = 0; f < 64; f++) { c->db.data[f].clear(); c->db.index[f].clear(); }
+  for (u32 f = 0; f < 64; f++) { c->db.dataVec[f].clear(); c->db.dataPtr[f] = nullptr; c->db.dataLen[f] = 0; c->db.index[f].clear(); }
+  c->outUsed = 0;
   std::vector<u64> fileBase(64, 0);
 
   std::vector<u64> segStart, segTile, binStart(MB_MAX_BINS + 1);
@@ -735,10 +739,26 @@ static int runCount(mb_ctx *c) {
             const u32 file = fileLo + f;
             const size_t fb = fm[f + 1].outByte - fm[f].outByte;
             const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
-            std::vector<uint8_t> &dv = c->db.data[file], &iv = c->db.index[file];
-            const size_t d0 = dv.size(), i0 = iv.size();
-            dv.resize(d0 + fb);  iv.resize(i0 + ib);
-            MB_CUDA(cudaMemcpyAsync(dv.data() + d0, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
+            std::vector<uint8_t> &iv = c->db.index[file];
+            uint8_t *dst;
+            if (c->outBuf) {                          //  append to the caller's buffer: a file's pieces arrive back to back
+              if (c->outUsed + fb > c->outCap)
+                return mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", file, fb, c->outUsed, c->outCap);
+              if (c->db.dataLen[file] == 0) c->db.dataPtr[file] = c->outBuf + c->outUsed;
+              else if (c->db.dataPtr[file] + c->db.dataLen[file] != c->outBuf + c->outUsed)
+                return mb_fail(MB_ESTATE, "internal: data file %u is not contiguous in the output buffer", file);
+              dst = c->outBuf + c->outUsed;
+              c->outUsed += fb;
+            } else {
+              std::vector<uint8_t> &dv = c->db.dataVec[file];
+              const size_t d0 = dv.size();
+              dv.resize(d0 + fb);
+              dst = dv.data() + d0;
+            }
+            c->db.dataLen[file] += fb;
+            const size_t i0 = iv.size();
+            iv.resize(i0 + ib);
+            MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
             MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
             c->st.d2hBytes += fb + ib;
           }
@@ -816,7 +836,10 @@ static int runCount(mb_ctx *c) {
 
     mb_build_master_index(k, wP, c->hist, c->db.master);
     c->st.dbBytes = (me == 0) ? c->db.master.size() : 0;
-    for (u32 f = 0; f < 64; f++) c->st.dbBytes += c->db.data[f].size() + c->db.index[f].size();
+    for (u32 f = 0; f < 64; f++) {
+      if (!c->outBuf) c->db.dataPtr[f] = c->db.dataVec[f].data();       //  vectors may have moved while growing
+      c->st.dbBytes += c->db.dataLen[f] + c->db.index[f].size();
+    }
   }
 
   tAll.stop(s);
@@ -827,6 +850,14 @@ static int runCount(mb_ctx *c) {
   return MB_OK;
 }
 
+
+extern "C" int mb_set_output_buffer(mb_ctx *c, void *hostBuf, uint64_t bytes) {
+  mb_clear_error();
+  if (!c || (!hostBuf && bytes))  return mb_fail(MB_EINVAL, "mb_set_output_buffer: NULL argument");
+  if (c->counted)                 return mb_fail(MB_ESTATE, "mb_set_output_buffer: already counted");
+  c->outBuf = (uint8_t *)hostBuf;  c->outCap = bytes;  c->outUsed = 0;
+  return MB_OK;
+}
 
 extern "C" int mb_count(mb_ctx *c) {
   mb_clear_error();
@@ -844,7 +875,8 @@ extern "C" int mb_get_image(mb_ctx *c, uint32_t which, const uint8_t **ptr, uint
   mb_clear_error();
   if (!c || !ptr || !len || which > 128)  return mb_fail(MB_EINVAL, "mb_get_image: bad argument");
   if (!c->counted)                        return mb_fail(MB_ESTATE, "mb_get_image: call mb_count first");
-  const std::vector<uint8_t> &v = which < 64 ? c->db.data[which] : which < 128 ? c->db.index[which - 64] : c->db.master;
+  if (which < 64) { *ptr = c->db.dataPtr[which]; *len = c->db.dataLen[which]; return MB_OK; }
+  const std::vector<uint8_t> &v = which < 128 ? c->db.index[which - 64] : c->db.master;
   *ptr = v.data();
   *len = v.size();
   return MB_OK;

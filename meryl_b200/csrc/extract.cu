@@ -14,16 +14,18 @@
 //  (cp.async.bulk + mbarrier), double buffered so the next tile streams in under the current
 //  tile's integer work.  Per thread: 32 consecutive positions.
 //    1. validity of all 32 windows at once by log-step erosion of the validity bits;
-//    2. cheap pre-filter: the prefix bin of the canonical k-mer is min(top bits of f, top bits of
-//       r) and needs only the first and last binBits/2 bases -> keep-mask of this pass's bins;
-//    3. kept positions take their rank within (tile, bin) by a shared-memory atomic; one global
-//       atomic per (tile, bin) reserves the run in the bin's segment;
-//    4. the full k-mer is computed only for kept positions and stored straight from registers
-//       (nothing is staged in shared memory: ~35 KB per CTA, 6 CTAs per SM).
+//    2. all lanes walk their 32 positions in lock step, rolling forward and reverse-complement
+//       k-mers (every shift is warp-uniform, no divergence, ~16 integer ops per position); the
+//       canonical k-mer's top bits are its prefix bin;
+//    3. k-mers of this pass's bins take their rank within (tile, bin) by a shared-memory atomic;
+//       one global atomic per (tile, bin) reserves the run in the bin's segment;
+//    4. the kept k-mers are produced again (rolling when the pass keeps most positions, direct
+//       window extraction when it keeps few) and stored straight from registers -- nothing is
+//       staged in shared memory: ~35 KB per CTA, 6 CTAs per SM.
 //  The same kernel in COUNT_ONLY form is the histogram pre-pass (K2a) that sizes the segments.
 //
-//  Work: integer/bit ops, ~16 per position for the pre-filter + ~40 per kept k-mer; HBM traffic
-//  0.375 B per position read + 8 (16) B per kept k-mer written -- compute bound, not HBM bound.
+//  Work: integer/bit ops, ~16-20 per position per phase; HBM traffic 0.375 B per position read +
+//  8 (16) B per kept k-mer written -- integer-ALU bound, not HBM bound.
 
 #include "kernels.cuh"
 
@@ -128,15 +130,6 @@ __device__ __forceinline__ u32 windows_valid(u32 m0, u32 m1, u32 m2, u32 k) {
   return (u32)(hi >> 32);
 }
 
-//  Prefix bin of the counted k-mer that starts at thread-relative position q.
-__device__ __forceinline__ u32 kmer_bin(const Window &w, u32 q, u32 k, u32 mode, u32 binBits) {
-  const u32 half = binBits >> 1;
-  const u32 fTop = (u32)bits_ending_at(w, 2 * q + binBits, binBits);
-  const u32 tail = (u32)bits_ending_at(w, 2 * (q + k), binBits);
-  const u32 rTop = (u32)revcomp64(tail, half);
-  return (mode == MB_MODE_FORWARD) ? fTop : (mode == MB_MODE_REVERSE) ? rTop : min(fTop, rTop);
-}
-
 __device__ __forceinline__ u64 kmer_key(const Window &w, u32 q, u32 k, u32 mode, u64 *) {
   const u64 f = bits_ending_at(w, 2 * (q + k), 2 * k);
   if (mode == MB_MODE_FORWARD) return f;
@@ -155,6 +148,53 @@ __device__ __forceinline__ ulonglong2 kmer_key(const Window &w, u32 q, u32 k, u3
   return useF ? make_ulonglong2(flo, fhi) : make_ulonglong2(rlo, rhi);
 }
 
+//  ---- lock-step rolling k-mers ------------------------------------------------------------------
+//  All lanes walk their 32 positions in the same order, so every shift amount is warp-uniform
+//  and there is no divergence: ~16 integer ops per position for forward + reverse complement.
+
+template <int KW> struct Roll;
+
+template <> struct Roll<1> {
+  u64 f, r;
+  __device__ __forceinline__ void init(const Window &w, u32 k) {
+    f = bits_ending_at(w, 2 * k, 2 * k);
+    r = revcomp64(f, k);
+  }
+  __device__ __forceinline__ void push(u32 code, u32 k, u64 mask) {
+    f = ((f << 2) | code) & mask;
+    r = (r >> 2) | ((u64)(code ^ 2) << (2 * k - 2));
+  }
+  __device__ __forceinline__ u64 key(u32 mode) const {
+    return (mode == MB_MODE_FORWARD) ? f : (mode == MB_MODE_REVERSE) ? r : (f < r ? f : r);
+  }
+};
+
+template <> struct Roll<2> {
+  u64 fl, fh, rl, rh;
+  __device__ __forceinline__ void init(const Window &w, u32 k) {
+    fl = bits_ending_at(w, 2 * k, 64);
+    fh = bits_ending_at(w, 2 * k - 64, 2 * k - 64);
+    revcomp128(fh, fl, k, rh, rl);
+  }
+  __device__ __forceinline__ void push(u32 code, u32 k, u64 maskHi) {
+    fh = ((fh << 2) | (fl >> 62)) & maskHi;
+    fl = (fl << 2) | code;
+    rl = (rl >> 2) | (rh << 62);
+    rh = (rh >> 2) | ((u64)(code ^ 2) << (2 * k - 66));
+  }
+  __device__ __forceinline__ ulonglong2 key(u32 mode) const {
+    bool useF = (mode == MB_MODE_FORWARD);
+    if (mode == MB_MODE_CANONICAL) useF = (fh < rh) || (fh == rh && fl < rl);
+    return useF ? make_ulonglong2(fl, fh) : make_ulonglong2(rl, rh);
+  }
+};
+
+//  2-bit code of thread-relative position pos (0..95); pos is warp-uniform.
+__device__ __forceinline__ u32 window_code(const Window &w, u32 pos) {
+  const u64 word = pos < 32 ? w.w0 : pos < 64 ? w.w1 : w.w2;
+  return (u32)(word >> (62 - 2 * (pos & 31))) & 3;
+}
+
 template <int KW, bool COUNT_ONLY>
 __global__ void __launch_bounds__(ExtractShape<KW>::THREADS)
 extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
@@ -171,6 +211,7 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
 
   const u32 t = threadIdx.x;
   const u32 nBins = 1u << p.binBits;
+  const bool rollAgain = (p.binHi - p.binLo) * 3 >= nBins;      //  this pass keeps >= 1/3 of the k-mers
 
   if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   for (u32 b = t; b < nBins; b += blockDim.x) cnt[b] = 0;
@@ -208,18 +249,26 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
     //  Positions at or beyond the end of the store never start a k-mer (their records are zero),
     //  so no bound check is needed here.
 
-    //  Pre-filter: which of my valid windows fall into this pass's bins?  The bin needs only the
-    //  first and last binBits/2 bases; kept positions take their rank inside (tile, bin) right away.
+    //  Phase A, lock-step over my 32 positions: canonical k-mer by rolling, its bin, and for the
+    //  bins of this pass a rank inside (tile, bin).
+    const u32 binShift = 2 * p.k - p.binBits;
+    const u64 rollMask = (KW == 1) ? ((p.k == 32) ? ~0ull : (((u64)1 << (2 * p.k)) - 1))
+                                   : ((p.k == 64) ? ~0ull : (((u64)1 << (2 * p.k - 64)) - 1));
     u32 keep = 0;
-    for (u32 v = valid; v; ) {
-      const u32 q   = __clz(v);                       //  position 0 is bit 31
-      v &= ~(0x80000000u >> q);
-      const u32 bin = kmer_bin(w, q, p.k, p.mode, p.binBits);
-      if (COUNT_ONLY) {
-        atomicAdd(&cnt[bin], 1u);
-      } else if (bin >= p.binLo && bin < p.binHi) {
-        keep |= 0x80000000u >> q;
-        rank[t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin], 1u);
+    if (valid) {
+      Roll<KW> roll;
+      roll.init(w, p.k);
+      for (u32 q = 0; q < 32; q++) {
+        if ((valid << q) & 0x80000000u) {
+          const u32 bin = key_field(roll.key(p.mode), binShift, p.binBits);
+          if (COUNT_ONLY) {
+            atomicAdd(&cnt[bin], 1u);
+          } else if (bin >= p.binLo && bin < p.binHi) {
+            keep |= 0x80000000u >> q;
+            rank[t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin], 1u);
+          }
+        }
+        roll.push(window_code(w, q + p.k), p.k, rollMask);
       }
     }
 
@@ -236,13 +285,27 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
       }
       __syncthreads();
 
-      //  Full k-mer only for the kept positions, straight from the window registers to HBM.
-      for (u32 v = keep; v; ) {
-        const u32 q = __clz(v);
-        v &= ~(0x80000000u >> q);
-        const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
-        const u32 bin = key_field(key, 2 * p.k - p.binBits, p.binBits);
-        out[gbase[bin] + rank[t * 32 + q]] = key;
+      //  Phase B: the kept k-mers go straight from registers to their reserved slots.  When the pass
+      //  keeps most positions, roll again in lock step; when it keeps few, rebuild only those.
+      if (keep) {
+        if (rollAgain) {
+          Roll<KW> roll;
+          roll.init(w, p.k);
+          for (u32 q = 0; q < 32; q++) {
+            if ((keep << q) & 0x80000000u) {
+              const Key key = roll.key(p.mode);
+              out[gbase[key_field(key, binShift, p.binBits)] + rank[t * 32 + q]] = key;
+            }
+            roll.push(window_code(w, q + p.k), p.k, rollMask);
+          }
+        } else {
+          for (u32 v = keep; v; ) {
+            const u32 q = __clz(v);
+            v &= ~(0x80000000u >> q);
+            const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
+            out[gbase[key_field(key, binShift, p.binBits)] + rank[t * 32 + q]] = key;
+          }
+        }
       }
     }
     __syncthreads();                                  //  all reads of rec[buf] / gbase done

@@ -152,10 +152,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 4)
 sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                   const TileInfo *__restrict__ info,
                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
-                  u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
+                  u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch, u64 *__restrict__ prof) {
   typedef typename KeyT<KW>::type Key;
   const int ITEMS = SortShape<KW>::ITEMS;
   const int TILE  = SORT_THREADS * ITEMS;
+
+  //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[0..7]
+  long long tk[8];
+  int ntk = 0;
+#define MB_TICK() do { if (prof && threadIdx.x == 0 && ntk < 8) tk[ntk++] = clock64(); } while (0)
+  MB_TICK();
 
   __shared__ Key  stage[TILE];
   __shared__ u32  wcnt[SORT_WARPS][MB_RADIX + 1];        //  [..][256] collects the padding of a ragged tile
@@ -170,6 +176,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   for (u32 i = t; i < SORT_WARPS * (MB_RADIX + 1); i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
   __syncthreads();
 
+  MB_TICK();                                             //  1: tile id
   const u64 tile = sTile;
   const TileInfo ti = info[tile];
   const u64  begin   = ti.begin;
@@ -190,17 +197,28 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     else       { dr[i] = MB_RADIX; }
   }
 
+  //  Peers holding the same digit: one ballot per digit bit (plus one for the padding flag) --
+  //  cheaper than match.any.  Each warp owns its counter row, so the running count per digit is a
+  //  plain shared-memory read (broadcast inside the peer group) and one write by the group's leader.
   const u32 ltMask = (1u << lane) - 1;
+  const u32 rbits  = bits + 1;                           //  digit bits + the "padding" bit (MB_RADIX)
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
-    const u32 m      = __match_any_sync(0xffffffffu, dr[i]);
-    const u32 leader = __ffs(m) - 1;
-    u32 prior = 0;
-    if (lane == leader) prior = atomicAdd(&wcnt[warp][dr[i]], (u32)__popc(m));
-    prior  = __shfl_sync(0xffffffffu, prior, leader);
+    u32 m = 0xffffffffu;
+    for (u32 b = 0; b < rbits; b++) {
+      const u32 bitpos = (b < bits) ? b : MB_RADIX_BITS; //  the padding flag is bit 8 of MB_RADIX
+      const u32 bit = (dr[i] >> bitpos) & 1;
+      const u32 bal = __ballot_sync(0xffffffffu, bit);
+      m &= bit ? bal : ~bal;
+    }
+    const u32 prior = wcnt[warp][dr[i]];
+    __syncwarp();
+    if ((m & ltMask) == 0) wcnt[warp][dr[i]] = prior + __popc(m);      //  lowest lane of the group
+    __syncwarp();
     dr[i] |= (prior + __popc(m & ltMask)) << 16;
   }
   __syncthreads();
+  MB_TICK();                                             //  2: keys loaded and ranked
 
   //  per digit: exclusive scan over the warps, tile total
   u32 myCount = 0;
@@ -233,6 +251,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     if ((dr[i] & 0xffff) < MB_RADIX)
       stage[binOff[dr[i] & 0xffff] + wcnt[warp][dr[i] & 0xffff] + (dr[i] >> 16)] = key[i];
 
+  MB_TICK();                                             //  3: tile scan + reorder issued
   //  publish, look back over the earlier tiles of this segment.  The walk is batched: LB status
   //  words are requested at once so a walk of d tiles costs ~d/LB L2 round trips, not d.
   {
@@ -263,13 +282,21 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     }
     gofs[d] = gbase[((u64)seg * nPasses + pass) * MB_RADIX + d] + excl - binOff[d];
   }
+  MB_TICK();                                             //  4: my own look-back done
   __syncthreads();
+  MB_TICK();                                             //  5: everybody's look-back done
 
   //  digit runs to HBM
   for (u32 j = t; j < n; j += SORT_THREADS) {
     const Key k = stage[j];
     out[gofs[key_field(k, shift, bits)] + j] = k;
   }
+  MB_TICK();                                             //  6: my stores issued
+  if (prof && threadIdx.x == 0) {
+    for (int i = 1; i < ntk; i++) atomicAdd((unsigned long long *)&prof[i], (unsigned long long)(tk[i] - tk[i - 1]));
+    atomicAdd((unsigned long long *)&prof[0], 1ull);
+  }
+#undef MB_TICK
 }
 
 }  //  namespace
@@ -290,6 +317,10 @@ void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
 u32 mb_sort_tile_keys(u32 keyWords) {
   return SORT_THREADS * (keyWords == 1 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
 }
+
+//  Debug: device buffer of 8 u64 that receives per-phase clock sums of the sweep kernel (NULL = off).
+static u64 *g_sortProf = nullptr;
+void mb_sort_set_profile_buffer(u64 *dProf) { g_sortProf = dProf; }
 
 //  workspace: [ghist: nSegs*nPasses*256 u64][tile counters: 16 u64][guard: 4*256 u64][status: nTiles*256 u64][tile info: nTiles*16 B]
 //  (the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
@@ -341,7 +372,7 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
   for (u32 p = 0; p < plan.nPasses; p++) {
     sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, 0, s>>>(src, dst, info, ghist, plan.nPasses, p,
-                                                                   plan.shift[p], plan.bits[p], status, counter + p, p + 1);
+                                                                   plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;
     Key *tmp = src; src = dst; dst = tmp;

@@ -249,3 +249,30 @@ def test_pinned_host_ingest_fast_path(tmp_path):
         c.write_db(b)
     assert sa.nKmers == sb.nKmers == n_reads * (L - 21 + 1)
     util.assert_same_db(a, b)
+
+
+def test_output_buffer_images_match_internal_images(tmp_path):
+    """mb_set_output_buffer: data images land in the caller's buffer, byte-identical to the internal ones."""
+    import torch
+    data = synth.reads_fastq_bytes(100_000, 20_000, 150, 0.002, 13)
+    with mb.Counter(21, 12) as c:
+        c.add_file_bytes(data)
+        c.count()
+        want = [c.image(i) for i in range(129)]
+    buf = torch.zeros(sum(len(x) for x in want[:64]) + 1024, dtype=torch.uint8, pin_memory=True)
+    with mb.Counter(21, 12) as c:
+        c.set_output_buffer(buf.data_ptr(), buf.numel())
+        c.add_file_bytes(data)
+        c.count()
+        got = [c.image(i) for i in range(129)]
+        out = str(tmp_path / "o.meryl")
+        c.write_db(out)
+    assert got == want
+    raw = buf.numpy().tobytes()
+    assert raw[: len(want[0])] == want[0]
+    with mb.Counter(21, 12) as c:
+        c.set_output_buffer(buf.data_ptr(), 1000)          # too small: loud error, no fallback
+        c.add_file_bytes(data)
+        with pytest.raises(mb.MerylB200Error) as e:
+            c.count()
+        assert e.value.code == -3
