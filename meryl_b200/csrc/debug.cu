@@ -64,6 +64,26 @@ extern "C" int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *base
 }
 
 void mb_sort_set_profile_buffer(u64 *dProf);
+void mb_extract_set_profile_buffer(u64 *dProf);
+
+//  Debug: phase timing of the extract (scatter) kernel.  out[0] = tiles, out[1..7] = summed clocks of:
+//  wait for the TMA tile, own phase A, CTA phase A, own reservations, CTA reservations, own phase B, CTA phase B.
+static u64 *g_dXProf = nullptr;
+extern "C" int mb_dbg_extract_profile(uint64_t out[8], int enable) {
+  mb_clear_error();
+  if (enable && !g_dXProf) {
+    MB_CUDA(cudaMalloc((void **)&g_dXProf, 8 * sizeof(u64)));
+    MB_CUDA(cudaMemset(g_dXProf, 0, 8 * sizeof(u64)));
+    mb_extract_set_profile_buffer(g_dXProf);
+  }
+  if (g_dXProf && out) {
+    MB_CUDA(cudaDeviceSynchronize());
+    MB_CUDA(cudaMemcpy(out, g_dXProf, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
+    MB_CUDA(cudaMemset(g_dXProf, 0, 8 * sizeof(u64)));
+  }
+  if (!enable && g_dXProf) { mb_extract_set_profile_buffer(nullptr); cudaFree(g_dXProf); g_dXProf = nullptr; }
+  return MB_OK;
+}
 
 //  Debug: turn the sweep kernel's phase timing on (returns 0) and read/reset it.
 //  out[0] = tiles, out[1..6] = summed clocks of: tile id, load+rank, scan+reorder, own look-back,

@@ -28,6 +28,8 @@
 #include "engine.h"
 #include "exchange.h"
 
+static u64 *g_extractProf = nullptr;                 //  debug: phase timing of the extract kernel
+
 namespace {
 
 const size_t kAlign      = 256;
@@ -412,6 +414,7 @@ static int runCount(mb_ctx *c) {
   MbExtractParams xp;
   xp.store = (const u32 *)c->arena;  xp.nPositions = c->nRecords * 32;
   xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;
+  xp.prof = g_extractProf;
 
   tStage.start(s);
   MB_CUDA(mb_launch_bin_histogram(xp, dCtl->binCount, s));
@@ -850,6 +853,9 @@ static int runCount(mb_ctx *c) {
   return MB_OK;
 }
 
+
+//  Debug: device buffer of 8 u64 receiving per-phase clock sums of the extract kernel (NULL = off).
+void mb_extract_set_profile_buffer(u64 *d) { g_extractProf = d; }
 
 extern "C" int mb_set_output_buffer(mb_ctx *c, void *hostBuf, uint64_t bytes) {
   mb_clear_error();

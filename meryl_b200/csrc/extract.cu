@@ -225,8 +225,12 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
     tma_bulk_g2s(rec[0], storeBytes + tile * (u64)(S::THREADS * MB_STORE_REC_WORDS * 4), S::REC_BYTES, &bar[0]);
   }
 
+  long long tk[8];
+#define MB_TICK(i) do { if (p.prof && t == 0) tk[i] = clock64(); } while (0)
+
   for (u32 it = 0; tile < nTiles; it++, tile += gridDim.x) {
     const u32 buf = it & 1;
+    MB_TICK(0);
 
     //  Prefetch the next tile into the other buffer (it was last read two iterations ago, and
     //  every thread has passed a __syncthreads since).
@@ -238,6 +242,7 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
     }
 
     while (!mbar_try_wait(&bar[buf], (it >> 1) & 1)) { }
+    MB_TICK(1);                                       //  tile landed
 
     const u32 *r = rec[buf] + t * MB_STORE_REC_WORDS;
     Window w;
@@ -272,8 +277,10 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
       }
     }
 
+    MB_TICK(2);                                       //  my phase A done
     if (!COUNT_ONLY) {
       __syncthreads();
+      MB_TICK(3);                                     //  everybody's phase A done
 
       //  Reserve this tile's run in every bin segment it contributes to.
       for (u32 b = p.binLo + t; b < p.binHi; b += blockDim.x) {
@@ -283,7 +290,9 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
           cnt[b]   = 0;
         }
       }
+      MB_TICK(4);                                     //  my reservations done
       __syncthreads();
+      MB_TICK(5);                                     //  everybody's reservations done
 
       //  Phase B: the kept k-mers go straight from registers to their reserved slots.  When the pass
       //  keeps most positions, roll again in lock step; when it keeps few, rebuild only those.
@@ -308,8 +317,15 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
         }
       }
     }
+    MB_TICK(6);                                       //  my phase B done
     __syncthreads();                                  //  all reads of rec[buf] / gbase done
+    if (!COUNT_ONLY && p.prof && t == 0) {
+      tk[7] = clock64();
+      for (int i = 1; i < 8; i++) atomicAdd((unsigned long long *)&p.prof[i], (unsigned long long)(tk[i] - tk[i - 1]));
+      atomicAdd((unsigned long long *)&p.prof[0], 1ull);
+    }
   }
+#undef MB_TICK
 
   if (COUNT_ONLY) {
     __syncthreads();

@@ -98,6 +98,7 @@ struct MbExtractParams {
   u32        mode;           //  MB_MODE_*
   u32        binBits;        //  bins = top binBits bits of the k-mer
   u32        binLo, binHi;   //  this pass keeps bins in [binLo, binHi)
+  u64       *prof;           //  debug: per-phase clock sums (NULL = off)
 };
 
 //  K2a extract.cu: bin histogram of every k-mer in the store (count-only pre-pass).  dBinCount[MB_MAX_BINS] += ...

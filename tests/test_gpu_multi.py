@@ -1,0 +1,67 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the reads are split over the ranks, k-mers
+travel to the owner of their data file through the library's NCCL all-to-all, every rank writes its
+own files into one directory, rank 0 the master index -- and the directory must be byte-identical to
+the single-process oracle db of the whole input."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, fq_path, out_dir, k, wp):
+    import torch.distributed as dist
+    from meryl_b200 import dist as mbd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        data = open(fq_path, "rb").read()
+        recs = data.split(b"@r")[1:]                      # synthetic FASTQ: every record starts with "@r"
+        first, cnt = mbd.shard_range(len(recs), rank, world)
+        mine = b"".join(b"@r" + r for r in recs[first:first + cnt])
+        c = mb.Counter(k, wp, "count", device=rank, rank=rank, world_size=world)
+        c.comm_init(mbd.broadcast_unique_id(mb.Counter.comm_unique_id, device="cuda"))
+        c.add_file_bytes(mine)
+        c.count()
+        st = c.stats()
+        total = mbd.all_ranks_sum(st.nKmers, "cuda")
+        c.write_db(out_dir)
+        c.close()
+        dist.barrier()
+        with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as fh:
+            fh.write("%d %d %d\n" % (st.nKmers, total, st.nPasses))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("k", [21, 51])
+def test_multi_gpu_db_bit_exact(tmp_path, world, k):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    n_reads, L = 60_000, 150
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(200_000, n_reads, L, 0.003, 17 + k))
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    os.makedirs(out)
+    port = 29600 + (os.getpid() + world * 7 + k) % 300
+    mp.spawn(_worker, args=(world, port, str(fq), out, k, 12), nprocs=world, join=True)
+    stats = []
+    for r in range(world):
+        p = os.path.join(out, "rank%d.txt" % r)
+        stats.append([int(x) for x in open(p).read().split()])
+        os.remove(p)
+    assert all(s[1] == n_reads * (L - k + 1) for s in stats)
+    assert sum(s[0] for s in stats) == n_reads * (L - k + 1)
+    util.assert_same_db(ora, out)
