@@ -316,12 +316,12 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "meryl count k=21 canonical, %.2f Gbp of synthetic 150 bp reads (3 Gbp uniform-random genome, both strands, 0.1%% substitutions)%s"
                                    % (total_reads * READ_LEN / 1e9, "; " + reduced if reduced else ""),
-                       "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix,
+                       "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix, "key_bytes": stats.keyBytes,
                        "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
                        "l2": "inputs (%.1f GB store, %.1f GB keys per pass on rank 0) far exceed the 126 MB L2" % (stats.nBases * 0.375 / 1e9, stats.nKmers * 8 / max(1, stats.nPasses) / 1e9),
                        "parallelism": "reads split over %d GPU(s); 64 data files sharded by owner(f)=min(f,63-f) mod N, one NCCL all-to-all per pass" % world},
             "stage_ms": {"histogram": stats.msHistogram, "extract": stats.msExtract, "sort_hist": stats.msSortHist,
-                         "sort": stats.msSort, "count": stats.msCount, "encode": stats.msEncode},
+                         "sort": stats.msSort, "count": stats.msCount, "encode": stats.msEncode, "exchange": stats.msExchange},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(stats.nLaunches),
         }))

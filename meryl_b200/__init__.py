@@ -94,6 +94,7 @@ def lib() -> ctypes.CDLL:
         L.mb_dbg_extract_sorted.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, u64p]
         L.mb_dbg_sort.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
+        L.mb_dbg_sort32.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
         L.mb_dbg_encode_block.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_uint64, u64p]

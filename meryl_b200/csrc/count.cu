@@ -132,6 +132,103 @@ count_kernel(typename KeyT<KW>::type *keys, u64 nKeys, u64 *__restrict__ runStar
   }
 }
 
+//  ---- u32 suffix keys: segmented run-length count with expansion to full keys ----------------------
+//
+//  The sorted pass array holds only the low suffixBits of every k-mer; the prefix bin is the
+//  segment.  Tiles are the sort's tiles (TileInfo: begin, n, segment, first-of-segment), so a tile
+//  never straddles two bins and the first key of a segment's first tile always starts a run.  The
+//  kernel walks the tiles [tileLo, tileHi) (whole segments), writes every distinct key expanded to
+//  u64 = (binLo + segment) << suffixBits | suffix, and the pass-array index of its first instance.
+//  Not in place (u64 out of u32 in); the look-back chain starts at tileLo.
+
+struct __align__(16) CountTileInfo { u64 begin; u32 n; u32 seg; };       //  == sort.cu's TileInfo
+
+const int C32_ITEMS = 32;                                                //  == SortShape<0>::ITEMS
+
+__global__ void __launch_bounds__(CNT_THREADS)
+count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nTilesInGroup,
+                      u64 endIndex, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart,
+                      u64 *__restrict__ numDistinct, u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
+  __shared__ u32 warpTot[CNT_WARPS];
+  __shared__ u64 sTile, sExcl;
+
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+  const u64 rel = sTile;                                     //  tile index inside the group
+  const CountTileInfo ti = info[tileLo + rel];
+  const u64  begin   = ti.begin;
+  const u32  n       = ti.n;
+  const u32  seg     = ti.seg & 0x7fffffffu;
+  const bool segHead = (ti.seg >> 31) != 0;
+
+  u32 key[C32_ITEMS];
+  u32 heads = 0;
+  const u32 wbase = warp * 32 * C32_ITEMS;
+  u32 carry = 0;
+  if (lane == 0 && wbase < n && !(segHead && wbase == 0)) carry = keys[begin + wbase - 1];
+  unsigned short before[C32_ITEMS];
+  u32 wrun = 0;
+#pragma unroll
+  for (int i = 0; i < C32_ITEMS; i++) {
+    const u32 j = wbase + i * 32 + lane;
+    const bool in = j < n;
+    key[i] = in ? keys[begin + j] : 0;
+    u32 prev = __shfl_up_sync(0xffffffffu, key[i], 1);
+    if (lane == 0) prev = carry;
+    const bool first = segHead && (j == 0);
+    const bool head  = in && (first || key[i] != prev);
+    const u32  b     = __ballot_sync(0xffffffffu, head);
+    before[i] = (unsigned short)(wrun + __popc(b & ((1u << lane) - 1)));
+    wrun += __popc(b);
+    if (head) heads |= 1u << i;
+    carry = __shfl_sync(0xffffffffu, key[i], 31);
+  }
+
+  if (lane == 0) warpTot[warp] = wrun;
+  __syncthreads();
+
+  u32 wOff = 0, tileTot = 0;
+#pragma unroll
+  for (int w = 0; w < CNT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) wOff += c; tileTot += c; }
+
+  if (t == 0) {
+    u64 excl = 0;
+    if (rel == 0) {
+      st_volatile_u64(status + rel, MB_ST_INC | tileTot);
+    } else {
+      st_volatile_u64(status + rel, MB_ST_AGG | tileTot);
+      u64 j = rel - 1;
+      for (;;) {
+        const u64 v = ld_volatile_u64(status + j);
+        if ((v >> 62) == 0) continue;
+        excl += v & MB_ST_MASK;
+        if ((v >> 62) == 2) break;
+        j--;
+      }
+      st_volatile_u64(status + rel, MB_ST_INC | (excl + tileTot));
+    }
+    sExcl = excl;
+    if (rel + 1 == nTilesInGroup) {                          //  last tile of the group: total and sentinel
+      *numDistinct = excl + tileTot;
+      runStart[excl + tileTot] = endIndex;
+    }
+  }
+  __syncthreads();
+
+  const u64 outBase = sExcl + wOff;
+  const u64 hiBits  = (u64)(binLo + seg) << suffixBits;
+#pragma unroll
+  for (int i = 0; i < C32_ITEMS; i++) {
+    if (heads & (1u << i)) {
+      const u64 o = outBase + before[i];
+      uniq[o]     = hiBits | key[i];
+      runStart[o] = begin + wbase + i * 32 + lane;
+    }
+  }
+}
+
 //  ---- value histogram --------------------------------------------------------------------------
 
 const int VH_THREADS = 256;
@@ -206,6 +303,22 @@ cudaError_t mb_launch_count(u32 keyWords, void *dKeys, u64 nKeys, u64 *dRunStart
   u64 *counter = (u64 *)dWorkspace, *status = counter + 2;
   if (keyWords == 1) count_kernel<1><<<(unsigned)nTiles, CNT_THREADS, 0, s>>>((u64 *)dKeys, nKeys, dRunStart, dNumDistinct, status, counter);
   else               count_kernel<2><<<(unsigned)nTiles, CNT_THREADS, 0, s>>>((ulonglong2 *)dKeys, nKeys, dRunStart, dNumDistinct, status, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u64 tileLo, u64 tileHi, u64 endIndex,
+                                     u32 binLo, u32 suffixBits, u64 *dUniq, u64 *dRunStart, u64 *dNumDistinct,
+                                     void *dWorkspace, cudaStream_t s) {
+  cudaError_t e;
+  if (tileHi <= tileLo) {                                    //  empty group: D = 0, the sentinel is never read
+    if ((e = cudaMemsetAsync(dNumDistinct, 0, sizeof(u64), s)) != cudaSuccess) return e;
+    return cudaMemsetAsync(dRunStart, 0, sizeof(u64), s);
+  }
+  const u64 nTiles = tileHi - tileLo;
+  if ((e = cudaMemsetAsync(dWorkspace, 0, (2 + nTiles) * sizeof(u64), s)) != cudaSuccess) return e;
+  u64 *counter = (u64 *)dWorkspace, *status = counter + 2;
+  count_suffix32_kernel<<<(unsigned)nTiles, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nTiles, endIndex,
+                                                                binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
   return cudaGetLastError();
 }
 

@@ -112,7 +112,7 @@ extern "C" int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits
   const u32 W  = 8 * kw;
   MbSortPlan plan;
   mb_sort_plan(bits, &plan);
-  const u32 tileKeys = mb_sort_tile_keys(kw);
+  const u32 tileKeys = mb_sort_tile_keys(W);
   const u64 nTiles   = (n + tileKeys - 1) / tileKeys;
   const size_t wsBytes = mb_sort_workspace_bytes(nTiles, 1, plan.nPasses);
 
@@ -128,10 +128,37 @@ extern "C" int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits
   MB_CUDA(cudaMemcpy(a, host.data(), W * n, cudaMemcpyHostToDevice));
   MB_CUDA(cudaMemcpy(seg, segs, sizeof(segs), cudaMemcpyHostToDevice));
   int inB = 0;
-  MB_CUDA(mb_launch_sort(kw, a, b, n, seg, seg + 2, 1, nTiles, plan, ws, wsBytes, &inB, nullptr, 0, nullptr));
+  MB_CUDA(mb_launch_sort(W, a, b, n, seg, seg + 2, 1, nTiles, plan, ws, wsBytes, &inB, nullptr, 0, nullptr));
   MB_CUDA(cudaDeviceSynchronize());
   MB_CUDA(cudaMemcpy(host.data(), inB ? b : a, W * n, cudaMemcpyDeviceToHost));
   for (u64 i = 0; i < n; i++) { lo[i] = host[kw * i]; if (hi) hi[i] = host[kw * i + 1]; }
+  cudaFree(a); cudaFree(b); cudaFree(ws); cudaFree(seg);
+  return MB_OK;
+}
+
+//  K4 on u32 keys (the suffix-key path used for k <= 21).
+extern "C" int mb_dbg_sort32(uint32_t *keys, uint64_t n, uint32_t bits) {
+  mb_clear_error();
+  if (!keys && n) return mb_fail(MB_EINVAL, "mb_dbg_sort32: NULL argument");
+  if (bits > 32)  return mb_fail(MB_EINVAL, "mb_dbg_sort32: bits > 32");
+  MbSortPlan plan;
+  mb_sort_plan(bits, &plan);
+  const u32 tileKeys = mb_sort_tile_keys(4);
+  const u64 nTiles   = (n + tileKeys - 1) / tileKeys;
+  const size_t wsBytes = mb_sort_workspace_bytes(nTiles, 1, plan.nPasses);
+  void *a = nullptr, *b = nullptr, *ws = nullptr;
+  u64  *seg = nullptr;
+  MB_CUDA(cudaMalloc(&a, 4 * n + 64));
+  MB_CUDA(cudaMalloc(&b, 4 * n + 64));
+  MB_CUDA(cudaMalloc(&ws, wsBytes + 64));
+  MB_CUDA(cudaMalloc((void **)&seg, 4 * sizeof(u64)));
+  const u64 segs[4] = { 0, n, 0, nTiles };
+  MB_CUDA(cudaMemcpy(a, keys, 4 * n, cudaMemcpyHostToDevice));
+  MB_CUDA(cudaMemcpy(seg, segs, sizeof(segs), cudaMemcpyHostToDevice));
+  int inB = 0;
+  MB_CUDA(mb_launch_sort(4, a, b, n, seg, seg + 2, 1, nTiles, plan, ws, wsBytes, &inB, nullptr, 0, nullptr));
+  MB_CUDA(cudaDeviceSynchronize());
+  MB_CUDA(cudaMemcpy(keys, inB ? b : a, 4 * n, cudaMemcpyDeviceToHost));
   cudaFree(a); cudaFree(b); cudaFree(ws); cudaFree(seg);
   return MB_OK;
 }

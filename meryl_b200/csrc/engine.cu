@@ -413,7 +413,7 @@ static int runCount(mb_ctx *c) {
   //  ---- K2a: k-mers per prefix bin ---------------------------------------------------------
   MbExtractParams xp;
   xp.store = (const u32 *)c->arena;  xp.nPositions = c->nRecords * 32;
-  xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;
+  xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;  xp.suffix32 = 0;
   xp.prof = g_extractProf;
 
   tStage.start(s);
@@ -458,7 +458,7 @@ static int runCount(mb_ctx *c) {
   const u64 nBlocksTotal = (u64)1 << wP;
   size_t encBytes = std::max<size_t>(std::max<size_t>((size_t)512 << 20, R / 6), (size_t)nBlocksTotal * 200 / world);
   if (encBytes > R / 2) encBytes = R / 2;
-  const u32 tileKeys = mb_sort_tile_keys(c->keyWords);
+  u32 tileKeys = mb_sort_tile_keys(W);
   //  per key: two key buffers + tile status; fixed: ragged tiles and tables of every segment
   const double perKey = 2.0 * W + (double)MB_RADIX * 8 / tileKeys + 16.0 / tileKeys;
   const size_t fixed  = (size_t)nBins * (MB_RADIX * 8 + 16 * MB_RADIX * 8) + ((size_t)8 << 20);
@@ -468,26 +468,57 @@ static int runCount(mb_ctx *c) {
 
   std::vector<Pass> passes;
   u32 sortBits;
+  bool suffix32 = false;                                //  u32 suffix keys (k <= 21): half the bytes, twice the keys per pass
   if (world == 1) {
     //  consecutive bins, as many as fit; segments = bins, sorted on the bits below the bin
     sortBits = 2 * k - binBits;
-    Pass cur;
-    for (u32 b = 0; b < nBins; b++) {
-      if (binCount[b] > capKeys)
-        return mb_fail(MB_ENOMEM, "prefix bin %u holds %llu k-mers, more than the %llu that fit the device at once "
-                                  "(spill-and-merge is not implemented; use more GPUs)", b, (u64)binCount[b], (u64)capKeys);
-      if (cur.nKeys + binCount[b] > capKeys) {
-        cur.binHi = b;  passes.push_back(cur);
-        cur = Pass();  cur.binLo = b;
+    auto planBins = [&](u64 cap, std::vector<Pass> &out) -> int {
+      out.clear();
+      Pass cur;
+      for (u32 b = 0; b < nBins; b++) {
+        if (binCount[b] > cap) return -1;
+        if (cur.nKeys + binCount[b] > cap) {
+          cur.binHi = b;  out.push_back(cur);
+          cur = Pass();  cur.binLo = b;
+        }
+        cur.nKeys += binCount[b];
+        cur.segCount.push_back(binCount[b]);
       }
-      cur.nKeys += binCount[b];
-      cur.segCount.push_back(binCount[b]);
+      cur.binHi = nBins;
+      out.push_back(cur);
+      for (Pass &P : out) {
+        P.nLocal = P.nKeys;
+        P.encRanges.push_back(std::make_pair((u64)P.binLo * blocksPerBin, (u64)(P.binHi - P.binLo) * blocksPerBin));
+      }
+      return 0;
+    };
+
+    if (sortBits <= 32 && !c->stopAfterSort && !getenv("MB_NO_SUFFIX32")) {
+      //  u32 keys: 2 x 4 B per key + tile status; counted groups of a pass are expanded to u64 into the
+      //  spare key buffer (<= half a pass at a time) and the encode region.
+      const u32 tile32 = mb_sort_tile_keys(4);
+      const double perKey32 = 2.0 * 4 + (double)MB_RADIX * 8 / tile32 + 16.0 / tile32;
+      size_t enc32 = std::max<size_t>((size_t)4 << 30, (size_t)nBlocksTotal * 200);
+      if (enc32 > R / 3) enc32 = R / 3;
+      if (R > enc32 + fixed + ((size_t)64 << 20)) {
+        u64 cap32 = (u64)((double)(R - enc32 - fixed) / perKey32);
+        cap32 = cap32 / 8192 * 8192;
+        std::vector<Pass> p32;
+        if (planBins(cap32, p32) == 0) {
+          bool ok = true;
+          for (const Pass &P : p32) {
+            const u64 gcap = std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / 3 / 8));
+            for (u64 cnt : P.segCount) if (cnt > gcap || cnt >= ((u64)1 << 32)) ok = false;
+          }
+          if (ok) { passes.swap(p32); suffix32 = true; }
+        }
+      }
     }
-    cur.binHi = nBins;
-    passes.push_back(cur);
-    for (Pass &P : passes) {
-      P.nLocal = P.nKeys;
-      P.encRanges.push_back(std::make_pair((u64)P.binLo * blocksPerBin, (u64)(P.binHi - P.binLo) * blocksPerBin));
+    if (!suffix32 && planBins(capKeys, passes) != 0) {
+      u32 worst = 0;
+      for (u32 b = 0; b < nBins; b++) if (binCount[b] > binCount[worst]) worst = b;
+      return mb_fail(MB_ENOMEM, "prefix bin %u holds %llu k-mers, more than the %llu that fit the device at once "
+                                "(spill-and-merge is not implemented; use more GPUs)", worst, (u64)binCount[worst], (u64)capKeys);
     }
   } else {
     //  slot j of every rank = files [j*world, (j+1)*world); a pass takes q consecutive slots.
@@ -526,8 +557,11 @@ static int runCount(mb_ctx *c) {
       passes.push_back(P);
     }
   }
+  const u32 keyBytes = suffix32 ? 4 : W;
+  c->st.keyBytes = keyBytes;
   c->st.nPasses = (u32)passes.size();
 
+  tileKeys = mb_sort_tile_keys(keyBytes);
   MbSortPlan plan;
   mb_sort_plan(sortBits, &plan);
   c->st.sortPasses = plan.nPasses;
@@ -549,8 +583,8 @@ static int runCount(mb_ctx *c) {
 
     //  ---- carve this pass ------------------------------------------------------------------
     Carver pc((uint8_t *)top.base + alignUp(top.off), top.left());
-    void *bufA = pc.take((size_t)W * bufKeys + 64);
-    void *bufB = pc.take((size_t)W * bufKeys + 64);
+    void *bufA = pc.take((size_t)keyBytes * bufKeys + 64);
+    void *bufB = pc.take((size_t)keyBytes * bufKeys + 64);
 
     //  extraction layout: every bin of the pass is a contiguous run, bins ascending
     std::fill(binStart.begin(), binStart.end(), 0);
@@ -588,7 +622,7 @@ static int runCount(mb_ctx *c) {
     c->st.h2dBytes += (nBins + 1 + 2 * (nSegs + 1) + 64) * sizeof(u64);
 
     //  ---- K2/K3 ------------------------------------------------------------------------------
-    xp.binLo = P.binLo;  xp.binHi = P.binHi;
+    xp.binLo = P.binLo;  xp.binHi = P.binHi;  xp.suffix32 = suffix32 ? 1 : 0;
     tStage.start(s);
     if (P.nLocal) { MB_CUDA(mb_launch_extract(xp, bufA, dCtl->binStart, dCtl->binCursor, s)); c->st.nLaunches++; }
     tStage.stop(s);
@@ -612,7 +646,7 @@ static int runCount(mb_ctx *c) {
     //  ---- K4 ---------------------------------------------------------------------------------
     int inSpare = 0;  u32 nl = 0;
     tSortHist.start(s);
-    MB_CUDA(mb_launch_sort(c->keyWords, unsorted, spare, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inSpare, &nl, s, evAfterHist));
+    MB_CUDA(mb_launch_sort(keyBytes, unsorted, spare, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inSpare, &nl, s, evAfterHist));
     tStage.stop(s);                                   //  [evAfterHist, tStage.b] = the sweep passes
     MB_CUDA(cudaStreamSynchronize(s));
     { float m = 0;  cudaEventElapsedTime(&m, tSortHist.a, evAfterHist);  c->st.msSortHist += m;
@@ -638,142 +672,183 @@ static int runCount(mb_ctx *c) {
       continue;
     }
 
-    //  ---- K5 ---------------------------------------------------------------------------------
-    u64 *runStart = (u64 *)other;
-    tStage.start(s);
-    MB_CUDA(mb_launch_count(c->keyWords, sorted, n, runStart, &dCtl->numDistinct, ws, s));
-    u64 D = 0;
-    MB_CUDA(cudaMemcpyAsync(&D, &dCtl->numDistinct, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    MB_CUDA(mb_launch_value_histogram(runStart, &dCtl->numDistinct, n, dHistSmall, dHistBig, &dCtl->histBigN, histBigCap, dCtl->histTotals, s));
-    tStage.stop(s);
-    MB_CUDA(cudaStreamSynchronize(s));
-    c->st.msCount += tStage.ms();
-    c->st.nLaunches += n ? 2 : 0;
-    c->st.d2hBytes += 8;
-
-    if (cfg.flags & MB_FLAG_KEEP_COUNTED) {
-      const size_t at = c->cLo.size();
-      c->cLo.resize(at + D);  c->cCnt.resize(at + D);
-      if (c->keyWords == 2) c->cHi.resize(at + D);
-      std::vector<u64> rs(D + 1);
-      if (D) {
-        MB_CUDA(cudaMemcpy(rs.data(), runStart, (D + 1) * 8, cudaMemcpyDeviceToHost));
-        if (c->keyWords == 1) {
-          MB_CUDA(cudaMemcpy(c->cLo.data() + at, sorted, D * 8, cudaMemcpyDeviceToHost));
-        } else {
-          std::vector<u64> tmp(2 * D);
-          MB_CUDA(cudaMemcpy(tmp.data(), sorted, D * 16, cudaMemcpyDeviceToHost));
-          for (u64 i = 0; i < D; i++) { c->cLo[at + i] = tmp[2 * i]; c->cHi[at + i] = tmp[2 * i + 1]; }
+    //  ---- K5 + K6, one group of whole segments at a time ----------------------------------------------
+    //  Full keys (8/16 B): a single group, counted in place.  u32 suffix keys: the pass is cut into
+    //  groups of consecutive bins whose distinct k-mers, expanded to u64, fit the spare key buffer.
+    struct Group { u32 segLo, segHi; u64 keyLo, keyHi, tileLo, tileHi; std::vector<std::pair<u64, u64>> encRanges; };
+    std::vector<Group> groups;
+    if (!suffix32) {
+      Group g;  g.segLo = 0;  g.segHi = nSegs;  g.keyLo = 0;  g.keyHi = n;  g.tileLo = 0;  g.tileHi = nTiles;
+      g.encRanges = P.encRanges;
+      groups.push_back(g);
+    } else {
+      const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / 3 / 8));
+      Group g;  g.segLo = 0;  g.keyLo = 0;  g.tileLo = 0;
+      u64 have = 0;
+      for (u32 i = 0; i <= nSegs; i++) {
+        if (i == nSegs || (have > 0 && have + P.segCount[i] > gcap)) {
+          g.segHi = i;  g.keyHi = segStart[i];  g.tileHi = segTile[i];
+          g.encRanges.clear();
+          g.encRanges.push_back(std::make_pair((u64)(P.binLo + g.segLo) * blocksPerBin, (u64)(g.segHi - g.segLo) * blocksPerBin));
+          groups.push_back(g);
+          g.segLo = i;  g.keyLo = segStart[i];  g.tileLo = segTile[i];  have = 0;
         }
-        for (u64 i = 0; i < D; i++) c->cCnt[at + i] = (u32)(rs[i + 1] - rs[i]);
+        if (i < nSegs) have += P.segCount[i];
       }
     }
 
-    //  ---- K6: every block range of the pass ------------------------------------------------------
-    tStage.start(s);
-    for (size_t ri = 0; ri < P.encRanges.size(); ri++) {
-      MbEncodeParams ep;
-      ep.keys = sorted;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = c->keyWords;
-      ep.k = k;  ep.wPrefix = wP;
-      ep.blockLo = P.encRanges[ri].first;
-      ep.nBlocks = P.encRanges[ri].second;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      const Group &G = groups[gi];
+      const u64 gKeys = G.keyHi - G.keyLo;
+      Carver gc((uint8_t *)ec.base + alignUp(ec.off), ec.left());      //  per-group slice of the encode region
 
-      Carver rc((uint8_t *)ec.base + alignUp(ec.off), ec.left());
-      MbBlockMeta *dMeta = (MbBlockMeta *)rc.take(ep.nBlocks * sizeof(MbBlockMeta));
-      void *dScanTmp     = rc.take(mb_encode_scan_tmp_bytes(ep.nBlocks));
-      if (!dMeta || !dScanTmp) return mb_fail(MB_ENOMEM, "device arena too small for the block table of pass %zu (%llu blocks)", pi, (u64)ep.nBlocks);
-
-      MB_CUDA(mb_launch_encode_layout(ep, dMeta, dCtl->encTotals, dScanTmp, s));
-      c->st.nLaunches += 4;
-
-      //  chunk boundaries: first block of every file touched by this range
-      const u32 fileLo = (u32)(ep.blockLo >> blockBits), fileHi = (u32)((ep.blockLo + ep.nBlocks - 1) >> blockBits);
-      const u32 nf = fileHi - fileLo + 1;
-      std::vector<MbBlockMeta> fm(nf + 1);
-      std::vector<u64> fblk(nf + 1);
-      for (u32 i = 0; i < nf; i++) {
-        const u64 fb = (u64)(fileLo + i) << blockBits;
-        fblk[i] = fb > ep.blockLo ? fb - ep.blockLo : 0;
+      void *distinctKeys;  u64 *runStart;  u32 encKeyWords;
+      tStage.start(s);
+      if (!suffix32) {
+        distinctKeys = sorted;  runStart = (u64 *)other;  encKeyWords = c->keyWords;
+        MB_CUDA(mb_launch_count(c->keyWords, sorted, n, runStart, &dCtl->numDistinct, ws, s));
+      } else {
+        distinctKeys = other;  encKeyWords = 1;
+        runStart = (u64 *)gc.take(8 * (size_t)(gKeys + 1));
+        void *cws = gc.take(8 * (size_t)(G.tileHi - G.tileLo + 2));     //  the sort workspace still holds the tile table
+        if (!runStart || !cws) return mb_fail(MB_ENOMEM, "internal: no room for the run table of pass %zu group %zu", pi, gi);
+        MB_CUDA(mb_launch_count_suffix32((const u32 *)sorted, mb_sort_tile_info(ws, nTiles, nSegs ? nSegs : 1, plan.nPasses),
+                                         G.tileLo, G.tileHi, G.keyHi, P.binLo, 2 * k - binBits, (u64 *)other, runStart,
+                                         &dCtl->numDistinct, cws, s));
       }
-      fblk[nf] = ep.nBlocks;
-      for (u32 i = 0; i < nf; i++)
-        MB_CUDA(cudaMemcpyAsync(&fm[i], dMeta + fblk[i], sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
-      u64 encTotals[4];
-      MB_CUDA(cudaMemcpyAsync(encTotals, dCtl->encTotals, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
+      u64 D = 0;
+      MB_CUDA(cudaMemcpyAsync(&D, &dCtl->numDistinct, sizeof(u64), cudaMemcpyDeviceToHost, s));
+      MB_CUDA(mb_launch_value_histogram(runStart, &dCtl->numDistinct, gKeys, dHistSmall, dHistBig, &dCtl->histBigN, histBigCap, dCtl->histTotals, s));
+      tStage.stop(s);
       MB_CUDA(cudaStreamSynchronize(s));
-      fm[nf].outByte = encTotals[0];  fm[nf].subFirst = (u32)encTotals[1];
-      c->st.d2hBytes += nf * sizeof(MbBlockMeta) + sizeof(encTotals);
+      c->st.msCount += tStage.ms();
+      c->st.nLaunches += gKeys ? 2 : 0;
+      c->st.d2hBytes += 8;
 
-      //  greedy groups of whole files that fit what is left of the arena
-      const size_t encLeft = rc.left();
-      u32 fi = 0;
-      while (fi < nf) {
-        u32 fj = fi;
-        while (fj < nf) {
-          const size_t bytes = fm[fj + 1].outByte - fm[fi].outByte;
-          const size_t subs  = (size_t)(fm[fj + 1].subFirst - fm[fi].subFirst);
-          const size_t idx   = (size_t)(fblk[fj + 1] - fblk[fi]) * 24;
-          const size_t tot   = alignUp(bytes) + alignUp(subs * 4) + alignUp(idx) + 3 * kAlign;
-          if (tot > encLeft) break;
-          fj++;
-        }
-        if (fj == fi)
-          return mb_fail(MB_ENOMEM, "encoded data file %u of pass %zu (%llu bytes) does not fit the %zu bytes left on the device",
-                         fileLo + fi, pi, (u64)(fm[fi + 1].outByte - fm[fi].outByte), encLeft);
-
-        MbEncodeChunk ch;
-        ch.chunkFirst = fblk[fi];  ch.chunkCount = fblk[fj] - fblk[fi];
-        ch.chunkByte0 = fm[fi].outByte;  ch.chunkSub0 = fm[fi].subFirst;
-        const size_t bytes = fm[fj].outByte - fm[fi].outByte;
-        const size_t subs  = (size_t)(fm[fj].subFirst - fm[fi].subFirst);
-
-        Carver cc((uint8_t *)rc.base + alignUp(rc.off), rc.left());
-        uint8_t *dOut  = (uint8_t *)cc.take(bytes);
-        u32     *dSub  = (u32 *)cc.take(subs * 4);
-        u64     *dIdx  = (u64 *)cc.take(ch.chunkCount * 24);
-        if (!dOut || !dSub || !dIdx) return mb_fail(MB_ENOMEM, "internal: encode chunk does not fit");
-
-        MB_CUDA(cudaMemsetAsync(dOut, 0, bytes, s));
-        MB_CUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl->encTotals, dSub, dOut, dIdx, dCtl->fileBase, s));
-        c->st.nLaunches += D ? 2 : 1;
-
-        if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
-          for (u32 f = fi; f < fj; f++) {
-            const u32 file = fileLo + f;
-            const size_t fb = fm[f + 1].outByte - fm[f].outByte;
-            const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
-            std::vector<uint8_t> &iv = c->db.index[file];
-            uint8_t *dst;
-            if (c->outBuf) {                          //  append to the caller's buffer: a file's pieces arrive back to back
-              if (c->outUsed + fb > c->outCap)
-                return mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", file, fb, c->outUsed, c->outCap);
-              if (c->db.dataLen[file] == 0) c->db.dataPtr[file] = c->outBuf + c->outUsed;
-              else if (c->db.dataPtr[file] + c->db.dataLen[file] != c->outBuf + c->outUsed)
-                return mb_fail(MB_ESTATE, "internal: data file %u is not contiguous in the output buffer", file);
-              dst = c->outBuf + c->outUsed;
-              c->outUsed += fb;
-            } else {
-              std::vector<uint8_t> &dv = c->db.dataVec[file];
-              const size_t d0 = dv.size();
-              dv.resize(d0 + fb);
-              dst = dv.data() + d0;
-            }
-            c->db.dataLen[file] += fb;
-            const size_t i0 = iv.size();
-            iv.resize(i0 + ib);
-            MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
-            MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
-            c->st.d2hBytes += fb + ib;
+      if (cfg.flags & MB_FLAG_KEEP_COUNTED) {
+        const size_t at = c->cLo.size();
+        c->cLo.resize(at + D);  c->cCnt.resize(at + D);
+        if (encKeyWords == 2) c->cHi.resize(at + D);
+        std::vector<u64> rs(D + 1);
+        if (D) {
+          MB_CUDA(cudaMemcpy(rs.data(), runStart, (D + 1) * 8, cudaMemcpyDeviceToHost));
+          if (encKeyWords == 1) {
+            MB_CUDA(cudaMemcpy(c->cLo.data() + at, distinctKeys, D * 8, cudaMemcpyDeviceToHost));
+          } else {
+            std::vector<u64> tmp(2 * D);
+            MB_CUDA(cudaMemcpy(tmp.data(), distinctKeys, D * 16, cudaMemcpyDeviceToHost));
+            for (u64 i = 0; i < D; i++) { c->cLo[at + i] = tmp[2 * i]; c->cHi[at + i] = tmp[2 * i + 1]; }
           }
+          for (u64 i = 0; i < D; i++) c->cCnt[at + i] = (u32)(rs[i + 1] - rs[i]);
         }
-        MB_CUDA(cudaStreamSynchronize(s));
-        for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
-        fi = fj;
       }
+
+      //  ---- K6: every block range of the group ---------------------------------------------------------
+      tStage.start(s);
+      for (size_t ri = 0; ri < G.encRanges.size(); ri++) {
+        MbEncodeParams ep;
+        ep.keys = distinctKeys;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = encKeyWords;
+        ep.k = k;  ep.wPrefix = wP;
+        ep.blockLo = G.encRanges[ri].first;
+        ep.nBlocks = G.encRanges[ri].second;
+
+        Carver rc((uint8_t *)gc.base + alignUp(gc.off), gc.left());
+        MbBlockMeta *dMeta = (MbBlockMeta *)rc.take(ep.nBlocks * sizeof(MbBlockMeta));
+        void *dScanTmp     = rc.take(mb_encode_scan_tmp_bytes(ep.nBlocks));
+        if (!dMeta || !dScanTmp) return mb_fail(MB_ENOMEM, "device arena too small for the block table of pass %zu (%llu blocks)", pi, (u64)ep.nBlocks);
+
+        MB_CUDA(mb_launch_encode_layout(ep, dMeta, dCtl->encTotals, dScanTmp, s));
+        c->st.nLaunches += 4;
+
+        //  chunk boundaries: first block of every file touched by this range
+        const u32 fileLo = (u32)(ep.blockLo >> blockBits), fileHi = (u32)((ep.blockLo + ep.nBlocks - 1) >> blockBits);
+        const u32 nf = fileHi - fileLo + 1;
+        std::vector<MbBlockMeta> fm(nf + 1);
+        std::vector<u64> fblk(nf + 1);
+        for (u32 i = 0; i < nf; i++) {
+          const u64 fb = (u64)(fileLo + i) << blockBits;
+          fblk[i] = fb > ep.blockLo ? fb - ep.blockLo : 0;
+        }
+        fblk[nf] = ep.nBlocks;
+        for (u32 i = 0; i < nf; i++)
+          MB_CUDA(cudaMemcpyAsync(&fm[i], dMeta + fblk[i], sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
+        u64 encTotals[4];
+        MB_CUDA(cudaMemcpyAsync(encTotals, dCtl->encTotals, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
+        MB_CUDA(cudaStreamSynchronize(s));
+        fm[nf].outByte = encTotals[0];  fm[nf].subFirst = (u32)encTotals[1];
+        c->st.d2hBytes += nf * sizeof(MbBlockMeta) + sizeof(encTotals);
+
+        //  greedy groups of whole files that fit what is left of the arena
+        const size_t encLeft = rc.left();
+        u32 fi = 0;
+        while (fi < nf) {
+          u32 fj = fi;
+          while (fj < nf) {
+            const size_t bytes = fm[fj + 1].outByte - fm[fi].outByte;
+            const size_t subs  = (size_t)(fm[fj + 1].subFirst - fm[fi].subFirst);
+            const size_t idx   = (size_t)(fblk[fj + 1] - fblk[fi]) * 24;
+            const size_t tot   = alignUp(bytes) + alignUp(subs * 4) + alignUp(idx) + 3 * kAlign;
+            if (tot > encLeft) break;
+            fj++;
+          }
+          if (fj == fi)
+            return mb_fail(MB_ENOMEM, "encoded data file %u of pass %zu (%llu bytes) does not fit the %zu bytes left on the device",
+                           fileLo + fi, pi, (u64)(fm[fi + 1].outByte - fm[fi].outByte), encLeft);
+
+          MbEncodeChunk ch;
+          ch.chunkFirst = fblk[fi];  ch.chunkCount = fblk[fj] - fblk[fi];
+          ch.chunkByte0 = fm[fi].outByte;  ch.chunkSub0 = fm[fi].subFirst;
+          const size_t bytes = fm[fj].outByte - fm[fi].outByte;
+          const size_t subs  = (size_t)(fm[fj].subFirst - fm[fi].subFirst);
+
+          Carver cc((uint8_t *)rc.base + alignUp(rc.off), rc.left());
+          uint8_t *dOut  = (uint8_t *)cc.take(bytes);
+          u32     *dSub  = (u32 *)cc.take(subs * 4);
+          u64     *dIdx  = (u64 *)cc.take(ch.chunkCount * 24);
+          if (!dOut || !dSub || !dIdx) return mb_fail(MB_ENOMEM, "internal: encode chunk does not fit");
+
+          MB_CUDA(cudaMemsetAsync(dOut, 0, bytes, s));
+          MB_CUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl->encTotals, dSub, dOut, dIdx, dCtl->fileBase, s));
+          c->st.nLaunches += D ? 2 : 1;
+
+          if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
+            for (u32 f = fi; f < fj; f++) {
+              const u32 file = fileLo + f;
+              const size_t fb = fm[f + 1].outByte - fm[f].outByte;
+              const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
+              std::vector<uint8_t> &iv = c->db.index[file];
+              uint8_t *dst;
+              if (c->outBuf) {                          //  append to the caller's buffer: a file's pieces arrive back to back
+                if (c->outUsed + fb > c->outCap)
+                  return mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", file, fb, c->outUsed, c->outCap);
+                if (c->db.dataLen[file] == 0) c->db.dataPtr[file] = c->outBuf + c->outUsed;
+                else if (c->db.dataPtr[file] + c->db.dataLen[file] != c->outBuf + c->outUsed)
+                  return mb_fail(MB_ESTATE, "internal: data file %u is not contiguous in the output buffer", file);
+                dst = c->outBuf + c->outUsed;
+                c->outUsed += fb;
+              } else {
+                std::vector<uint8_t> &dv = c->db.dataVec[file];
+                const size_t d0 = dv.size();
+                dv.resize(d0 + fb);
+                dst = dv.data() + d0;
+              }
+              c->db.dataLen[file] += fb;
+              const size_t i0 = iv.size();
+              iv.resize(i0 + ib);
+              MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
+              MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
+              c->st.d2hBytes += fb + ib;
+            }
+          }
+          MB_CUDA(cudaStreamSynchronize(s));
+          for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
+          fi = fj;
+        }
+      }
+      tStage.stop(s);
+      MB_CUDA(cudaStreamSynchronize(s));
+      c->st.msEncode += tStage.ms();
     }
-    tStage.stop(s);
-    MB_CUDA(cudaStreamSynchronize(s));
-    c->st.msEncode += tStage.ms();
   }
 
   cudaEventDestroy(evAfterHist);

@@ -72,8 +72,12 @@ struct MbComm {
   u32 rank = 0, world = 1;
 };
 
+//  The communicator is created once per process and shared by every context: NCCL sets up its
+//  peer-to-peer channels lazily (seconds for the first send/recv), which must not be paid per job.
+static MbComm *g_processComm = nullptr;
+
 void mb_comm_destroy(MbComm *m) {
-  if (!m) return;
+  if (!m || m == g_processComm) return;                      //  the process-wide communicator lives until exit
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   delete m;
 }
@@ -109,12 +113,34 @@ extern "C" int mb_comm_init(mb_ctx *ctx, const uint8_t id[128]) {
   if (cfg.rank >= cfg.worldSize) return mb_fail(MB_EINVAL, "mb_comm_init: rank %u >= worldSize %u", cfg.rank, cfg.worldSize);
   MB_TRY(loadNccl());
   MB_CUDA(cudaSetDevice(mb_ctx_device(ctx)));
+  if (g_processComm) {
+    if (g_processComm->rank != cfg.rank || g_processComm->world != cfg.worldSize)
+      return mb_fail(MB_ECOMM, "mb_comm_init: this process already joined a communicator as rank %u of %u", g_processComm->rank, g_processComm->world);
+    mb_ctx_set_comm(ctx, g_processComm);
+    return MB_OK;
+  }
   ncclUniqueId_t u;
   memcpy(u.internal, id, 128);
   MbComm *m = new MbComm();
   m->rank = cfg.rank;  m->world = cfg.worldSize;
   const int r = g_nccl.CommInitRank(&m->comm, (int)cfg.worldSize, u, (int)cfg.rank);
   if (r != 0) { delete m; return mb_fail(MB_ECOMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+
+  //  Warm-up: one word to and from every peer, so the channels exist before the first timed exchange.
+  u64 *d = nullptr;
+  MB_CUDA(cudaMalloc((void **)&d, 2 * sizeof(u64) * cfg.worldSize));
+  MB_CUDA(cudaMemset(d, 0, 2 * sizeof(u64) * cfg.worldSize));
+  cudaStream_t s = mb_ctx_stream(ctx);
+  MB_NCCL(g_nccl.GroupStart());
+  for (u32 p = 0; p < cfg.worldSize; p++) {
+    MB_NCCL(g_nccl.Send(d + p, 1, kNcclUint64, (int)p, m->comm, s));
+    MB_NCCL(g_nccl.Recv(d + cfg.worldSize + p, 1, kNcclUint64, (int)p, m->comm, s));
+  }
+  MB_NCCL(g_nccl.GroupEnd());
+  MB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d);
+
+  g_processComm = m;
   mb_ctx_set_comm(ctx, m);
   return MB_OK;
 }

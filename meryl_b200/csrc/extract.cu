@@ -20,8 +20,8 @@
 //    3. k-mers of this pass's bins take their rank within (tile, bin) by a shared-memory atomic;
 //       one global atomic per (tile, bin) reserves the run in the bin's segment;
 //    4. the kept k-mers are produced again (rolling when the pass keeps most positions, direct
-//       window extraction when it keeps few) and stored straight from registers -- nothing is
-//       staged in shared memory: ~35 KB per CTA, 6 CTAs per SM.
+//       window extraction when it keeps few), placed bin-sorted in a 32 KB shared-memory stage
+//       buffer and written out as coalesced per-bin runs.
 //  The same kernel in COUNT_ONLY form is the histogram pre-pass (K2a) that sizes the segments.
 //
 //  Work: integer/bit ops, ~16-20 per position per phase; HBM traffic 0.375 B per position read +
@@ -100,20 +100,24 @@ template <int KW> struct ExtractShape;
 template <> struct ExtractShape<1> { static const int THREADS = 256; };
 template <> struct ExtractShape<2> { static const int THREADS = 128; };
 
-template <int KW>
+template <int KW, bool S32>
 struct ExtractSmem {
+  typedef typename KeyT<S32 ? 0 : KW>::type Key;             //  what is stored: full key, or its low 32 bits
   static const int    THREADS   = ExtractShape<KW>::THREADS;
   static const int    TILE_POS  = THREADS * 32;
+  static const int    STAGE_CAP = 32768 / sizeof(Key);                      //  keys staged per tile (the rest go out directly)
   static const int    REC_U32   = (THREADS + 4) * MB_STORE_REC_WORDS;       //  records incl. halo
   static const int    REC_BYTES = REC_U32 * 4;                              //  multiple of 16
   static const size_t OFF_BAR   = 0;
   static const size_t OFF_REC0  = 128;
   static const size_t OFF_REC1  = OFF_REC0 + ((REC_BYTES + 127) / 128) * 128;
   static const size_t OFF_CNT   = OFF_REC1 + ((REC_BYTES + 127) / 128) * 128;
-  static const size_t OFF_GBASE = OFF_CNT + MB_MAX_BINS * sizeof(u32);
-  static const size_t OFF_RANK  = OFF_GBASE + MB_MAX_BINS * sizeof(u64);
-  static const size_t SCATTER_BYTES = OFF_RANK + (size_t)TILE_POS * sizeof(unsigned short);
-  static const size_t COUNT_BYTES   = OFF_GBASE;
+  static const size_t OFF_BINOFF= OFF_CNT + MB_MAX_BINS * sizeof(u32);
+  static const size_t OFF_GOFS  = OFF_BINOFF + MB_MAX_BINS * sizeof(u32);
+  static const size_t OFF_RANK  = OFF_GOFS + MB_MAX_BINS * sizeof(u64);
+  static const size_t OFF_STAGE = OFF_RANK + (size_t)TILE_POS * sizeof(unsigned short);
+  static const size_t SCATTER_BYTES = OFF_STAGE + (size_t)STAGE_CAP * sizeof(Key);
+  static const size_t COUNT_BYTES   = OFF_BINOFF;
 };
 
 //  Validity of the 32 windows of length k that start at this thread's positions.
@@ -195,19 +199,28 @@ __device__ __forceinline__ u32 window_code(const Window &w, u32 pos) {
   return (u32)(word >> (62 - 2 * (pos & 31))) & 3;
 }
 
-template <int KW, bool COUNT_ONLY>
+//  Stored form of a key: itself, or (suffix32) its low 32 bits.
+__device__ __forceinline__ void to_stored(u64 k, u32 &o)                         { o = (u32)k; }
+__device__ __forceinline__ void to_stored(u64 k, u64 &o)                         { o = k; }
+__device__ __forceinline__ void to_stored(const ulonglong2 &k, ulonglong2 &o)    { o = k; }
+
+template <int KW, bool COUNT_ONLY, bool S32>
 __global__ void __launch_bounds__(ExtractShape<KW>::THREADS)
-extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
+extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict__ out,
                const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles) {
-  typedef typename KeyT<KW>::type Key;
-  typedef ExtractSmem<KW>         S;
+  typedef typename KeyT<KW>::type           Key;             //  what is computed
+  typedef typename KeyT<S32 ? 0 : KW>::type Stored;          //  what is written
+  typedef ExtractSmem<KW, S32>              S;
   extern __shared__ __align__(128) unsigned char smem[];
 
   u64            *bar   = (u64 *)(smem + S::OFF_BAR);
   u32            *rec[2] = { (u32 *)(smem + S::OFF_REC0), (u32 *)(smem + S::OFF_REC1) };
-  u32            *cnt   = (u32 *)(smem + S::OFF_CNT);
-  u64            *gbase = (u64 *)(smem + S::OFF_GBASE);
-  unsigned short *rank  = (unsigned short *)(smem + S::OFF_RANK);
+  u32            *cnt    = (u32 *)(smem + S::OFF_CNT);
+  u32            *binOff = (u32 *)(smem + S::OFF_BINOFF);
+  u64            *gofs   = (u64 *)(smem + S::OFF_GOFS);
+  unsigned short *rank   = (unsigned short *)(smem + S::OFF_RANK);
+  Stored         *stage  = (Stored *)(smem + S::OFF_STAGE);
+  __shared__ u32 sWarpSum[ExtractShape<KW>::THREADS / 32];
 
   const u32 t = threadIdx.x;
   const u32 nBins = 1u << p.binBits;
@@ -282,20 +295,41 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
       __syncthreads();
       MB_TICK(3);                                     //  everybody's phase A done
 
-      //  Reserve this tile's run in every bin segment it contributes to.
-      for (u32 b = p.binLo + t; b < p.binHi; b += blockDim.x) {
-        const u32 c = cnt[b];
-        if (c) {
-          gbase[b] = binStart[b] + atomicAdd((unsigned long long *)&binCursor[b], (unsigned long long)c);
-          cnt[b]   = 0;
+      //  Exclusive scan of the tile's bin counts (-> place of every bin's run in the stage buffer)
+      //  and, in the same sweep, one global atomic per non-empty bin to reserve its run in HBM.
+      const u32 nPassBins = p.binHi - p.binLo;
+      const u32 perThread = (nPassBins + blockDim.x - 1) / blockDim.x;
+      const u32 b0 = p.binLo + t * perThread;
+      u32 mySum = 0;
+      for (u32 i = 0; i < perThread; i++) { const u32 b = b0 + i; if (b < p.binHi) mySum += cnt[b]; }
+      u32 incl = mySum;
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= (u32)o) incl += v;
+      }
+      if ((t & 31) == 31) sWarpSum[t >> 5] = incl;
+      __syncthreads();
+      u32 run = incl - mySum, total = 0;
+      for (u32 wi = 0; wi < blockDim.x / 32; wi++) { const u32 ws = sWarpSum[wi]; if (wi < (t >> 5)) run += ws; total += ws; }
+      for (u32 i = 0; i < perThread; i++) {
+        const u32 b = b0 + i;
+        if (b < p.binHi) {
+          const u32 c = cnt[b];
+          binOff[b] = run;
+          if (c) {
+            gofs[b] = binStart[b] + atomicAdd((unsigned long long *)&binCursor[b], (unsigned long long)c) - run;
+            cnt[b]  = 0;
+          }
+          run += c;
         }
       }
       MB_TICK(4);                                     //  my reservations done
       __syncthreads();
       MB_TICK(5);                                     //  everybody's reservations done
 
-      //  Phase B: the kept k-mers go straight from registers to their reserved slots.  When the pass
-      //  keeps most positions, roll again in lock step; when it keeps few, rebuild only those.
+      //  Phase B: the kept k-mers are produced again (rolling when the pass keeps most positions,
+      //  direct window extraction when it keeps few) and placed bin-sorted in the stage buffer;
+      //  what does not fit goes straight to its reserved slot.
       if (keep) {
         if (rollAgain) {
           Roll<KW> roll;
@@ -303,7 +337,10 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
           for (u32 q = 0; q < 32; q++) {
             if ((keep << q) & 0x80000000u) {
               const Key key = roll.key(p.mode);
-              out[gbase[key_field(key, binShift, p.binBits)] + rank[t * 32 + q]] = key;
+              const u32 bin = key_field(key, binShift, p.binBits);
+              const u32 pos = binOff[bin] + rank[t * 32 + q];
+              Stored sk;  to_stored(key, sk);
+              if (pos < (u32)S::STAGE_CAP) stage[pos] = sk; else out[gofs[bin] + pos] = sk;
             }
             roll.push(window_code(w, q + p.k), p.k, rollMask);
           }
@@ -312,9 +349,28 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
             const u32 q = __clz(v);
             v &= ~(0x80000000u >> q);
             const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
-            out[gbase[key_field(key, binShift, p.binBits)] + rank[t * 32 + q]] = key;
+            const u32 bin = key_field(key, binShift, p.binBits);
+            const u32 pos = binOff[bin] + rank[t * 32 + q];
+            Stored sk;  to_stored(key, sk);
+            if (pos < (u32)S::STAGE_CAP) stage[pos] = sk; else out[gofs[bin] + pos] = sk;
           }
         }
+      }
+      __syncthreads();
+
+      //  Copy-out: consecutive threads, consecutive staged keys -> every bin's run is written coalesced.
+      const u32 nStaged = total < (u32)S::STAGE_CAP ? total : (u32)S::STAGE_CAP;
+      for (u32 j = t; j < nStaged; j += blockDim.x) {
+        const Stored sk = stage[j];
+        u32 bin;
+        if (S32) {                                    //  the bin is not in a suffix key: largest b with binOff[b] <= j
+          u32 lo = p.binLo, hi = p.binHi;
+          while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (binOff[mid] <= j) lo = mid; else hi = mid; }
+          bin = lo;
+        } else {
+          bin = key_field(sk, binShift, p.binBits);
+        }
+        out[gofs[bin] + j] = sk;
       }
     }
     MB_TICK(6);                                       //  my phase B done
@@ -334,11 +390,11 @@ extract_kernel(MbExtractParams p, typename KeyT<KW>::type *__restrict__ out,
   }
 }
 
-template <int KW, bool COUNT_ONLY>
+template <int KW, bool COUNT_ONLY, bool S32>
 cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, u64 *binCount, cudaStream_t s) {
-  typedef ExtractSmem<KW> S;
+  typedef ExtractSmem<KW, S32> S;
   const size_t smem = COUNT_ONLY ? S::COUNT_BYTES : S::SCATTER_BYTES;
-  auto kern = extract_kernel<KW, COUNT_ONLY>;
+  auto kern = extract_kernel<KW, COUNT_ONLY, S32>;
 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -356,7 +412,7 @@ cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64
   u64 grid = (u64)sms * perSm;                                   //  persistent: a multiple of the SM count
   if (grid > nTiles) grid = nTiles;
 
-  kern<<<(unsigned)grid, S::THREADS, smem, s>>>(p, (typename KeyT<KW>::type *)out, binStart, binCursor, binCount, nTiles);
+  kern<<<(unsigned)grid, S::THREADS, smem, s>>>(p, (typename KeyT<S32 ? 0 : KW>::type *)out, binStart, binCursor, binCount, nTiles);
   return cudaGetLastError();
 }
 
@@ -364,11 +420,15 @@ cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64
 
 
 cudaError_t mb_launch_bin_histogram(const MbExtractParams &p, u64 *dBinCount, cudaStream_t s) {
-  return (p.k <= 32) ? launch<1, true>(p, nullptr, nullptr, nullptr, dBinCount, s)
-                     : launch<2, true>(p, nullptr, nullptr, nullptr, dBinCount, s);
+  return (p.k <= 32) ? launch<1, true, false>(p, nullptr, nullptr, nullptr, dBinCount, s)
+                     : launch<2, true, false>(p, nullptr, nullptr, nullptr, dBinCount, s);
 }
 
 cudaError_t mb_launch_extract(const MbExtractParams &p, void *dKeys, const u64 *dBinStart, u64 *dBinCursor, cudaStream_t s) {
-  return (p.k <= 32) ? launch<1, false>(p, dKeys, dBinStart, dBinCursor, nullptr, s)
-                     : launch<2, false>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
+  if (p.suffix32) {
+    if (p.k > 32 || 2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;
+    return launch<1, false, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
+  }
+  return (p.k <= 32) ? launch<1, false, false>(p, dKeys, dBinStart, dBinCursor, nullptr, s)
+                     : launch<2, false, false>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
 }

@@ -38,9 +38,22 @@ typedef unsigned int       u32;
 
 //  ---- key helpers -----------------------------------------------------------------------
 
+//  KW = key words: 1 -> u64 (k <= 32), 2 -> 128 bits (k <= 64), 0 -> u32 SUFFIX keys: when the bits
+//  below the prefix bin fit 32 bits (2k - binBits <= 32, i.e. k <= 21) a pass stores only those;
+//  the bin is implied by the segment the key sits in.  Halves the sort traffic and doubles the
+//  number of k-mers per pass for the common k = 21.
 template <int KW> struct KeyT;
+template <> struct KeyT<0> { typedef u32        type; };
 template <> struct KeyT<1> { typedef u64        type; };
 template <> struct KeyT<2> { typedef ulonglong2 type; };     //  x = low 64 bits, y = high bits
+
+__host__ __device__ __forceinline__ u64 key_lo(u32 k)               { return k;   }
+__host__ __device__ __forceinline__ u64 key_hi(u32)                 { return 0;   }
+__host__ __device__ __forceinline__ bool key_eq(u32 a, u32 b)       { return a == b; }
+__host__ __device__ __forceinline__ u32 key_field(u32 k, u32 shift, u32 bits) {
+  return (shift >= 32 ? 0u : (k >> shift)) & ((1u << bits) - 1);
+}
+__host__ __device__ __forceinline__ u64 key_shr64(u32 k, u32 shift) { return shift >= 32 ? 0 : (u64)(k >> shift); }
 
 __host__ __device__ __forceinline__ u64 key_lo(u64 k)               { return k;   }
 __host__ __device__ __forceinline__ u64 key_hi(u64)                 { return 0;   }
@@ -98,6 +111,7 @@ struct MbExtractParams {
   u32        mode;           //  MB_MODE_*
   u32        binBits;        //  bins = top binBits bits of the k-mer
   u32        binLo, binHi;   //  this pass keeps bins in [binLo, binHi)
+  u32        suffix32;       //  1: store only the low 2k-binBits (<= 32) bits of each k-mer as u32
   u64       *prof;           //  debug: per-phase clock sums (NULL = off)
 };
 
@@ -118,9 +132,10 @@ struct MbSortPlan {
   u32  bits[16];
 };
 void        mb_sort_plan(u32 sortBits, MbSortPlan *plan);
-u32         mb_sort_tile_keys(u32 keyWords);
+u32         mb_sort_tile_keys(u32 keyBytes);                //  keyBytes: 4 (u32 suffix keys), 8 or 16
 size_t      mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses);
-cudaError_t mb_launch_sort(u32 keyWords, void *dKeysA, void *dKeysB, u64 nKeys,
+const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses);   //  device TileInfo table left by mb_launch_sort
+cudaError_t mb_launch_sort(u32 keyBytes, void *dKeysA, void *dKeysB, u64 nKeys,
                            const u64 *dSegStart, const u64 *dSegTile, u32 nSegs, u64 nTiles,
                            const MbSortPlan &plan, void *dWorkspace, size_t workspaceBytes,
                            int *resultInB, u32 *nLaunches, cudaStream_t s,
@@ -133,6 +148,12 @@ cudaError_t mb_launch_sort(u32 keyWords, void *dKeysA, void *dKeysB, u64 nKeys,
 size_t      mb_count_workspace_bytes(u64 nKeys);
 cudaError_t mb_launch_count(u32 keyWords, void *dKeys, u64 nKeys, u64 *dRunStart, u64 *dNumDistinct,
                             void *dWorkspace, cudaStream_t s);
+//  u32 suffix keys: run-length count of the sort tiles [tileLo, tileHi) (whole segments), expanding
+//  every distinct key to u64 = (binLo + segment) << suffixBits | suffix.  dUniq / dRunStart receive the
+//  group's distinct keys and the pass-array index of each run's first instance (+ a sentinel).
+cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u64 tileLo, u64 tileHi, u64 endIndex,
+                                     u32 binLo, u32 suffixBits, u64 *dUniq, u64 *dRunStart, u64 *dNumDistinct,
+                                     void *dWorkspace, cudaStream_t s);
 cudaError_t mb_launch_value_histogram(const u64 *dRunStart, const u64 *dNumDistinct, u64 nMaxDistinct,
                                       u64 *dHistSmall, u32 *dHistBig, u64 *dHistBigN, u64 histBigCap,
                                       u64 *dTotals /* [3]: unique, distinct, total */, cudaStream_t s);

@@ -25,8 +25,9 @@ const int SORT_THREADS = 256;
 const int SORT_WARPS   = SORT_THREADS / 32;
 
 template <int KW> struct SortShape;
-template <> struct SortShape<1> { static const int ITEMS = 16; };
-template <> struct SortShape<2> { static const int ITEMS = 8;  };
+template <> struct SortShape<0> { static const int ITEMS = 32; static const int MIN_CTAS = 3; };   //  u32 suffix keys: 8192 per tile
+template <> struct SortShape<1> { static const int ITEMS = 16; static const int MIN_CTAS = 4; };
+template <> struct SortShape<2> { static const int ITEMS = 8;  static const int MIN_CTAS = 4; };
 
 //  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:57] epoch (pass tag, 1..16)  [56:0] value
 #define ST_FLAG(v)    ((u32)((v) >> 62))
@@ -148,7 +149,7 @@ sort_tiles_kernel(const u64 *__restrict__ segStart, const u64 *__restrict__ segT
 //  ---- one digit pass ---------------------------------------------------------------------------
 
 template <int KW>
-__global__ void __launch_bounds__(SORT_THREADS, 4)
+__global__ void __launch_bounds__(SORT_THREADS, SortShape<KW>::MIN_CTAS)
 sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                   const TileInfo *__restrict__ info,
                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
@@ -158,10 +159,9 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   const int TILE  = SORT_THREADS * ITEMS;
 
   //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[0..7]
-  long long tk[8];
-  int ntk = 0;
-#define MB_TICK() do { if (prof && threadIdx.x == 0 && ntk < 8) tk[ntk++] = clock64(); } while (0)
-  MB_TICK();
+  long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
+#define MB_TICK(i) do { if (prof && threadIdx.x == 0) tk##i = clock64(); } while (0)
+  MB_TICK(0);
 
   __shared__ Key  stage[TILE];
   __shared__ u32  wcnt[SORT_WARPS][MB_RADIX + 1];        //  [..][256] collects the padding of a ragged tile
@@ -176,7 +176,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   for (u32 i = t; i < SORT_WARPS * (MB_RADIX + 1); i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
   __syncthreads();
 
-  MB_TICK();                                             //  1: tile id
+  MB_TICK(1);                                            //  1: tile id
   const u64 tile = sTile;
   const TileInfo ti = info[tile];
   const u64  begin   = ti.begin;
@@ -218,7 +218,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     dr[i] |= (prior + __popc(m & ltMask)) << 16;
   }
   __syncthreads();
-  MB_TICK();                                             //  2: keys loaded and ranked
+  MB_TICK(2);                                            //  2: keys loaded and ranked
 
   //  per digit: exclusive scan over the warps, tile total
   u32 myCount = 0;
@@ -251,7 +251,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     if ((dr[i] & 0xffff) < MB_RADIX)
       stage[binOff[dr[i] & 0xffff] + wcnt[warp][dr[i] & 0xffff] + (dr[i] >> 16)] = key[i];
 
-  MB_TICK();                                             //  3: tile scan + reorder issued
+  MB_TICK(3);                                            //  3: tile scan + reorder issued
   //  publish, look back over the earlier tiles of this segment.  The walk is batched: LB status
   //  words are requested at once so a walk of d tiles costs ~d/LB L2 round trips, not d.
   {
@@ -282,18 +282,23 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     }
     gofs[d] = gbase[((u64)seg * nPasses + pass) * MB_RADIX + d] + excl - binOff[d];
   }
-  MB_TICK();                                             //  4: my own look-back done
+  MB_TICK(4);                                            //  4: my own look-back done
   __syncthreads();
-  MB_TICK();                                             //  5: everybody's look-back done
+  MB_TICK(5);                                            //  5: everybody's look-back done
 
   //  digit runs to HBM
   for (u32 j = t; j < n; j += SORT_THREADS) {
     const Key k = stage[j];
     out[gofs[key_field(k, shift, bits)] + j] = k;
   }
-  MB_TICK();                                             //  6: my stores issued
+  MB_TICK(6);                                            //  6: my stores issued
   if (prof && threadIdx.x == 0) {
-    for (int i = 1; i < ntk; i++) atomicAdd((unsigned long long *)&prof[i], (unsigned long long)(tk[i] - tk[i - 1]));
+    atomicAdd((unsigned long long *)&prof[1], (unsigned long long)(tk1 - tk0));
+    atomicAdd((unsigned long long *)&prof[2], (unsigned long long)(tk2 - tk1));
+    atomicAdd((unsigned long long *)&prof[3], (unsigned long long)(tk3 - tk2));
+    atomicAdd((unsigned long long *)&prof[4], (unsigned long long)(tk4 - tk3));
+    atomicAdd((unsigned long long *)&prof[5], (unsigned long long)(tk5 - tk4));
+    atomicAdd((unsigned long long *)&prof[6], (unsigned long long)(tk6 - tk5));
     atomicAdd((unsigned long long *)&prof[0], 1ull);
   }
 #undef MB_TICK
@@ -314,8 +319,8 @@ void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
   }
 }
 
-u32 mb_sort_tile_keys(u32 keyWords) {
-  return SORT_THREADS * (keyWords == 1 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
+u32 mb_sort_tile_keys(u32 keyBytes) {
+  return SORT_THREADS * (keyBytes == 4 ? SortShape<0>::ITEMS : keyBytes == 8 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
 }
 
 //  Debug: device buffer of 8 u64 that receives per-phase clock sums of the sweep kernel (NULL = off).
@@ -325,6 +330,7 @@ void mb_sort_set_profile_buffer(u64 *dProf) { g_sortProf = dProf; }
 //  workspace: [ghist: nSegs*nPasses*256 u64][tile counters: 16 u64][guard: 4*256 u64][status: nTiles*256 u64][tile info: nTiles*16 B]
 //  (the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
 static const size_t kStatusGuard = 4 * MB_RADIX;
+const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses);
 
 size_t mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses) {
   return ((size_t)nSegs * nPasses * MB_RADIX + 16 + kStatusGuard + (size_t)nTiles * MB_RADIX) * sizeof(u64) + (size_t)nTiles * sizeof(TileInfo) + 64;
@@ -338,12 +344,18 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   typedef typename KeyT<KW>::type Key;
   *resultInB = 0;
   if (nLaunches) *nLaunches = 0;
-  if (nKeys == 0 || plan.nPasses == 0 || nTiles == 0) {
+  if (nKeys == 0 || nTiles == 0) {
     if (evAfterHist) cudaEventRecord(evAfterHist, s);
     return cudaSuccess;
   }
   if (plan.nPasses > 16) return cudaErrorInvalidValue;
   if (workspaceBytes < mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses)) return cudaErrorInvalidValue;
+  if (plan.nPasses == 0) {                               //  nothing to sort, but the tile table is part of the contract
+    TileInfo *ti = (TileInfo *)mb_sort_tile_info(dWorkspace, nTiles, nSegs, 0);
+    sort_tiles_kernel<<<(unsigned)((nTiles + 255) / 256), 256, 0, s>>>(dSegStart, dSegTile, nSegs, nTiles, SORT_THREADS * SortShape<KW>::ITEMS, ti);
+    if (evAfterHist) cudaEventRecord(evAfterHist, s);
+    return cudaGetLastError();
+  }
 
   u64 *ghist   = (u64 *)dWorkspace;
   u64 *counter = ghist + (size_t)nSegs * plan.nPasses * MB_RADIX;
@@ -381,11 +393,20 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   return cudaSuccess;
 }
 
-cudaError_t mb_launch_sort(u32 keyWords, void *dKeysA, void *dKeysB, u64 nKeys,
+const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses) {
+  u64 *ghist   = (u64 *)dWorkspace;
+  u64 *counter = ghist + (size_t)nSegs * nPasses * MB_RADIX;
+  u64 *status  = counter + 16 + kStatusGuard;
+  return (const void *)(((uintptr_t)(status + (size_t)nTiles * MB_RADIX) + 15) & ~(uintptr_t)15);
+}
+
+cudaError_t mb_launch_sort(u32 keyBytes, void *dKeysA, void *dKeysB, u64 nKeys,
                            const u64 *dSegStart, const u64 *dSegTile, u32 nSegs, u64 nTiles,
                            const MbSortPlan &plan, void *dWorkspace, size_t workspaceBytes,
                            int *resultInB, u32 *nLaunches, cudaStream_t s, cudaEvent_t evAfterHist) {
-  return keyWords == 1
+  if (keyBytes == 4)
+    return sort_impl<0>(dKeysA, dKeysB, nKeys, dSegStart, dSegTile, nSegs, nTiles, plan, dWorkspace, workspaceBytes, resultInB, nLaunches, s, evAfterHist);
+  return keyBytes == 8
     ? sort_impl<1>(dKeysA, dKeysB, nKeys, dSegStart, dSegTile, nSegs, nTiles, plan, dWorkspace, workspaceBytes, resultInB, nLaunches, s, evAfterHist)
     : sort_impl<2>(dKeysA, dKeysB, nKeys, dSegStart, dSegTile, nSegs, nTiles, plan, dWorkspace, workspaceBytes, resultInB, nLaunches, s, evAfterHist);
 }

@@ -276,3 +276,26 @@ def test_output_buffer_images_match_internal_images(tmp_path):
         with pytest.raises(mb.MerylB200Error) as e:
             c.count()
         assert e.value.code == -3
+
+
+def test_suffix32_path_equals_full_key_path(tmp_path, monkeypatch):
+    """k <= 21 on one GPU stores 32-bit suffix keys (half the sort traffic); MB_NO_SUFFIX32 forces the
+    64-bit path.  Both must give the same bytes, also with several passes and several count groups."""
+    data = synth.reads_fastq_bytes(400_000, 150_000, 150, 0.002, 91)
+    dbs = []
+    for env, ws in (("", 0), ("1", 0), ("", 3 << 28), ("1", 3 << 28)):
+        if env:
+            monkeypatch.setenv("MB_NO_SUFFIX32", env)
+        else:
+            monkeypatch.delenv("MB_NO_SUFFIX32", raising=False)
+        out = str(tmp_path / ("db%d" % len(dbs)))
+        with mb.Counter(21, 13, workspace_bytes=ws) as c:
+            c.add_file_bytes(data)
+            c.count()
+            st = c.stats()
+            c.write_db(out)
+        assert st.keyBytes == (8 if env else 4)
+        dbs.append((out, st.nPasses))
+    for out, _ in dbs[1:]:
+        util.assert_same_db(dbs[0][0], out)
+    assert dbs[2][1] > 1 and dbs[3][1] > 1

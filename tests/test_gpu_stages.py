@@ -88,6 +88,23 @@ def test_sort_u64(n, bits):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n", [0, 1, 33, 8191, 8192, 8193, 100_000, 3_000_001])
+@pytest.mark.parametrize("bits", [1, 8, 9, 22, 32])
+def test_sort_u32(n, bits):
+    rng = np.random.default_rng(n * 7 + bits)
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if bits < 32:
+        keys &= np.uint32((1 << bits) - 1)
+    if n > 10:
+        keys[: n // 3] = keys[n // 2]
+    ref = np.sort(keys)
+    got = keys.copy()
+    L = mb.lib()
+    rc = L.mb_dbg_sort32(got.ctypes.data, n, bits)
+    assert rc == 0, L.mb_last_error().decode()
+    assert np.array_equal(got, ref)
+
+
 @pytest.mark.parametrize("n", [0, 1, 2047, 2048, 2049, 300_001])
 @pytest.mark.parametrize("bits", [65, 70, 92, 118, 128])
 def test_sort_u128(n, bits):
