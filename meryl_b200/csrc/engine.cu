@@ -745,6 +745,7 @@ static int runCount(mb_ctx *c) {
 
       //  ---- K6: every block range of the group ---------------------------------------------------------
       tStage.start(s);
+      MB_CUDA(cudaMemcpyAsync(dCtl->fileBase, fileBase.data(), 64 * sizeof(u64), cudaMemcpyHostToDevice, s));   //  bytes already emitted per file
       for (size_t ri = 0; ri < G.encRanges.size(); ri++) {
         MbEncodeParams ep;
         ep.keys = distinctKeys;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = encKeyWords;

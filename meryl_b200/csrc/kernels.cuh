@@ -33,8 +33,8 @@ typedef unsigned int       u32;
 #define MB_STORE_PAD_RECORDS 1024       //  zero records that must follow the last record of the store
 #define MB_STORE_REC_WORDS   3          //  u32 words per 32-position record
 #define MB_MAX_BINS          1024       //  2^10 prefix bins
-#define MB_RADIX_BITS        8
-#define MB_RADIX             256
+#define MB_RADIX_BITS        6          //  LSD digit width: 64 digits = 32 words of two 16-bit private counters per thread
+#define MB_RADIX             64
 
 //  ---- key helpers -----------------------------------------------------------------------
 
@@ -128,8 +128,8 @@ cudaError_t mb_launch_extract(const MbExtractParams &p, void *dKeys, const u64 *
 //  Result is left in dKeysA if the number of digit passes is even, else in dKeysB; *resultInB says which.
 struct MbSortPlan {
   u32  nPasses;
-  u32  shift[16];
-  u32  bits[16];
+  u32  shift[24];
+  u32  bits[24];
 };
 void        mb_sort_plan(u32 sortBits, MbSortPlan *plan);
 u32         mb_sort_tile_keys(u32 keyBytes);                //  keyBytes: 4 (u32 suffix keys), 8 or 16

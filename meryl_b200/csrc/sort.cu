@@ -4,18 +4,29 @@
 //  Replaces std::sort of each prefix bucket (merylCountArray::countSingleKmers,
 //  src/meryl/merylCountArray.C:324-330).  The reference sorts 2^wPrefix small buckets on the CPU;
 //  here one launch per digit sorts ALL prefix-bin segments of a pass at once: a segment is the
-//  run of keys sharing their top binBits bits (put there by the extraction scatter), and only the
-//  remaining 2k-binBits low bits are sorted, 8 (or fewer) bits per pass.
+//  run of keys sharing their top bits (put there by the extraction scatter), and only the
+//  remaining low bits are sorted, MB_RADIX_BITS (6) or fewer bits per pass.
 //
+//   sort_tiles_kernel   one 16-byte descriptor per tile (first key, count, segment, first-of-segment)
 //   sort_hist_kernel    one read of the keys: per (segment, pass, digit) counts
 //   sort_scan_kernel    exclusive scan over digits -> first output index of every (segment, pass, digit)
-//   sort_sweep_kernel   per pass: tile = 256 threads x ITEMS keys.  Keys are ranked inside the tile
-//                       (warp match_any multisplit, stable), the tile publishes its digit counts,
-//                       looks back over the earlier tiles OF ITS SEGMENT for its exclusive prefix,
-//                       reorders the keys by digit in shared memory and writes digit runs to HBM.
+//   sort_sweep_kernel   per pass: tile = 256 threads x ITEMS keys
+//       1. coalesced (warp-striped) load, transposed through shared memory so that every thread
+//          owns ITEMS CONSECUTIVE keys -- rank order == memory order, which LSD needs (stable);
+//       2. rank by PRIVATE counters: thread t bumps its own 16-bit counter of the key's digit
+//          (two digits per 32-bit word, no atomics, no warp votes), a raking scan over the
+//          32 x 256 packed counters turns them into tile-wide positions -- ~25 instructions per 32
+//          keys, against ~95 for a match/ballot multisplit, which is what lets the kernel approach
+//          the HBM roofline on B200 (0.17 warp-instructions per byte at peak bandwidth);
+//       3. the tile publishes its 64 digit counts, and resolves its exclusive prefix by a batched
+//          decoupled look-back over the earlier tiles OF ITS SEGMENT (status words carry a pass
+//          epoch, so the table is cleared once per sort);
+//       4. keys are placed digit-sorted in shared memory and leave as coalesced digit runs.
 //
-//  Algorithmic HBM bytes per key: hist 1*W, each sweep pass 2*W (W = 8 or 16 bytes), plus the tile
-//  status traffic (2 KB per tile written, >= 2 KB read).  Bound: HBM bandwidth.
+//  Algorithmic HBM bytes per key: hist 1*W, each sweep pass 2*W (W = 4, 8 or 16 bytes), plus the
+//  tile status (512 B per tile written twice, read >= once).  Bound: HBM bandwidth.
+
+#include <string.h>
 
 #include "kernels.cuh"
 
@@ -23,13 +34,14 @@ namespace {
 
 const int SORT_THREADS = 256;
 const int SORT_WARPS   = SORT_THREADS / 32;
+const int SORT_MAX_PASSES = 24;
 
 template <int KW> struct SortShape;
-template <> struct SortShape<0> { static const int ITEMS = 32; static const int MIN_CTAS = 3; };   //  u32 suffix keys: 8192 per tile
-template <> struct SortShape<1> { static const int ITEMS = 16; static const int MIN_CTAS = 4; };
-template <> struct SortShape<2> { static const int ITEMS = 8;  static const int MIN_CTAS = 4; };
+template <> struct SortShape<0> { static const int ITEMS = 32; };      //  u32 suffix keys: 8192 per tile
+template <> struct SortShape<1> { static const int ITEMS = 16; };      //  u64: 4096 per tile
+template <> struct SortShape<2> { static const int ITEMS = 8;  };      //  128 bit: 2048 per tile
 
-//  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:57] epoch (pass tag, 1..16)  [56:0] value
+//  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:57] epoch (pass tag, 1..24)  [56:0] value
 #define ST_FLAG(v)    ((u32)((v) >> 62))
 #define ST_EPOCH(v)   ((u32)(((v) >> 57) & 31))
 #define ST_VALUE(v)   ((v) & ((1ull << 57) - 1))
@@ -45,7 +57,30 @@ __device__ __forceinline__ u32 find_segment(const u64 *__restrict__ tileStart, u
   return lo;
 }
 
-struct SortPassTable { u32 nPasses; u32 shift[16]; u32 bits[16]; };
+struct SortPassTable { u32 nPasses; u32 shift[SORT_MAX_PASSES]; u32 bits[SORT_MAX_PASSES]; };
+
+//  ---- tile descriptors: one 16-byte record per tile, so a sweep CTA starts with ONE dependent load --
+
+struct __align__(16) TileInfo {
+  u64 begin;                                 //  index of the tile's first key
+  u32 n;                                     //  keys in the tile
+  u32 seg;                                   //  segment; bit 31: first tile of its segment
+};
+
+__global__ void __launch_bounds__(256)
+sort_tiles_kernel(const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
+                  u32 tileKeys, TileInfo *__restrict__ info) {
+  const u64 tile = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= nTiles) return;
+  const u32 seg   = find_segment(segTile, nSegs, tile);
+  const u64 first = segTile[seg];
+  const u64 begin = segStart[seg] + (tile - first) * tileKeys;
+  u64 n = segStart[seg + 1] - begin;
+  if (n > tileKeys) n = tileKeys;
+  TileInfo t;
+  t.begin = begin;  t.n = (u32)n;  t.seg = seg | (tile == first ? 0x80000000u : 0u);
+  info[tile] = t;
+}
 
 //  ---- histogram ------------------------------------------------------------------------------
 
@@ -58,7 +93,7 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
                  SortPassTable pt, u64 *__restrict__ ghist) {
   typedef typename KeyT<KW>::type Key;
   const int TILE = SORT_THREADS * SortShape<KW>::ITEMS;
-  __shared__ u32 sh[16 * MB_RADIX];
+  __shared__ u32 sh[SORT_MAX_PASSES * MB_RADIX];
 
   const u32 t = threadIdx.x;
   for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) sh[i] = 0;
@@ -123,60 +158,58 @@ sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 
   h[d] = segStart[seg] + base + incl - c;
 }
 
-//  ---- tile descriptors: one 16-byte record per tile, so a sweep CTA starts with ONE dependent load --
-
-struct __align__(16) TileInfo {
-  u64 begin;
-  u32 n;
-  u32 seg;                                   //  bit 31: first tile of its segment
-};
-
-__global__ void __launch_bounds__(256)
-sort_tiles_kernel(const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
-                  u32 tileKeys, TileInfo *__restrict__ info) {
-  const u64 tile = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tile >= nTiles) return;
-  const u32 seg   = find_segment(segTile, nSegs, tile);
-  const u64 first = segTile[seg];
-  const u64 begin = segStart[seg] + (tile - first) * tileKeys;
-  u64 n = segStart[seg + 1] - begin;
-  if (n > tileKeys) n = tileKeys;
-  TileInfo t;
-  t.begin = begin;  t.n = (u32)n;  t.seg = seg | (tile == first ? 0x80000000u : 0u);
-  info[tile] = t;
-}
-
 //  ---- one digit pass ---------------------------------------------------------------------------
 
+//  Shared buffer, used in turn as (a) the striped->blocked transpose area, (b) the private digit
+//  counters, (c) the digit-sorted stage.  Sizes in bytes, for TILE keys of KB bytes:
+//    transpose / stage : TILE*KB, plus one key of padding per 128 bytes (bank-conflict-free blocked reads)
+//    counters          : (MB_RADIX/2) lanes x 256 threads x 4 B = 32 KB, plus one word of padding per 32
+template <int KW> struct SweepSmem {
+  typedef typename KeyT<KW>::type Key;
+  static const int TILE     = SORT_THREADS * SortShape<KW>::ITEMS;
+  static const int PAD_EVERY= 128 / sizeof(Key);                               //  keys between two padding keys
+  static const int XPOSE    = (TILE + TILE / PAD_EVERY) * sizeof(Key);
+  static const int LANES    = MB_RADIX / 2;                                     //  two 16-bit counters per word
+  static const int CWORDS   = LANES * SORT_THREADS;
+  static const int COUNTERS = (CWORDS + CWORDS / 32) * 4;
+  static const int BYTES    = XPOSE > COUNTERS ? XPOSE : COUNTERS;
+};
+
+__device__ __forceinline__ void key_zero(u32 &k)        { k = 0; }
+__device__ __forceinline__ void key_zero(u64 &k)        { k = 0; }
+__device__ __forceinline__ void key_zero(ulonglong2 &k) { k.x = 0; k.y = 0; }
+
 template <int KW>
-__global__ void __launch_bounds__(SORT_THREADS, SortShape<KW>::MIN_CTAS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                   const TileInfo *__restrict__ info,
                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch, u64 *__restrict__ prof) {
   typedef typename KeyT<KW>::type Key;
+  typedef SweepSmem<KW>           S;
   const int ITEMS = SortShape<KW>::ITEMS;
-  const int TILE  = SORT_THREADS * ITEMS;
 
-  //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[0..7]
+  //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[1..6]
   long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
 #define MB_TICK(i) do { if (prof && threadIdx.x == 0) tk##i = clock64(); } while (0)
   MB_TICK(0);
 
-  __shared__ Key  stage[TILE];
-  __shared__ u32  wcnt[SORT_WARPS][MB_RADIX + 1];        //  [..][256] collects the padding of a ragged tile
-  __shared__ u32  binOff[MB_RADIX];
+  __shared__ __align__(16) unsigned char buf[S::BYTES];
+  __shared__ u32  binOff[MB_RADIX + 1];
   __shared__ u64  gofs[MB_RADIX];
   __shared__ u32  warpTot[SORT_WARPS];
   __shared__ u64  sTile;
 
+  Key *xpose    = (Key *)buf;
+  u32 *counters = (u32 *)buf;
+  Key *stage    = (Key *)buf;
+
   const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
   if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
-  for (u32 i = t; i < SORT_WARPS * (MB_RADIX + 1); i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
   __syncthreads();
-
   MB_TICK(1);                                            //  1: tile id
+
   const u64 tile = sTile;
   const TileInfo ti = info[tile];
   const u64  begin   = ti.begin;
@@ -184,79 +217,105 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   const u32  seg     = ti.seg & 0x7fffffffu;
   const bool isFirst = (ti.seg >> 31) != 0;
 
-  //  load (warp-striped: consecutive lanes, consecutive keys) and rank
-  //  dr[i]: digit in the low 16 bits (MB_RADIX for the padding of a ragged tile), rank within
-  //  (warp, digit) in the high 16 bits.
+  //  1. load striped (coalesced), transpose to blocked: thread t ends up with keys [t*ITEMS, (t+1)*ITEMS)
   Key key[ITEMS];
-  u32 dr[ITEMS];
-  const u32 wbase = warp * 32 * ITEMS;
+  {
+    const u32 wbase = warp * 32 * ITEMS;                 //  the warp's slice is private: only __syncwarp needed
 #pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    const u32 j = wbase + i * 32 + lane;
-    if (j < n) { key[i] = in[begin + j]; dr[i] = key_field(key[i], shift, bits); }
-    else       { dr[i] = MB_RADIX; }
-  }
-
-  //  Peers holding the same digit: one ballot per digit bit (plus one for the padding flag) --
-  //  cheaper than match.any.  Each warp owns its counter row, so the running count per digit is a
-  //  plain shared-memory read (broadcast inside the peer group) and one write by the group's leader.
-  const u32 ltMask = (1u << lane) - 1;
-  const u32 rbits  = bits + 1;                           //  digit bits + the "padding" bit (MB_RADIX)
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    u32 m = 0xffffffffu;
-    for (u32 b = 0; b < rbits; b++) {
-      const u32 bitpos = (b < bits) ? b : MB_RADIX_BITS; //  the padding flag is bit 8 of MB_RADIX
-      const u32 bit = (dr[i] >> bitpos) & 1;
-      const u32 bal = __ballot_sync(0xffffffffu, bit);
-      m &= bit ? bal : ~bal;
+    for (int i = 0; i < ITEMS; i++) {
+      const u32 j = wbase + i * 32 + lane;
+      Key k;
+      if (j < n) k = in[begin + j]; else key_zero(k);
+      xpose[j + j / S::PAD_EVERY] = k;
     }
-    const u32 prior = wcnt[warp][dr[i]];
     __syncwarp();
-    if ((m & ltMask) == 0) wcnt[warp][dr[i]] = prior + __popc(m);      //  lowest lane of the group
-    __syncwarp();
-    dr[i] |= (prior + __popc(m & ltMask)) << 16;
-  }
-  __syncthreads();
-  MB_TICK(2);                                            //  2: keys loaded and ranked
-
-  //  per digit: exclusive scan over the warps, tile total
-  u32 myCount = 0;
-  {
-    const u32 d = t;                                    //  SORT_THREADS == MB_RADIX
-    u32 run = 0;
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) { const u32 c = wcnt[w][d]; wcnt[w][d] = run; run += c; }
-    myCount = run;
+    for (int i = 0; i < ITEMS; i++) {
+      const u32 j = t * ITEMS + i;
+      key[i] = xpose[j + j / S::PAD_EVERY];
+    }
   }
+  __syncthreads();                                       //  everybody has its keys: the buffer becomes the counters
 
-  //  exclusive scan of the tile's digit counts -> position of each digit run in the stage buffer
-  u32 incl = myCount;
-  for (int o = 1; o < 32; o <<= 1) {
-    const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (u32)o) incl += v;
-  }
-  if (lane == 31) warpTot[warp] = incl;
+  //  2. private counters.  Digit d lives in word (d & 31) of my column, half (d >> 5).
+  for (u32 i = t; i < (u32)(S::CWORDS + S::CWORDS / 32); i += SORT_THREADS) counters[i] = 0;
   __syncthreads();
+
+  const u32 myFirst = t * ITEMS;                         //  my keys are tile positions [myFirst, myFirst + ITEMS)
+  unsigned short prior[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    prior[i] = 0;
+    if (myFirst + i < n) {
+      const u32 d    = key_field(key[i], shift, bits);
+      const u32 lin  = (d & 31) * SORT_THREADS + t;      //  (word-of-digit, thread): digit-major within each half
+      u32 *cp        = &counters[lin + (lin >> 5)];
+      const u32 sh16 = (d >> 5) * 16;
+      const u32 wv   = *cp;
+      prior[i] = (unsigned short)((wv >> sh16) & 0xffff);
+      *cp = wv + (1u << sh16);
+    }
+  }
+  __syncthreads();
+
+  //  raking scan over the CWORDS packed words: thread t owns the 32 consecutive words [32t, 32t+32)
+  u32 tileLow = 0;                                       //  keys whose digit is < 32 (low halves)
   {
-    u32 base = 0;
-    for (u32 w = 0; w < warp; w++) base += warpTot[w];
-    binOff[t] = base + incl - myCount;
+    u32 *seg32 = &counters[t * 33];
+    u32 sum = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) sum += seg32[j];
+    u32 incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32)o) incl += v;
+    }
+    if (lane == 31) warpTot[warp] = incl;
+    __syncthreads();
+    u32 run = incl - sum, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) run += c; tot += c; }
+    tileLow = tot & 0xffff;
+#pragma unroll
+    for (int j = 0; j < 32; j++) { const u32 c = seg32[j]; seg32[j] = run; run += c; }
   }
   __syncthreads();
+  MB_TICK(2);                                            //  2: keys loaded, counted, scanned
 
-  //  reorder in shared memory (needs only tile-local offsets; frees the key registers before the wait)
+  //  tile position of every key; start of every digit's run
+  //  (prior[] is overwritten in place by the final position; 0xffff marks the padding of a ragged tile)
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    if (myFirst + i < n) {
+      const u32 d   = key_field(key[i], shift, bits);
+      const u32 lin = (d & 31) * SORT_THREADS + t;
+      const u32 wv  = counters[lin + (lin >> 5)];
+      const u32 hi  = d >> 5;
+      prior[i] = (unsigned short)(((wv >> (hi * 16)) & 0xffff) + (hi ? tileLow : 0) + prior[i]);
+    } else {
+      prior[i] = 0xffff;
+    }
+  }
+  if (t < MB_RADIX) {
+    const u32 lin = (t & 31) * SORT_THREADS;             //  thread 0's slot of digit t == first key of that digit
+    const u32 wv  = counters[lin + (lin >> 5)];
+    const u32 hi  = t >> 5;
+    binOff[t] = ((wv >> (hi * 16)) & 0xffff) + (hi ? tileLow : 0);
+  }
+  if (t == 0) binOff[MB_RADIX] = n;
+  __syncthreads();                                       //  counters fully consumed: the buffer becomes the stage
+
+  //  4a. digit-sorted order in shared memory
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
-    if ((dr[i] & 0xffff) < MB_RADIX)
-      stage[binOff[dr[i] & 0xffff] + wcnt[warp][dr[i] & 0xffff] + (dr[i] >> 16)] = key[i];
+    if (prior[i] != 0xffff) stage[prior[i]] = key[i];
+  MB_TICK(3);                                            //  3: reorder issued
 
-  MB_TICK(3);                                            //  3: tile scan + reorder issued
-  //  publish, look back over the earlier tiles of this segment.  The walk is batched: LB status
-  //  words are requested at once so a walk of d tiles costs ~d/LB L2 round trips, not d.
-  {
+  //  3. publish, look back over the earlier tiles of this segment (batched: LB status words per round trip)
+  if (t < MB_RADIX) {
     const int LB = 4;
     const u32 d = t;
+    const u32 myCount = binOff[d + 1] - binOff[d];
     u64 *mine = status + tile * MB_RADIX + d;
     u64 excl = 0;
     if (isFirst) {
@@ -286,7 +345,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   __syncthreads();
   MB_TICK(5);                                            //  5: everybody's look-back done
 
-  //  digit runs to HBM
+  //  4b. digit runs to HBM
   for (u32 j = t; j < n; j += SORT_THREADS) {
     const Key k = stage[j];
     out[gofs[key_field(k, shift, bits)] + j] = k;
@@ -327,13 +386,20 @@ u32 mb_sort_tile_keys(u32 keyBytes) {
 static u64 *g_sortProf = nullptr;
 void mb_sort_set_profile_buffer(u64 *dProf) { g_sortProf = dProf; }
 
-//  workspace: [ghist: nSegs*nPasses*256 u64][tile counters: 16 u64][guard: 4*256 u64][status: nTiles*256 u64][tile info: nTiles*16 B]
-//  (the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
+//  workspace: [ghist: nSegs*nPasses*R u64][tile counters: 32 u64][guard: 4*R u64][status: nTiles*R u64][tile info: nTiles*16 B]
+//  (R = MB_RADIX; the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
 static const size_t kStatusGuard = 4 * MB_RADIX;
-const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses);
+static const size_t kCounters    = 32;
 
 size_t mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses) {
-  return ((size_t)nSegs * nPasses * MB_RADIX + 16 + kStatusGuard + (size_t)nTiles * MB_RADIX) * sizeof(u64) + (size_t)nTiles * sizeof(TileInfo) + 64;
+  return ((size_t)nSegs * nPasses * MB_RADIX + kCounters + kStatusGuard + (size_t)nTiles * MB_RADIX) * sizeof(u64) + (size_t)nTiles * sizeof(TileInfo) + 64;
+}
+
+const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses) {
+  u64 *ghist   = (u64 *)dWorkspace;
+  u64 *counter = ghist + (size_t)nSegs * nPasses * MB_RADIX;
+  u64 *status  = counter + kCounters + kStatusGuard;
+  return (const void *)(((uintptr_t)(status + (size_t)nTiles * MB_RADIX) + 15) & ~(uintptr_t)15);
 }
 
 template <int KW>
@@ -348,37 +414,37 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     if (evAfterHist) cudaEventRecord(evAfterHist, s);
     return cudaSuccess;
   }
-  if (plan.nPasses > 16) return cudaErrorInvalidValue;
+  if (plan.nPasses > SORT_MAX_PASSES) return cudaErrorInvalidValue;
   if (workspaceBytes < mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses)) return cudaErrorInvalidValue;
-  if (plan.nPasses == 0) {                               //  nothing to sort, but the tile table is part of the contract
-    TileInfo *ti = (TileInfo *)mb_sort_tile_info(dWorkspace, nTiles, nSegs, 0);
-    sort_tiles_kernel<<<(unsigned)((nTiles + 255) / 256), 256, 0, s>>>(dSegStart, dSegTile, nSegs, nTiles, SORT_THREADS * SortShape<KW>::ITEMS, ti);
-    if (evAfterHist) cudaEventRecord(evAfterHist, s);
-    return cudaGetLastError();
-  }
 
   u64 *ghist   = (u64 *)dWorkspace;
   u64 *counter = ghist + (size_t)nSegs * plan.nPasses * MB_RADIX;
-  u64 *status  = counter + 16 + kStatusGuard;
-  TileInfo *info = (TileInfo *)(((uintptr_t)(status + (size_t)nTiles * MB_RADIX) + 15) & ~(uintptr_t)15);
+  u64 *status  = counter + kCounters + kStatusGuard;
+  TileInfo *info = (TileInfo *)mb_sort_tile_info(dWorkspace, nTiles, nSegs, plan.nPasses);
+  const u32 tileKeys = SORT_THREADS * SortShape<KW>::ITEMS;
+
+  sort_tiles_kernel<<<(unsigned)((nTiles + 255) / 256), 256, 0, s>>>(dSegStart, dSegTile, nSegs, nTiles, tileKeys, info);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (nLaunches) *nLaunches += 1;
+  if (plan.nPasses == 0) {                               //  nothing to sort, but the tile table is part of the contract
+    if (evAfterHist) cudaEventRecord(evAfterHist, s);
+    return cudaSuccess;
+  }
 
   const size_t zeroBytes = (size_t)((uint8_t *)(status + (size_t)nTiles * MB_RADIX) - (uint8_t *)dWorkspace);
-  cudaError_t e = cudaMemsetAsync(dWorkspace, 0, zeroBytes, s);
-  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(dWorkspace, 0, zeroBytes, s)) != cudaSuccess) return e;
 
   SortPassTable pt;
   pt.nPasses = plan.nPasses;
-  for (u32 p = 0; p < 16; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
+  for (u32 p = 0; p < SORT_MAX_PASSES; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
 
-  const u32 tileKeys = SORT_THREADS * SortShape<KW>::ITEMS;
-  sort_tiles_kernel<<<(unsigned)((nTiles + 255) / 256), 256, 0, s>>>(dSegStart, dSegTile, nSegs, nTiles, tileKeys, info);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
   sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, ghist);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   sort_scan_kernel<<<dim3(nSegs, plan.nPasses), MB_RADIX, 0, s>>>(ghist, dSegStart, plan.nPasses);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (nLaunches) *nLaunches += 3;
+  if (nLaunches) *nLaunches += 2;
   if (evAfterHist) cudaEventRecord(evAfterHist, s);
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
@@ -391,13 +457,6 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   }
   *resultInB = (plan.nPasses & 1);
   return cudaSuccess;
-}
-
-const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses) {
-  u64 *ghist   = (u64 *)dWorkspace;
-  u64 *counter = ghist + (size_t)nSegs * nPasses * MB_RADIX;
-  u64 *status  = counter + 16 + kStatusGuard;
-  return (const void *)(((uintptr_t)(status + (size_t)nTiles * MB_RADIX) + 15) & ~(uintptr_t)15);
 }
 
 cudaError_t mb_launch_sort(u32 keyBytes, void *dKeysA, void *dKeysB, u64 nKeys,
