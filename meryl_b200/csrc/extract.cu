@@ -116,7 +116,8 @@ struct ExtractSmem {
   static const size_t OFF_GOFS  = OFF_BINOFF + MB_MAX_BINS * sizeof(u32);
   static const size_t OFF_RANK  = OFF_GOFS + MB_MAX_BINS * sizeof(u64);
   static const size_t OFF_STAGE = OFF_RANK + (size_t)TILE_POS * sizeof(unsigned short);
-  static const size_t SCATTER_BYTES = OFF_STAGE + (size_t)STAGE_CAP * sizeof(Key);
+  static const size_t OFF_SBIN  = OFF_STAGE + (size_t)STAGE_CAP * sizeof(Key);          //  suffix keys do not carry their bin:
+  static const size_t SCATTER_BYTES = OFF_SBIN + (S32 ? (size_t)STAGE_CAP * sizeof(unsigned short) : 0);   //  it is staged next to them
   static const size_t COUNT_BYTES   = OFF_BINOFF;
 };
 
@@ -220,6 +221,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   u64            *gofs   = (u64 *)(smem + S::OFF_GOFS);
   unsigned short *rank   = (unsigned short *)(smem + S::OFF_RANK);
   Stored         *stage  = (Stored *)(smem + S::OFF_STAGE);
+  unsigned short *sbin   = (unsigned short *)(smem + S::OFF_SBIN);
   __shared__ u32 sWarpSum[ExtractShape<KW>::THREADS / 32];
 
   const u32 t = threadIdx.x;
@@ -340,7 +342,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
               const u32 bin = key_field(key, binShift, p.binBits);
               const u32 pos = binOff[bin] + rank[t * 32 + q];
               Stored sk;  to_stored(key, sk);
-              if (pos < (u32)S::STAGE_CAP) stage[pos] = sk; else out[gofs[bin] + pos] = sk;
+              if (pos < (u32)S::STAGE_CAP) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
             }
             roll.push(window_code(w, q + p.k), p.k, rollMask);
           }
@@ -352,7 +354,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
             const u32 bin = key_field(key, binShift, p.binBits);
             const u32 pos = binOff[bin] + rank[t * 32 + q];
             Stored sk;  to_stored(key, sk);
-            if (pos < (u32)S::STAGE_CAP) stage[pos] = sk; else out[gofs[bin] + pos] = sk;
+            if (pos < (u32)S::STAGE_CAP) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
           }
         }
       }
@@ -362,14 +364,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
       const u32 nStaged = total < (u32)S::STAGE_CAP ? total : (u32)S::STAGE_CAP;
       for (u32 j = t; j < nStaged; j += blockDim.x) {
         const Stored sk = stage[j];
-        u32 bin;
-        if (S32) {                                    //  the bin is not in a suffix key: largest b with binOff[b] <= j
-          u32 lo = p.binLo, hi = p.binHi;
-          while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (binOff[mid] <= j) lo = mid; else hi = mid; }
-          bin = lo;
-        } else {
-          bin = key_field(sk, binShift, p.binBits);
-        }
+        const u32 bin = S32 ? (u32)sbin[j] : key_field(sk, binShift, p.binBits);
         out[gofs[bin] + j] = sk;
       }
     }

@@ -305,24 +305,25 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   if (t == 0) binOff[MB_RADIX] = n;
   __syncthreads();                                       //  counters fully consumed: the buffer becomes the stage
 
-  //  4a. digit-sorted order in shared memory
+  //  3a. publish this tile's digit counts as early as possible ...
+  const u32 myCount = (t < MB_RADIX) ? binOff[t + 1] - binOff[t] : 0;
+  if (t < MB_RADIX)
+    st_volatile_u64(status + tile * MB_RADIX + t, ST_MAKE(isFirst ? 2 : 1, epoch, myCount));
+
+  //  4a. ... put the keys in digit-sorted order in shared memory ...
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
     if (prior[i] != 0xffff) stage[prior[i]] = key[i];
   MB_TICK(3);                                            //  3: reorder issued
 
-  //  3. publish, look back over the earlier tiles of this segment (batched: LB status words per round trip)
+  //  3b. ... and only then wait for the earlier tiles of this segment (batched walk: LB status words
+  //  per L2 round trip; the segment's first tile ends it).
   if (t < MB_RADIX) {
-    const int LB = 4;
+    const int LB = 8;
     const u32 d = t;
-    const u32 myCount = binOff[d + 1] - binOff[d];
-    u64 *mine = status + tile * MB_RADIX + d;
     u64 excl = 0;
-    if (isFirst) {
-      st_volatile_u64(mine, ST_MAKE(2, epoch, myCount));
-    } else {
-      st_volatile_u64(mine, ST_MAKE(1, epoch, myCount));
-      const u64 *p = status + (tile - 1) * MB_RADIX + d;            //  predecessor; the segment's first tile ends the walk
+    if (!isFirst) {
+      const u64 *p = status + (tile - 1) * MB_RADIX + d;
       bool done = false;
       while (!done) {
         u64 v[LB];
@@ -337,7 +338,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
           if (ST_FLAG(v[b]) == 2) done = true;
         }
       }
-      st_volatile_u64(mine, ST_MAKE(2, epoch, excl + myCount));
+      st_volatile_u64(status + tile * MB_RADIX + d, ST_MAKE(2, epoch, excl + myCount));
     }
     gofs[d] = gbase[((u64)seg * nPasses + pass) * MB_RADIX + d] + excl - binOff[d];
   }
@@ -386,9 +387,9 @@ u32 mb_sort_tile_keys(u32 keyBytes) {
 static u64 *g_sortProf = nullptr;
 void mb_sort_set_profile_buffer(u64 *dProf) { g_sortProf = dProf; }
 
-//  workspace: [ghist: nSegs*nPasses*R u64][tile counters: 32 u64][guard: 4*R u64][status: nTiles*R u64][tile info: nTiles*16 B]
+//  workspace: [ghist: nSegs*nPasses*R u64][tile counters: 32 u64][guard: 8*R u64][status: nTiles*R u64][tile info: nTiles*16 B]
 //  (R = MB_RADIX; the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
-static const size_t kStatusGuard = 4 * MB_RADIX;
+static const size_t kStatusGuard = 8 * MB_RADIX;
 static const size_t kCounters    = 32;
 
 size_t mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses) {

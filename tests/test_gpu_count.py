@@ -178,14 +178,14 @@ def test_counted_arrays_and_histogram_properties():
 
 def test_multi_pass_equals_single_pass(tmp_path):
     """A small workspace forces several prefix-range passes; the db must not change."""
-    data = synth.reads_fastq_bytes(300_000, 120_000, 150, 0.002, 77)
+    data = synth.reads_fastq_bytes(300_000, 400_000, 150, 0.002, 77)
     a, b = str(tmp_path / "a.meryl"), str(tmp_path / "b.meryl")
     with mb.Counter(21, 12) as c:
         c.add_file_bytes(data)
         c.count()
         one = c.stats().nPasses
         c.write_db(a)
-    with mb.Counter(21, 12, workspace_bytes=1 << 29) as c:
+    with mb.Counter(21, 12, workspace_bytes=1 << 28) as c:
         c.add_file_bytes(data)
         c.count()
         many = c.stats().nPasses
@@ -283,7 +283,7 @@ def test_suffix32_path_equals_full_key_path(tmp_path, monkeypatch):
     64-bit path.  Both must give the same bytes, also with several passes and several count groups."""
     data = synth.reads_fastq_bytes(400_000, 150_000, 150, 0.002, 91)
     dbs = []
-    for env, ws in (("", 0), ("1", 0), ("", 3 << 28), ("1", 3 << 28)):
+    for env, ws in (("", 0), ("1", 0), ("", 1 << 28), ("1", 1 << 28)):
         if env:
             monkeypatch.setenv("MB_NO_SUFFIX32", env)
         else:
