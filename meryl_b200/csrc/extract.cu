@@ -105,20 +105,19 @@ struct ExtractSmem {
   typedef typename KeyT<S32 ? 0 : KW>::type Key;             //  what is stored: full key, or its low 32 bits
   static const int    THREADS   = ExtractShape<KW>::THREADS;
   static const int    TILE_POS  = THREADS * 32;
-  static const int    STAGE_CAP = 32768 / sizeof(Key);                      //  keys staged per tile (the rest go out directly)
   static const int    REC_U32   = (THREADS + 4) * MB_STORE_REC_WORDS;       //  records incl. halo
   static const int    REC_BYTES = REC_U32 * 4;                              //  multiple of 16
   static const size_t OFF_BAR   = 0;
   static const size_t OFF_REC0  = 128;
   static const size_t OFF_REC1  = OFF_REC0 + ((REC_BYTES + 127) / 128) * 128;
-  static const size_t OFF_CNT   = OFF_REC1 + ((REC_BYTES + 127) / 128) * 128;
-  static const size_t OFF_BINOFF= OFF_CNT + MB_MAX_BINS * sizeof(u32);
-  static const size_t OFF_GOFS  = OFF_BINOFF + MB_MAX_BINS * sizeof(u32);
-  static const size_t OFF_RANK  = OFF_GOFS + MB_MAX_BINS * sizeof(u64);
-  static const size_t OFF_STAGE = OFF_RANK + (size_t)TILE_POS * sizeof(unsigned short);
-  static const size_t OFF_SBIN  = OFF_STAGE + (size_t)STAGE_CAP * sizeof(Key);          //  suffix keys do not carry their bin:
-  static const size_t SCATTER_BYTES = OFF_SBIN + (S32 ? (size_t)STAGE_CAP * sizeof(unsigned short) : 0);   //  it is staged next to them
-  static const size_t COUNT_BYTES   = OFF_BINOFF;
+  static const size_t OFF_TABLES= OFF_REC1 + ((REC_BYTES + 127) / 128) * 128;
+  //  After OFF_TABLES the layout depends on the pass (nT = bins of the pass, cap = staged keys per tile):
+  //    u32 cnt[nT] | u32 binOff[nT] | u64 gofs[nT] | u16 rank[TILE_POS] | Key stage[cap] | u16 sbin[cap] (suffix keys only)
+  //  A pass over a fifth of the bins needs ~45 KB instead of 86 KB: 4 CTAs per SM instead of 2, which the
+  //  latency-bound rolling loop of phase A needs.
+  __host__ __device__ static size_t tablesBytes(u32 nT)            { return ((size_t)nT * 16 + 15) / 16 * 16; }
+  __host__ __device__ static size_t scatterBytes(u32 nT, u32 cap)  { return OFF_TABLES + tablesBytes(nT) + (size_t)TILE_POS * 2 + (size_t)cap * sizeof(Key) + (S32 ? (size_t)cap * 2 : 0) + 16; }
+  __host__ __device__ static size_t countBytes(u32 nT)             { return OFF_TABLES + (size_t)nT * 4; }
 };
 
 //  Validity of the 32 windows of length k that start at this thread's positions.
@@ -208,7 +207,7 @@ __device__ __forceinline__ void to_stored(const ulonglong2 &k, ulonglong2 &o)   
 template <int KW, bool COUNT_ONLY, bool S32>
 __global__ void __launch_bounds__(ExtractShape<KW>::THREADS)
 extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict__ out,
-               const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles) {
+               const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles, u32 stageCap) {
   typedef typename KeyT<KW>::type           Key;             //  what is computed
   typedef typename KeyT<S32 ? 0 : KW>::type Stored;          //  what is written
   typedef ExtractSmem<KW, S32>              S;
@@ -216,12 +215,14 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
 
   u64            *bar   = (u64 *)(smem + S::OFF_BAR);
   u32            *rec[2] = { (u32 *)(smem + S::OFF_REC0), (u32 *)(smem + S::OFF_REC1) };
-  u32            *cnt    = (u32 *)(smem + S::OFF_CNT);
-  u32            *binOff = (u32 *)(smem + S::OFF_BINOFF);
-  u64            *gofs   = (u64 *)(smem + S::OFF_GOFS);
-  unsigned short *rank   = (unsigned short *)(smem + S::OFF_RANK);
-  Stored         *stage  = (Stored *)(smem + S::OFF_STAGE);
-  unsigned short *sbin   = (unsigned short *)(smem + S::OFF_SBIN);
+  //  tables are indexed by (bin - binLo); COUNT_ONLY uses only cnt[], over all bins (binLo == 0)
+  const u32       nT     = p.binHi - p.binLo;
+  u32            *cnt    = (u32 *)(smem + S::OFF_TABLES);
+  u32            *binOff = cnt + nT;
+  u64            *gofs   = (u64 *)(smem + S::OFF_TABLES + (((size_t)nT * 8 + 7) / 8) * 8);
+  unsigned short *rank   = (unsigned short *)(smem + S::OFF_TABLES + S::tablesBytes(nT));
+  Stored         *stage  = (Stored *)(((uintptr_t)(rank + S::TILE_POS) + 15) & ~(uintptr_t)15);
+  unsigned short *sbin   = (unsigned short *)(stage + stageCap);
   __shared__ u32 sWarpSum[ExtractShape<KW>::THREADS / 32];
 
   const u32 t = threadIdx.x;
@@ -229,7 +230,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   const bool rollAgain = (p.binHi - p.binLo) * 3 >= nBins;      //  this pass keeps >= 1/3 of the k-mers
 
   if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
-  for (u32 b = t; b < nBins; b += blockDim.x) cnt[b] = 0;
+  for (u32 b = t; b < nT; b += blockDim.x) cnt[b] = 0;
   __syncthreads();
 
   const unsigned char *storeBytes = (const unsigned char *)p.store;
@@ -282,10 +283,10 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
         if ((valid << q) & 0x80000000u) {
           const u32 bin = key_field(roll.key(p.mode), binShift, p.binBits);
           if (COUNT_ONLY) {
-            atomicAdd(&cnt[bin], 1u);
+            atomicAdd(&cnt[bin - p.binLo], 1u);
           } else if (bin >= p.binLo && bin < p.binHi) {
             keep |= 0x80000000u >> q;
-            rank[t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin], 1u);
+            rank[t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin - p.binLo], 1u);
           }
         }
         roll.push(window_code(w, q + p.k), p.k, rollMask);
@@ -303,7 +304,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
       const u32 perThread = (nPassBins + blockDim.x - 1) / blockDim.x;
       const u32 b0 = p.binLo + t * perThread;
       u32 mySum = 0;
-      for (u32 i = 0; i < perThread; i++) { const u32 b = b0 + i; if (b < p.binHi) mySum += cnt[b]; }
+      for (u32 i = 0; i < perThread; i++) { const u32 b = b0 + i; if (b < p.binHi) mySum += cnt[b - p.binLo]; }
       u32 incl = mySum;
       for (int o = 1; o < 32; o <<= 1) {
         const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -316,11 +317,11 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
       for (u32 i = 0; i < perThread; i++) {
         const u32 b = b0 + i;
         if (b < p.binHi) {
-          const u32 c = cnt[b];
-          binOff[b] = run;
+          const u32 c = cnt[b - p.binLo];
+          binOff[b - p.binLo] = run;
           if (c) {
-            gofs[b] = binStart[b] + atomicAdd((unsigned long long *)&binCursor[b], (unsigned long long)c) - run;
-            cnt[b]  = 0;
+            gofs[b - p.binLo] = binStart[b] + atomicAdd((unsigned long long *)&binCursor[b], (unsigned long long)c) - run;
+            cnt[b - p.binLo]  = 0;
           }
           run += c;
         }
@@ -339,10 +340,10 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
           for (u32 q = 0; q < 32; q++) {
             if ((keep << q) & 0x80000000u) {
               const Key key = roll.key(p.mode);
-              const u32 bin = key_field(key, binShift, p.binBits);
+              const u32 bin = key_field(key, binShift, p.binBits) - p.binLo;
               const u32 pos = binOff[bin] + rank[t * 32 + q];
               Stored sk;  to_stored(key, sk);
-              if (pos < (u32)S::STAGE_CAP) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
+              if (pos < stageCap) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
             }
             roll.push(window_code(w, q + p.k), p.k, rollMask);
           }
@@ -351,20 +352,20 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
             const u32 q = __clz(v);
             v &= ~(0x80000000u >> q);
             const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
-            const u32 bin = key_field(key, binShift, p.binBits);
+            const u32 bin = key_field(key, binShift, p.binBits) - p.binLo;
             const u32 pos = binOff[bin] + rank[t * 32 + q];
             Stored sk;  to_stored(key, sk);
-            if (pos < (u32)S::STAGE_CAP) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
+            if (pos < stageCap) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
           }
         }
       }
       __syncthreads();
 
       //  Copy-out: consecutive threads, consecutive staged keys -> every bin's run is written coalesced.
-      const u32 nStaged = total < (u32)S::STAGE_CAP ? total : (u32)S::STAGE_CAP;
+      const u32 nStaged = total < stageCap ? total : stageCap;
       for (u32 j = t; j < nStaged; j += blockDim.x) {
         const Stored sk = stage[j];
-        const u32 bin = S32 ? (u32)sbin[j] : key_field(sk, binShift, p.binBits);
+        const u32 bin = S32 ? (u32)sbin[j] : key_field(sk, binShift, p.binBits) - p.binLo;
         out[gofs[bin] + j] = sk;
       }
     }
@@ -381,14 +382,25 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   if (COUNT_ONLY) {
     __syncthreads();
     for (u32 b = t; b < nBins; b += blockDim.x)
-      if (cnt[b]) atomicAdd((unsigned long long *)&binCount[b], (unsigned long long)cnt[b]);
+      if (cnt[b]) atomicAdd((unsigned long long *)&binCount[b], (unsigned long long)cnt[b]);   //  COUNT_ONLY: binLo == 0
   }
 }
 
 template <int KW, bool COUNT_ONLY, bool S32>
 cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, u64 *binCount, cudaStream_t s) {
   typedef ExtractSmem<KW, S32> S;
-  const size_t smem = COUNT_ONLY ? S::COUNT_BYTES : S::SCATTER_BYTES;
+  const u32 nBins = 1u << p.binBits, nT = p.binHi - p.binLo;
+  //  stage capacity per tile: everything when the pass keeps all bins, else twice the expected share
+  //  (what does not fit is written directly -- slower, never wrong)
+  u32 stageCap = S::TILE_POS;
+  if (nT < nBins) {
+    u64 want = 2ull * S::TILE_POS * nT / nBins;
+    if (want < 1024) want = 1024;
+    want = (want + 255) / 256 * 256;
+    if (want < stageCap) stageCap = (u32)want;
+  }
+  if (sizeof(typename S::Key) * stageCap > 32768) stageCap = 32768 / sizeof(typename S::Key);
+  const size_t smem = COUNT_ONLY ? S::countBytes(nT) : S::scatterBytes(nT, stageCap);
   auto kern = extract_kernel<KW, COUNT_ONLY, S32>;
 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -407,7 +419,7 @@ cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64
   u64 grid = (u64)sms * perSm;                                   //  persistent: a multiple of the SM count
   if (grid > nTiles) grid = nTiles;
 
-  kern<<<(unsigned)grid, S::THREADS, smem, s>>>(p, (typename KeyT<S32 ? 0 : KW>::type *)out, binStart, binCursor, binCount, nTiles);
+  kern<<<(unsigned)grid, S::THREADS, smem, s>>>(p, (typename KeyT<S32 ? 0 : KW>::type *)out, binStart, binCursor, binCount, nTiles, stageCap);
   return cudaGetLastError();
 }
 
