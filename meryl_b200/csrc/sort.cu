@@ -163,7 +163,7 @@ sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 
 //  Shared buffer, used in turn as (a) the striped->blocked transpose area, (b) the private digit
 //  counters, (c) the digit-sorted stage.  Sizes in bytes, for TILE keys of KB bytes:
 //    transpose / stage : TILE*KB, plus one key of padding per 128 bytes (bank-conflict-free blocked reads)
-//    counters          : (MB_RADIX/2) lanes x 256 threads x 4 B = 32 KB, plus four words of padding per 32
+//    counters          : (MB_RADIX/2) lanes x 256 threads x 4 B = 32 KB, plus one word of padding per 32
 template <int KW> struct SweepSmem {
   typedef typename KeyT<KW>::type Key;
   static const int TILE     = SORT_THREADS * SortShape<KW>::ITEMS;
@@ -171,7 +171,7 @@ template <int KW> struct SweepSmem {
   static const int XPOSE    = (TILE + TILE / PAD_EVERY) * sizeof(Key);
   static const int LANES    = MB_RADIX / 2;                                     //  two 16-bit counters per word
   static const int CWORDS   = LANES * SORT_THREADS;
-  static const int COUNTERS = (CWORDS + CWORDS / 32 * 4) * 4;                   //  4 words of padding per 32: 16-byte aligned rake segments
+  static const int COUNTERS = (CWORDS + CWORDS / 32) * 4;
   static const int BYTES    = XPOSE > COUNTERS ? XPOSE : COUNTERS;
 };
 
@@ -238,7 +238,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   __syncthreads();                                       //  everybody has its keys: the buffer becomes the counters
 
   //  2. private counters.  Digit d lives in word (d & 31) of my column, half (d >> 5).
-  for (u32 i = t; i < (u32)(S::COUNTERS / 16); i += SORT_THREADS) ((uint4 *)counters)[i] = make_uint4(0, 0, 0, 0);
+  for (u32 i = t; i < (u32)(S::CWORDS + S::CWORDS / 32); i += SORT_THREADS) counters[i] = 0;
   __syncthreads();
 
   const u32 myFirst = t * ITEMS;                         //  my keys are tile positions [myFirst, myFirst + ITEMS)
@@ -249,7 +249,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     if (myFirst + i < n) {
       const u32 d    = key_field(key[i], shift, bits);
       const u32 lin  = (d & 31) * SORT_THREADS + t;      //  (word-of-digit, thread): digit-major within each half
-      u32 *cp        = &counters[lin + (lin >> 5) * 4];
+      u32 *cp        = &counters[lin + (lin >> 5)];
       const u32 sh16 = (d >> 5) * 16;
       const u32 wv   = *cp;
       prior[i] = (unsigned short)((wv >> sh16) & 0xffff);
@@ -261,10 +261,10 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   //  raking scan over the CWORDS packed words: thread t owns the 32 consecutive words [32t, 32t+32)
   u32 tileLow = 0;                                       //  keys whose digit is < 32 (low halves)
   {
-    uint4 *seg4 = (uint4 *)&counters[t * 36];             //  my 32 words, 128 bits at a time
+    u32 *seg32 = &counters[t * 33];
     u32 sum = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { const uint4 v = seg4[j]; sum += v.x + v.y + v.z + v.w; }
+    for (int j = 0; j < 32; j++) sum += seg32[j];
     u32 incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
       const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -277,15 +277,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     for (int w = 0; w < SORT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) run += c; tot += c; }
     tileLow = tot & 0xffff;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint4 v = seg4[j];
-      uint4 o;
-      o.x = run;  run += v.x;
-      o.y = run;  run += v.y;
-      o.z = run;  run += v.z;
-      o.w = run;  run += v.w;
-      seg4[j] = o;
-    }
+    for (int j = 0; j < 32; j++) { const u32 c = seg32[j]; seg32[j] = run; run += c; }
   }
   __syncthreads();
   MB_TICK(2);                                            //  2: keys loaded, counted, scanned
@@ -297,7 +289,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     if (myFirst + i < n) {
       const u32 d   = key_field(key[i], shift, bits);
       const u32 lin = (d & 31) * SORT_THREADS + t;
-      const u32 wv  = counters[lin + (lin >> 5) * 4];
+      const u32 wv  = counters[lin + (lin >> 5)];
       const u32 hi  = d >> 5;
       prior[i] = (unsigned short)(((wv >> (hi * 16)) & 0xffff) + (hi ? tileLow : 0) + prior[i]);
     } else {
@@ -306,7 +298,7 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   }
   if (t < MB_RADIX) {
     const u32 lin = (t & 31) * SORT_THREADS;             //  thread 0's slot of digit t == first key of that digit
-    const u32 wv  = counters[lin + (lin >> 5) * 4];
+    const u32 wv  = counters[lin + (lin >> 5)];
     const u32 hi  = t >> 5;
     binOff[t] = ((wv >> (hi * 16)) & 0xffff) + (hi ? tileLow : 0);
   }
