@@ -143,10 +143,11 @@ count_kernel(typename KeyT<KW>::type *keys, u64 nKeys, u64 *__restrict__ runStar
 
 struct __align__(16) CountTileInfo { u64 begin; u32 n; u32 seg; };       //  == sort.cu's TileInfo
 
-const int C32_ITEMS = 32;                                                //  == SortShape<0>::ITEMS
+const int C32_ITEMS  = 16;                                               //  a CTA counts HALF a sort tile (SortShape<0>::ITEMS == 32):
+const int C32_HALF   = CNT_THREADS * C32_ITEMS;                          //  16 keys per thread keep it at 64 registers, 4 CTAs per SM
 
-__global__ void __launch_bounds__(CNT_THREADS)
-count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nTilesInGroup,
+__global__ void __launch_bounds__(CNT_THREADS, 4)
+count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nHalves,
                       u64 endIndex, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart,
                       u64 *__restrict__ numDistinct, u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
   __shared__ u32 warpTot[CNT_WARPS];
@@ -156,12 +157,13 @@ count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restr
 
   if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
   __syncthreads();
-  const u64 rel = sTile;                                     //  tile index inside the group
-  const CountTileInfo ti = info[tileLo + rel];
-  const u64  begin   = ti.begin;
-  const u32  n       = ti.n;
+  const u64 rel  = sTile;                                    //  half-tile index inside the group
+  const u32 half = (u32)(rel & 1);
+  const CountTileInfo ti = info[tileLo + (rel >> 1)];
+  const u64  begin   = ti.begin + (u64)half * C32_HALF;
+  const u32  n       = ti.n > half * C32_HALF ? min(ti.n - half * C32_HALF, (u32)C32_HALF) : 0;
   const u32  seg     = ti.seg & 0x7fffffffu;
-  const bool segHead = (ti.seg >> 31) != 0;
+  const bool segHead = (ti.seg >> 31) != 0 && half == 0;     //  the segment's very first key always starts a run
 
   u32 key[C32_ITEMS];
   u32 heads = 0;
@@ -210,7 +212,7 @@ count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restr
       st_volatile_u64(status + rel, MB_ST_INC | (excl + tileTot));
     }
     sExcl = excl;
-    if (rel + 1 == nTilesInGroup) {                          //  last tile of the group: total and sentinel
+    if (rel + 1 == nHalves) {                                //  last half-tile of the group: total and sentinel
       *numDistinct = excl + tileTot;
       runStart[excl + tileTot] = endIndex;
     }
@@ -314,10 +316,10 @@ cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u6
     if ((e = cudaMemsetAsync(dNumDistinct, 0, sizeof(u64), s)) != cudaSuccess) return e;
     return cudaMemsetAsync(dRunStart, 0, sizeof(u64), s);
   }
-  const u64 nTiles = tileHi - tileLo;
-  if ((e = cudaMemsetAsync(dWorkspace, 0, (2 + nTiles) * sizeof(u64), s)) != cudaSuccess) return e;
+  const u64 nHalves = 2 * (tileHi - tileLo);                 //  workspace: (2 + nHalves) u64
+  if ((e = cudaMemsetAsync(dWorkspace, 0, (2 + nHalves) * sizeof(u64), s)) != cudaSuccess) return e;
   u64 *counter = (u64 *)dWorkspace, *status = counter + 2;
-  count_suffix32_kernel<<<(unsigned)nTiles, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nTiles, endIndex,
+  count_suffix32_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
                                                                 binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
   return cudaGetLastError();
 }

@@ -710,7 +710,7 @@ static int runCount(mb_ctx *c) {
       } else {
         distinctKeys = other;  encKeyWords = 1;
         runStart = (u64 *)gc.take(8 * (size_t)(gKeys + 1));
-        void *cws = gc.take(8 * (size_t)(G.tileHi - G.tileLo + 2));     //  the sort workspace still holds the tile table
+        void *cws = gc.take(8 * (size_t)(2 * (G.tileHi - G.tileLo) + 2));   //  (the sort workspace still holds the tile table)
         if (!runStart || !cws) return mb_fail(MB_ENOMEM, "internal: no room for the run table of pass %zu group %zu", pi, gi);
         MB_CUDA(mb_launch_count_suffix32((const u32 *)sorted, mb_sort_tile_info(ws, nTiles, nSegs ? nSegs : 1, plan.nPasses),
                                          G.tileLo, G.tileHi, G.keyHi, P.binLo, 2 * k - binBits, (u64 *)other, runStart,
