@@ -32,6 +32,18 @@ def sort_phases(n):
     assert np.all(keys[1:] >= keys[:-1])
 
 
+def sort32_phases(n):
+    L.mb_dbg_sort32.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
+    rng = np.random.default_rng(2)
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    out = (ctypes.c_uint64 * 8)()
+    L.mb_dbg_sort_profile(None, 1)
+    assert L.mb_dbg_sort32(keys.ctypes.data, n, 32) == 0
+    L.mb_dbg_sort_profile(out, 0)
+    report("sort_sweep<u32>", list(out), ["tile id", "load+rank", "scan+reorder", "own lookback", "cta lookback wait", "copy-out"])
+    assert np.all(keys[1:] >= keys[:-1])
+
+
 def extract_phases(gbp):
     import torch
     n_reads = int(gbp * 1e9) // 150
@@ -52,4 +64,5 @@ def extract_phases(gbp):
 
 if __name__ == "__main__":
     sort_phases(int(float(sys.argv[1])) if len(sys.argv) > 1 else 200_000_000)
+    sort32_phases(int(float(sys.argv[1])) * 2 if len(sys.argv) > 1 else 400_000_000)
     extract_phases(float(sys.argv[2]) if len(sys.argv) > 2 else 1.0)
