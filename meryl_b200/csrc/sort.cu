@@ -180,7 +180,7 @@ __device__ __forceinline__ void key_zero(u64 &k)        { k = 0; }
 __device__ __forceinline__ void key_zero(ulonglong2 &k) { k.x = 0; k.y = 0; }
 
 template <int KW>
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                   const TileInfo *__restrict__ info,
                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
