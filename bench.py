@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gbp", type=float, default=0.0, help="billion bases of reads in total (0 = 100, reduced to what fits)")
-    ap.add_argument("--ref-gbp", type=float, default=1.5, help="size of the reference's bounded sample")
+    ap.add_argument("--ref-gbp", type=float, default=0.0, help="size of the reference's bounded sample (0 = sized so that all its steps take ~2.5 min)")
     ap.add_argument("--ref-memory-gb", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -155,6 +155,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.ref_gbp <= 0:
+        # the reference counts ~15 M k-mers/s on this host: keep (steps + warmup) runs within ~2.5 minutes
+        runs = (args.steps + args.warmup) if args.impl == "reference" else 1
+        args.ref_gbp = max(0.1, min(0.6, 2.6 / max(1, runs)))
 
     import torch
     import torch.distributed as dist

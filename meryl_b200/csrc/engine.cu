@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <stdio.h>
 #include <string.h>
 #include <unistd.h>
@@ -104,7 +105,8 @@ extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
     return mb_fail(MB_ENODEVICE, "mb_create: no CUDA device (this library has no CPU path)");
 
-  mb_ctx *c = new mb_ctx();
+  std::unique_ptr<mb_ctx, void (*)(mb_ctx *)> guard(new mb_ctx(), mb_destroy);   //  released on success, destroyed on any early return
+  mb_ctx *c = guard.get();
   c->cfg = *cfg;
   if (cfg->device >= 0) { c->device = cfg->device; MB_CUDA(cudaSetDevice(c->device)); }
   else                  { MB_CUDA(cudaGetDevice(&c->device)); }
@@ -112,9 +114,7 @@ extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
   cudaDeviceProp prop;
   MB_CUDA(cudaGetDeviceProperties(&prop, c->device));
   if (prop.major < 10) {
-    const int dev = c->device;
-    delete c;
-    return mb_fail(MB_ENODEVICE, "mb_create: device %d is sm_%d%d; this build is sm_100a only", dev, prop.major, prop.minor);
+    return mb_fail(MB_ENODEVICE, "mb_create: device %d is sm_%d%d; this build is sm_100a only", c->device, prop.major, prop.minor);
   }
 
   c->keyWords = cfg->k <= 32 ? 1 : 2;
@@ -131,9 +131,10 @@ extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
   if (want == 0) want = freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2;
   if (want > freeB) want = freeB;
   want = want / kAlign * kAlign;
-  if (want < ((size_t)256 << 20)) { delete c; return mb_fail(MB_ENOMEM, "mb_create: only %zu bytes of device memory free", freeB); }
+  if (want < ((size_t)256 << 20)) return mb_fail(MB_ENOMEM, "mb_create: only %zu bytes of device memory free", freeB);
   if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
-    delete c;
+    cudaGetLastError();
+    c->arena = nullptr;
     return mb_fail(MB_ENOMEM, "mb_create: cannot allocate a %zu byte device arena", want);
   }
   c->arenaBytes = want;
@@ -145,7 +146,7 @@ extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
   }
   c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
 
-  *out = c;
+  *out = guard.release();
   return MB_OK;
 }
 

@@ -150,3 +150,40 @@ def test_estimate_kmers_in_file(tmp_path):
     b = tmp_path / "a.fa.bz2"
     b.write_bytes(b"x" * 1001)
     assert mb.estimate_kmers_in_file(str(b)) == int(1001 * 3.5)
+
+
+def _cli(args, env=None):
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    return subprocess.run([mb.CLI_PATH] + args, capture_output=True, text=True, env=e)
+
+
+def test_cli_errors_like_the_reference(tmp_path):
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">x\nACGTACGTACGTACGTACGTACGTACGT\n")
+    p = _cli(["count", str(fa), "output", str(tmp_path / "o.meryl")])
+    assert p.returncode == 1 and "Kmer size not supplied" in p.stderr          # merylOp-count.C:311-312
+    p = _cli(["k=21", "count", str(fa)])
+    assert p.returncode == 1 and "No output specified" in p.stderr             # merylOp-count.C:314-315
+    p = _cli(["k=21", "union-sum", "x.meryl", "y.meryl", "output", "z.meryl"])
+    assert p.returncode == 1 and "not part of `meryl count`" in p.stderr
+
+
+def test_cli_config_only_prints_the_canu_line(tmp_path):
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(synth.fasta_bytes(1, 10_000, 3))
+    p = _cli(["-C", "k=21", "memory=8", "n=626888890", "count", str(fa)])
+    assert p.returncode == 0
+    assert "Configured complex mode for" in p.stderr and "GB memory per batch, and up to" in p.stderr
+    assert "prefix width %d bits" % mb.plan(21, 626_888_890, 8 << 30).w_prefix in p.stderr
+    assert not (tmp_path / "o.meryl").exists()
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+def test_cli_hands_other_operations_to_the_reference(tmp_path):
+    """With MERYL_REFERENCE set, anything that is not a count is exec'd to the reference unchanged."""
+    inp, gold, words, _ = util.load_golden("edge_k21", str(tmp_path))
+    p = _cli(["statistics", gold], env={"MERYL_REFERENCE": util.REF_BIN})
+    q = subprocess.run([util.REF_BIN, "statistics", gold], capture_output=True, text=True)
+    assert p.returncode == q.returncode == 0 and p.stdout == q.stdout and "unique" in p.stdout
