@@ -84,7 +84,7 @@ typedef struct mb_stats {
   uint64_t h2dBytes;        /*  host->device bytes moved                                  */
   uint64_t d2hBytes;        /*  device->host bytes moved                                  */
   /*  device time (CUDA events on the launching stream), milliseconds, summed over passes  */
-  float    msPack;          /*  K1  ASCII -> 2-bit + validity                              */
+  float    msPack;          /*  ingest span on the device: first chunk queued -> last chunk packed (H2D + K1)  */
   float    msHistogram;     /*  K2a prefix-bin histogram pre-pass                          */
   float    msExtract;       /*  K2/K3 canonical extraction + prefix scatter                */
   float    msSortHist;      /*  K4a digit histograms                                       */

@@ -68,6 +68,8 @@ struct mb_ctx {
   char       *hStage[2]  = { nullptr, nullptr };
   uint8_t    *dStage[2]  = { nullptr, nullptr };
   cudaEvent_t evH2D[2]   = { nullptr, nullptr };     //  hStage[i] has been copied
+  cudaEvent_t evIngest[2]= { nullptr, nullptr };     //  first chunk queued / last chunk packed (st.msPack)
+  bool        ingestStarted = false;
   size_t      fill       = 0;
   int         cur        = 0;
   bool        inRecord   = false;                    //  bases since the last '.'
@@ -124,27 +126,12 @@ extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
   for (u32 f = 0; f < 64; f++) c->db.owned[f] = true;
 
   MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-
-  size_t freeB = 0, totalB = 0;
-  MB_CUDA(cudaMemGetInfo(&freeB, &totalB));
-  size_t want = cfg->workspaceBytes;
-  if (want == 0) want = freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2;
-  if (want > freeB) want = freeB;
-  want = want / kAlign * kAlign;
-  if (want < ((size_t)256 << 20)) return mb_fail(MB_ENOMEM, "mb_create: only %zu bytes of device memory free", freeB);
-  if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
-    cudaGetLastError();
-    c->arena = nullptr;
-    return mb_fail(MB_ENOMEM, "mb_create: cannot allocate a %zu byte device arena", want);
-  }
-  c->arenaBytes = want;
-
   for (int i = 0; i < 2; i++) {
-    MB_CUDA(cudaMallocHost((void **)&c->hStage[i], kStageBytes));
-    c->dStage[i] = c->arena + c->arenaBytes - (size_t)(i + 1) * kStageBytes;
     MB_CUDA(cudaEventCreateWithFlags(&c->evH2D[i], cudaEventDisableTiming));
+    MB_CUDA(cudaEventCreate(&c->evIngest[i]));
   }
-  c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
+  //  The device arena is taken at the first use (ensureArena), i.e. AFTER mb_comm_init in a multi-GPU
+  //  job: NCCL allocates its own channel buffers (gigabytes with 8 peers) and must find room.
 
   *out = guard.release();
   return MB_OK;
@@ -159,6 +146,7 @@ extern "C" void mb_destroy(mb_ctx *c) {
   for (int i = 0; i < 2; i++) {
     if (c->hStage[i]) cudaFreeHost(c->hStage[i]);
     if (c->evH2D[i])  cudaEventDestroy(c->evH2D[i]);
+    if (c->evIngest[i]) cudaEventDestroy(c->evIngest[i]);
   }
   if (c->arena)  cudaFree(c->arena);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -169,6 +157,31 @@ extern "C" void mb_destroy(mb_ctx *c) {
 //  ------------------------------------------------------------------------------------------
 //  ingest
 //  ------------------------------------------------------------------------------------------
+
+static int ensureArena(mb_ctx *c) {
+  if (c->arena) return MB_OK;
+  MB_CUDA(cudaSetDevice(c->device));
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+  const size_t margin = (size_t)(c->cfg.worldSize > 1 ? 4 : 2) << 30;
+  size_t want = c->cfg.workspaceBytes;
+  if (want == 0) want = freeB > margin + ((size_t)1 << 30) ? freeB - margin : freeB / 2;
+  if (want > freeB) want = freeB;
+  want = want / kAlign * kAlign;
+  if (want < ((size_t)256 << 20)) return mb_fail(MB_ENOMEM, "only %zu bytes of device memory free", freeB);
+  if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
+    cudaGetLastError();
+    c->arena = nullptr;
+    return mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want);
+  }
+  c->arenaBytes = want;
+  for (int i = 0; i < 2; i++) {
+    MB_CUDA(cudaMallocHost((void **)&c->hStage[i], kStageBytes));
+    c->dStage[i] = c->arena + c->arenaBytes - (size_t)(i + 1) * kStageBytes;
+  }
+  c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
+  return MB_OK;
+}
 
 static int storeReserve(mb_ctx *c, u64 moreRecords) {
   const size_t need = (size_t)(c->nRecords + moreRecords + MB_STORE_PAD_RECORDS) * MB_STORE_REC_WORDS * 4;
@@ -186,6 +199,7 @@ static int flushStage(mb_ctx *c) {
   const u64 recs = (n + 31) / 32;
   MB_TRY(storeReserve(c, recs));
   MB_CUDA(cudaSetDevice(c->device));
+  if (!c->ingestStarted) { c->ingestStarted = true; MB_CUDA(cudaEventRecord(c->evIngest[0], c->stream)); }
   MB_CUDA(cudaMemcpyAsync(c->dStage[i], c->hStage[i], n, cudaMemcpyHostToDevice, c->stream));
   MB_CUDA(cudaEventRecord(c->evH2D[i], c->stream));
   MB_CUDA(mb_launch_pack(c->dStage[i], n, (u32 *)c->arena, c->nRecords, c->stream));
@@ -199,6 +213,7 @@ static int flushStage(mb_ctx *c) {
 }
 
 static int appendHost(mb_ctx *c, const char *p, size_t n) {
+  MB_TRY(ensureArena(c));
   while (n) {
     size_t room = kStageBytes - c->fill;
     if (room == 0) { MB_TRY(flushStage(c)); room = kStageBytes; }
@@ -219,11 +234,13 @@ static int parserSink(void *arg, const char *bases, size_t n) {
 //  skip the staging memcpy: the DMA engine reads them in place, 64 MB at a time.
 static int appendPinnedDirect(mb_ctx *c, const char *&p, uint64_t &n) {
   if (n < 4 * kStageBytes || c->inRecord) return MB_OK;
+  MB_TRY(ensureArena(c));
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return MB_OK; }
   if (at.type != cudaMemoryTypeHost) return MB_OK;
   MB_TRY(flushStage(c));                                 //  stream is at a record boundary: padding is harmless
   MB_CUDA(cudaSetDevice(c->device));
+  if (!c->ingestStarted) { c->ingestStarted = true; MB_CUDA(cudaEventRecord(c->evIngest[0], c->stream)); }
   int i = 0;
   while (n >= kStageBytes) {
     const u64 recs = kStageBytes / 32;
@@ -256,12 +273,14 @@ extern "C" int mb_add_bases_device(mb_ctx *c, const char *dBases, uint64_t len) 
   if (!c || (!dBases && len))  return mb_fail(MB_EINVAL, "mb_add_bases_device: NULL argument");
   if (c->counted)              return mb_fail(MB_ESTATE, "mb_add_bases_device: already counted");
   if (((uintptr_t)dBases & 15) != 0) return mb_fail(MB_EINVAL, "mb_add_bases_device: pointer must be 16-byte aligned");
+  MB_TRY(ensureArena(c));
   //  A device chunk holds whole records: the stream is padded to a record boundary before and after.
   if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
   MB_TRY(flushStage(c));
   const u64 recs = (len + 31) / 32;
   MB_TRY(storeReserve(c, recs));
   MB_CUDA(cudaSetDevice(c->device));
+  if (!c->ingestStarted) { c->ingestStarted = true; MB_CUDA(cudaEventRecord(c->evIngest[0], c->stream)); }
   MB_CUDA(mb_launch_pack((const uint8_t *)dBases, len, (u32 *)c->arena, c->nRecords, c->stream));
   MB_CUDA(cudaStreamSynchronize(c->stream));            //  the caller may reuse dBases when we return
   c->st.nLaunches++;
@@ -388,6 +407,7 @@ static int runCount(mb_ctx *c) {
     return mb_fail(MB_ESTATE, "mb_count: context has worldSize %u but mb_comm_init was not called", cfg.worldSize);
 
   MB_CUDA(cudaSetDevice(c->device));
+  MB_TRY(ensureArena(c));
 
   EventTimer tAll, tStage;
   tAll.init(); tStage.init();
@@ -397,6 +417,11 @@ static int runCount(mb_ctx *c) {
   if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
   MB_TRY(flushStage(c));
   MB_TRY(storeReserve(c, 0));
+  if (c->ingestStarted) {                              //  device span of the ingest: first chunk queued -> last chunk packed
+    MB_CUDA(cudaEventRecord(c->evIngest[1], s));
+    MB_CUDA(cudaEventSynchronize(c->evIngest[1]));
+    float m = 0;  cudaEventElapsedTime(&m, c->evIngest[0], c->evIngest[1]);  c->st.msPack = m;
+  }
   const size_t storeBytes = (size_t)c->nRecords * MB_STORE_REC_WORDS * 4;
   const size_t padBytes   = (size_t)MB_STORE_PAD_RECORDS * MB_STORE_REC_WORDS * 4;
   MB_CUDA(cudaMemsetAsync(c->arena + storeBytes, 0, padBytes, s));
