@@ -299,3 +299,20 @@ def test_suffix32_path_equals_full_key_path(tmp_path, monkeypatch):
     for out, _ in dbs[1:]:
         util.assert_same_db(dbs[0][0], out)
     assert dbs[2][1] > 1 and dbs[3][1] > 1
+
+
+@pytest.mark.parametrize("k", [31, 51])
+def test_multi_pass_full_keys(tmp_path, k):
+    """Several prefix-range passes with 64- and 128-bit keys (the in-place count path) == oracle."""
+    data = synth.reads_fastq_bytes(200_000, 150_000, 150, 0.003, 300 + k)
+    p = tmp_path / "r.fq"
+    p.write_bytes(data)
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(p), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    with mb.Counter(k, 12, workspace_bytes=1 << 28) as c:
+        c.add_file(str(p))
+        c.count()
+        assert c.stats().nPasses > 1
+        c.write_db(out)
+    util.assert_same_db(ora, out)
