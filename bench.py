@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--gbp", type=float, default=0.0, help="billion bases of reads in total (0 = 100, reduced to what fits)")
     ap.add_argument("--ref-gbp", type=float, default=0.0, help="size of the reference's bounded sample (0 = sized so that all its steps take ~2.5 min)")
     ap.add_argument("--ref-memory-gb", type=int, default=64)
+    ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena per GPU (0 = all free memory); small values keep ncu replays fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -203,7 +204,8 @@ def main():
     pl = mb.plan(K, n_est, 1024 << 30)
 
     def new_counter(flags):
-        c = mb.Counter(K, pl.w_prefix, "count", device=local, flags=flags, rank=rank, world_size=world)
+        c = mb.Counter(K, pl.w_prefix, "count", device=local, flags=flags, rank=rank, world_size=world,
+                       workspace_bytes=int(args.workspace_gb * (1 << 30)))
         if world > 1:
             c.comm_init(mbd.broadcast_unique_id(mb.Counter.comm_unique_id, device="cuda"))
         return c
