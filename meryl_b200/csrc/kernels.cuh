@@ -50,8 +50,8 @@ template <> struct KeyT<2> { typedef ulonglong2 type; };     //  x = low 64 bits
 __host__ __device__ __forceinline__ u64 key_lo(u32 k)               { return k;   }
 __host__ __device__ __forceinline__ u64 key_hi(u32)                 { return 0;   }
 __host__ __device__ __forceinline__ bool key_eq(u32 a, u32 b)       { return a == b; }
-__host__ __device__ __forceinline__ u32 key_field(u32 k, u32 shift, u32 bits) {
-  return (shift >= 32 ? 0u : (k >> shift)) & ((1u << bits) - 1);
+__host__ __device__ __forceinline__ u32 key_field(u32 k, u32 shift, u32 bits) {      //  shift < 32 (a field of a 32-bit key)
+  return (k >> shift) & ((1u << bits) - 1);
 }
 __host__ __device__ __forceinline__ u64 key_shr64(u32 k, u32 shift) { return shift >= 32 ? 0 : (u64)(k >> shift); }
 

@@ -37,11 +37,11 @@ const int SORT_WARPS   = SORT_THREADS / 32;
 const int SORT_MAX_PASSES = 24;
 
 template <int KW> struct SortShape;
-//  MIN_CTAS: resident CTAs per SM the register budget is compiled for (measured: 4 is ~4 % faster than 3
-//  for 64-bit keys; the 32-key u32 variant spills at 64 registers and is faster at 3).
+//  MIN_CTAS: resident CTAs per SM the register budget is compiled for; ~68 KB of shared memory per CTA
+//  (counters + key buffer) allow three.
 template <> struct SortShape<0> { static const int ITEMS = 32; static const int MIN_CTAS = 3; };   //  u32 suffix keys: 8192 per tile
-template <> struct SortShape<1> { static const int ITEMS = 16; static const int MIN_CTAS = 4; };   //  u64: 4096 per tile
-template <> struct SortShape<2> { static const int ITEMS = 8;  static const int MIN_CTAS = 4; };   //  128 bit: 2048 per tile
+template <> struct SortShape<1> { static const int ITEMS = 16; static const int MIN_CTAS = 3; };   //  u64: 4096 per tile
+template <> struct SortShape<2> { static const int ITEMS = 8;  static const int MIN_CTAS = 3; };   //  128 bit: 2048 per tile
 
 //  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:57] epoch (pass tag, 1..24)  [56:0] value
 #define ST_FLAG(v)    ((u32)((v) >> 62))
@@ -162,8 +162,8 @@ sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 
 
 //  ---- one digit pass ---------------------------------------------------------------------------
 
-//  Shared buffer, used in turn as (a) the striped->blocked transpose area, (b) the private digit
-//  counters, (c) the digit-sorted stage.  Sizes in bytes, for TILE keys of KB bytes:
+//  Dynamic shared memory: the private digit counters, then a key buffer used first as the
+//  striped->blocked transpose area and later as the digit-sorted stage.  Sizes in bytes, for TILE keys of KB bytes:
 //    transpose / stage : TILE*KB, plus one key of padding per 128 bytes (bank-conflict-free blocked reads)
 //    counters          : (MB_RADIX/2) lanes x 256 threads x 4 B = 32 KB, plus one word of padding per 32
 template <int KW> struct SweepSmem {
@@ -174,88 +174,77 @@ template <int KW> struct SweepSmem {
   static const int LANES    = MB_RADIX / 2;                                     //  two 16-bit counters per word
   static const int CWORDS   = LANES * SORT_THREADS;
   static const int COUNTERS = (CWORDS + CWORDS / 32) * 4;
-  static const int BYTES    = XPOSE > COUNTERS ? XPOSE : COUNTERS;
+  static const int BYTES    = COUNTERS + XPOSE;                                 //  [counters][transpose area == stage]
 };
 
 __device__ __forceinline__ void key_zero(u32 &k)        { k = 0; }
 __device__ __forceinline__ void key_zero(u64 &k)        { k = 0; }
 __device__ __forceinline__ void key_zero(ulonglong2 &k) { k.x = 0; k.y = 0; }
 
-template <int KW>
-__global__ void __launch_bounds__(SORT_THREADS, SortShape<KW>::MIN_CTAS)
-sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
-                  const TileInfo *__restrict__ info,
-                  const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
-                  u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch, u64 *__restrict__ prof) {
+//  The work of one tile.  FULL: the tile holds exactly TILE keys, so the per-key bounds checks vanish
+//  (all tiles but the last one of each segment); the kernel picks the variant per tile, uniformly.
+struct SweepShared {
+  unsigned char *buf;  u32 *binOff;  u64 *gofs;  u32 *warpTot;
+};
+
+template <int KW, bool FULL>
+__device__ __forceinline__ void
+sweep_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+           u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
+           const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
+           u64 *__restrict__ status, u32 epoch, const SweepShared &sm,
+           u64 *prof, long long &tk2, long long &tk3, long long &tk4, long long &tk5) {
   typedef typename KeyT<KW>::type Key;
   typedef SweepSmem<KW>           S;
   const int ITEMS = SortShape<KW>::ITEMS;
-
-  //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[1..6]
-  long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
 #define MB_TICK(i) do { if (prof && threadIdx.x == 0) tk##i = clock64(); } while (0)
-  MB_TICK(0);
 
-  __shared__ __align__(16) unsigned char buf[S::BYTES];
-  __shared__ u32  binOff[MB_RADIX + 1];
-  __shared__ u64  gofs[MB_RADIX];
-  __shared__ u32  warpTot[SORT_WARPS];
-  __shared__ u64  sTile;
-
-  Key *xpose    = (Key *)buf;
-  u32 *counters = (u32 *)buf;
-  Key *stage    = (Key *)buf;
+  u32 *counters = (u32 *)sm.buf;
+  Key *xpose    = (Key *)(sm.buf + S::COUNTERS);
+  Key *stage    = xpose;
+  u32 *binOff   = sm.binOff;
+  u64 *gofs     = sm.gofs;
+  u32 *warpTot  = sm.warpTot;
 
   const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
-
-  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
-  __syncthreads();
-  MB_TICK(1);                                            //  1: tile id
-
-  const u64 tile = sTile;
-  const TileInfo ti = info[tile];
-  const u64  begin   = ti.begin;
-  const u32  n       = ti.n;
-  const u32  seg     = ti.seg & 0x7fffffffu;
-  const bool isFirst = (ti.seg >> 31) != 0;
+  const u32 n = FULL ? (u32)S::TILE : nIn;
 
   //  1. load striped (coalesced), transpose to blocked: thread t ends up with keys [t*ITEMS, (t+1)*ITEMS)
   Key key[ITEMS];
   {
-    const u32 wbase = warp * 32 * ITEMS;                 //  the warp's slice is private: only __syncwarp needed
+    //  The warp's slice is private: only __syncwarp needed.  One padding key per 128 bytes; ITEMS keys are
+    //  exactly 128 bytes, so the padded index of key j = t*ITEMS + i is t*(ITEMS+1) + i, and that of the
+    //  striped key wbase + i*32 + lane is w0 + i*(32 + 32/PAD) -- constant strides the compiler can fold.
+    const u32 wbase = warp * 32 * ITEMS;
+    const u32 w0    = wbase + wbase / S::PAD_EVERY + lane + lane / S::PAD_EVERY;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
-      const u32 j = wbase + i * 32 + lane;
       Key k;
-      if (j < n) k = in[begin + j]; else key_zero(k);
-      xpose[j + j / S::PAD_EVERY] = k;
+      if (FULL || wbase + i * 32 + lane < n) k = in[begin + wbase + i * 32 + lane]; else key_zero(k);
+      xpose[w0 + i * (32 + 32 / S::PAD_EVERY)] = k;
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      const u32 j = t * ITEMS + i;
-      key[i] = xpose[j + j / S::PAD_EVERY];
-    }
+    for (int i = 0; i < ITEMS; i++)
+      key[i] = xpose[t * (ITEMS + 1) + i];
   }
-  __syncthreads();                                       //  everybody has its keys: the buffer becomes the counters
+  //  (the transpose area is read only by the warp that wrote it; its next use, as the stage, comes after
+  //  several block-wide barriers)
 
   //  2. private counters.  Digit d lives in word (d & 31) of my column, half (d >> 5).
   for (u32 i = t; i < (u32)(S::CWORDS + S::CWORDS / 32); i += SORT_THREADS) counters[i] = 0;
   __syncthreads();
 
   const u32 myFirst = t * ITEMS;                         //  my keys are tile positions [myFirst, myFirst + ITEMS)
-  unsigned short prior[ITEMS];
+  const u32 tcol    = t + (t >> 5);                      //  my column in the padded counter array
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
-    prior[i] = 0;
-    if (myFirst + i < n) {
-      const u32 d    = key_field(key[i], shift, bits);
-      const u32 lin  = (d & 31) * SORT_THREADS + t;      //  (word-of-digit, thread): digit-major within each half
-      u32 *cp        = &counters[lin + (lin >> 5)];
-      const u32 sh16 = (d >> 5) * 16;
-      const u32 wv   = *cp;
-      prior[i] = (unsigned short)((wv >> sh16) & 0xffff);
-      *cp = wv + (1u << sh16);
+    if (FULL || myFirst + i < n) {
+      const u32 d = key_field(key[i], shift, bits);
+      //  word (d & 31) of my column: linear index (d&31)*256 + t, padded by one word per 32;
+      //  digits >= 32 use the high half-word
+      u32 *cp = &counters[(d & 31) * (SORT_THREADS + SORT_THREADS / 32) + tcol];
+      *cp += 1u << ((d & 32) >> 1);
     }
   }
   __syncthreads();
@@ -284,28 +273,15 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
   __syncthreads();
   MB_TICK(2);                                            //  2: keys loaded, counted, scanned
 
-  //  tile position of every key; start of every digit's run
-  //  (prior[] is overwritten in place by the final position; 0xffff marks the padding of a ragged tile)
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    if (myFirst + i < n) {
-      const u32 d   = key_field(key[i], shift, bits);
-      const u32 lin = (d & 31) * SORT_THREADS + t;
-      const u32 wv  = counters[lin + (lin >> 5)];
-      const u32 hi  = d >> 5;
-      prior[i] = (unsigned short)(((wv >> (hi * 16)) & 0xffff) + (hi ? tileLow : 0) + prior[i]);
-    } else {
-      prior[i] = 0xffff;
-    }
-  }
+  //  start of every digit's run (thread 0's slot of digit d holds it), then my keys go straight to their
+  //  place in the stage buffer: position = my (digit, thread) prefix, bumped as I walk my keys in order.
   if (t < MB_RADIX) {
-    const u32 lin = (t & 31) * SORT_THREADS;             //  thread 0's slot of digit t == first key of that digit
-    const u32 wv  = counters[lin + (lin >> 5)];
-    const u32 hi  = t >> 5;
-    binOff[t] = ((wv >> (hi * 16)) & 0xffff) + (hi ? tileLow : 0);
+    const u32 wv = counters[(t & 31) * (SORT_THREADS + SORT_THREADS / 32)];
+    const u32 hi = t & 32;
+    binOff[t] = ((wv >> (hi >> 1)) & 0xffff) + (hi ? tileLow : 0);
   }
   if (t == 0) binOff[MB_RADIX] = n;
-  __syncthreads();                                       //  counters fully consumed: the buffer becomes the stage
+  __syncthreads();                                       //  thread 0's column is read before its owner bumps it
 
   //  3a. publish this tile's digit counts as early as possible ...
   const u32 myCount = (t < MB_RADIX) ? binOff[t + 1] - binOff[t] : 0;
@@ -314,8 +290,16 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
 
   //  4a. ... put the keys in digit-sorted order in shared memory ...
 #pragma unroll
-  for (int i = 0; i < ITEMS; i++)
-    if (prior[i] != 0xffff) stage[prior[i]] = key[i];
+  for (int i = 0; i < ITEMS; i++) {
+    if (FULL || myFirst + i < n) {
+      const u32 d    = key_field(key[i], shift, bits);
+      u32 *cp        = &counters[(d & 31) * (SORT_THREADS + SORT_THREADS / 32) + tcol];
+      const u32 hi   = d & 32;
+      const u32 wv   = *cp;
+      *cp = wv + (1u << (hi >> 1));
+      stage[((wv >> (hi >> 1)) & 0xffff) + (hi ? tileLow : 0)] = key[i];
+    }
+  }
   MB_TICK(3);                                            //  3: reorder issued
 
   //  3b. ... and only then wait for the earlier tiles of this segment (batched walk: LB status words
@@ -353,6 +337,50 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
     const Key k = stage[j];
     out[gofs[key_field(k, shift, bits)] + j] = k;
   }
+#undef MB_TICK
+}
+
+template <int KW>
+__global__ void __launch_bounds__(SORT_THREADS, SortShape<KW>::MIN_CTAS)
+sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+                  const TileInfo *__restrict__ info,
+                  const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
+                  u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch, u64 *__restrict__ prof) {
+  typedef SweepSmem<KW> S;
+
+  //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[1..6]
+  long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
+#define MB_TICK(i) do { if (prof && threadIdx.x == 0) tk##i = clock64(); } while (0)
+  MB_TICK(0);
+
+  extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
+  __shared__ u32  binOff[MB_RADIX + 1];
+  __shared__ u64  gofs[MB_RADIX];
+  __shared__ u32  warpTot[SORT_WARPS];
+  __shared__ u64  sTile;
+
+  if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+  MB_TICK(1);                                            //  1: tile id
+
+  const u64 tile = sTile;
+  const TileInfo ti = info[tile];
+  const u32  seg     = ti.seg & 0x7fffffffu;
+  const bool isFirst = (ti.seg >> 31) != 0;
+  SweepShared sm;
+  sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.warpTot = warpTot;
+
+#ifdef MB_SWEEP_ONLY_FULL
+  if (true)
+#else
+  if (ti.n == (u32)S::TILE)
+#endif
+    sweep_tile<KW, true >(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, status, epoch, sm, prof, tk2, tk3, tk4, tk5);
+#ifndef MB_SWEEP_ONLY_FULL
+  else
+    sweep_tile<KW, false>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, status, epoch, sm, prof, tk2, tk3, tk4, tk5);
+#endif
+
   MB_TICK(6);                                            //  6: my stores issued
   if (prof && threadIdx.x == 0) {
     atomicAdd((unsigned long long *)&prof[1], (unsigned long long)(tk1 - tk0));
@@ -451,8 +479,9 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if (evAfterHist) cudaEventRecord(evAfterHist, s);
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
+  if ((e = cudaFuncSetAttribute(sort_sweep_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem<KW>::BYTES)) != cudaSuccess) return e;
   for (u32 p = 0; p < plan.nPasses; p++) {
-    sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, 0, s>>>(src, dst, info, ghist, plan.nPasses, p,
+    sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
                                                                    plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;
