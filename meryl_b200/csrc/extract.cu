@@ -33,6 +33,16 @@ namespace {
 
 //  ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ------------------------------------------
 
+#ifdef MB_CUSIM
+//  Host emulator used by the CPU tests (tests/cusim): the barrier word holds the phase, the bulk copy is a
+//  memcpy that completes at once.
+__device__ __forceinline__ void mbar_init(u64 *bar, u32)            { *bar = 0; }
+__device__ __forceinline__ void mbar_fence_init(void)               { }
+__device__ __forceinline__ void mbar_expect_tx(u64 *, u32)          { }
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) { if ((*bar & 1) != parity) return true; cusim::yield(); return false; }
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) { memcpy(dst, src, bytes); *bar ^= 1; cusim::g_progress++; }
+__device__ __forceinline__ void fence_proxy_async(void)             { }
+#else
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
@@ -57,6 +67,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 byt
 __device__ __forceinline__ void fence_proxy_async(void) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+#endif
 
 //  ---- bit helpers ---------------------------------------------------------------------------
 

@@ -89,6 +89,10 @@ __host__ __device__ __forceinline__ u64 key_shr64(const ulonglong2 &k, u32 shift
 #define MB_ST_INC   (2ull << 62)
 #define MB_ST_MASK  ((1ull << 62) - 1)
 
+#ifdef MB_CUSIM   //  host emulator used by the CPU tests (tests/cusim): a polling load lets the other fibers run
+__device__ __forceinline__ u64  ld_volatile_u64(const u64 *p)  { cusim::yield(); return *(const volatile u64 *)p; }
+__device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) { *(volatile u64 *)p = v; cusim::g_progress++; }
+#else
 __device__ __forceinline__ u64 ld_volatile_u64(const u64 *p) {
   u64 v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -97,6 +101,7 @@ __device__ __forceinline__ u64 ld_volatile_u64(const u64 *p) {
 __device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+#endif
 
 //  ---- launch entry points (each returns cudaGetLastError()) ----------------------------
 

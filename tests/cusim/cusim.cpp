@@ -1,0 +1,171 @@
+//  cusim runtime: fibers + block scheduler.  TEST INFRASTRUCTURE ONLY (see cusim.h).
+#include "cusim.h"
+
+#include <sys/mman.h>
+#include <time.h>
+#include <vector>
+
+#if !defined(__x86_64__)
+#error "cusim's context switch is written for x86-64"
+#endif
+
+//  cusim_switch(&fromSp, toSp): save callee-saved registers on the current stack, switch stacks.
+extern "C" void cusim_switch(void **fromSp, void *toSp);
+asm(".text\n"
+    ".globl cusim_switch\n"
+    ".type cusim_switch,@function\n"
+    "cusim_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size cusim_switch,.-cusim_switch\n");
+
+namespace cusim {
+
+Fiber   *g_cur = nullptr;
+uint3    g_blockIdx;
+dim3     g_blockDim, g_gridDim;
+unsigned long long g_clock = 0, g_progress = 0;
+
+namespace {
+
+const size_t kStackBytes = (size_t)256 << 10;
+const unsigned kMaxThreads = 1024;
+
+unsigned char *g_stacks = nullptr;
+void          *g_schedSp = nullptr;
+std::vector<Fiber> g_fibers;
+std::vector<Warp>  g_warps;
+const std::function<void()> *g_body = nullptr;
+unsigned g_alive = 0, g_barArrived = 0, g_barGen = 0;
+unsigned char *g_dynSmem = nullptr;
+size_t   g_dynCap = 0;
+unsigned long long g_launches = 0;
+
+void fiber_main() {
+  (*g_body)();
+  Fiber *f = g_cur;
+  f->done = true;
+  f->warp->alive &= ~(1u << f->lane);
+  g_alive--;
+  g_progress++;
+  //  an exited thread no longer takes part in barriers: release whoever is waiting for it
+  if (g_alive && g_barArrived == g_alive) { g_barArrived = 0; g_barGen++; }
+  if (f->warp->alive && f->warp->arrived && f->warp->arrived == (unsigned)__builtin_popcount(f->warp->alive)) { f->warp->arrived = 0; f->warp->gen++; }
+  cusim_switch(&f->sp, g_schedSp);
+  abort();                                              //  a finished fiber is never resumed
+}
+
+void prepare(Fiber &f, unsigned idx) {
+  unsigned char *top = g_stacks + (size_t)(idx + 1) * kStackBytes;
+  void **sp = (void **)top;
+  *--sp = nullptr;                                      //  fake return address of fiber_main (keeps the ABI alignment)
+  *--sp = (void *)fiber_main;
+  for (int i = 0; i < 6; i++) *--sp = nullptr;         //  rbp rbx r12 r13 r14 r15
+  f.sp = sp;
+}
+
+}  //  namespace
+
+void *dyn_smem(void) { return g_dynSmem; }
+
+//  "Device" allocations: anonymous mappings (large arenas stay untouched until used); small ones are
+//  filled with garbage, like fresh device memory, so a kernel cannot rely on zeroed buffers.
+void *dev_alloc(size_t bytes) {
+  const size_t total = ((bytes ? bytes : 1) + 4096 + 4095) / 4096 * 4096;
+  unsigned char *p = (unsigned char *)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  if (p == MAP_FAILED) return nullptr;
+  *(size_t *)p = total;
+  if (bytes <= ((size_t)64 << 20)) memset(p + 4096, 0xa5, bytes);
+  return p + 4096;
+}
+void dev_free(void *q) {
+  if (!q) return;
+  unsigned char *p = (unsigned char *)q - 4096;
+  munmap(p, *(size_t *)p);
+}
+unsigned long long launches(void) { return g_launches; }
+
+void yield(void) {
+  g_clock++;
+  Fiber *f = g_cur;
+  cusim_switch(&f->sp, g_schedSp);
+}
+
+void block_barrier(void) {
+  const unsigned gen = g_barGen;
+  if (++g_barArrived == g_alive) { g_barArrived = 0; g_barGen++; g_progress++; return; }
+  while (g_barGen == gen) yield();
+}
+
+void warp_barrier(unsigned mask) {
+  Warp *w = g_cur->warp;
+  const unsigned expect = (unsigned)__builtin_popcount(w->alive & mask);
+  const unsigned gen = w->gen;
+  if (++w->arrived >= expect) { w->arrived = 0; w->gen++; g_progress++; return; }
+  while (w->gen == gen) yield();
+}
+
+void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &body) {
+  const unsigned nThreads = block.x * block.y * block.z;
+  if (nThreads == 0 || nThreads > kMaxThreads) { fprintf(stderr, "cusim: bad block size %u\n", nThreads); abort(); }
+  if (g_cur) { fprintf(stderr, "cusim: nested launch\n"); abort(); }
+  if (!g_stacks) {
+    g_stacks = (unsigned char *)mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (g_stacks == MAP_FAILED) { perror("cusim: mmap"); abort(); }
+  }
+  if (dynSmem > g_dynCap) { free(g_dynSmem); g_dynSmem = (unsigned char *)aligned_alloc(128, (dynSmem + 127) / 128 * 128); g_dynCap = dynSmem; }
+  if (dynSmem > (size_t)227 << 10) { fprintf(stderr, "cusim: %zu bytes of dynamic shared memory exceed the 227 KB of an SM\n", dynSmem); abort(); }
+  g_launches++;
+  g_body = &body;
+  static const bool trace = getenv("CUSIM_TRACE") != nullptr;
+  struct timespec t0;  clock_gettime(CLOCK_MONOTONIC, &t0);
+  g_blockDim = block;  g_gridDim = grid;
+  const unsigned nWarps = (nThreads + 31) / 32;
+  g_fibers.resize(nThreads);
+  g_warps.resize(nWarps);
+
+  for (unsigned bz = 0; bz < grid.z; bz++)
+  for (unsigned by = 0; by < grid.y; by++)
+  for (unsigned bx = 0; bx < grid.x; bx++) {
+    g_blockIdx.x = bx;  g_blockIdx.y = by;  g_blockIdx.z = bz;
+    if (g_dynSmem) memset(g_dynSmem, 0xcd, g_dynCap);   //  shared memory starts as garbage
+    for (unsigned w = 0; w < nWarps; w++) { g_warps[w].alive = 0; g_warps[w].arrived = 0; g_warps[w].gen = 0; }
+    for (unsigned t = 0; t < nThreads; t++) {
+      Fiber &f = g_fibers[t];
+      f.linear = t;
+      f.tid.x = t % block.x;  f.tid.y = (t / block.x) % block.y;  f.tid.z = t / (block.x * block.y);
+      f.lane = t & 31;  f.warpId = t >> 5;  f.warp = &g_warps[t >> 5];
+      f.warp->alive |= 1u << f.lane;
+      f.done = false;
+      prepare(f, t);
+    }
+    g_alive = nThreads;  g_barArrived = 0;  g_barGen = 0;
+    unsigned long long lastProgress = g_progress, idleRounds = 0;
+    while (g_alive) {
+      for (unsigned t = 0; t < nThreads; t++) {
+        Fiber &f = g_fibers[t];
+        if (f.done) continue;
+        g_cur = &f;
+        cusim_switch(&g_schedSp, f.sp);
+      }
+      g_cur = nullptr;
+      if (g_progress != lastProgress) { lastProgress = g_progress; idleRounds = 0; }
+      else if (++idleRounds > 200000) {
+        fprintf(stderr, "cusim: block (%u,%u,%u) makes no progress (%u threads alive): deadlock or a wait on a block that has not run\n", bx, by, bz, g_alive);
+        abort();
+      }
+    }
+    g_cur = nullptr;
+  }
+  g_body = nullptr;
+  if (trace) {
+    struct timespec t1;  clock_gettime(CLOCK_MONOTONIC, &t1);
+    fprintf(stderr, "cusim: launch %llu grid (%u,%u,%u) block %u smem %zu: %.3f s\n", g_launches, grid.x, grid.y, grid.z, nThreads, dynSmem,
+            (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+  }
+}
+
+}  //  namespace cusim

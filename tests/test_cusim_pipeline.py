@@ -1,0 +1,96 @@
+"""The product's CUDA sources, run on the CPU.
+
+This container has no GPU, so the kernels' indexing / synchronisation logic is checked here with the
+cusim host emulator (tests/cusim: every CUDA thread is a fiber, barriers and warp collectives are
+rendezvous points, TMA bulk copies are memcpys).  tests/cusim/Makefile rewrites every .cu file of
+meryl_b200/csrc and builds a library with the same C ABI; these tests drive it exactly like the GPU
+parity tests drive libmeryl_b200.so and compare with the oracle / golden dbs byte for byte.
+
+This is TEST INFRASTRUCTURE: it proves the kernel logic, not the speed, and it is no fallback -- the
+product library still refuses to run without a CUDA device (tests/test_host_logic.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import synth
+
+SIM_DIR = os.path.join(util.ROOT, "tests", "cusim")
+SIM_LIB = os.path.join(SIM_DIR, "_build", "libmeryl_b200_sim.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def sim_library():
+    subprocess.run(["make", "-s", "-j8", "-C", SIM_DIR], check=True)
+    saved = (mb.LIB_PATH, mb._lib)
+    mb.LIB_PATH, mb._lib = SIM_LIB, None
+    yield
+    mb.LIB_PATH, mb._lib = saved
+
+
+def _vs_oracle(tmp_path, files, k, w_prefix, op="count", workspace_bytes=0, expect_key_bytes=None, min_passes=1):
+    paths = []
+    for name, data in files.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        paths.append(str(p))
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=%d" % w_prefix, op, *paths, "output", ora])
+    with mb.Counter(k, w_prefix, op, workspace_bytes=workspace_bytes) as c:
+        for p in paths:
+            c.add_file(p)
+        c.count()
+        st = c.stats()
+        c.write_db(out)
+    util.assert_same_db(ora, out)
+    if expect_key_bytes is not None:
+        assert st.keyBytes == expect_key_bytes
+    assert st.nPasses >= min_passes
+    return st
+
+
+@pytest.mark.parametrize("name", ["edge_k21", "edge_k8_simple"])
+def test_sim_golden(tmp_path, name):
+    inp, gold, words, _ = util.load_golden(name, str(tmp_path))
+    k = int([w for w in words if w.startswith("k=")][0][2:])
+    mem = float([w for w in words if w.startswith("memory=")][0][7:])
+    out = str(tmp_path / "sim.meryl")
+    mb.count([inp], out, k, "count", memory_gb=mem)
+    util.assert_same_db(gold, out)
+
+
+@pytest.mark.parametrize("k,w_prefix,key_bytes", [(21, 10, 4), (19, 8, 4), (22, 8, 8), (31, 7, 8), (32, 6, 8), (33, 6, 16), (51, 8, 16), (64, 6, 16), (8, 6, 4)])
+def test_sim_k_sweep(tmp_path, k, w_prefix, key_bytes):
+    """u32 suffix keys (2k - binBits <= 32), u64 keys and 128-bit keys through the same kernels."""
+    _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 6_000, 100 + k)}, k, w_prefix, expect_key_bytes=key_bytes)
+
+
+@pytest.mark.parametrize("op", ["count-forward", "count-reverse"])
+def test_sim_forward_reverse(tmp_path, op):
+    _vs_oracle(tmp_path, {"a.fq": synth.reads_fastq_bytes(3_000, 150, 120, 0.01, 5)}, 21, 8, op=op)
+
+
+def test_sim_reads_with_errors_and_ragged_tiles(tmp_path):
+    """More than one sort tile per segment (full + ragged tiles, look-back between tiles)."""
+    _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 3_000, 150, 0.003, 9)}, 21, 6, expect_key_bytes=8)
+    (tmp_path / "b").mkdir()
+    _vs_oracle(tmp_path / "b", {"r.fq": synth.reads_fastq_bytes(20_000, 3_000, 150, 0.003, 9)}, 19, 6, expect_key_bytes=4)
+
+
+def test_sim_low_complexity(tmp_path):
+    rng = np.random.default_rng(5)
+    unit = synth.random_bases(500, rng).tobytes()
+    recs = [b">r%d\n" % i + unit[: 100 + (1 + (i * 7) % 40) * 9] + b"\n" for i in range(60)]
+    recs.append(b">polyA\n" + b"A" * 20_000 + b"\n")
+    recs.append(b">polyAC\n" + b"AC" * 9_000 + b"\nNNNN\n")
+    recs.append(b">short\nACG\n>empty\n\n")
+    _vs_oracle(tmp_path, {"rep.fa": b"".join(recs)}, 21, 8)
+
+
+def test_sim_multi_pass(tmp_path):
+    """A tiny arena forces several prefix-range passes (both key forms); the db must not change."""
+    data = {"r.fq": synth.reads_fastq_bytes(30_000, 4_000, 150, 0.002, 77)}
+    _vs_oracle(tmp_path, data, 21, 12, workspace_bytes=300 << 20, expect_key_bytes=4)
