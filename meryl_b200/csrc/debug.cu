@@ -128,6 +128,7 @@ extern "C" int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits
   MB_CUDA(cudaMemcpy(a, host.data(), W * n, cudaMemcpyHostToDevice));
   MB_CUDA(cudaMemcpy(seg, segs, sizeof(segs), cudaMemcpyHostToDevice));
   int inB = 0;
+  plan.maxSegKeys = (n & 1) ? n : 0;                    //  exercise both the 32-bit and the 64-bit output offsets
   MB_CUDA(mb_launch_sort(W, a, b, n, seg, seg + 2, 1, nTiles, plan, ws, wsBytes, &inB, nullptr, 0, nullptr));
   MB_CUDA(cudaDeviceSynchronize());
   MB_CUDA(cudaMemcpy(host.data(), inB ? b : a, W * n, cudaMemcpyDeviceToHost));
@@ -156,6 +157,7 @@ extern "C" int mb_dbg_sort32(uint32_t *keys, uint64_t n, uint32_t bits) {
   MB_CUDA(cudaMemcpy(a, keys, 4 * n, cudaMemcpyHostToDevice));
   MB_CUDA(cudaMemcpy(seg, segs, sizeof(segs), cudaMemcpyHostToDevice));
   int inB = 0;
+  plan.maxSegKeys = (n & 1) ? n : 0;
   MB_CUDA(mb_launch_sort(4, a, b, n, seg, seg + 2, 1, nTiles, plan, ws, wsBytes, &inB, nullptr, 0, nullptr));
   MB_CUDA(cudaDeviceSynchronize());
   MB_CUDA(cudaMemcpy(keys, inB ? b : a, 4 * n, cudaMemcpyDeviceToHost));
@@ -220,4 +222,11 @@ extern "C" int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix
   cudaFree(dKeys); cudaFree(dRs); cudaFree(dTot); cudaFree(dFileBase); cudaFree(dMeta); cudaFree(dTmp);
   cudaFree(dOut); cudaFree(dSub); cudaFree(dIdx);
   return rc;
+}
+
+//  Select the sweep kernel (1: 6-bit digits, 2: 8-bit digits) for the contexts created afterwards; returns the previous one.
+extern "C" int mb_dbg_sort_version(int v) {
+  const int old = mb_sort_version();
+  if (v == 1 || v == 2) mb_sort_set_version(v);
+  return old;
 }

@@ -486,8 +486,9 @@ static int runCount(mb_ctx *c) {
   if (encBytes > R / 2) encBytes = R / 2;
   u32 tileKeys = mb_sort_tile_keys(W);
   //  per key: two key buffers + tile status; fixed: ragged tiles and tables of every segment
-  const double perKey = 2.0 * W + (double)MB_RADIX * 8 / tileKeys + 16.0 / tileKeys;
-  const size_t fixed  = (size_t)nBins * (MB_RADIX * 8 + 16 * MB_RADIX * 8) + ((size_t)8 << 20);
+  const u32 radix = mb_sort_radix();
+  const double perKey = 2.0 * W + (double)radix * 8 / tileKeys + 16.0 / tileKeys;
+  const size_t fixed  = (size_t)nBins * (radix * 8 + 16 * radix * 8) + ((size_t)8 << 20);
   if (R < encBytes + fixed + ((size_t)64 << 20)) return mb_fail(MB_ENOMEM, "device arena too small: %zu bytes left after the read store", R);
   u64 capKeys = (u64)((double)(R - encBytes - fixed) / perKey);
   capKeys = capKeys / 4096 * 4096;
@@ -523,7 +524,7 @@ static int runCount(mb_ctx *c) {
       //  u32 keys: 2 x 4 B per key + tile status; counted groups of a pass are expanded to u64 into the
       //  spare key buffer (<= half a pass at a time) and the encode region.
       const u32 tile32 = mb_sort_tile_keys(4);
-      const double perKey32 = 2.0 * 4 + (double)MB_RADIX * 8 / tile32 + 16.0 / tile32;
+      const double perKey32 = 2.0 * 4 + (double)radix * 8 / tile32 + 16.0 / tile32;
       size_t enc32 = std::max<size_t>((size_t)4 << 30, (size_t)nBlocksTotal * 200);
       if (enc32 > R / 3) enc32 = R / 3;
       if (R > enc32 + fixed + ((size_t)64 << 20)) {
@@ -671,6 +672,8 @@ static int runCount(mb_ctx *c) {
 
     //  ---- K4 ---------------------------------------------------------------------------------
     int inSpare = 0;  u32 nl = 0;
+    plan.maxSegKeys = 1;
+    for (u64 cnt : P.segCount) if (cnt > plan.maxSegKeys) plan.maxSegKeys = cnt;
     tSortHist.start(s);
     MB_CUDA(mb_launch_sort(keyBytes, unsorted, spare, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inSpare, &nl, s, evAfterHist));
     tStage.stop(s);                                   //  [evAfterHist, tStage.b] = the sweep passes

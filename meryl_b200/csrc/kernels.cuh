@@ -35,6 +35,8 @@ typedef unsigned int       u32;
 #define MB_MAX_BINS          1024       //  2^10 prefix bins
 #define MB_RADIX_BITS        6          //  LSD digit width: 64 digits = 32 words of two 16-bit private counters per thread
 #define MB_RADIX             64
+#define MB_RADIX2_BITS       8          //  sweep kernel v2: 256 digits, 128 threads x 64 words of two 16-bit private counters
+#define MB_RADIX2            256
 
 //  ---- key helpers -----------------------------------------------------------------------
 
@@ -89,6 +91,13 @@ __host__ __device__ __forceinline__ u64 key_shr64(const ulonglong2 &k, u32 shift
 #define MB_ST_INC   (2ull << 62)
 #define MB_ST_MASK  ((1ull << 62) - 1)
 
+//  Hide a pointer's provenance from the optimiser (it otherwise re-associates base + index arithmetic).
+#ifdef MB_CUSIM
+#define MB_OPAQUE_PTR(p) do { } while (0)
+#else
+#define MB_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
+#endif
+
 #ifdef MB_CUSIM   //  host emulator used by the CPU tests (tests/cusim): a polling load lets the other fibers run
 __device__ __forceinline__ u64  ld_volatile_u64(const u64 *p)  { cusim::yield(); return *(const volatile u64 *)p; }
 __device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) { *(volatile u64 *)p = v; cusim::g_progress++; }
@@ -135,7 +144,12 @@ struct MbSortPlan {
   u32  nPasses;
   u32  shift[24];
   u32  bits[24];
+  u64  maxSegKeys;             //  longest segment, if the caller knows it (0 = unknown): < 2^32 enables 32-bit output offsets
 };
+int         mb_sort_version(void);                          //  1: 6-bit digits (sort_sweep_kernel), 2: 8-bit digits (sort2_sweep_kernel); env MB_SORT
+void        mb_sort_set_version(int v);
+u32         mb_sort_radix_bits(void);
+u32         mb_sort_radix(void);
 void        mb_sort_plan(u32 sortBits, MbSortPlan *plan);
 u32         mb_sort_tile_keys(u32 keyBytes);                //  keyBytes: 4 (u32 suffix keys), 8 or 16
 size_t      mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses);

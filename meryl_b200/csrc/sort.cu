@@ -25,6 +25,15 @@
 //
 //  Algorithmic HBM bytes per key: hist 1*W, each sweep pass 2*W (W = 4, 8 or 16 bytes), plus the
 //  tile status (512 B per tile written twice, read >= once).  Bound: HBM bandwidth.
+//
+//  Two sweep kernels share the tile table, the histogram and the scan (mb_sort_version()):
+//   v1  sort_sweep_kernel    256 threads x 32/16/8 keys, 6-bit digits  (32 suffix bits = 6 passes)
+//   v2  sort2_sweep_kernel   128 threads x 64/32/16 keys, 8-bit digits (32 suffix bits = 4 passes): the
+//       kernel is issue-bound, not DRAM-bound (ncu: 63 % issue slots busy at 21 % DRAM), so the lever is
+//       instructions per key over the whole sort: a third fewer passes at about the same instructions
+//       per key and pass.  256 digits x 128 threads x 16 bit = 64 KB of private counters + 32 KB of keys
+//       = 2 CTAs per SM; each thread carries 64 independent keys, which is where the latency hiding
+//       comes from at 8 warps per SM.
 
 #include <string.h>
 
@@ -87,18 +96,19 @@ sort_tiles_kernel(const u64 *__restrict__ segStart, const u64 *__restrict__ segT
 //  ---- histogram ------------------------------------------------------------------------------
 
 const int HIST_TILES_PER_CTA = 16;
+const int HIST_WORDS = 4096;                          //  24 passes x 64 digits, or 16 passes x 256 digits
 
 template <int KW>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
                  const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
-                 SortPassTable pt, u64 *__restrict__ ghist) {
+                 SortPassTable pt, u32 radix, u64 *__restrict__ ghist) {
   typedef typename KeyT<KW>::type Key;
   const int TILE = SORT_THREADS * SortShape<KW>::ITEMS;
-  __shared__ u32 sh[SORT_MAX_PASSES * MB_RADIX];
+  __shared__ u32 sh[HIST_WORDS];                      //  nPasses * radix <= HIST_WORDS (checked by the host)
 
   const u32 t = threadIdx.x;
-  for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) sh[i] = 0;
+  for (u32 i = t; i < pt.nPasses * radix; i += SORT_THREADS) sh[i] = 0;
   __syncthreads();
 
   const u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
@@ -113,9 +123,9 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
     while (segTile[s + 1] <= tile) s++;
     if (s != seg) {
       __syncthreads();
-      for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) {
+      for (u32 i = t; i < pt.nPasses * radix; i += SORT_THREADS) {
         const u32 c = sh[i];
-        if (c) { atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * MB_RADIX + i], (unsigned long long)c); sh[i] = 0; }
+        if (c) { atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * radix + i], (unsigned long long)c); sh[i] = 0; }
       }
       __syncthreads();
       seg = s;
@@ -128,24 +138,24 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
     for (u32 j = t; j < (u32)n; j += SORT_THREADS) {
       const Key key = keys[begin + j];
       for (u32 p = 0; p < pt.nPasses; p++)
-        atomicAdd(&sh[p * MB_RADIX + key_field(key, pt.shift[p], pt.bits[p])], 1u);
+        atomicAdd(&sh[p * radix + key_field(key, pt.shift[p], pt.bits[p])], 1u);
     }
   }
 
   __syncthreads();
-  for (u32 i = t; i < pt.nPasses * MB_RADIX; i += SORT_THREADS) {
+  for (u32 i = t; i < pt.nPasses * radix; i += SORT_THREADS) {
     const u32 c = sh[i];
-    if (c) atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * MB_RADIX + i], (unsigned long long)c);
+    if (c) atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * radix + i], (unsigned long long)c);
   }
 }
 
 //  ---- scan: counts -> first output index of each (segment, pass, digit) -------------------------
 
-__global__ void __launch_bounds__(MB_RADIX)
+__global__ void __launch_bounds__(256)
 sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 nPasses) {
-  __shared__ u64 warpSum[MB_RADIX / 32];
-  const u32 seg = blockIdx.x, pass = blockIdx.y, d = threadIdx.x;
-  u64 *h = ghist + ((u64)seg * nPasses + pass) * MB_RADIX;
+  __shared__ u64 warpSum[8];
+  const u32 seg = blockIdx.x, pass = blockIdx.y, d = threadIdx.x;       //  blockDim.x == radix (64 or 256)
+  u64 *h = ghist + ((u64)seg * nPasses + pass) * blockDim.x;
 
   const u64 c = h[d];
   u64 incl = c;
@@ -394,22 +404,309 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
 #undef MB_TICK
 }
 
+//  ---- v2: one 8-bit digit pass --------------------------------------------------------------------
+//
+//  Same algorithm as sort_sweep_kernel (blocked keys, private 16-bit counters, raking scan, publish,
+//  reorder in shared memory, look-back inside the segment, coalesced digit runs), reshaped for 256 digits:
+//    * 128 threads, each owning 64 / 32 / 16 consecutive keys (256 bytes);
+//    * counter word (d & 127, t) holds digit d in its low and digit d + 128 in its high half; a row (all
+//      threads of one digit pair) is 128 words + 4 words of padding, so thread t rakes row t with 128-bit
+//      shared-memory accesses, bank-conflict free;
+//    * thread t publishes / resolves digits t and t + 128.
+
+const int S2_THREADS = 128;
+const int S2_WARPS   = S2_THREADS / 32;
+const int S2_ROW     = S2_THREADS + 4;                 //  words per counter row (16-byte aligned, 4-bank skew per row)
+
+template <int KW> struct Sort2Shape;
+template <> struct Sort2Shape<0> { static const int ITEMS = 64; };   //  u32 suffix keys: 8192 per tile
+template <> struct Sort2Shape<1> { static const int ITEMS = 32; };   //  u64: 4096 per tile
+template <> struct Sort2Shape<2> { static const int ITEMS = 16; };   //  128 bit: 2048 per tile
+
+template <int KW> struct Sweep2Smem {
+  typedef typename KeyT<KW>::type Key;
+  static const int ITEMS    = Sort2Shape<KW>::ITEMS;
+  static const int TILE     = S2_THREADS * ITEMS;
+  static const int XPOSE    = (TILE + S2_THREADS) * sizeof(Key);                 //  one padding key per thread (ITEMS + 1 stride)
+  static const int CWORDS   = (MB_RADIX2 / 2) * S2_ROW;
+  static const int COUNTERS = CWORDS * 4;                                        //  67584 bytes
+  static const int BYTES    = COUNTERS + XPOSE;                                  //  [counters][transpose area == stage]
+};
+
+struct Sweep2Shared {
+  unsigned char *buf;  u32 *binOff;  u64 *gofs;  u32 *gofs32;  u32 *warpTot;
+};
+
+//  Digit of a pass.  BYTE: the digit is one whole byte of the key (8 bits at a multiple of 8) -- a single
+//  PRMT instead of shift + mask; the v2 pass plan makes every pass but possibly the top one of this form.
+template <bool BYTE> __device__ __forceinline__ u32 digit_of(u32 k, u32 shift, u32 bits) {
+  return BYTE ? __byte_perm(k, 0, 0x4440 | (shift >> 3)) : key_field(k, shift, bits);
+}
+template <bool BYTE> __device__ __forceinline__ u32 digit_of(u64 k, u32 shift, u32 bits) {
+  if (!BYTE) return key_field(k, shift, bits);
+  const u32 w = (shift & 32) ? (u32)(k >> 32) : (u32)k;
+  return __byte_perm(w, 0, 0x4440 | ((shift >> 3) & 3));
+}
+template <bool BYTE> __device__ __forceinline__ u32 digit_of(const ulonglong2 &k, u32 shift, u32 bits) {
+  if (!BYTE) return key_field(k, shift, bits);
+  const u64 v = (shift & 64) ? k.y : k.x;
+  const u32 w = (shift & 32) ? (u32)(v >> 32) : (u32)v;
+  return __byte_perm(w, 0, 0x4440 | ((shift >> 3) & 3));
+}
+
+//  16-bit counter of (digit d, thread t): row d & 127, low half for d < 128.  cbOff = 4 t; the result is
+//  buf + (d & 127) * ROWBYTES + (d >> 7) * 2 + 4 t, written so that it compiles to a shift and two multiply-adds.
+__device__ __forceinline__ unsigned short *counter_of(unsigned char *buf, u32 cbOff, u32 d) {
+  u32 off = d * (S2_ROW * 4) + cbOff;
+  off -= (d >> 7) * (128 * S2_ROW * 4 - 2);
+  return (unsigned short *)(buf + off);
+}
+
+template <int KW, bool FULL, bool BYTE>
+__device__ __forceinline__ void
+sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+            u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
+            const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, bool wide,
+            u64 *__restrict__ status, u32 epoch, const Sweep2Shared &sm) {
+  typedef typename KeyT<KW>::type Key;
+  typedef Sweep2Smem<KW>          S;
+  const int ITEMS = S::ITEMS;
+
+  u32 *counters = (u32 *)sm.buf;
+  Key *xpose    = (Key *)(sm.buf + S::COUNTERS);
+  Key *stage    = xpose;
+  u32 *binOff   = sm.binOff;
+  u64 *gofs     = sm.gofs;
+  u32 *gofs32   = sm.gofs32;
+  u32 *warpTot  = sm.warpTot;
+
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const u32 n = FULL ? (u32)S::TILE : nIn;
+
+  //  1. load striped (coalesced), transpose to blocked: thread t ends up with keys [t*ITEMS, (t+1)*ITEMS).
+  //     Key j of the tile sits at xpose[j + j / ITEMS] (one padding key per thread: conflict-free blocked
+  //     reads); a warp only touches the slice of its own 32 threads, so __syncwarp is enough.
+  //     j = wbase + 32 i + lane: the padding term splits into constants the compiler folds into the addresses.
+  Key key[ITEMS];
+  {
+    const u32 wbase = warp * 32 * ITEMS;
+    const u32 w0    = wbase + wbase / ITEMS + lane + (ITEMS >= 32 ? 0 : lane / ITEMS);
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const u32 j = wbase + i * 32 + lane;
+      Key k;
+      if (FULL || j < n) k = in[begin + j]; else key_zero(k);
+      xpose[w0 + i * 32 + (i * 32) / ITEMS] = k;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+      key[i] = xpose[t * (ITEMS + 1) + i];
+  }
+
+  //  2. private counters: thread t zeroes row t, then bumps its 16-bit counter of each key's digit
+  {
+    uint4 *row = (uint4 *)&counters[t * S2_ROW];
+#pragma unroll
+    for (int j = 0; j < S2_ROW / 4; j++) row[j] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  const u32 myFirst = t * ITEMS;
+  const u32 cbOff = 4 * t;                               //  my column of the counter rows
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    if (FULL || myFirst + i < n) {
+      unsigned short *cp = counter_of(sm.buf, cbOff, digit_of<BYTE>(key[i], shift, bits));
+      *cp = (unsigned short)(*cp + 1);
+    }
+  }
+  __syncthreads();
+
+  //  raking scan, digit-major: thread t owns row t (digits t and t + 128 of all threads) as packed words.
+  //  Digits >= 128 (high halves) follow all digits < 128 in the stage: their prefixes start at tileLow.
+  {
+    uint4 *row = (uint4 *)&counters[t * S2_ROW];
+    u32 sum = 0;
+#pragma unroll
+    for (int j = 0; j < S2_THREADS / 4; j++) { const uint4 v = row[j]; sum += v.x + v.y + v.z + v.w; }
+    u32 incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32)o) incl += v;
+    }
+    if (lane == 31) warpTot[warp] = incl;
+    __syncthreads();
+    u32 run = incl - sum, tot = 0;
+#pragma unroll
+    for (int w = 0; w < S2_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) run += c; tot += c; }
+    run += tot << 16;                                    //  + tileLow in the high half (both halves stay <= 16384)
+    binOff[t]       = run & 0xffff;                      //  start of my two digits' runs in the tile
+    binOff[t + 128] = run >> 16;
+#pragma unroll
+    for (int j = 0; j < S2_THREADS / 4; j++) {
+      const uint4 v = row[j];
+      uint4 o;
+      o.x = run;  run += v.x;
+      o.y = run;  run += v.y;
+      o.z = run;  run += v.z;
+      o.w = run;  run += v.w;
+      row[j] = o;
+    }
+  }
+  if (t == 0) binOff[MB_RADIX2] = n;
+  __syncthreads();
+
+  //  3a. publish this tile's digit counts as early as possible ...
+  //  (digit 127's run ends where digit 128's begins, so binOff[d + 1] - binOff[d] holds for every d)
+  u32 myCount[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const u32 d = t + 128 * h;
+    myCount[h] = binOff[d + 1] - binOff[d];
+    st_volatile_u64(status + tile * MB_RADIX2 + d, ST_MAKE(isFirst ? 2 : 1, epoch, myCount[h]));
+  }
+
+  //  4a. ... put the keys in digit-sorted order in shared memory: my counter of the key's digit now holds the
+  //  place of my next key with that digit ...
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    if (FULL || myFirst + i < n) {
+      unsigned short *cp = counter_of(sm.buf, cbOff, digit_of<BYTE>(key[i], shift, bits));
+      const u32 pos = *cp;
+      *cp = (unsigned short)(pos + 1);
+      stage[pos] = key[i];
+    }
+  }
+
+  //  3b. ... and only then wait for the earlier tiles of this segment (batched walk, LB status words per
+  //  L2 round trip; the segment's first tile ends it).
+  const u64 segBase = gbase[((u64)seg * nPasses + pass) * MB_RADIX2];        //  first key of the segment (digit 0 starts there)
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int LB = 4;
+    const u32 d = t + 128 * h;
+    u64 excl = 0;
+    if (!isFirst) {
+      const u64 *p = status + (tile - 1) * MB_RADIX2 + d;
+      bool done = false;
+      while (!done) {
+        u64 v[LB];
+#pragma unroll
+        for (int b = 0; b < LB; b++) v[b] = ld_volatile_u64(p - (size_t)b * MB_RADIX2);   //  may read before the segment: ignored below
+#pragma unroll
+        for (int b = 0; b < LB; b++) {
+          if (done) break;
+          if (ST_FLAG(v[b]) == 0 || ST_EPOCH(v[b]) != epoch) break;                       //  not published yet: poll again from here
+          excl += ST_VALUE(v[b]);
+          p -= MB_RADIX2;
+          if (ST_FLAG(v[b]) == 2) done = true;
+        }
+      }
+      st_volatile_u64(status + tile * MB_RADIX2 + d, ST_MAKE(2, epoch, excl + myCount[h]));
+    }
+    const u64 g = gbase[((u64)seg * nPasses + pass) * MB_RADIX2 + d] + excl - binOff[d];   //  + stage index = global index
+    gofs[d]   = g;
+    gofs32[d] = (u32)(g - segBase);                      //  same, relative to the segment (mod 2^32)
+  }
+  __syncthreads();
+
+  //  4b. digit runs to HBM.  Segments shorter than 2^32 keys: 32-bit offsets from the segment's first key.
+  if (!wide) {
+    Key *outSeg = out + segBase;
+    MB_OPAQUE_PTR(outSeg);                               //  keep it a base pointer: one IMAD.WIDE per store instead of 64-bit index math
+    if (FULL) {
+#pragma unroll 16
+      for (u32 j = t; j < (u32)S::TILE; j += S2_THREADS) {
+        const Key k = stage[j];
+        outSeg[(u32)(gofs32[digit_of<BYTE>(k, shift, bits)] + j)] = k;
+      }
+    } else {
+      for (u32 j = t; j < n; j += S2_THREADS) {
+        const Key k = stage[j];
+        outSeg[(u32)(gofs32[digit_of<BYTE>(k, shift, bits)] + j)] = k;
+      }
+    }
+  } else {
+    for (u32 j = t; j < n; j += S2_THREADS) {
+      const Key k = stage[j];
+      out[gofs[digit_of<BYTE>(k, shift, bits)] + j] = k;
+    }
+  }
+}
+
+template <int KW>
+__global__ void __launch_bounds__(S2_THREADS, 2)
+sort2_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+                   const TileInfo *__restrict__ info,
+                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, u32 wide,
+                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
+  typedef Sweep2Smem<KW> S;
+  extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
+  __shared__ u32  binOff[MB_RADIX2 + 1];
+  __shared__ u64  gofs[MB_RADIX2];
+  __shared__ u32  gofs32[MB_RADIX2];
+  __shared__ u32  warpTot[S2_WARPS];
+  __shared__ u64  sTile;
+
+  if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+
+  const u64 tile = sTile;
+  const TileInfo ti = info[tile];
+  const u32  seg     = ti.seg & 0x7fffffffu;
+  const bool isFirst = (ti.seg >> 31) != 0;
+  Sweep2Shared sm;
+  sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.gofs32 = gofs32;  sm.warpTot = warpTot;
+
+  const bool full = (ti.n == (u32)S::TILE);
+  const bool byte = (bits == 8) && ((shift & 7) == 0);
+#define MB_S2_CALL(F, B) sweep2_tile<KW, F, B>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm)
+  if (full) { if (byte) MB_S2_CALL(true,  true); else MB_S2_CALL(true,  false); }
+  else      { if (byte) MB_S2_CALL(false, true); else MB_S2_CALL(false, false); }
+#undef MB_S2_CALL
+}
+
 }  //  namespace
 
 
+//  ---- host side ---------------------------------------------------------------------------------
+
+//  Which sweep kernel: 1 (6-bit digits) or 2 (8-bit digits).  MB_SORT=1|2 in the environment, or
+//  mb_sort_set_version(); fixed for the lifetime of a plan / workspace.
+static int g_sortVersion = 0;
+int mb_sort_version(void) {
+  if (g_sortVersion == 0) {
+    const char *e = getenv("MB_SORT");
+    g_sortVersion = (e && e[0] == '2') ? 2 : 1;
+  }
+  return g_sortVersion;
+}
+void mb_sort_set_version(int v) { g_sortVersion = (v == 2) ? 2 : 1; }
+u32  mb_sort_radix_bits(void)   { return mb_sort_version() == 2 ? MB_RADIX2_BITS : MB_RADIX_BITS; }
+u32  mb_sort_radix(void)        { return 1u << mb_sort_radix_bits(); }
+
 void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
-  const u32 P = (sortBits + MB_RADIX_BITS - 1) / MB_RADIX_BITS;
+  const u32 RB = mb_sort_radix_bits();
+  const u32 P = (sortBits + RB - 1) / RB;
   plan->nPasses = P;
+  plan->maxSegKeys = 0;
   u32 shift = 0;
   for (u32 p = 0; p < P; p++) {
-    const u32 b = sortBits / P + (p < sortBits % P ? 1 : 0);
+    //  v1: digits of (almost) equal width.  v2: whole bytes from the bottom (one PRMT per digit), the top
+    //  pass takes what is left.
+    u32 b = sortBits / P + (p < sortBits % P ? 1 : 0);
+    if (mb_sort_version() == 2) b = (sortBits - shift < 8) ? sortBits - shift : 8;
     plan->shift[p] = shift;
     plan->bits[p]  = b;
     shift += b;
   }
 }
 
-u32 mb_sort_tile_keys(u32 keyBytes) {
+u32 mb_sort_tile_keys(u32 keyBytes) {                  //  the same for both sweep kernels: 8192 / 4096 / 2048
+  static_assert(SORT_THREADS * SortShape<0>::ITEMS == S2_THREADS * Sort2Shape<0>::ITEMS, "tile size");
+  static_assert(SORT_THREADS * SortShape<1>::ITEMS == S2_THREADS * Sort2Shape<1>::ITEMS, "tile size");
+  static_assert(SORT_THREADS * SortShape<2>::ITEMS == S2_THREADS * Sort2Shape<2>::ITEMS, "tile size");
   return SORT_THREADS * (keyBytes == 4 ? SortShape<0>::ITEMS : keyBytes == 8 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
 }
 
@@ -418,19 +715,21 @@ static u64 *g_sortProf = nullptr;
 void mb_sort_set_profile_buffer(u64 *dProf) { g_sortProf = dProf; }
 
 //  workspace: [ghist: nSegs*nPasses*R u64][tile counters: 32 u64][guard: 8*R u64][status: nTiles*R u64][tile info: nTiles*16 B]
-//  (R = MB_RADIX; the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
-static const size_t kStatusGuard = 8 * MB_RADIX;
+//  (R = mb_sort_radix(); the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
 static const size_t kCounters    = 32;
+static size_t statusGuard(void) { return 8 * (size_t)mb_sort_radix(); }
 
 size_t mb_sort_workspace_bytes(u64 nTiles, u32 nSegs, u32 nPasses) {
-  return ((size_t)nSegs * nPasses * MB_RADIX + kCounters + kStatusGuard + (size_t)nTiles * MB_RADIX) * sizeof(u64) + (size_t)nTiles * sizeof(TileInfo) + 64;
+  const size_t R = mb_sort_radix();
+  return ((size_t)nSegs * nPasses * R + kCounters + statusGuard() + (size_t)nTiles * R) * sizeof(u64) + (size_t)nTiles * sizeof(TileInfo) + 64;
 }
 
 const void *mb_sort_tile_info(void *dWorkspace, u64 nTiles, u32 nSegs, u32 nPasses) {
+  const size_t R = mb_sort_radix();
   u64 *ghist   = (u64 *)dWorkspace;
-  u64 *counter = ghist + (size_t)nSegs * nPasses * MB_RADIX;
-  u64 *status  = counter + kCounters + kStatusGuard;
-  return (const void *)(((uintptr_t)(status + (size_t)nTiles * MB_RADIX) + 15) & ~(uintptr_t)15);
+  u64 *counter = ghist + (size_t)nSegs * nPasses * R;
+  u64 *status  = counter + kCounters + statusGuard();
+  return (const void *)(((uintptr_t)(status + (size_t)nTiles * R) + 15) & ~(uintptr_t)15);
 }
 
 template <int KW>
@@ -448,9 +747,14 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if (plan.nPasses > SORT_MAX_PASSES) return cudaErrorInvalidValue;
   if (workspaceBytes < mb_sort_workspace_bytes(nTiles, nSegs, plan.nPasses)) return cudaErrorInvalidValue;
 
+  const int    version = mb_sort_version();
+  const size_t R = mb_sort_radix();
+  //  v2 writes with 32-bit offsets from the segment start when every segment is known to be shorter than 2^32 keys
+  const u32    wide = (plan.maxSegKeys == 0 || plan.maxSegKeys >= ((u64)1 << 32)) ? 1 : 0;
+  if ((size_t)plan.nPasses * R > (size_t)HIST_WORDS) return cudaErrorInvalidValue;
   u64 *ghist   = (u64 *)dWorkspace;
-  u64 *counter = ghist + (size_t)nSegs * plan.nPasses * MB_RADIX;
-  u64 *status  = counter + kCounters + kStatusGuard;
+  u64 *counter = ghist + (size_t)nSegs * plan.nPasses * R;
+  u64 *status  = counter + kCounters + statusGuard();
   TileInfo *info = (TileInfo *)mb_sort_tile_info(dWorkspace, nTiles, nSegs, plan.nPasses);
   const u32 tileKeys = SORT_THREADS * SortShape<KW>::ITEMS;
 
@@ -463,7 +767,7 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     return cudaSuccess;
   }
 
-  const size_t zeroBytes = (size_t)((uint8_t *)(status + (size_t)nTiles * MB_RADIX) - (uint8_t *)dWorkspace);
+  const size_t zeroBytes = (size_t)((uint8_t *)(status + (size_t)nTiles * R) - (uint8_t *)dWorkspace);
   if ((e = cudaMemsetAsync(dWorkspace, 0, zeroBytes, s)) != cudaSuccess) return e;
 
   SortPassTable pt;
@@ -471,18 +775,23 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   for (u32 p = 0; p < SORT_MAX_PASSES; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
 
   const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
-  sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, ghist);
+  sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  sort_scan_kernel<<<dim3(nSegs, plan.nPasses), MB_RADIX, 0, s>>>(ghist, dSegStart, plan.nPasses);
+  sort_scan_kernel<<<dim3(nSegs, plan.nPasses), (unsigned)R, 0, s>>>(ghist, dSegStart, plan.nPasses);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (nLaunches) *nLaunches += 2;
   if (evAfterHist) cudaEventRecord(evAfterHist, s);
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
   if ((e = cudaFuncSetAttribute(sort_sweep_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem<KW>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sort2_sweep_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sweep2Smem<KW>::BYTES)) != cudaSuccess) return e;
   for (u32 p = 0; p < plan.nPasses; p++) {
-    sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
-                                                                   plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
+    if (version == 2)
+      sort2_sweep_kernel<KW><<<(unsigned)nTiles, S2_THREADS, Sweep2Smem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
+                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1);
+    else
+      sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
+                                                                     plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;
     Key *tmp = src; src = dst; dst = tmp;

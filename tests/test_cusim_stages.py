@@ -1,0 +1,93 @@
+"""Single device stages run in the cusim host emulator (see tests/test_cusim_pipeline.py): both sweep
+kernels of the segmented radix sort on adversarial key sets, through the same debug entry points the GPU
+stage tests use (meryl_b200/csrc/debug.cu)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+import meryl_b200 as mb
+
+SIM_DIR = os.path.join(util.ROOT, "tests", "cusim")
+SIM_LIB = os.path.join(SIM_DIR, "_build", "libmeryl_b200_sim.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def sim_library():
+    subprocess.run(["make", "-s", "-j8", "-C", SIM_DIR], check=True)
+    saved = (mb.LIB_PATH, mb._lib)
+    mb.LIB_PATH, mb._lib = SIM_LIB, None
+    yield
+    mb.LIB_PATH, mb._lib = saved
+
+
+@pytest.fixture(params=[1, 2], ids=["sweep6bit", "sweep8bit"])
+def sort_version(request):
+    L = mb.lib()
+    L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
+    old = L.mb_dbg_sort_version(request.param)
+    yield request.param
+    L.mb_dbg_sort_version(old)
+
+
+def _keys32(n, bits, kind, seed):
+    rng = np.random.default_rng(seed)
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if kind == "dups" and n > 10:
+        keys[: n // 3] = keys[n // 2]
+    elif kind == "equal":
+        keys[:] = 0xdeadbeef                     # one digit gets the whole tile in every pass
+    elif kind == "sorted":
+        keys = np.sort(keys)
+    elif kind == "reversed":
+        keys = np.sort(keys)[::-1].copy()
+    if bits < 32:
+        keys &= np.uint32((1 << bits) - 1)
+    return keys
+
+
+@pytest.mark.parametrize("n,bits,kind", [(0, 32, "random"), (1, 32, "random"), (33, 9, "random"), (8191, 32, "dups"), (8192, 32, "equal"),
+                                         (8193, 22, "random"), (30_000, 32, "dups"), (20_000, 32, "reversed"), (17_000, 8, "sorted")])
+def test_sim_sort_u32(n, bits, kind, sort_version):
+    keys = _keys32(n, bits, kind, n * 7 + bits)
+    got = keys.copy()
+    L = mb.lib()
+    rc = L.mb_dbg_sort32(got.ctypes.data, n, bits)
+    assert rc == 0, L.mb_last_error().decode()
+    assert np.array_equal(got, np.sort(keys))
+
+
+@pytest.mark.parametrize("n,bits", [(2, 64), (4095, 36), (4096, 56), (4097, 64), (13_000, 52), (9_000, 7)])
+def test_sim_sort_u64(n, bits, sort_version):
+    rng = np.random.default_rng(n * 131 + bits)
+    keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    if bits < 64:
+        keys &= np.uint64((1 << bits) - 1)
+    if n > 10:
+        keys[: n // 3] = keys[n // 2]
+    got = keys.copy()
+    L = mb.lib()
+    rc = L.mb_dbg_sort(got.ctypes.data, None, n, bits)
+    assert rc == 0, L.mb_last_error().decode()
+    assert np.array_equal(got, np.sort(keys))
+
+
+@pytest.mark.parametrize("n,bits", [(1, 128), (2047, 65), (2048, 92), (2049, 128), (7_000, 118)])
+def test_sim_sort_u128(n, bits, sort_version):
+    rng = np.random.default_rng(n * 17 + bits)
+    lo = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    hi = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    if bits < 128:
+        hi &= np.uint64((1 << (bits - 64)) - 1)
+    if n > 10:
+        hi[: n // 2] = hi[0]
+        lo[: n // 4] = lo[0]
+    order = np.lexsort((lo, hi))
+    glo, ghi = lo.copy(), hi.copy()
+    L = mb.lib()
+    rc = L.mb_dbg_sort(glo.ctypes.data, ghi.ctypes.data, n, bits)
+    assert rc == 0, L.mb_last_error().decode()
+    assert np.array_equal(glo, lo[order]) and np.array_equal(ghi, hi[order])

@@ -71,9 +71,19 @@ def test_extract_empty_and_no_kmers():
         assert len(glo) == 0
 
 
+@pytest.fixture(params=[1, 2], ids=["sweep6bit", "sweep8bit"])
+def sort_version(request):
+    """Both sweep kernels (csrc/sort.cu): v1 = 6-bit digits, v2 = 8-bit digits."""
+    L = mb.lib()
+    L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
+    old = L.mb_dbg_sort_version(request.param)
+    yield request.param
+    L.mb_dbg_sort_version(old)
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 4095, 4096, 4097, 100_000, 1_000_003])
 @pytest.mark.parametrize("bits", [1, 7, 8, 9, 32, 36, 56, 64])
-def test_sort_u64(n, bits):
+def test_sort_u64(n, bits, sort_version):
     rng = np.random.default_rng(n * 131 + bits)
     keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
     if bits < 64:
@@ -90,7 +100,7 @@ def test_sort_u64(n, bits):
 
 @pytest.mark.parametrize("n", [0, 1, 33, 8191, 8192, 8193, 100_000, 3_000_001])
 @pytest.mark.parametrize("bits", [1, 8, 9, 22, 32])
-def test_sort_u32(n, bits):
+def test_sort_u32(n, bits, sort_version):
     rng = np.random.default_rng(n * 7 + bits)
     keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
     if bits < 32:
@@ -107,7 +117,7 @@ def test_sort_u32(n, bits):
 
 @pytest.mark.parametrize("n", [0, 1, 2047, 2048, 2049, 300_001])
 @pytest.mark.parametrize("bits", [65, 70, 92, 118, 128])
-def test_sort_u128(n, bits):
+def test_sort_u128(n, bits, sort_version):
     rng = np.random.default_rng(n * 17 + bits)
     lo = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
     hi = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
