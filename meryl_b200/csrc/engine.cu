@@ -440,6 +440,8 @@ static int runCount(mb_ctx *c) {
   MbExtractParams xp;
   xp.store = (const u32 *)c->arena;  xp.nPositions = c->nRecords * 32;
   xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;  xp.suffix32 = 0;
+  xp.noPrefilter = getenv("MB_NO_PREFILTER") ? 1 : 0;
+  xp.keptPerMille = 0;
   xp.prof = g_extractProf;
 
   tStage.start(s);
@@ -492,6 +494,9 @@ static int runCount(mb_ctx *c) {
   if (R < encBytes + fixed + ((size_t)64 << 20)) return mb_fail(MB_ENOMEM, "device arena too small: %zu bytes left after the read store", R);
   u64 capKeys = (u64)((double)(R - encBytes - fixed) / perKey);
   capKeys = capKeys / 4096 * 4096;
+  //  testing knob: cap the keys of a pass so that small inputs exercise the multi-pass machinery
+  const u64 capLimit = getenv("MB_MAX_PASS_KEYS") ? strtoull(getenv("MB_MAX_PASS_KEYS"), nullptr, 10) : 0;
+  if (capLimit && capKeys > capLimit) capKeys = capLimit;
 
   std::vector<Pass> passes;
   u32 sortBits;
@@ -499,12 +504,27 @@ static int runCount(mb_ctx *c) {
   if (world == 1) {
     //  consecutive bins, as many as fit; segments = bins, sorted on the bits below the bin
     sortBits = 2 * k - binBits;
+    //  A pass is cut at a data-file boundary (a multiple of binsPerFile bins) whenever every file fits a pass:
+    //  the extraction kernel then tests pass membership on the first three bases alone (extract.cu).
+    bool fileCuts = true;
     auto planBins = [&](u64 cap, std::vector<Pass> &out) -> int {
       out.clear();
+      fileCuts = true;
+      for (u32 f = 0; f < 64 && fileCuts; f++) {
+        u64 inFile = 0;
+        for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) inFile += binCount[b];
+        if (inFile > cap) fileCuts = false;
+      }
       Pass cur;
       for (u32 b = 0; b < nBins; b++) {
         if (binCount[b] > cap) return -1;
-        if (cur.nKeys + binCount[b] > cap) {
+        bool cut = cur.nKeys + binCount[b] > cap;
+        if (fileCuts && b % binsPerFile == 0) {            //  would the whole file still fit?
+          u64 inFile = 0;
+          for (u32 bb = b; bb < b + binsPerFile; bb++) inFile += binCount[bb];
+          cut = cur.nKeys + inFile > cap;
+        } else if (fileCuts) cut = false;
+        if (cut && cur.nKeys > 0) {
           cur.binHi = b;  out.push_back(cur);
           cur = Pass();  cur.binLo = b;
         }
@@ -530,6 +550,7 @@ static int runCount(mb_ctx *c) {
       if (R > enc32 + fixed + ((size_t)64 << 20)) {
         u64 cap32 = (u64)((double)(R - enc32 - fixed) / perKey32);
         cap32 = cap32 / 8192 * 8192;
+        if (capLimit && cap32 > capLimit) cap32 = capLimit;
         std::vector<Pass> p32;
         if (planBins(cap32, p32) == 0) {
           bool ok = true;
@@ -650,6 +671,7 @@ static int runCount(mb_ctx *c) {
 
     //  ---- K2/K3 ------------------------------------------------------------------------------
     xp.binLo = P.binLo;  xp.binHi = P.binHi;  xp.suffix32 = suffix32 ? 1 : 0;
+    xp.keptPerMille = nLocalKmers ? (u32)std::max<u64>(1, P.nLocal * 1000 / nLocalKmers) : 0;
     tStage.start(s);
     if (P.nLocal) { MB_CUDA(mb_launch_extract(xp, bufA, dCtl->binStart, dCtl->binCursor, s)); c->st.nLaunches++; }
     tStage.stop(s);
@@ -953,7 +975,6 @@ static int runCount(mb_ctx *c) {
   tAll.stop(s);
   c->st.msTotal = tAll.ms();
   tAll.destroy();  tStage.destroy();
-  (void)nLocalKmers;
   c->counted = true;
   return MB_OK;
 }

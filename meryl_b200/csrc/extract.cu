@@ -107,6 +107,79 @@ __device__ __forceinline__ void revcomp128(u64 hi, u64 lo, u32 n, u64 &rhi, u64 
   rlo ^= 0xaaaaaaaaaaaaaaaaull;
 }
 
+//  ---- bit-sliced file-range filter ------------------------------------------------------------------
+//  A pass keeps the k-mers of a contiguous range of the 64 file prefixes (top 6 bits = first 3 bases of the
+//  canonical k-mer).  With F3(p) = value of bases p..p+2 and R3(p) = reverse-complement value of bases
+//  p+k-3..p+k-1, the canonical k-mer's file prefix is exactly min(F3, R3) (if the two differ the smaller one
+//  decides which strand is canonical; if they are equal both strands start alike).  So "is position p in
+//  this pass" is a pair of 6-bit comparisons -- evaluated here for all 32 positions of a thread at once,
+//  bit-sliced, instead of rolling two 2k-bit k-mers through every position only to drop most of them.
+//
+//  Slot word: slot p (0..31) = bits [63-2p, 62-2p]; a boolean of position p lives in the slot's top bit.
+
+//  Slot p = 2-bit code of thread-relative position p + o  (o < 96; positions beyond the window read as 0).
+__device__ __forceinline__ u64 win_slots(const Window &w, u32 o) {
+  const u32 s = 2 * (o & 31);
+  u64 a, b;
+  if (o < 32)      { a = w.w0; b = w.w1; }
+  else if (o < 64) { a = w.w1; b = w.w2; }
+  else             { a = w.w2; b = 0;    }
+  return s ? ((a << s) | (b >> (64 - s))) : a;
+}
+
+//  Running comparison "value >= bound" over bit planes fed most significant first (planes live in the slots' top
+//  bits).  Branch-free: m = all ones where the bound has a 1 in this plane.
+//    bound bit 1:  still-equal positions need a 1;             bound bit 0:  a 1 makes an equal position greater.
+struct GeChain {
+  u64 gt, eq;
+  __device__ __forceinline__ void init(void)            { gt = 0; eq = ~0ull; }
+  __device__ __forceinline__ void step(u64 x, u64 m)    { gt |= eq & x & ~m;  eq &= ~(x ^ m); }
+  __device__ __forceinline__ u64  ge(void) const        { return gt | eq; }
+};
+
+//  Slot mask (top bit of each slot) of the positions whose k-mer has its file prefix in [fLo, fHi), 0 <= fLo < fHi <= 64.
+//  Planes are produced and consumed one base at a time (few live registers).
+__device__ __forceinline__ u64 file_range_slots(const Window &w, u32 k, u32 mode, u32 fLo, u32 fHi) {
+  GeChain fl, fh, rl, rh;
+  fl.init();  fh.init();  rl.init();  rh.init();
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const u64 lo1 = 0ull - (u64)((fLo >> (5 - 2 * i)) & 1), lo0 = 0ull - (u64)((fLo >> (4 - 2 * i)) & 1);
+    const u64 hi1 = 0ull - (u64)((fHi >> (5 - 2 * i)) & 1), hi0 = 0ull - (u64)((fHi >> (4 - 2 * i)) & 1);
+    if (mode != MB_MODE_REVERSE) {
+      const u64 c = win_slots(w, i);                   //  base p + i: high bit in place, low bit one to the right
+      fl.step(c, lo1);  fl.step(c << 1, lo0);
+      fh.step(c, hi1);  fh.step(c << 1, hi0);
+    }
+    if (mode != MB_MODE_FORWARD) {
+      const u64 d = win_slots(w, k - 1 - i);           //  base p + k-1-i, complemented (code ^ 2: the high bit flips)
+      rl.step(~d, lo1);  rl.step(d << 1, lo0);
+      rh.step(~d, hi1);  rh.step(d << 1, hi0);
+    }
+  }
+  const u64 fGeLo = fl.ge(), rGeLo = rl.ge();
+  const u64 fGeHi = fHi >= 64 ? 0 : fh.ge(), rGeHi = fHi >= 64 ? 0 : rh.ge();
+  u64 m;
+  if      (mode == MB_MODE_FORWARD) m = fGeLo & ~fGeHi;
+  else if (mode == MB_MODE_REVERSE) m = rGeLo & ~rGeHi;
+  else                              m = fGeLo & rGeLo & ~(fGeHi & rGeHi);   //  lo <= min(F, R) < hi
+  return m & 0xaaaaaaaaaaaaaaaaull;
+}
+
+//  10 bits (5 bases) starting at slot q (0..31) of the 96 bits (v0:v1:v2).
+__device__ __forceinline__ u32 five_bases_at(u32 v0, u32 v1, u32 v2, u32 q) {
+  const u32 s = 2 * q;
+  const u32 x = (s < 32) ? __funnelshift_l(v1, v0, s) : __funnelshift_l(v2, v1, s - 32);
+  return x >> 22;
+}
+
+//  Reverse complement of a 5-base (10-bit) value.
+__device__ __forceinline__ u32 revcomp5(u32 v) {
+  u32 r = __brev(v) >> 22;
+  r = ((r >> 1) & 0x155u) | ((r & 0x155u) << 1);
+  return r ^ 0x2aau;
+}
+
 template <int KW> struct ExtractShape;
 template <> struct ExtractShape<1> { static const int THREADS = 256; };
 template <> struct ExtractShape<2> { static const int THREADS = 128; };
@@ -216,7 +289,7 @@ __device__ __forceinline__ void to_stored(u64 k, u64 &o)                        
 __device__ __forceinline__ void to_stored(const ulonglong2 &k, ulonglong2 &o)    { o = k; }
 
 template <int KW, bool COUNT_ONLY, bool S32>
-__global__ void __launch_bounds__(ExtractShape<KW>::THREADS)
+__global__ void __launch_bounds__(ExtractShape<KW>::THREADS, 4)
 extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict__ out,
                const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles, u32 stageCap) {
   typedef typename KeyT<KW>::type           Key;             //  what is computed
@@ -238,7 +311,18 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
 
   const u32 t = threadIdx.x;
   const u32 nBins = 1u << p.binBits;
-  const bool rollAgain = (p.binHi - p.binLo) * 3 >= nBins;      //  this pass keeps >= 1/3 of the k-mers
+  //  Does this pass keep >= 1/3 of the k-mers?  The caller knows (canonical k-mers are heavily skewed towards the
+  //  low bins, so the share of bins says little); without a hint, judge by the bins.
+  const bool rollAgain = p.keptPerMille ? (p.keptPerMille >= 333) : ((p.binHi - p.binLo) * 3 >= nBins);
+  //  file-aligned minority pass: bit-sliced membership test instead of rolling through every position
+  const u32  perFile   = p.binBits >= 6 ? (1u << (p.binBits - 6)) : 0;
+  const bool prefilter = !rollAgain && p.k >= 5 && p.binBits >= 6 && p.binBits <= 10 && !p.noPrefilter &&
+                         (p.binLo & (perFile - 1)) == 0 && (p.binHi & (perFile - 1)) == 0;
+  const u32  fLo = perFile ? p.binLo / perFile : 0, fHi = perFile ? p.binHi / perFile : 0;
+#ifdef MB_CUSIM
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !COUNT_ONLY && getenv("CUSIM_TRACE"))
+    fprintf(stderr, "cusim: extract bins [%u,%u) of %u: %s\n", p.binLo, p.binHi, nBins, prefilter ? "bit-sliced prefilter" : rollAgain ? "rolling" : "rolling + direct");
+#endif
 
   if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   for (u32 b = t; b < nT; b += blockDim.x) cnt[b] = 0;
@@ -287,7 +371,29 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
     const u64 rollMask = (KW == 1) ? ((p.k == 32) ? ~0ull : (((u64)1 << (2 * p.k)) - 1))
                                    : ((p.k == 64) ? ~0ull : (((u64)1 << (2 * p.k - 64)) - 1));
     u32 keep = 0;
-    if (valid) {
+    if (!COUNT_ONLY && prefilter) {
+      //  Phase A for a file-aligned pass that keeps a minority of the bins: bit-sliced membership test of all
+      //  32 positions, then only the members get their exact bin (5 bases of each strand) and a rank.
+      u64 cand = valid ? file_range_slots(w, p.k, p.mode, fLo, fHi) : 0;
+      if (cand) {
+        const u64 ya = win_slots(w, p.k - 5), yb = win_slots(w, p.k - 5 + 32);
+        const u32 f0 = (u32)(w.w0 >> 32), f1 = (u32)w.w0, f2 = (u32)(w.w1 >> 32);
+        const u32 r0 = (u32)(ya >> 32),   r1 = (u32)ya,   r2 = (u32)(yb >> 32);
+        while (cand) {
+          const u32 b = __clzll((long long)cand);      //  top set bit = slot q's top bit: 63 - b = 63 - 2q
+          cand &= ~(0x8000000000000000ull >> b);
+          const u32 q = b >> 1;
+          if ((valid << q) & 0x80000000u) {
+            const u32 f5 = five_bases_at(f0, f1, f2, q);
+            const u32 r5 = revcomp5(five_bases_at(r0, r1, r2, q));
+            const u32 top10 = (p.mode == MB_MODE_FORWARD) ? f5 : (p.mode == MB_MODE_REVERSE) ? r5 : min(f5, r5);
+            const u32 bin = top10 >> (10 - p.binBits);
+            keep |= 0x80000000u >> q;
+            rank[t * 32 + q] = (unsigned short)atomicAdd(&cnt[bin - p.binLo], 1u);
+          }
+        }
+      }
+    } else if (valid) {
       Roll<KW> roll;
       roll.init(w, p.k);
       for (u32 q = 0; q < 32; q++) {
@@ -405,7 +511,7 @@ cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64
   //  (what does not fit is written directly -- slower, never wrong)
   u32 stageCap = S::TILE_POS;
   if (nT < nBins) {
-    u64 want = 2ull * S::TILE_POS * nT / nBins;
+    u64 want = p.keptPerMille ? 2ull * S::TILE_POS * p.keptPerMille / 1000 : 2ull * S::TILE_POS * nT / nBins;
     if (want < 1024) want = 1024;
     want = (want + 255) / 256 * 256;
     if (want < stageCap) stageCap = (u32)want;

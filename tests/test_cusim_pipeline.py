@@ -90,6 +90,25 @@ def test_sim_low_complexity(tmp_path):
     _vs_oracle(tmp_path, {"rep.fa": b"".join(recs)}, 21, 8)
 
 
+@pytest.mark.parametrize("k,w_prefix,op", [(21, 12, "count"), (21, 10, "count-forward"), (22, 11, "count-reverse"), (31, 9, "count"),
+                                           (32, 10, "count"), (51, 10, "count"), (64, 8, "count"), (5, 6, "count"), (33, 7, "count-reverse")])
+def test_sim_multi_pass_prefilter(tmp_path, monkeypatch, k, w_prefix, op):
+    """Several file-aligned passes: the extraction kernel's bit-sliced pass-membership test (first three bases of
+    either strand) must select exactly the k-mers the rolling path selects -- N runs, lowercase, short and empty
+    records, reads on both strands included."""
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
+    reads = synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 77 + k)
+    odd = b">n\nACGTNNNNNacgtacgtacgtacgtnnACGTACGTACGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGTTTTTTTT\n>s\nACG\n>e\n\n"
+    _vs_oracle(tmp_path, {"r.fq": reads, "odd.fa": odd + synth.fasta_bytes(2, 3_000, k)}, k, w_prefix, op=op, min_passes=3)
+
+
+def test_sim_multi_pass_rolling(tmp_path, monkeypatch):
+    """The same kind of passes through the rolling path (filter switched off)."""
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
+    monkeypatch.setenv("MB_NO_PREFILTER", "1")
+    _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 5)}, 21, 12, min_passes=3)
+
+
 def test_sim_multi_pass(tmp_path):
     """A tiny arena forces several prefix-range passes (both key forms); the db must not change."""
     data = {"r.fq": synth.reads_fastq_bytes(30_000, 4_000, 150, 0.002, 77)}

@@ -194,6 +194,25 @@ def test_multi_pass_equals_single_pass(tmp_path):
     util.assert_same_db(a, b)
 
 
+@pytest.mark.parametrize("k,op", [(21, "count"), (21, "count-forward"), (22, "count-reverse"), (31, "count"), (51, "count"), (64, "count")])
+@pytest.mark.parametrize("sort_version", ["1", "2"])
+def test_multi_pass_file_aligned_prefilter(tmp_path, monkeypatch, k, op, sort_version):
+    """Capped passes (MB_MAX_PASS_KEYS) exercise the file-aligned pass plan and the extraction kernel's bit-sliced
+    pass-membership filter; run with both sweep kernels (MB_SORT is read when the first sort is planned, so each
+    combination runs in its own process)."""
+    data = synth.reads_fastq_bytes(200_000, 60_000, 150, 0.003, 100 + k)
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "gpu.meryl")
+    util.run_oracle(["k=%d" % k, "memory=2", op, str(fq), "output", ora])
+    env = dict(os.environ, MB_MAX_PASS_KEYS="1500000", MB_SORT=sort_version)
+    p = subprocess.run([mb.CLI_PATH, "k=%d" % k, "memory=2", op, str(fq), "output", out], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    import re
+    assert int(re.search(r"in (\d+) pass", p.stderr).group(1)) >= 3, p.stderr
+    util.assert_same_db(ora, out)
+
+
 def test_device_generator_and_device_ingest_match_oracle(tmp_path):
     """bench.py's input path: reads generated on the device (csrc/synth.cu) and ingested from device
     memory must give the same db as the oracle run on the same reads written as a FASTQ file."""
