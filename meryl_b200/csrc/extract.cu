@@ -371,7 +371,28 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
     const u64 rollMask = (KW == 1) ? ((p.k == 32) ? ~0ull : (((u64)1 << (2 * p.k)) - 1))
                                    : ((p.k == 64) ? ~0ull : (((u64)1 << (2 * p.k - 64)) - 1));
     u32 keep = 0;
-    if (!COUNT_ONLY && prefilter) {
+    if (COUNT_ONLY && p.k >= 5 && p.binBits <= 10 && !p.noPrefilter) {
+      //  Histogram pre-pass: the bin is the top of min(F5, R5) -- 5 bases of each strand, no 2k-bit k-mers.
+      //  z = reverse complement of the 36 bases from position k-5 on, so that R5 of position q is the plain
+      //  10-bit field at slot 31-q of z; with q a compile-time constant every field is one funnel shift.
+      if (valid) {
+        const u64 ya = win_slots(w, p.k - 5), yb = win_slots(w, p.k - 5 + 32);
+        const u64 rcA = revcomp64(ya, 32);
+        const u32 rcB = (u32)revcomp64(yb >> 56, 4);
+        const u32 z0 = (rcB << 24) | (u32)(rcA >> 40), z1 = (u32)(rcA >> 8), z2 = (u32)rcA << 24;
+        const u32 f0 = (u32)(w.w0 >> 32), f1 = (u32)w.w0, f2 = (u32)(w.w1 >> 32);
+        const u32 sh = 10 - p.binBits;
+#pragma unroll
+        for (u32 q = 0; q < 32; q++) {
+          if ((valid << q) & 0x80000000u) {
+            const u32 f5 = five_bases_at(f0, f1, f2, q);
+            const u32 r5 = five_bases_at(z0, z1, z2, 31 - q);
+            const u32 top10 = (p.mode == MB_MODE_FORWARD) ? f5 : (p.mode == MB_MODE_REVERSE) ? r5 : min(f5, r5);
+            atomicAdd(&cnt[top10 >> sh], 1u);
+          }
+        }
+      }
+    } else if (!COUNT_ONLY && prefilter) {
       //  Phase A for a file-aligned pass that keeps a minority of the bins: bit-sliced membership test of all
       //  32 positions, then only the members get their exact bin (5 bases of each strand) and a rank.
       u64 cand = valid ? file_range_slots(w, p.k, p.mode, fLo, fHi) : 0;
