@@ -25,6 +25,34 @@ template <int KW> struct CountShape;
 template <> struct CountShape<1> { static const int ITEMS = 16; };
 template <> struct CountShape<2> { static const int ITEMS = 8;  };
 
+//  Decoupled look-back by one warp: exclusive prefix of the aggregates of tiles [0, tile).  Every round trip to
+//  L2 fetches the 32 status words below the current position; the walk consumes the published ones up to and
+//  including the first inclusive prefix.  (A single thread walking one word per round trip made this kernel
+//  latency-bound: with ~1000 tiles in flight the chain of aggregates to cross is hundreds of tiles long.)
+//  Call with all 32 lanes of a warp; returns the same value in every lane.
+__device__ __forceinline__ u64 lookback_warp(const u64 *__restrict__ status, u64 tile, u32 lane) {
+  u64 excl = 0;
+  u64 top  = tile;                                           //  tiles [0, top) are still to be accounted for
+  while (top > 0) {
+    const bool have = top > (u64)lane;                       //  my word: tile top - 1 - lane
+    const u64  v    = have ? ld_volatile_u64(status + (top - 1 - lane)) : MB_ST_INC;   //  below tile 0: an inclusive prefix of 0
+    const u32  flag = (u32)(v >> 62);
+    const u32  ready = __ballot_sync(0xffffffffu, flag != 0);
+    const u32  inc   = __ballot_sync(0xffffffffu, flag == 2);
+    const u32  nReady = (ready == 0xffffffffu) ? 32u : (u32)(__ffs((int)~ready) - 1);   //  published words from lane 0 on
+    if (nReady == 0) continue;                               //  the nearest predecessor has not published yet: poll
+    u32 take = nReady;                                       //  stop behind the first inclusive prefix among them
+    const u32 incIn = inc & (nReady == 32 ? 0xffffffffu : ((1u << nReady) - 1));
+    if (incIn) take = (u32)__ffs((int)incIn);
+    u64 c = (lane < take) ? (v & MB_ST_MASK) : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    excl += c;
+    if (incIn) break;
+    top -= take;
+  }
+  return excl;
+}
+
 template <int KW>
 __global__ void __launch_bounds__(CNT_THREADS)
 count_kernel(typename KeyT<KW>::type *keys, u64 nKeys, u64 *__restrict__ runStart, u64 *__restrict__ numDistinct,
@@ -96,27 +124,17 @@ count_kernel(typename KeyT<KW>::type *keys, u64 nKeys, u64 *__restrict__ runStar
 #pragma unroll
   for (int w = 0; w < CNT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) wOff += c; tileTot += c; }
 
-  //  look back (one thread)
-  if (t == 0) {
-    u64 excl = 0;
-    if (tile == 0) {
-      st_volatile_u64(status + tile, MB_ST_INC | tileTot);
-    } else {
-      st_volatile_u64(status + tile, MB_ST_AGG | tileTot);
-      u64 j = tile - 1;
-      for (;;) {
-        const u64 v = ld_volatile_u64(status + j);
-        if ((v >> 62) == 0) continue;
-        excl += v & MB_ST_MASK;
-        if ((v >> 62) == 2) break;
-        j--;
+  //  look back (warp 0)
+  if (warp == 0) {
+    if (lane == 0) st_volatile_u64(status + tile, (tile == 0 ? MB_ST_INC : MB_ST_AGG) | tileTot);
+    const u64 excl = lookback_warp(status, tile, lane);
+    if (lane == 0) {
+      if (tile != 0) st_volatile_u64(status + tile, MB_ST_INC | (excl + tileTot));
+      sExcl = excl;
+      if (begin + n == nKeys) {                              //  last tile: totals and the sentinel
+        *numDistinct = excl + tileTot;
+        runStart[excl + tileTot] = nKeys;
       }
-      st_volatile_u64(status + tile, MB_ST_INC | (excl + tileTot));
-    }
-    sExcl = excl;
-    if (begin + n == nKeys) {                                //  last tile: totals and the sentinel
-      *numDistinct = excl + tileTot;
-      runStart[excl + tileTot] = nKeys;
     }
   }
   __syncthreads();
@@ -195,26 +213,16 @@ count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restr
 #pragma unroll
   for (int w = 0; w < CNT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) wOff += c; tileTot += c; }
 
-  if (t == 0) {
-    u64 excl = 0;
-    if (rel == 0) {
-      st_volatile_u64(status + rel, MB_ST_INC | tileTot);
-    } else {
-      st_volatile_u64(status + rel, MB_ST_AGG | tileTot);
-      u64 j = rel - 1;
-      for (;;) {
-        const u64 v = ld_volatile_u64(status + j);
-        if ((v >> 62) == 0) continue;
-        excl += v & MB_ST_MASK;
-        if ((v >> 62) == 2) break;
-        j--;
+  if (warp == 0) {
+    if (lane == 0) st_volatile_u64(status + rel, (rel == 0 ? MB_ST_INC : MB_ST_AGG) | tileTot);
+    const u64 excl = lookback_warp(status, rel, lane);
+    if (lane == 0) {
+      if (rel != 0) st_volatile_u64(status + rel, MB_ST_INC | (excl + tileTot));
+      sExcl = excl;
+      if (rel + 1 == nHalves) {                              //  last half-tile of the group: total and sentinel
+        *numDistinct = excl + tileTot;
+        runStart[excl + tileTot] = endIndex;
       }
-      st_volatile_u64(status + rel, MB_ST_INC | (excl + tileTot));
-    }
-    sExcl = excl;
-    if (rel + 1 == nHalves) {                                //  last half-tile of the group: total and sentinel
-      *numDistinct = excl + tileTot;
-      runStart[excl + tileTot] = endIndex;
     }
   }
   __syncthreads();
@@ -280,8 +288,20 @@ value_hist_kernel(const u64 *__restrict__ runStart, const u64 *__restrict__ numD
     if (sh[i]) atomicAdd((unsigned long long *)&histSmall[i], (unsigned long long)sh[i]);
 }
 
+//  test hook: one warp walks a prepared status array
+__global__ void __launch_bounds__(32)
+lookback_test_kernel(const u64 *__restrict__ status, u64 tile, u64 *__restrict__ out) {
+  const u64 e = lookback_warp(status, tile, threadIdx.x);
+  if (threadIdx.x == 0) *out = e;
+}
+
 }  //  namespace
 
+
+cudaError_t mb_launch_lookback_test(const u64 *dStatus, u64 tile, u64 *dOut, cudaStream_t s) {
+  lookback_test_kernel<<<1, 32, 0, s>>>(dStatus, tile, dOut);
+  return cudaGetLastError();
+}
 
 static u64 count_tiles(u32 keyWords, u64 nKeys) {
   const u64 tile = CNT_THREADS * (keyWords == 1 ? CountShape<1>::ITEMS : CountShape<2>::ITEMS);

@@ -230,3 +230,19 @@ extern "C" int mb_dbg_sort_version(int v) {
   if (v == 1 || v == 2) mb_sort_set_version(v);
   return old;
 }
+
+//  The count kernels' warp-wide decoupled look-back on a caller-made status array (words: flag << 62 | value; flag 1 =
+//  aggregate, 2 = inclusive prefix; every word below `tile` must be published).  *out = exclusive prefix of `tile`.
+extern "C" int mb_dbg_lookback(const uint64_t *status, uint64_t n, uint64_t tile, uint64_t *out) {
+  mb_clear_error();
+  if (!status || !out || tile > n) return mb_fail(MB_EINVAL, "mb_dbg_lookback: bad argument");
+  u64 *dSt = nullptr, *dOut = nullptr;
+  MB_CUDA(cudaMalloc((void **)&dSt, (n + 1) * 8));
+  MB_CUDA(cudaMalloc((void **)&dOut, 8));
+  MB_CUDA(cudaMemcpy(dSt, status, n * 8, cudaMemcpyHostToDevice));
+  MB_CUDA(mb_launch_lookback_test(dSt, tile, dOut, 0));
+  MB_CUDA(cudaDeviceSynchronize());
+  MB_CUDA(cudaMemcpy(out, dOut, 8, cudaMemcpyDeviceToHost));
+  cudaFree(dSt);  cudaFree(dOut);
+  return MB_OK;
+}

@@ -175,6 +175,7 @@ cudaError_t mb_launch_count(u32 keyWords, void *dKeys, u64 nKeys, u64 *dRunStart
 cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u64 tileLo, u64 tileHi, u64 endIndex,
                                      u32 binLo, u32 suffixBits, u64 *dUniq, u64 *dRunStart, u64 *dNumDistinct,
                                      void *dWorkspace, cudaStream_t s);
+cudaError_t mb_launch_lookback_test(const u64 *dStatus, u64 tile, u64 *dOut, cudaStream_t s);     //  test hook (debug.cu)
 cudaError_t mb_launch_value_histogram(const u64 *dRunStart, const u64 *dNumDistinct, u64 nMaxDistinct,
                                       u64 *dHistSmall, u32 *dHistBig, u64 *dHistBigN, u64 histBigCap,
                                       u64 *dTotals /* [3]: unique, distinct, total */, cudaStream_t s);

@@ -91,3 +91,37 @@ def test_sim_sort_u128(n, bits, sort_version):
     rc = L.mb_dbg_sort(glo.ctypes.data, ghi.ctypes.data, n, bits)
     assert rc == 0, L.mb_last_error().decode()
     assert np.array_equal(glo, lo[order]) and np.array_equal(ghi, hi[order])
+
+
+def _lookback_cases():
+    rng = np.random.default_rng(3)
+    cases = []
+    for n, inc_every in [(1, 1), (5, 2), (31, 40), (32, 40), (33, 40), (64, 70), (65, 33), (200, 64), (1000, 1001), (1000, 7), (97, 1)]:
+        vals = rng.integers(0, 1 << 20, size=n, dtype=np.uint64)
+        flags = np.ones(n, dtype=np.uint64)                       # aggregates ...
+        flags[::inc_every] = 2                                   # ... with an inclusive prefix now and then (tile 0 always)
+        cases.append((vals, flags))
+    return cases
+
+
+def check_lookback(L):
+    """Expected: walking down from tile-1, add aggregates until (and including) the first inclusive prefix."""
+    L.mb_dbg_lookback.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    for vals, flags in _lookback_cases():
+        status = (flags << np.uint64(62)) | vals
+        n = len(vals)
+        for tile in sorted({0, 1, n // 2, n - 1, n}):
+            want, j = 0, tile - 1
+            while j >= 0:
+                want += int(vals[j])
+                if flags[j] == 2:
+                    break
+                j -= 1
+            got = ctypes.c_uint64(0)
+            rc = L.mb_dbg_lookback(status.ctypes.data, n, tile, ctypes.byref(got))
+            assert rc == 0, L.mb_last_error().decode()
+            assert got.value == want, (n, tile, got.value, want)
+
+
+def test_sim_lookback_warp():
+    check_lookback(mb.lib())

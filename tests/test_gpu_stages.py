@@ -216,3 +216,9 @@ def test_encode_clustered_suffixes_long_unary_runs():
         want = util.oracle_encode_block(w_suffix, 1, hi, lo, vals)
         got = _encode_gpu(k, wp, 1, lo, hi, vals)
         assert got == want
+
+
+def test_count_lookback_warp():
+    """The count kernels' warp-wide look-back on prepared status arrays (chains longer than one 32-word window)."""
+    from test_cusim_stages import check_lookback
+    check_lookback(mb.lib())
