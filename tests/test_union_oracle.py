@@ -1,0 +1,70 @@
+"""`meryl union-sum`: the C oracle's restatement of the reader / merge / stream writer
+(oracle/meryl_oracle.c, sections R1-R3, M1, S1) pinned to the UNMODIFIED reference binary -- against the
+committed golden dbs it wrote (tests/golden/make_golden_union.py), and, where oracle/_ref/meryl is present,
+against the binary itself on more shapes."""
+import os
+
+import pytest
+
+import util
+from meryl_b200 import synth
+
+
+@pytest.mark.parametrize("name", util.union_golden_cases())
+def test_oracle_union_sum_matches_golden(tmp_path, name):
+    dbs, gold = util.load_union_golden(name, str(tmp_path))
+    out = str(tmp_path / "ora.meryl")
+    util.run_oracle(["union-sum", *dbs, "output", out])
+    util.assert_same_db(gold, out)
+
+
+def _count_ref(tmp_path, name, data, k, words=("memory=2",), op="count"):
+    p = tmp_path / (name + ".fa")
+    p.write_bytes(data)
+    db = str(tmp_path / (name + ".meryl"))
+    util.run_ref(["k=%d" % k, *words, "threads=2", op, str(p), "output", db])
+    return db
+
+
+needs_ref = pytest.mark.skipif(not util.have_ref(), reason="reference binary oracle/_ref/meryl not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("k", [8, 21, 31, 32, 33, 64])
+def test_oracle_union_sum_vs_reference(tmp_path, k):
+    a = _count_ref(tmp_path, "a", synth.fasta_bytes(2, 40_000, 10 + k), k)
+    b = _count_ref(tmp_path, "b", synth.fasta_bytes(1, 40_000, 10 + k) + synth.fasta_bytes(2, 30_000, 99 + k), k)
+    ref, ora = str(tmp_path / "ref.meryl"), str(tmp_path / "ora.meryl")
+    util.run_ref(["threads=3", "union-sum", a, b, "output", ref])
+    util.run_oracle(["union-sum", a, b, "output", ora])
+    util.assert_same_db(ref, ora)
+
+
+@needs_ref
+def test_oracle_union_of_unions_and_empty(tmp_path):
+    """Stream-written inputs (prefix 12, absent blocks), an input without k-mers, a single input."""
+    k = 21
+    a = _count_ref(tmp_path, "a", synth.reads_fastq_bytes(30_000, 2_000, 150, 0.01, 1), k)
+    b = _count_ref(tmp_path, "b", synth.reads_fastq_bytes(30_000, 2_000, 150, 0.01, 2), k, op="count-forward")
+    e = _count_ref(tmp_path, "e", b">x\nACGT\n", k)
+    u1, u2 = str(tmp_path / "u1.meryl"), str(tmp_path / "u2.meryl")
+    util.run_ref(["union-sum", a, b, "output", u1])
+    util.run_ref(["union-sum", e, b, "output", u2])
+    for i, ins in enumerate([[u1, u2], [u1, a, e], [e, e], [u1]]):
+        ref, ora = str(tmp_path / ("ref%d.meryl" % i)), str(tmp_path / ("ora%d.meryl" % i))
+        util.run_ref(["union-sum", *ins, "output", ref])
+        util.run_oracle(["union-sum", *ins, "output", ora])
+        util.assert_same_db(ref, ora)
+
+
+@needs_ref
+def test_oracle_union_sum_low_complexity_big_blocks(tmp_path):
+    """Few distinct k-mers with large counts; sums of counts; k-mers sharing long prefixes (small unary deltas)."""
+    k = 21
+    rep = b">r\n" + b"ACGTTGCA" * 5_000 + b"\n>p\n" + b"A" * 60_000 + b"\n"
+    a = _count_ref(tmp_path, "a", rep + synth.fasta_bytes(1, 50_000, 3), k)
+    b = _count_ref(tmp_path, "b", rep + rep, k)
+    ref, ora = str(tmp_path / "ref.meryl"), str(tmp_path / "ora.meryl")
+    util.run_ref(["union-sum", a, b, "output", ref])
+    util.run_oracle(["union-sum", a, b, "output", ora])
+    util.assert_same_db(ref, ora)

@@ -184,3 +184,31 @@ def load_golden(name: str, tmp: str):
             tf.extractall(db, filter="data")
     assert db_digest(db) == ent["digest"]
     return inp, db, ent["words"], ent
+
+
+def union_golden_cases() -> list[str]:
+    import json
+    with open(os.path.join(GOLDEN_DIR, "manifest_union.json")) as fh:
+        return sorted(json.load(fh))
+
+
+def load_union_golden(name: str, tmp: str):
+    """Unpacks a union-sum golden case: returns (list of input db dirs, reference output db dir)."""
+    import gzip
+    import io
+    import json
+    import tarfile
+    with open(os.path.join(GOLDEN_DIR, "manifest_union.json")) as fh:
+        ent = json.load(fh)[name]
+    dbs = []
+    for i, case in enumerate(ent["inputs"]):
+        sub = os.path.join(tmp, "in%d" % i)
+        os.makedirs(sub)
+        dbs.append(load_golden(case, sub)[1])
+    out = os.path.join(tmp, "golden_union.meryl")
+    os.makedirs(out)
+    with gzip.open(os.path.join(GOLDEN_DIR, name + ".db.tar.gz"), "rb") as g:
+        with tarfile.open(fileobj=io.BytesIO(g.read())) as tf:
+            tf.extractall(out, filter="data")
+    assert db_digest(out) == ent["digest"]
+    return dbs, out
