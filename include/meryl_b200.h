@@ -158,6 +158,36 @@ int mb_merge_histogram(mb_ctx *ctx, const uint64_t *values, const uint64_t *occu
 /*  One-shot: `meryl k=K [n=N] [memory=GB] count* <paths> output <outDir>` on one GPU.  */
 int mb_count_files(const mb_config *cfg, const char **paths, uint32_t nPaths, const char *outDir, mb_stats *st);
 
+/* ---- `meryl union-sum A B ... output C` (csrc/union.cu) ------------------------
+ *
+ *  Replaces, for this operator, merylOperation::nextMer + findSumCount (src/meryl/merylOp-nextMer.C:419-683, :44-48)
+ *  between merylFileReader (src/utility/src/kmers-v1/kmers-reader.C:456-531, kmers-files.C:25-128) and
+ *  merylStreamWriter (src/utility/src/kmers-v1/kmers-writer-stream.C:89-157): every k-mer of any input is written
+ *  once with the sum of its values (kmvalu = uint32, wraps; a zero sum is dropped).  The output is what the
+ *  reference writes: prefix width 12, no blocks for absent prefixes, 64 data + 64 index files + merylIndex.
+ *  Inputs must be meryl v.03 databases of the same k (>= 7), not multisets.  Decode, merge and encode run on the
+ *  device, one group of consecutive data files at a time.                                                      */
+typedef struct mb_union_stats {
+  uint64_t nInputKmers;     /*  (k-mer, value) pairs read from all inputs                 */
+  uint64_t nOutputKmers;    /*  distinct k-mers written                                   */
+  uint64_t nUnique, nDistinct, nTotal;   /*  master-index statistics of the output       */
+  uint64_t inBytes;         /*  .merylData bytes read                                     */
+  uint64_t outBytes;        /*  bytes of the 129 files written                            */
+  uint64_t h2dBytes, d2hBytes;
+  uint32_t nInputs;
+  uint32_t nGroups;         /*  groups of data files processed one after the other        */
+  uint32_t nLaunches;       /*  CUDA kernels launched                                     */
+  uint32_t k;
+  float    msDecode;        /*  device time incl. the host reads feeding it (CUDA events) */
+  float    msMerge;
+  float    msEncode;        /*  value histogram + encode + copy back                      */
+  float    msTotal;
+} mb_union_stats;
+
+/*  device: CUDA ordinal or -1 (current); workspaceBytes: device arena, 0 = all free memory minus a margin.  */
+int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                 uint64_t workspaceBytes, mb_union_stats *st);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the
@@ -177,6 +207,10 @@ int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix, uint64_t 
                         uint8_t *out, uint64_t cap, uint64_t *outLen);
 /*  P1/P2 alone (host parser): file image -> base stream in work-buffer format.  */
 int mb_dbg_parse(const uint8_t *data, uint64_t len, char *out, uint64_t cap, uint64_t *outLen);
+/*  Select the sort sweep kernel (1: 6-bit digits, 2: 8-bit digits) for contexts created afterwards; returns the previous one.  */
+int mb_dbg_sort_version(int version);
+/*  The count / merge kernels' warp-wide decoupled look-back on a prepared status array: *out = exclusive prefix of `tile`.  */
+int mb_dbg_lookback(const uint64_t *status, uint64_t n, uint64_t tile, uint64_t *out);
 
 /* ---- synthetic input for the benchmark and the tests (csrc/synth.cu) --------------------------- */
 

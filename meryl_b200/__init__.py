@@ -54,6 +54,18 @@ class Stats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class UnionStats(ctypes.Structure):
+    _fields_ = [("nInputKmers", ctypes.c_uint64), ("nOutputKmers", ctypes.c_uint64),
+                ("nUnique", ctypes.c_uint64), ("nDistinct", ctypes.c_uint64), ("nTotal", ctypes.c_uint64),
+                ("inBytes", ctypes.c_uint64), ("outBytes", ctypes.c_uint64),
+                ("h2dBytes", ctypes.c_uint64), ("d2hBytes", ctypes.c_uint64),
+                ("nInputs", ctypes.c_uint32), ("nGroups", ctypes.c_uint32), ("nLaunches", ctypes.c_uint32), ("k", ctypes.c_uint32),
+                ("msDecode", ctypes.c_float), ("msMerge", ctypes.c_float), ("msEncode", ctypes.c_float), ("msTotal", ctypes.c_float)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -274,3 +286,15 @@ def count(inputs, output: str, k: int, operation: str = "count", memory_gb: floa
         c.count()
         c.write_db(os.fspath(output))
         return c.stats()
+
+
+def union_sum(inputs, output: str, device: int = -1, workspace_bytes: int = 0) -> UnionStats:
+    """`meryl union-sum <inputs> output <output>` on one GPU (include/meryl_b200.h: mb_union_sum)."""
+    inputs = [os.fsencode(os.fspath(p)) for p in inputs]
+    L = lib()
+    L.mb_union_sum.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int32,
+                               ctypes.c_uint64, ctypes.POINTER(UnionStats)]
+    arr = (ctypes.c_char_p * len(inputs))(*inputs)
+    st = UnionStats()
+    _check(L.mb_union_sum(arr, len(inputs), os.fsencode(os.fspath(output)), device, workspace_bytes, ctypes.byref(st)))
+    return st

@@ -8,8 +8,9 @@
 //                 count|count-forward|count-reverse <seq files...> output <db.meryl>
 //
 //  Words are order-free like the reference's.  Errors are a message on stderr and exit(1)
-//  (missing k: merylOp-count.C:311-312; missing output: :314-315).  Any other operation (union-sum,
-//  print, statistics, ...) is not part of this tool: if $MERYL_REFERENCE names the reference
+//  (missing k: merylOp-count.C:311-312; missing output: :314-315).  `union-sum <dbs> output <db>` is the one
+//  set operation implemented (csrc/union.cu).  Any other operation (print, statistics, intersect, ...)
+//  is not part of this tool: if $MERYL_REFERENCE names the reference
 //  binary the whole command line is handed to it unchanged, otherwise it is an error.
 
 #include <stdio.h>
@@ -37,7 +38,48 @@ static bool isCountWord(const char *w, uint32_t *mode) {
   return false;
 }
 
+//  meryl-b200 [threads=T] [memory=GB] union-sum <db.meryl> <db.meryl> ... output <db.meryl>
+//  (merylCommandBuilder.C:333-435: the operation word; database inputs are directories holding a merylIndex)
+static int unionSumMain(int argc, char **argv) {
+  std::vector<const char *> dbs;
+  const char *outDir = nullptr;
+  bool quiet = false;
+  for (int i = 1; i < argc; i++) {
+    const char *w = argv[i];
+    if (!strcmp(w, "union-sum") || !strncmp(w, "threads=", 8) || !strncmp(w, "memory=", 7) || !strncmp(w, "-V", 2) || !strcmp(w, "-P") ||
+        !strcmp(w, "[") || !strcmp(w, "]")) continue;
+    if (!strcmp(w, "-Q")) { quiet = true; continue; }
+    if (!strcmp(w, "output")) {
+      if (i + 1 >= argc) { fprintf(stderr, "ERROR: 'output' needs a database name.\n"); return 1; }
+      outDir = argv[++i];
+      continue;
+    }
+    const std::string idx = std::string(w) + "/merylIndex";
+    if (access(idx.c_str(), R_OK) != 0) { fprintf(stderr, "ERROR: '%s' is not a meryl database (no readable merylIndex).\n", w); return 1; }
+    dbs.push_back(w);
+  }
+  if (dbs.empty()) { fprintf(stderr, "ERROR: union-sum needs at least one input database.\n"); return 1; }
+  if (!outDir)     { fprintf(stderr, "ERROR: No output specified for union-sum operation.\n"); return 1; }
+  mb_union_stats st;
+  if (mb_union_sum(dbs.data(), (uint32_t)dbs.size(), outDir, -1, 0, &st) != MB_OK) {
+    fprintf(stderr, "ERROR: %s\n", mb_last_error());
+    return 1;
+  }
+  if (!quiet) {
+    fprintf(stderr, "union-sum of %u databases (k=%u): %llu k-mers in, %llu distinct out (%llu unique), %u group%s, %.1f ms\n",
+            st.nInputs, st.k, (unsigned long long)st.nInputKmers, (unsigned long long)st.nOutputKmers, (unsigned long long)st.nUnique,
+            st.nGroups, st.nGroups == 1 ? "" : "s", st.msTotal);
+    fprintf(stderr, "  read+decode %.2f  merge %.2f  encode+write %.2f ms;  %llu bytes in, %llu bytes out\n",
+            st.msDecode, st.msMerge, st.msEncode, (unsigned long long)st.inBytes, (unsigned long long)st.outBytes);
+    fprintf(stderr, "\nBye.\n");
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  for (int i = 1; i < argc; i++)
+    if (!strcmp(argv[i], "union-sum")) return unionSumMain(argc, argv);
+
   uint32_t k = 0, mode = 0;
   uint64_t nExpected = 0, memBytes = physicalMemory();
   bool haveOp = false, onlyConfig = false, quiet = false;

@@ -25,34 +25,6 @@ template <int KW> struct CountShape;
 template <> struct CountShape<1> { static const int ITEMS = 16; };
 template <> struct CountShape<2> { static const int ITEMS = 8;  };
 
-//  Decoupled look-back by one warp: exclusive prefix of the aggregates of tiles [0, tile).  Every round trip to
-//  L2 fetches the 32 status words below the current position; the walk consumes the published ones up to and
-//  including the first inclusive prefix.  (A single thread walking one word per round trip made this kernel
-//  latency-bound: with ~1000 tiles in flight the chain of aggregates to cross is hundreds of tiles long.)
-//  Call with all 32 lanes of a warp; returns the same value in every lane.
-__device__ __forceinline__ u64 lookback_warp(const u64 *__restrict__ status, u64 tile, u32 lane) {
-  u64 excl = 0;
-  u64 top  = tile;                                           //  tiles [0, top) are still to be accounted for
-  while (top > 0) {
-    const bool have = top > (u64)lane;                       //  my word: tile top - 1 - lane
-    const u64  v    = have ? ld_volatile_u64(status + (top - 1 - lane)) : MB_ST_INC;   //  below tile 0: an inclusive prefix of 0
-    const u32  flag = (u32)(v >> 62);
-    const u32  ready = __ballot_sync(0xffffffffu, flag != 0);
-    const u32  inc   = __ballot_sync(0xffffffffu, flag == 2);
-    const u32  nReady = (ready == 0xffffffffu) ? 32u : (u32)(__ffs((int)~ready) - 1);   //  published words from lane 0 on
-    if (nReady == 0) continue;                               //  the nearest predecessor has not published yet: poll
-    u32 take = nReady;                                       //  stop behind the first inclusive prefix among them
-    const u32 incIn = inc & (nReady == 32 ? 0xffffffffu : ((1u << nReady) - 1));
-    if (incIn) take = (u32)__ffs((int)incIn);
-    u64 c = (lane < take) ? (v & MB_ST_MASK) : 0;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    excl += c;
-    if (incIn) break;
-    top -= take;
-  }
-  return excl;
-}
-
 template <int KW>
 __global__ void __launch_bounds__(CNT_THREADS)
 count_kernel(typename KeyT<KW>::type *keys, u64 nKeys, u64 *__restrict__ runStart, u64 *__restrict__ numDistinct,
@@ -245,7 +217,7 @@ const int VH_THREADS = 256;
 const int VH_SMEM    = 1024;
 
 __global__ void __launch_bounds__(VH_THREADS)
-value_hist_kernel(const u64 *__restrict__ runStart, const u64 *__restrict__ numDistinct,
+value_hist_kernel(const u64 *__restrict__ runStart, const u32 *__restrict__ counts, const u64 *__restrict__ numDistinct,
                   u64 *__restrict__ histSmall, u32 *__restrict__ histBig, u64 *__restrict__ histBigN, u64 histBigCap,
                   u64 *__restrict__ totals) {
   __shared__ u32 sh[VH_SMEM];
@@ -258,7 +230,7 @@ value_hist_kernel(const u64 *__restrict__ runStart, const u64 *__restrict__ numD
   const u64 D = *numDistinct;
   u64 uniq = 0, dist = 0, tot = 0;
   for (u64 j = (u64)blockIdx.x * VH_THREADS + t; j < D; j += (u64)gridDim.x * VH_THREADS) {
-    const u32 c = (u32)(runStart[j + 1] - runStart[j]);      //  kmvalu is 32 bits and wraps (merylCountArray.C:357)
+    const u32 c = counts ? counts[j] : (u32)(runStart[j + 1] - runStart[j]);      //  kmvalu is 32 bits and wraps (merylCountArray.C:357)
     if (c == 0) continue;                                    //  addValue ignores zero
     uniq += (c == 1);
     dist += 1;
@@ -354,6 +326,20 @@ cudaError_t mb_launch_value_histogram(const u64 *dRunStart, const u64 *dNumDisti
   u64 grid = (nMaxDistinct + VH_THREADS - 1) / VH_THREADS;
   const u64 cap = (u64)sms * 8;
   if (grid > cap) grid = cap;
-  value_hist_kernel<<<(unsigned)grid, VH_THREADS, 0, s>>>(dRunStart, dNumDistinct, dHistSmall, dHistBig, dHistBigN, histBigCap, dTotals);
+  value_hist_kernel<<<(unsigned)grid, VH_THREADS, 0, s>>>(dRunStart, nullptr, dNumDistinct, dHistSmall, dHistBig, dHistBigN, histBigCap, dTotals);
+  return cudaGetLastError();
+}
+
+cudaError_t mb_launch_value_histogram_counts(const u32 *dCounts, const u64 *dNumDistinct, u64 nMaxDistinct,
+                                             u64 *dHistSmall, u32 *dHistBig, u64 *dHistBigN, u64 histBigCap,
+                                             u64 *dTotals, cudaStream_t s) {
+  if (nMaxDistinct == 0) return cudaSuccess;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 grid = (nMaxDistinct + VH_THREADS - 1) / VH_THREADS;
+  const u64 cap = (u64)sms * 8;
+  if (grid > cap) grid = cap;
+  value_hist_kernel<<<(unsigned)grid, VH_THREADS, 0, s>>>(nullptr, dCounts, dNumDistinct, dHistSmall, dHistBig, dHistBigN, histBigCap, dTotals);
   return cudaGetLastError();
 }

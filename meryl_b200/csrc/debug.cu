@@ -198,7 +198,7 @@ extern "C" int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix
   MB_CUDA(cudaMemset(dTot, 0, 4 * 8));
 
   MbEncodeParams ep;
-  ep.keys = dKeys;  ep.runStart = dRs;  ep.nDistinct = n;  ep.keyWords = kw;  ep.k = k;  ep.wPrefix = wPrefix;
+  ep.keys = dKeys;  ep.runStart = dRs;  ep.nDistinct = n;  ep.keyWords = kw;  ep.k = k;  ep.wPrefix = wPrefix;  ep.counts = nullptr;  ep.streamMode = 0;
   ep.blockLo = prefix;  ep.nBlocks = 1;
   MB_CUDA(mb_launch_encode_layout(ep, dMeta, dTot, dTmp, 0));
   u64 tot[4];

@@ -136,14 +136,17 @@ layout_kernel(MbEncodeParams p, MbBlockMeta *__restrict__ meta, u64 *__restrict_
 
   const BlockShape s = block_shape(n, wSuffix);
   u64 words = 0;
-  const u32 nSub = walk_subblocks(keys, first, n, s, [&](u32, u64, u64 len) { words += (len + 63) >> 6; });
+  u32 nSub  = 0;
+  const bool skip = p.streamMode && n == 0;                 //  the stream writer never writes a block without k-mers
+  if (!skip) nSub = walk_subblocks(keys, first, n, s, [&](u32, u64, u64 len) { words += (len + 63) >> 6; });
+  if (p.streamMode && n > ((u64)16 << 20)) totals[4] = 1;   //  would be split by merylStreamWriter::addMer
 
   MbBlockMeta m;
   m.first    = first;
   m.outByte  = 0;
   m.nSub     = nSub;
   m.subFirst = 0;
-  m.bytes    = 16 + 16 * (u64)nSub + 8 * words;
+  m.bytes    = skip ? 0 : 16 + 16 * (u64)nSub + 8 * words;
   meta[blk]  = m;
 
   if (blk == 0)             totals[2] = first;             //  the chunk's distinct k-mers are [totals[2], totals[3])
@@ -261,6 +264,13 @@ header_kernel(MbEncodeParams p, MbEncodeChunk c, const MbBlockMeta *__restrict__
   const u64  n       = end - m.first;
   const BlockShape s = block_shape(n, wSuffix);
 
+  if (p.streamMode && n == 0) {                              //  no block; merylFileIndex::clear() (kmers-files.H:141-145)
+    index[3 * rel + 0] = 0;
+    index[3 * rel + 1] = ~0ull;
+    index[3 * rel + 2] = 0;
+    return;
+  }
+
   u64 *o    = (u64 *)(out + (m.outByte - c.chunkByte0));
   u64 *bgn  = o + 2;
   u64 *len  = bgn + m.nSub;
@@ -357,7 +367,7 @@ fields_kernel(MbEncodeParams p, MbEncodeChunk c, const MbBlockMeta *__restrict__
     const u32 mid = (lo + hi) >> 1;
     if (bgn[mid] <= V) lo = mid; else hi = mid;
   }
-  const u32 cnt = (u32)(p.runStart[g + 1] - p.runStart[g]);
+  const u32 cnt = p.counts ? p.counts[g] : (u32)(p.runStart[g + 1] - p.runStart[g]);
   or_bits(data, 64 * (u64)sw[lo] + (V - bgn[lo]), 32, cnt);
 }
 

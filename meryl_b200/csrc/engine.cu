@@ -800,7 +800,7 @@ static int runCount(mb_ctx *c) {
       for (size_t ri = 0; ri < G.encRanges.size(); ri++) {
         MbEncodeParams ep;
         ep.keys = distinctKeys;  ep.runStart = runStart;  ep.nDistinct = D;  ep.keyWords = encKeyWords;
-        ep.k = k;  ep.wPrefix = wP;
+        ep.k = k;  ep.wPrefix = wP;  ep.counts = nullptr;  ep.streamMode = 0;
         ep.blockLo = G.encRanges[ri].first;
         ep.nBlocks = G.encRanges[ri].second;
 

@@ -112,6 +112,34 @@ __device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) {
 }
 #endif
 
+//  Decoupled look-back by one warp: exclusive prefix of the aggregates of tiles [0, tile).  Every round trip to
+//  L2 fetches the 32 status words below the current position; the walk consumes the published ones up to and
+//  including the first inclusive prefix.  (A single thread walking one word per round trip is latency-bound:
+//  with ~1000 tiles in flight the chain of aggregates to cross is hundreds of tiles long.)
+//  Call with all 32 lanes of a warp; returns the same value in every lane.
+__device__ __forceinline__ u64 lookback_warp(const u64 *__restrict__ status, u64 tile, u32 lane) {
+  u64 excl = 0;
+  u64 top  = tile;                                           //  tiles [0, top) are still to be accounted for
+  while (top > 0) {
+    const bool have = top > (u64)lane;                       //  my word: tile top - 1 - lane
+    const u64  v    = have ? ld_volatile_u64(status + (top - 1 - lane)) : MB_ST_INC;   //  below tile 0: an inclusive prefix of 0
+    const u32  flag = (u32)(v >> 62);
+    const u32  ready = __ballot_sync(0xffffffffu, flag != 0);
+    const u32  inc   = __ballot_sync(0xffffffffu, flag == 2);
+    const u32  nReady = (ready == 0xffffffffu) ? 32u : (u32)(__ffs((int)~ready) - 1);   //  published words from lane 0 on
+    if (nReady == 0) continue;                               //  the nearest predecessor has not published yet: poll
+    u32 take = nReady;                                       //  stop behind the first inclusive prefix among them
+    const u32 incIn = inc & (nReady == 32 ? 0xffffffffu : ((1u << nReady) - 1));
+    if (incIn) take = (u32)__ffs((int)incIn);
+    u64 c = (lane < take) ? (v & MB_ST_MASK) : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    excl += c;
+    if (incIn) break;
+    top -= take;
+  }
+  return excl;
+}
+
 //  ---- launch entry points (each returns cudaGetLastError()) ----------------------------
 
 //  K1  pack.cu: ASCII work-buffer bytes -> store records.  nBytes is padded by the kernel with
@@ -179,6 +207,10 @@ cudaError_t mb_launch_lookback_test(const u64 *dStatus, u64 tile, u64 *dOut, cud
 cudaError_t mb_launch_value_histogram(const u64 *dRunStart, const u64 *dNumDistinct, u64 nMaxDistinct,
                                       u64 *dHistSmall, u32 *dHistBig, u64 *dHistBigN, u64 histBigCap,
                                       u64 *dTotals /* [3]: unique, distinct, total */, cudaStream_t s);
+//  Same with explicit values (set operations): value j = dCounts[j], j < *dNumDistinct.
+cudaError_t mb_launch_value_histogram_counts(const u32 *dCounts, const u64 *dNumDistinct, u64 nMaxDistinct,
+                                             u64 *dHistSmall, u32 *dHistBig, u64 *dHistBigN, u64 histBigCap,
+                                             u64 *dTotals, cudaStream_t s);
 
 //  K6  encode.cu
 struct MbBlockMeta {           //  one per block of the pass, written by the layout kernel
@@ -196,6 +228,10 @@ struct MbEncodeParams {
   u32         k, wPrefix;
   u64         blockLo;         //  first block prefix of the pass
   u64         nBlocks;         //  number of consecutive block prefixes in the pass
+  const u32  *counts;          //  NULL: value j = runStart[j+1] - runStart[j];  else value j = counts[j] (set operations)
+  u32         streamMode;      //  1: merylStreamWriter rules (kmers-writer-stream.C:89-157): a prefix without k-mers writes
+                               //     no block and leaves its index entry {0, UINT64_MAX, 0}; dTotals[4] is set if a block
+                               //     holds more than 16 Mi k-mers (the stream writer would split it; not implemented)
 };
 //  E0+E1 for the whole pass: per-block extent and layout size into dMeta[nBlocks]; an exclusive scan
 //  then fills outByte/subFirst (relative to the pass).  dTotals[0] = total bytes, dTotals[1] = total

@@ -1,0 +1,653 @@
+//  `meryl union-sum A B ... output C` on the device (BASELINE.json configs[4]).
+//
+//  Replaces, for this one operator, the reference's streaming set-operation path:
+//    merylFileReader / merylFileBlockReader   src/utility/src/kmers-v1/kmers-reader.C:456-531,
+//                                             src/utility/src/kmers-v1/kmers-files.C:25-128     (read + decode blocks)
+//    merylOperation::nextMer, findSumCount    src/meryl/merylOp-nextMer.C:419-683, :44-48       (k-way merge, uint32 sum)
+//    merylStreamWriter                        src/utility/src/kmers-v1/kmers-writer-stream.C:89-157 (block per prefix, prefix 12)
+//
+//  The reference walks 64 files with 64 threads, one k-mer at a time.  Here the unit of work is a GROUP of
+//  consecutive data files that fits the device:
+//    host     reads the group's .merylData bytes of every input and walks the block containers (sizes only)
+//    K7       decode_kernel      one thread per block: Elias-Fano fields -> full k-mers + values, at the block's
+//                                exclusive k-mer offset (a block is a strictly sequential bit stream: every unary
+//                                code must be decoded to find the next field; blocks are the parallelism)
+//    K8       merge_sum_kernel   merge-path union of two sorted k-mer lists with the counts of equal k-mers added
+//                                (uint32, wraps; zero sums are dropped), compacted by a chained scan; more than two
+//                                inputs fold left to right
+//    K5'/K6   value histogram and the stuffedBits encoder of the count path, in stream-writer mode
+//  Output bytes go straight to the 129 files.  HBM bytes per input k-mer: ~(b+34)/8 read, 2(W+4) written+read by the
+//  merge, (W+4) read by the encoder.  Bound: HBM bandwidth (decode: latency of one dependent chain per thread).
+
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.cuh"
+
+namespace {
+
+//  ---- K7: block decode ------------------------------------------------------------------------------
+
+struct __align__(16) UnionBlock {       //  one serialised block of an input file (host-made table)
+  u64 byteOff;                          //  of the container, in the group's byte buffer of that input (8-aligned)
+  u64 outIdx;                           //  exclusive number of k-mers before it
+};
+
+//  Sequential MSB-first reader over the sub-blocks of one stuffedBits container (stuffedBits-v1.H:246-285:
+//  a field lies wholly inside one sub-block; it is read from the next one iff it does not fit the rest of this one).
+struct SubReader {
+  const u64 *len;                       //  sub-block lengths in bits
+  const u64 *cur;                       //  first word of the current sub-block
+  u32        blk, nSub;
+  u64        pos;                       //  bit position inside the current sub-block
+  bool       bad;
+
+  __device__ __forceinline__ void move(u64 w) {
+    if (pos + w <= len[blk]) return;
+    if (blk + 1 >= nSub) { bad = true; return; }
+    cur += (len[blk] + 63) >> 6;
+    blk++;
+    pos = 0;
+  }
+  __device__ __forceinline__ u64 binary(u32 w) {           //  0 < w <= 64
+    move(w);
+    if (bad) return 0;
+    const u64 wd = pos >> 6;
+    const u32 fr = 64 - (u32)(pos & 63);
+    u64 v;
+    if (w <= fr) v = cur[wd] >> (fr - w);
+    else         v = (cur[wd] << (w - fr)) | (cur[wd + 1] >> (64 - (w - fr)));
+    if (w < 64) v &= (((u64)1 << w) - 1);
+    pos += w;
+    return v;
+  }
+  __device__ __forceinline__ u64 unary(void) {             //  zeros before the next one
+    move(1);
+    if (bad) return 0;
+    const u64 end = len[blk];
+    u64 v = 0;
+    u64 wd = pos >> 6;
+    u64 word = cur[wd] << (pos & 63);                       //  bits from pos on, at the top
+    u32 have = 64 - (u32)(pos & 63);                        //  of which are valid
+    while (word == 0) {
+      v += have;  pos += have;
+      if (pos >= end) { bad = true; return 0; }
+      wd++;  word = cur[wd];  have = 64;
+    }
+    const u32 z = (u32)__clzll((long long)word);
+    v += z;  pos += z + 1;
+    if (pos > end) bad = true;
+    return v;
+  }
+};
+
+__device__ __forceinline__ void store_kmer(u64 *out, u64 i, u64 prefix, u32 wSuffix, u64 sufHi, u64 sufLo) {
+  out[i] = (wSuffix >= 64 ? 0 : (prefix << wSuffix)) | sufLo;      //  k <= 32: 2k <= 64
+  (void)sufHi;
+}
+__device__ __forceinline__ void store_kmer(ulonglong2 *out, u64 i, u64 prefix, u32 wSuffix, u64 sufHi, u64 sufLo) {
+  ulonglong2 v;
+  v.x = sufLo;  v.y = sufHi;
+  if (wSuffix < 64)       { v.x |= prefix << wSuffix;  v.y |= wSuffix ? (prefix >> (64 - wSuffix)) : 0; }
+  else if (wSuffix < 128) { v.y |= prefix << (wSuffix - 64); }
+  out[i] = v;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(128)
+decode_kernel(const uint8_t *__restrict__ data, const UnionBlock *__restrict__ tab, u64 nBlocks, u32 wSuffix,
+              typename KeyT<KW>::type *__restrict__ keys, u32 *__restrict__ vals, u64 capacity, u32 *__restrict__ err) {
+  const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nBlocks) return;
+  const u64 *c = (const u64 *)(data + tab[b].byteOff);
+  SubReader r;
+  r.nSub = (u32)c[1];
+  r.len  = c + 2 + r.nSub;
+  r.cur  = r.len + r.nSub;
+  r.blk  = 0;  r.pos = 0;  r.bad = (r.nSub == 0);
+  if (r.bad) { atomicOr(err, 1u); return; }
+
+  //  528 header bits (kmers-files.C:36-52)
+  const u64 m1 = r.binary(64), m2 = r.binary(64);
+  const u64 prefix = r.binary(64), n = r.binary(64);
+  const u32 kCode = (u32)r.binary(8);
+  r.binary(32);                                             //  unaryBits: implied by the stream
+  const u32 bBits = (u32)r.binary(32);
+  r.binary(64);
+  const u32 cCode = (u32)r.binary(8);
+  r.binary(64);  r.binary(64);
+  if (r.bad || m1 != 0x7461446c7972656dull || m2 != 0x0a3030656c694661ull || kCode != 1 || cCode != 1 ||
+      bBits > wSuffix || tab[b].outIdx + n > capacity) { atomicOr(err, 2u); return; }
+
+  const u32 ls = bBits <= 64 ? 0 : bBits - 64, rs = bBits <= 64 ? bBits : 64;
+  const u64 o  = tab[b].outIdx;
+  u64 hi = 0;                                               //  running high part (<= 2^unaryBits)
+  for (u64 i = 0; i < n && !r.bad; i++) {
+    hi += r.unary();
+    const u64 bh = ls ? r.binary(ls) : 0;
+    const u64 bl = rs ? r.binary(rs) : 0;
+    //  suffix = hi << bBits | binary  (kmers-files.C:97-107), as (sufHi : sufLo)
+    u64 sLo, sHi;
+    if (bBits >= 64) { sLo = bl;  sHi = bh | (bBits - 64 < 64 ? (hi << (bBits - 64)) : 0); }
+    else             { sLo = bl | (bBits ? (hi << bBits) : hi);  sHi = bBits ? (hi >> (64 - bBits)) : 0; }
+    store_kmer(keys, o + i, prefix, wSuffix, sHi, sLo);
+  }
+  for (u64 i = 0; i < n && !r.bad; i++) vals[o + i] = (u32)r.binary(32);
+  if (r.bad) atomicOr(err, 4u);
+}
+
+//  ---- K8: merge-path union with summed values ------------------------------------------------------------
+
+__device__ __forceinline__ bool key_less(u64 a, u64 b)                              { return a < b; }
+__device__ __forceinline__ bool key_less(const ulonglong2 &a, const ulonglong2 &b)  { return a.y < b.y || (a.y == b.y && a.x < b.x); }
+
+const int MG_THREADS = 256;
+const int MG_ITEMS   = 8;
+const int MG_TILE    = MG_THREADS * MG_ITEMS;
+
+//  Merge path: how many elements of A are among the first `diag` elements of merge(A, B), A first on ties.
+template <typename Key>
+__device__ __forceinline__ u64 merge_path(const Key *a, u64 nA, const Key *b, u64 nB, u64 diag) {
+  u64 lo = diag > nB ? diag - nB : 0, hi = diag < nA ? diag : nA;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;                         //  take mid from A, diag - mid from B?
+    if (!key_less(b[diag - 1 - mid], a[mid])) lo = mid + 1; //  a[mid] <= b[diag-1-mid]: a[mid] comes first
+    else                                      hi = mid;
+  }
+  return lo;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(MG_THREADS)
+merge_sum_kernel(const typename KeyT<KW>::type *__restrict__ ka, const u32 *__restrict__ va, u64 nA,
+                 const typename KeyT<KW>::type *__restrict__ kb, const u32 *__restrict__ vb, u64 nB,
+                 typename KeyT<KW>::type *__restrict__ ko, u32 *__restrict__ vo, u64 *__restrict__ nOut,
+                 u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
+  typedef typename KeyT<KW>::type Key;
+  __shared__ Key  sKey[MG_TILE + 2];
+  __shared__ u32  sVal[MG_TILE + 2];
+  __shared__ u64  sPart[2], sTile, sExcl;
+  __shared__ u32  warpTot[MG_THREADS / 32];
+
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+  const u64 tile  = sTile;
+  const u64 total = nA + nB;
+  const u64 d0 = tile * MG_TILE, d1 = (d0 + MG_TILE < total) ? d0 + MG_TILE : total;
+  if (t < 2) sPart[t] = merge_path(ka, nA, kb, nB, t == 0 ? d0 : d1);
+  __syncthreads();
+  const u64 aLo = sPart[0], aHi = sPart[1], bLo = d0 - aLo, bHi = d1 - aHi;
+  const u32 na = (u32)(aHi - aLo), nb = (u32)(bHi - bLo);
+
+  //  window: [A part | B part] plus, behind each, the element that follows it in its list (partner / guard)
+  Key *sa = sKey;            u32 *sva = sVal;
+  Key *sb = sKey + na + 1;   u32 *svb = sVal + na + 1;
+  for (u32 i = t; i < na; i += MG_THREADS) { sa[i] = ka[aLo + i]; sva[i] = va[aLo + i]; }
+  for (u32 i = t; i <= nb; i += MG_THREADS) if (bLo + i < nB) { sb[i] = kb[bLo + i]; svb[i] = vb[bLo + i]; }
+  __syncthreads();
+
+  //  my MG_ITEMS consecutive outputs of the tile
+  const u32 n  = (u32)(d1 - d0);
+  const u32 m0 = min(t * MG_ITEMS, n), m1 = min(m0 + MG_ITEMS, n);
+  u32 ai = (u32)merge_path(sa, (u64)na, sb, (u64)nb, (u64)m0), bi = m0 - ai;
+
+  Key oKey[MG_ITEMS];
+  u32 oVal[MG_ITEMS];
+  u32 keepMask = 0;
+  for (u32 m = m0; m < m1; m++) {
+    const bool takeA = (bi >= nb) || (ai < na && !key_less(sb[bi], sa[ai]));
+    Key k;  u32 v;  bool head;
+    if (takeA) {
+      k = sa[ai];  v = sva[ai];  head = true;                //  k-mers are distinct within a database
+      if (bLo + bi < nB && key_eq(sb[bi], k)) v += svb[bi];   //  its partner in B (next unconsumed element; may be the guard)
+      ai++;
+    } else {
+      k = sb[bi];  v = svb[bi];
+      //  a duplicate iff A holds the same k-mer: it would be the last element of A before this point
+      bool dup = false;
+      if (ai > 0)        dup = key_eq(sa[ai - 1], k);
+      else if (aLo > 0)  dup = key_eq(ka[aLo - 1], k);
+      head = !dup;
+      bi++;
+    }
+    const u32 j = m - m0;
+    oKey[j] = k;  oVal[j] = v;
+    if (head && v != 0) keepMask |= 1u << j;                 //  merylOp-nextMer.C:640-641: a zero value is not output
+  }
+
+  //  compaction: exclusive position of my kept elements in the tile, then in the output (chained scan)
+  const u32 mine = __popc(keepMask);
+  u32 incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32)o) incl += x;
+  }
+  if (lane == 31) warpTot[warp] = incl;
+  __syncthreads();
+  u32 wOff = 0, tileTot = 0;
+  for (u32 w = 0; w < MG_THREADS / 32; w++) { const u32 c = warpTot[w]; if (w < warp) wOff += c; tileTot += c; }
+
+  if (warp == 0) {
+    if (lane == 0) st_volatile_u64(status + tile, (tile == 0 ? MB_ST_INC : MB_ST_AGG) | tileTot);
+    const u64 excl = lookback_warp(status, tile, lane);
+    if (lane == 0) {
+      if (tile != 0) st_volatile_u64(status + tile, MB_ST_INC | (excl + tileTot));
+      sExcl = excl;
+      if (d1 == total) *nOut = excl + tileTot;
+    }
+  }
+  __syncthreads();
+
+  u64 o = sExcl + wOff + (incl - mine);
+  for (u32 j = 0; j < MG_ITEMS; j++)
+    if (keepMask & (1u << j)) { ko[o] = oKey[j]; vo[o] = oVal[j]; o++; }
+}
+
+//  Drop zero values of a single list (a lone input still goes through `_value == 0` -> skip).
+template <int KW>
+__global__ void __launch_bounds__(256)
+count_nonzero_kernel(const u32 *__restrict__ v, u64 n, u64 *__restrict__ out) {
+  u64 c = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) c += (v[i] != 0);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long *)out, (unsigned long long)c);
+}
+
+
+//  ---- host: stuffedBits reader for the master index, file helpers ------------------------------------------
+
+struct HostBits {                                           //  sequential reader over a serialised stuffedBits
+  const u64 *len = nullptr, *cur = nullptr;
+  u32 blk = 0, nSub = 0;
+  u64 pos = 0;
+  bool open(const uint8_t *d, size_t n) {
+    if (n < 16) return false;
+    memcpy(&nSub, d + 8, 4);
+    if (nSub == 0 || n < 16 + 16 * (size_t)nSub) return false;
+    len = (const u64 *)(d + 16) + nSub;
+    cur = len + nSub;
+    size_t words = 0;
+    for (u32 i = 0; i < nSub; i++) words += (len[i] + 63) / 64;
+    return n >= 16 + 16 * (size_t)nSub + 8 * words;
+  }
+  u64 get(u32 w) {
+    if (pos + w > len[blk]) { cur += (len[blk] + 63) / 64; blk++; pos = 0; }
+    const u64 wd = pos >> 6;  const u32 fr = 64 - (u32)(pos & 63);
+    u64 v = (w <= fr) ? (cur[wd] >> (fr - w)) : ((cur[wd] << (w - fr)) | (cur[wd + 1] >> (64 - (w - fr))));
+    if (w < 64) v &= (((u64)1 << w) - 1);
+    pos += w;
+    return v;
+  }
+};
+
+int readWhole(const std::string &path, std::vector<uint8_t> &out) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return mb_fail(MB_EIO, "cannot open '%s': %s", path.c_str(), strerror(errno));
+  struct stat st;
+  if (fstat(fileno(f), &st) != 0) { fclose(f); return mb_fail(MB_EIO, "cannot stat '%s'", path.c_str()); }
+  out.resize((size_t)st.st_size);
+  if (st.st_size && fread(out.data(), 1, out.size(), f) != out.size()) { fclose(f); return mb_fail(MB_EIO, "short read from '%s'", path.c_str()); }
+  fclose(f);
+  return MB_OK;
+}
+
+int writeFile(const std::string &path, const void *p, size_t n) {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return mb_fail(MB_EIO, "cannot create '%s': %s", path.c_str(), strerror(errno));
+  if (n && fwrite(p, 1, n, f) != n) { fclose(f); return mb_fail(MB_EIO, "short write to '%s'", path.c_str()); }
+  if (fclose(f) != 0) return mb_fail(MB_EIO, "cannot close '%s'", path.c_str());
+  return MB_OK;
+}
+
+struct InputDb {
+  std::string dir;
+  u32 k = 0, wPrefix = 0, wSuffix = 0;
+  u64 fileBytes[64] = { 0 };                                //  .merylData sizes
+  u64 fileKmers[64] = { 0 };                                //  from the per-file block indexes
+};
+
+int openDb(const char *dir, InputDb &db) {
+  db.dir = dir;
+  std::vector<uint8_t> m;
+  MB_TRY(readWhole(db.dir + "/merylIndex", m));
+  HostBits hb;
+  if (!hb.open(m.data(), m.size())) return mb_fail(MB_EFORMAT, "'%s/merylIndex' is not a meryl index", dir);
+  const u64 m1 = hb.get(64), m2 = hb.get(64);
+  if (m1 != 0x646e496c7972656dull || m2 != 0x33302e765f5f7865ull)
+    return mb_fail(MB_EFORMAT, "'%s' is not a meryl v.03 database (kmers-reader.C:41-120)", dir);
+  db.wPrefix = (u32)hb.get(32);  db.wSuffix = (u32)hb.get(32);
+  const u32 nfb = (u32)hb.get(32), nbb = (u32)hb.get(32);
+  const u32 flags = (u32)hb.get(32);
+  if (nfb != 6 || nbb + 6 != db.wPrefix || ((db.wPrefix + db.wSuffix) & 1))
+    return mb_fail(MB_EFORMAT, "'%s': unexpected index geometry (%u file bits, %u block bits, prefix %u, suffix %u)", dir, nfb, nbb, db.wPrefix, db.wSuffix);
+  if (flags & 1) return mb_fail(MB_EINVAL, "'%s' is a multiset database; union-sum of multisets is not supported", dir);
+  db.k = (db.wPrefix + db.wSuffix) / 2;
+  if (db.k < 3 || db.k > 64) return mb_fail(MB_EFORMAT, "'%s': k=%u", dir, db.k);
+  char path[4096];
+  for (u32 f = 0; f < 64; f++) {
+    struct stat st;
+    mb_file_name(path, sizeof(path), dir, f, false);
+    if (stat(path, &st) != 0) return mb_fail(MB_EIO, "cannot stat '%s': %s", path, strerror(errno));
+    db.fileBytes[f] = (u64)st.st_size;
+    std::vector<uint8_t> ix;
+    mb_file_name(path, sizeof(path), dir, f, true);
+    MB_TRY(readWhole(path, ix));
+    if (ix.size() % 24) return mb_fail(MB_EFORMAT, "'%s' is not a block index", path);
+    for (size_t i = 0; i + 24 <= ix.size(); i += 24) { u64 nk; memcpy(&nk, ix.data() + i + 16, 8); db.fileKmers[f] += nk; }
+  }
+  return MB_OK;
+}
+
+struct Carve {
+  uint8_t *base; size_t size, off = 0;
+  Carve(uint8_t *b, size_t s) : base(b), size(s) {}
+  void *take(size_t bytes) {
+    const size_t o = (off + 255) / 256 * 256;
+    if (o + bytes > size) return nullptr;
+    off = o + bytes;
+    return base + o;
+  }
+};
+
+#define MB_UCUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) { rc = mb_fail(MB_ENODEVICE, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } \
+  } while (0)
+#define MB_UTRY(call)  do { rc = (call); if (rc != MB_OK) goto done; } while (0)
+
+}  //  namespace
+
+
+extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                            uint64_t workspaceBytes, mb_union_stats *stOut) {
+  mb_clear_error();
+  if (!inDirs || nInputs == 0 || !outDir) return mb_fail(MB_EINVAL, "mb_union_sum: NULL argument");
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return mb_fail(MB_ENODEVICE, "mb_union_sum: no CUDA device (this library has no CPU path)");
+
+  std::vector<InputDb> in(nInputs);
+  for (u32 i = 0; i < nInputs; i++) {
+    if (!inDirs[i]) return mb_fail(MB_EINVAL, "mb_union_sum: NULL input");
+    MB_TRY(openDb(inDirs[i], in[i]));
+    if (in[i].k != in[0].k) return mb_fail(MB_EINVAL, "k-mer sizes differ: '%s' has k=%u, '%s' has k=%u", inDirs[0], in[0].k, inDirs[i], in[i].k);
+  }
+  const u32 k = in[0].k, kw = k <= 32 ? 1 : 2, W = 8 * kw;
+  const u32 wP = 12, wS = 2 * k - wP;                       //  kmers-writer.C:52-58: every non-count operation writes prefix 12
+  if (2 * k < wP + 1) return mb_fail(MB_EINVAL, "union-sum needs k >= 7 (the stream writer's 12-bit prefix)");
+
+  mb_union_stats st;
+  memset(&st, 0, sizeof(st));
+  st.nInputs = nInputs;  st.k = k;
+
+  int rc = MB_OK;
+  uint8_t *arena = nullptr;
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[2] = { nullptr, nullptr }, evAll[2] = { nullptr, nullptr };
+  MbHistogram hist;
+  std::map<u64, u64> histMap;
+  u64 nUnique = 0, nDistinct = 0, nTotal = 0;
+
+  {
+    if (device >= 0) MB_UCUDA(cudaSetDevice(device));
+    size_t freeB = 0, totalB = 0;
+    MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
+    size_t want = workspaceBytes ? (size_t)workspaceBytes : (freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2);
+    if (want > freeB) want = freeB;
+    want = want / 256 * 256;
+    if (cudaMalloc((void **)&arena, want) != cudaSuccess) { cudaGetLastError(); arena = nullptr; rc = mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want); goto done; }
+    MB_UCUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { MB_UCUDA(cudaEventCreate(&ev[i])); MB_UCUDA(cudaEventCreate(&evAll[i])); }
+    MB_UCUDA(cudaEventRecord(evAll[0], s));
+
+    if (mkdir(outDir, 0777) != 0 && errno != EEXIST) { rc = mb_fail(MB_EIO, "cannot create directory '%s': %s", outDir, strerror(errno)); goto done; }
+
+    //  small fixed tables at the bottom of the arena
+    Carve top(arena, want);
+    u64 *dHistSmall = (u64 *)top.take((size_t)MB_HIST_SMALL * 8);
+    u64 *dCtl       = (u64 *)top.take(64 * 8);              //  [0..7] encoder totals, [8] nOut, [9] hist overflow count, [10..12] hist totals, [16] err
+    u64 *dFileBase  = (u64 *)top.take(64 * 8);
+    if (!dHistSmall || !dCtl || !dFileBase) { rc = mb_fail(MB_ENOMEM, "device arena too small"); goto done; }
+    MB_UCUDA(cudaMemsetAsync(dHistSmall, 0, (size_t)MB_HIST_SMALL * 8, s));
+    MB_UCUDA(cudaMemsetAsync(dCtl, 0, 64 * 8, s));
+    MB_UCUDA(cudaMemsetAsync(dFileBase, 0, 64 * 8, s));
+    const size_t fixedOff = top.off;
+
+    //  what a group of files needs on the device (upper bound):
+    //    raw bytes + block tables | decoded inputs | two merge buffers | encoder (meta, output, sub-block table, index) | big-value list
+    auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
+      size_t need = (size_t)64 << 20;
+      u64 nk = 0;
+      for (u32 i = 0; i < nInputs; i++)
+        for (u32 f = f0; f < f1; f++) {
+          need += in[i].fileBytes[f] + 256;
+          need += in[i].fileBytes[f] / 104 * sizeof(UnionBlock) + 4096;      //  a block is at least 104 bytes
+          need += in[i].fileKmers[f] * (W + 4) + 512;
+          nk   += in[i].fileKmers[f];
+        }
+      need += 2 * (nk * (W + 4) + 1024);                                    //  merge ping-pong
+      need += nk * ((wS + 34 + 7) / 8 + 1) + (size_t)(f1 - f0) * 64 * 4096 + nk / 64;   //  encoded blocks (every block <= n(b+34) + headers)
+      need += nk / MG_TILE * 16 + nk / MB_HIST_SMALL * 4 + 65536;
+      return need;
+    };
+
+    std::vector<uint8_t> hostFile;
+    u32 f0 = 0;
+    while (f0 < 64) {
+      u32 f1 = f0 + 1;
+      if (fixedOff + groupNeed(f0, f1) > want) {
+        rc = mb_fail(MB_ENOMEM, "data file %u of the inputs needs %zu bytes on the device, %zu available", f0, groupNeed(f0, f1), want - fixedOff);
+        goto done;
+      }
+      const u32 maxFiles = getenv("MB_UNION_MAX_FILES") ? (u32)strtoul(getenv("MB_UNION_MAX_FILES"), nullptr, 10) : 64;   //  testing knob
+      while (f1 < 64 && f1 - f0 < maxFiles && fixedOff + groupNeed(f0, f1 + 1) <= want) f1++;
+      st.nGroups++;
+
+      Carve g(arena + fixedOff, want - fixedOff);
+      typedef std::pair<void *, u32 *> List;
+      std::vector<List> lists(nInputs);
+      std::vector<u64>  listN(nInputs, 0);
+      u32 *dErr = (u32 *)(dCtl + 16);
+
+      //  ---- read + decode every input's part of the group -------------------------------------------------
+      MB_UCUDA(cudaEventRecord(ev[0], s));
+      for (u32 i = 0; i < nInputs; i++) {
+        u64 bytes = 0, nk = 0;
+        for (u32 f = f0; f < f1; f++) { bytes += (in[i].fileBytes[f] + 7) / 8 * 8; nk += in[i].fileKmers[f]; }
+        uint8_t *dRaw = (uint8_t *)g.take(bytes + 16);
+        void    *dKey = g.take(nk * W + 16);
+        u32     *dVal = (u32 *)g.take(nk * 4 + 16);
+        if (!dRaw || !dKey || !dVal) { rc = mb_fail(MB_ENOMEM, "internal: union group does not fit"); goto done; }
+        std::vector<UnionBlock> tab;
+        u64 at = 0, idx = 0;
+        char path[4096];
+        for (u32 f = f0; f < f1; f++) {
+          mb_file_name(path, sizeof(path), in[i].dir.c_str(), f, false);
+          MB_UTRY(readWhole(path, hostFile));
+          size_t p = 0;
+          while (p < hostFile.size()) {                      //  walk the containers (stuffedBits-v1.C:117-196)
+            if (hostFile.size() - p < 16) { rc = mb_fail(MB_EFORMAT, "'%s': truncated block at byte %zu", path, p); goto done; }
+            u32 nSub;  memcpy(&nSub, hostFile.data() + p + 8, 4);
+            if (nSub == 0 || hostFile.size() - p < 16 + 16 * (size_t)nSub + 32) { rc = mb_fail(MB_EFORMAT, "'%s': bad block at byte %zu", path, p); goto done; }
+            const u64 *len = (const u64 *)(hostFile.data() + p + 16) + nSub;
+            size_t words = 0;
+            for (u32 j = 0; j < nSub; j++) words += (len[j] + 63) / 64;
+            const size_t sz = 16 + 16 * (size_t)nSub + 8 * words;
+            if (hostFile.size() - p < sz) { rc = mb_fail(MB_EFORMAT, "'%s': truncated block at byte %zu", path, p); goto done; }
+            u64 nkB;  memcpy(&nkB, hostFile.data() + p + 16 + 16 * (size_t)nSub + 24, 8);      //  header word 3 = nKmers
+            UnionBlock ub;  ub.byteOff = at + p;  ub.outIdx = idx;
+            tab.push_back(ub);
+            idx += nkB;
+            p += sz;
+          }
+          if (idx > nk) { rc = mb_fail(MB_EFORMAT, "'%s' holds more k-mers than its index says", path); goto done; }
+          if (!hostFile.empty()) MB_UCUDA(cudaMemcpyAsync(dRaw + at, hostFile.data(), hostFile.size(), cudaMemcpyHostToDevice, s));
+          MB_UCUDA(cudaStreamSynchronize(s));                //  hostFile is reused
+          st.h2dBytes += hostFile.size();  st.inBytes += hostFile.size();
+          at += (hostFile.size() + 7) / 8 * 8;
+        }
+        UnionBlock *dTab = (UnionBlock *)g.take(tab.size() * sizeof(UnionBlock) + 16);
+        if (!dTab) { rc = mb_fail(MB_ENOMEM, "internal: union block table does not fit"); goto done; }
+        if (!tab.empty()) {
+          MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
+          const unsigned grid = (unsigned)((tab.size() + 127) / 128);
+          if (kw == 1) decode_kernel<1><<<grid, 128, 0, s>>>(dRaw, dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
+          else         decode_kernel<2><<<grid, 128, 0, s>>>(dRaw, dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
+          MB_UCUDA(cudaGetLastError());
+          MB_UCUDA(cudaStreamSynchronize(s));                //  tab is a local
+          st.nLaunches++;
+          st.h2dBytes += tab.size() * sizeof(UnionBlock);
+        }
+        lists[i] = List(dKey, dVal);  listN[i] = idx;
+        st.nInputKmers += idx;
+      }
+      {
+        u32 err = 0;
+        MB_UCUDA(cudaMemcpyAsync(&err, dErr, 4, cudaMemcpyDeviceToHost, s));
+        MB_UCUDA(cudaEventRecord(ev[1], s));
+        MB_UCUDA(cudaStreamSynchronize(s));
+        if (err) { rc = mb_fail(MB_EFORMAT, "corrupt block in the inputs (decoder flags 0x%x)", err); goto done; }
+        float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msDecode += ms;
+      }
+
+      //  ---- fold the lists: ((A + B) + C) + ... ; a lone input is merged with an empty list (drops zero values) ----
+      u64 total = 0;
+      for (u32 i = 0; i < nInputs; i++) total += listN[i];
+      void *mk[2] = { g.take(total * W + 16), g.take(total * W + 16) };
+      u32  *mv[2] = { (u32 *)g.take(total * 4 + 16), (u32 *)g.take(total * 4 + 16) };
+      const u64 maxTiles = total / MG_TILE + 2;
+      u64 *dStatus = (u64 *)g.take((maxTiles + 2) * 8);
+      if (!mk[0] || !mk[1] || !mv[0] || !mv[1] || !dStatus) { rc = mb_fail(MB_ENOMEM, "internal: union merge buffers do not fit"); goto done; }
+
+      MB_UCUDA(cudaEventRecord(ev[0], s));
+      const void *curK = lists[0].first;  const u32 *curV = lists[0].second;  u64 curN = listN[0];
+      int pp = 0;
+      for (u32 i = 1; i <= nInputs; i++) {
+        if (i == nInputs && nInputs > 1) break;
+        const void *bk = (i < nInputs) ? lists[i].first : nullptr;
+        const u32  *bv = (i < nInputs) ? lists[i].second : nullptr;
+        const u64   bn = (i < nInputs) ? listN[i] : 0;
+        const u64 tiles = (curN + bn + MG_TILE - 1) / MG_TILE;
+        MB_UCUDA(cudaMemsetAsync(dCtl + 8, 0, 8, s));
+        if (tiles) {
+          MB_UCUDA(cudaMemsetAsync(dStatus, 0, (tiles + 2) * 8, s));
+          if (kw == 1) merge_sum_kernel<1><<<(unsigned)tiles, MG_THREADS, 0, s>>>((const u64 *)curK, curV, curN, (const u64 *)bk, bv, bn, (u64 *)mk[pp], mv[pp], dCtl + 8, dStatus + 2, dStatus);
+          else         merge_sum_kernel<2><<<(unsigned)tiles, MG_THREADS, 0, s>>>((const ulonglong2 *)curK, curV, curN, (const ulonglong2 *)bk, bv, bn, (ulonglong2 *)mk[pp], mv[pp], dCtl + 8, dStatus + 2, dStatus);
+          MB_UCUDA(cudaGetLastError());
+          st.nLaunches++;
+        }
+        u64 nOut = 0;
+        MB_UCUDA(cudaMemcpyAsync(&nOut, dCtl + 8, 8, cudaMemcpyDeviceToHost, s));
+        MB_UCUDA(cudaStreamSynchronize(s));
+        curK = mk[pp];  curV = mv[pp];  curN = nOut;
+        pp ^= 1;
+      }
+      MB_UCUDA(cudaEventRecord(ev[1], s));
+      MB_UCUDA(cudaStreamSynchronize(s));
+      { float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msMerge += ms; }
+      const u64 D = curN;
+      st.nOutputKmers += D;
+
+      //  ---- value histogram + encode (stream-writer rules) + write the group's files -------------------------------
+      MB_UCUDA(cudaEventRecord(ev[0], s));
+      const u64 histBigCap = D / MB_HIST_SMALL + 1024;
+      u32 *dHistBig = (u32 *)g.take(histBigCap * 4);
+      const u64 nBlocks = (u64)(f1 - f0) * 64;
+      MbBlockMeta *dMeta = (MbBlockMeta *)g.take(nBlocks * sizeof(MbBlockMeta));
+      void *dScanTmp     = g.take(mb_encode_scan_tmp_bytes(nBlocks));
+      u64  *dIdx         = (u64 *)g.take(nBlocks * 24);
+      if (!dHistBig || !dMeta || !dScanTmp || !dIdx) { rc = mb_fail(MB_ENOMEM, "internal: union encode tables do not fit"); goto done; }
+      MB_UCUDA(cudaMemsetAsync(dCtl + 9, 0, 8, s));
+      MB_UCUDA(cudaMemcpyAsync(dCtl + 8, &D, 8, cudaMemcpyHostToDevice, s));
+      MB_UCUDA(mb_launch_value_histogram_counts(curV, dCtl + 8, D, dHistSmall, dHistBig, dCtl + 9, histBigCap, dCtl + 10, s));
+
+      MbEncodeParams ep;
+      ep.keys = curK;  ep.runStart = nullptr;  ep.nDistinct = D;  ep.keyWords = kw;  ep.k = k;  ep.wPrefix = wP;
+      ep.blockLo = (u64)f0 * 64;  ep.nBlocks = nBlocks;  ep.counts = curV;  ep.streamMode = 1;
+      MB_UCUDA(cudaMemsetAsync(dCtl, 0, 8 * 8, s));
+      MB_UCUDA(mb_launch_encode_layout(ep, dMeta, dCtl, dScanTmp, s));
+      u64 encTotals[8];
+      MB_UCUDA(cudaMemcpyAsync(encTotals, dCtl, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
+      std::vector<MbBlockMeta> meta(nBlocks);
+      MB_UCUDA(cudaMemcpyAsync(meta.data(), dMeta, nBlocks * sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
+      MB_UCUDA(cudaStreamSynchronize(s));
+      st.nLaunches += 6;
+      if (encTotals[4]) { rc = mb_fail(MB_ENOMEM, "a 12-bit prefix holds more than 16 Mi k-mers; splitting such blocks (kmers-writer-stream.C:131-141) is not implemented"); goto done; }
+
+      uint8_t *dOut = (uint8_t *)g.take(encTotals[0] + 16);
+      u32     *dSub = (u32 *)g.take(encTotals[1] * 4 + 16);
+      if (!dOut || !dSub) { rc = mb_fail(MB_ENOMEM, "internal: the encoded group (%llu bytes) does not fit", (unsigned long long)encTotals[0]); goto done; }
+      MB_UCUDA(cudaMemsetAsync(dOut, 0, encTotals[0], s));
+      MbEncodeChunk ch = { 0, nBlocks, 0, 0 };
+      MB_UCUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl, dSub, dOut, dIdx, dFileBase, s));
+      st.nLaunches += 2;
+
+      std::vector<uint8_t> outBytes(encTotals[0]), outIdx(nBlocks * 24);
+      if (encTotals[0]) MB_UCUDA(cudaMemcpyAsync(outBytes.data(), dOut, encTotals[0], cudaMemcpyDeviceToHost, s));
+      MB_UCUDA(cudaMemcpyAsync(outIdx.data(), dIdx, nBlocks * 24, cudaMemcpyDeviceToHost, s));
+      MB_UCUDA(cudaEventRecord(ev[1], s));
+      MB_UCUDA(cudaStreamSynchronize(s));
+      { float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msEncode += ms; }
+      st.d2hBytes += encTotals[0] + nBlocks * 24;
+
+      for (u32 f = f0; f < f1; f++) {
+        const u64 b0 = (u64)(f - f0) * 64;
+        const u64 byte0 = meta[b0].outByte, byte1 = (f + 1 < f1) ? meta[b0 + 64].outByte : encTotals[0];
+        char path[4096];
+        mb_file_name(path, sizeof(path), outDir, f, false);
+        MB_UTRY(writeFile(path, outBytes.data() + byte0, byte1 - byte0));
+        mb_file_name(path, sizeof(path), outDir, f, true);
+        MB_UTRY(writeFile(path, outIdx.data() + b0 * 24, 64 * 24));
+        st.outBytes += byte1 - byte0 + 64 * 24;
+      }
+
+      //  big histogram values of this group
+      u64 bigN = 0;
+      MB_UCUDA(cudaMemcpy(&bigN, dCtl + 9, 8, cudaMemcpyDeviceToHost));
+      if (bigN > histBigCap) { rc = mb_fail(MB_ENOMEM, "internal: value histogram overflow list too small"); goto done; }
+      if (bigN) {
+        std::vector<u32> big(bigN);
+        MB_UCUDA(cudaMemcpy(big.data(), dHistBig, bigN * 4, cudaMemcpyDeviceToHost));
+        for (u32 v : big) histMap[v]++;
+      }
+      f0 = f1;
+    }
+
+    //  ---- master index --------------------------------------------------------------------------------------
+    std::vector<u64> hs(MB_HIST_SMALL);
+    u64 totals[3];
+    MB_UCUDA(cudaMemcpy(hs.data(), dHistSmall, (size_t)MB_HIST_SMALL * 8, cudaMemcpyDeviceToHost));
+    MB_UCUDA(cudaMemcpy(totals, dCtl + 10, sizeof(totals), cudaMemcpyDeviceToHost));
+    st.d2hBytes += (size_t)MB_HIST_SMALL * 8;
+    nUnique = totals[0];  nDistinct = totals[1];  nTotal = totals[2];
+    for (u64 v = 1; v < MB_HIST_SMALL; v++) if (hs[v]) { hist.values.push_back(v); hist.occ.push_back(hs[v]); }
+    for (auto &kv : histMap) { hist.values.push_back(kv.first); hist.occ.push_back(kv.second); }
+    hist.nUnique = nUnique;  hist.nDistinct = nDistinct;  hist.nTotal = nTotal;
+    std::vector<uint8_t> master;
+    mb_build_master_index(k, wP, hist, master);
+    MB_UTRY(writeFile(std::string(outDir) + "/merylIndex", master.data(), master.size()));
+    st.outBytes += master.size();
+    st.nUnique = nUnique;  st.nDistinct = nDistinct;  st.nTotal = nTotal;
+
+    MB_UCUDA(cudaEventRecord(evAll[1], s));
+    MB_UCUDA(cudaStreamSynchronize(s));
+    { float ms = 0;  cudaEventElapsedTime(&ms, evAll[0], evAll[1]);  st.msTotal = ms; }
+  }
+
+done:
+  for (int i = 0; i < 2; i++) { if (ev[i]) cudaEventDestroy(ev[i]); if (evAll[i]) cudaEventDestroy(evAll[i]); }
+  if (s) cudaStreamDestroy(s);
+  if (arena) cudaFree(arena);
+  if (rc == MB_OK && stOut) *stOut = st;
+  return rc;
+}

@@ -1,0 +1,73 @@
+"""GPU parity tests of `meryl union-sum` through the C ABI (mb_union_sum) and the command line: byte-identical with
+the golden union dbs written by the unmodified reference binary, with the C oracle on seeded inputs, and -- when
+oracle/_ref/meryl travelled to this box -- with the reference binary itself."""
+import os
+import subprocess
+
+import pytest
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import synth
+import union_cases as uc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", util.union_golden_cases())
+def test_union_golden(tmp_path, name):
+    uc.case_golden(str(tmp_path), name)
+
+
+@pytest.mark.parametrize("k", [7, 8, 15, 21, 31, 32, 33, 51, 64])
+def test_union_k_sweep(tmp_path, k):
+    uc.case_k_sweep(str(tmp_path), k, n=60_000)
+
+
+def test_union_of_unions_empty_single(tmp_path):
+    uc.case_union_of_unions(str(tmp_path), n=40_000)
+
+
+def test_union_low_complexity(tmp_path):
+    uc.case_low_complexity(str(tmp_path))
+
+
+def test_union_groups(tmp_path, monkeypatch):
+    uc.case_groups(str(tmp_path), monkeypatch)
+
+
+def test_union_cli_and_reference(tmp_path):
+    """Count two read sets with the GPU count path, union-sum them with the CLI; the result must equal the oracle's
+    (and the reference binary's) union of the oracle's counts."""
+    k = 21
+    fa, fb = tmp_path / "a.fq", tmp_path / "b.fq"
+    fa.write_bytes(synth.reads_fastq_bytes(300_000, 30_000, 150, 0.002, 5))
+    fb.write_bytes(synth.reads_fastq_bytes(300_000, 30_000, 150, 0.002, 6))
+    ga, gb, gu = str(tmp_path / "ga.meryl"), str(tmp_path / "gb.meryl"), str(tmp_path / "gu.meryl")
+    mb.count([str(fa)], ga, k, memory_gb=2)
+    mb.count([str(fb)], gb, k, memory_gb=2)
+    p = subprocess.run([mb.CLI_PATH, "union-sum", ga, gb, "output", gu], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    ou = str(tmp_path / "ou.meryl")
+    util.run_oracle(["union-sum", ga, gb, "output", ou])
+    util.assert_same_db(ou, gu)
+    if util.have_ref():
+        ru = str(tmp_path / "ru.meryl")
+        util.run_ref(["threads=8", "union-sum", ga, gb, "output", ru])
+        util.assert_same_db(ru, gu)
+
+
+def test_union_properties_large():
+    """Size-independent checks at a size the oracle does not reach quickly: union-sum of a db with itself doubles every
+    count and keeps the k-mers; totals add up."""
+    import tempfile
+    k = 21
+    with tempfile.TemporaryDirectory() as t:
+        fq = os.path.join(t, "r.fq")
+        with open(fq, "wb") as fh:
+            fh.write(synth.reads_fastq_bytes(5_000_000, 400_000, 150, 0.001, 11))
+        a, u = os.path.join(t, "a.meryl"), os.path.join(t, "u.meryl")
+        sa = mb.count([fq], a, k, memory_gb=4)
+        st = mb.union_sum([a, a], u)
+        assert st.nInputKmers == 2 * sa.nDistinct and st.nOutputKmers == sa.nDistinct
+        assert st.nTotal == 2 * sa.nTotal and st.nUnique == 0 and st.nDistinct == sa.nDistinct

@@ -1,0 +1,68 @@
+"""Shared bodies of the union-sum parity tests: the same cases run against the emulated library on the CPU
+(tests/test_cusim_union.py) and against the CUDA library on the GPU (tests/test_gpu_union.py)."""
+import os
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import synth
+
+
+def oracle_db(tmp, name, data, k, op="count", wprefix=None):
+    """A count db written by the C oracle (pinned to the reference by tests/test_oracle_vs_ref.py)."""
+    p = os.path.join(tmp, name + ".fa")
+    with open(p, "wb") as fh:
+        fh.write(data)
+    db = os.path.join(tmp, name + ".meryl")
+    words = ["k=%d" % k, "memory=2"] + (["wprefix=%d" % wprefix] if wprefix else [])
+    util.run_oracle(words + [op, p, "output", db])
+    return db
+
+
+def check_union(tmp, inputs, tag="u", **kw):
+    ora, out = os.path.join(tmp, tag + "_ora.meryl"), os.path.join(tmp, tag + "_dev.meryl")
+    util.run_oracle(["union-sum", *inputs, "output", ora])
+    st = mb.union_sum(inputs, out, **kw)
+    util.assert_same_db(ora, out)
+    return st, out
+
+
+def case_golden(tmp, name):
+    dbs, gold = util.load_union_golden(name, tmp)
+    out = os.path.join(tmp, "dev.meryl")
+    mb.union_sum(dbs, out)
+    util.assert_same_db(gold, out)
+
+
+def case_k_sweep(tmp, k, n=20_000):
+    common = synth.fasta_bytes(1, n, 500 + k)
+    a = oracle_db(tmp, "a", common + synth.fasta_bytes(1, n, 10 + k), k)
+    b = oracle_db(tmp, "b", synth.fasta_bytes(1, n, 99 + k) + common + common, k, wprefix=8 if k < 12 else None)
+    st, _ = check_union(tmp, [a, b])
+    assert st.nOutputKmers < st.nInputKmers           # the common part merged
+
+
+def case_union_of_unions(tmp, k=21, n=15_000):
+    """Stream-written inputs (prefix 12, absent blocks), an input without k-mers, a single input, itself twice."""
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(n, n // 20, 150, 0.01, 1), k)
+    b = oracle_db(tmp, "b", synth.reads_fastq_bytes(n, n // 20, 150, 0.01, 2), k, op="count-forward")
+    e = oracle_db(tmp, "e", b">x\nACGT\n", k)
+    _, u1 = check_union(tmp, [a, b], "u1")
+    _, u2 = check_union(tmp, [e, b], "u2")
+    for i, ins in enumerate([[u1, u2], [u1, a, e], [e, e], [u1], [a, a, a, a]]):
+        check_union(tmp, ins, "c%d" % i)
+
+
+def case_low_complexity(tmp, k=21):
+    rep = b">r\n" + b"ACGTTGCA" * 3_000 + b"\n>p\n" + b"A" * 30_000 + b"\n"
+    a = oracle_db(tmp, "a", rep + synth.fasta_bytes(1, 20_000, 3), k)
+    b = oracle_db(tmp, "b", rep + rep, k)
+    check_union(tmp, [a, b])
+
+
+def case_groups(tmp, monkeypatch, k=31):
+    """Several groups of data files (the device-memory plan), forced small."""
+    a = oracle_db(tmp, "a", synth.fasta_bytes(2, 20_000, 7), k)
+    b = oracle_db(tmp, "b", synth.fasta_bytes(2, 20_000, 8) + synth.fasta_bytes(1, 20_000, 7), k)
+    monkeypatch.setenv("MB_UNION_MAX_FILES", "5")
+    st, _ = check_union(tmp, [a, b])
+    assert st.nGroups == 13
