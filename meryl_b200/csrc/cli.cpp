@@ -46,7 +46,7 @@ static int unionSumMain(int argc, char **argv) {
   bool quiet = false;
   for (int i = 1; i < argc; i++) {
     const char *w = argv[i];
-    if (!strcmp(w, "union-sum") || !strncmp(w, "threads=", 8) || !strncmp(w, "memory=", 7) || !strncmp(w, "-V", 2) || !strcmp(w, "-P") ||
+    if (!strcmp(w, "union-sum") || !strncmp(w, "threads=", 8) || !strncmp(w, "memory=", 7) || !strncmp(w, "k=", 2) || !strncmp(w, "-V", 2) || !strcmp(w, "-P") ||
         !strcmp(w, "[") || !strcmp(w, "]")) continue;
     if (!strcmp(w, "-Q")) { quiet = true; continue; }
     if (!strcmp(w, "output")) {
