@@ -35,8 +35,7 @@ typedef unsigned int       u32;
 #define MB_MAX_BINS          1024       //  2^10 prefix bins
 #define MB_RADIX_BITS        6          //  LSD digit width: 64 digits = 32 words of two 16-bit private counters per thread
 #define MB_RADIX             64
-#define MB_RADIX2_BITS       8          //  sweep kernel v2: 256 digits, 128 threads x 64 words of two 16-bit private counters
-#define MB_RADIX2            256
+#define MB_SORT_DEFAULT_VERSION 1       //  sweep kernel used unless MB_SORT / mb_sort_set_version says otherwise (sort.cu)
 
 //  ---- key helpers -----------------------------------------------------------------------
 
@@ -176,7 +175,7 @@ struct MbSortPlan {
   u32  bits[24];
   u64  maxSegKeys;             //  longest segment, if the caller knows it (0 = unknown): < 2^32 enables 32-bit output offsets
 };
-int         mb_sort_version(void);                          //  1: 6-bit digits (sort_sweep_kernel), 2: 8-bit digits (sort2_sweep_kernel); env MB_SORT
+int         mb_sort_version(void);                          //  1: sort_sweep_kernel (6-bit digits); 2..4: sortx_sweep_kernel shapes (8 / 6 / 7 bits); env MB_SORT
 void        mb_sort_set_version(int v);
 u32         mb_sort_radix_bits(void);
 u32         mb_sort_radix(void);

@@ -28,12 +28,11 @@
 //
 //  Two sweep kernels share the tile table, the histogram and the scan (mb_sort_version()):
 //   v1  sort_sweep_kernel    256 threads x 32/16/8 keys, 6-bit digits  (32 suffix bits = 6 passes)
-//   v2  sort2_sweep_kernel   128 threads x 64/32/16 keys, 8-bit digits (32 suffix bits = 4 passes): the
-//       kernel is issue-bound, not DRAM-bound (ncu: 63 % issue slots busy at 21 % DRAM), so the lever is
-//       instructions per key over the whole sort: a third fewer passes at about the same instructions
-//       per key and pass.  256 digits x 128 threads x 16 bit = 64 KB of private counters + 32 KB of keys
-//       = 2 CTAs per SM; each thread carries 64 independent keys, which is where the latency hiding
-//       comes from at 8 warps per SM.
+//   v2-4 sortx_sweep_kernel  second generation, shaped by (threads, digit bits): the first one is issue-bound, not
+//       DRAM-bound (ncu: 63 % of the issue slots busy at 21 % DRAM), so the lever is instructions per key: 16-bit
+//       counter accesses, one PRMT per whole-byte digit, 32-bit output offsets -- about half the instructions per
+//       key and pass.  Measured on B200 (profiles/): the 8-bit shape (4 passes for 32 bits, but 64 KB of counters
+//       = 8 warps per SM) is latency-bound at 17 % issue utilisation and no faster than v1 over the whole sort.
 
 #include <string.h>
 
@@ -404,41 +403,52 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
 #undef MB_TICK
 }
 
-//  ---- v2: one 8-bit digit pass --------------------------------------------------------------------
+//  ---- sweep kernel, second generation: one digit pass, shaped by (threads, digit bits) ------------------------
 //
 //  Same algorithm as sort_sweep_kernel (blocked keys, private 16-bit counters, raking scan, publish,
-//  reorder in shared memory, look-back inside the segment, coalesced digit runs), reshaped for 256 digits:
-//    * 128 threads, each owning 64 / 32 / 16 consecutive keys (256 bytes);
-//    * counter word (d & 127, t) holds digit d in its low and digit d + 128 in its high half; a row (all
-//      threads of one digit pair) is 128 words + 4 words of padding, so thread t rakes row t with 128-bit
-//      shared-memory accesses, bank-conflict free;
-//    * thread t publishes / resolves digits t and t + 128.
+//  reorder in shared memory, look-back inside the segment, coalesced digit runs) on a smaller instruction
+//  budget, and for any digit width:
+//    * 16-bit counter accesses: counter word (d mod ROWS, t) holds digit d in its low and digit d + ROWS in
+//      its high half (ROWS = half the radix); the scan leaves every counter holding the stage position of the
+//      thread's next key of that digit (the high halves start at the number of low-half keys), so placing a
+//      key is load / +1 / store / store;
+//    * thread t rakes the ROWS consecutive words [ROWS t, ROWS t + ROWS) of the row-major counter array with
+//      128-bit accesses; 4 words of padding behind every such segment keep them bank-conflict free;
+//    * whole-byte digits are extracted with one PRMT; output offsets are 32 bits from the segment start when
+//      the segments are shorter than 2^32 keys.
+//  Shapes (mb_sort_version):  2: 128 threads x 8 bits, 2 CTAs/SM   3: 256 threads x 6 bits, 3 CTAs/SM
+//                             4: 256 threads x 7 bits, 2 CTAs/SM
 
-const int S2_THREADS = 128;
-const int S2_WARPS   = S2_THREADS / 32;
-const int S2_ROW     = S2_THREADS + 4;                 //  words per counter row (16-byte aligned, 4-bank skew per row)
+template <int VER> struct SweepShape;
+template <> struct SweepShape<2> { static const int THREADS = 128, RBITS = 8, MIN_CTAS = 2; };
+template <> struct SweepShape<3> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 3; };
+template <> struct SweepShape<4> { static const int THREADS = 256, RBITS = 7, MIN_CTAS = 2; };
 
-template <int KW> struct Sort2Shape;
-template <> struct Sort2Shape<0> { static const int ITEMS = 64; };   //  u32 suffix keys: 8192 per tile
-template <> struct Sort2Shape<1> { static const int ITEMS = 32; };   //  u64: 4096 per tile
-template <> struct Sort2Shape<2> { static const int ITEMS = 16; };   //  128 bit: 2048 per tile
-
-template <int KW> struct Sweep2Smem {
+template <int KW, int VER> struct SweepX {
   typedef typename KeyT<KW>::type Key;
-  static const int ITEMS    = Sort2Shape<KW>::ITEMS;
-  static const int TILE     = S2_THREADS * ITEMS;
-  static const int XPOSE    = (TILE + S2_THREADS) * sizeof(Key);                 //  one padding key per thread (ITEMS + 1 stride)
-  static const int CWORDS   = (MB_RADIX2 / 2) * S2_ROW;
-  static const int COUNTERS = CWORDS * 4;                                        //  67584 bytes
-  static const int BYTES    = COUNTERS + XPOSE;                                  //  [counters][transpose area == stage]
+  static const int THREADS  = SweepShape<VER>::THREADS;
+  static const int WARPS    = THREADS / 32;
+  static const int RBITS    = SweepShape<VER>::RBITS;
+  static const int RADIX    = 1 << RBITS;
+  static const int ROWS     = RADIX / 2;                                        //  counter rows (digit pairs d, d + ROWS)
+  static const int SEG      = ROWS + 4;                                         //  a thread's rake segment + padding, in words
+  static const int PER_ROW  = THREADS / ROWS;                                   //  rake segments per counter row
+  static const int ROWW     = THREADS + 4 * PER_ROW;                            //  padded row stride in words
+  static const int TILE     = (KW == 0 ? 8192 : KW == 1 ? 4096 : 2048);         //  == mb_sort_tile_keys()
+  static const int ITEMS    = TILE / THREADS;
+  static const int XPOSE    = (TILE + THREADS) * sizeof(Key);                   //  one padding key per thread (ITEMS + 1 stride)
+  static const int COUNTERS = THREADS * SEG * 4;
+  static const int BYTES    = COUNTERS + XPOSE;                                 //  [counters][transpose area == stage]
+  static const int DPT      = (RADIX + THREADS - 1) / THREADS;                  //  digits a thread publishes / resolves
+  static_assert(THREADS % ROWS == 0 && ROWS % 32 == 0, "shape");
 };
 
-struct Sweep2Shared {
+struct SweepXShared {
   unsigned char *buf;  u32 *binOff;  u64 *gofs;  u32 *gofs32;  u32 *warpTot;
 };
 
 //  Digit of a pass.  BYTE: the digit is one whole byte of the key (8 bits at a multiple of 8) -- a single
-//  PRMT instead of shift + mask; the v2 pass plan makes every pass but possibly the top one of this form.
+//  PRMT instead of shift + mask; the pass plan of the 8-bit shape makes every pass but possibly the top one so.
 template <bool BYTE> __device__ __forceinline__ u32 digit_of(u32 k, u32 shift, u32 bits) {
   return BYTE ? __byte_perm(k, 0, 0x4440 | (shift >> 3)) : key_field(k, shift, bits);
 }
@@ -454,23 +464,24 @@ template <bool BYTE> __device__ __forceinline__ u32 digit_of(const ulonglong2 &k
   return __byte_perm(w, 0, 0x4440 | ((shift >> 3) & 3));
 }
 
-//  16-bit counter of (digit d, thread t): row d & 127, low half for d < 128.  cbOff = 4 t; the result is
-//  buf + (d & 127) * ROWBYTES + (d >> 7) * 2 + 4 t, written so that it compiles to a shift and two multiply-adds.
+//  16-bit counter of (digit d, thread t): row d mod ROWS, low half for d < ROWS.  cbOff = 4 * (t + 4 * (t / ROWS)); the
+//  result is buf + (d mod ROWS) * ROWBYTES + (d / ROWS) * 2 + cbOff, written so that it compiles to a shift and two multiply-adds.
+template <int ROWS, int ROWW>
 __device__ __forceinline__ unsigned short *counter_of(unsigned char *buf, u32 cbOff, u32 d) {
-  u32 off = d * (S2_ROW * 4) + cbOff;
-  off -= (d >> 7) * (128 * S2_ROW * 4 - 2);
+  u32 off = d * (ROWW * 4) + cbOff;
+  off -= (d / ROWS) * (ROWS * ROWW * 4 - 2);
   return (unsigned short *)(buf + off);
 }
 
-template <int KW, bool FULL, bool BYTE>
+template <int KW, int VER, bool FULL, bool BYTE>
 __device__ __forceinline__ void
-sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
             u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
             const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, bool wide,
-            u64 *__restrict__ status, u32 epoch, const Sweep2Shared &sm) {
+            u64 *__restrict__ status, u32 epoch, const SweepXShared &sm) {
   typedef typename KeyT<KW>::type Key;
-  typedef Sweep2Smem<KW>          S;
-  const int ITEMS = S::ITEMS;
+  typedef SweepX<KW, VER>         S;
+  const int ITEMS = S::ITEMS, THREADS = S::THREADS, ROWS = S::ROWS, RADIX = S::RADIX;
 
   u32 *counters = (u32 *)sm.buf;
   Key *xpose    = (Key *)(sm.buf + S::COUNTERS);
@@ -504,32 +515,29 @@ sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
       key[i] = xpose[t * (ITEMS + 1) + i];
   }
 
-  //  2. private counters: thread t zeroes row t, then bumps its 16-bit counter of each key's digit
-  {
-    uint4 *row = (uint4 *)&counters[t * S2_ROW];
+  //  2. private counters: thread t zeroes its rake segment, then bumps its 16-bit counter of each key's digit
+  uint4 *segp = (uint4 *)&counters[t * S::SEG];
 #pragma unroll
-    for (int j = 0; j < S2_ROW / 4; j++) row[j] = make_uint4(0, 0, 0, 0);
-  }
+  for (int j = 0; j < S::SEG / 4; j++) segp[j] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   const u32 myFirst = t * ITEMS;
-  const u32 cbOff = 4 * t;                               //  my column of the counter rows
+  const u32 cbOff   = 4 * (t + 4 * (t / ROWS));          //  my column of the counter rows
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
     if (FULL || myFirst + i < n) {
-      unsigned short *cp = counter_of(sm.buf, cbOff, digit_of<BYTE>(key[i], shift, bits));
+      unsigned short *cp = counter_of<ROWS, S::ROWW>(sm.buf, cbOff, digit_of<BYTE>(key[i], shift, bits));
       *cp = (unsigned short)(*cp + 1);
     }
   }
   __syncthreads();
 
-  //  raking scan, digit-major: thread t owns row t (digits t and t + 128 of all threads) as packed words.
-  //  Digits >= 128 (high halves) follow all digits < 128 in the stage: their prefixes start at tileLow.
+  //  raking scan, digit-major, over packed words.  Digits >= ROWS (high halves) follow all lower digits in the
+  //  stage: their prefixes start at the number of low-half keys.
   {
-    uint4 *row = (uint4 *)&counters[t * S2_ROW];
     u32 sum = 0;
 #pragma unroll
-    for (int j = 0; j < S2_THREADS / 4; j++) { const uint4 v = row[j]; sum += v.x + v.y + v.z + v.w; }
+    for (int j = 0; j < ROWS / 4; j++) { const uint4 v = segp[j]; sum += v.x + v.y + v.z + v.w; }
     u32 incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
       const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -539,32 +547,37 @@ sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
     __syncthreads();
     u32 run = incl - sum, tot = 0;
 #pragma unroll
-    for (int w = 0; w < S2_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) run += c; tot += c; }
-    run += tot << 16;                                    //  + tileLow in the high half (both halves stay <= 16384)
-    binOff[t]       = run & 0xffff;                      //  start of my two digits' runs in the tile
-    binOff[t + 128] = run >> 16;
+    for (int w = 0; w < S::WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) run += c; tot += c; }
+    run += tot << 16;                                    //  + low-half total in the high half (both halves stay <= 2 * TILE)
+    if (t % S::PER_ROW == 0) {                           //  my segment starts a counter row: thread 0's slot of digits dl, dl + ROWS
+      const u32 dl = t / S::PER_ROW;
+      binOff[dl]        = run & 0xffff;                  //  start of the two digits' runs in the tile
+      binOff[dl + ROWS] = run >> 16;
+    }
 #pragma unroll
-    for (int j = 0; j < S2_THREADS / 4; j++) {
-      const uint4 v = row[j];
+    for (int j = 0; j < ROWS / 4; j++) {
+      const uint4 v = segp[j];
       uint4 o;
       o.x = run;  run += v.x;
       o.y = run;  run += v.y;
       o.z = run;  run += v.z;
       o.w = run;  run += v.w;
-      row[j] = o;
+      segp[j] = o;
     }
   }
-  if (t == 0) binOff[MB_RADIX2] = n;
+  if (t == 0) binOff[RADIX] = n;
   __syncthreads();
 
   //  3a. publish this tile's digit counts as early as possible ...
-  //  (digit 127's run ends where digit 128's begins, so binOff[d + 1] - binOff[d] holds for every d)
-  u32 myCount[2];
+  //  (digit ROWS-1's run ends where digit ROWS's begins, so binOff[d + 1] - binOff[d] holds for every d)
+  u32 myCount[S::DPT];
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const u32 d = t + 128 * h;
-    myCount[h] = binOff[d + 1] - binOff[d];
-    st_volatile_u64(status + tile * MB_RADIX2 + d, ST_MAKE(isFirst ? 2 : 1, epoch, myCount[h]));
+  for (int h = 0; h < S::DPT; h++) {
+    const u32 d = t + THREADS * h;
+    if (d < (u32)RADIX) {
+      myCount[h] = binOff[d + 1] - binOff[d];
+      st_volatile_u64(status + tile * RADIX + d, ST_MAKE(isFirst ? 2 : 1, epoch, myCount[h]));
+    }
   }
 
   //  4a. ... put the keys in digit-sorted order in shared memory: my counter of the key's digit now holds the
@@ -572,7 +585,7 @@ sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
     if (FULL || myFirst + i < n) {
-      unsigned short *cp = counter_of(sm.buf, cbOff, digit_of<BYTE>(key[i], shift, bits));
+      unsigned short *cp = counter_of<ROWS, S::ROWW>(sm.buf, cbOff, digit_of<BYTE>(key[i], shift, bits));
       const u32 pos = *cp;
       *cp = (unsigned short)(pos + 1);
       stage[pos] = key[i];
@@ -581,33 +594,35 @@ sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
 
   //  3b. ... and only then wait for the earlier tiles of this segment (batched walk, LB status words per
   //  L2 round trip; the segment's first tile ends it).
-  const u64 segBase = gbase[((u64)seg * nPasses + pass) * MB_RADIX2];        //  first key of the segment (digit 0 starts there)
+  const u64 segBase = gbase[((u64)seg * nPasses + pass) * RADIX];              //  first key of the segment (digit 0 starts there)
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int LB = 4;
-    const u32 d = t + 128 * h;
-    u64 excl = 0;
-    if (!isFirst) {
-      const u64 *p = status + (tile - 1) * MB_RADIX2 + d;
-      bool done = false;
-      while (!done) {
-        u64 v[LB];
+  for (int h = 0; h < S::DPT; h++) {
+    const int LB = (S::DPT > 1) ? 4 : 8;
+    const u32 d = t + THREADS * h;
+    if (d < (u32)RADIX) {
+      u64 excl = 0;
+      if (!isFirst) {
+        const u64 *p = status + (tile - 1) * RADIX + d;
+        bool done = false;
+        while (!done) {
+          u64 v[LB];
 #pragma unroll
-        for (int b = 0; b < LB; b++) v[b] = ld_volatile_u64(p - (size_t)b * MB_RADIX2);   //  may read before the segment: ignored below
+          for (int b = 0; b < LB; b++) v[b] = ld_volatile_u64(p - (size_t)b * RADIX);     //  may read before the segment: ignored below
 #pragma unroll
-        for (int b = 0; b < LB; b++) {
-          if (done) break;
-          if (ST_FLAG(v[b]) == 0 || ST_EPOCH(v[b]) != epoch) break;                       //  not published yet: poll again from here
-          excl += ST_VALUE(v[b]);
-          p -= MB_RADIX2;
-          if (ST_FLAG(v[b]) == 2) done = true;
+          for (int b = 0; b < LB; b++) {
+            if (done) break;
+            if (ST_FLAG(v[b]) == 0 || ST_EPOCH(v[b]) != epoch) break;                     //  not published yet: poll again from here
+            excl += ST_VALUE(v[b]);
+            p -= RADIX;
+            if (ST_FLAG(v[b]) == 2) done = true;
+          }
         }
+        st_volatile_u64(status + tile * RADIX + d, ST_MAKE(2, epoch, excl + myCount[h]));
       }
-      st_volatile_u64(status + tile * MB_RADIX2 + d, ST_MAKE(2, epoch, excl + myCount[h]));
+      const u64 g = gbase[((u64)seg * nPasses + pass) * RADIX + d] + excl - binOff[d];   //  + stage index = global index
+      gofs[d]   = g;
+      gofs32[d] = (u32)(g - segBase);                    //  same, relative to the segment (mod 2^32)
     }
-    const u64 g = gbase[((u64)seg * nPasses + pass) * MB_RADIX2 + d] + excl - binOff[d];   //  + stage index = global index
-    gofs[d]   = g;
-    gofs32[d] = (u32)(g - segBase);                      //  same, relative to the segment (mod 2^32)
   }
   __syncthreads();
 
@@ -617,36 +632,36 @@ sweep2_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
     MB_OPAQUE_PTR(outSeg);                               //  keep it a base pointer: one IMAD.WIDE per store instead of 64-bit index math
     if (FULL) {
 #pragma unroll 16
-      for (u32 j = t; j < (u32)S::TILE; j += S2_THREADS) {
+      for (u32 j = t; j < (u32)S::TILE; j += THREADS) {
         const Key k = stage[j];
         outSeg[(u32)(gofs32[digit_of<BYTE>(k, shift, bits)] + j)] = k;
       }
     } else {
-      for (u32 j = t; j < n; j += S2_THREADS) {
+      for (u32 j = t; j < n; j += THREADS) {
         const Key k = stage[j];
         outSeg[(u32)(gofs32[digit_of<BYTE>(k, shift, bits)] + j)] = k;
       }
     }
   } else {
-    for (u32 j = t; j < n; j += S2_THREADS) {
+    for (u32 j = t; j < n; j += THREADS) {
       const Key k = stage[j];
       out[gofs[digit_of<BYTE>(k, shift, bits)] + j] = k;
     }
   }
 }
 
-template <int KW>
-__global__ void __launch_bounds__(S2_THREADS, 2)
-sort2_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+template <int KW, int VER>
+__global__ void __launch_bounds__(SweepShape<VER>::THREADS, SweepShape<VER>::MIN_CTAS)
+sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                    const TileInfo *__restrict__ info,
                    const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, u32 wide,
                    u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
-  typedef Sweep2Smem<KW> S;
+  typedef SweepX<KW, VER> S;
   extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
-  __shared__ u32  binOff[MB_RADIX2 + 1];
-  __shared__ u64  gofs[MB_RADIX2];
-  __shared__ u32  gofs32[MB_RADIX2];
-  __shared__ u32  warpTot[S2_WARPS];
+  __shared__ u32  binOff[S::RADIX + 1];
+  __shared__ u64  gofs[S::RADIX];
+  __shared__ u32  gofs32[S::RADIX];
+  __shared__ u32  warpTot[S::WARPS];
   __shared__ u64  sTile;
 
   if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
@@ -656,15 +671,15 @@ sort2_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
   const TileInfo ti = info[tile];
   const u32  seg     = ti.seg & 0x7fffffffu;
   const bool isFirst = (ti.seg >> 31) != 0;
-  Sweep2Shared sm;
+  SweepXShared sm;
   sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.gofs32 = gofs32;  sm.warpTot = warpTot;
 
   const bool full = (ti.n == (u32)S::TILE);
-  const bool byte = (bits == 8) && ((shift & 7) == 0);
-#define MB_S2_CALL(F, B) sweep2_tile<KW, F, B>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm)
-  if (full) { if (byte) MB_S2_CALL(true,  true); else MB_S2_CALL(true,  false); }
-  else      { if (byte) MB_S2_CALL(false, true); else MB_S2_CALL(false, false); }
-#undef MB_S2_CALL
+  const bool byte = (S::RBITS == 8) && (bits == 8) && ((shift & 7) == 0);
+#define MB_SX_CALL(F, B) sweepx_tile<KW, VER, F, B>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm)
+  if (S::RBITS == 8 && byte) { if (full) MB_SX_CALL(true, true);  else MB_SX_CALL(false, true);  }
+  else                       { if (full) MB_SX_CALL(true, false); else MB_SX_CALL(false, false); }
+#undef MB_SX_CALL
 }
 
 }  //  namespace
@@ -672,18 +687,26 @@ sort2_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
 
 //  ---- host side ---------------------------------------------------------------------------------
 
-//  Which sweep kernel: 1 (6-bit digits) or 2 (8-bit digits).  MB_SORT=1|2 in the environment, or
-//  mb_sort_set_version(); fixed for the lifetime of a plan / workspace.
+//  Which sweep kernel: 1 (first generation, 6-bit digits) or a shape of the second generation (2: 128 threads x
+//  8 bits, 3: 256 x 6, 4: 256 x 7).  MB_SORT=1..4 in the environment, or mb_sort_set_version(); fixed for the
+//  lifetime of a plan / workspace.
 static int g_sortVersion = 0;
 int mb_sort_version(void) {
   if (g_sortVersion == 0) {
     const char *e = getenv("MB_SORT");
-    g_sortVersion = (e && e[0] == '2') ? 2 : 1;
+    g_sortVersion = (e && e[0] >= '1' && e[0] <= '4' && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
   }
   return g_sortVersion;
 }
-void mb_sort_set_version(int v) { g_sortVersion = (v == 2) ? 2 : 1; }
-u32  mb_sort_radix_bits(void)   { return mb_sort_version() == 2 ? MB_RADIX2_BITS : MB_RADIX_BITS; }
+void mb_sort_set_version(int v) { g_sortVersion = (v >= 1 && v <= 4) ? v : MB_SORT_DEFAULT_VERSION; }
+u32  mb_sort_radix_bits(void) {
+  switch (mb_sort_version()) {
+    case 2:  return SweepShape<2>::RBITS;
+    case 3:  return SweepShape<3>::RBITS;
+    case 4:  return SweepShape<4>::RBITS;
+    default: return MB_RADIX_BITS;
+  }
+}
 u32  mb_sort_radix(void)        { return 1u << mb_sort_radix_bits(); }
 
 void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
@@ -696,7 +719,7 @@ void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
     //  v1: digits of (almost) equal width.  v2: whole bytes from the bottom (one PRMT per digit), the top
     //  pass takes what is left.
     u32 b = sortBits / P + (p < sortBits % P ? 1 : 0);
-    if (mb_sort_version() == 2) b = (sortBits - shift < 8) ? sortBits - shift : 8;
+    if (RB == 8) b = (sortBits - shift < 8) ? sortBits - shift : 8;
     plan->shift[p] = shift;
     plan->bits[p]  = b;
     shift += b;
@@ -704,9 +727,9 @@ void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
 }
 
 u32 mb_sort_tile_keys(u32 keyBytes) {                  //  the same for both sweep kernels: 8192 / 4096 / 2048
-  static_assert(SORT_THREADS * SortShape<0>::ITEMS == S2_THREADS * Sort2Shape<0>::ITEMS, "tile size");
-  static_assert(SORT_THREADS * SortShape<1>::ITEMS == S2_THREADS * Sort2Shape<1>::ITEMS, "tile size");
-  static_assert(SORT_THREADS * SortShape<2>::ITEMS == S2_THREADS * Sort2Shape<2>::ITEMS, "tile size");
+  static_assert(SORT_THREADS * SortShape<0>::ITEMS == SweepX<0, 2>::TILE && SweepX<0, 2>::TILE == SweepX<0, 3>::TILE, "tile size");
+  static_assert(SORT_THREADS * SortShape<1>::ITEMS == SweepX<1, 2>::TILE && SweepX<1, 4>::TILE == SweepX<1, 3>::TILE, "tile size");
+  static_assert(SORT_THREADS * SortShape<2>::ITEMS == SweepX<2, 2>::TILE && SweepX<2, 4>::TILE == SweepX<2, 3>::TILE, "tile size");
   return SORT_THREADS * (keyBytes == 4 ? SortShape<0>::ITEMS : keyBytes == 8 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
 }
 
@@ -784,14 +807,20 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
   if ((e = cudaFuncSetAttribute(sort_sweep_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem<KW>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sort2_sweep_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sweep2Smem<KW>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 2>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 3>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 4>::BYTES)) != cudaSuccess) return e;
   for (u32 p = 0; p < plan.nPasses; p++) {
-    if (version == 2)
-      sort2_sweep_kernel<KW><<<(unsigned)nTiles, S2_THREADS, Sweep2Smem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
-                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1);
+#define MB_SX_LAUNCH(V) do { typedef SweepX<KW, V> SX;                                                                                         \
+      sortx_sweep_kernel<KW, V><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                       \
+                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1); } while (0)
+    if      (version == 2) MB_SX_LAUNCH(2);
+    else if (version == 3) MB_SX_LAUNCH(3);
+    else if (version == 4) MB_SX_LAUNCH(4);
     else
       sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
                                                                      plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
+#undef MB_SX_LAUNCH
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;
     Key *tmp = src; src = dst; dst = tmp;

@@ -71,7 +71,7 @@ def test_extract_empty_and_no_kmers():
         assert len(glo) == 0
 
 
-@pytest.fixture(params=[1, 2], ids=["sweep6bit", "sweep8bit"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["sweep_v1", "sweep_128x8", "sweep_256x6", "sweep_256x7"])
 def sort_version(request):
     """Both sweep kernels (csrc/sort.cu): v1 = 6-bit digits, v2 = 8-bit digits."""
     L = mb.lib()

@@ -26,7 +26,10 @@ L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
 if passes > 1:
     os.environ["MB_MAX_PASS_KEYS"] = str(int(n_kmers / passes * 1.02))
 
-for sort_v, nofilter in [(1, 1), (1, 0), (2, 1), (2, 0)]:
+configs = [(1, 1), (1, 0), (2, 1), (2, 0)]
+if len(sys.argv) > 3 and sys.argv[3] == "sortonly":          # the sweep kernel shapes, filter on
+    configs = [(1, 0), (2, 0), (3, 0), (4, 0)]
+for sort_v, nofilter in configs:
     L.mb_dbg_sort_version(sort_v)
     if nofilter:
         os.environ["MB_NO_PREFILTER"] = "1"
