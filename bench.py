@@ -257,7 +257,10 @@ def main():
     peaks, peak_kind = _peaks()
     sort_bytes = stats.sortLaunchKeys * 2 * stats.keyBytes
     achieved = sort_bytes / (stats.msSort / 1000) / 1e9 if stats.msSort > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "sort_sweep_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    sweep_version = mb.lib().mb_dbg_sort_version(0)            # 0: query only
+    sweep_name = {1: "sort_sweep_kernel (256 threads, 6-bit digits)", 2: "sortx_sweep_kernel<128 threads, 8-bit digits>",
+                  3: "sortx_sweep_kernel<256 threads, 6-bit digits>", 4: "sortx_sweep_kernel<256 threads, 7-bit digits>"}.get(sweep_version, "?")
+    roofline = {"bound": "hbm", "kernel": sweep_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": sort_bytes / max(1, stats.sortPasses * stats.nPasses),
                 "launches": stats.sortPasses * stats.nPasses}

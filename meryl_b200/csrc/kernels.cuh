@@ -35,7 +35,7 @@ typedef unsigned int       u32;
 #define MB_MAX_BINS          1024       //  2^10 prefix bins
 #define MB_RADIX_BITS        6          //  LSD digit width: 64 digits = 32 words of two 16-bit private counters per thread
 #define MB_RADIX             64
-#define MB_SORT_DEFAULT_VERSION 1       //  sweep kernel used unless MB_SORT / mb_sort_set_version says otherwise (sort.cu)
+#define MB_SORT_DEFAULT_VERSION 3       //  sweep kernel used unless MB_SORT / mb_sort_set_version says otherwise (sort.cu)
 
 //  ---- key helpers -----------------------------------------------------------------------
 
