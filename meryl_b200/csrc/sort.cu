@@ -34,6 +34,7 @@
 //       key and pass.  Measured on B200 (profiles/): the 8-bit shape (4 passes for 32 bits, but 64 KB of counters
 //       = 8 warps per SM) is latency-bound at 17 % issue utilisation and no faster than v1 over the whole sort.
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.cuh"
@@ -146,6 +147,80 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
     const u32 c = sh[i];
     if (c) atomicAdd((unsigned long long *)&ghist[(u64)seg * pt.nPasses * radix + i], (unsigned long long)c);
   }
+}
+
+//  Joint form: adjacent passes are histogrammed together (one shared-memory atomic per PAIR of digits into a
+//  2^(b1+b2)-entry table) and split into the two marginal histograms only when a CTA flushes.  The kernel is
+//  bound by shared-memory atomic throughput, so halving the atomics per key about halves its time.
+struct SortHistGroups {
+  u32 nGroups;
+  u32 shift[SORT_MAX_PASSES];          //  of the group's first pass
+  u32 bitsLo[SORT_MAX_PASSES];         //  digit width of the first pass
+  u32 bitsAll[SORT_MAX_PASSES];        //  of the whole group (== bitsLo for a single pass)
+  u32 firstPass[SORT_MAX_PASSES];
+  u32 offset[SORT_MAX_PASSES];         //  of the group's table in shared memory (entries)
+  u32 total;                           //  entries of all tables
+};
+
+template <int KW>
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist2_kernel(const typename KeyT<KW>::type *__restrict__ keys,
+                  const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
+                  SortHistGroups hg, u32 nPasses, u32 radix, u64 *__restrict__ ghist) {
+  typedef typename KeyT<KW>::type Key;
+  const int TILE = SORT_THREADS * SortShape<KW>::ITEMS;
+  extern __shared__ __align__(16) unsigned char histSmem[];
+  u32 *jt = (u32 *)histSmem;                           //  hg.total joint counters
+  __shared__ u32 marg[HIST_WORDS];                     //  nPasses * radix marginal counters
+
+  const u32 t = threadIdx.x;
+  for (u32 i = t; i < hg.total; i += SORT_THREADS) jt[i] = 0;
+  __syncthreads();
+
+  const u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
+  u64 tileEnd = tile0 + HIST_TILES_PER_CTA;
+  if (tileEnd > nTiles) tileEnd = nTiles;
+  u32 seg = find_segment(segTile, nSegs, tile0);
+
+  auto flush = [&](u32 sg) {                           //  called by all threads
+    __syncthreads();
+    for (u32 i = t; i < nPasses * radix; i += SORT_THREADS) marg[i] = 0;
+    __syncthreads();
+    for (u32 g = 0; g < hg.nGroups; g++) {
+      const u32 n = 1u << hg.bitsAll[g], lowMask = (1u << hg.bitsLo[g]) - 1;
+      const bool pair = hg.bitsAll[g] != hg.bitsLo[g];
+      u32 *tab = jt + hg.offset[g];
+      for (u32 e = t; e < n; e += SORT_THREADS) {
+        const u32 c = tab[e];
+        if (c) {
+          atomicAdd(&marg[hg.firstPass[g] * radix + (e & lowMask)], c);
+          if (pair) atomicAdd(&marg[(hg.firstPass[g] + 1) * radix + (e >> hg.bitsLo[g])], c);
+          tab[e] = 0;
+        }
+      }
+    }
+    __syncthreads();
+    for (u32 i = t; i < nPasses * radix; i += SORT_THREADS) {
+      const u32 c = marg[i];
+      if (c) atomicAdd((unsigned long long *)&ghist[(u64)sg * nPasses * radix + i], (unsigned long long)c);
+    }
+  };
+
+  for (u64 tile = tile0; tile < tileEnd; tile++) {
+    u32 sNow = seg;
+    while (segTile[sNow + 1] <= tile) sNow++;
+    if (sNow != seg) { flush(seg); __syncthreads(); seg = sNow; }
+
+    const u64 begin = segStart[seg] + (tile - segTile[seg]) * TILE;
+    u64 n = segStart[seg + 1] - begin;
+    if (n > (u64)TILE) n = TILE;
+    for (u32 j = t; j < (u32)n; j += SORT_THREADS) {
+      const Key key = keys[begin + j];
+      for (u32 g = 0; g < hg.nGroups; g++)
+        atomicAdd(&jt[hg.offset[g] + key_field(key, hg.shift[g], hg.bitsAll[g])], 1u);
+    }
+  }
+  flush(seg);
 }
 
 //  ---- scan: counts -> first output index of each (segment, pass, digit) -------------------------
@@ -798,7 +873,24 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   for (u32 p = 0; p < SORT_MAX_PASSES; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
 
   const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
-  sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist);
+  const bool histSingle = getenv("MB_HIST_SINGLE") != nullptr;             //  A/B: one atomic per digit (the first form)
+  SortHistGroups hg;
+  memset(&hg, 0, sizeof(hg));
+  for (u32 p = 0; p < plan.nPasses; ) {                 //  pair adjacent passes while the joint table stays small
+    const u32 g = hg.nGroups++;
+    hg.shift[g] = plan.shift[p];  hg.bitsLo[g] = plan.bits[p];  hg.bitsAll[g] = plan.bits[p];  hg.firstPass[g] = p;  hg.offset[g] = hg.total;
+    if (!histSingle && p + 1 < plan.nPasses && plan.bits[p] + plan.bits[p + 1] <= 12 && hg.total + (1u << (plan.bits[p] + plan.bits[p + 1])) <= 16384) {
+      hg.bitsAll[g] += plan.bits[p + 1];
+      p += 2;
+    } else p += 1;
+    hg.total += 1u << hg.bitsAll[g];
+  }
+  if (histSingle || hg.total * 4 > 96 * 1024) {
+    sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist);
+  } else {
+    if ((e = cudaFuncSetAttribute(sort_hist2_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(hg.total * 4))) != cudaSuccess) return e;
+    sort_hist2_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, hg.total * 4, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, hg, plan.nPasses, (u32)R, ghist);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   sort_scan_kernel<<<dim3(nSegs, plan.nPasses), (unsigned)R, 0, s>>>(ghist, dSegStart, plan.nPasses);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -25,8 +25,10 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -308,6 +310,40 @@ int writeFile(const std::string &path, const void *p, size_t n) {
   return MB_OK;
 }
 
+//  Run job(0..n-1) on a few host threads (file reads / writes only: no CUDA calls inside).
+template <typename F>
+void parallelFor(size_t n, F job) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt < 1)  nt = 1;
+  if (nt > n)  nt = (unsigned)n;
+  if (nt <= 1) { for (size_t i = 0; i < n; i++) job(i); return; }
+  std::atomic<size_t> next(0);
+  std::vector<std::thread> th;
+  for (unsigned w = 0; w < nt; w++)
+    th.emplace_back([&]() { for (size_t i = next++; i < n; i = next++) job(i); });
+  for (auto &x : th) x.join();
+}
+
+struct HostBuf {                                            //  grow-only, never zero-filled
+  uint8_t *p = nullptr;  size_t cap = 0;
+  HostBuf() {}
+  HostBuf(const HostBuf &) = delete;
+  HostBuf &operator=(const HostBuf &) = delete;
+  ~HostBuf() { free(p); }
+  bool need(size_t n) { if (n > cap) { free(p); p = (uint8_t *)malloc(n ? n : 1); cap = p ? n : 0; } return p != nullptr; }
+  uint8_t *data(void) { return p; }
+};
+
+struct FileJob {                                            //  one input data file of the group
+  u32 input = 0, file = 0;
+  size_t off = 0, bytes = 0;                                //  place in the input's host buffer
+  std::vector<UnionBlock> tab;                              //  byteOff relative to the file, outIdx relative to its first k-mer
+  u64 nk = 0;
+  int rc = MB_OK;
+  std::string err;
+};
+
 struct InputDb {
   std::string dir;
   u32 k = 0, wPrefix = 0, wSuffix = 0;
@@ -441,7 +477,8 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
       return need;
     };
 
-    std::vector<uint8_t> hostFile;
+    std::vector<HostBuf> hostIn(nInputs);                    //  the group's file bytes, one buffer per input (reused by the next group)
+    HostBuf outBytes, outIdx;
     u32 f0 = 0;
     while (f0 < 64) {
       u32 f1 = f0 + 1;
@@ -460,51 +497,72 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
       u32 *dErr = (u32 *)(dCtl + 16);
 
       //  ---- read + decode every input's part of the group -------------------------------------------------
+      //  Host threads read the files into one buffer per input and walk the block containers (sizes only);
+      //  then one copy and one decode launch per input.
       MB_UCUDA(cudaEventRecord(ev[0], s));
+      std::vector<FileJob> jobs;
+      std::vector<size_t>  inBytes(nInputs, 0);
+      for (u32 i = 0; i < nInputs; i++)
+        for (u32 f = f0; f < f1; f++) {
+          FileJob j;  j.input = i;  j.file = f;  j.off = inBytes[i];  j.bytes = (size_t)in[i].fileBytes[f];
+          inBytes[i] += (j.bytes + 7) / 8 * 8;
+          jobs.push_back(std::move(j));
+        }
+      for (u32 i = 0; i < nInputs; i++)
+        if (!hostIn[i].need(inBytes[i] + 8)) { rc = mb_fail(MB_ENOMEM, "cannot allocate %zu bytes of host memory", inBytes[i]); goto done; }
+      parallelFor(jobs.size(), [&](size_t ji) {
+        FileJob &j = jobs[ji];
+        char path[4096];
+        mb_file_name(path, sizeof(path), in[j.input].dir.c_str(), j.file, false);
+        uint8_t *d = hostIn[j.input].data() + j.off;
+        FILE *fp = fopen(path, "rb");
+        if (!fp || (j.bytes && fread(d, 1, j.bytes, fp) != j.bytes)) { j.rc = MB_EIO; j.err = std::string("cannot read '") + path + "'"; if (fp) fclose(fp); return; }
+        fclose(fp);
+        size_t p = 0;
+        while (p < j.bytes) {                                //  walk the containers (stuffedBits-v1.C:117-196)
+          u32 nSub = 0;
+          if (j.bytes - p >= 16) memcpy(&nSub, d + p + 8, 4);
+          if (nSub == 0 || j.bytes - p < 16 + 16 * (size_t)nSub + 32) { j.rc = MB_EFORMAT; j.err = std::string("'") + path + "': bad block at byte " + std::to_string(p); return; }
+          const u64 *len = (const u64 *)(d + p + 16) + nSub;
+          size_t words = 0;
+          for (u32 q = 0; q < nSub; q++) words += (len[q] + 63) / 64;
+          const size_t sz = 16 + 16 * (size_t)nSub + 8 * words;
+          if (j.bytes - p < sz) { j.rc = MB_EFORMAT; j.err = std::string("'") + path + "': truncated block at byte " + std::to_string(p); return; }
+          u64 nkB;  memcpy(&nkB, d + p + 16 + 16 * (size_t)nSub + 24, 8);      //  header word 3 = nKmers
+          UnionBlock ub;  ub.byteOff = p;  ub.outIdx = j.nk;
+          j.tab.push_back(ub);
+          j.nk += nkB;
+          p += sz;
+        }
+      });
+      for (const FileJob &j : jobs) if (j.rc != MB_OK) { rc = mb_fail(j.rc, "%s", j.err.c_str()); goto done; }
+
+      std::vector<std::vector<UnionBlock>> tabs(nInputs);    //  alive until the stream has consumed them
       for (u32 i = 0; i < nInputs; i++) {
-        u64 bytes = 0, nk = 0;
-        for (u32 f = f0; f < f1; f++) { bytes += (in[i].fileBytes[f] + 7) / 8 * 8; nk += in[i].fileKmers[f]; }
-        uint8_t *dRaw = (uint8_t *)g.take(bytes + 16);
+        u64 nk = 0;
+        for (u32 f = f0; f < f1; f++) nk += in[i].fileKmers[f];
+        uint8_t *dRaw = (uint8_t *)g.take(inBytes[i] + 16);
         void    *dKey = g.take(nk * W + 16);
         u32     *dVal = (u32 *)g.take(nk * 4 + 16);
         if (!dRaw || !dKey || !dVal) { rc = mb_fail(MB_ENOMEM, "internal: union group does not fit"); goto done; }
-        std::vector<UnionBlock> tab;
-        u64 at = 0, idx = 0;
-        char path[4096];
-        for (u32 f = f0; f < f1; f++) {
-          mb_file_name(path, sizeof(path), in[i].dir.c_str(), f, false);
-          MB_UTRY(readWhole(path, hostFile));
-          size_t p = 0;
-          while (p < hostFile.size()) {                      //  walk the containers (stuffedBits-v1.C:117-196)
-            if (hostFile.size() - p < 16) { rc = mb_fail(MB_EFORMAT, "'%s': truncated block at byte %zu", path, p); goto done; }
-            u32 nSub;  memcpy(&nSub, hostFile.data() + p + 8, 4);
-            if (nSub == 0 || hostFile.size() - p < 16 + 16 * (size_t)nSub + 32) { rc = mb_fail(MB_EFORMAT, "'%s': bad block at byte %zu", path, p); goto done; }
-            const u64 *len = (const u64 *)(hostFile.data() + p + 16) + nSub;
-            size_t words = 0;
-            for (u32 j = 0; j < nSub; j++) words += (len[j] + 63) / 64;
-            const size_t sz = 16 + 16 * (size_t)nSub + 8 * words;
-            if (hostFile.size() - p < sz) { rc = mb_fail(MB_EFORMAT, "'%s': truncated block at byte %zu", path, p); goto done; }
-            u64 nkB;  memcpy(&nkB, hostFile.data() + p + 16 + 16 * (size_t)nSub + 24, 8);      //  header word 3 = nKmers
-            UnionBlock ub;  ub.byteOff = at + p;  ub.outIdx = idx;
-            tab.push_back(ub);
-            idx += nkB;
-            p += sz;
-          }
-          if (idx > nk) { rc = mb_fail(MB_EFORMAT, "'%s' holds more k-mers than its index says", path); goto done; }
-          if (!hostFile.empty()) MB_UCUDA(cudaMemcpyAsync(dRaw + at, hostFile.data(), hostFile.size(), cudaMemcpyHostToDevice, s));
-          MB_UCUDA(cudaStreamSynchronize(s));                //  hostFile is reused
-          st.h2dBytes += hostFile.size();  st.inBytes += hostFile.size();
-          at += (hostFile.size() + 7) / 8 * 8;
+        std::vector<UnionBlock> &tab = tabs[i];
+        u64 idx = 0;
+        for (const FileJob &j : jobs) {
+          if (j.input != i) continue;
+          for (UnionBlock ub : j.tab) { ub.byteOff += j.off;  ub.outIdx += idx;  tab.push_back(ub); }
+          idx += j.nk;
+          st.h2dBytes += j.bytes;  st.inBytes += j.bytes;
         }
+        if (idx > nk) { rc = mb_fail(MB_EFORMAT, "'%s' holds more k-mers than its block indexes say", in[i].dir.c_str()); goto done; }
         UnionBlock *dTab = (UnionBlock *)g.take(tab.size() * sizeof(UnionBlock) + 16);
         if (!dTab) { rc = mb_fail(MB_ENOMEM, "internal: union block table does not fit"); goto done; }
         if (!tab.empty()) {
+          MB_UCUDA(cudaMemcpyAsync(dRaw, hostIn[i].data(), inBytes[i], cudaMemcpyHostToDevice, s));
           MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
           const unsigned grid = (unsigned)((tab.size() + 127) / 128);
           if (kw == 1) decode_kernel<1><<<grid, 128, 0, s>>>(dRaw, dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
           else         decode_kernel<2><<<grid, 128, 0, s>>>(dRaw, dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
           MB_UCUDA(cudaGetLastError());
-          MB_UCUDA(cudaStreamSynchronize(s));                //  tab is a local
           st.nLaunches++;
           st.h2dBytes += tab.size() * sizeof(UnionBlock);
         }
@@ -592,7 +650,7 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
       MB_UCUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl, dSub, dOut, dIdx, dFileBase, s));
       st.nLaunches += 2;
 
-      std::vector<uint8_t> outBytes(encTotals[0]), outIdx(nBlocks * 24);
+      if (!outBytes.need(encTotals[0] + 8) || !outIdx.need(nBlocks * 24)) { rc = mb_fail(MB_ENOMEM, "cannot allocate %llu bytes of host memory", (unsigned long long)encTotals[0]); goto done; }
       if (encTotals[0]) MB_UCUDA(cudaMemcpyAsync(outBytes.data(), dOut, encTotals[0], cudaMemcpyDeviceToHost, s));
       MB_UCUDA(cudaMemcpyAsync(outIdx.data(), dIdx, nBlocks * 24, cudaMemcpyDeviceToHost, s));
       MB_UCUDA(cudaEventRecord(ev[1], s));
@@ -600,15 +658,28 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
       { float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msEncode += ms; }
       st.d2hBytes += encTotals[0] + nBlocks * 24;
 
-      for (u32 f = f0; f < f1; f++) {
-        const u64 b0 = (u64)(f - f0) * 64;
-        const u64 byte0 = meta[b0].outByte, byte1 = (f + 1 < f1) ? meta[b0 + 64].outByte : encTotals[0];
-        char path[4096];
-        mb_file_name(path, sizeof(path), outDir, f, false);
-        MB_UTRY(writeFile(path, outBytes.data() + byte0, byte1 - byte0));
-        mb_file_name(path, sizeof(path), outDir, f, true);
-        MB_UTRY(writeFile(path, outIdx.data() + b0 * 24, 64 * 24));
-        st.outBytes += byte1 - byte0 + 64 * 24;
+      {
+        std::vector<int> wrc(f1 - f0, MB_OK);
+        std::vector<std::string> werr(f1 - f0);
+        parallelFor(f1 - f0, [&](size_t fi) {
+          const u32 f = f0 + (u32)fi;
+          const u64 b0 = (u64)fi * 64;
+          const u64 byte0 = meta[b0].outByte, byte1 = (f + 1 < f1) ? meta[b0 + 64].outByte : encTotals[0];
+          char path[4096];
+          for (int isIdx = 0; isIdx < 2; isIdx++) {
+            mb_file_name(path, sizeof(path), outDir, f, isIdx != 0);
+            const void  *ptr = isIdx ? (const void *)(outIdx.data() + b0 * 24) : (const void *)(outBytes.data() + byte0);
+            const size_t len = isIdx ? (size_t)64 * 24 : (size_t)(byte1 - byte0);
+            FILE *fp = fopen(path, "wb");
+            if (!fp || (len && fwrite(ptr, 1, len, fp) != len) || fclose(fp) != 0) { wrc[fi] = MB_EIO; werr[fi] = std::string("cannot write '") + path + "': " + strerror(errno); return; }
+          }
+        });
+        for (u32 f = f0; f < f1; f++) {
+          if (wrc[f - f0] != MB_OK) { rc = mb_fail(MB_EIO, "%s", werr[f - f0].c_str()); goto done; }
+          const u64 b0 = (u64)(f - f0) * 64;
+          const u64 byte0 = meta[b0].outByte, byte1 = (f + 1 < f1) ? meta[b0 + 64].outByte : encTotals[0];
+          st.outBytes += byte1 - byte0 + 64 * 24;
+        }
       }
 
       //  big histogram values of this group

@@ -29,7 +29,14 @@ if passes > 1:
 configs = [(1, 1), (1, 0), (2, 1), (2, 0)]
 if len(sys.argv) > 3 and sys.argv[3] == "sortonly":          # the sweep kernel shapes, filter on
     configs = [(1, 0), (2, 0), (3, 0), (4, 0)]
-for sort_v, nofilter in configs:
+extra = [{}]
+if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel striped/blocked x histogram single/joint (default sweep)
+    configs = [(L.mb_dbg_sort_version(0), 0)]
+    extra = [{"MB_COUNT_STRIPED": "1", "MB_HIST_SINGLE": "1"}, {"MB_HIST_SINGLE": "1"}, {"MB_COUNT_STRIPED": "1"}, {}]
+for (sort_v, nofilter), env in [(c, e) for c in configs for e in extra]:
+    for k in ("MB_COUNT_STRIPED", "MB_HIST_SINGLE"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
     L.mb_dbg_sort_version(sort_v)
     if nofilter:
         os.environ["MB_NO_PREFILTER"] = "1"
@@ -54,7 +61,7 @@ for sort_v, nofilter in configs:
             c.close()
     d = best.as_dict()
     sort_bytes = d["sortLaunchKeys"] * 2 * d["keyBytes"]
-    print(json.dumps({"sort": sort_v, "prefilter": not nofilter, "gbp": gbp, "kmers": n_kmers, "passes": d["nPasses"], "sort_passes": d["sortPasses"],
+    print(json.dumps({"sort": sort_v, "prefilter": not nofilter, "env": env, "gbp": gbp, "kmers": n_kmers, "passes": d["nPasses"], "sort_passes": d["sortPasses"],
                       "ms": {k: round(d[k], 2) for k in ("msTotal", "msHistogram", "msExtract", "msSortHist", "msSort", "msCount", "msEncode")},
                       "gkmers_per_s": round(n_kmers / d["msTotal"] / 1e6, 2),
                       "sweep_GBps": round(sort_bytes / (d["msSort"] / 1000) / 1e9, 1) if d["msSort"] else None,
