@@ -260,8 +260,16 @@ def main():
     sweep_version = mb.lib().mb_dbg_sort_version(0)            # 0: query only
     sweep_name = {1: "sort_sweep_kernel (256 threads, 6-bit digits)", 2: "sortx_sweep_kernel<128 threads, 8-bit digits>",
                   3: "sortx_sweep_kernel<256 threads, 6-bit digits>", 4: "sortx_sweep_kernel<256 threads, 7-bit digits>"}.get(sweep_version, "?")
+    traffic = None                                              # DRAM bytes per launch, from the committed ncu capture of this kernel
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic_sweep.json")) as fh:
+            tr = json.load(fh)
+        if sweep_version == 3 and stats.keyBytes == 4:
+            traffic = tr["dram_bytes_per_key"] * stats.sortLaunchKeys / max(1, stats.sortPasses * stats.nPasses)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": sweep_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": sort_bytes / max(1, stats.sortPasses * stats.nPasses),
                 "launches": stats.sortPasses * stats.nPasses}
 

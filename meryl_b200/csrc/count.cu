@@ -213,11 +213,11 @@ count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restr
   }
 }
 
-//  Second form of the same kernel: blocked keys.  The striped form above spends three warp collectives per
-//  32 keys (shuffle for the predecessor, ballot, shuffle for the carry) and is latency-bound on them (ncu:
-//  24 % issue utilisation).  Here a warp transposes its rows through shared memory so that every thread owns
-//  16 CONSECUTIVE keys: run heads are plain compares against the previous register, and the only collectives
-//  left are one warp scan per thread and the block scan.
+//  Second form of the same kernel (MB_COUNT_BLOCKED=1; NOT the default: measured 40 % slower on B200): blocked keys.
+//  The striped form above spends three warp collectives per 32 keys (shuffle for the predecessor, ballot, shuffle
+//  for the carry).  Here a warp transposes its rows through shared memory so that every thread owns 16 CONSECUTIVE
+//  keys: run heads are plain compares against the previous register, and the only collectives left are one warp
+//  scan per thread and the block scan.
 __global__ void __launch_bounds__(CNT_THREADS, 4)
 count_suffix32b_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nHalves,
                        u64 endIndex, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart,
@@ -401,7 +401,9 @@ cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u6
   const u64 nHalves = 2 * (tileHi - tileLo);                 //  workspace: (2 + nHalves) u64
   if ((e = cudaMemsetAsync(dWorkspace, 0, (2 + nHalves) * sizeof(u64), s)) != cudaSuccess) return e;
   u64 *counter = (u64 *)dWorkspace, *status = counter + 2;
-  const bool striped = getenv("MB_COUNT_STRIPED") != nullptr;              //  A/B: the first (striped, collective-based) form
+  //  Measured on B200 (profiles/r1_ab_8gbp_countopts.jsonl): the striped form takes 36 ms per 6.9 G keys, the blocked form 50 ms
+  //  (its transposition through shared memory costs more than the collectives it saves) -- striped is the default.
+  const bool striped = getenv("MB_COUNT_BLOCKED") == nullptr;
   if (striped)
     count_suffix32_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
                                                                   binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);

@@ -149,9 +149,9 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
   }
 }
 
-//  Joint form: adjacent passes are histogrammed together (one shared-memory atomic per PAIR of digits into a
-//  2^(b1+b2)-entry table) and split into the two marginal histograms only when a CTA flushes.  The kernel is
-//  bound by shared-memory atomic throughput, so halving the atomics per key about halves its time.
+//  Joint form (MB_HIST_JOINT=1; not the default: measured equal): adjacent passes are histogrammed together (one
+//  shared-memory atomic per PAIR of digits into a 2^(b1+b2)-entry table) and split into the two marginal histograms
+//  only when a CTA flushes.
 struct SortHistGroups {
   u32 nGroups;
   u32 shift[SORT_MAX_PASSES];          //  of the group's first pass
@@ -873,7 +873,9 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   for (u32 p = 0; p < SORT_MAX_PASSES; p++) { pt.shift[p] = p < plan.nPasses ? plan.shift[p] : 0; pt.bits[p] = p < plan.nPasses ? plan.bits[p] : 0; }
 
   const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
-  const bool histSingle = getenv("MB_HIST_SINGLE") != nullptr;             //  A/B: one atomic per digit (the first form)
+  //  Measured on B200 (profiles/r1_ab_8gbp_countopts.jsonl): the joint form is no faster (22.2 ms either way per 6.9 G keys:
+  //  the kernel is not bound by the number of shared-memory atomics) -- the single form stays the default.
+  const bool histSingle = getenv("MB_HIST_JOINT") == nullptr;
   SortHistGroups hg;
   memset(&hg, 0, sizeof(hg));
   for (u32 p = 0; p < plan.nPasses; ) {                 //  pair adjacent passes while the joint table stays small

@@ -32,9 +32,9 @@ if len(sys.argv) > 3 and sys.argv[3] == "sortonly":          # the sweep kernel 
 extra = [{}]
 if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel striped/blocked x histogram single/joint (default sweep)
     configs = [(L.mb_dbg_sort_version(0), 0)]
-    extra = [{"MB_COUNT_STRIPED": "1", "MB_HIST_SINGLE": "1"}, {"MB_HIST_SINGLE": "1"}, {"MB_COUNT_STRIPED": "1"}, {}]
+    extra = [{}, {"MB_COUNT_BLOCKED": "1"}, {"MB_HIST_JOINT": "1"}, {"MB_COUNT_BLOCKED": "1", "MB_HIST_JOINT": "1"}]
 for (sort_v, nofilter), env in [(c, e) for c in configs for e in extra]:
-    for k in ("MB_COUNT_STRIPED", "MB_HIST_SINGLE"):
+    for k in ("MB_COUNT_BLOCKED", "MB_HIST_JOINT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     L.mb_dbg_sort_version(sort_v)
