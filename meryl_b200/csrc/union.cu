@@ -50,14 +50,30 @@ struct SubReader {
   const u64 *cur;                       //  first word of the current sub-block
   u32        blk, nSub;
   u64        pos;                       //  bit position inside the current sub-block
+  u64        lenCur;                    //  len[blk], in a register
+  u64        cw, cv;                    //  one-word cache: cv == cur[cw] (every word is fetched from memory once)
   bool       bad;
 
+  __device__ __forceinline__ void open(const u64 *container) {
+    nSub = (u32)container[1];
+    len  = container + 2 + nSub;
+    cur  = len + nSub;
+    blk  = 0;  pos = 0;  bad = (nSub == 0);
+    lenCur = bad ? 0 : len[0];
+    cw = ~0ull;  cv = 0;
+  }
+  __device__ __forceinline__ u64 word(u64 wd) {
+    if (wd != cw) { cv = cur[wd]; cw = wd; }
+    return cv;
+  }
   __device__ __forceinline__ void move(u64 w) {
-    if (pos + w <= len[blk]) return;
+    if (pos + w <= lenCur) return;
     if (blk + 1 >= nSub) { bad = true; return; }
-    cur += (len[blk] + 63) >> 6;
+    cur += (lenCur + 63) >> 6;
     blk++;
+    lenCur = len[blk];
     pos = 0;
+    cw = ~0ull;
   }
   __device__ __forceinline__ u64 binary(u32 w) {           //  0 < w <= 64
     move(w);
@@ -65,8 +81,8 @@ struct SubReader {
     const u64 wd = pos >> 6;
     const u32 fr = 64 - (u32)(pos & 63);
     u64 v;
-    if (w <= fr) v = cur[wd] >> (fr - w);
-    else         v = (cur[wd] << (w - fr)) | (cur[wd + 1] >> (64 - (w - fr)));
+    if (w <= fr) v = word(wd) >> (fr - w);
+    else       { const u64 a = word(wd);  v = (a << (w - fr)) | (word(wd + 1) >> (64 - (w - fr))); }
     if (w < 64) v &= (((u64)1 << w) - 1);
     pos += w;
     return v;
@@ -74,19 +90,18 @@ struct SubReader {
   __device__ __forceinline__ u64 unary(void) {             //  zeros before the next one
     move(1);
     if (bad) return 0;
-    const u64 end = len[blk];
     u64 v = 0;
     u64 wd = pos >> 6;
-    u64 word = cur[wd] << (pos & 63);                       //  bits from pos on, at the top
+    u64 bits = word(wd) << (pos & 63);                      //  bits from pos on, at the top
     u32 have = 64 - (u32)(pos & 63);                        //  of which are valid
-    while (word == 0) {
+    while (bits == 0) {
       v += have;  pos += have;
-      if (pos >= end) { bad = true; return 0; }
-      wd++;  word = cur[wd];  have = 64;
+      if (pos >= lenCur) { bad = true; return 0; }
+      wd++;  bits = word(wd);  have = 64;
     }
-    const u32 z = (u32)__clzll((long long)word);
+    const u32 z = (u32)__clzll((long long)bits);
     v += z;  pos += z + 1;
-    if (pos > end) bad = true;
+    if (pos > lenCur) bad = true;
     return v;
   }
 };
@@ -111,10 +126,7 @@ decode_kernel(const uint8_t *__restrict__ data, const UnionBlock *__restrict__ t
   if (b >= nBlocks) return;
   const u64 *c = (const u64 *)(data + tab[b].byteOff);
   SubReader r;
-  r.nSub = (u32)c[1];
-  r.len  = c + 2 + r.nSub;
-  r.cur  = r.len + r.nSub;
-  r.blk  = 0;  r.pos = 0;  r.bad = (r.nSub == 0);
+  r.open(c);
   if (r.bad) { atomicOr(err, 1u); return; }
 
   //  528 header bits (kmers-files.C:36-52)
