@@ -71,6 +71,11 @@ typedef struct mb_config {
 
 #define MB_FLAG_KEEP_COUNTED   1u   /*  keep (distinct k-mer, count) arrays on the host for mb_get_counted (tests)  */
 #define MB_FLAG_NO_IMAGES      2u   /*  do not copy the encoded db to the host (kernel-only benchmarking)           */
+#define MB_FLAG_COMPRESS       4u   /*  `compress`: homopolymer-compress the bases of file inputs (mb_add_file / mb_add_file_bytes) before
+                                     *  counting -- every run of one letter (case-insensitive, any letter) becomes its first letter, as
+                                     *  merylInput::loadBases does with homopolyCompress (src/meryl/merylInput.C:258-262,
+                                     *  src/utility/src/sequence/sequence-v1.C:204-260).  Bases pushed with mb_add_bases are taken as they
+                                     *  are: at that seam the reference has already compressed them.                                     */
 
 typedef struct mb_stats {
   uint64_t nBases;          /*  positions in the packed store (bases + record breaks)     */

@@ -25,6 +25,7 @@ _MODES = {"count": MODE_CANONICAL, "count-forward": MODE_FORWARD, "count-reverse
 
 FLAG_KEEP_COUNTED = 1
 FLAG_NO_IMAGES = 2
+FLAG_COMPRESS = 4
 
 
 class MerylB200Error(RuntimeError):

@@ -5,7 +5,7 @@
 //  :538-549 sequence inputs; usage text src/meryl/meryl.C:96-171):
 //
 //      meryl-b200 [-V|-Q|-P|-C] [k=K] [n=N] [memory=GB] [threads=T]
-//                 count|count-forward|count-reverse <seq files...> output <db.meryl>
+//                 count|count-forward|count-reverse [compress] <seq files...> output <db.meryl>
 //
 //  Words are order-free like the reference's.  Errors are a message on stderr and exit(1)
 //  (missing k: merylOp-count.C:311-312; missing output: :314-315).  `union-sum <dbs> output <db>` is the one
@@ -82,7 +82,7 @@ int main(int argc, char **argv) {
 
   uint32_t k = 0, mode = 0;
   uint64_t nExpected = 0, memBytes = physicalMemory();
-  bool haveOp = false, onlyConfig = false, quiet = false;
+  bool haveOp = false, onlyConfig = false, quiet = false, compress = false;
   const char *outDir = nullptr;
   std::vector<const char *> inputs;
 
@@ -97,6 +97,7 @@ int main(int argc, char **argv) {
     else if (!strncmp(w, "memory=", 7))       { memBytes = (uint64_t)(strtod(w + 7, 0) * 1024 * 1024 * 1024); }
     else if (!strncmp(w, "threads=", 8))      { }                         //  no CPU worker threads to size
     else if (isCountWord(w, &mode))           { haveOp = true; }
+    else if (!strcmp(w, "compress"))          { compress = true; }           //  merylCommandBuilder.C:237-240 (here: all inputs)
     else if (!strcmp(w, "output")) {
       if (i + 1 >= argc) { fprintf(stderr, "ERROR: 'output' needs a database name.\n"); return 1; }
       outDir = argv[++i];
@@ -147,6 +148,7 @@ int main(int argc, char **argv) {
   mb_config cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.k = k;  cfg.mode = mode;  cfg.wPrefix = wPrefix;  cfg.device = -1;
+  if (compress) cfg.flags |= MB_FLAG_COMPRESS;
 
   mb_stats st;
   if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), outDir, &st) != MB_OK) {

@@ -73,6 +73,8 @@ struct mb_ctx {
   size_t      fill       = 0;
   int         cur        = 0;
   bool        inRecord   = false;                    //  bases since the last '.'
+  uint8_t     hpLast     = 0;                        //  MB_FLAG_COMPRESS: last letter kept in this record (lower case), 0 at a record start
+  std::vector<char> hpBuf;
 
   //  results
   bool        counted    = false;
@@ -227,7 +229,24 @@ static int appendHost(mb_ctx *c, const char *p, size_t n) {
 static int parserSink(void *arg, const char *bases, size_t n) {
   mb_ctx *c = (mb_ctx *)arg;
   c->inRecord = !(n == 1 && bases[0] == '.');
-  return appendHost(c, bases, n);
+  if (!(c->cfg.flags & MB_FLAG_COMPRESS)) return appendHost(c, bases, n);
+  //  homopolymer compression (merylInput.C:258-262): a run of one letter keeps its first letter; the run state
+  //  carries over the pieces of a record (the reference's `skip` argument) and ends with the record.
+  //  (Two corners of the reference are not reproduced: a piece boundary of its 2 MB work buffers inside a run of
+  //  MIXED case is compared case-sensitively there, and a piece that consists only of the previous piece's last
+  //  letter yields one undefined byte there.)
+  c->hpBuf.resize(n);
+  size_t m = 0;
+  uint8_t last = c->hpLast;
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t b = (uint8_t)bases[i];
+    if (b == '.') { c->hpBuf[m++] = '.'; last = 0; continue; }
+    if ((b | 0x20) == last) continue;
+    c->hpBuf[m++] = (char)b;
+    last = b | 0x20;
+  }
+  c->hpLast = last;
+  return appendHost(c, c->hpBuf.data(), m);
 }
 
 //  Large buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)

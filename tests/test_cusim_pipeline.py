@@ -113,3 +113,20 @@ def test_sim_multi_pass(tmp_path):
     """A tiny arena forces several prefix-range passes (both key forms); the db must not change."""
     data = {"r.fq": synth.reads_fastq_bytes(30_000, 4_000, 150, 0.002, 77)}
     _vs_oracle(tmp_path, data, 21, 12, workspace_bytes=300 << 20, expect_key_bytes=4)
+
+
+def test_sim_compress(tmp_path):
+    """MB_FLAG_COMPRESS: homopolymer compression of file inputs (merylInput.C:258-262) on the host side of the ingest."""
+    rng = np.random.default_rng(4)
+    seq = bytearray()
+    for _ in range(6000):
+        seq += bytes([b"ACGTacgtN"[int(rng.integers(0, 9))]]) * int(rng.integers(1, 5))
+    fa = tmp_path / "hp.fa"
+    fa.write_bytes(b">a\n" + bytes(seq[:9000]) + b"\n" + bytes(seq[9000:]) + b"\n>b\nAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAACCCCCCCCCCCCCGT\n")
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=15", "wprefix=8", "compress", "count", str(fa), "output", ora])
+    with mb.Counter(15, 8, flags=mb.FLAG_COMPRESS) as c:
+        c.add_file(str(fa))
+        c.count()
+        c.write_db(out)
+    util.assert_same_db(ora, out)

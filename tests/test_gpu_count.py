@@ -213,6 +213,25 @@ def test_multi_pass_file_aligned_prefilter(tmp_path, monkeypatch, k, op, sort_ve
     util.assert_same_db(ora, out)
 
 
+def test_compress_cli(tmp_path):
+    """`meryl-b200 k=K count compress <files>`: homopolymer-compressed counting, against the oracle (and the reference)."""
+    rng = np.random.default_rng(8)
+    seq = bytearray()
+    for _ in range(60_000):
+        seq += bytes([b"ACGTacgtN"[int(rng.integers(0, 9))]]) * int(rng.integers(1, 5))
+    fa = tmp_path / "hp.fa"
+    fa.write_bytes(b">a\n" + bytes(seq) + b"\n")
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "gpu.meryl")
+    util.run_oracle(["k=21", "memory=2", "compress", "count", str(fa), "output", ora])
+    p = subprocess.run([mb.CLI_PATH, "k=21", "memory=2", "count", "compress", str(fa), "output", out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    util.assert_same_db(ora, out)
+    if util.have_ref():
+        ref = str(tmp_path / "ref.meryl")
+        util.run_ref(["k=21", "memory=2", "threads=4", "count", "compress", str(fa), "output", ref])
+        util.assert_same_db(ref, out)
+
+
 def test_device_generator_and_device_ingest_match_oracle(tmp_path):
     """bench.py's input path: reads generated on the device (csrc/synth.cu) and ingested from device
     memory must give the same db as the oracle run on the same reads written as a FASTQ file."""

@@ -107,3 +107,18 @@ def test_empty_and_no_kmers(tmp_path):
                                      (21, 86_670_000_000, 180)])
 def test_prefix_width_planner(k, n, mem):
     assert util.oracle_plan(k, n, int(mem * 1024 ** 3)) == util.ref_wprefix(k, n, mem)
+
+
+@pytest.mark.parametrize("k", [15, 21, 40])
+def test_compress_homopolymer_runs(tmp_path, k):
+    """`count compress`: runs of one letter collapse (case-insensitive, N runs too) before k-mers are formed."""
+    rng = np.random.default_rng(k)
+    recs = []
+    for i in range(40):
+        seq = bytearray()
+        for _ in range(400):
+            base = b"ACGTacgtN"[int(rng.integers(0, 9))]
+            seq += bytes([base]) * int(rng.integers(1, 6))
+        recs.append(b">r%d\n" % i + bytes(seq) + b"\n")
+    recs.append(b">polyA\n" + b"A" * 5000 + b"C" + b"a" * 70 + b"\n" + b"AAAA\n" + b"aaCC\n")   # runs across line ends
+    _both(tmp_path, {"hp.fa": b"".join(recs), "reads.fq": synth.reads_fastq_bytes(20_000, 500, 150, 0.01, 3)}, k, extra=("compress",))
