@@ -68,3 +68,31 @@ def test_oracle_union_sum_low_complexity_big_blocks(tmp_path):
     util.run_ref(["union-sum", a, b, "output", ref])
     util.run_oracle(["union-sum", a, b, "output", ora])
     util.assert_same_db(ref, ora)
+
+
+SET_OPS = ["union", "union-min", "union-max", "union-sum", "intersect", "intersect-min", "intersect-max", "intersect-sum",
+           "subtract", "difference", "symmetric-difference"]
+
+
+@pytest.fixture(scope="module")
+def three_dbs(tmp_path_factory):
+    """Three count dbs (written by the reference binary) that share some k-mers with different counts."""
+    t = tmp_path_factory.mktemp("setops")
+    k = 21
+    common = synth.reads_fastq_bytes(20_000, 1_500, 150, 0.0, 1)
+    a = _count_ref(t, "a", common + synth.reads_fastq_bytes(20_000, 700, 150, 0.0, 2), k)
+    b = _count_ref(t, "b", common[: len(common) // 2] + synth.reads_fastq_bytes(20_000, 900, 150, 0.0, 3), k)
+    c = _count_ref(t, "c", common + common + synth.reads_fastq_bytes(20_000, 300, 150, 0.0, 2), k)
+    return a, b, c
+
+
+@needs_ref
+@pytest.mark.parametrize("op", SET_OPS)
+def test_oracle_set_operations_vs_reference(tmp_path, three_dbs, op):
+    """Every operator of the merge family (merylOp-nextMer.C:559-612): one, two and three inputs, counts that differ."""
+    a, b, c = three_dbs
+    for tag, ins in (("2", [a, b]), ("3", [a, b, c]), ("1", [c]), ("rev", [c, a])):
+        ref, ora = str(tmp_path / ("ref" + tag)), str(tmp_path / ("ora" + tag))
+        util.run_ref(["threads=3", op, *ins, "output", ref])
+        util.run_oracle([op, *ins, "output", ora])
+        util.assert_same_db(ref, ora)
