@@ -193,6 +193,28 @@ typedef struct mb_union_stats {
 int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                  uint64_t workspaceBytes, mb_union_stats *st);
 
+/*  The whole merge family of merylOperation::nextMer (src/meryl/merylOp-nextMer.C:559-612; operation words of
+ *  merylCommandBuilder.C:364-377) through the same decode / merge / encode pipeline; mb_union_sum == MB_OP_UNION_SUM.
+ *  "Active" = the inputs that hold a k-mer:
+ *    union: value = number of active inputs;  union-min/-max/-sum: min / max / uint32 sum of their values;
+ *    intersect*: only k-mers of ALL inputs, value = the first input's / min / max / sum;
+ *    subtract: k-mers of the first input, its value minus the others' in turn, dropped as soon as it would not stay positive;
+ *    difference: k-mers of the first input that no other input holds;
+ *    symmetric-difference: k-mers of exactly one input (two inputs only here).                                       */
+#define MB_OP_UNION                 0
+#define MB_OP_UNION_MIN             1
+#define MB_OP_UNION_MAX             2
+#define MB_OP_UNION_SUM             3
+#define MB_OP_INTERSECT             4
+#define MB_OP_INTERSECT_MIN         5
+#define MB_OP_INTERSECT_MAX         6
+#define MB_OP_INTERSECT_SUM         7
+#define MB_OP_SUBTRACT              8
+#define MB_OP_DIFFERENCE            9
+#define MB_OP_SYMMETRIC_DIFFERENCE 10
+int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                     uint64_t workspaceBytes, mb_union_stats *st);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

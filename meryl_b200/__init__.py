@@ -299,3 +299,19 @@ def union_sum(inputs, output: str, device: int = -1, workspace_bytes: int = 0) -
     st = UnionStats()
     _check(L.mb_union_sum(arr, len(inputs), os.fsencode(os.fspath(output)), device, workspace_bytes, ctypes.byref(st)))
     return st
+
+
+SET_OPERATIONS = ("union", "union-min", "union-max", "union-sum", "intersect", "intersect-min", "intersect-max", "intersect-sum",
+                  "subtract", "difference", "symmetric-difference")
+
+
+def set_operation(op: str, inputs, output: str, device: int = -1, workspace_bytes: int = 0) -> UnionStats:
+    """`meryl <op> <inputs> output <output>` for the merge family of operators (include/meryl_b200.h: mb_set_operation)."""
+    inputs = [os.fsencode(os.fspath(p)) for p in inputs]
+    L = lib()
+    L.mb_set_operation.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int32,
+                                   ctypes.c_uint64, ctypes.POINTER(UnionStats)]
+    arr = (ctypes.c_char_p * len(inputs))(*inputs)
+    st = UnionStats()
+    _check(L.mb_set_operation(SET_OPERATIONS.index(op), arr, len(inputs), os.fsencode(os.fspath(output)), device, workspace_bytes, ctypes.byref(st)))
+    return st

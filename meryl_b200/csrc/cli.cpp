@@ -38,15 +38,25 @@ static bool isCountWord(const char *w, uint32_t *mode) {
   return false;
 }
 
-//  meryl-b200 [threads=T] [memory=GB] union-sum <db.meryl> <db.meryl> ... output <db.meryl>
+//  meryl-b200 [threads=T] [memory=GB] union|union-min|union-max|union-sum|intersect|intersect-min|intersect-max|intersect-sum|
+//             subtract|difference|symmetric-difference <db.meryl> <db.meryl> ... output <db.meryl>
 //  (merylCommandBuilder.C:333-435: the operation word; database inputs are directories holding a merylIndex)
+static const char *kSetOps[] = { "union", "union-min", "union-max", "union-sum", "intersect", "intersect-min", "intersect-max",
+                                 "intersect-sum", "subtract", "difference", "symmetric-difference" };
+static int setOpOf(const char *w) {
+  for (int i = 0; i < 11; i++) if (!strcmp(w, kSetOps[i])) return i;
+  return -1;
+}
+
 static int unionSumMain(int argc, char **argv) {
   std::vector<const char *> dbs;
+  int op = -1;
   const char *outDir = nullptr;
   bool quiet = false;
   for (int i = 1; i < argc; i++) {
     const char *w = argv[i];
-    if (!strcmp(w, "union-sum") || !strncmp(w, "threads=", 8) || !strncmp(w, "memory=", 7) || !strncmp(w, "k=", 2) || !strncmp(w, "-V", 2) || !strcmp(w, "-P") ||
+    if (setOpOf(w) >= 0 && op < 0) { op = setOpOf(w); continue; }
+    if (!strncmp(w, "threads=", 8) || !strncmp(w, "memory=", 7) || !strncmp(w, "k=", 2) || !strncmp(w, "-V", 2) || !strcmp(w, "-P") ||
         !strcmp(w, "[") || !strcmp(w, "]")) continue;
     if (!strcmp(w, "-Q")) { quiet = true; continue; }
     if (!strcmp(w, "output")) {
@@ -58,16 +68,16 @@ static int unionSumMain(int argc, char **argv) {
     if (access(idx.c_str(), R_OK) != 0) { fprintf(stderr, "ERROR: '%s' is not a meryl database (no readable merylIndex).\n", w); return 1; }
     dbs.push_back(w);
   }
-  if (dbs.empty()) { fprintf(stderr, "ERROR: union-sum needs at least one input database.\n"); return 1; }
-  if (!outDir)     { fprintf(stderr, "ERROR: No output specified for union-sum operation.\n"); return 1; }
+  if (dbs.empty()) { fprintf(stderr, "ERROR: %s needs at least one input database.\n", kSetOps[op]); return 1; }
+  if (!outDir)     { fprintf(stderr, "ERROR: No output specified for %s operation.\n", kSetOps[op]); return 1; }
   mb_union_stats st;
-  if (mb_union_sum(dbs.data(), (uint32_t)dbs.size(), outDir, -1, 0, &st) != MB_OK) {
+  if (mb_set_operation((uint32_t)op, dbs.data(), (uint32_t)dbs.size(), outDir, -1, 0, &st) != MB_OK) {
     fprintf(stderr, "ERROR: %s\n", mb_last_error());
     return 1;
   }
   if (!quiet) {
-    fprintf(stderr, "union-sum of %u databases (k=%u): %llu k-mers in, %llu distinct out (%llu unique), %u group%s, %.1f ms\n",
-            st.nInputs, st.k, (unsigned long long)st.nInputKmers, (unsigned long long)st.nOutputKmers, (unsigned long long)st.nUnique,
+    fprintf(stderr, "%s of %u databases (k=%u): %llu k-mers in, %llu distinct out (%llu unique), %u group%s, %.1f ms\n",
+            kSetOps[op], st.nInputs, st.k, (unsigned long long)st.nInputKmers, (unsigned long long)st.nOutputKmers, (unsigned long long)st.nUnique,
             st.nGroups, st.nGroups == 1 ? "" : "s", st.msTotal);
     fprintf(stderr, "  read+decode %.2f  merge %.2f  encode+write %.2f ms;  %llu bytes in, %llu bytes out\n",
             st.msDecode, st.msMerge, st.msEncode, (unsigned long long)st.inBytes, (unsigned long long)st.outBytes);
@@ -78,7 +88,7 @@ static int unionSumMain(int argc, char **argv) {
 
 int main(int argc, char **argv) {
   for (int i = 1; i < argc; i++)
-    if (!strcmp(argv[i], "union-sum")) return unionSumMain(argc, argv);
+    if (setOpOf(argv[i]) >= 0) return unionSumMain(argc, argv);
 
   uint32_t k = 0, mode = 0;
   uint64_t nExpected = 0, memBytes = physicalMemory();

@@ -12,7 +12,7 @@
 //    K7       decode_kernel      one thread per block: Elias-Fano fields -> full k-mers + values, at the block's
 //                                exclusive k-mer offset (a block is a strictly sequential bit stream: every unary
 //                                code must be decoded to find the next field; blocks are the parallelism)
-//    K8       merge_sum_kernel   merge-path union of two sorted k-mer lists with the counts of equal k-mers added
+//    K8       merge_op_kernel    merge-path union of two sorted k-mer lists with the counts of equal k-mers added
 //                                (uint32, wraps; zero sums are dropped), compacted by a chained scan; more than two
 //                                inputs fold left to right
 //    K5'/K6   value histogram and the stuffedBits encoder of the count path, in stream-writer mode
@@ -179,12 +179,53 @@ __device__ __forceinline__ u64 merge_path(const Key *a, u64 nA, const Key *b, u6
   return lo;
 }
 
+//  One fold step of a set operation: list A (the result so far; input 0 in the first step) against list B (the next
+//  input).  keep / value of a k-mer that is only in A, only in B, or in both (merylOp-nextMer.C:559-612, folded left to
+//  right: every operator of the family is a left fold of a binary rule):
+//    union                 count of inputs holding it: A's value (1 if A is raw input 0) + 1
+//    union-min/-max/-sum   min / max / uint32 sum of the values present
+//    intersect             in both: A's value (== input 0's)        intersect-min/-max/-sum   in both: min / max / sum
+//    subtract              only A: A's value;  both: A - B if that stays positive, else dropped for good;  only B: dropped
+//    difference            only A                                    symmetric-difference (two inputs)   only A or only B
+//  dropZero: values that are 0 are not written (only sums can wrap to 0; a wrapped intermediate sum of intersect-sum
+//  must survive to the next step, so the host sets dropZero in the last step only for that operator).
+struct MergeRule { u32 op, firstRaw, dropZero; };
+
+__device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u32 &v) {
+  switch (r.op) {
+    case MB_OP_UNION:        v = r.firstRaw ? 1u : va;  return true;
+    case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM:
+    case MB_OP_SUBTRACT:  case MB_OP_DIFFERENCE: case MB_OP_SYMMETRIC_DIFFERENCE:
+                             v = va;  return true;
+    default:                 return false;                 //  the intersections
+  }
+}
+__device__ __forceinline__ bool rule_only_b(const MergeRule &r, u32 vb, u32 &v) {
+  switch (r.op) {
+    case MB_OP_UNION:        v = 1u;  return true;
+    case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM: case MB_OP_SYMMETRIC_DIFFERENCE:
+                             v = vb;  return true;
+    default:                 return false;
+  }
+}
+__device__ __forceinline__ bool rule_both(const MergeRule &r, u32 va, u32 vb, u32 &v) {
+  switch (r.op) {
+    case MB_OP_UNION:          v = (r.firstRaw ? 1u : va) + 1u;  return true;
+    case MB_OP_UNION_MIN: case MB_OP_INTERSECT_MIN:   v = va < vb ? va : vb;  return true;
+    case MB_OP_UNION_MAX: case MB_OP_INTERSECT_MAX:   v = va < vb ? vb : va;  return true;
+    case MB_OP_UNION_SUM: case MB_OP_INTERSECT_SUM:   v = va + vb;            return true;
+    case MB_OP_INTERSECT:      v = va;  return true;
+    case MB_OP_SUBTRACT:       v = va - vb;  return va > vb;
+    default:                   return false;               //  difference, symmetric-difference
+  }
+}
+
 template <int KW>
 __global__ void __launch_bounds__(MG_THREADS)
-merge_sum_kernel(const typename KeyT<KW>::type *__restrict__ ka, const u32 *__restrict__ va, u64 nA,
-                 const typename KeyT<KW>::type *__restrict__ kb, const u32 *__restrict__ vb, u64 nB,
-                 typename KeyT<KW>::type *__restrict__ ko, u32 *__restrict__ vo, u64 *__restrict__ nOut,
-                 u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
+merge_op_kernel(const typename KeyT<KW>::type *__restrict__ ka, const u32 *__restrict__ va, u64 nA,
+                const typename KeyT<KW>::type *__restrict__ kb, const u32 *__restrict__ vb, u64 nB,
+                typename KeyT<KW>::type *__restrict__ ko, u32 *__restrict__ vo, u64 *__restrict__ nOut,
+                u64 *__restrict__ status, u64 *__restrict__ tileCounter, MergeRule rule) {
   typedef typename KeyT<KW>::type Key;
   __shared__ Key  sKey[MG_TILE + 2];
   __shared__ u32  sVal[MG_TILE + 2];
@@ -219,23 +260,25 @@ merge_sum_kernel(const typename KeyT<KW>::type *__restrict__ ka, const u32 *__re
   u32 keepMask = 0;
   for (u32 m = m0; m < m1; m++) {
     const bool takeA = (bi >= nb) || (ai < na && !key_less(sb[bi], sa[ai]));
-    Key k;  u32 v;  bool head;
+    Key k;  u32 v = 0;  bool keep;
     if (takeA) {
-      k = sa[ai];  v = sva[ai];  head = true;                //  k-mers are distinct within a database
-      if (bLo + bi < nB && key_eq(sb[bi], k)) v += svb[bi];   //  its partner in B (next unconsumed element; may be the guard)
+      k = sa[ai];                                            //  k-mers are distinct within a database
+      //  its partner in B, if any, is the next unconsumed element there (possibly the guard behind the window)
+      if (bLo + bi < nB && key_eq(sb[bi], k)) keep = rule_both(rule, sva[ai], svb[bi], v);
+      else                                    keep = rule_only_a(rule, sva[ai], v);
       ai++;
     } else {
-      k = sb[bi];  v = svb[bi];
-      //  a duplicate iff A holds the same k-mer: it would be the last element of A before this point
+      k = sb[bi];
+      //  already handled with its partner iff A holds the same k-mer: it would be the last element of A before this point
       bool dup = false;
       if (ai > 0)        dup = key_eq(sa[ai - 1], k);
       else if (aLo > 0)  dup = key_eq(ka[aLo - 1], k);
-      head = !dup;
+      keep = !dup && rule_only_b(rule, svb[bi], v);
       bi++;
     }
     const u32 j = m - m0;
     oKey[j] = k;  oVal[j] = v;
-    if (head && v != 0) keepMask |= 1u << j;                 //  merylOp-nextMer.C:640-641: a zero value is not output
+    if (keep && !(rule.dropZero && v == 0)) keepMask |= 1u << j;   //  merylOp-nextMer.C:640-641: a zero value is not output
   }
 
   //  compaction: exclusive position of my kept elements in the tile, then in the output (chained scan)
@@ -418,11 +461,19 @@ struct Carve {
 
 extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                             uint64_t workspaceBytes, mb_union_stats *stOut) {
+  return mb_set_operation(MB_OP_UNION_SUM, inDirs, nInputs, outDir, device, workspaceBytes, stOut);
+}
+
+extern "C" int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                                uint64_t workspaceBytes, mb_union_stats *stOut) {
   mb_clear_error();
-  if (!inDirs || nInputs == 0 || !outDir) return mb_fail(MB_EINVAL, "mb_union_sum: NULL argument");
+  if (!inDirs || nInputs == 0 || !outDir) return mb_fail(MB_EINVAL, "mb_set_operation: NULL argument");
+  if (op > MB_OP_SYMMETRIC_DIFFERENCE)     return mb_fail(MB_EINVAL, "mb_set_operation: unknown operation %u", op);
+  if (op == MB_OP_SYMMETRIC_DIFFERENCE && nInputs > 2)
+    return mb_fail(MB_EINVAL, "symmetric-difference of more than two databases is not implemented (it is not a left fold)");
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
-    return mb_fail(MB_ENODEVICE, "mb_union_sum: no CUDA device (this library has no CPU path)");
+    return mb_fail(MB_ENODEVICE, "mb_set_operation: no CUDA device (this library has no CPU path)");
 
   std::vector<InputDb> in(nInputs);
   for (u32 i = 0; i < nInputs; i++) {
@@ -432,7 +483,7 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
   }
   const u32 k = in[0].k, kw = k <= 32 ? 1 : 2, W = 8 * kw;
   const u32 wP = 12, wS = 2 * k - wP;                       //  kmers-writer.C:52-58: every non-count operation writes prefix 12
-  if (2 * k < wP + 1) return mb_fail(MB_EINVAL, "union-sum needs k >= 7 (the stream writer's 12-bit prefix)");
+  if (2 * k < wP + 1) return mb_fail(MB_EINVAL, "set operations need k >= 7 (the stream writer's 12-bit prefix)");
 
   mb_union_stats st;
   memset(&st, 0, sizeof(st));
@@ -607,12 +658,17 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
         const void *bk = (i < nInputs) ? lists[i].first : nullptr;
         const u32  *bv = (i < nInputs) ? lists[i].second : nullptr;
         const u64   bn = (i < nInputs) ? listN[i] : 0;
+        //  a lone input: union counts it (value 1), every other operator passes its values through
+        MergeRule rule;
+        rule.op       = (nInputs == 1 && op != MB_OP_UNION) ? (u32)MB_OP_UNION_SUM : op;
+        rule.firstRaw = (i == 1) ? 1 : 0;
+        rule.dropZero = (op != MB_OP_INTERSECT_SUM || i + 1 >= nInputs) ? 1 : 0;
         const u64 tiles = (curN + bn + MG_TILE - 1) / MG_TILE;
         MB_UCUDA(cudaMemsetAsync(dCtl + 8, 0, 8, s));
         if (tiles) {
           MB_UCUDA(cudaMemsetAsync(dStatus, 0, (tiles + 2) * 8, s));
-          if (kw == 1) merge_sum_kernel<1><<<(unsigned)tiles, MG_THREADS, 0, s>>>((const u64 *)curK, curV, curN, (const u64 *)bk, bv, bn, (u64 *)mk[pp], mv[pp], dCtl + 8, dStatus + 2, dStatus);
-          else         merge_sum_kernel<2><<<(unsigned)tiles, MG_THREADS, 0, s>>>((const ulonglong2 *)curK, curV, curN, (const ulonglong2 *)bk, bv, bn, (ulonglong2 *)mk[pp], mv[pp], dCtl + 8, dStatus + 2, dStatus);
+          if (kw == 1) merge_op_kernel<1><<<(unsigned)tiles, MG_THREADS, 0, s>>>((const u64 *)curK, curV, curN, (const u64 *)bk, bv, bn, (u64 *)mk[pp], mv[pp], dCtl + 8, dStatus + 2, dStatus, rule);
+          else         merge_op_kernel<2><<<(unsigned)tiles, MG_THREADS, 0, s>>>((const ulonglong2 *)curK, curV, curN, (const ulonglong2 *)bk, bv, bn, (ulonglong2 *)mk[pp], mv[pp], dCtl + 8, dStatus + 2, dStatus, rule);
           MB_UCUDA(cudaGetLastError());
           st.nLaunches++;
         }

@@ -43,3 +43,8 @@ def test_sim_union_low_complexity(tmp_path):
 
 def test_sim_union_groups(tmp_path, monkeypatch):
     uc.case_groups(str(tmp_path), monkeypatch)
+
+
+@pytest.mark.parametrize("op", mb.SET_OPERATIONS)
+def test_sim_set_operations(tmp_path, op):
+    uc.case_set_operations(str(tmp_path), op, n=6_000)

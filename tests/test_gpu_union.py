@@ -71,3 +71,8 @@ def test_union_properties_large():
         st = mb.union_sum([a, a], u)
         assert st.nInputKmers == 2 * sa.nDistinct and st.nOutputKmers == sa.nDistinct
         assert st.nTotal == 2 * sa.nTotal and st.nUnique == 0 and st.nDistinct == sa.nDistinct
+
+
+@pytest.mark.parametrize("op", mb.SET_OPERATIONS)
+def test_set_operations(tmp_path, op):
+    uc.case_set_operations(str(tmp_path), op, n=40_000)

@@ -91,7 +91,10 @@ def three_dbs(tmp_path_factory):
 def test_oracle_set_operations_vs_reference(tmp_path, three_dbs, op):
     """Every operator of the merge family (merylOp-nextMer.C:559-612): one, two and three inputs, counts that differ."""
     a, b, c = three_dbs
-    for tag, ins in (("2", [a, b]), ("3", [a, b, c]), ("1", [c]), ("rev", [c, a])):
+    cases = [("3", [a, b, c]), ("rev", [c, a])]            # (every reference run costs ~2.4 s of start-up)
+    if op in ("union", "subtract"):
+        cases.append(("1", [c]))
+    for tag, ins in cases:
         ref, ora = str(tmp_path / ("ref" + tag)), str(tmp_path / ("ora" + tag))
         util.run_ref(["threads=3", op, *ins, "output", ref])
         util.run_oracle([op, *ins, "output", ora])

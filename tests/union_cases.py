@@ -18,10 +18,10 @@ def oracle_db(tmp, name, data, k, op="count", wprefix=None):
     return db
 
 
-def check_union(tmp, inputs, tag="u", **kw):
+def check_union(tmp, inputs, tag="u", op="union-sum", **kw):
     ora, out = os.path.join(tmp, tag + "_ora.meryl"), os.path.join(tmp, tag + "_dev.meryl")
-    util.run_oracle(["union-sum", *inputs, "output", ora])
-    st = mb.union_sum(inputs, out, **kw)
+    util.run_oracle([op, *inputs, "output", ora])
+    st = mb.union_sum(inputs, out, **kw) if op == "union-sum" else mb.set_operation(op, inputs, out, **kw)
     util.assert_same_db(ora, out)
     return st, out
 
@@ -66,3 +66,21 @@ def case_groups(tmp, monkeypatch, k=31):
     monkeypatch.setenv("MB_UNION_MAX_FILES", "5")
     st, _ = check_union(tmp, [a, b])
     assert st.nGroups == 13
+
+
+def case_set_operations(tmp, op, k=21, n=15_000):
+    """The merge family (merylOp-nextMer.C:559-612) on one, two and three inputs that share k-mers with different counts,
+    a 128-bit k, and an empty input."""
+    common = synth.reads_fastq_bytes(n, n // 12, 150, 0.0, 1)
+    a = oracle_db(tmp, "a", common + synth.reads_fastq_bytes(n, n // 25, 150, 0.0, 2), k)
+    b = oracle_db(tmp, "b", common[: len(common) // 2] + synth.reads_fastq_bytes(n, n // 20, 150, 0.0, 3), k, op="count-forward")
+    c = oracle_db(tmp, "c", common + common + synth.reads_fastq_bytes(n, n // 50, 150, 0.0, 2), k)
+    e = oracle_db(tmp, "e", b">x\nACGT\n", k)
+    cases = [[a, b], [c, a], [a], [a, e], [e, a]]
+    if op != "symmetric-difference":
+        cases += [[a, b, c], [c, b, a, a]]
+    for i, ins in enumerate(cases):
+        check_union(tmp, ins, "s%d" % i, op=op)
+    a2 = oracle_db(tmp, "a2", synth.fasta_bytes(2, n // 2, 5), 40)
+    b2 = oracle_db(tmp, "b2", synth.fasta_bytes(1, n // 2, 5) + synth.fasta_bytes(1, n // 2, 6), 40)
+    check_union(tmp, [a2, b2], "w", op=op)
