@@ -215,6 +215,25 @@ int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir
 int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                      uint64_t workspaceBytes, mb_union_stats *st);
 
+/*  The one-input operators with a number (merylOp-nextMer.C:497-557; words of merylCommandBuilder.C:350-362):
+ *  filters keep a k-mer iff its value compares so with `param`; arithmetic changes the value (computed in 64 bits,
+ *  stored as uint32; increase / multiply become 2^32-1 only on 64-bit overflow; decrease below the constant, divide or
+ *  modulo by 0 give 0, i.e. the k-mer is not written).  Same pipeline: decode, one pass of the merge kernel, encode.  */
+#define MB_OP_LESS_THAN            11
+#define MB_OP_GREATER_THAN         12
+#define MB_OP_AT_LEAST             13
+#define MB_OP_AT_MOST              14
+#define MB_OP_EQUAL_TO             15
+#define MB_OP_NOT_EQUAL_TO         16
+#define MB_OP_INCREASE             17
+#define MB_OP_DECREASE             18
+#define MB_OP_MULTIPLY             19
+#define MB_OP_DIVIDE               20
+#define MB_OP_DIVIDE_ROUND         21
+#define MB_OP_MODULO               22
+int mb_value_operation(uint32_t op, uint64_t param, const char *inDir, const char *outDir, int32_t device,
+                       uint64_t workspaceBytes, mb_union_stats *st);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

@@ -315,3 +315,18 @@ def set_operation(op: str, inputs, output: str, device: int = -1, workspace_byte
     st = UnionStats()
     _check(L.mb_set_operation(SET_OPERATIONS.index(op), arr, len(inputs), os.fsencode(os.fspath(output)), device, workspace_bytes, ctypes.byref(st)))
     return st
+
+
+VALUE_OPERATIONS = ("less-than", "greater-than", "at-least", "at-most", "equal-to", "not-equal-to",
+                    "increase", "decrease", "multiply", "divide", "divide-round", "modulo")
+
+
+def value_operation(op: str, param: int, inp, output: str, device: int = -1, workspace_bytes: int = 0) -> UnionStats:
+    """`meryl <op> <param> <input> output <output>` for the one-input filters / arithmetic (mb_value_operation)."""
+    L = lib()
+    L.mb_value_operation.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32,
+                                     ctypes.c_uint64, ctypes.POINTER(UnionStats)]
+    st = UnionStats()
+    _check(L.mb_value_operation(11 + VALUE_OPERATIONS.index(op), param, os.fsencode(os.fspath(inp)), os.fsencode(os.fspath(output)),
+                                device, workspace_bytes, ctypes.byref(st)))
+    return st

@@ -42,15 +42,19 @@ static bool isCountWord(const char *w, uint32_t *mode) {
 //             subtract|difference|symmetric-difference <db.meryl> <db.meryl> ... output <db.meryl>
 //  (merylCommandBuilder.C:333-435: the operation word; database inputs are directories holding a merylIndex)
 static const char *kSetOps[] = { "union", "union-min", "union-max", "union-sum", "intersect", "intersect-min", "intersect-max",
-                                 "intersect-sum", "subtract", "difference", "symmetric-difference" };
+                                 "intersect-sum", "subtract", "difference", "symmetric-difference",
+                                 "less-than", "greater-than", "at-least", "at-most", "equal-to", "not-equal-to",
+                                 "increase", "decrease", "multiply", "divide", "divide-round", "modulo" };
 static int setOpOf(const char *w) {
-  for (int i = 0; i < 11; i++) if (!strcmp(w, kSetOps[i])) return i;
+  for (int i = 0; i < 23; i++) if (!strcmp(w, kSetOps[i])) return i;
   return -1;
 }
 
 static int unionSumMain(int argc, char **argv) {
   std::vector<const char *> dbs;
   int op = -1;
+  bool haveParam = false;
+  uint64_t param = 0;
   const char *outDir = nullptr;
   bool quiet = false;
   for (int i = 1; i < argc; i++) {
@@ -64,6 +68,10 @@ static int unionSumMain(int argc, char **argv) {
       outDir = argv[++i];
       continue;
     }
+    if (op >= MB_OP_LESS_THAN && !haveParam && w[0] >= '0' && w[0] <= '9' && w[strspn(w, "0123456789")] == 0) {   //  merylCommandBuilder.C:225-233
+      param = strtoull(w, 0, 10);  haveParam = true;
+      continue;
+    }
     const std::string idx = std::string(w) + "/merylIndex";
     if (access(idx.c_str(), R_OK) != 0) { fprintf(stderr, "ERROR: '%s' is not a meryl database (no readable merylIndex).\n", w); return 1; }
     dbs.push_back(w);
@@ -71,7 +79,14 @@ static int unionSumMain(int argc, char **argv) {
   if (dbs.empty()) { fprintf(stderr, "ERROR: %s needs at least one input database.\n", kSetOps[op]); return 1; }
   if (!outDir)     { fprintf(stderr, "ERROR: No output specified for %s operation.\n", kSetOps[op]); return 1; }
   mb_union_stats st;
-  if (mb_set_operation((uint32_t)op, dbs.data(), (uint32_t)dbs.size(), outDir, -1, 0, &st) != MB_OK) {
+  int rc;
+  if (op >= MB_OP_LESS_THAN) {
+    if (!haveParam)      { fprintf(stderr, "ERROR: %s needs a number (e.g. '%s 5').\n", kSetOps[op], kSetOps[op]); return 1; }
+    if (dbs.size() != 1) { fprintf(stderr, "ERROR: %s takes exactly one input database.\n", kSetOps[op]); return 1; }
+    rc = mb_value_operation((uint32_t)op, param, dbs[0], outDir, -1, 0, &st);
+  } else
+    rc = mb_set_operation((uint32_t)op, dbs.data(), (uint32_t)dbs.size(), outDir, -1, 0, &st);
+  if (rc != MB_OK) {
     fprintf(stderr, "ERROR: %s\n", mb_last_error());
     return 1;
   }

@@ -20,6 +20,7 @@
 //  merge, (W+4) read by the encoder.  Bound: HBM bandwidth (decode: latency of one dependent chain per thread).
 
 #include <errno.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -189,7 +190,28 @@ __device__ __forceinline__ u64 merge_path(const Key *a, u64 nA, const Key *b, u6
 //    difference            only A                                    symmetric-difference (two inputs)   only A or only B
 //  dropZero: values that are 0 are not written (only sums can wrap to 0; a wrapped intermediate sum of intersect-sum
 //  must survive to the next step, so the host sets dropZero in the last step only for that operator).
-struct MergeRule { u32 op, firstRaw, dropZero; };
+struct MergeRule { u32 op, firstRaw, dropZero; u64 param; };
+
+__device__ __forceinline__ double rint_half_away(double x) { return floor(x + 0.5); }      //  C round() for x >= 0
+
+//  The one-input operators (merylOp-nextMer.C:497-557): value -> value, 0 = not written.
+__device__ __forceinline__ u32 value_rule(u32 op, u64 param, u32 a) {
+  switch (op) {
+    case MB_OP_LESS_THAN:     return ((u64)a <  param) ? a : 0;
+    case MB_OP_GREATER_THAN:  return ((u64)a >  param) ? a : 0;
+    case MB_OP_AT_LEAST:      return ((u64)a >= param) ? a : 0;
+    case MB_OP_AT_MOST:       return ((u64)a <= param) ? a : 0;
+    case MB_OP_EQUAL_TO:      return ((u64)a == param) ? a : 0;
+    case MB_OP_NOT_EQUAL_TO:  return ((u64)a != param) ? a : 0;
+    case MB_OP_INCREASE:      return (~0ull - a < param) ? ~0u : (u32)(a + param);
+    case MB_OP_DECREASE:      return ((u64)a < param) ? 0 : (u32)(a - param);
+    case MB_OP_MULTIPLY:      return (a && ~0ull / a < param) ? ~0u : (u32)(a * param);
+    case MB_OP_DIVIDE:        return param ? (u32)(a / param) : 0;
+    case MB_OP_DIVIDE_ROUND:  return !param ? 0 : ((u64)a < param) ? 1u : (u32)(long long)rint_half_away((double)a / (double)param);
+    case MB_OP_MODULO:        return param ? (u32)(a % param) : 0;
+    default:                  return a;
+  }
+}
 
 __device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u32 &v) {
   switch (r.op) {
@@ -197,7 +219,9 @@ __device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u32 &v) 
     case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM:
     case MB_OP_SUBTRACT:  case MB_OP_DIFFERENCE: case MB_OP_SYMMETRIC_DIFFERENCE:
                              v = va;  return true;
-    default:                 return false;                 //  the intersections
+    case MB_OP_INTERSECT: case MB_OP_INTERSECT_MIN: case MB_OP_INTERSECT_MAX: case MB_OP_INTERSECT_SUM:
+                             return false;
+    default:                 v = value_rule(r.op, r.param, va);  return true;     //  one-input operators
   }
 }
 __device__ __forceinline__ bool rule_only_b(const MergeRule &r, u32 vb, u32 &v) {
@@ -464,11 +488,27 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
   return mb_set_operation(MB_OP_UNION_SUM, inDirs, nInputs, outDir, device, workspaceBytes, stOut);
 }
 
+static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                            uint64_t workspaceBytes, mb_union_stats *stOut);
+
 extern "C" int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                                 uint64_t workspaceBytes, mb_union_stats *stOut) {
   mb_clear_error();
+  if (op > MB_OP_SYMMETRIC_DIFFERENCE) return mb_fail(MB_EINVAL, "mb_set_operation: unknown operation %u", op);
+  return setOperationImpl(op, 0, inDirs, nInputs, outDir, device, workspaceBytes, stOut);
+}
+
+extern "C" int mb_value_operation(uint32_t op, uint64_t param, const char *inDir, const char *outDir, int32_t device,
+                                  uint64_t workspaceBytes, mb_union_stats *stOut) {
+  mb_clear_error();
+  if (op < MB_OP_LESS_THAN || op > MB_OP_MODULO) return mb_fail(MB_EINVAL, "mb_value_operation: unknown operation %u", op);
+  return setOperationImpl(op, param, &inDir, 1, outDir, device, workspaceBytes, stOut);
+}
+
+static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                            uint64_t workspaceBytes, mb_union_stats *stOut) {
+  mb_clear_error();
   if (!inDirs || nInputs == 0 || !outDir) return mb_fail(MB_EINVAL, "mb_set_operation: NULL argument");
-  if (op > MB_OP_SYMMETRIC_DIFFERENCE)     return mb_fail(MB_EINVAL, "mb_set_operation: unknown operation %u", op);
   if (op == MB_OP_SYMMETRIC_DIFFERENCE && nInputs > 2)
     return mb_fail(MB_EINVAL, "symmetric-difference of more than two databases is not implemented (it is not a left fold)");
   int nDev = 0;
@@ -660,7 +700,8 @@ extern "C" int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t
         const u64   bn = (i < nInputs) ? listN[i] : 0;
         //  a lone input: union counts it (value 1), every other operator passes its values through
         MergeRule rule;
-        rule.op       = (nInputs == 1 && op != MB_OP_UNION) ? (u32)MB_OP_UNION_SUM : op;
+        rule.op       = (nInputs == 1 && op != MB_OP_UNION && op <= MB_OP_SYMMETRIC_DIFFERENCE) ? (u32)MB_OP_UNION_SUM : op;
+        rule.param    = param;
         rule.firstRaw = (i == 1) ? 1 : 0;
         rule.dropZero = (op != MB_OP_INTERSECT_SUM || i + 1 >= nInputs) ? 1 : 0;
         const u64 tiles = (curN + bn + MG_TILE - 1) / MG_TILE;

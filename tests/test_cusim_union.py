@@ -48,3 +48,7 @@ def test_sim_union_groups(tmp_path, monkeypatch):
 @pytest.mark.parametrize("op", mb.SET_OPERATIONS)
 def test_sim_set_operations(tmp_path, op):
     uc.case_set_operations(str(tmp_path), op, n=6_000)
+
+
+def test_sim_value_operations(tmp_path):
+    uc.case_value_operations(str(tmp_path), n=5_000)

@@ -76,3 +76,7 @@ def test_union_properties_large():
 @pytest.mark.parametrize("op", mb.SET_OPERATIONS)
 def test_set_operations(tmp_path, op):
     uc.case_set_operations(str(tmp_path), op, n=40_000)
+
+
+def test_value_operations(tmp_path):
+    uc.case_value_operations(str(tmp_path), n=40_000)

@@ -99,3 +99,17 @@ def test_oracle_set_operations_vs_reference(tmp_path, three_dbs, op):
         util.run_ref(["threads=3", op, *ins, "output", ref])
         util.run_oracle([op, *ins, "output", ora])
         util.assert_same_db(ref, ora)
+
+
+@needs_ref
+def test_oracle_value_operations_vs_reference(tmp_path, three_dbs):
+    """The one-input filters / arithmetic with their overflow and zero corners (merylOp-nextMer.C:497-557)."""
+    import union_cases as uc
+    a, b, c = three_dbs
+    u = str(tmp_path / "u.meryl")
+    util.run_ref(["union-sum", a, b, c, "output", u])          # values 1..4
+    for i, (op, param) in enumerate(uc.VALUE_CASES):
+        ref, ora = str(tmp_path / ("ref%d" % i)), str(tmp_path / ("ora%d" % i))
+        util.run_ref(["threads=2", op, str(param), u, "output", ref])
+        util.run_oracle([op, str(param), u, "output", ora])
+        util.assert_same_db(ref, ora)

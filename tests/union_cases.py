@@ -84,3 +84,19 @@ def case_set_operations(tmp, op, k=21, n=15_000):
     a2 = oracle_db(tmp, "a2", synth.fasta_bytes(2, n // 2, 5), 40)
     b2 = oracle_db(tmp, "b2", synth.fasta_bytes(1, n // 2, 5) + synth.fasta_bytes(1, n // 2, 6), 40)
     check_union(tmp, [a2, b2], "w", op=op)
+
+
+VALUE_CASES = [("less-than", 3), ("greater-than", 1), ("at-least", 2), ("at-most", 1), ("equal-to", 2), ("not-equal-to", 2),
+               ("increase", 7), ("increase", 4294967295), ("decrease", 1), ("multiply", 3), ("multiply", 4294967296),
+               ("divide", 2), ("divide", 0), ("divide-round", 2), ("divide-round", 3), ("modulo", 2)]
+
+
+def case_value_operations(tmp, n=15_000):
+    """The one-input filters and arithmetic (merylOp-nextMer.C:497-557) on a db whose values range over 1..4."""
+    common = synth.reads_fastq_bytes(n, n // 12, 150, 0.0, 1)
+    a = oracle_db(tmp, "a", common + common + common[: len(common) // 2] + synth.reads_fastq_bytes(n, n // 25, 150, 0.0, 2), 21)
+    for i, (op, param) in enumerate(VALUE_CASES):
+        ora, out = os.path.join(tmp, "v%d_ora.meryl" % i), os.path.join(tmp, "v%d_dev.meryl" % i)
+        util.run_oracle([op, str(param), a, "output", ora])
+        mb.value_operation(op, param, a, out)
+        util.assert_same_db(ora, out)
