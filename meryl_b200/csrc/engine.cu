@@ -461,6 +461,7 @@ static int runCount(mb_ctx *c) {
   xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;  xp.suffix32 = 0;
   xp.noPrefilter = getenv("MB_NO_PREFILTER") ? 1 : 0;
   xp.keptPerMille = 0;
+  xp.rankMatch = getenv("MB_RANK_MATCH") ? 1 : 0;
   xp.prof = g_extractProf;
 
   tStage.start(s);

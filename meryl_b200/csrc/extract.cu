@@ -201,6 +201,8 @@ struct ExtractSmem {
   //  latency-bound rolling loop of phase A needs.
   __host__ __device__ static size_t tablesBytes(u32 nT)            { return ((size_t)nT * 16 + 15) / 16 * 16; }
   __host__ __device__ static size_t scatterBytes(u32 nT, u32 cap)  { return OFF_TABLES + tablesBytes(nT) + (size_t)TILE_POS * 2 + (size_t)cap * sizeof(Key) + (S32 ? (size_t)cap * 2 : 0) + 16; }
+  //  MATCH variant: + one u32 counter per (warp, bin of the pass)
+  __host__ __device__ static size_t matchBytes(u32 nT)             { return (size_t)(THREADS / 32) * nT * 4 + 16; }
   __host__ __device__ static size_t countBytes(u32 nT)             { return OFF_TABLES + (size_t)nT * 4; }
 };
 
@@ -288,7 +290,13 @@ __device__ __forceinline__ void to_stored(u64 k, u32 &o)                        
 __device__ __forceinline__ void to_stored(u64 k, u64 &o)                         { o = k; }
 __device__ __forceinline__ void to_stored(const ulonglong2 &k, ulonglong2 &o)    { o = k; }
 
-template <int KW, bool COUNT_ONLY, bool S32>
+//  MATCH (experimental, MB_RANK_MATCH=1; not the default until it is measured): in a filtered pass the rank of a kept k-mer
+//  inside (tile, bin) comes from warp-private counters instead of a returning shared-memory atomic (~2 cycles per lane
+//  per SM, a third of the extraction time): the lanes of a warp take their candidates in lock-step rounds,
+//  __match_any_sync groups the lanes of a round by bin, the first lane of a group bumps the warp's counter of that bin
+//  by the group size (plain load/store: the counter is private to the warp) and every lane's rank is the old value plus
+//  its place in the group; a per-bin scan over the warps' counters then turns (warp, rank) into a tile-wide position.
+template <int KW, bool COUNT_ONLY, bool S32, bool MATCH>
 __global__ void __launch_bounds__(ExtractShape<KW>::THREADS, 4)
 extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict__ out,
                const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles, u32 stageCap) {
@@ -307,6 +315,8 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   unsigned short *rank   = (unsigned short *)(smem + S::OFF_TABLES + S::tablesBytes(nT));
   Stored         *stage  = (Stored *)(((uintptr_t)(rank + S::TILE_POS) + 15) & ~(uintptr_t)15);
   unsigned short *sbin   = (unsigned short *)(stage + stageCap);
+  const int       WARPS  = ExtractShape<KW>::THREADS / 32;
+  u32            *wcnt   = (u32 *)(((uintptr_t)(sbin + (S32 ? stageCap : 0)) + 15) & ~(uintptr_t)15);   //  MATCH: [warp][bin]
   __shared__ u32 sWarpSum[ExtractShape<KW>::THREADS / 32];
 
   const u32 t = threadIdx.x;
@@ -326,6 +336,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
 
   if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   for (u32 b = t; b < nT; b += blockDim.x) cnt[b] = 0;
+  if (MATCH && !COUNT_ONLY) for (u32 b = t; b < (u32)WARPS * nT; b += blockDim.x) wcnt[b] = 0;
   __syncthreads();
 
   const unsigned char *storeBytes = (const unsigned char *)p.store;
@@ -396,7 +407,40 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
       //  Phase A for a file-aligned pass that keeps a minority of the bins: bit-sliced membership test of all
       //  32 positions, then only the members get their exact bin (5 bases of each strand) and a rank.
       u64 cand = valid ? file_range_slots(w, p.k, p.mode, fLo, fHi) : 0;
-      if (cand) {
+      if (MATCH) {
+        const u64 ya = win_slots(w, p.k - 5), yb = win_slots(w, p.k - 5 + 32);
+        const u32 f0 = (u32)(w.w0 >> 32), f1 = (u32)w.w0, f2 = (u32)(w.w1 >> 32);
+        const u32 r0 = (u32)(ya >> 32),   r1 = (u32)ya,   r2 = (u32)(yb >> 32);
+        const u32 lane = t & 31;
+        u32 *myw = wcnt + (t >> 5) * nT;
+        for (;;) {                                     //  one round: every lane brings its next member, if it has one
+          bool have = false;
+          u32 q = 0, bin = 0;
+          while (cand && !have) {
+            const u32 b = __clzll((long long)cand);
+            cand &= ~(0x8000000000000000ull >> b);
+            q = b >> 1;
+            if ((valid << q) & 0x80000000u) {
+              const u32 f5 = five_bases_at(f0, f1, f2, q);
+              const u32 r5 = revcomp5(five_bases_at(r0, r1, r2, q));
+              const u32 top10 = (p.mode == MB_MODE_FORWARD) ? f5 : (p.mode == MB_MODE_REVERSE) ? r5 : min(f5, r5);
+              bin = (top10 >> (10 - p.binBits)) - p.binLo;
+              have = true;
+            }
+          }
+          const u32 act = __ballot_sync(0xffffffffu, have);
+          if (act == 0) break;
+          if (have) {
+            const u32 peers  = __match_any_sync(act, bin);          //  lanes of this round with my bin
+            const u32 leader = (u32)__ffs((int)peers) - 1;
+            u32 base = 0;
+            if (lane == leader) { base = myw[bin]; myw[bin] = base + (u32)__popc(peers); }
+            base = __shfl_sync(act, base, (int)leader);
+            keep |= 0x80000000u >> q;
+            rank[t * 32 + q] = (unsigned short)(base + (u32)__popc(peers & ((1u << lane) - 1)));
+          }
+        }
+      } else if (cand) {
         const u64 ya = win_slots(w, p.k - 5), yb = win_slots(w, p.k - 5 + 32);
         const u32 f0 = (u32)(w.w0 >> 32), f1 = (u32)w.w0, f2 = (u32)(w.w1 >> 32);
         const u32 r0 = (u32)(ya >> 32),   r1 = (u32)ya,   r2 = (u32)(yb >> 32);
@@ -441,6 +485,17 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
       const u32 nPassBins = p.binHi - p.binLo;
       const u32 perThread = (nPassBins + blockDim.x - 1) / blockDim.x;
       const u32 b0 = p.binLo + t * perThread;
+      if (MATCH && prefilter) {
+        //  the tile's count of a bin = sum of the warps' counters; leave in them each warp's exclusive share
+        for (u32 i = 0; i < perThread; i++) {
+          const u32 b = b0 + i;
+          if (b < p.binHi) {
+            u32 run = 0;
+            for (int wi = 0; wi < WARPS; wi++) { const u32 c = wcnt[wi * nT + (b - p.binLo)]; wcnt[wi * nT + (b - p.binLo)] = run; run += c; }
+            cnt[b - p.binLo] = run;
+          }
+        }
+      }
       u32 mySum = 0;
       for (u32 i = 0; i < perThread; i++) { const u32 b = b0 + i; if (b < p.binHi) mySum += cnt[b - p.binLo]; }
       u32 incl = mySum;
@@ -491,13 +546,18 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
             v &= ~(0x80000000u >> q);
             const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
             const u32 bin = key_field(key, binShift, p.binBits) - p.binLo;
-            const u32 pos = binOff[bin] + rank[t * 32 + q];
+            const u32 pos = binOff[bin] + rank[t * 32 + q] + ((MATCH && prefilter) ? wcnt[(t >> 5) * nT + bin] : 0);
             Stored sk;  to_stored(key, sk);
             if (pos < stageCap) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
           }
         }
       }
       __syncthreads();
+      if (MATCH && prefilter)                             //  warp counters back to zero for the next tile (the bins I own)
+        for (u32 i = 0; i < perThread; i++) {
+          const u32 b = b0 + i;
+          if (b < p.binHi) for (int wi = 0; wi < WARPS; wi++) wcnt[wi * nT + (b - p.binLo)] = 0;
+        }
 
       //  Copy-out: consecutive threads, consecutive staged keys -> every bin's run is written coalesced.
       const u32 nStaged = total < stageCap ? total : stageCap;
@@ -524,7 +584,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   }
 }
 
-template <int KW, bool COUNT_ONLY, bool S32>
+template <int KW, bool COUNT_ONLY, bool S32, bool MATCH = false>
 cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, u64 *binCount, cudaStream_t s) {
   typedef ExtractSmem<KW, S32> S;
   const u32 nBins = 1u << p.binBits, nT = p.binHi - p.binLo;
@@ -538,8 +598,8 @@ cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64
     if (want < stageCap) stageCap = (u32)want;
   }
   if (sizeof(typename S::Key) * stageCap > 32768) stageCap = 32768 / sizeof(typename S::Key);
-  const size_t smem = COUNT_ONLY ? S::countBytes(nT) : S::scatterBytes(nT, stageCap);
-  auto kern = extract_kernel<KW, COUNT_ONLY, S32>;
+  const size_t smem = COUNT_ONLY ? S::countBytes(nT) : S::scatterBytes(nT, stageCap) + (MATCH ? S::matchBytes(nT) : 0);
+  auto kern = extract_kernel<KW, COUNT_ONLY, S32, MATCH>;
 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -570,6 +630,14 @@ cudaError_t mb_launch_bin_histogram(const MbExtractParams &p, u64 *dBinCount, cu
 }
 
 cudaError_t mb_launch_extract(const MbExtractParams &p, void *dKeys, const u64 *dBinStart, u64 *dBinCursor, cudaStream_t s) {
+  if (p.rankMatch) {                                     //  experimental ranking without returning atomics
+    if (p.suffix32) {
+      if (p.k > 32 || 2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;
+      return launch<1, false, true, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
+    }
+    return (p.k <= 32) ? launch<1, false, false, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s)
+                       : launch<2, false, false, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
+  }
   if (p.suffix32) {
     if (p.k > 32 || 2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;
     return launch<1, false, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s);

@@ -53,7 +53,8 @@ void fiber_main() {
   g_progress++;
   //  an exited thread no longer takes part in barriers: release whoever is waiting for it
   if (g_alive && g_barArrived == g_alive) { g_barArrived = 0; g_barGen++; }
-  if (f->warp->alive && f->warp->arrived && f->warp->arrived == (unsigned)__builtin_popcount(f->warp->alive)) { f->warp->arrived = 0; f->warp->gen++; }
+  for (WarpBarrier &b : f->warp->bar)
+    if (b.arrived && b.arrived >= (unsigned)__builtin_popcount(f->warp->alive & b.mask)) { b.arrived = 0; b.mask = 0; b.gen++; }
   cusim_switch(&f->sp, g_schedSp);
   abort();                                              //  a finished fiber is never resumed
 }
@@ -103,9 +104,13 @@ void block_barrier(void) {
 void warp_barrier(unsigned mask) {
   Warp *w = g_cur->warp;
   const unsigned expect = (unsigned)__builtin_popcount(w->alive & mask);
-  const unsigned gen = w->gen;
-  if (++w->arrived >= expect) { w->arrived = 0; w->gen++; g_progress++; return; }
-  while (w->gen == gen) yield();
+  WarpBarrier *b = nullptr;
+  for (WarpBarrier &x : w->bar) if (x.arrived && x.mask == mask) { b = &x; break; }      //  join the rendezvous of my lane set
+  if (!b) for (WarpBarrier &x : w->bar) if (!x.arrived) { b = &x; b->mask = mask; break; }
+  if (!b) { fprintf(stderr, "cusim: more than 8 warp collectives in flight in one warp\n"); abort(); }
+  const unsigned gen = b->gen;
+  if (++b->arrived >= expect) { b->arrived = 0; b->mask = 0; b->gen++; g_progress++; return; }
+  while (b->gen == gen) yield();
 }
 
 void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &body) {
@@ -132,7 +137,7 @@ void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &
   for (unsigned bx = 0; bx < grid.x; bx++) {
     g_blockIdx.x = bx;  g_blockIdx.y = by;  g_blockIdx.z = bz;
     if (g_dynSmem) memset(g_dynSmem, 0xcd, g_dynCap);   //  shared memory starts as garbage
-    for (unsigned w = 0; w < nWarps; w++) { g_warps[w].alive = 0; g_warps[w].arrived = 0; g_warps[w].gen = 0; }
+    for (unsigned w = 0; w < nWarps; w++) { g_warps[w].alive = 0; memset(g_warps[w].bar, 0, sizeof(g_warps[w].bar)); }
     for (unsigned t = 0; t < nThreads; t++) {
       Fiber &f = g_fibers[t];
       f.linear = t;

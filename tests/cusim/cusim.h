@@ -88,12 +88,12 @@ template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMult
 //  ---- the emulator --------------------------------------------------------------------------------
 namespace cusim {
 
+struct WarpBarrier { unsigned mask, arrived, gen; };   //  one rendezvous in flight (keyed by its lane mask)
 struct Warp {
   unsigned char slot[32][16];
   unsigned      pred;                 //  ballot bits
   unsigned      alive;                //  lanes that exist and have not exited
-  unsigned      arrived;
-  unsigned      gen;
+  WarpBarrier   bar[8];               //  disjoint lane sets of a diverged warp may be in different collectives at once
 };
 
 struct Fiber {

@@ -130,3 +130,12 @@ def test_sim_compress(tmp_path):
         c.count()
         c.write_db(out)
     util.assert_same_db(ora, out)
+
+
+@pytest.mark.parametrize("k,w_prefix,op", [(21, 12, "count"), (31, 9, "count-forward"), (51, 8, "count")])
+def test_sim_experimental_match_rank(tmp_path, monkeypatch, k, w_prefix, op):
+    """MB_RANK_MATCH=1 (not the default; to be measured on the GPU in round 2): ranks inside (tile, bin) from warp-private
+    counters and __match_any_sync instead of returning shared-memory atomics."""
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
+    monkeypatch.setenv("MB_RANK_MATCH", "1")
+    _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 7 + k)}, k, w_prefix, op=op, min_passes=3)

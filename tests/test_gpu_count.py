@@ -232,6 +232,21 @@ def test_compress_cli(tmp_path):
         util.assert_same_db(ref, out)
 
 
+@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental kernels: set MB_TEST_EXPERIMENTAL=1 (not yet run on a GPU)")
+@pytest.mark.parametrize("k", [21, 31, 51])
+def test_experimental_match_rank(tmp_path, k):
+    """MB_RANK_MATCH=1: warp-private counters + __match_any_sync instead of returning shared-memory atomics in the extraction."""
+    data = synth.reads_fastq_bytes(200_000, 60_000, 150, 0.003, 300 + k)
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "gpu.meryl")
+    util.run_oracle(["k=%d" % k, "memory=2", "count", str(fq), "output", ora])
+    env = dict(os.environ, MB_MAX_PASS_KEYS="1500000", MB_RANK_MATCH="1")
+    p = subprocess.run([mb.CLI_PATH, "k=%d" % k, "memory=2", "count", str(fq), "output", out], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    util.assert_same_db(ora, out)
+
+
 def test_device_generator_and_device_ingest_match_oracle(tmp_path):
     """bench.py's input path: reads generated on the device (csrc/synth.cu) and ingested from device
     memory must give the same db as the oracle run on the same reads written as a FASTQ file."""

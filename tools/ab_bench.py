@@ -33,8 +33,11 @@ extra = [{}]
 if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel striped/blocked x histogram single/joint (default sweep)
     configs = [(L.mb_dbg_sort_version(0), 0)]
     extra = [{}, {"MB_COUNT_BLOCKED": "1"}, {"MB_HIST_JOINT": "1"}, {"MB_COUNT_BLOCKED": "1", "MB_HIST_JOINT": "1"}]
+if len(sys.argv) > 3 and sys.argv[3] == "experiments":       # things written without a GPU at hand, to be measured
+    configs = [(L.mb_dbg_sort_version(0), 0)]
+    extra = [{}, {"MB_RANK_MATCH": "1"}]
 for (sort_v, nofilter), env in [(c, e) for c in configs for e in extra]:
-    for k in ("MB_COUNT_BLOCKED", "MB_HIST_JOINT"):
+    for k in ("MB_COUNT_BLOCKED", "MB_HIST_JOINT", "MB_RANK_MATCH"):
         os.environ.pop(k, None)
     os.environ.update(env)
     L.mb_dbg_sort_version(sort_v)
