@@ -501,6 +501,21 @@ static int runCount(mb_ctx *c) {
   u32 *dHistBig = (u32 *)top.take(histBigCap * sizeof(u32));
   if (!dHistBig) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
 
+  //  Experimental (MB_OVERLAP_D2H=1, not the default until it is measured): the device-to-host copy of a group's encoded
+  //  blocks runs on a second stream while the next group is counted and encoded.  Groups alternate between two halves
+  //  of the encode region; a half is reused only after its copy has finished.  Needs a caller-owned output buffer
+  //  (mb_set_output_buffer): the destination must not move while a copy is in flight.
+  const bool overlapD2H = getenv("MB_OVERLAP_D2H") != nullptr && c->outBuf != nullptr && !(cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED));
+  cudaStream_t sCopy = nullptr;
+  cudaEvent_t  evEnc = nullptr, evCopied[2] = { nullptr, nullptr };
+  bool         copyPending[2] = { false, false };
+  u64          groupSeq = 0;
+  if (overlapD2H) {
+    MB_CUDA(cudaStreamCreateWithFlags(&sCopy, cudaStreamNonBlocking));
+    MB_CUDA(cudaEventCreateWithFlags(&evEnc, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) MB_CUDA(cudaEventCreateWithFlags(&evCopied[i], cudaEventDisableTiming));
+  }
+
   //  ---- plan the passes --------------------------------------------------------------------
   const size_t R = top.left();
   const u64 nBlocksTotal = (u64)1 << wP;
@@ -566,6 +581,7 @@ static int runCount(mb_ctx *c) {
       const u32 tile32 = mb_sort_tile_keys(4);
       const double perKey32 = 2.0 * 4 + (double)radix * 8 / tile32 + 16.0 / tile32;
       size_t enc32 = std::max<size_t>((size_t)4 << 30, (size_t)nBlocksTotal * 200);
+      if (overlapD2H) enc32 *= 2;                          //  two alternating halves
       if (enc32 > R / 3) enc32 = R / 3;
       if (R > enc32 + fixed + ((size_t)64 << 20)) {
         u64 cap32 = (u64)((double)(R - enc32 - fixed) / perKey32);
@@ -575,7 +591,7 @@ static int runCount(mb_ctx *c) {
         if (planBins(cap32, p32) == 0) {
           bool ok = true;
           for (const Pass &P : p32) {
-            const u64 gcap = std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / 3 / 8));
+            const u64 gcap = std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / (overlapD2H ? 2 : 1) / 3 / 8));
             for (u64 cnt : P.segCount) if (cnt > gcap || cnt >= ((u64)1 << 32)) ok = false;
           }
           if (ok) { passes.swap(p32); suffix32 = true; }
@@ -637,6 +653,7 @@ static int runCount(mb_ctx *c) {
   //  host images
   for (u32 f = 0; f < 64; f++) { c->db.dataVec[f].clear(); c->db.dataPtr[f] = nullptr; c->db.dataLen[f] = 0; c->db.index[f].clear(); }
   c->outUsed = 0;
+  if (overlapD2H) for (u32 f = 0; f < 64; f++) c->db.index[f].reserve((size_t)blocksPerFile * 24);   //  no reallocation under a copy in flight
   std::vector<u64> fileBase(64, 0);
 
   std::vector<u64> segStart, segTile, binStart(MB_MAX_BINS + 1);
@@ -753,7 +770,7 @@ static int runCount(mb_ctx *c) {
       g.encRanges = P.encRanges;
       groups.push_back(g);
     } else {
-      const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / 3 / 8));
+      const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / (overlapD2H ? 2 : 1) / 3 / 8));
       Group g;  g.segLo = 0;  g.keyLo = 0;  g.tileLo = 0;
       u64 have = 0;
       for (u32 i = 0; i <= nSegs; i++) {
@@ -771,7 +788,10 @@ static int runCount(mb_ctx *c) {
     for (size_t gi = 0; gi < groups.size(); gi++) {
       const Group &G = groups[gi];
       const u64 gKeys = G.keyHi - G.keyLo;
-      Carver gc((uint8_t *)ec.base + alignUp(ec.off), ec.left());      //  per-group slice of the encode region
+      const int    half    = overlapD2H ? (int)(groupSeq++ & 1) : 0;
+      const size_t halfLen = overlapD2H ? ec.left() / 2 / kAlign * kAlign : ec.left();
+      Carver gc((uint8_t *)ec.base + alignUp(ec.off) + (size_t)half * halfLen, halfLen);      //  per-group slice of the encode region
+      if (overlapD2H && copyPending[half]) { MB_CUDA(cudaEventSynchronize(evCopied[half])); copyPending[half] = false; }
 
       void *distinctKeys;  u64 *runStart;  u32 encKeyWords;
       tStage.start(s);
@@ -907,12 +927,15 @@ static int runCount(mb_ctx *c) {
               c->db.dataLen[file] += fb;
               const size_t i0 = iv.size();
               iv.resize(i0 + ib);
-              MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
-              MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
+              if (overlapD2H && f == fi) { MB_CUDA(cudaEventRecord(evEnc, s)); MB_CUDA(cudaStreamWaitEvent(sCopy, evEnc, 0)); }
+              cudaStream_t cs = overlapD2H ? sCopy : s;
+              MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, cs));
+              MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, cs));
               c->st.d2hBytes += fb + ib;
             }
+            if (overlapD2H) { MB_CUDA(cudaEventRecord(evCopied[half], sCopy)); copyPending[half] = true; }
           }
-          MB_CUDA(cudaStreamSynchronize(s));
+          if (!overlapD2H) MB_CUDA(cudaStreamSynchronize(s));
           for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
           fi = fj;
         }
@@ -921,8 +944,17 @@ static int runCount(mb_ctx *c) {
       MB_CUDA(cudaStreamSynchronize(s));
       c->st.msEncode += tStage.ms();
     }
+    if (overlapD2H) {                                    //  the next pass carves the arena differently: no copy may still read it
+      MB_CUDA(cudaStreamSynchronize(sCopy));
+      copyPending[0] = copyPending[1] = false;
+    }
   }
 
+  if (overlapD2H) {
+    MB_CUDA(cudaStreamSynchronize(sCopy));
+    cudaEventDestroy(evEnc);  cudaEventDestroy(evCopied[0]);  cudaEventDestroy(evCopied[1]);
+    cudaStreamDestroy(sCopy);
+  }
   cudaEventDestroy(evAfterHist);
   tSortHist.destroy();
 

@@ -139,3 +139,26 @@ def test_sim_experimental_match_rank(tmp_path, monkeypatch, k, w_prefix, op):
     monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
     monkeypatch.setenv("MB_RANK_MATCH", "1")
     _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 7 + k)}, k, w_prefix, op=op, min_passes=3)
+
+
+@pytest.mark.parametrize("k,w_prefix", [(21, 12), (31, 9)])
+def test_sim_experimental_overlap_d2h(tmp_path, monkeypatch, k, w_prefix):
+    """MB_OVERLAP_D2H=1 (not the default; to be measured in round 2): the copy-back of a group's encoded blocks on a second
+    stream, groups alternating between two halves of the encode region.  The emulator is synchronous, so this checks the
+    carving and bookkeeping (same bytes in the caller's buffer), not the asynchrony."""
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
+    data = synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 70 + k)
+    ora = str(tmp_path / "ora.meryl")
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(data)
+    util.run_oracle(["k=%d" % k, "wprefix=%d" % w_prefix, "count", str(fq), "output", ora])
+    monkeypatch.setenv("MB_OVERLAP_D2H", "1")
+    buf = np.zeros(64 << 20, dtype=np.uint8)
+    out = str(tmp_path / "sim.meryl")
+    with mb.Counter(k, w_prefix) as c:
+        c.set_output_buffer(buf.ctypes.data, buf.size)
+        c.add_file(str(fq))
+        c.count()
+        assert c.stats().nPasses >= 3
+        c.write_db(out)
+    util.assert_same_db(ora, out)

@@ -247,6 +247,27 @@ def test_experimental_match_rank(tmp_path, k):
     util.assert_same_db(ora, out)
 
 
+@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental host path: set MB_TEST_EXPERIMENTAL=1 (not yet run on a GPU)")
+def test_experimental_overlap_d2h(tmp_path, monkeypatch):
+    """MB_OVERLAP_D2H=1: copy-back of the encoded blocks on a second stream while the next group is counted."""
+    import torch
+    data = synth.reads_fastq_bytes(300_000, 200_000, 150, 0.002, 41)
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "gpu.meryl")
+    util.run_oracle(["k=21", "wprefix=12", "count", str(fq), "output", ora])
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", "4000000")
+    monkeypatch.setenv("MB_OVERLAP_D2H", "1")
+    buf = torch.zeros(512 << 20, dtype=torch.uint8, pin_memory=True)
+    for _ in range(3):                                   # a race would not show every time
+        with mb.Counter(21, 12) as c:
+            c.set_output_buffer(buf.data_ptr(), buf.numel())
+            c.add_file(str(fq))
+            c.count()
+            c.write_db(out)
+        util.assert_same_db(ora, out)
+
+
 def test_device_generator_and_device_ingest_match_oracle(tmp_path):
     """bench.py's input path: reads generated on the device (csrc/synth.cu) and ingested from device
     memory must give the same db as the oracle run on the same reads written as a FASTQ file."""

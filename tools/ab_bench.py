@@ -35,7 +35,7 @@ if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel stri
     extra = [{}, {"MB_COUNT_BLOCKED": "1"}, {"MB_HIST_JOINT": "1"}, {"MB_COUNT_BLOCKED": "1", "MB_HIST_JOINT": "1"}]
 if len(sys.argv) > 3 and sys.argv[3] == "experiments":       # things written without a GPU at hand, to be measured
     configs = [(L.mb_dbg_sort_version(0), 0)]
-    extra = [{}, {"MB_RANK_MATCH": "1"}]
+    extra = [{}, {"MB_RANK_MATCH": "1"}]                     # (MB_OVERLAP_D2H needs host images: measure it with bench.py's e2e leg)
 for (sort_v, nofilter), env in [(c, e) for c in configs for e in extra]:
     for k in ("MB_COUNT_BLOCKED", "MB_HIST_JOINT", "MB_RANK_MATCH"):
         os.environ.pop(k, None)
