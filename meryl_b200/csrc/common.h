@@ -53,15 +53,25 @@ public:
   //  Format check on the first bytes of a file (needs >= 1001 bytes or the whole file).
   static bool sniff(const uint8_t *d, size_t n);
 
+  //  The machine's state, for parsing a file in pieces on several threads (engine.cu: parseParallel).
+  enum State { A, P1, P1CR, P2, P2CR, Q, H, HCR, L, W, G };
+  State state(void) const   { return _st; }
+  void  setState(State s)   { _st = s; }
+  int   breakRecord(void)   { return brk(); }
+  std::vector<std::string> &pool(void) { return _pool; }     //  output buffers of the pieces, reused from block to block
+
 private:
   int  emit(const uint8_t *p, size_t n) { return n ? _sink(_arg, (const char *)p, n) : 0; }
   int  brk(void)                        { static const char dot = '.'; return _sink(_arg, &dot, 1); }
 
-  enum State { A, P1, P1CR, P2, P2CR, Q, H, HCR, L, W, G };
   State  _st = A;
+  std::vector<std::string> _pool;
   Sink   _sink;
   void  *_arg;
 };
+
+//  One block of a file parsed on several host threads, exactly as one sequential pass would (engine.cu).
+int mb_parse_parallel(SeqParser::Sink out, void *outArg, SeqParser &ps, const uint8_t *d, size_t n);
 
 //  ---- db assembly on the host (dbwriter.cpp) ------------------------------------------------
 struct MbHistogram {                      //  value -> occurrences, plus the master-index totals

@@ -246,3 +246,21 @@ extern "C" int mb_dbg_lookback(const uint64_t *status, uint64_t n, uint64_t tile
   cudaFree(dSt);  cudaFree(dOut);
   return MB_OK;
 }
+
+//  P1/P2 through the multi-threaded block parser (mb_parse_parallel): the file image in blocks of `block` bytes.
+extern "C" int mb_dbg_parse_parallel(const uint8_t *data, uint64_t len, uint64_t block, char *out, uint64_t cap, uint64_t *outLen) {
+  mb_clear_error();
+  if (!outLen || block == 0) return mb_fail(MB_EINVAL, "mb_dbg_parse_parallel: bad argument");
+  if (!SeqParser::sniff(data, len < 65536 ? len : 65536)) return mb_fail(MB_EFORMAT, "input is not FASTA or FASTQ");
+  std::string acc;
+  auto sink = [](void *a, const char *b, size_t n) -> int { ((std::string *)a)->append(b, n); return 0; };
+  SeqParser ps(sink, &acc);
+  for (uint64_t at = 0; at < len; at += block) MB_TRY(mb_parse_parallel(sink, &acc, ps, data + at, (size_t)(len - at < block ? len - at : block)));
+  MB_TRY(ps.finish());
+  *outLen = acc.size();
+  if (out) {
+    if (acc.size() > cap) return mb_fail(MB_EINVAL, "mb_dbg_parse_parallel: output needs %zu bytes", acc.size());
+    memcpy(out, acc.data(), acc.size());
+  }
+  return MB_OK;
+}

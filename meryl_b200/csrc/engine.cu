@@ -19,10 +19,14 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <string>
+#include <thread>
 #include <stdio.h>
 #include <string.h>
 #include <unistd.h>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 
 #include "common.h"
 #include "kernels.cuh"
@@ -228,7 +232,7 @@ static int appendHost(mb_ctx *c, const char *p, size_t n) {
 
 static int parserSink(void *arg, const char *bases, size_t n) {
   mb_ctx *c = (mb_ctx *)arg;
-  c->inRecord = !(n == 1 && bases[0] == '.');
+  if (n) c->inRecord = (bases[n - 1] != '.');
   if (!(c->cfg.flags & MB_FLAG_COMPRESS)) return appendHost(c, bases, n);
   //  homopolymer compression (merylInput.C:258-262): a run of one letter keeps its first letter; the run state
   //  carries over the pieces of a record (the reference's `skip` argument) and ends with the record.
@@ -314,7 +318,8 @@ extern "C" int mb_add_file_bytes(mb_ctx *c, const uint8_t *data, uint64_t len) {
   if (!SeqParser::sniff(data, len < 65536 ? len : 65536))
     return mb_fail(MB_EFORMAT, "input is not FASTA or FASTQ");
   SeqParser ps(parserSink, c);
-  MB_TRY(ps.feed(data, len));
+  const size_t BLK = (size_t)256 << 20;
+  for (uint64_t at = 0; at < len; at += BLK) MB_TRY(mb_parse_parallel(parserSink, c, ps, data + at, (size_t)std::min<uint64_t>(BLK, len - at)));
   return ps.finish();
 }
 
@@ -332,6 +337,30 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
   else if (L > 3 && !strcmp(path + L - 3, ".xz"))   tool = "xz -dc";
   else if (L > 4 && !strcmp(path + L - 4, ".zst"))  tool = "zstd -dc";
 
+  //  A plain file is mapped and parsed in place, block by block, on several threads (the page cache is read by the
+  //  parsing threads themselves); pipes and stdin go through a read buffer.
+  if (!tool && strcmp(path, "-") != 0) {
+    const int fd = open(path, O_RDONLY);
+    struct stat stt;
+    if (fd >= 0 && fstat(fd, &stt) == 0 && S_ISREG(stt.st_mode) && stt.st_size > 0) {
+      const size_t sz = (size_t)stt.st_size;
+      void *m = mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0);
+      close(fd);
+      if (m != MAP_FAILED) {
+        madvise(m, sz, MADV_SEQUENTIAL);
+        const uint8_t *d = (const uint8_t *)m;
+        int rc = MB_OK;
+        if (!SeqParser::sniff(d, sz < 65536 ? sz : 65536)) rc = mb_fail(MB_EFORMAT, "'%s' is not FASTA or FASTQ", path);
+        SeqParser ps(parserSink, c);
+        const size_t BLK = (size_t)256 << 20;
+        for (size_t at = 0; rc == MB_OK && at < sz; at += BLK) rc = mb_parse_parallel(parserSink, c, ps, d + at, std::min(BLK, sz - at));
+        munmap(m, sz);
+        if (rc != MB_OK) return rc;
+        return ps.finish();
+      }
+    } else if (fd >= 0) close(fd);
+  }
+
   FILE *f = nullptr;
   if (tool) {
     if (access(path, R_OK) != 0) return mb_fail(MB_EIO, "cannot read '%s'", path);
@@ -344,7 +373,7 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
   }
   if (!f) return mb_fail(MB_EIO, "cannot open '%s'", path);
 
-  const size_t CH = (size_t)16 << 20;
+  const size_t CH = (size_t)128 << 20;                    //  a block is parsed on several threads (parseParallel)
   std::vector<uint8_t> buf(CH);
   SeqParser ps(parserSink, c);
   bool first = true;
@@ -356,7 +385,7 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
       if (!SeqParser::sniff(buf.data(), n < 65536 ? n : 65536)) { rc = mb_fail(MB_EFORMAT, "'%s' is not FASTA or FASTQ", path); break; }
     }
     if (n == 0) break;
-    if ((rc = ps.feed(buf.data(), n)) != MB_OK) break;
+    if ((rc = mb_parse_parallel(parserSink, c, ps, buf.data(), n)) != MB_OK) break;
     if (n < CH) break;
   }
   if (tool) pclose(f); else if (f != stdin) fclose(f);

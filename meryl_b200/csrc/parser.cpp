@@ -24,7 +24,12 @@
 //  reference spin forever (copyVisible stops, skipWhitespace does not advance); here it is
 //  an MB_EFORMAT error.
 
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "common.h"
 
@@ -109,6 +114,19 @@ int SeqParser::feed(const uint8_t *d, size_t n) {
 
       case W: {
         const uint8_t *q = p;
+        //  Fast path for the common line of bases: everything up to the next LF is visible (checked 64 bytes at a
+        //  time in a loop the compiler vectorises); anything else -- CR, blanks inside the line, a stray byte -- stops
+        //  the fast path in front of it and the byte-wise scan takes over.
+        {
+          const uint8_t *lf = (const uint8_t *)memchr(q, '\n', e - q);
+          const uint8_t *lim = lf ? lf : e;
+          while (lim - q >= 64) {
+            uint8_t bad = 0;
+            for (int i = 0; i < 64; i++) bad |= (uint8_t)((uint8_t)(q[i] - '!') > (uint8_t)('~' - '!'));
+            if (bad) break;
+            q += 64;
+          }
+        }
         while (q < e && isVis(*q)) q++;
         MB_TRY(emit(p, q - p));
         p = q;
@@ -135,3 +153,89 @@ int SeqParser::finish(void) {
   _st = A;
   return brk();                                            //  merylOp-countThreads.C:196
 }
+
+
+//  Parse one block of a file on several host threads.  The block is cut where a record seems to start (a line that
+//  begins with '>' or '@'; for '@' the line after next must begin with '+', because a quality line may begin with '@'
+//  too); every piece but the first is parsed by its own SeqParser from state A into its own buffer.  Afterwards the
+//  pieces are stitched in order and the guess is VERIFIED: the state the machine really has at a cut must be one from
+//  which a '>' / '@' starts a record (A, or Q = behind a quality line, or G = behind a sequence line, which first ends
+//  the record); if it is not, that piece is parsed again, sequentially, from the true state.  The result is therefore
+//  exactly what one sequential pass produces.  `ps` carries the state from block to block.
+int mb_parse_parallel(SeqParser::Sink out, void *outArg, SeqParser &ps, const uint8_t *d, size_t n) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  size_t minPiece = (size_t)4 << 20;
+  if (getenv("MB_PARSE_THREADS"))   nt = (unsigned)atoi(getenv("MB_PARSE_THREADS"));          //  testing knobs
+  if (getenv("MB_PARSE_MIN_PIECE")) minPiece = (size_t)strtoull(getenv("MB_PARSE_MIN_PIECE"), nullptr, 10);
+  if (minPiece < 16) minPiece = 16;
+  if (nt < 2 || n < 2 * minPiece) return ps.feed(d, n);
+  if (n / nt < minPiece) nt = (unsigned)(n / minPiece);
+
+  //  cut points
+  std::vector<size_t> cut(1, 0);
+  for (unsigned i = 1; i < nt; i++) {
+    size_t p = n / nt * i;
+    if (p <= cut.back()) continue;
+    bool found = false;
+    for (int tries = 0; tries < 64 && !found; tries++) {          //  next line start that looks like a record start
+      const uint8_t *lf = (const uint8_t *)memchr(d + p, '\n', n - p);
+      if (!lf || (size_t)(lf - d) + 1 >= n) break;
+      p = (size_t)(lf - d) + 1;
+      if (d[p] == '>') found = true;
+      else if (d[p] == '@') {
+        const uint8_t *l1 = (const uint8_t *)memchr(d + p, '\n', n - p);
+        const uint8_t *l2 = l1 ? (const uint8_t *)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - d)) : nullptr;
+        if (l2 && (size_t)(l2 + 1 - d) < n && l2[1] == '+') found = true;
+      }
+    }
+    if (found && p > cut.back()) cut.push_back(p);
+  }
+  cut.push_back(n);
+  const size_t np = cut.size() - 1;
+  if (np < 2) return ps.feed(d, n);
+
+  struct Piece { std::string *outp = nullptr; int rc = MB_OK; SeqParser::State end = SeqParser::A; std::string err; };
+  std::vector<Piece> pc(np);
+  if (ps.pool().size() < np) ps.pool().resize(np);
+  for (size_t i = 0; i < np; i++) { pc[i].outp = &ps.pool()[i]; pc[i].outp->clear(); }
+  auto sink = [](void *a, const char *b, size_t m) -> int { ((std::string *)a)->append(b, m); return 0; };
+  const SeqParser::State st0 = ps.state();
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < np; i++)
+    th.emplace_back([&, i]() {
+      Piece &P = pc[i];
+      P.outp->reserve((cut[i + 1] - cut[i]) / 2 + 4096);
+      SeqParser q(sink, P.outp);
+      q.setState(i == 0 ? st0 : SeqParser::A);
+      P.rc = q.feed(d + cut[i], cut[i + 1] - cut[i]);
+      if (P.rc != MB_OK) P.err = mb_last_error();
+      P.end = q.state();
+    });
+  for (auto &x : th) x.join();
+
+  //  stitch + verify
+  SeqParser::State cur = st0;
+  for (size_t i = 0; i < np; i++) {
+    bool ok = (i == 0);
+    if (i > 0) {
+      if (cur == SeqParser::G) { MB_TRY(out(outArg, ".", 1)); cur = SeqParser::A; }     //  what G does on '>' / '@'
+      ok = (cur == SeqParser::A || cur == SeqParser::Q);
+    }
+    if (ok) {
+      if (pc[i].rc != MB_OK) return mb_fail(pc[i].rc, "%s", pc[i].err.c_str());
+      //  hand the piece on in bounded slices (the sink copies into the pinned staging buffers)
+      for (size_t at = 0; at < pc[i].outp->size(); at += (size_t)8 << 20)
+        MB_TRY(out(outArg, pc[i].outp->data() + at, std::min<size_t>((size_t)8 << 20, pc[i].outp->size() - at)));
+      cur = pc[i].end;
+    } else {                                                 //  the cut was not at a record start: sequentially from the true state
+      SeqParser q(out, outArg);
+      q.setState(cur);
+      MB_TRY(q.feed(d + cut[i], cut[i + 1] - cut[i]));
+      cur = q.state();
+    }
+  }
+  ps.setState(cur);
+  return MB_OK;
+}
+

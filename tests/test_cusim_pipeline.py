@@ -162,3 +162,10 @@ def test_sim_experimental_overlap_d2h(tmp_path, monkeypatch, k, w_prefix):
         assert c.stats().nPasses >= 3
         c.write_db(out)
     util.assert_same_db(ora, out)
+
+
+def test_sim_parallel_parse_in_the_pipeline(tmp_path, monkeypatch):
+    """mb_add_file maps the file and parses it in blocks on several threads (cuts verified against the state machine)."""
+    monkeypatch.setenv("MB_PARSE_THREADS", "4")
+    monkeypatch.setenv("MB_PARSE_MIN_PIECE", "256")
+    _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(5_000, 600, 150, 0.01, 3), "g.fa": synth.fasta_bytes(7, 2_000, 4, width=60, eol=b"\r\n")}, 21, 8)

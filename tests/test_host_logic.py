@@ -140,6 +140,40 @@ def test_parser_large_fastq_and_fasta():
         assert _collapse(_product_parse(data)) == _collapse(util.oracle_parse(data))
 
 
+def _product_parse_parallel(data: bytes, block: int) -> bytes:
+    L = mb.lib()
+    L.mb_dbg_parse_parallel.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64,
+                                        ctypes.POINTER(ctypes.c_uint64)]
+    n = ctypes.c_uint64(0)
+    buf = ctypes.create_string_buffer(len(data) + 64)
+    rc = L.mb_dbg_parse_parallel(data, len(data), block, buf, len(data) + 64, ctypes.byref(n))
+    if rc != 0:
+        raise mb.MerylB200Error(rc, L.mb_last_error().decode())
+    return buf.raw[: n.value]
+
+
+def test_parallel_parser_equals_sequential(monkeypatch):
+    """File inputs are parsed in blocks on several threads, cut at guessed record starts; the guess is verified against the
+    state machine, so the result must be byte-identical to one sequential pass -- including the traps: quality lines that
+    begin with '@', '>' or '+', CRLF, multi-line FASTA, cuts that fall inside a record, blocks that end mid-line."""
+    monkeypatch.setenv("MB_PARSE_THREADS", "5")
+    monkeypatch.setenv("MB_PARSE_MIN_PIECE", "64")
+    rng = np.random.default_rng(9)
+    trap = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"ACGTTGCAAC"[: 3 + i % 8] * 3, [b"@", b">", b"+", b"I"][i % 4] * (3 * (3 + i % 8))) for i in range(400))
+    cases = [synth.reads_fastq_bytes(10_000, 2_000, 150, 0.01, 5), synth.fasta_bytes(40, 3_000, 6),
+             synth.fasta_bytes(5, 20_000, 7, width=70, eol=b"\r\n"), trap, trap.replace(b"\n", b"\r\n"),
+             b">x\n" + b"ACGT" * 50_000 + b"\n"]
+    for data in cases:
+        want = _product_parse(data)
+        for block in (len(data) + 1, 4096, 1000 + int(rng.integers(0, 5000))):
+            assert _product_parse_parallel(data, block) == want
+    alphabet = np.frombuffer(b"ACGTacgtN>@+\n\n\r \tIx", dtype=np.uint8)
+    for it in range(200):                                  # fuzz: arbitrary bytes, every cut guess gets verified or redone
+        n = int(rng.integers(200, 3000))
+        data = (b">" if it % 2 else b">s\n") + alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        assert _collapse(_product_parse_parallel(data, 700)) == _collapse(_product_parse(data)), data
+
+
 def test_estimate_kmers_in_file(tmp_path):
     p = tmp_path / "a.fa"
     p.write_bytes(b">x\nACGT\n" * 100)
