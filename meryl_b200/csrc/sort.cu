@@ -491,13 +491,16 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
 //      128-bit accesses; 4 words of padding behind every such segment keep them bank-conflict free;
 //    * whole-byte digits are extracted with one PRMT; output offsets are 32 bits from the segment start when
 //      the segments are shorter than 2^32 keys.
-//  Shapes (mb_sort_version):  2: 128 threads x 8 bits, 2 CTAs/SM   3: 256 threads x 6 bits, 3 CTAs/SM
-//                             4: 256 threads x 7 bits, 2 CTAs/SM
+//  Shapes (mb_sort_version):  2: 128 threads x 8 bits, 2 CTAs/SM   3: 256 threads x 6 bits, 3 CTAs/SM (default)
+//                             4: 256 threads x 7 bits, 2 CTAs/SM   5: 512 x 6, 2 CTAs/SM   6: 256 x 6, 2 CTAs/SM
 
 template <int VER> struct SweepShape;
 template <> struct SweepShape<2> { static const int THREADS = 128, RBITS = 8, MIN_CTAS = 2; };
 template <> struct SweepShape<3> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 3; };
 template <> struct SweepShape<4> { static const int THREADS = 256, RBITS = 7, MIN_CTAS = 2; };
+//  not yet measured (written without a GPU at hand; tools/ab_bench.py ... sortonly compares all shapes):
+template <> struct SweepShape<5> { static const int THREADS = 512, RBITS = 6, MIN_CTAS = 2; };   //  32 warps/SM, 16 keys per thread
+template <> struct SweepShape<6> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 2; };   //  16 warps/SM, 128 registers: no address recomputation
 
 template <int KW, int VER> struct SweepX {
   typedef typename KeyT<KW>::type Key;
@@ -769,16 +772,18 @@ static int g_sortVersion = 0;
 int mb_sort_version(void) {
   if (g_sortVersion == 0) {
     const char *e = getenv("MB_SORT");
-    g_sortVersion = (e && e[0] >= '1' && e[0] <= '4' && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
+    g_sortVersion = (e && e[0] >= '1' && e[0] <= '6' && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
   }
   return g_sortVersion;
 }
-void mb_sort_set_version(int v) { g_sortVersion = (v >= 1 && v <= 4) ? v : MB_SORT_DEFAULT_VERSION; }
+void mb_sort_set_version(int v) { g_sortVersion = (v >= 1 && v <= 6) ? v : MB_SORT_DEFAULT_VERSION; }
 u32  mb_sort_radix_bits(void) {
   switch (mb_sort_version()) {
     case 2:  return SweepShape<2>::RBITS;
     case 3:  return SweepShape<3>::RBITS;
     case 4:  return SweepShape<4>::RBITS;
+    case 5:  return SweepShape<5>::RBITS;
+    case 6:  return SweepShape<6>::RBITS;
     default: return MB_RADIX_BITS;
   }
 }
@@ -904,6 +909,8 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 2>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 3>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 4>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 5>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 6>::BYTES)) != cudaSuccess) return e;
   for (u32 p = 0; p < plan.nPasses; p++) {
 #define MB_SX_LAUNCH(V) do { typedef SweepX<KW, V> SX;                                                                                         \
       sortx_sweep_kernel<KW, V><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                       \
@@ -911,6 +918,8 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     if      (version == 2) MB_SX_LAUNCH(2);
     else if (version == 3) MB_SX_LAUNCH(3);
     else if (version == 4) MB_SX_LAUNCH(4);
+    else if (version == 5) MB_SX_LAUNCH(5);
+    else if (version == 6) MB_SX_LAUNCH(6);
     else
       sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
                                                                      plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
