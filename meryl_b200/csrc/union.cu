@@ -541,7 +541,30 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
     if (device >= 0) MB_UCUDA(cudaSetDevice(device));
     size_t freeB = 0, totalB = 0;
     MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
+    //  what a group of files needs on the device (upper bound):
+    //    raw bytes + block tables | decoded inputs | two merge buffers | encoder (meta, output, sub-block table, index) | big-value list
+    auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
+      size_t need = (size_t)64 << 20;
+      u64 nk = 0;
+      for (u32 i = 0; i < nInputs; i++)
+        for (u32 f = f0; f < f1; f++) {
+          need += in[i].fileBytes[f] + 256;
+          need += in[i].fileBytes[f] / 104 * sizeof(UnionBlock) + 4096;      //  a block is at least 104 bytes
+          need += in[i].fileKmers[f] * (W + 4) + 512;
+          nk   += in[i].fileKmers[f];
+        }
+      need += 2 * (nk * (W + 4) + 1024);                                    //  merge ping-pong
+      need += nk * ((wS + 34 + 7) / 8 + 1) + (size_t)(f1 - f0) * 64 * 4096 + nk / 64;   //  encoded blocks (every block <= n(b+34) + headers)
+      need += nk / MG_TILE * 16 + nk / MB_HIST_SMALL * 4 + 65536;
+      return need;
+    };
+
     size_t want = workspaceBytes ? (size_t)workspaceBytes : (freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2);
+    if (!workspaceBytes) {                                   //  no more than all 64 files at once need (allocating ~175 GB takes time)
+      const size_t all = groupNeed(0, 64);
+      const size_t cap = all + all / 8 + ((size_t)288 << 20);
+      if (cap < want) want = cap;
+    }
     if (want > freeB) want = freeB;
     want = want / 256 * 256;
     if (cudaMalloc((void **)&arena, want) != cudaSuccess) { cudaGetLastError(); arena = nullptr; rc = mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want); goto done; }
@@ -561,24 +584,6 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
     MB_UCUDA(cudaMemsetAsync(dCtl, 0, 64 * 8, s));
     MB_UCUDA(cudaMemsetAsync(dFileBase, 0, 64 * 8, s));
     const size_t fixedOff = top.off;
-
-    //  what a group of files needs on the device (upper bound):
-    //    raw bytes + block tables | decoded inputs | two merge buffers | encoder (meta, output, sub-block table, index) | big-value list
-    auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
-      size_t need = (size_t)64 << 20;
-      u64 nk = 0;
-      for (u32 i = 0; i < nInputs; i++)
-        for (u32 f = f0; f < f1; f++) {
-          need += in[i].fileBytes[f] + 256;
-          need += in[i].fileBytes[f] / 104 * sizeof(UnionBlock) + 4096;      //  a block is at least 104 bytes
-          need += in[i].fileKmers[f] * (W + 4) + 512;
-          nk   += in[i].fileKmers[f];
-        }
-      need += 2 * (nk * (W + 4) + 1024);                                    //  merge ping-pong
-      need += nk * ((wS + 34 + 7) / 8 + 1) + (size_t)(f1 - f0) * 64 * 4096 + nk / 64;   //  encoded blocks (every block <= n(b+34) + headers)
-      need += nk / MG_TILE * 16 + nk / MB_HIST_SMALL * 4 + 65536;
-      return need;
-    };
 
     std::vector<HostBuf> hostIn(nInputs);                    //  the group's file bytes, one buffer per input (reused by the next group)
     HostBuf outBytes, outIdx;
