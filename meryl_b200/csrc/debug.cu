@@ -264,3 +264,34 @@ extern "C" int mb_dbg_parse_parallel(const uint8_t *data, uint64_t len, uint64_t
   }
   return MB_OK;
 }
+
+#ifdef MB_CUSIM
+//  Emulator only (tests/cusim): `world` ranks as fibers of this process, each with its own context and its share of the
+//  input (file images), the emulated collectives of exchange.cu between them; every rank writes its files into outDir.
+extern "C" int mb_sim_comm_attach(mb_ctx *ctx);
+extern "C" int mb_sim_multi_count(uint32_t world, uint32_t k, uint32_t mode, uint32_t wPrefix, const uint8_t *const *data, const uint64_t *lens,
+                                  const char *outDir, uint64_t *nKmersPerRank, uint32_t *nPassesPerRank) {
+  mb_clear_error();
+  std::vector<int> rcs(world, MB_OK);
+  std::vector<std::string> errs(world);
+  cusim::run_ranks(world, [&](unsigned r) {
+    mb_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.k = k;  cfg.mode = mode;  cfg.wPrefix = wPrefix;  cfg.device = -1;  cfg.rank = r;  cfg.worldSize = world;
+    cfg.workspaceBytes = (size_t)384 << 20;
+    mb_ctx *c = nullptr;
+    int rc = mb_create(&cfg, &c);
+    if (rc == MB_OK) rc = mb_sim_comm_attach(c);
+    if (rc == MB_OK && lens[r]) rc = mb_add_file_bytes(c, data[r], lens[r]);
+    if (rc == MB_OK) rc = mb_count(c);
+    if (rc == MB_OK) rc = mb_write_db(c, outDir);
+    mb_stats st;
+    if (rc == MB_OK && mb_get_stats(c, &st) == MB_OK) { if (nKmersPerRank) nKmersPerRank[r] = st.nKmers; if (nPassesPerRank) nPassesPerRank[r] = st.nPasses; }
+    if (rc != MB_OK) errs[r] = mb_last_error();
+    rcs[r] = rc;
+    if (c) mb_destroy(c);
+  });
+  for (uint32_t r = 0; r < world; r++) if (rcs[r] != MB_OK) return mb_fail(rcs[r], "rank %u: %s", r, errs[r].c_str());
+  return MB_OK;
+}
+#endif

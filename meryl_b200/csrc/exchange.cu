@@ -72,6 +72,34 @@ struct MbComm {
   u32 rank = 0, world = 1;
 };
 
+#ifdef MB_CUSIM
+//  Host emulator (tests/cusim): the ranks are fibers of one process, "device" pointers are host pointers, so a
+//  collective is a rendezvous: every rank deposits its arguments, the last one to arrive moves the data for all.
+namespace {
+struct SimHub {
+  u32 world = 0, arrived = 0;  u64 gen = 0;
+  struct Args { const void *a = nullptr; void *b = nullptr; const u64 *c = nullptr; const u64 *d = nullptr; u64 n = 0; u32 x = 0, y = 0, z = 0; } args[32];
+} g_hub;
+
+template <typename F> int simCollective(MbComm *m, const SimHub::Args &mine, F moveAll) {
+  g_hub.args[m->rank] = mine;
+  const u64 gen = g_hub.gen;
+  if (++g_hub.arrived == m->world) { moveAll(); g_hub.arrived = 0; g_hub.gen++; }
+  else while (g_hub.gen == gen) cusim::rank_yield();
+  return MB_OK;
+}
+}  //  namespace
+
+extern "C" int mb_sim_comm_attach(mb_ctx *ctx) {             //  instead of mb_comm_unique_id + mb_comm_init
+  const mb_config &cfg = mb_ctx_config(ctx);
+  MbComm *m = new MbComm();
+  m->rank = cfg.rank;  m->world = cfg.worldSize;
+  g_hub.world = cfg.worldSize;
+  mb_ctx_set_comm(ctx, m);
+  return MB_OK;
+}
+#endif
+
 //  The communicator is created once per process and shared by every context: NCCL sets up its
 //  peer-to-peer channels lazily (seconds for the first send/recv), which must not be paid per job.
 static MbComm *g_processComm = nullptr;
@@ -147,6 +175,14 @@ extern "C" int mb_comm_init(mb_ctx *ctx, const uint8_t id[128]) {
 
 //  All-gather `n` u64 per rank (device pointers; dAll holds world*n).
 int mb_comm_allgather_u64(MbComm *m, const u64 *dMine, u64 *dAll, size_t n, cudaStream_t s) {
+#ifdef MB_CUSIM
+  SimHub::Args a;  a.a = dMine;  a.b = dAll;  a.n = n;
+  return simCollective(m, a, [&]() {
+    for (u32 dst = 0; dst < m->world; dst++)
+      for (u32 src = 0; src < m->world; src++)
+        memcpy((u64 *)g_hub.args[dst].b + (size_t)src * n, g_hub.args[src].a, n * sizeof(u64));
+  });
+#endif
   MB_NCCL(g_nccl.AllGather(dMine, dAll, n, kNcclUint64, m->comm, s));
   return MB_OK;
 }
@@ -161,6 +197,26 @@ int mb_comm_exchange_keys(MbComm *m, u32 keyWords, const void *sendBuf, void *re
   const u32 me = m->rank, world = m->world;
   const u64 *sb = (const u64 *)sendBuf;
   u64       *rb = (u64 *)recvBuf;
+#ifdef MB_CUSIM
+  {
+    SimHub::Args a;  a.a = sendBuf;  a.b = recvBuf;  a.c = sendStart;  a.d = C;  a.x = fileLo;  a.y = fileHi;  a.z = keyWords;
+    return simCollective(m, a, [&]() {
+      //  what the grouped ncclSend / ncclRecv pairs below do, for every (file, source, owner)
+      for (u32 dst = 0; dst < world; dst++) {
+        u64 recvAt = 0;
+        for (u32 f = fileLo; f < fileHi; f++) {
+          if (mb_file_owner(f, world) != dst) continue;
+          for (u32 src = 0; src < world; src++) {
+            const u64 c = C[(size_t)src * 64 + f];
+            if (c) memcpy((u64 *)g_hub.args[dst].b + recvAt * keyWords,
+                          (const u64 *)g_hub.args[src].a + g_hub.args[src].c[f - fileLo] * keyWords, c * keyWords * sizeof(u64));
+            recvAt += c;
+          }
+        }
+      }
+    });
+  }
+#endif
   MB_NCCL(g_nccl.GroupStart());
   u64 recvAt = 0;
   for (u32 f = fileLo; f < fileHi; f++) {
@@ -182,6 +238,18 @@ int mb_comm_exchange_keys(MbComm *m, u32 keyWords, const void *sendBuf, void *re
 //  Gather variable-length u64 arrays on rank 0 (device staging provided by the caller):
 //  every rank sends `n` words from dSend; rank 0 receives rank r's words at dRecv + offsets[r].
 int mb_comm_gather_u64(MbComm *m, const u64 *dSend, u64 n, u64 *dRecv, const u64 *counts, cudaStream_t s) {
+#ifdef MB_CUSIM
+  {
+    SimHub::Args a;  a.a = dSend;  a.b = dRecv;  a.n = n;
+    return simCollective(m, a, [&]() {
+      u64 at = 0;
+      for (u32 r = 1; r < m->world; r++) {
+        if (g_hub.args[r].n) memcpy((u64 *)g_hub.args[0].b + at, g_hub.args[r].a, g_hub.args[r].n * sizeof(u64));
+        at += g_hub.args[r].n;
+      }
+    });
+  }
+#endif
   MB_NCCL(g_nccl.GroupStart());
   if (m->rank != 0) {
     if (n) MB_NCCL(g_nccl.Send(dSend, n, kNcclUint64, 0, m->comm, s));

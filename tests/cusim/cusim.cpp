@@ -173,4 +173,62 @@ void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &
   }
 }
 
+//  ---- rank fibers ---------------------------------------------------------------------------------------------
+
+namespace {
+struct RankFiber { void *sp = nullptr; bool done = false; unsigned char *stack = nullptr; };
+std::vector<RankFiber> g_ranks;
+void *g_rankSchedSp = nullptr;
+int   g_curRank = -1;
+const std::function<void(unsigned)> *g_rankBody = nullptr;
+const size_t kRankStack = (size_t)64 << 20;
+
+void rank_main() {
+  (*g_rankBody)((unsigned)g_curRank);
+  RankFiber &r = g_ranks[g_curRank];
+  r.done = true;
+  cusim_switch(&r.sp, g_rankSchedSp);
+  abort();
+}
+}  //  namespace
+
+bool in_rank(void) { return g_curRank >= 0; }
+
+void rank_yield(void) {
+  if (g_curRank < 0) return;
+  RankFiber &r = g_ranks[g_curRank];
+  cusim_switch(&r.sp, g_rankSchedSp);
+}
+
+void run_ranks(unsigned world, const std::function<void(unsigned rank)> &body) {
+  if (g_curRank >= 0) { fprintf(stderr, "cusim: nested run_ranks\n"); abort(); }
+  g_ranks.assign(world, RankFiber());
+  g_rankBody = &body;
+  for (unsigned i = 0; i < world; i++) {
+    RankFiber &r = g_ranks[i];
+    r.stack = (unsigned char *)mmap(nullptr, kRankStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (r.stack == MAP_FAILED) { perror("cusim: mmap"); abort(); }
+    void **sp = (void **)(r.stack + kRankStack);
+    *--sp = nullptr;
+    *--sp = (void *)rank_main;
+    for (int k = 0; k < 6; k++) *--sp = nullptr;
+    r.sp = sp;
+  }
+  unsigned live = world;
+  unsigned long long rounds = 0;
+  while (live) {
+    for (unsigned i = 0; i < world; i++) {
+      if (g_ranks[i].done) continue;
+      g_curRank = (int)i;
+      cusim_switch(&g_rankSchedSp, g_ranks[i].sp);
+      g_curRank = -1;
+      if (g_ranks[i].done) live--;
+    }
+    if (++rounds > 50000000ull) { fprintf(stderr, "cusim: ranks make no progress (a collective some rank never joins?)\n"); abort(); }
+  }
+  for (unsigned i = 0; i < world; i++) munmap(g_ranks[i].stack, kRankStack);
+  g_ranks.clear();
+  g_rankBody = nullptr;
+}
+
 }  //  namespace cusim

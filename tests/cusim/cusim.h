@@ -111,6 +111,13 @@ extern unsigned long long g_clock;    //  advances at every fiber switch
 extern unsigned long long g_progress; //  bumped by every event that can unblock somebody
 
 void  launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &body);
+
+//  Several "ranks" (one GPU process each, in the product) inside this one process: every rank runs its host code as a
+//  fiber; rank_yield() lets the others run (the emulated collectives of csrc/exchange.cu wait with it).  Kernel launches
+//  stay synchronous inside a rank.
+void  run_ranks(unsigned world, const std::function<void(unsigned rank)> &body);
+void  rank_yield(void);
+bool  in_rank(void);
 void *dyn_smem(void);
 void  yield(void);                    //  let the other fibers of the block run
 void  block_barrier(void);

@@ -1,0 +1,59 @@
+"""The multi-GPU path on the CPU: `world` ranks run as fibers inside the cusim emulator (tests/cusim), the NCCL collectives
+of csrc/exchange.cu are replaced by in-process rendezvous copies with the same semantics, and the directory written by all
+ranks must be byte-identical to the single-process oracle db -- the CPU twin of tests/test_gpu_multi.py, which needs
+2-8 GPUs."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+import util
+import meryl_b200 as mb
+from meryl_b200 import dist as mbd
+from meryl_b200 import synth
+
+SIM_DIR = os.path.join(util.ROOT, "tests", "cusim")
+SIM_LIB = os.path.join(SIM_DIR, "_build", "libmeryl_b200_sim.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def sim_library():
+    subprocess.run(["make", "-s", "-j8", "-C", SIM_DIR], check=True)
+    saved = (mb.LIB_PATH, mb._lib)
+    mb.LIB_PATH, mb._lib = SIM_LIB, None
+    yield
+    mb.LIB_PATH, mb._lib = saved
+
+
+def multi_count(world, k, w_prefix, data: bytes, out_dir: str, mode: int = 0):
+    recs = data.split(b"@r")[1:]                          # synthetic FASTQ: every record starts with "@r"
+    parts = []
+    for r in range(world):
+        first, cnt = mbd.shard_range(len(recs), r, world)
+        parts.append(b"".join(b"@r" + x for x in recs[first:first + cnt]))
+    L = mb.lib()
+    L.mb_sim_multi_count.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p),
+                                     ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
+    arr = (ctypes.c_char_p * world)(*parts)
+    lens = (ctypes.c_uint64 * world)(*[len(p) for p in parts])
+    nk = (ctypes.c_uint64 * world)()
+    npass = (ctypes.c_uint32 * world)()
+    os.makedirs(out_dir, exist_ok=True)
+    rc = L.mb_sim_multi_count(world, k, mode, w_prefix, arr, lens, out_dir.encode(), nk, npass)
+    assert rc == 0, L.mb_last_error().decode()
+    return list(nk), list(npass)
+
+
+@pytest.mark.parametrize("world,k", [(2, 21), (4, 21), (8, 31), (2, 51)])
+def test_sim_multi_rank_db_bit_exact(tmp_path, world, k):
+    n_reads, rl = 6_000, 150
+    data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 17 + k)
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
+    nk, npass = multi_count(world, k, 12, data, out)
+    util.assert_same_db(ora, out)
+    assert sum(nk) == n_reads * (rl - k + 1)                # every k-mer is counted by exactly one rank
+    assert max(nk) < 1.6 * sum(nk) / world                  # and the file ownership map balances the ranks
