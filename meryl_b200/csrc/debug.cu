@@ -269,6 +269,8 @@ extern "C" int mb_dbg_parse_parallel(const uint8_t *data, uint64_t len, uint64_t
 //  Emulator only (tests/cusim): `world` ranks as fibers of this process, each with its own context and its share of the
 //  input (file images), the emulated collectives of exchange.cu between them; every rank writes its files into outDir.
 extern "C" int mb_sim_comm_attach(mb_ctx *ctx);
+static uint32_t g_simKeyBytes[32];
+extern "C" uint32_t mb_sim_last_key_bytes(uint32_t rank) { return rank < 32 ? g_simKeyBytes[rank] : 0; }   //  of the last mb_sim_multi_count
 extern "C" int mb_sim_multi_count(uint32_t world, uint32_t k, uint32_t mode, uint32_t wPrefix, const uint8_t *const *data, const uint64_t *lens,
                                   const char *outDir, uint64_t *nKmersPerRank, uint32_t *nPassesPerRank) {
   mb_clear_error();
@@ -286,7 +288,7 @@ extern "C" int mb_sim_multi_count(uint32_t world, uint32_t k, uint32_t mode, uin
     if (rc == MB_OK) rc = mb_count(c);
     if (rc == MB_OK) rc = mb_write_db(c, outDir);
     mb_stats st;
-    if (rc == MB_OK && mb_get_stats(c, &st) == MB_OK) { if (nKmersPerRank) nKmersPerRank[r] = st.nKmers; if (nPassesPerRank) nPassesPerRank[r] = st.nPasses; }
+    if (rc == MB_OK && mb_get_stats(c, &st) == MB_OK) { if (nKmersPerRank) nKmersPerRank[r] = st.nKmers; if (nPassesPerRank) nPassesPerRank[r] = st.nPasses; if (r < 32) g_simKeyBytes[r] = st.keyBytes; }
     if (rc != MB_OK) errs[r] = mb_last_error();
     rcs[r] = rc;
     if (c) mb_destroy(c);

@@ -433,6 +433,7 @@ struct Pass {
   u64 nLocal = 0;                                     //  keys this rank extracts
   u64 nKeys  = 0;                                     //  keys this rank sorts (== nLocal on one GPU)
   std::vector<u64> segCount;                          //  sort segments, in memory order
+  std::vector<u32> segBin;                            //  multi-GPU u32 suffix keys: prefix bin of every segment (else binLo + i)
   std::vector<std::pair<u64, u64>> encRanges;         //  (first block prefix, number of blocks) to encode
 };
 
@@ -519,6 +520,23 @@ static int runCount(mb_ctx *c) {
   }
   std::vector<u64> fileTotal(64, 0);
   for (u32 r = 0; r < world; r++) for (u32 f = 0; f < 64; f++) fileTotal[f] += C[(size_t)r * 64 + f];
+
+  //  Experimental (MB_MULTI_SUFFIX32=1, not the default until it has run on real GPUs): on several GPUs, too, a k-mer
+  //  travels and is sorted as the 32 bits below its prefix bin when they fit a word (k <= 21).  Routing is then by bin,
+  //  so everybody also learns everybody's per-bin counts.
+  const bool want32 = world > 1 && getenv("MB_MULTI_SUFFIX32") != nullptr && 2 * k - binBits <= 32 && !c->stopAfterSort;
+  std::vector<u64> Cb;                                  //  Cb[r][b]
+  std::vector<u64> binTotal;
+  if (want32) {
+    u64 *dBinAll = (u64 *)top.take((size_t)(world + 1) * nBins * sizeof(u64));
+    if (!dBinAll) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
+    Cb.assign((size_t)world * nBins, 0);
+    MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->binCount, dBinAll, nBins, s));
+    MB_CUDA(cudaMemcpyAsync(Cb.data(), dBinAll, (size_t)world * nBins * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    binTotal.assign(nBins, 0);
+    for (u32 r = 0; r < world; r++) for (u32 b = 0; b < nBins; b++) binTotal[b] += Cb[(size_t)r * nBins + b];
+  }
   u64 nMine = 0;                                        //  k-mers this rank will count
   for (u32 f = 0; f < 64; f++) {
     c->db.owned[f] = (mb_file_owner(f, world) == me);
@@ -636,23 +654,58 @@ static int runCount(mb_ctx *c) {
   } else {
     //  slot j of every rank = files [j*world, (j+1)*world); a pass takes q consecutive slots.
     //  Every rank must fit what it sends and what it receives, in every pass: pick the largest q.
-    sortBits = 2 * k - 6;
-    const u32 slots = 64 / world;
-    u32 q = 0;
-    for (u32 tryQ = slots; tryQ >= 1 && q == 0; tryQ--) {
-      if (slots % tryQ) continue;
-      bool ok = true;
-      for (u32 p0 = 0; p0 < slots && ok; p0 += tryQ)
-        for (u32 r = 0; r < world && ok; r++) {
-          u64 snd = 0, rcv = 0;
-          for (u32 f = p0 * world; f < (p0 + tryQ) * world; f++) {
-            snd += C[(size_t)r * 64 + f];
-            if (mb_file_owner(f, world) == r) rcv += fileTotal[f];
-          }
-          if (snd > capKeys || rcv > capKeys) ok = false;
-        }
-      if (ok) q = tryQ;
+    //  The plan must come out the same on every rank, so the capacities are the smallest of all ranks'.
+    const u32 tile32 = mb_sort_tile_keys(4);
+    const double perKey32 = 2.0 * 4 + (double)radix * 8 / tile32 + 16.0 / tile32;
+    size_t enc32 = std::max<size_t>((size_t)4 << 30, (size_t)nBlocksTotal * 200 / world);
+    if (enc32 > R / 3) enc32 = R / 3;
+    u64 cap32 = 0;
+    if (want32 && R > enc32 + fixed + ((size_t)64 << 20)) {
+      cap32 = (u64)((double)(R - enc32 - fixed) / perKey32) / 8192 * 8192;
+      if (capLimit && cap32 > capLimit) cap32 = capLimit;
     }
+    {
+      u64 caps[3] = { capKeys, cap32, (u64)enc32 };
+      std::vector<u64> all((size_t)world * 3);
+      MB_CUDA(cudaMemcpyAsync(dCtl->fileCount, caps, sizeof(caps), cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 3, s));
+      MB_CUDA(cudaMemcpyAsync(all.data(), dCtl->allFileCount, all.size() * sizeof(u64), cudaMemcpyDeviceToHost, s));
+      MB_CUDA(cudaStreamSynchronize(s));
+      for (u32 r = 0; r < world; r++) {
+        capKeys = std::min(capKeys, all[(size_t)r * 3]);
+        cap32   = std::min(cap32,   all[(size_t)r * 3 + 1]);
+        enc32   = (size_t)std::min<u64>(enc32, all[(size_t)r * 3 + 2]);
+      }
+    }
+    const u32 slots = 64 / world;
+    auto planSlots = [&](u64 cap, bool s32) -> u32 {
+      for (u32 tryQ = slots; tryQ >= 1; tryQ--) {
+        if (slots % tryQ) continue;
+        bool ok = true;
+        for (u32 p0 = 0; p0 < slots && ok; p0 += tryQ)
+          for (u32 r = 0; r < world && ok; r++) {
+            u64 snd = 0, rcv = 0;
+            for (u32 f = p0 * world; f < (p0 + tryQ) * world; f++) {
+              snd += C[(size_t)r * 64 + f];
+              if (mb_file_owner(f, world) == r) rcv += fileTotal[f];
+            }
+            if (snd > cap || rcv > cap) ok = false;
+            if (ok && s32) {                               //  every owned bin must fit a count group (see the groups below)
+              const u64 gcap = std::min<u64>(std::max(snd, rcv) / 2 + 8, (u64)(enc32 / 3 / 8));
+              for (u32 f = p0 * world; f < (p0 + tryQ) * world && ok; f++)
+                if (mb_file_owner(f, world) == r)
+                  for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++)
+                    if (binTotal[b] > gcap || binTotal[b] >= ((u64)1 << 32)) ok = false;
+            }
+          }
+        if (ok) return tryQ;
+      }
+      return 0;
+    };
+    u32 q = 0;
+    if (want32 && cap32 > 0 && (q = planSlots(cap32, true)) != 0) suffix32 = true;
+    if (q == 0) q = planSlots(capKeys, false);
+    sortBits = suffix32 ? 2 * k - binBits : 2 * k - 6;
     if (q == 0)
       return mb_fail(MB_ENOMEM, "a single data file's k-mers do not fit one of the %u devices (capacity %llu keys); use more GPUs", world, (u64)capKeys);
     for (u32 p0 = 0; p0 < slots; p0 += q) {
@@ -661,8 +714,11 @@ static int runCount(mb_ctx *c) {
       P.binLo = fLo * binsPerFile;  P.binHi = fHi * binsPerFile;
       for (u32 f = fLo; f < fHi; f++) {
         P.nLocal += C[(size_t)me * 64 + f];
-        if (c->db.owned[f]) {
-          P.nKeys += fileTotal[f];
+        if (!c->db.owned[f]) continue;
+        P.nKeys += fileTotal[f];
+        if (suffix32) {
+          for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) { P.segCount.push_back(binTotal[b]); P.segBin.push_back(b); }
+        } else {
           P.segCount.push_back(fileTotal[f]);
           P.encRanges.push_back(std::make_pair((u64)f * blocksPerFile, blocksPerFile));
         }
@@ -751,7 +807,8 @@ static int runCount(mb_ctx *c) {
       std::vector<u64> sendStart(fHi - fLo);
       for (u32 f = fLo; f < fHi; f++) sendStart[f - fLo] = binStart[f * binsPerFile];
       tStage.start(s);
-      MB_TRY(mb_comm_exchange_keys(c->comm, c->keyWords, bufA, bufB, fLo, fHi, sendStart.data(), C.data(), s));
+      if (suffix32) MB_TRY(mb_comm_exchange_suffixes(c->comm, bufA, bufB, P.binLo, P.binHi, binsPerFile, &binStart[P.binLo], Cb.data(), nBins, s));
+      else          MB_TRY(mb_comm_exchange_keys(c->comm, c->keyWords, bufA, bufB, fLo, fHi, sendStart.data(), C.data(), s));
       tStage.stop(s);
       MB_CUDA(cudaStreamSynchronize(s));
       c->st.msExchange += tStage.ms();
@@ -792,21 +849,24 @@ static int runCount(mb_ctx *c) {
     //  ---- K5 + K6, one group of whole segments at a time ----------------------------------------------
     //  Full keys (8/16 B): a single group, counted in place.  u32 suffix keys: the pass is cut into
     //  groups of consecutive bins whose distinct k-mers, expanded to u64, fit the spare key buffer.
-    struct Group { u32 segLo, segHi; u64 keyLo, keyHi, tileLo, tileHi; std::vector<std::pair<u64, u64>> encRanges; };
+    struct Group { u32 segLo, segHi, binLo; u64 keyLo, keyHi, tileLo, tileHi; std::vector<std::pair<u64, u64>> encRanges; };
     std::vector<Group> groups;
     if (!suffix32) {
-      Group g;  g.segLo = 0;  g.segHi = nSegs;  g.keyLo = 0;  g.keyHi = n;  g.tileLo = 0;  g.tileHi = nTiles;
+      Group g;  g.segLo = 0;  g.segHi = nSegs;  g.binLo = P.binLo;  g.keyLo = 0;  g.keyHi = n;  g.tileLo = 0;  g.tileHi = nTiles;
       g.encRanges = P.encRanges;
       groups.push_back(g);
     } else {
       const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / (overlapD2H ? 2 : 1) / 3 / 8));
-      Group g;  g.segLo = 0;  g.keyLo = 0;  g.tileLo = 0;
+      Group g;  g.segLo = 0;  g.binLo = P.binLo;  g.keyLo = 0;  g.tileLo = 0;
       u64 have = 0;
+      auto segBin = [&](u32 i) -> u32 { return P.segBin.empty() ? P.binLo + i : P.segBin[i]; };
       for (u32 i = 0; i <= nSegs; i++) {
-        if (i == nSegs || (have > 0 && have + P.segCount[i] > gcap)) {
+        //  a group is a run of consecutive bins (several GPUs: the owned files of a pass are not adjacent)
+        if (i == nSegs || (have > 0 && have + P.segCount[i] > gcap) || (i > g.segLo && segBin(i) != segBin(i - 1) + 1)) {
           g.segHi = i;  g.keyHi = segStart[i];  g.tileHi = segTile[i];
+          g.binLo = segBin(g.segLo) - g.segLo;              //  (wraps; the kernel adds the segment index back)
           g.encRanges.clear();
-          g.encRanges.push_back(std::make_pair((u64)(P.binLo + g.segLo) * blocksPerBin, (u64)(g.segHi - g.segLo) * blocksPerBin));
+          g.encRanges.push_back(std::make_pair((u64)segBin(g.segLo) * blocksPerBin, (u64)(g.segHi - g.segLo) * blocksPerBin));
           groups.push_back(g);
           g.segLo = i;  g.keyLo = segStart[i];  g.tileLo = segTile[i];  have = 0;
         }
@@ -829,11 +889,12 @@ static int runCount(mb_ctx *c) {
         MB_CUDA(mb_launch_count(c->keyWords, sorted, n, runStart, &dCtl->numDistinct, ws, s));
       } else {
         distinctKeys = other;  encKeyWords = 1;
+        if (gKeys > bufKeys / 2 + 8) return mb_fail(MB_ENOMEM, "internal: group %zu of pass %zu (%llu k-mers) does not fit the spare key buffer", gi, pi, (u64)gKeys);
         runStart = (u64 *)gc.take(8 * (size_t)(gKeys + 1));
         void *cws = gc.take(8 * (size_t)(2 * (G.tileHi - G.tileLo) + 2));   //  (the sort workspace still holds the tile table)
         if (!runStart || !cws) return mb_fail(MB_ENOMEM, "internal: no room for the run table of pass %zu group %zu", pi, gi);
         MB_CUDA(mb_launch_count_suffix32((const u32 *)sorted, mb_sort_tile_info(ws, nTiles, nSegs ? nSegs : 1, plan.nPasses),
-                                         G.tileLo, G.tileHi, G.keyHi, P.binLo, 2 * k - binBits, (u64 *)other, runStart,
+                                         G.tileLo, G.tileHi, G.keyHi, G.binLo, 2 * k - binBits, (u64 *)other, runStart,
                                          &dCtl->numDistinct, cws, s));
       }
       u64 D = 0;

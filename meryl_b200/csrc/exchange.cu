@@ -235,6 +235,53 @@ int mb_comm_exchange_keys(MbComm *m, u32 keyWords, const void *sendBuf, void *re
   return MB_OK;
 }
 
+//  The same all-to-all for u32 suffix keys (k <= 21: the bits below the prefix bin fit one word, the bin is implied by
+//  the segment a key sits in).  The unit is the prefix BIN: bins [binLo, binHi) of this pass, bin b belongs to the owner
+//  of its data file b / binsPerFile.  sendBuf holds this rank's suffixes grouped by bin (sendStart[b - binLo] in keys,
+//  counts Cb[me][b]); recvBuf receives, for every bin of every file this rank owns (ascending), the chunks of ranks
+//  0..world-1 back to back, so every owned bin ends up as one contiguous sort segment.  Cb is the [world][nBins] matrix
+//  of per-rank bin counts (host).  One message per (bin, peer): 4 bytes per k-mer on the wire instead of 8.
+int mb_comm_exchange_suffixes(MbComm *m, const void *sendBuf, void *recvBuf, u32 binLo, u32 binHi, u32 binsPerFile,
+                              const u64 *sendStart, const u64 *Cb, u32 nBins, cudaStream_t s) {
+  const u32 me = m->rank, world = m->world;
+  const u32 *sb = (const u32 *)sendBuf;
+  u32       *rb = (u32 *)recvBuf;
+#ifdef MB_CUSIM
+  {
+    SimHub::Args a;  a.a = sendBuf;  a.b = recvBuf;  a.c = sendStart;  a.d = Cb;  a.x = binLo;  a.y = binHi;  a.z = binsPerFile;  a.n = nBins;
+    return simCollective(m, a, [&]() {
+      for (u32 dst = 0; dst < world; dst++) {
+        u64 recvAt = 0;
+        for (u32 b = binLo; b < binHi; b++) {
+          if (mb_file_owner(b / binsPerFile, world) != dst) continue;
+          for (u32 src = 0; src < world; src++) {
+            const u64 c = Cb[(size_t)src * nBins + b];
+            if (c) memcpy((u32 *)g_hub.args[dst].b + recvAt, (const u32 *)g_hub.args[src].a + g_hub.args[src].c[b - binLo], c * sizeof(u32));
+            recvAt += c;
+          }
+        }
+      }
+    });
+  }
+#endif
+  MB_NCCL(g_nccl.GroupStart());
+  u64 recvAt = 0;
+  for (u32 b = binLo; b < binHi; b++) {
+    const u32 own = mb_file_owner(b / binsPerFile, world);
+    const u64 mine = Cb[(size_t)me * nBins + b];
+    if (mine) MB_NCCL(g_nccl.Send(sb + sendStart[b - binLo], mine * sizeof(u32), kNcclUint8, (int)own, m->comm, s));
+    if (own == me) {
+      for (u32 src = 0; src < world; src++) {
+        const u64 c = Cb[(size_t)src * nBins + b];
+        if (c) MB_NCCL(g_nccl.Recv(rb + recvAt, c * sizeof(u32), kNcclUint8, (int)src, m->comm, s));
+        recvAt += c;
+      }
+    }
+  }
+  MB_NCCL(g_nccl.GroupEnd());
+  return MB_OK;
+}
+
 //  Gather variable-length u64 arrays on rank 0 (device staging provided by the caller):
 //  every rank sends `n` words from dSend; rank 0 receives rank r's words at dRecv + offsets[r].
 int mb_comm_gather_u64(MbComm *m, const u64 *dSend, u64 n, u64 *dRecv, const u64 *counts, cudaStream_t s) {

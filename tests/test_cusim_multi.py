@@ -41,8 +41,16 @@ def multi_count(world, k, w_prefix, data: bytes, out_dir: str, mode: int = 0):
     npass = (ctypes.c_uint32 * world)()
     os.makedirs(out_dir, exist_ok=True)
     rc = L.mb_sim_multi_count(world, k, mode, w_prefix, arr, lens, out_dir.encode(), nk, npass)
+    multi_key_bytes.world = world
     assert rc == 0, L.mb_last_error().decode()
     return list(nk), list(npass)
+
+
+def multi_key_bytes():
+    """Key bytes every rank of the last multi_count() sorted with."""
+    L = mb.lib()
+    L.mb_sim_last_key_bytes.restype = ctypes.c_uint32
+    return [L.mb_sim_last_key_bytes(r) for r in range(multi_key_bytes.world)]
 
 
 @pytest.mark.parametrize("world,k", [(2, 21), (4, 21), (8, 31), (2, 51)])
@@ -57,3 +65,55 @@ def test_sim_multi_rank_db_bit_exact(tmp_path, world, k):
     util.assert_same_db(ora, out)
     assert sum(nk) == n_reads * (rl - k + 1)                # every k-mer is counted by exactly one rank
     assert max(nk) < 1.6 * sum(nk) / world                  # and the file ownership map balances the ranks
+
+
+@pytest.mark.parametrize("world,k,cap", [(2, 21, 60_000), (4, 31, 40_000), (2, 51, 80_000)])
+def test_sim_multi_rank_multi_pass(tmp_path, monkeypatch, world, k, cap):
+    """100 Gbp on 2 or 4 GPUs does not fit one pass (64-bit keys): passes over groups of file slots, one exchange per pass.
+    MB_MAX_PASS_KEYS caps what a rank may send or receive per pass, so a small input takes the same road."""
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    n_reads, rl = 3_000, 150
+    data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 5 + k)
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
+    nk, npass = multi_count(world, k, 12, data, out)
+    util.assert_same_db(ora, out)
+    assert sum(nk) == n_reads * (rl - k + 1)
+    assert min(npass) == max(npass) and npass[0] > 1         # every rank walks the same, multi-pass plan
+
+
+@pytest.mark.parametrize("world,k,wp,cap", [(2, 21, 12, 0), (4, 21, 12, 0), (8, 21, 14, 0), (2, 17, 10, 0), (4, 15, 8, 0),
+                                            (2, 21, 12, 60_000), (8, 20, 12, 25_000)])
+def test_sim_multi_rank_suffix32(tmp_path, monkeypatch, world, k, wp, cap):
+    """MB_MULTI_SUFFIX32=1 (experimental): on several GPUs, too, k <= 21 travels and is sorted as u32 suffixes below the
+    prefix bin; routing is by bin (one message per bin and peer), every owned bin is a sort segment, count groups are runs
+    of consecutive bins inside an owned file.  Same db bytes as the oracle; k-mers per rank as in the u64 form."""
+    monkeypatch.setenv("MB_MULTI_SUFFIX32", "1")
+    if cap:
+        monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    n_reads, rl = 4_000, 150
+    data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 40 + k + world)
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=%d" % wp, "count", str(fq), "output", ora])
+    nk, npass = multi_count(world, k, wp, data, out)
+    util.assert_same_db(ora, out)
+    assert sum(nk) == n_reads * (rl - k + 1)
+    assert min(npass) == max(npass) and (npass[0] > 1) == bool(cap)
+    assert multi_key_bytes() == [4] * world
+
+
+def test_sim_multi_rank_suffix32_falls_back_for_long_kmers(tmp_path, monkeypatch):
+    """k = 31 does not fit 32 bits below the bin: the switch changes nothing."""
+    monkeypatch.setenv("MB_MULTI_SUFFIX32", "1")
+    data = synth.reads_fastq_bytes(20_000, 2_000, 150, 0.003, 3)
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=31", "wprefix=12", "count", str(fq), "output", ora])
+    multi_count(2, 31, 12, data, out)
+    util.assert_same_db(ora, out)
+    assert multi_key_bytes() == [8, 8]

@@ -15,7 +15,8 @@ from meryl_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, fq_path, out_dir, k, wp):
+def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
+    os.environ.update(env or {})
     import torch.distributed as dist
     from meryl_b200 import dist as mbd
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,7 +38,7 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp):
         c.close()
         dist.barrier()
         with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as fh:
-            fh.write("%d %d %d\n" % (st.nKmers, total, st.nPasses))
+            fh.write("%d %d %d %d\n" % (st.nKmers, total, st.nPasses, st.keyBytes))
     finally:
         dist.destroy_process_group()
 
@@ -64,4 +65,32 @@ def test_multi_gpu_db_bit_exact(tmp_path, world, k):
         os.remove(p)
     assert all(s[1] == n_reads * (L - k + 1) for s in stats)
     assert sum(s[0] for s in stats) == n_reads * (L - k + 1)
+    util.assert_same_db(ora, out)
+
+
+@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental path: MB_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("world,cap", [(2, 0), (2, 700_000), (8, 0)])
+def test_multi_gpu_suffix32_db_bit_exact(tmp_path, world, cap):
+    """MB_MULTI_SUFFIX32=1: u32 suffix keys routed by prefix bin (one NCCL message per bin and peer); emulator twin:
+    tests/test_cusim_multi.py::test_sim_multi_rank_suffix32."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    n_reads, L, k = 60_000, 150, 21
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(200_000, n_reads, L, 0.003, 91))
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    os.makedirs(out)
+    env = {"MB_MULTI_SUFFIX32": "1"}
+    if cap:
+        env["MB_MAX_PASS_KEYS"] = str(cap)
+    port = 29600 + (os.getpid() + world * 11 + cap) % 300
+    mp.spawn(_worker, args=(world, port, str(fq), out, k, 12, env), nprocs=world, join=True)
+    for r in range(world):
+        p = os.path.join(out, "rank%d.txt" % r)
+        st = [int(x) for x in open(p).read().split()]
+        os.remove(p)
+        assert st[1] == n_reads * (L - k + 1) and st[3] == 4 and (st[2] > 1) == bool(cap)
     util.assert_same_db(ora, out)
