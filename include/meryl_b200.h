@@ -101,6 +101,9 @@ typedef struct mb_stats {
   uint32_t sortPasses;      /*  onesweep digit passes per key                              */
   uint32_t keyBytes;        /*  8 (k<=32) or 16                                            */
   uint64_t sortLaunchKeys;  /*  sum over onesweep launches of keys moved                   */
+  uint32_t nBatches;        /*  count batches (1 unless the packed reads outgrew the device: merylBlockWriter::finishBatch /
+                             *  mergeBatches, src/utility/src/kmers-v1/kmers-writer-block.C:172-386)  */
+  float    msMerge;         /*  decode + merge + encode of the batches (0 for one batch)   */
 } mb_stats;
 
 /*  Thread-local message of the last failing call on this thread.  */

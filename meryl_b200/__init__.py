@@ -49,7 +49,8 @@ class Stats(ctypes.Structure):
                 ("msPack", ctypes.c_float), ("msHistogram", ctypes.c_float), ("msExtract", ctypes.c_float),
                 ("msSortHist", ctypes.c_float), ("msSort", ctypes.c_float), ("msCount", ctypes.c_float),
                 ("msEncode", ctypes.c_float), ("msExchange", ctypes.c_float), ("msTotal", ctypes.c_float),
-                ("sortPasses", ctypes.c_uint32), ("keyBytes", ctypes.c_uint32), ("sortLaunchKeys", ctypes.c_uint64)]
+                ("sortPasses", ctypes.c_uint32), ("keyBytes", ctypes.c_uint32), ("sortLaunchKeys", ctypes.c_uint64),
+                ("nBatches", ctypes.c_uint32), ("msMerge", ctypes.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

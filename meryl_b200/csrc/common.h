@@ -93,3 +93,24 @@ struct MbDbImages {
 void mb_build_master_index(u32 k, u32 wPrefix, const MbHistogram &h, std::vector<uint8_t> &out);
 int  mb_write_db_dir(const MbDbImages &db, const char *dir, bool writeMaster);
 void mb_file_name(char *out, size_t cap, const char *dir, u32 file, bool isIndex);
+
+//  ---- decode / merge / encode pipeline (union.cu) with explicit endpoints ----------------------
+//  The set operations read directories and write a directory (mb_set_operation); the merge of count batches
+//  (merylBlockWriter::mergeBatches, src/utility/src/kmers-v1/kmers-writer-block.C:221-386) reads the batches' images from
+//  host memory, writes images, keeps the batches' prefix width and the block writer's rules (a block for every prefix),
+//  sums with saturation, and works inside the counting context's device arena.
+#define MB_OP_MERGE_BATCHES 100u          //  internal operator: saturating uint32 sum (kmers-writer-block.C:305-309)
+struct MbMergeEndpoints {
+  const MbDbImages *const *memInputs = nullptr;      //  inputs in host memory instead of directories ...
+  u32          nMem = 0, k = 0, wPrefix = 0;         //  ... all of this k and prefix width
+  MbDbImages  *outImages = nullptr;                  //  output images instead of a directory (data, index; master by the caller)
+  uint8_t     *outBuf = nullptr;                     //  optional caller-owned memory for the data images, appended in file order
+  size_t       outCap = 0, *outUsed = nullptr;
+  MbHistogram *outHist = nullptr;
+  uint8_t     *arena = nullptr;                      //  device arena to work in (NULL: allocate one)
+  size_t       arenaBytes = 0;
+  u32          outPrefix = 12;                       //  kmers-writer.C:52-58: every non-count operation writes prefix 12
+  u32          streamMode = 1;                       //  1: stream writer (blocks of present prefixes), 0: block writer (all prefixes)
+};
+int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir,
+                      int32_t device, uint64_t workspaceBytes, mb_union_stats *st, const MbMergeEndpoints *ends);

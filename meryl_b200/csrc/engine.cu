@@ -94,6 +94,13 @@ struct mb_ctx {
   size_t      outCap     = 0, outUsed = 0;
 
   MbComm     *comm       = nullptr;                  //  multi-GPU (exchange.cu)
+
+  //  Count batches (the reference's finishBatch / mergeBatches, kmers-writer-block.C:172-386): when the packed reads
+  //  reach batchLimit records the store is counted at the next record break, its encoded images are set aside in host
+  //  memory and the store starts again; mb_count merges the batches (union.cu pipeline, saturating sums).
+  std::vector<std::unique_ptr<MbDbImages>> batches;
+  u64         batchLimit = 0;                        //  records; 0 = never
+  bool        closing    = false;
 };
 
 
@@ -186,6 +193,12 @@ static int ensureArena(mb_ctx *c) {
     c->dStage[i] = c->arena + c->arenaBytes - (size_t)(i + 1) * kStageBytes;
   }
   c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
+  //  One batch = as many reads as leave half of the arena to the key buffers of a pass.  Not with several GPUs (every
+  //  rank would have to close its batches together) and not for the kernel-only / debugging forms that keep no images.
+  if (c->cfg.worldSize <= 1 && !(c->cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED)) && !c->stopAfterSort) {
+    c->batchLimit = c->storeLimit / 2 / (MB_STORE_REC_WORDS * 4);
+    if (getenv("MB_MAX_BATCH_BASES")) c->batchLimit = std::max<u64>(1, strtoull(getenv("MB_MAX_BATCH_BASES"), nullptr, 10) / 32);   //  testing knob
+  }
   return MB_OK;
 }
 
@@ -218,7 +231,7 @@ static int flushStage(mb_ctx *c) {
   return MB_OK;
 }
 
-static int appendHost(mb_ctx *c, const char *p, size_t n) {
+static int appendRaw(mb_ctx *c, const char *p, size_t n) {
   MB_TRY(ensureArena(c));
   while (n) {
     size_t room = kStageBytes - c->fill;
@@ -226,6 +239,34 @@ static int appendHost(mb_ctx *c, const char *p, size_t n) {
     const size_t m = n < room ? n : room;
     memcpy(c->hStage[c->cur] + c->fill, p, m);
     c->fill += m;  p += m;  n -= m;
+  }
+  return MB_OK;
+}
+
+static int closeBatch(mb_ctx *c);
+
+static inline bool batchDue(const mb_ctx *c) {
+  return c->batchLimit && !c->closing && c->nRecords + c->fill / 32 >= c->batchLimit;
+}
+
+//  The ingest's append: once a batch is due, the stream is cut after the next record break ('.': no k-mer spans it).
+static int appendHost(mb_ctx *c, const char *p, size_t n) {
+  MB_TRY(ensureArena(c));
+  while (n) {
+    size_t m = n;
+    if (batchDue(c)) {
+      const char *dot = (const char *)memchr(p, '.', n);
+      m = dot ? (size_t)(dot - p) + 1 : n;
+      MB_TRY(appendRaw(c, p, m));
+      if (dot) MB_TRY(closeBatch(c));
+    } else {
+      if (c->batchLimit && !c->closing) {                  //  no further than the point where the batch becomes due
+        const u64 room = (c->batchLimit - (c->nRecords + c->fill / 32)) * 32;
+        if (m > room) m = (size_t)room;
+      }
+      MB_TRY(appendRaw(c, p, m));
+    }
+    p += m;  n -= m;
   }
   return MB_OK;
 }
@@ -264,8 +305,9 @@ static int appendPinnedDirect(mb_ctx *c, const char *&p, uint64_t &n) {
   MB_TRY(flushStage(c));                                 //  stream is at a record boundary: padding is harmless
   MB_CUDA(cudaSetDevice(c->device));
   if (!c->ingestStarted) { c->ingestStarted = true; MB_CUDA(cudaEventRecord(c->evIngest[0], c->stream)); }
+  const char *const p0 = p;
   int i = 0;
-  while (n >= kStageBytes) {
+  while (n >= kStageBytes && !batchDue(c)) {
     const u64 recs = kStageBytes / 32;
     MB_TRY(storeReserve(c, recs));
     MB_CUDA(cudaMemcpyAsync(c->dStage[i], p, kStageBytes, cudaMemcpyHostToDevice, c->stream));
@@ -276,7 +318,7 @@ static int appendPinnedDirect(mb_ctx *c, const char *&p, uint64_t &n) {
     p += kStageBytes;  n -= kStageBytes;  i ^= 1;
   }
   MB_CUDA(cudaStreamSynchronize(c->stream));             //  the caller may touch its buffer when we return
-  c->inRecord = (p[-1] != '.');
+  if (p != p0) c->inRecord = (p[-1] != '.');
   return MB_OK;
 }
 
@@ -284,7 +326,17 @@ extern "C" int mb_add_bases(mb_ctx *c, const char *bases, uint64_t len, int endO
   mb_clear_error();
   if (!c || (!bases && len))  return mb_fail(MB_EINVAL, "mb_add_bases: NULL argument");
   if (c->counted)             return mb_fail(MB_ESTATE, "mb_add_bases: already counted");
-  MB_TRY(appendPinnedDirect(c, bases, len));
+  for (;;) {
+    MB_TRY(appendPinnedDirect(c, bases, len));            //  stops early when a batch is due
+    if (!len || !batchDue(c)) break;
+    //  up to and including the next record break through the staged path: that closes the batch
+    const char *dot = (const char *)memchr(bases, '.', len);
+    const size_t head = dot ? (size_t)(dot - bases) + 1 : (size_t)len;
+    MB_TRY(appendHost(c, bases, head));
+    bases += head;  len -= head;
+    c->inRecord = (dot == nullptr);
+    if (!dot) break;
+  }
   MB_TRY(appendHost(c, bases, len));
   if (len) c->inRecord = (bases[len - 1] != '.');
   if (endOfSequence) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
@@ -300,6 +352,7 @@ extern "C" int mb_add_bases_device(mb_ctx *c, const char *dBases, uint64_t len) 
   //  A device chunk holds whole records: the stream is padded to a record boundary before and after.
   if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
   MB_TRY(flushStage(c));
+  if (batchDue(c)) MB_TRY(closeBatch(c));                 //  (a device chunk holds whole records)
   const u64 recs = (len + 31) / 32;
   MB_TRY(storeReserve(c, recs));
   MB_CUDA(cudaSetDevice(c->device));
@@ -463,7 +516,7 @@ static int runCount(mb_ctx *c) {
   tAll.start(s);
 
   //  ---- finish the ingest ------------------------------------------------------------------
-  if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
+  if (c->inRecord) { const char dot = '.'; MB_TRY(appendRaw(c, &dot, 1)); c->inRecord = false; }
   MB_TRY(flushStage(c));
   MB_TRY(storeReserve(c, 0));
   if (c->ingestStarted) {                              //  device span of the ingest: first chunk queued -> last chunk packed
@@ -1133,11 +1186,62 @@ extern "C" int mb_set_output_buffer(mb_ctx *c, void *hostBuf, uint64_t bytes) {
   return MB_OK;
 }
 
+//  Count what the store holds as one batch, set its images aside, start the store again (finishBatch).
+static int closeBatch(mb_ctx *c) {
+  const mb_stats prev = c->st;
+  uint8_t *const ob = c->outBuf;
+  const bool inRecord = c->inRecord;
+  c->outBuf = nullptr;  c->inRecord = false;  c->closing = true;     //  a batch's images live in their own vectors
+  c->st.nBases = 0;  c->st.nKmers = 0;  c->st.nPasses = 0;  c->st.msPack = 0;  c->st.msTotal = 0;
+  const int rc = runCount(c);
+  c->outBuf = ob;  c->inRecord = inRecord;  c->closing = false;
+  if (rc != MB_OK) return rc;
+  //  (the other statistics are sums already)
+  c->st.nBases += prev.nBases;  c->st.nKmers += prev.nKmers;  c->st.nPasses += prev.nPasses;
+  c->st.msPack += prev.msPack;  c->st.msTotal += prev.msTotal;
+  c->st.nBatches = prev.nBatches + 1;
+  std::unique_ptr<MbDbImages> b(new MbDbImages());
+  for (u32 f = 0; f < 64; f++) {
+    b->dataVec[f] = std::move(c->db.dataVec[f]);  b->dataLen[f] = c->db.dataLen[f];  b->dataPtr[f] = b->dataVec[f].data();
+    b->index[f]   = std::move(c->db.index[f]);    b->owned[f] = true;
+    c->db.dataVec[f].clear();  c->db.dataLen[f] = 0;  c->db.dataPtr[f] = nullptr;  c->db.index[f].clear();
+  }
+  c->batches.push_back(std::move(b));
+  c->nRecords = 0;  c->ingestStarted = false;  c->counted = false;
+  return MB_OK;
+}
+
+//  mergeBatches: the batches' blocks are decoded, merged with saturating sums and encoded again with the block writer's
+//  rules, file group by file group, inside this context's arena (the read store is not needed any more).
+static int mergeBatches(mb_ctx *c) {
+  std::vector<const MbDbImages *> in;
+  for (auto &b : c->batches) in.push_back(b.get());
+  MbMergeEndpoints E;
+  E.memInputs = in.data();  E.nMem = (u32)in.size();  E.k = c->cfg.k;  E.wPrefix = c->cfg.wPrefix;
+  E.outImages = &c->db;  E.outBuf = c->outBuf;  E.outCap = c->outCap;  E.outUsed = &c->outUsed;  E.outHist = &c->hist;
+  E.arena = c->arena;  E.arenaBytes = c->arenaBytes;
+  E.outPrefix = c->cfg.wPrefix;  E.streamMode = 0;
+  c->outUsed = 0;
+  mb_union_stats us;
+  MB_TRY(mb_merge_pipeline(MB_OP_MERGE_BATCHES, 0, nullptr, 0, nullptr, c->device, 0, &us, &E));
+  c->batches.clear();
+  mb_build_master_index(c->cfg.k, c->cfg.wPrefix, c->hist, c->db.master);
+  c->st.nUnique = c->hist.nUnique;  c->st.nDistinct = c->hist.nDistinct;  c->st.nTotal = c->hist.nTotal;
+  c->st.dbBytes = c->db.master.size();
+  for (u32 f = 0; f < 64; f++) c->st.dbBytes += c->db.dataLen[f] + c->db.index[f].size();
+  c->st.nLaunches += us.nLaunches;  c->st.h2dBytes += us.h2dBytes;  c->st.d2hBytes += us.d2hBytes;
+  c->st.msMerge = us.msTotal;  c->st.msTotal += us.msTotal;
+  c->counted = true;
+  return MB_OK;
+}
+
 extern "C" int mb_count(mb_ctx *c) {
   mb_clear_error();
   if (!c)          return mb_fail(MB_EINVAL, "mb_count: NULL context");
   if (c->counted)  return mb_fail(MB_ESTATE, "mb_count: already counted");
-  return runCount(c);
+  if (c->batches.empty()) { MB_TRY(runCount(c)); c->st.nBatches = 1; return MB_OK; }
+  if (c->nRecords || c->fill || c->inRecord) MB_TRY(closeBatch(c));        //  the last batch
+  return mergeBatches(c);
 }
 
 

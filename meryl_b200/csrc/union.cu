@@ -216,7 +216,7 @@ __device__ __forceinline__ u32 value_rule(u32 op, u64 param, u32 a) {
 __device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u32 &v) {
   switch (r.op) {
     case MB_OP_UNION:        v = r.firstRaw ? 1u : va;  return true;
-    case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM:
+    case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM: case MB_OP_MERGE_BATCHES:
     case MB_OP_SUBTRACT:  case MB_OP_DIFFERENCE: case MB_OP_SYMMETRIC_DIFFERENCE:
                              v = va;  return true;
     case MB_OP_INTERSECT: case MB_OP_INTERSECT_MIN: case MB_OP_INTERSECT_MAX: case MB_OP_INTERSECT_SUM:
@@ -227,7 +227,7 @@ __device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u32 &v) 
 __device__ __forceinline__ bool rule_only_b(const MergeRule &r, u32 vb, u32 &v) {
   switch (r.op) {
     case MB_OP_UNION:        v = 1u;  return true;
-    case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM: case MB_OP_SYMMETRIC_DIFFERENCE:
+    case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM: case MB_OP_SYMMETRIC_DIFFERENCE: case MB_OP_MERGE_BATCHES:
                              v = vb;  return true;
     default:                 return false;
   }
@@ -239,6 +239,7 @@ __device__ __forceinline__ bool rule_both(const MergeRule &r, u32 va, u32 vb, u3
     case MB_OP_UNION_MAX: case MB_OP_INTERSECT_MAX:   v = va < vb ? vb : va;  return true;
     case MB_OP_UNION_SUM: case MB_OP_INTERSECT_SUM:   v = va + vb;            return true;
     case MB_OP_INTERSECT:      v = va;  return true;
+    case MB_OP_MERGE_BATCHES:  v = va + vb;  if (v < vb) v = ~0u;  return true;     //  kmers-writer-block.C:305-309: saturates
     case MB_OP_SUBTRACT:       v = va - vb;  return va > vb;
     default:                   return false;               //  difference, symmetric-difference
   }
@@ -425,6 +426,7 @@ struct FileJob {                                            //  one input data f
 
 struct InputDb {
   std::string dir;
+  const MbDbImages *mem = nullptr;                          //  instead of a directory: images in host memory (count batches)
   u32 k = 0, wPrefix = 0, wSuffix = 0;
   u64 fileBytes[64] = { 0 };                                //  .merylData sizes
   u64 fileKmers[64] = { 0 };                                //  from the per-file block indexes
@@ -462,6 +464,17 @@ int openDb(const char *dir, InputDb &db) {
   return MB_OK;
 }
 
+int openMem(const MbDbImages *img, u32 k, u32 wPrefix, InputDb &db) {
+  db.dir = "(batch in memory)";  db.mem = img;
+  db.k = k;  db.wPrefix = wPrefix;  db.wSuffix = 2 * k - wPrefix;
+  for (u32 f = 0; f < 64; f++) {
+    db.fileBytes[f] = img->dataLen[f];
+    const std::vector<uint8_t> &ix = img->index[f];
+    for (size_t i = 0; i + 24 <= ix.size(); i += 24) { u64 nk; memcpy(&nk, ix.data() + i + 16, 8); db.fileKmers[f] += nk; }
+  }
+  return MB_OK;
+}
+
 struct Carve {
   uint8_t *base; size_t size, off = 0;
   Carve(uint8_t *b, size_t s) : base(b), size(s) {}
@@ -489,7 +502,9 @@ extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const c
 }
 
 static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
-                            uint64_t workspaceBytes, mb_union_stats *stOut);
+                            uint64_t workspaceBytes, mb_union_stats *stOut) {
+  return mb_merge_pipeline(op, param, inDirs, nInputs, outDir, device, workspaceBytes, stOut, nullptr);
+}
 
 extern "C" int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                                 uint64_t workspaceBytes, mb_union_stats *stOut) {
@@ -505,10 +520,13 @@ extern "C" int mb_value_operation(uint32_t op, uint64_t param, const char *inDir
   return setOperationImpl(op, param, &inDir, 1, outDir, device, workspaceBytes, stOut);
 }
 
-static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
-                            uint64_t workspaceBytes, mb_union_stats *stOut) {
+int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
+                      uint64_t workspaceBytes, mb_union_stats *stOut, const MbMergeEndpoints *ends) {
   mb_clear_error();
-  if (!inDirs || nInputs == 0 || !outDir) return mb_fail(MB_EINVAL, "mb_set_operation: NULL argument");
+  MbMergeEndpoints dflt;
+  const MbMergeEndpoints &E = ends ? *ends : dflt;
+  if (E.memInputs) nInputs = E.nMem;
+  if ((!inDirs && !E.memInputs) || nInputs == 0 || (!outDir && !E.outImages)) return mb_fail(MB_EINVAL, "mb_set_operation: NULL argument");
   if (op == MB_OP_SYMMETRIC_DIFFERENCE && nInputs > 2)
     return mb_fail(MB_EINVAL, "symmetric-difference of more than two databases is not implemented (it is not a left fold)");
   int nDev = 0;
@@ -517,13 +535,15 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
 
   std::vector<InputDb> in(nInputs);
   for (u32 i = 0; i < nInputs; i++) {
+    if (E.memInputs) { MB_TRY(openMem(E.memInputs[i], E.k, E.wPrefix, in[i])); continue; }
     if (!inDirs[i]) return mb_fail(MB_EINVAL, "mb_union_sum: NULL input");
     MB_TRY(openDb(inDirs[i], in[i]));
     if (in[i].k != in[0].k) return mb_fail(MB_EINVAL, "k-mer sizes differ: '%s' has k=%u, '%s' has k=%u", inDirs[0], in[0].k, inDirs[i], in[i].k);
   }
   const u32 k = in[0].k, kw = k <= 32 ? 1 : 2, W = 8 * kw;
-  const u32 wP = 12, wS = 2 * k - wP;                       //  kmers-writer.C:52-58: every non-count operation writes prefix 12
+  const u32 wP = E.outPrefix, wS = 2 * k - wP;
   if (2 * k < wP + 1) return mb_fail(MB_EINVAL, "set operations need k >= 7 (the stream writer's 12-bit prefix)");
+  const u64 blocksPerFile = (u64)1 << (wP - 6);
 
   mb_union_stats st;
   memset(&st, 0, sizeof(st));
@@ -541,6 +561,7 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
     if (device >= 0) MB_UCUDA(cudaSetDevice(device));
     size_t freeB = 0, totalB = 0;
     MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
+    if (E.arena) freeB = E.arenaBytes;
     //  what a group of files needs on the device (upper bound):
     //    raw bytes + block tables | decoded inputs | two merge buffers | encoder (meta, output, sub-block table, index) | big-value list
     auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
@@ -554,7 +575,8 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
           nk   += in[i].fileKmers[f];
         }
       need += 2 * (nk * (W + 4) + 1024);                                    //  merge ping-pong
-      need += nk * ((wS + 34 + 7) / 8 + 1) + (size_t)(f1 - f0) * 64 * 4096 + nk / 64;   //  encoded blocks (every block <= n(b+34) + headers)
+      need += nk * ((wS + 34 + 7) / 8 + 1) + nk / 64;                    //  encoded blocks (every block <= n(b+34) + headers) ...
+      need += (size_t)(f1 - f0) * blocksPerFile * (E.streamMode ? 4096 : 512 + sizeof(MbBlockMeta) + 24 + 16);   //  ... headers, tables
       need += nk / MG_TILE * 16 + nk / MB_HIST_SMALL * 4 + 65536;
       return need;
     };
@@ -567,12 +589,13 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
     }
     if (want > freeB) want = freeB;
     want = want / 256 * 256;
-    if (cudaMalloc((void **)&arena, want) != cudaSuccess) { cudaGetLastError(); arena = nullptr; rc = mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want); goto done; }
+    if (E.arena) { arena = E.arena;  want = E.arenaBytes / 256 * 256; }
+    else if (cudaMalloc((void **)&arena, want) != cudaSuccess) { cudaGetLastError(); arena = nullptr; rc = mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want); goto done; }
     MB_UCUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) { MB_UCUDA(cudaEventCreate(&ev[i])); MB_UCUDA(cudaEventCreate(&evAll[i])); }
     MB_UCUDA(cudaEventRecord(evAll[0], s));
 
-    if (mkdir(outDir, 0777) != 0 && errno != EEXIST) { rc = mb_fail(MB_EIO, "cannot create directory '%s': %s", outDir, strerror(errno)); goto done; }
+    if (outDir && mkdir(outDir, 0777) != 0 && errno != EEXIST) { rc = mb_fail(MB_EIO, "cannot create directory '%s': %s", outDir, strerror(errno)); goto done; }
 
     //  small fixed tables at the bottom of the arena
     Carve top(arena, want);
@@ -623,9 +646,13 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
         char path[4096];
         mb_file_name(path, sizeof(path), in[j.input].dir.c_str(), j.file, false);
         uint8_t *d = hostIn[j.input].data() + j.off;
-        FILE *fp = fopen(path, "rb");
-        if (!fp || (j.bytes && fread(d, 1, j.bytes, fp) != j.bytes)) { j.rc = MB_EIO; j.err = std::string("cannot read '") + path + "'"; if (fp) fclose(fp); return; }
-        fclose(fp);
+        if (in[j.input].mem) {
+          if (j.bytes) memcpy(d, in[j.input].mem->dataPtr[j.file], j.bytes);
+        } else {
+          FILE *fp = fopen(path, "rb");
+          if (!fp || (j.bytes && fread(d, 1, j.bytes, fp) != j.bytes)) { j.rc = MB_EIO; j.err = std::string("cannot read '") + path + "'"; if (fp) fclose(fp); return; }
+          fclose(fp);
+        }
         size_t p = 0;
         while (p < j.bytes) {                                //  walk the containers (stuffedBits-v1.C:117-196)
           u32 nSub = 0;
@@ -734,7 +761,7 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
       MB_UCUDA(cudaEventRecord(ev[0], s));
       const u64 histBigCap = D / MB_HIST_SMALL + 1024;
       u32 *dHistBig = (u32 *)g.take(histBigCap * 4);
-      const u64 nBlocks = (u64)(f1 - f0) * 64;
+      const u64 nBlocks = (u64)(f1 - f0) * blocksPerFile;
       MbBlockMeta *dMeta = (MbBlockMeta *)g.take(nBlocks * sizeof(MbBlockMeta));
       void *dScanTmp     = g.take(mb_encode_scan_tmp_bytes(nBlocks));
       u64  *dIdx         = (u64 *)g.take(nBlocks * 24);
@@ -745,13 +772,14 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
 
       MbEncodeParams ep;
       ep.keys = curK;  ep.runStart = nullptr;  ep.nDistinct = D;  ep.keyWords = kw;  ep.k = k;  ep.wPrefix = wP;
-      ep.blockLo = (u64)f0 * 64;  ep.nBlocks = nBlocks;  ep.counts = curV;  ep.streamMode = 1;
+      ep.blockLo = (u64)f0 * blocksPerFile;  ep.nBlocks = nBlocks;  ep.counts = curV;  ep.streamMode = E.streamMode;
       MB_UCUDA(cudaMemsetAsync(dCtl, 0, 8 * 8, s));
       MB_UCUDA(mb_launch_encode_layout(ep, dMeta, dCtl, dScanTmp, s));
       u64 encTotals[8];
       MB_UCUDA(cudaMemcpyAsync(encTotals, dCtl, sizeof(encTotals), cudaMemcpyDeviceToHost, s));
-      std::vector<MbBlockMeta> meta(nBlocks);
-      MB_UCUDA(cudaMemcpyAsync(meta.data(), dMeta, nBlocks * sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
+      std::vector<MbBlockMeta> meta(f1 - f0);                  //  of the first block of every file of the group
+      for (u32 f = f0; f < f1; f++)
+        MB_UCUDA(cudaMemcpyAsync(&meta[f - f0], dMeta + (u64)(f - f0) * blocksPerFile, sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
       MB_UCUDA(cudaStreamSynchronize(s));
       st.nLaunches += 6;
       if (encTotals[4]) { rc = mb_fail(MB_ENOMEM, "a 12-bit prefix holds more than 16 Mi k-mers; splitting such blocks (kmers-writer-stream.C:131-141) is not implemented"); goto done; }
@@ -772,27 +800,42 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
       { float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msEncode += ms; }
       st.d2hBytes += encTotals[0] + nBlocks * 24;
 
-      {
+      if (E.outImages) {                                       //  images in host memory (merge of count batches)
+        for (u32 f = f0; f < f1; f++) {
+          const u64 byte0 = meta[f - f0].outByte, byte1 = (f + 1 < f1) ? meta[f - f0 + 1].outByte : encTotals[0];
+          const size_t len = (size_t)(byte1 - byte0);
+          MbDbImages &o = *E.outImages;
+          if (E.outBuf) {
+            if (*E.outUsed + len > E.outCap) { rc = mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", f, len, *E.outUsed, E.outCap); goto done; }
+            memcpy(E.outBuf + *E.outUsed, outBytes.data() + byte0, len);
+            o.dataVec[f].clear();  o.dataPtr[f] = E.outBuf + *E.outUsed;  *E.outUsed += len;
+          } else {
+            o.dataVec[f].assign(outBytes.data() + byte0, outBytes.data() + byte1);
+            o.dataPtr[f] = o.dataVec[f].data();
+          }
+          o.dataLen[f] = len;
+          o.index[f].assign(outIdx.data() + (u64)(f - f0) * blocksPerFile * 24, outIdx.data() + (u64)(f - f0 + 1) * blocksPerFile * 24);
+          st.outBytes += len + blocksPerFile * 24;
+        }
+      } else {
         std::vector<int> wrc(f1 - f0, MB_OK);
         std::vector<std::string> werr(f1 - f0);
         parallelFor(f1 - f0, [&](size_t fi) {
           const u32 f = f0 + (u32)fi;
-          const u64 b0 = (u64)fi * 64;
-          const u64 byte0 = meta[b0].outByte, byte1 = (f + 1 < f1) ? meta[b0 + 64].outByte : encTotals[0];
+          const u64 byte0 = meta[fi].outByte, byte1 = (f + 1 < f1) ? meta[fi + 1].outByte : encTotals[0];
           char path[4096];
           for (int isIdx = 0; isIdx < 2; isIdx++) {
             mb_file_name(path, sizeof(path), outDir, f, isIdx != 0);
-            const void  *ptr = isIdx ? (const void *)(outIdx.data() + b0 * 24) : (const void *)(outBytes.data() + byte0);
-            const size_t len = isIdx ? (size_t)64 * 24 : (size_t)(byte1 - byte0);
+            const void  *ptr = isIdx ? (const void *)(outIdx.data() + fi * blocksPerFile * 24) : (const void *)(outBytes.data() + byte0);
+            const size_t len = isIdx ? (size_t)blocksPerFile * 24 : (size_t)(byte1 - byte0);
             FILE *fp = fopen(path, "wb");
             if (!fp || (len && fwrite(ptr, 1, len, fp) != len) || fclose(fp) != 0) { wrc[fi] = MB_EIO; werr[fi] = std::string("cannot write '") + path + "': " + strerror(errno); return; }
           }
         });
         for (u32 f = f0; f < f1; f++) {
           if (wrc[f - f0] != MB_OK) { rc = mb_fail(MB_EIO, "%s", werr[f - f0].c_str()); goto done; }
-          const u64 b0 = (u64)(f - f0) * 64;
-          const u64 byte0 = meta[b0].outByte, byte1 = (f + 1 < f1) ? meta[b0 + 64].outByte : encTotals[0];
-          st.outBytes += byte1 - byte0 + 64 * 24;
+          const u64 byte0 = meta[f - f0].outByte, byte1 = (f + 1 < f1) ? meta[f - f0 + 1].outByte : encTotals[0];
+          st.outBytes += byte1 - byte0 + blocksPerFile * 24;
         }
       }
 
@@ -818,10 +861,13 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
     for (u64 v = 1; v < MB_HIST_SMALL; v++) if (hs[v]) { hist.values.push_back(v); hist.occ.push_back(hs[v]); }
     for (auto &kv : histMap) { hist.values.push_back(kv.first); hist.occ.push_back(kv.second); }
     hist.nUnique = nUnique;  hist.nDistinct = nDistinct;  hist.nTotal = nTotal;
-    std::vector<uint8_t> master;
-    mb_build_master_index(k, wP, hist, master);
-    MB_UTRY(writeFile(std::string(outDir) + "/merylIndex", master.data(), master.size()));
-    st.outBytes += master.size();
+    if (E.outHist) *E.outHist = hist;
+    if (outDir) {
+      std::vector<uint8_t> master;
+      mb_build_master_index(k, wP, hist, master);
+      MB_UTRY(writeFile(std::string(outDir) + "/merylIndex", master.data(), master.size()));
+      st.outBytes += master.size();
+    }
     st.nUnique = nUnique;  st.nDistinct = nDistinct;  st.nTotal = nTotal;
 
     MB_UCUDA(cudaEventRecord(evAll[1], s));
@@ -832,7 +878,7 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
 done:
   for (int i = 0; i < 2; i++) { if (ev[i]) cudaEventDestroy(ev[i]); if (evAll[i]) cudaEventDestroy(evAll[i]); }
   if (s) cudaStreamDestroy(s);
-  if (arena) cudaFree(arena);
+  if (arena && !E.arena) cudaFree(arena);
   if (rc == MB_OK && stOut) *stOut = st;
   return rc;
 }

@@ -169,3 +169,46 @@ def test_sim_parallel_parse_in_the_pipeline(tmp_path, monkeypatch):
     monkeypatch.setenv("MB_PARSE_THREADS", "4")
     monkeypatch.setenv("MB_PARSE_MIN_PIECE", "256")
     _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(5_000, 600, 150, 0.01, 3), "g.fa": synth.fasta_bytes(7, 2_000, 4, width=60, eol=b"\r\n")}, 21, 8)
+
+
+# ---- count batches (W6: merylBlockWriter::finishBatch / mergeBatches, kmers-writer-block.C:172-386) --------------------
+
+@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 12, "count", 150_000), (31, 9, "count-forward", 120_000),
+                                                       (51, 8, "count", 150_000), (8, 6, "count-reverse", 100_000)])
+def test_sim_count_batches(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
+    """Reads that outgrow the device are counted in batches cut at record breaks; the batches' blocks are decoded, merged
+    (saturating sums) and encoded again with the block writer's rules.  MB_MAX_BATCH_BASES makes a small input take that
+    road; the db must be the single-batch db of the oracle, empty blocks and all."""
+    monkeypatch.setenv("MB_MAX_BATCH_BASES", str(batch_bases))
+    reads = synth.reads_fastq_bytes(20_000, 2_000, 150, 0.004, 7 + k)
+    st = _vs_oracle(tmp_path, {"r.fq": reads, "g.fa": synth.fasta_bytes(2, 30_000, k)}, k, w_prefix, op=op)
+    assert st.nBatches >= 3 and st.msMerge >= 0
+    assert st.nKmers == 2_000 * (150 - k + 1) + 2 * (30_000 - k + 1)
+    assert st.nTotal == st.nKmers
+
+
+def test_sim_count_batches_pushed_bases_and_output_buffer(tmp_path, monkeypatch):
+    """The same through mb_add_bases (one long push: the cut falls inside the call) with a caller-owned output buffer."""
+    monkeypatch.setenv("MB_MAX_BATCH_BASES", "80000")
+    rng = np.random.default_rng(11)
+    recs = [synth.random_bases(int(rng.integers(30, 400)), rng).tobytes() for _ in range(1_600)]
+    fa = tmp_path / "r.fa"
+    fa.write_bytes(b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(recs)))
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=21", "wprefix=11", "count", str(fa), "output", ora])
+    stream = b".".join(recs)                                   # work-buffer form; the last record ends with the call
+    buf = np.zeros(32 << 20, dtype=np.uint8)
+    with mb.Counter(21, 11) as c:
+        c.set_output_buffer(buf.ctypes.data, buf.size)
+        c.add_bases(stream[:100_000], end_of_sequence=False)
+        c.add_bases(stream[100_000:], end_of_sequence=True)
+        c.count()
+        st = c.stats()
+        c.write_db(out)
+    util.assert_same_db(ora, out)
+    assert st.nBatches >= 4
+
+
+def test_sim_one_batch_is_the_old_road(tmp_path):
+    st = _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 6_000, 3)}, 21, 10)
+    assert st.nBatches == 1 and st.msMerge == 0
