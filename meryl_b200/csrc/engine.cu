@@ -578,6 +578,22 @@ static int runCount(mb_ctx *c) {
   //  travels and is sorted as the 32 bits below its prefix bin when they fit a word (k <= 21).  Routing is then by bin,
   //  so everybody also learns everybody's per-bin counts.
   const bool want32 = world > 1 && getenv("MB_MULTI_SUFFIX32") != nullptr && 2 * k - binBits <= 32 && !c->stopAfterSort;
+
+  //  Experimental (MB_P2P_SCATTER=1, not the default until it has run on real GPUs): extraction fused with the exchange.
+  //  Every rank maps every other rank's arena (CUDA IPC) and the extraction kernel stores a kept k-mer straight into the
+  //  receive segment of the GPU that owns its file -- the bin's "start" handed to the kernel is the peer address expressed
+  //  as an index relative to the local key buffer, so the kernel itself does not change.  The k-mers cross NVLink tile by
+  //  tile under the extraction; no send buffer is filled and no all-to-all follows.
+  const bool p2p = world > 1 && getenv("MB_P2P_SCATTER") != nullptr;
+  struct PeerMap {
+    MbComm *comm = nullptr;  std::vector<uint8_t *> base;
+    ~PeerMap() { if (comm) mb_comm_close_peer_arenas(comm, base.data()); }
+  } peers;
+  if (p2p) {
+    peers.base.assign(world, nullptr);
+    MB_TRY(mb_comm_open_peer_arenas(c->comm, c->arena, dCtl->allFileCount, peers.base.data(), s));
+    peers.comm = c->comm;
+  }
   std::vector<u64> Cb;                                  //  Cb[r][b]
   std::vector<u64> binTotal;
   if (want32) {
@@ -835,6 +851,49 @@ static int runCount(mb_ctx *c) {
     void *ws = pc.take(sortWs);
     if (!bufA || !bufB || !ws) return mb_fail(MB_ENOMEM, "internal: pass %zu does not fit the arena", pi);
 
+    if (p2p) {
+      //  Everybody says where this pass's receive buffer lies in its arena.  The all-gather is also the barrier after
+      //  which no rank still reads the buffers of the previous pass.
+      std::vector<u64> recvOff(world);
+      const u64 myOff = (u64)((uint8_t *)bufB - c->arena);
+      tStage.start(s);
+      MB_CUDA(cudaMemcpyAsync(dCtl->fileCount, &myOff, 8, cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 1, s));
+      MB_CUDA(cudaMemcpyAsync(recvOff.data(), dCtl->allFileCount, (size_t)world * 8, cudaMemcpyDeviceToHost, s));
+      tStage.stop(s);
+      MB_CUDA(cudaStreamSynchronize(s));
+      c->st.msExchange += tStage.ms();
+      //  bin b of file f goes to owner(f): into the segment of its unit (file; bin for suffix keys), behind the chunks of
+      //  the ranks before me (and, inside my chunk of a file, behind my lower bins)
+      std::vector<u64> at(world, 0);                      //  keys laid out so far in every destination's buffer
+      bool aligned = true;
+      auto target = [&](u32 d, u64 elem) -> u64 {
+        const uint8_t *t = peers.base[d] + recvOff[d] + elem * keyBytes;
+        const long long diff = (long long)((uintptr_t)t - (uintptr_t)bufA);
+        if (diff % (long long)keyBytes) aligned = false;
+        return (u64)(diff / (long long)keyBytes);          //  two's complement: bufA + index * keyBytes == t (mod 2^64)
+      };
+      for (u32 f = P.binLo / binsPerFile; f < P.binHi / binsPerFile; f++) {
+        const u32 d = mb_file_owner(f, world);
+        if (suffix32) {
+          for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) {
+            u64 before = 0;
+            for (u32 r = 0; r < me; r++) before += Cb[(size_t)r * nBins + b];
+            binStart[b] = target(d, at[d] + before);
+            at[d] += binTotal[b];
+          }
+        } else {
+          u64 base = at[d];
+          for (u32 r = 0; r < me; r++) base += C[(size_t)r * 64 + f];
+          for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) { binStart[b] = target(d, base); base += binCount[b]; }
+          at[d] += fileTotal[f];
+        }
+      }
+      if (getenv("MB_TRACE")) fprintf(stderr, "[meryl-b200] rank %u pass %zu: peer scatter, %llu keys out, %llu keys in, %u-byte keys\n", me, pi, (u64)P.nLocal, (u64)n, keyBytes);
+      if (!aligned) return mb_fail(MB_ESTATE, "internal: a peer arena is not aligned to the key size");
+      if (at[me] != n) return mb_fail(MB_ESTATE, "internal: receive layout of pass %zu holds %llu keys, expected %llu", pi, (u64)at[me], (u64)n);
+    }
+
     Carver ec((uint8_t *)pc.base + alignUp(pc.off), pc.left());       //  encode region: everything that is left
 
     MB_CUDA(cudaMemcpyAsync(dCtl->binStart, binStart.data(), (nBins + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
@@ -855,7 +914,15 @@ static int runCount(mb_ctx *c) {
 
     //  ---- multi-GPU: route k-mers to the owners of their files ----------------------------------
     void *unsorted = bufA, *spare = bufB;
-    if (world > 1) {
+    if (p2p) {
+      //  the k-mers are where they belong already; wait until every rank's extraction has finished
+      tStage.start(s);
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 1, s));
+      tStage.stop(s);
+      MB_CUDA(cudaStreamSynchronize(s));
+      c->st.msExchange += tStage.ms();
+      unsorted = bufB;  spare = bufA;
+    } else if (world > 1) {
       const u32 fLo = P.binLo / binsPerFile, fHi = P.binHi / binsPerFile;
       std::vector<u64> sendStart(fHi - fLo);
       for (u32 f = fLo; f < fHi; f++) sendStart[f - fLo] = binStart[f * binsPerFile];
@@ -1100,6 +1167,14 @@ static int runCount(mb_ctx *c) {
   }
   cudaEventDestroy(evAfterHist);
   tSortHist.destroy();
+
+  if (p2p) {
+    //  Unmap the peers' arenas, then a barrier: nobody returns (and later frees its arena) while somebody still maps it.
+    mb_comm_close_peer_arenas(c->comm, peers.base.data());
+    peers.comm = nullptr;
+    MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 1, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+  }
 
   if (!c->stopAfterSort) {
     //  ---- value histogram -> host ------------------------------------------------------------

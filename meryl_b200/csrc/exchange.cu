@@ -20,6 +20,7 @@
 
 #include <dlfcn.h>
 #include <string.h>
+#include <vector>
 
 #include "common.h"
 #include "engine.h"
@@ -279,6 +280,57 @@ int mb_comm_exchange_suffixes(MbComm *m, const void *sendBuf, void *recvBuf, u32
     }
   }
   MB_NCCL(g_nccl.GroupEnd());
+  return MB_OK;
+}
+
+//  ---- extraction fused with the exchange: peer memory over NVLink -------------------------------------------------
+//  Every rank's arena is mapped into every other rank's address space (CUDA IPC; one process per GPU), so the
+//  extraction kernel of a pass can store a kept k-mer straight into the receive segment of the GPU that owns its file:
+//  the k-mers cross NVLink tile by tile while the extraction runs, no send buffer and no separate all-to-all.
+//  dScratch: device memory for (world + 1) * 8 u64.  peerBase[r] = rank r's arena in this process (own arena for r == me).
+int mb_comm_open_peer_arenas(MbComm *m, void *myArena, u64 *dScratch, uint8_t **peerBase, cudaStream_t s) {
+  const u32 me = m->rank, world = m->world;
+#ifdef MB_CUSIM
+  {
+    SimHub::Args a;  a.a = myArena;  a.b = (void *)peerBase;
+    return simCollective(m, a, [&]() {
+      for (u32 dst = 0; dst < world; dst++)
+        for (u32 src = 0; src < world; src++) ((uint8_t **)g_hub.args[dst].b)[src] = (uint8_t *)g_hub.args[src].a;
+    });
+  }
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t mine;
+  MB_CUDA(cudaIpcGetMemHandle(&mine, myArena));
+  std::vector<cudaIpcMemHandle_t> all(world);
+  MB_CUDA(cudaMemcpyAsync(dScratch, &mine, 64, cudaMemcpyHostToDevice, s));
+  MB_TRY(mb_comm_allgather_u64(m, dScratch, dScratch + 8, 8, s));
+  MB_CUDA(cudaMemcpyAsync(all.data(), dScratch + 8, (size_t)world * 64, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  for (u32 r = 0; r < world; r++) peerBase[r] = nullptr;
+  for (u32 r = 0; r < world; r++) {
+    if (r == me) { peerBase[r] = (uint8_t *)myArena; continue; }
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      mb_comm_close_peer_arenas(m, peerBase);
+      return mb_fail(MB_ECOMM, "cannot map the arena of rank %u into rank %u: %s", r, me, cudaGetErrorString(e));
+    }
+    peerBase[r] = (uint8_t *)p;
+  }
+  return MB_OK;
+#endif
+}
+
+//  Unmap the peers' arenas (call after a collective that follows the last use, and before any rank frees its arena).
+int mb_comm_close_peer_arenas(MbComm *m, uint8_t **peerBase) {
+#ifndef MB_CUSIM
+  for (u32 r = 0; r < m->world; r++)
+    if (r != m->rank && peerBase[r]) { cudaIpcCloseMemHandle(peerBase[r]); peerBase[r] = nullptr; }
+#else
+  (void)m;  (void)peerBase;
+#endif
   return MB_OK;
 }
 

@@ -117,3 +117,28 @@ def test_sim_multi_rank_suffix32_falls_back_for_long_kmers(tmp_path, monkeypatch
     multi_count(2, 31, 12, data, out)
     util.assert_same_db(ora, out)
     assert multi_key_bytes() == [8, 8]
+
+
+@pytest.mark.parametrize("world,k,wp,cap,s32", [(2, 21, 12, 0, False), (4, 31, 12, 0, False), (8, 51, 10, 0, False), (2, 21, 12, 60_000, False),
+                                                (4, 21, 12, 0, True), (8, 21, 14, 0, True), (2, 19, 12, 50_000, True)])
+def test_sim_multi_rank_p2p_scatter(tmp_path, monkeypatch, world, k, wp, cap, s32):
+    """MB_P2P_SCATTER=1 (experimental): extraction fused with the exchange -- every rank maps the other ranks' arenas and
+    the extraction kernel stores each kept k-mer straight into the receive segment of the GPU that owns its file (in the
+    emulator the ranks share one address space, so the 'mapping' is the pointer itself).  All key forms, with and without
+    several passes, with and without the u32 suffix form; same db bytes as the oracle."""
+    monkeypatch.setenv("MB_P2P_SCATTER", "1")
+    if s32:
+        monkeypatch.setenv("MB_MULTI_SUFFIX32", "1")
+    if cap:
+        monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    n_reads, rl = 3_000, 150
+    data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 60 + k + world)
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=%d" % wp, "count", str(fq), "output", ora])
+    nk, npass = multi_count(world, k, wp, data, out)
+    util.assert_same_db(ora, out)
+    assert sum(nk) == n_reads * (rl - k + 1)
+    assert (npass[0] > 1) == bool(cap)
+    assert multi_key_bytes() == [4 if s32 else (8 if k <= 32 else 16)] * world

@@ -94,3 +94,34 @@ def test_multi_gpu_suffix32_db_bit_exact(tmp_path, world, cap):
         os.remove(p)
         assert st[1] == n_reads * (L - k + 1) and st[3] == 4 and (st[2] > 1) == bool(cap)
     util.assert_same_db(ora, out)
+
+
+@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental path: MB_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("world,k,cap,s32", [(2, 21, 0, False), (2, 51, 0, False), (2, 21, 700_000, False), (2, 21, 0, True), (8, 21, 0, True), (8, 31, 0, False)])
+def test_multi_gpu_p2p_scatter_db_bit_exact(tmp_path, world, k, cap, s32):
+    """MB_P2P_SCATTER=1: the extraction kernel stores every kept k-mer straight into the owning GPU's receive segment
+    (peer arenas mapped with CUDA IPC, stores over NVLink); no all-to-all.  Emulator twin:
+    tests/test_cusim_multi.py::test_sim_multi_rank_p2p_scatter."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    n_reads, L = 60_000, 150
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(200_000, n_reads, L, 0.003, 33 + k))
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    os.makedirs(out)
+    env = {"MB_P2P_SCATTER": "1"}
+    if s32:
+        env["MB_MULTI_SUFFIX32"] = "1"
+    if cap:
+        env["MB_MAX_PASS_KEYS"] = str(cap)
+    port = 29600 + (os.getpid() + world * 13 + k + cap + int(s32)) % 300
+    mp.spawn(_worker, args=(world, port, str(fq), out, k, 12, env), nprocs=world, join=True)
+    for r in range(world):
+        p = os.path.join(out, "rank%d.txt" % r)
+        st = [int(x) for x in open(p).read().split()]
+        os.remove(p)
+        assert st[1] == n_reads * (L - k + 1) and st[3] == (4 if s32 else 8 if k <= 32 else 16) and (st[2] > 1) == bool(cap)
+    util.assert_same_db(ora, out)
