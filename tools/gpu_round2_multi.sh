@@ -1,0 +1,25 @@
+#!/bin/bash
+#  Multi-GPU call of the next round: the two multi-GPU forms written without GPUs at hand (u32 suffix keys routed by bin,
+#  extraction fused with the exchange over peer memory) get their parity tests and an A/B against the default
+#  (u64 keys, NCCL all-to-all), at N GPUs of one box.
+#  usage (from the repo root):  gpurun --gpus 8 --timeout 1500 -- 'bash tools/gpu_round2_multi.sh 8'
+set -u
+N=${1:-8}
+OUT=gpurun_out
+mkdir -p $OUT
+exec > >(tee $OUT/round2_multi_$N.log) 2>&1
+date; nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -$N
+echo "== a. multi-GPU parity, experimental forms included";  date +%T
+MB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -5
+run() {   #  name, env...
+  local name=$1; shift
+  echo "== bench $name";  date +%T
+  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
+      bench.py --gpus $N --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_${N}gpu_$name.json 2> $OUT/bench_${N}gpu_$name.err
+  cut -c1-1800 $OUT/bench_${N}gpu_$name.json; tail -3 $OUT/bench_${N}gpu_$name.err
+}
+run default     MB_NOP=1
+run suffix32    MB_MULTI_SUFFIX32=1
+run p2p         MB_P2P_SCATTER=1
+run suffix32p2p MB_MULTI_SUFFIX32=1 MB_P2P_SCATTER=1
+date
