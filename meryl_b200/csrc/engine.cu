@@ -747,39 +747,55 @@ static int runCount(mb_ctx *c) {
       }
     }
     const u32 slots = 64 / world;
-    auto planSlots = [&](u64 cap, bool s32) -> u32 {
-      for (u32 tryQ = slots; tryQ >= 1; tryQ--) {
-        if (slots % tryQ) continue;
-        bool ok = true;
-        for (u32 p0 = 0; p0 < slots && ok; p0 += tryQ)
-          for (u32 r = 0; r < world && ok; r++) {
-            u64 snd = 0, rcv = 0;
-            for (u32 f = p0 * world; f < (p0 + tryQ) * world; f++) {
-              snd += C[(size_t)r * 64 + f];
-              if (mb_file_owner(f, world) == r) rcv += fileTotal[f];
-            }
-            if (snd > cap || rcv > cap) ok = false;
-            if (ok && s32) {                               //  every owned bin must fit a count group (see the groups below)
-              const u64 gcap = std::min<u64>(std::max(snd, rcv) / 2 + 8, (u64)(enc32 / 3 / 8));
-              for (u32 f = p0 * world; f < (p0 + tryQ) * world && ok; f++)
-                if (mb_file_owner(f, world) == r)
-                  for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++)
-                    if (binTotal[b] > gcap || binTotal[b] >= ((u64)1 << 32)) ok = false;
-            }
+    //  Greedy: a pass takes consecutive slots while every rank still fits what it sends and what it receives.  (Canonical
+    //  k-mers are skewed towards the low files, so the passes get longer towards the end.)  Every rank knows the whole count
+    //  matrix and the agreed capacities, so every rank cuts at the same slots.
+    typedef std::vector<std::pair<u32, u32>> SlotRanges;
+    auto planSlots = [&](u64 cap, bool s32, SlotRanges &out) -> bool {
+      out.clear();
+      std::vector<u64> snd(world), rcv(world);
+      auto add = [&](u32 slot, std::vector<u64> &sn, std::vector<u64> &rc) {
+        for (u32 f = slot * world; f < (slot + 1) * world; f++) {
+          for (u32 r = 0; r < world; r++) sn[r] += C[(size_t)r * 64 + f];
+          rc[mb_file_owner(f, world)] += fileTotal[f];
+        }
+      };
+      auto fits = [&](const std::vector<u64> &sn, const std::vector<u64> &rc) {
+        for (u32 r = 0; r < world; r++) if (sn[r] > cap || rc[r] > cap) return false;
+        return true;
+      };
+      u32 p0 = 0;
+      while (p0 < slots) {
+        std::fill(snd.begin(), snd.end(), 0);  std::fill(rcv.begin(), rcv.end(), 0);
+        add(p0, snd, rcv);
+        if (!fits(snd, rcv)) return false;                 //  a single slot is too much
+        u32 p1 = p0 + 1;
+        while (p1 < slots) {
+          std::vector<u64> sn(snd), rc(rcv);
+          add(p1, sn, rc);
+          if (!fits(sn, rc)) break;
+          snd.swap(sn);  rcv.swap(rc);  p1++;
+        }
+        if (s32)                                            //  every owned bin must fit a count group (see the groups below)
+          for (u32 f = p0 * world; f < p1 * world; f++) {
+            const u32 r = mb_file_owner(f, world);
+            const u64 gcap = std::min<u64>(std::max(snd[r], rcv[r]) / 2 + 8, (u64)(enc32 / 3 / 8));
+            for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++)
+              if (binTotal[b] > gcap || binTotal[b] >= ((u64)1 << 32)) return false;
           }
-        if (ok) return tryQ;
+        out.push_back(std::make_pair(p0, p1));
+        p0 = p1;
       }
-      return 0;
+      return true;
     };
-    u32 q = 0;
-    if (want32 && cap32 > 0 && (q = planSlots(cap32, true)) != 0) suffix32 = true;
-    if (q == 0) q = planSlots(capKeys, false);
-    sortBits = suffix32 ? 2 * k - binBits : 2 * k - 6;
-    if (q == 0)
+    SlotRanges ranges;
+    if (want32 && cap32 > 0 && planSlots(cap32, true, ranges)) suffix32 = true;
+    else if (!planSlots(capKeys, false, ranges))
       return mb_fail(MB_ENOMEM, "a single data file's k-mers do not fit one of the %u devices (capacity %llu keys); use more GPUs", world, (u64)capKeys);
-    for (u32 p0 = 0; p0 < slots; p0 += q) {
+    sortBits = suffix32 ? 2 * k - binBits : 2 * k - 6;
+    for (const auto &rg : ranges) {
       Pass P;
-      const u32 fLo = p0 * world, fHi = (p0 + q) * world;
+      const u32 fLo = rg.first * world, fHi = rg.second * world;
       P.binLo = fLo * binsPerFile;  P.binHi = fHi * binsPerFile;
       for (u32 f = fLo; f < fHi; f++) {
         P.nLocal += C[(size_t)me * 64 + f];
