@@ -24,6 +24,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <sys/stat.h>
 #include <algorithm>
 #include <atomic>
@@ -55,11 +57,22 @@ struct SubReader {
   u64        cw, cv;                    //  one-word cache: cv == cur[cw] (every word is fetched from memory once)
   bool       bad;
 
-  __device__ __forceinline__ void open(const u64 *container) {
-    nSub = (u32)container[1];
+  //  bytesLeft: what the buffer holds from the container's first byte on; a container that claims more is bad
+  //  (its place comes from the block index, nobody has walked the bytes before).
+  __device__ __forceinline__ void open(const u64 *container, u64 bytesLeft) {
+    nSub = bytesLeft >= 16 ? (u32)container[1] : 0;
     len  = container + 2 + nSub;
     cur  = len + nSub;
-    blk  = 0;  pos = 0;  bad = (nSub == 0);
+    blk  = 0;  pos = 0;  bad = (nSub == 0) || (16 + 16 * (u64)nSub > bytesLeft);
+    if (!bad) {
+      u64 words = 0;
+      for (u32 i = 0; i < nSub; i++) {
+        const u64 w = (len[i] + 63) >> 6;
+        if (w > (bytesLeft >> 3)) { bad = true; break; }
+        words += w;
+      }
+      if (!bad && 16 + 16 * (u64)nSub + 8 * words > bytesLeft) bad = true;
+    }
     lenCur = bad ? 0 : len[0];
     cw = ~0ull;  cv = 0;
   }
@@ -121,14 +134,17 @@ __device__ __forceinline__ void store_kmer(ulonglong2 *out, u64 i, u64 prefix, u
 
 template <int KW>
 __global__ void __launch_bounds__(128)
-decode_kernel(const uint8_t *__restrict__ data, const UnionBlock *__restrict__ tab, u64 nBlocks, u32 wSuffix,
+decode_kernel(const uint8_t *__restrict__ data, u64 dataBytes, const UnionBlock *__restrict__ tab, u64 nBlocks, u32 wSuffix,
               typename KeyT<KW>::type *__restrict__ keys, u32 *__restrict__ vals, u64 capacity, u32 *__restrict__ err) {
   const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nBlocks) return;
-  const u64 *c = (const u64 *)(data + tab[b].byteOff);
+  const u64 at = tab[b].byteOff;
+  if (at >= dataBytes || (at & 7)) { atomicOr(err, 1u); return; }
+  const u64 *c = (const u64 *)(data + at);
   SubReader r;
-  r.open(c);
+  r.open(c, dataBytes - at);
   if (r.bad) { atomicOr(err, 1u); return; }
+  const u64 expect = (b + 1 < nBlocks ? tab[b + 1].outIdx : capacity) - tab[b].outIdx;     //  what the block index says
 
   //  528 header bits (kmers-files.C:36-52)
   const u64 m1 = r.binary(64), m2 = r.binary(64);
@@ -140,7 +156,7 @@ decode_kernel(const uint8_t *__restrict__ data, const UnionBlock *__restrict__ t
   const u32 cCode = (u32)r.binary(8);
   r.binary(64);  r.binary(64);
   if (r.bad || m1 != 0x7461446c7972656dull || m2 != 0x0a3030656c694661ull || kCode != 1 || cCode != 1 ||
-      bBits > wSuffix || tab[b].outIdx + n > capacity) { atomicOr(err, 2u); return; }
+      bBits > wSuffix || n != expect) { atomicOr(err, 2u); return; }
 
   const u32 ls = bBits <= 64 ? 0 : bBits - 64, rs = bBits <= 64 ? bBits : 64;
   const u64 o  = tab[b].outIdx;
@@ -415,9 +431,71 @@ struct HostBuf {                                            //  grow-only, never
   uint8_t *data(void) { return p; }
 };
 
+//  File bytes travel through a few page-locked staging buffers: host threads fill (or drain) one buffer while the DMA
+//  engine moves another, so neither a pageable copy nor a whole-group host buffer sits between the files and the device.
+struct PinnedRing {
+  static const int    N     = 4;
+  size_t      BYTES      = (size_t)32 << 20;          //  (MB_RING_BYTES: testing knob, so that small inputs take many chunks)
+  size_t      PIECE      = (size_t)4 << 20;           //  what one host thread reads or writes at a time
+  uint8_t    *buf[N]     = { nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t ev[N]      = { nullptr, nullptr, nullptr, nullptr };
+  bool        pending[N] = { false, false, false, false };
+  int init(void) {
+    if (getenv("MB_RING_BYTES")) { BYTES = std::max<size_t>(4096, strtoull(getenv("MB_RING_BYTES"), nullptr, 10) / 4096 * 4096); PIECE = std::max<size_t>(1024, BYTES / 8); }
+    for (int i = 0; i < N; i++) {
+      if (cudaMallocHost((void **)&buf[i], BYTES) != cudaSuccess) { cudaGetLastError(); buf[i] = nullptr; return mb_fail(MB_ENOMEM, "cannot allocate page-locked staging buffers"); }
+      if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return mb_fail(MB_ENODEVICE, "cudaEventCreate failed");
+    }
+    return MB_OK;
+  }
+  void quiesce(void) { for (int i = 0; i < N; i++) if (pending[i]) { cudaEventSynchronize(ev[i]); pending[i] = false; } }
+  ~PinnedRing() { for (int i = 0; i < N; i++) { if (ev[i]) cudaEventDestroy(ev[i]); if (buf[i]) cudaFreeHost(buf[i]); } }
+};
+
+//  fill(off, len, dst) -> MB_*: produce bytes [off, off + len) of the logical stream into dst (host threads inside).
+template <typename Fill>
+int streamToDevice(PinnedRing &R, uint8_t *dDst, size_t total, cudaStream_t s, Fill fill) {
+  size_t i = 0;
+  for (size_t off = 0; off < total; off += R.BYTES, i++) {
+    const int b = (int)(i % PinnedRing::N);
+    const size_t len = std::min(R.BYTES, total - off);
+    if (R.pending[b]) { MB_CUDA(cudaEventSynchronize(R.ev[b])); R.pending[b] = false; }      //  its last copy has left the host
+    MB_TRY(fill(off, len, R.buf[b]));
+    MB_CUDA(cudaMemcpyAsync(dDst + off, R.buf[b], len, cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaEventRecord(R.ev[b], s));
+    R.pending[b] = true;
+  }
+  return MB_OK;
+}
+
+//  consume(off, len, src) -> MB_*: take bytes [off, off + len) of the device range; the copy of the next chunk is in
+//  flight while a chunk is consumed.
+template <typename Consume>
+int streamFromDevice(PinnedRing &R, const uint8_t *dSrc, size_t total, cudaStream_t s, Consume consume) {
+  R.quiesce();
+  const size_t nChunks = (total + R.BYTES - 1) / R.BYTES;
+  for (size_t i = 0; i <= nChunks; i++) {
+    if (i < nChunks) {
+      const int b = (int)(i % PinnedRing::N);
+      const size_t off = i * R.BYTES, len = std::min(R.BYTES, total - off);
+      MB_CUDA(cudaMemcpyAsync(R.buf[b], dSrc + off, len, cudaMemcpyDeviceToHost, s));
+      MB_CUDA(cudaEventRecord(R.ev[b], s));
+    }
+    if (i >= 1) {
+      const size_t j = i - 1;
+      const int b = (int)(j % PinnedRing::N);
+      const size_t off = j * R.BYTES, len = std::min(R.BYTES, total - off);
+      MB_CUDA(cudaEventSynchronize(R.ev[b]));
+      MB_TRY(consume(off, len, (const uint8_t *)R.buf[b]));
+    }
+  }
+  return MB_OK;
+}
+
 struct FileJob {                                            //  one input data file of the group
   u32 input = 0, file = 0;
-  size_t off = 0, bytes = 0;                                //  place in the input's host buffer
+  int fd = -1;
+  size_t off = 0, bytes = 0;                                //  place in the input's byte stream (8-aligned)
   std::vector<UnionBlock> tab;                              //  byteOff relative to the file, outIdx relative to its first k-mer
   u64 nk = 0;
   int rc = MB_OK;
@@ -430,6 +508,8 @@ struct InputDb {
   u32 k = 0, wPrefix = 0, wSuffix = 0;
   u64 fileBytes[64] = { 0 };                                //  .merylData sizes
   u64 fileKmers[64] = { 0 };                                //  from the per-file block indexes
+  std::vector<uint8_t> index[64];                           //  the .merylIndex images: {prefix, byte offset, nKmers} per block
+  const std::vector<uint8_t> &indexOf(u32 f) const { return mem ? mem->index[f] : index[f]; }
 };
 
 int openDb(const char *dir, InputDb &db) {
@@ -455,7 +535,7 @@ int openDb(const char *dir, InputDb &db) {
     mb_file_name(path, sizeof(path), dir, f, false);
     if (stat(path, &st) != 0) return mb_fail(MB_EIO, "cannot stat '%s': %s", path, strerror(errno));
     db.fileBytes[f] = (u64)st.st_size;
-    std::vector<uint8_t> ix;
+    std::vector<uint8_t> &ix = db.index[f];
     mb_file_name(path, sizeof(path), dir, f, true);
     MB_TRY(readWhole(path, ix));
     if (ix.size() % 24) return mb_fail(MB_EFORMAT, "'%s' is not a block index", path);
@@ -608,8 +688,9 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
     MB_UCUDA(cudaMemsetAsync(dFileBase, 0, 64 * 8, s));
     const size_t fixedOff = top.off;
 
-    std::vector<HostBuf> hostIn(nInputs);                    //  the group's file bytes, one buffer per input (reused by the next group)
-    HostBuf outBytes, outIdx;
+    PinnedRing ring;
+    MB_UTRY(ring.init());
+    HostBuf outIdx;
     u32 f0 = 0;
     while (f0 < 64) {
       u32 f1 = f0 + 1;
@@ -628,49 +709,36 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
       u32 *dErr = (u32 *)(dCtl + 16);
 
       //  ---- read + decode every input's part of the group -------------------------------------------------
-      //  Host threads read the files into one buffer per input and walk the block containers (sizes only);
-      //  then one copy and one decode launch per input.
+      //  The block tables come from the inputs' block indexes ({prefix, byte offset, nKmers} per block); the data files'
+      //  bytes stream through the page-locked ring to the device (host threads pread one chunk while the previous one is
+      //  on the bus); one decode launch per input.  The decoder checks every container against the buffer's end and
+      //  every block's k-mer count against the index.
       MB_UCUDA(cudaEventRecord(ev[0], s));
       std::vector<FileJob> jobs;
+      struct FdCloser { std::vector<FileJob> &v; ~FdCloser() { for (FileJob &j : v) if (j.fd >= 0) { close(j.fd); j.fd = -1; } } } fdCloser{ jobs };
       std::vector<size_t>  inBytes(nInputs, 0);
       for (u32 i = 0; i < nInputs; i++)
         for (u32 f = f0; f < f1; f++) {
           FileJob j;  j.input = i;  j.file = f;  j.off = inBytes[i];  j.bytes = (size_t)in[i].fileBytes[f];
           inBytes[i] += (j.bytes + 7) / 8 * 8;
+          const std::vector<uint8_t> &ix = in[i].indexOf(f);
+          for (size_t e = 0; e + 24 <= ix.size(); e += 24) {
+            u64 at, nkB;
+            memcpy(&at, ix.data() + e + 8, 8);  memcpy(&nkB, ix.data() + e + 16, 8);
+            if (nkB == 0) continue;                         //  an empty block (block writer) or an absent one (stream writer)
+            if (at >= j.bytes) { rc = mb_fail(MB_EFORMAT, "'%s': block index of data file %u points past the end of the file", in[i].dir.c_str(), f); goto done; }
+            UnionBlock ub;  ub.byteOff = at;  ub.outIdx = j.nk;
+            j.tab.push_back(ub);
+            j.nk += nkB;
+          }
+          if (!in[i].mem && j.bytes) {
+            char path[4096];
+            mb_file_name(path, sizeof(path), in[i].dir.c_str(), f, false);
+            j.fd = open(path, O_RDONLY);
+            if (j.fd < 0) { rc = mb_fail(MB_EIO, "cannot open '%s': %s", path, strerror(errno)); jobs.push_back(std::move(j)); goto done; }
+          }
           jobs.push_back(std::move(j));
         }
-      for (u32 i = 0; i < nInputs; i++)
-        if (!hostIn[i].need(inBytes[i] + 8)) { rc = mb_fail(MB_ENOMEM, "cannot allocate %zu bytes of host memory", inBytes[i]); goto done; }
-      parallelFor(jobs.size(), [&](size_t ji) {
-        FileJob &j = jobs[ji];
-        char path[4096];
-        mb_file_name(path, sizeof(path), in[j.input].dir.c_str(), j.file, false);
-        uint8_t *d = hostIn[j.input].data() + j.off;
-        if (in[j.input].mem) {
-          if (j.bytes) memcpy(d, in[j.input].mem->dataPtr[j.file], j.bytes);
-        } else {
-          FILE *fp = fopen(path, "rb");
-          if (!fp || (j.bytes && fread(d, 1, j.bytes, fp) != j.bytes)) { j.rc = MB_EIO; j.err = std::string("cannot read '") + path + "'"; if (fp) fclose(fp); return; }
-          fclose(fp);
-        }
-        size_t p = 0;
-        while (p < j.bytes) {                                //  walk the containers (stuffedBits-v1.C:117-196)
-          u32 nSub = 0;
-          if (j.bytes - p >= 16) memcpy(&nSub, d + p + 8, 4);
-          if (nSub == 0 || j.bytes - p < 16 + 16 * (size_t)nSub + 32) { j.rc = MB_EFORMAT; j.err = std::string("'") + path + "': bad block at byte " + std::to_string(p); return; }
-          const u64 *len = (const u64 *)(d + p + 16) + nSub;
-          size_t words = 0;
-          for (u32 q = 0; q < nSub; q++) words += (len[q] + 63) / 64;
-          const size_t sz = 16 + 16 * (size_t)nSub + 8 * words;
-          if (j.bytes - p < sz) { j.rc = MB_EFORMAT; j.err = std::string("'") + path + "': truncated block at byte " + std::to_string(p); return; }
-          u64 nkB;  memcpy(&nkB, d + p + 16 + 16 * (size_t)nSub + 24, 8);      //  header word 3 = nKmers
-          UnionBlock ub;  ub.byteOff = p;  ub.outIdx = j.nk;
-          j.tab.push_back(ub);
-          j.nk += nkB;
-          p += sz;
-        }
-      });
-      for (const FileJob &j : jobs) if (j.rc != MB_OK) { rc = mb_fail(j.rc, "%s", j.err.c_str()); goto done; }
 
       std::vector<std::vector<UnionBlock>> tabs(nInputs);    //  alive until the stream has consumed them
       for (u32 i = 0; i < nInputs; i++) {
@@ -688,15 +756,42 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
           idx += j.nk;
           st.h2dBytes += j.bytes;  st.inBytes += j.bytes;
         }
-        if (idx > nk) { rc = mb_fail(MB_EFORMAT, "'%s' holds more k-mers than its block indexes say", in[i].dir.c_str()); goto done; }
+        if (idx != nk) { rc = mb_fail(MB_EFORMAT, "internal: block tables of '%s' disagree", in[i].dir.c_str()); goto done; }
         UnionBlock *dTab = (UnionBlock *)g.take(tab.size() * sizeof(UnionBlock) + 16);
         if (!dTab) { rc = mb_fail(MB_ENOMEM, "internal: union block table does not fit"); goto done; }
         if (!tab.empty()) {
-          MB_UCUDA(cudaMemcpyAsync(dRaw, hostIn[i].data(), inBytes[i], cudaMemcpyHostToDevice, s));
+          //  this input's files of the group, back to back (8-aligned), chunk by chunk
+          size_t jFirst = 0;
+          while (jobs[jFirst].input != i) jFirst++;
+          const size_t jEnd = jFirst + (f1 - f0);
+          rc = streamToDevice(ring, dRaw, inBytes[i], s, [&](size_t off, size_t len, uint8_t *dst) -> int {
+            const size_t PIECE = ring.PIECE;
+            const size_t nPieces = (len + PIECE - 1) / PIECE;
+            std::atomic<int> bad(-1);
+            parallelFor(nPieces, [&](size_t pi) {
+              const size_t lo = off + pi * PIECE, hi = std::min(off + len, lo + PIECE);
+              for (size_t ji = jFirst; ji < jEnd; ji++) {
+                const FileJob &j = jobs[ji];
+                const size_t a0 = std::max(lo, j.off), a1 = std::min(hi, j.off + j.bytes);
+                if (a0 >= a1) continue;
+                uint8_t *to = dst + (a0 - off);
+                if (in[i].mem) { memcpy(to, in[i].mem->dataPtr[j.file] + (a0 - j.off), a1 - a0); continue; }
+                size_t got = 0;
+                while (got < a1 - a0) {
+                  const ssize_t r = pread(j.fd, to + got, a1 - a0 - got, (off_t)(a0 - j.off + got));
+                  if (r <= 0) { bad = (int)ji; return; }
+                  got += (size_t)r;
+                }
+              }
+            });
+            if (bad >= 0) return mb_fail(MB_EIO, "cannot read data file %u of '%s'", jobs[bad].file, in[i].dir.c_str());
+            return MB_OK;
+          });
+          if (rc != MB_OK) goto done;
           MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
           const unsigned grid = (unsigned)((tab.size() + 127) / 128);
-          if (kw == 1) decode_kernel<1><<<grid, 128, 0, s>>>(dRaw, dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
-          else         decode_kernel<2><<<grid, 128, 0, s>>>(dRaw, dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
+          if (kw == 1) decode_kernel<1><<<grid, 128, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
+          else         decode_kernel<2><<<grid, 128, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
           MB_UCUDA(cudaGetLastError());
           st.nLaunches++;
           st.h2dBytes += tab.size() * sizeof(UnionBlock);
@@ -709,6 +804,8 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
         MB_UCUDA(cudaMemcpyAsync(&err, dErr, 4, cudaMemcpyDeviceToHost, s));
         MB_UCUDA(cudaEventRecord(ev[1], s));
         MB_UCUDA(cudaStreamSynchronize(s));
+        ring.quiesce();
+        for (FileJob &j : jobs) if (j.fd >= 0) { close(j.fd); j.fd = -1; }
         if (err) { rc = mb_fail(MB_EFORMAT, "corrupt block in the inputs (decoder flags 0x%x)", err); goto done; }
         float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msDecode += ms;
       }
@@ -792,50 +889,83 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
       MB_UCUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl, dSub, dOut, dIdx, dFileBase, s));
       st.nLaunches += 2;
 
-      if (!outBytes.need(encTotals[0] + 8) || !outIdx.need(nBlocks * 24)) { rc = mb_fail(MB_ENOMEM, "cannot allocate %llu bytes of host memory", (unsigned long long)encTotals[0]); goto done; }
-      if (encTotals[0]) MB_UCUDA(cudaMemcpyAsync(outBytes.data(), dOut, encTotals[0], cudaMemcpyDeviceToHost, s));
+      //  ---- copy back + write: the encoded bytes stream through the page-locked ring, host threads write one chunk to
+      //  the files (or the images) while the next one is on the bus --------------------------------------------------------
+      if (!outIdx.need(nBlocks * 24)) { rc = mb_fail(MB_ENOMEM, "cannot allocate %llu bytes of host memory", (unsigned long long)(nBlocks * 24)); goto done; }
       MB_UCUDA(cudaMemcpyAsync(outIdx.data(), dIdx, nBlocks * 24, cudaMemcpyDeviceToHost, s));
-      MB_UCUDA(cudaEventRecord(ev[1], s));
-      MB_UCUDA(cudaStreamSynchronize(s));
-      { float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msEncode += ms; }
-      st.d2hBytes += encTotals[0] + nBlocks * 24;
-
-      if (E.outImages) {                                       //  images in host memory (merge of count batches)
-        for (u32 f = f0; f < f1; f++) {
-          const u64 byte0 = meta[f - f0].outByte, byte1 = (f + 1 < f1) ? meta[f - f0 + 1].outByte : encTotals[0];
-          const size_t len = (size_t)(byte1 - byte0);
-          MbDbImages &o = *E.outImages;
-          if (E.outBuf) {
-            if (*E.outUsed + len > E.outCap) { rc = mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", f, len, *E.outUsed, E.outCap); goto done; }
-            memcpy(E.outBuf + *E.outUsed, outBytes.data() + byte0, len);
-            o.dataVec[f].clear();  o.dataPtr[f] = E.outBuf + *E.outUsed;  *E.outUsed += len;
+      {
+        const u32 nf = f1 - f0;
+        std::vector<u64> fileByte(nf + 1);                     //  the files' places in the group's encoded bytes
+        for (u32 fi = 0; fi < nf; fi++) fileByte[fi] = meta[fi].outByte;
+        fileByte[nf] = encTotals[0];
+        std::vector<int>       fds(nf, -1);
+        std::vector<uint8_t *> dest(nf, nullptr);              //  images in host memory (merge of count batches)
+        int wrc = MB_OK;
+        for (u32 fi = 0; fi < nf && wrc == MB_OK; fi++) {
+          const u32 f = f0 + fi;
+          const size_t len = (size_t)(fileByte[fi + 1] - fileByte[fi]);
+          if (E.outImages) {
+            MbDbImages &o = *E.outImages;
+            if (E.outBuf) {
+              if (*E.outUsed + len > E.outCap) { wrc = mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", f, len, *E.outUsed, E.outCap); break; }
+              o.dataVec[f].clear();  dest[fi] = E.outBuf + *E.outUsed;  *E.outUsed += len;
+            } else {
+              o.dataVec[f].resize(len);  dest[fi] = o.dataVec[f].data();
+            }
+            o.dataPtr[f] = dest[fi];  o.dataLen[f] = len;
           } else {
-            o.dataVec[f].assign(outBytes.data() + byte0, outBytes.data() + byte1);
-            o.dataPtr[f] = o.dataVec[f].data();
+            char path[4096];
+            mb_file_name(path, sizeof(path), outDir, f, false);
+            fds[fi] = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (fds[fi] < 0) wrc = mb_fail(MB_EIO, "cannot create '%s': %s", path, strerror(errno));
           }
-          o.dataLen[f] = len;
-          o.index[f].assign(outIdx.data() + (u64)(f - f0) * blocksPerFile * 24, outIdx.data() + (u64)(f - f0 + 1) * blocksPerFile * 24);
-          st.outBytes += len + blocksPerFile * 24;
         }
-      } else {
-        std::vector<int> wrc(f1 - f0, MB_OK);
-        std::vector<std::string> werr(f1 - f0);
-        parallelFor(f1 - f0, [&](size_t fi) {
-          const u32 f = f0 + (u32)fi;
-          const u64 byte0 = meta[fi].outByte, byte1 = (f + 1 < f1) ? meta[fi + 1].outByte : encTotals[0];
-          char path[4096];
-          for (int isIdx = 0; isIdx < 2; isIdx++) {
-            mb_file_name(path, sizeof(path), outDir, f, isIdx != 0);
-            const void  *ptr = isIdx ? (const void *)(outIdx.data() + fi * blocksPerFile * 24) : (const void *)(outBytes.data() + byte0);
-            const size_t len = isIdx ? (size_t)blocksPerFile * 24 : (size_t)(byte1 - byte0);
-            FILE *fp = fopen(path, "wb");
-            if (!fp || (len && fwrite(ptr, 1, len, fp) != len) || fclose(fp) != 0) { wrc[fi] = MB_EIO; werr[fi] = std::string("cannot write '") + path + "': " + strerror(errno); return; }
+        if (wrc == MB_OK)
+          wrc = streamFromDevice(ring, dOut, (size_t)encTotals[0], s, [&](size_t off, size_t len, const uint8_t *src) -> int {
+            //  pieces: (file, range) intersections of this chunk, at most 4 MB each
+            struct Piece { u32 fi; size_t a0, a1; };
+            std::vector<Piece> pieces;
+            const size_t PIECE = ring.PIECE;
+            u32 fi = (u32)(std::upper_bound(fileByte.begin(), fileByte.end(), (u64)off) - fileByte.begin());
+            fi = fi ? fi - 1 : 0;
+            for (; fi < nf && fileByte[fi] < off + len; fi++) {
+              const size_t a0 = std::max<size_t>(off, fileByte[fi]), a1 = std::min<size_t>(off + len, fileByte[fi + 1]);
+              for (size_t p = a0; p < a1; p += PIECE) pieces.push_back(Piece{ fi, p, std::min(a1, p + PIECE) });
+            }
+            std::atomic<int> bad(-1);
+            parallelFor(pieces.size(), [&](size_t pi) {
+              const Piece &pc = pieces[pi];
+              const uint8_t *from = src + (pc.a0 - off);
+              const size_t inFile = pc.a0 - (size_t)fileByte[pc.fi];
+              if (dest[pc.fi]) { memcpy(dest[pc.fi] + inFile, from, pc.a1 - pc.a0); return; }
+              size_t put = 0;
+              while (put < pc.a1 - pc.a0) {
+                const ssize_t r = pwrite(fds[pc.fi], from + put, pc.a1 - pc.a0 - put, (off_t)(inFile + put));
+                if (r <= 0) { bad = (int)pc.fi; return; }
+                put += (size_t)r;
+              }
+            });
+            if (bad >= 0) return mb_fail(MB_EIO, "cannot write data file %u in '%s': %s", f0 + (u32)bad, outDir, strerror(errno));
+            return MB_OK;
+          });
+        for (u32 fi = 0; fi < nf; fi++) if (fds[fi] >= 0 && close(fds[fi]) != 0 && wrc == MB_OK) wrc = mb_fail(MB_EIO, "cannot close data file %u in '%s': %s", f0 + fi, outDir, strerror(errno));
+        if (wrc != MB_OK) { rc = wrc; goto done; }
+        MB_UCUDA(cudaEventRecord(ev[1], s));
+        MB_UCUDA(cudaStreamSynchronize(s));
+        { float ms = 0;  cudaEventElapsedTime(&ms, ev[0], ev[1]);  st.msEncode += ms; }
+        st.d2hBytes += encTotals[0] + nBlocks * 24;
+
+        //  the block indexes (small)
+        for (u32 fi = 0; fi < nf; fi++) {
+          const u32 f = f0 + fi;
+          const uint8_t *ix = outIdx.data() + (u64)fi * blocksPerFile * 24;
+          if (E.outImages) E.outImages->index[f].assign(ix, ix + blocksPerFile * 24);
+          else {
+            char path[4096];
+            mb_file_name(path, sizeof(path), outDir, f, true);
+            MB_UTRY(writeFile(path, ix, (size_t)blocksPerFile * 24));
           }
-        });
-        for (u32 f = f0; f < f1; f++) {
-          if (wrc[f - f0] != MB_OK) { rc = mb_fail(MB_EIO, "%s", werr[f - f0].c_str()); goto done; }
-          const u64 byte0 = meta[f - f0].outByte, byte1 = (f + 1 < f1) ? meta[f - f0 + 1].outByte : encTotals[0];
-          st.outBytes += byte1 - byte0 + blocksPerFile * 24;
+          st.outBytes += fileByte[fi + 1] - fileByte[fi] + blocksPerFile * 24;
         }
       }
 

@@ -190,6 +190,7 @@ def test_sim_count_batches(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
 def test_sim_count_batches_pushed_bases_and_output_buffer(tmp_path, monkeypatch):
     """The same through mb_add_bases (one long push: the cut falls inside the call) with a caller-owned output buffer."""
     monkeypatch.setenv("MB_MAX_BATCH_BASES", "80000")
+    monkeypatch.setenv("MB_RING_BYTES", "8192")               # the batches' images pass through small staging chunks
     rng = np.random.default_rng(11)
     recs = [synth.random_bases(int(rng.integers(30, 400)), rng).tobytes() for _ in range(1_600)]
     fa = tmp_path / "r.fa"

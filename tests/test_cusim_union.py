@@ -52,3 +52,7 @@ def test_sim_set_operations(tmp_path, op):
 
 def test_sim_value_operations(tmp_path):
     uc.case_value_operations(str(tmp_path), n=5_000)
+
+
+def test_sim_union_small_ring(tmp_path, monkeypatch):
+    uc.case_small_ring(str(tmp_path), monkeypatch)

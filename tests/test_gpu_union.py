@@ -80,3 +80,7 @@ def test_set_operations(tmp_path, op):
 
 def test_value_operations(tmp_path):
     uc.case_value_operations(str(tmp_path), n=40_000)
+
+
+def test_union_small_ring(tmp_path, monkeypatch):
+    uc.case_small_ring(str(tmp_path), monkeypatch)

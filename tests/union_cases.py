@@ -100,3 +100,15 @@ def case_value_operations(tmp, n=15_000):
         util.run_oracle([op, str(param), a, "output", ora])
         mb.value_operation(op, param, a, out)
         util.assert_same_db(ora, out)
+
+
+def case_small_ring(tmp, monkeypatch, k=21):
+    """The data files' bytes travel through page-locked staging chunks in both directions (MB_RING_BYTES makes them
+    small): chunks that hold several files, files that span several chunks, chunk edges inside a block, more chunks than
+    ring buffers."""
+    monkeypatch.setenv("MB_RING_BYTES", "4096")
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(30_000, 1_500, 150, 0.003, 5), k)
+    b = oracle_db(tmp, "b", synth.reads_fastq_bytes(30_000, 1_000, 150, 0.003, 6), k)
+    check_union(tmp, [a, b], tag="ring")
+    monkeypatch.setenv("MB_UNION_MAX_FILES", "5")
+    check_union(tmp, [a, b, a], tag="ring3")
