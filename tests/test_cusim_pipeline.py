@@ -65,7 +65,8 @@ def test_sim_golden(tmp_path, name):
 @pytest.mark.parametrize("k,w_prefix,key_bytes", [(21, 10, 4), (19, 8, 4), (22, 8, 8), (31, 7, 8), (32, 6, 8), (33, 6, 16), (51, 8, 16), (64, 6, 16), (8, 6, 4)])
 def test_sim_k_sweep(tmp_path, k, w_prefix, key_bytes):
     """u32 suffix keys (2k - binBits <= 32), u64 keys and 128-bit keys through the same kernels."""
-    _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 6_000, 100 + k)}, k, w_prefix, expect_key_bytes=key_bytes)
+    st = _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 6_000, 100 + k)}, k, w_prefix, expect_key_bytes=key_bytes)
+    assert st.nBatches == 1 and st.msMerge == 0             # one batch: nothing is merged
 
 
 @pytest.mark.parametrize("op", ["count-forward", "count-reverse"])
@@ -173,7 +174,7 @@ def test_sim_parallel_parse_in_the_pipeline(tmp_path, monkeypatch):
 
 # ---- count batches (W6: merylBlockWriter::finishBatch / mergeBatches, kmers-writer-block.C:172-386) --------------------
 
-@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 12, "count", 150_000), (31, 9, "count-forward", 120_000),
+@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 10, "count", 190_000), (31, 9, "count-forward", 120_000),
                                                        (51, 8, "count", 150_000), (8, 6, "count-reverse", 100_000)])
 def test_sim_count_batches(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
     """Reads that outgrow the device are counted in batches cut at record breaks; the batches' blocks are decoded, merged
@@ -182,24 +183,24 @@ def test_sim_count_batches(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
     monkeypatch.setenv("MB_MAX_BATCH_BASES", str(batch_bases))
     reads = synth.reads_fastq_bytes(20_000, 2_000, 150, 0.004, 7 + k)
     st = _vs_oracle(tmp_path, {"r.fq": reads, "g.fa": synth.fasta_bytes(2, 30_000, k)}, k, w_prefix, op=op)
-    assert st.nBatches >= 3 and st.msMerge >= 0
+    assert st.nBatches >= 2 and st.msMerge >= 0
     assert st.nKmers == 2_000 * (150 - k + 1) + 2 * (30_000 - k + 1)
     assert st.nTotal == st.nKmers
 
 
 def test_sim_count_batches_pushed_bases_and_output_buffer(tmp_path, monkeypatch):
     """The same through mb_add_bases (one long push: the cut falls inside the call) with a caller-owned output buffer."""
-    monkeypatch.setenv("MB_MAX_BATCH_BASES", "80000")
+    monkeypatch.setenv("MB_MAX_BATCH_BASES", "100000")
     monkeypatch.setenv("MB_RING_BYTES", "8192")               # the batches' images pass through small staging chunks
     rng = np.random.default_rng(11)
     recs = [synth.random_bases(int(rng.integers(30, 400)), rng).tobytes() for _ in range(1_600)]
     fa = tmp_path / "r.fa"
     fa.write_bytes(b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(recs)))
     ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
-    util.run_oracle(["k=21", "wprefix=11", "count", str(fa), "output", ora])
+    util.run_oracle(["k=25", "wprefix=8", "count", str(fa), "output", ora])
     stream = b".".join(recs)                                   # work-buffer form; the last record ends with the call
     buf = np.zeros(32 << 20, dtype=np.uint8)
-    with mb.Counter(21, 11) as c:
+    with mb.Counter(25, 8) as c:
         c.set_output_buffer(buf.ctypes.data, buf.size)
         c.add_bases(stream[:100_000], end_of_sequence=False)
         c.add_bases(stream[100_000:], end_of_sequence=True)
@@ -207,9 +208,4 @@ def test_sim_count_batches_pushed_bases_and_output_buffer(tmp_path, monkeypatch)
         st = c.stats()
         c.write_db(out)
     util.assert_same_db(ora, out)
-    assert st.nBatches >= 4
-
-
-def test_sim_one_batch_is_the_old_road(tmp_path):
-    st = _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 6_000, 3)}, 21, 10)
-    assert st.nBatches == 1 and st.msMerge == 0
+    assert st.nBatches >= 3
