@@ -48,7 +48,31 @@ struct __align__(16) UnionBlock {       //  one serialised block of an input fil
 
 //  Sequential MSB-first reader over the sub-blocks of one stuffedBits container (stuffedBits-v1.H:246-285:
 //  a field lies wholly inside one sub-block; it is read from the next one iff it does not fit the rest of this one).
-struct SubReader {
+struct FetchGlobal {                    //  words straight from global memory (one reader per thread)
+  __device__ __forceinline__ u64 fetch(const u64 *p) { return *p; }
+};
+
+//  A warp's sliding window over the container's words in shared memory: all lanes walk the same bit stream in lock step
+//  (every call has the same p in every lane), the window is refilled by one coalesced load whenever the walk leaves it.
+const int DW_WINDOW = 64;               //  words
+struct FetchWindow {
+  u64       *win;                       //  DW_WINDOW words of shared memory, this warp's
+  const u64 *first;                     //  win[i] == first[i]
+  const u64 *end;                       //  end of the input buffer
+  u32        lane;
+  __device__ __forceinline__ u64 fetch(const u64 *p) {
+    if (p < first || p >= first + DW_WINDOW) {
+      __syncwarp();
+      first = p;
+      for (int t = (int)lane; t < DW_WINDOW; t += 32) win[t] = (p + t < end) ? p[t] : 0;
+      __syncwarp();
+    }
+    return win[p - first];
+  }
+};
+
+template <class Fetch>
+struct SubReaderT : Fetch {
   const u64 *len;                       //  sub-block lengths in bits
   const u64 *cur;                       //  first word of the current sub-block
   u32        blk, nSub;
@@ -77,7 +101,7 @@ struct SubReader {
     cw = ~0ull;  cv = 0;
   }
   __device__ __forceinline__ u64 word(u64 wd) {
-    if (wd != cw) { cv = cur[wd]; cw = wd; }
+    if (wd != cw) { cv = this->fetch(cur + wd); cw = wd; }
     return cv;
   }
   __device__ __forceinline__ void move(u64 w) {
@@ -88,6 +112,10 @@ struct SubReader {
     lenCur = len[blk];
     pos = 0;
     cw = ~0ull;
+  }
+  __device__ __forceinline__ void skip(u32 w) {             //  step over a w-bit field without reading it
+    move(w);
+    pos += w;
   }
   __device__ __forceinline__ u64 binary(u32 w) {           //  0 < w <= 64
     move(w);
@@ -119,6 +147,7 @@ struct SubReader {
     return v;
   }
 };
+typedef SubReaderT<FetchGlobal> SubReader;
 
 __device__ __forceinline__ void store_kmer(u64 *out, u64 i, u64 prefix, u32 wSuffix, u64 sufHi, u64 sufLo) {
   out[i] = (wSuffix >= 64 ? 0 : (prefix << wSuffix)) | sufLo;      //  k <= 32: 2k <= 64
@@ -173,6 +202,91 @@ decode_kernel(const uint8_t *__restrict__ data, u64 dataBytes, const UnionBlock 
   }
   for (u64 i = 0; i < n && !r.bad; i++) vals[o + i] = (u32)r.binary(32);
   if (r.bad) atomicOr(err, 4u);
+}
+
+//  K7w: one WARP per block, for inputs with few, long blocks (a database written by the stream writer has 4096 blocks
+//  of up to 16 Mi k-mers; one thread per block leaves the device empty and walks a dependent chain of global loads).
+//  The boundaries of the k-mer fields can only be found one after the other (every unary code must be read to find the
+//  next field), so all lanes walk that chain together, in lock step, over a shared-memory window of the stream that is
+//  refilled with coalesced loads; at step j lane j keeps the reader's state.  Then the 32 lanes read the binary parts of
+//  "their" k-mers (from global memory: the lines are hot) and store 32 consecutive k-mers with one coalesced store.  The
+//  32-bit values have closed-form places inside a sub-block and are read lane-strided.
+const int DW_WARPS = 4;
+
+template <int KW>
+__global__ void __launch_bounds__(DW_WARPS * 32)
+decode_warp_kernel(const uint8_t *__restrict__ data, u64 dataBytes, const UnionBlock *__restrict__ tab, u64 nBlocks, u32 wSuffix,
+                   typename KeyT<KW>::type *__restrict__ keys, u32 *__restrict__ vals, u64 capacity, u32 *__restrict__ err) {
+  __shared__ u64 window[DW_WARPS][DW_WINDOW];
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u64 b = (u64)blockIdx.x * DW_WARPS + warp;
+  if (b >= nBlocks) return;                                 //  (whole warps leave)
+  const u64 at = tab[b].byteOff;
+  if (at >= dataBytes || (at & 7)) { if (lane == 0) atomicOr(err, 1u); return; }
+  const u64 *c = (const u64 *)(data + at);
+
+  SubReaderT<FetchWindow> r;
+  r.win = window[warp];  r.first = nullptr;  r.end = (const u64 *)(data + (dataBytes & ~7ull));  r.lane = lane;
+  r.first = r.end;                                          //  empty window: the first fetch fills it
+  r.open(c, dataBytes - at);
+  if (r.bad) { if (lane == 0) atomicOr(err, 1u); return; }
+  const u64 expect = (b + 1 < nBlocks ? tab[b + 1].outIdx : capacity) - tab[b].outIdx;
+
+  const u64 m1 = r.binary(64), m2 = r.binary(64);
+  const u64 prefix = r.binary(64), n = r.binary(64);
+  const u32 kCode = (u32)r.binary(8);
+  r.binary(32);
+  const u32 bBits = (u32)r.binary(32);
+  r.binary(64);
+  const u32 cCode = (u32)r.binary(8);
+  r.binary(64);  r.binary(64);
+  if (r.bad || m1 != 0x7461446c7972656dull || m2 != 0x0a3030656c694661ull || kCode != 1 || cCode != 1 ||
+      bBits > wSuffix || n != expect) { if (lane == 0) atomicOr(err, 2u); return; }
+
+  const u32 ls = bBits <= 64 ? 0 : bBits - 64, rs = bBits <= 64 ? bBits : 64;
+  const u64 o  = tab[b].outIdx;
+  u64 hi = 0;
+  bool laneBad = false;
+  for (u64 i0 = 0; i0 < n && !r.bad; i0 += 32) {
+    const u32 m = (u32)(n - i0 < 32 ? n - i0 : 32);
+    SubReader mine;                                         //  the reader's state in front of my k-mer's binary fields
+    mine.bad = true;  mine.len = r.len;  mine.nSub = r.nSub;  mine.cw = ~0ull;  mine.cv = 0;
+    mine.cur = r.cur;  mine.blk = 0;  mine.pos = 0;  mine.lenCur = 0;
+    u64 myHi = 0;
+    for (u32 j = 0; j < m; j++) {                           //  the chain, all lanes together
+      hi += r.unary();
+      if (lane == j) { mine.cur = r.cur;  mine.blk = r.blk;  mine.pos = r.pos;  mine.lenCur = r.lenCur;  mine.bad = r.bad;  myHi = hi; }
+      if (ls) r.skip(ls);
+      if (rs) r.skip(rs);
+    }
+    if (lane < m) {
+      const u64 bh = ls ? mine.binary(ls) : 0;
+      const u64 bl = rs ? mine.binary(rs) : 0;
+      u64 sLo, sHi;
+      if (bBits >= 64) { sLo = bl;  sHi = bh | (bBits - 64 < 64 ? (myHi << (bBits - 64)) : 0); }
+      else             { sLo = bl | (bBits ? (myHi << bBits) : myHi);  sHi = bBits ? (myHi >> (64 - bBits)) : 0; }
+      if (!mine.bad) store_kmer(keys, o + i0 + lane, prefix, wSuffix, sHi, sLo);
+      else           laneBad = true;
+    }
+  }
+
+  //  values: inside a sub-block they follow each other every 32 bits; a value that does not fit starts the next one
+  u64 i = 0;
+  while (i < n && !r.bad) {
+    const u64 fit = (r.pos + 32 <= r.lenCur) ? (r.lenCur - r.pos) / 32 : 0;
+    if (fit == 0) { r.move(32); if (r.pos + 32 > r.lenCur) r.bad = true; continue; }
+    const u64 m = fit < n - i ? fit : n - i;
+    for (u64 t = lane; t < m; t += 32) {
+      const u64 p  = r.pos + 32 * t;
+      const u64 wd = p >> 6;
+      const u32 fr = 64 - (u32)(p & 63);                    //  bits left in the word from p on
+      const u64 a  = r.cur[wd];
+      const u64 v  = (32 <= fr) ? (a >> (fr - 32)) : ((a << (32 - fr)) | (r.cur[wd + 1] >> (64 - (32 - fr))));
+      vals[o + i + t] = (u32)v;
+    }
+    r.pos += 32 * m;  i += m;
+  }
+  if (__any_sync(0xffffffffu, r.bad || laneBad) && lane == 0) atomicOr(err, 4u);
 }
 
 //  ---- K8: merge-path union with summed values ------------------------------------------------------------
@@ -789,9 +903,19 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
           });
           if (rc != MB_OK) goto done;
           MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
-          const unsigned grid = (unsigned)((tab.size() + 127) / 128);
-          if (kw == 1) decode_kernel<1><<<grid, 128, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
-          else         decode_kernel<2><<<grid, 128, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
+          //  many short blocks (a count db at prefix width 24 has 16.8 M of them): one thread per block fills the device;
+          //  few long blocks (stream-writer output, small count dbs): one warp per block (MB_DECODE=thread|warp forces one)
+          const char *dm = getenv("MB_DECODE");
+          const bool byWarp = dm ? !strcmp(dm, "warp") : tab.size() < ((size_t)1 << 18);
+          if (byWarp) {
+            const unsigned grid = (unsigned)((tab.size() + DW_WARPS - 1) / DW_WARPS);
+            if (kw == 1) decode_warp_kernel<1><<<grid, DW_WARPS * 32, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
+            else         decode_warp_kernel<2><<<grid, DW_WARPS * 32, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
+          } else {
+            const unsigned grid = (unsigned)((tab.size() + 127) / 128);
+            if (kw == 1) decode_kernel<1><<<grid, 128, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);
+            else         decode_kernel<2><<<grid, 128, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (ulonglong2 *)dKey, dVal, idx, dErr);
+          }
           MB_UCUDA(cudaGetLastError());
           st.nLaunches++;
           st.h2dBytes += tab.size() * sizeof(UnionBlock);

@@ -112,3 +112,15 @@ def case_small_ring(tmp, monkeypatch, k=21):
     check_union(tmp, [a, b], tag="ring")
     monkeypatch.setenv("MB_UNION_MAX_FILES", "5")
     check_union(tmp, [a, b, a], tag="ring3")
+
+
+def case_long_blocks(tmp, monkeypatch, k, decoder):
+    """Few, long blocks (count dbs of prefix width 6 and 8: thousands of k-mers per block, several sub-blocks each, fields
+    that hop to the next sub-block) through both block decoders: one thread per block, and one warp per block walking
+    the unary chain in lock step over a shared-memory window (MB_DECODE picks one; the default goes by the block count)."""
+    monkeypatch.setenv("MB_DECODE", decoder)
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(40_000, 600, 150, 0.004, 50 + k), k, wprefix=6)
+    b = oracle_db(tmp, "b", synth.fasta_bytes(2, 30_000, k) + b">p\n" + b"ACGGT" * 2_000 + b"\n", k, wprefix=8)
+    st, out = check_union(tmp, [a, b], tag="long")
+    assert st.nInputKmers > 50_000
+    check_union(tmp, [out, a], tag="long2")                  # and the stream writer's own blocks (prefix 12) as input
