@@ -42,8 +42,12 @@ const size_t kStageBytes = (size_t)64 << 20;        //  ingest staging buffer (m
 
 inline size_t alignUp(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
 
-struct EventTimer {                                  //  device time of a stream section
+struct EventTimer {                                  //  device time of a stream section (events released on every way out)
   cudaEvent_t a = nullptr, b = nullptr;
+  EventTimer() {}
+  EventTimer(const EventTimer &) = delete;
+  EventTimer &operator=(const EventTimer &) = delete;
+  ~EventTimer()                       { destroy(); }
   void init()                         { cudaEventCreate(&a); cudaEventCreate(&b); }
   void destroy()                      { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
   void start(cudaStream_t s)          { cudaEventRecord(a, s); }
@@ -622,8 +626,18 @@ static int runCount(mb_ctx *c) {
   //  of the encode region; a half is reused only after its copy has finished.  Needs a caller-owned output buffer
   //  (mb_set_output_buffer): the destination must not move while a copy is in flight.
   const bool overlapD2H = getenv("MB_OVERLAP_D2H") != nullptr && c->outBuf != nullptr && !(cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED));
-  cudaStream_t sCopy = nullptr;
-  cudaEvent_t  evEnc = nullptr, evCopied[2] = { nullptr, nullptr };
+  struct CopySide {                                     //  released on every way out of the function
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  enc = nullptr, copied[2] = { nullptr, nullptr }, afterHist = nullptr;
+    ~CopySide() {
+      if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+      if (enc) cudaEventDestroy(enc);
+      for (int i = 0; i < 2; i++) if (copied[i]) cudaEventDestroy(copied[i]);
+      if (afterHist) cudaEventDestroy(afterHist);
+    }
+  } side;
+  cudaStream_t &sCopy = side.stream;
+  cudaEvent_t  &evEnc = side.enc, (&evCopied)[2] = side.copied;
   bool         copyPending[2] = { false, false };
   u64          groupSeq = 0;
   if (overlapD2H) {
@@ -828,7 +842,7 @@ static int runCount(mb_ctx *c) {
 
   std::vector<u64> segStart, segTile, binStart(MB_MAX_BINS + 1);
   EventTimer tSortHist;  tSortHist.init();
-  cudaEvent_t evAfterHist;  MB_CUDA(cudaEventCreate(&evAfterHist));
+  cudaEvent_t &evAfterHist = side.afterHist;  MB_CUDA(cudaEventCreate(&evAfterHist));
 
   for (size_t pi = 0; pi < passes.size(); pi++) {
     const Pass &P = passes[pi];
@@ -1178,11 +1192,7 @@ static int runCount(mb_ctx *c) {
 
   if (overlapD2H) {
     MB_CUDA(cudaStreamSynchronize(sCopy));
-    cudaEventDestroy(evEnc);  cudaEventDestroy(evCopied[0]);  cudaEventDestroy(evCopied[1]);
-    cudaStreamDestroy(sCopy);
   }
-  cudaEventDestroy(evAfterHist);
-  tSortHist.destroy();
 
   if (p2p) {
     //  Unmap the peers' arenas, then a barrier: nobody returns (and later frees its arena) while somebody still maps it.
@@ -1260,7 +1270,6 @@ static int runCount(mb_ctx *c) {
 
   tAll.stop(s);
   c->st.msTotal = tAll.ms();
-  tAll.destroy();  tStage.destroy();
   c->counted = true;
   return MB_OK;
 }
