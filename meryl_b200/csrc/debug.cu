@@ -227,7 +227,7 @@ extern "C" int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix
 //  Select the sweep kernel (1..6, see sort.cu) for the contexts created afterwards; returns the previous one.
 extern "C" int mb_dbg_sort_version(int v) {
   const int old = mb_sort_version();
-  if (v >= 1 && v <= 6) mb_sort_set_version(v);
+  if (v >= 1 && v <= 7) mb_sort_set_version(v);
   return old;
 }
 

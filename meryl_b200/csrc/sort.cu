@@ -36,6 +36,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 #include "kernels.cuh"
 
@@ -501,6 +502,7 @@ template <> struct SweepShape<4> { static const int THREADS = 256, RBITS = 7, MI
 //  not yet measured (written without a GPU at hand; tools/ab_bench.py ... sortonly compares all shapes):
 template <> struct SweepShape<5> { static const int THREADS = 512, RBITS = 6, MIN_CTAS = 2; };   //  32 warps/SM, 16 keys per thread
 template <> struct SweepShape<6> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 2; };   //  16 warps/SM, 128 registers: no address recomputation
+template <> struct SweepShape<7> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 3; };   //  shape 3 as a persistent kernel that prefetches the next tile (sortp_sweep_kernel)
 
 template <int KW, int VER> struct SweepX {
   typedef typename KeyT<KW>::type Key;
@@ -551,12 +553,26 @@ __device__ __forceinline__ unsigned short *counter_of(unsigned char *buf, u32 cb
   return (unsigned short *)(buf + off);
 }
 
-template <int KW, int VER, bool FULL, bool BYTE>
+//  Persistent form (sortp_sweep_kernel): a CTA keeps claiming tiles.  While it works on a tile it claims the next one (the
+//  atomic's round trip hides behind the counting), fetches that tile's descriptor after the scan, and -- as soon as this
+//  tile's keys sit in the stage buffer and their registers are free -- loads the next tile's keys, so the loads fly during
+//  the look-back and the copy-out instead of in front of an idle CTA.
+template <int KW, int VER> struct SweepNext {
+  typename KeyT<KW>::type key[SweepX<KW, VER>::ITEMS];   //  in: this tile's keys, striped (thread t holds keys wbase + 32 i + lane); out: the next tile's
+  const TileInfo *info;
+  u64   nTiles;
+  u64  *tileCounter;
+  u64  *sNext;                                            //  shared memory word: the tile claimed for the next round
+  u64   nextTile;
+  TileInfo nextInfo;
+};
+
+template <int KW, int VER, bool FULL, bool BYTE, bool PRE = false>
 __device__ __forceinline__ void
 sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
             u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
             const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, bool wide,
-            u64 *__restrict__ status, u32 epoch, const SweepXShared &sm) {
+            u64 *__restrict__ status, u32 epoch, const SweepXShared &sm, SweepNext<KW, VER> *nx = nullptr) {
   typedef typename KeyT<KW>::type Key;
   typedef SweepX<KW, VER>         S;
   const int ITEMS = S::ITEMS, THREADS = S::THREADS, ROWS = S::ROWS, RADIX = S::RADIX;
@@ -584,9 +600,11 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
     for (int i = 0; i < ITEMS; i++) {
       const u32 j = wbase + i * 32 + lane;
       Key k;
-      if (FULL || j < n) k = in[begin + j]; else key_zero(k);
+      if (PRE) k = nx->key[i];
+      else if (FULL || j < n) k = in[begin + j]; else key_zero(k);
       xpose[w0 + i * 32 + (i * 32) / ITEMS] = k;
     }
+    if (PRE && t == 0) *nx->sNext = atomicAdd((unsigned long long *)nx->tileCounter, 1ull);     //  claim the next tile now, read it after the scan
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < ITEMS; i++)
@@ -645,6 +663,10 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
   }
   if (t == 0) binOff[RADIX] = n;
   __syncthreads();
+  if (PRE) {
+    nx->nextTile = *nx->sNext;
+    if (nx->nextTile < nx->nTiles) nx->nextInfo = nx->info[nx->nextTile];
+  }
 
   //  3a. publish this tile's digit counts as early as possible ...
   //  (digit ROWS-1's run ends where digit ROWS's begins, so binOff[d + 1] - binOff[d] holds for every d)
@@ -667,6 +689,18 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
       const u32 pos = *cp;
       *cp = (unsigned short)(pos + 1);
       stage[pos] = key[i];
+    }
+  }
+
+  //  (persistent form: my key registers are free now -- the next tile's keys start their way from HBM)
+  if (PRE && nx->nextTile < nx->nTiles) {
+    const u32 wbase = warp * 32 * ITEMS;
+    const u64 nb = nx->nextInfo.begin;
+    const u32 nn = nx->nextInfo.n;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const u32 j = wbase + i * 32 + lane;
+      if (j < nn) nx->key[i] = in[nb + j]; else key_zero(nx->key[i]);
     }
   }
 
@@ -760,6 +794,56 @@ sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
 #undef MB_SX_CALL
 }
 
+//  Persistent form of the sweep (MB_SORT=7): grid = the CTAs that fit the device at once; tiles are still claimed from the
+//  pass's counter in increasing order, so a tile's predecessors are always claimed by a resident CTA that depends on lower
+//  tiles only -- the look-back cannot dead-lock.
+template <int KW, int VER>
+__global__ void __launch_bounds__(SweepShape<VER>::THREADS, SweepShape<VER>::MIN_CTAS)
+sortp_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
+                   const TileInfo *__restrict__ info, u64 nTiles,
+                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, u32 wide,
+                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
+  typedef SweepX<KW, VER> S;
+  extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
+  __shared__ u32  binOff[S::RADIX + 1];
+  __shared__ u64  gofs[S::RADIX];
+  __shared__ u32  gofs32[S::RADIX];
+  __shared__ u32  warpTot[S::WARPS];
+  __shared__ u64  sTile, sNext;
+
+  if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+  u64 tile = sTile;
+  if (tile >= nTiles) return;
+  TileInfo ti = info[tile];
+
+  SweepXShared sm;
+  sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.gofs32 = gofs32;  sm.warpTot = warpTot;
+  SweepNext<KW, VER> nx;
+  nx.info = info;  nx.nTiles = nTiles;  nx.tileCounter = tileCounter;  nx.sNext = &sNext;  nx.nextTile = ~0ull;
+  {                                                       //  the first tile's keys: the only exposed load of this CTA
+    const u32 lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 32 * S::ITEMS;
+#pragma unroll
+    for (int i = 0; i < S::ITEMS; i++) {
+      const u32 j = wbase + i * 32 + lane;
+      if (j < ti.n) nx.key[i] = in[ti.begin + j]; else key_zero(nx.key[i]);
+    }
+  }
+  const bool byte = (S::RBITS == 8) && (bits == 8) && ((shift & 7) == 0);
+  for (;;) {
+    const u32  seg     = ti.seg & 0x7fffffffu;
+    const bool isFirst = (ti.seg >> 31) != 0;
+    const bool full    = (ti.n == (u32)S::TILE);
+#define MB_SP_CALL(F, B) sweepx_tile<KW, VER, F, B, true>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm, &nx)
+    if (S::RBITS == 8 && byte) { if (full) MB_SP_CALL(true, true);  else MB_SP_CALL(false, true);  }
+    else                       { if (full) MB_SP_CALL(true, false); else MB_SP_CALL(false, false); }
+#undef MB_SP_CALL
+    if (nx.nextTile >= nTiles) break;
+    tile = nx.nextTile;  ti = nx.nextInfo;
+    __syncthreads();                                      //  everybody has copied its keys out of the stage buffer
+  }
+}
+
 }  //  namespace
 
 
@@ -772,11 +856,11 @@ static int g_sortVersion = 0;
 int mb_sort_version(void) {
   if (g_sortVersion == 0) {
     const char *e = getenv("MB_SORT");
-    g_sortVersion = (e && e[0] >= '1' && e[0] <= '6' && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
+    g_sortVersion = (e && e[0] >= '1' && e[0] <= '7' && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
   }
   return g_sortVersion;
 }
-void mb_sort_set_version(int v) { g_sortVersion = (v >= 1 && v <= 6) ? v : MB_SORT_DEFAULT_VERSION; }
+void mb_sort_set_version(int v) { g_sortVersion = (v >= 1 && v <= 7) ? v : MB_SORT_DEFAULT_VERSION; }
 u32  mb_sort_radix_bits(void) {
   switch (mb_sort_version()) {
     case 2:  return SweepShape<2>::RBITS;
@@ -784,6 +868,7 @@ u32  mb_sort_radix_bits(void) {
     case 4:  return SweepShape<4>::RBITS;
     case 5:  return SweepShape<5>::RBITS;
     case 6:  return SweepShape<6>::RBITS;
+    case 7:  return SweepShape<7>::RBITS;
     default: return MB_RADIX_BITS;
   }
 }
@@ -911,6 +996,7 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 4>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 5>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 6>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortp_sweep_kernel<KW, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 7>::BYTES)) != cudaSuccess) return e;
   for (u32 p = 0; p < plan.nPasses; p++) {
 #define MB_SX_LAUNCH(V) do { typedef SweepX<KW, V> SX;                                                                                         \
       sortx_sweep_kernel<KW, V><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                       \
@@ -920,6 +1006,19 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     else if (version == 4) MB_SX_LAUNCH(4);
     else if (version == 5) MB_SX_LAUNCH(5);
     else if (version == 6) MB_SX_LAUNCH(6);
+    else if (version == 7) {
+      typedef SweepX<KW, 7> SX;
+      static int perSm = 0, sms = 0;                         //  co-resident CTAs: the grid of the persistent kernel
+      if (!perSm) {
+        int dev = 0;  cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sortp_sweep_kernel<KW, 7>, SX::THREADS, SX::BYTES)) != cudaSuccess) return e;
+        if (perSm < 1) perSm = 1;
+      }
+      const u64 grid = std::min<u64>(nTiles, (u64)sms * perSm);
+      sortp_sweep_kernel<KW, 7><<<(unsigned)grid, SX::THREADS, SX::BYTES, s>>>(src, dst, info, nTiles, ghist, plan.nPasses, p,
+                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1);
+    }
     else
       sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
                                                                      plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);

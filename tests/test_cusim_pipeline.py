@@ -209,3 +209,18 @@ def test_sim_count_batches_pushed_bases_and_output_buffer(tmp_path, monkeypatch)
         c.write_db(out)
     util.assert_same_db(ora, out)
     assert st.nBatches >= 3
+
+
+@pytest.mark.parametrize("k,w_prefix", [(21, 12), (31, 9), (51, 8)])
+def test_sim_experimental_persistent_sweep(tmp_path, k, w_prefix):
+    """MB_SORT=7 (not the default; to be measured in round 2): the sweep as a persistent kernel whose CTAs claim the next tile
+    and load its keys while the current tile waits for its predecessors and copies out -- whole pipeline, many segments,
+    full and ragged tiles, all three key widths."""
+    import ctypes
+    L = mb.lib()
+    L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
+    old = L.mb_dbg_sort_version(7)
+    try:
+        _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 3_000, 150, 0.004, 17 + k)}, k, w_prefix)
+    finally:
+        L.mb_dbg_sort_version(old)

@@ -72,10 +72,10 @@ def test_extract_empty_and_no_kmers():
         assert len(glo) == 0
 
 
-_SHAPES = [1, 2, 3, 4] + ([5, 6] if os.environ.get("MB_TEST_EXPERIMENTAL") else [])     # 5, 6: not yet run on a GPU
+_SHAPES = [1, 2, 3, 4] + ([5, 6, 7] if os.environ.get("MB_TEST_EXPERIMENTAL") else [])     # 5, 6, 7: not yet run on a GPU
 
 
-@pytest.fixture(params=_SHAPES, ids=["sweep_v1", "sweep_128x8", "sweep_256x6", "sweep_256x7", "sweep_512x6", "sweep_256x6r"][: len(_SHAPES)])
+@pytest.fixture(params=_SHAPES, ids=["sweep_v1", "sweep_128x8", "sweep_256x6", "sweep_256x7", "sweep_512x6", "sweep_256x6r", "sweep_persistent"][: len(_SHAPES)])
 def sort_version(request):
     """Both sweep kernels (csrc/sort.cu): v1 = 6-bit digits, v2 = 8-bit digits."""
     L = mb.lib()

@@ -11,6 +11,8 @@ echo "== a. the GPU suite, experimental tests included";  date +%T
 MB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 echo "== b. A/B: experiments (rank by match, ...) at 8 Gbp in 5 passes";  date +%T
 timeout 120 python tools/ab_bench.py 8 5 experiments 2>&1 | tee $OUT/ab_8gbp_experiments.jsonl | cut -c1-420
+echo "== b2. A/B: the sweep shapes, incl. the unmeasured ones (5: 512x6, 6: 256x6 at 128 registers, 7: persistent with prefetch)";  date +%T
+timeout 240 python tools/ab_bench.py 8 5 sortonly 2>&1 | tee $OUT/ab_8gbp_shapes_r2.jsonl | cut -c1-420
 echo "== c. bench 100 Gbp: default, then with the copy-back overlapped";  date +%T
 timeout 420 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_100gbp_default.json 2> $OUT/bench_100gbp_default.err; cut -c1-1500 $OUT/bench_100gbp_default.json
 MB_OVERLAP_D2H=1 timeout 420 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_100gbp_overlap.json 2> $OUT/bench_100gbp_overlap.err; cut -c1-1500 $OUT/bench_100gbp_overlap.json
