@@ -259,7 +259,9 @@ def main():
     achieved = sort_bytes / (stats.msSort / 1000) / 1e9 if stats.msSort > 0 else 0.0
     sweep_version = mb.lib().mb_dbg_sort_version(0)            # 0: query only
     sweep_name = {1: "sort_sweep_kernel (256 threads, 6-bit digits)", 2: "sortx_sweep_kernel<128 threads, 8-bit digits>",
-                  3: "sortx_sweep_kernel<256 threads, 6-bit digits>", 4: "sortx_sweep_kernel<256 threads, 7-bit digits>"}.get(sweep_version, "?")
+                  3: "sortx_sweep_kernel<256 threads, 6-bit digits>", 4: "sortx_sweep_kernel<256 threads, 7-bit digits>",
+                  5: "sortx_sweep_kernel<512 threads, 6-bit digits>", 6: "sortx_sweep_kernel<256 threads, 6-bit digits, 2 CTAs/SM>",
+                  7: "sortp_sweep_kernel<256 threads, 6-bit digits, persistent>"}.get(sweep_version, "?")
     traffic = None                                              # DRAM bytes per launch, from the committed ncu capture of this kernel
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic_sweep.json")) as fh:
