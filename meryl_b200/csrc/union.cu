@@ -904,9 +904,10 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
           if (rc != MB_OK) goto done;
           MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
           //  many short blocks (a count db at prefix width 24 has 16.8 M of them): one thread per block fills the device;
-          //  few long blocks (stream-writer output, small count dbs): one warp per block (MB_DECODE=thread|warp forces one)
+          //  few long blocks (stream-writer output, small count dbs): one warp per block.  MB_DECODE=thread|warp|auto; the
+          //  warp form has not run on a GPU yet, so it is not chosen unless asked for (auto: by the block count).
           const char *dm = getenv("MB_DECODE");
-          const bool byWarp = dm ? !strcmp(dm, "warp") : tab.size() < ((size_t)1 << 18);
+          const bool byWarp = dm && (!strcmp(dm, "warp") || (!strcmp(dm, "auto") && tab.size() < ((size_t)1 << 18)));
           if (byWarp) {
             const unsigned grid = (unsigned)((tab.size() + DW_WARPS - 1) / DW_WARPS);
             if (kw == 1) decode_warp_kernel<1><<<grid, DW_WARPS * 32, 0, s>>>(dRaw, inBytes[i], dTab, tab.size(), in[i].wSuffix, (u64 *)dKey, dVal, idx, dErr);

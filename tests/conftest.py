@@ -18,3 +18,12 @@ def _build_oracle():
     """oracle/ is test infrastructure: build the C restatement (and, where
     /root/reference exists, the unmodified reference binary) before any test."""
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+
+
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that hangs (a spinning kernel) must end the process, not sit on the box until the outer limit."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900, method="thread"))

@@ -58,6 +58,6 @@ def test_sim_union_small_ring(tmp_path, monkeypatch):
     uc.case_small_ring(str(tmp_path), monkeypatch)
 
 
-@pytest.mark.parametrize("k,decoder", [(21, "warp"), (21, "thread"), (51, "warp"), (64, "thread"), (32, "warp")])
+@pytest.mark.parametrize("k,decoder", [(21, "warp"), (21, "thread"), (51, "warp"), (64, "thread"), (32, "warp"), (31, "auto")])
 def test_sim_union_long_blocks(tmp_path, monkeypatch, k, decoder):
     uc.case_long_blocks(str(tmp_path), monkeypatch, k, decoder)

@@ -8,7 +8,7 @@ mkdir -p $OUT
 exec > >(tee $OUT/round2a.log) 2>&1
 date; nvidia-smi --query-gpu=name,memory.total --format=csv,noheader
 echo "== a. the GPU suite, experimental tests included";  date +%T
-MB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+MB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4
 echo "== b. A/B: experiments (rank by match, ...) at 8 Gbp in 5 passes";  date +%T
 timeout 120 python tools/ab_bench.py 8 5 experiments 2>&1 | tee $OUT/ab_8gbp_experiments.jsonl | cut -c1-420
 echo "== b2. A/B: the sweep shapes, incl. the unmeasured ones (5: 512x6, 6: 256x6 at 128 registers, 7: persistent with prefetch)";  date +%T
