@@ -278,43 +278,48 @@ def main():
     # ---- e2e: host buffer -> C ABI -> host images ----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host = torch.empty(n_reads * rec0, dtype=torch.uint8, pin_memory=True)
-        for first in range(0, n_reads, chunk_reads):
-            m = min(chunk_reads, n_reads - first)
-            mb.synth_reads_device(dev_chunk.data_ptr(), first_read + first, m, READ_LEN, GENOME_LEN, ERR, SEED, 0)
-            host[first * rec0: (first + m) * rec0].copy_(dev_chunk[: m * rec0])
-        torch.cuda.synchronize()
-        e_steps, est = [], None
-        n_e2e = max(1, min(args.steps, 2)) + 1
-        out_host = None                               # caller-owned pinned buffer for the db images (sized by the warm-up step)
-        for it in range(n_e2e):
-            barrier()
-            t0 = time.perf_counter()
-            c = new_counter(0)
-            try:
-                if out_host is not None:
-                    c.set_output_buffer(out_host.data_ptr(), out_host.numel())
-                c.add_bases_ptr(host.data_ptr(), n_reads * rec0, end_of_sequence=True)
-                c.count()
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                est = c.stats()
-            finally:
-                c.close()
-            barrier()
-            if it >= 1:
-                e_steps.append(dt)
-            elif out_host is None:
-                out_host = torch.empty(int(est.dbBytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
-        dt = sum(e_steps) / len(e_steps)
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_kmers / dt, "unit": "k-mers/s", "h2d_bytes_per_step": int(est.h2dBytes),
-               "d2h_bytes_per_step": int(est.d2hBytes), "seconds_per_step": dt,
-               "input": "pinned host buffer of the base stream (1 B/base + '.' per read), output: 129 db images in (pinned) host memory"}
-        del host, out_host
+        try:
+            host = torch.empty(n_reads * rec0, dtype=torch.uint8, pin_memory=True)
+            for first in range(0, n_reads, chunk_reads):
+                m = min(chunk_reads, n_reads - first)
+                mb.synth_reads_device(dev_chunk.data_ptr(), first_read + first, m, READ_LEN, GENOME_LEN, ERR, SEED, 0)
+                host[first * rec0: (first + m) * rec0].copy_(dev_chunk[: m * rec0])
+            torch.cuda.synchronize()
+            e_steps, est = [], None
+            n_e2e = max(1, min(args.steps, 2)) + 1
+            out_host = None                               # caller-owned pinned buffer for the db images (sized by the warm-up step)
+            for it in range(n_e2e):
+                barrier()
+                t0 = time.perf_counter()
+                c = new_counter(0)
+                try:
+                    if out_host is not None:
+                        c.set_output_buffer(out_host.data_ptr(), out_host.numel())
+                    c.add_bases_ptr(host.data_ptr(), n_reads * rec0, end_of_sequence=True)
+                    c.count()
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    est = c.stats()
+                finally:
+                    c.close()
+                barrier()
+                if it >= 1:
+                    e_steps.append(dt)
+                elif out_host is None:
+                    out_host = torch.empty(int(est.dbBytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
+            dt = sum(e_steps) / len(e_steps)
+            if world > 1:
+                t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": total_kmers / dt, "unit": "k-mers/s", "h2d_bytes_per_step": int(est.h2dBytes),
+                   "d2h_bytes_per_step": int(est.d2hBytes), "seconds_per_step": dt,
+                   "input": "pinned host buffer of the base stream (1 B/base + '.' per read), output: 129 db images in (pinned) host memory"}
+            del host, out_host
+        except Exception as ex:                 # the device-resident line above stands; say why there is no end-to-end number
+            if world > 1:
+                raise                           # (a rank that drops out of the collectives would hang the others)
+            e2e = {"value": None, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:300]}
     del dev_chunk
 
     # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
