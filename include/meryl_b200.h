@@ -128,6 +128,10 @@ int mb_add_bases(mb_ctx *ctx, const char *bases, uint64_t len, int endOfSequence
 int mb_add_bases_device(mb_ctx *ctx, const char *dBases, uint64_t len);             /*  device memory, work-buffer format ('.' = break)  */
 int mb_add_file(mb_ctx *ctx, const char *path);                                     /*  FASTA/FASTQ, optionally .gz/.bz2/.xz via popen like the reference  */
 int mb_add_file_bytes(mb_ctx *ctx, const uint8_t *data, uint64_t len);              /*  a FASTA/FASTQ file image in host memory  */
+/*  Shard `shard` of `nShards` of a plain FASTA/FASTQ file, cut at record starts (multi-GPU: rank r adds shard r of every
+ *  input).  All shards together are exactly the file if every call succeeds; a shard that does not end at a record boundary
+ *  (the cut was guessed wrong) fails with MB_EFORMAT.  Compressed files and stdin: MB_EINVAL.  */
+int mb_add_file_shard(mb_ctx *ctx, const char *path, uint32_t shard, uint32_t nShards);
 
 /*  Multi-GPU (one process per GPU).  Rank 0 calls mb_comm_unique_id, the caller broadcasts the
  *  128 bytes (torch.distributed / MPI / files), every rank calls mb_comm_init before mb_count.  */

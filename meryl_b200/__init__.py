@@ -90,6 +90,7 @@ def lib() -> ctypes.CDLL:
         L.mb_add_bases_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
         L.mb_add_file.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.mb_add_file_bytes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.mb_add_file_shard.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32]
         L.mb_comm_unique_id.argtypes = [ctypes.c_void_p]
         L.mb_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mb_file_owner_of.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
@@ -187,6 +188,9 @@ class Counter:
 
     def add_file(self, path: str) -> None:
         _check(lib().mb_add_file(self._h, os.fsencode(path)))
+
+    def add_file_shard(self, path: str, shard: int, n_shards: int) -> None:
+        _check(lib().mb_add_file_shard(self._h, os.fsencode(path), shard, n_shards))
 
     def add_file_bytes(self, data: bytes) -> None:
         _check(lib().mb_add_file_bytes(self._h, data, len(data)))

@@ -4,7 +4,7 @@
 //  (src/meryl/merylCommandBuilder.C:188-326 options, :346-348 operations, :441-461 output,
 //  :538-549 sequence inputs; usage text src/meryl/meryl.C:96-171):
 //
-//      meryl-b200 [-V|-Q|-P|-C] [k=K] [n=N] [memory=GB] [threads=T]
+//      meryl-b200 [-V|-Q|-P|-C] [k=K] [n=N] [memory=GB] [threads=T] [gpus=N]
 //                 count|count-forward|count-reverse [compress] <seq files...> output <db.meryl>
 //
 //  Words are order-free like the reference's.  Errors are a message on stderr and exit(1)
@@ -17,6 +17,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <sched.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
 #include <string>
 #include <vector>
 
@@ -101,11 +105,74 @@ static int unionSumMain(int argc, char **argv) {
   return 0;
 }
 
+//  gpus=N: one process per GPU (forked before anything touches CUDA), rank r = device r.  Every rank ingests shard r of every
+//  input (mb_add_file_shard: the reads are split evenly, cut at record starts), the library routes the k-mers to the GPU that
+//  owns their data file, every rank writes its own files into the output directory, rank 0 the master index.
+//  The NCCL id travels through a page of shared memory.
+struct SharedPage {
+  volatile int idReady;                 //  1: id[] is valid, -1: rank 0 failed before it had one
+  uint8_t      id[128];
+  mb_stats     st[32];
+  char         err[32][512];
+};
+
+static int multiGpuCount(uint32_t nGpus, mb_config cfg, const std::vector<const char *> &inputs, const char *outDir, mb_stats *total) {
+  SharedPage *sh = (SharedPage *)mmap(nullptr, sizeof(SharedPage), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (sh == MAP_FAILED) { perror("mmap"); return 1; }
+  memset((void *)sh, 0, sizeof(SharedPage));
+  std::vector<pid_t> pids(nGpus, -1);
+  for (uint32_t r = 0; r < nGpus; r++) {
+    pids[r] = fork();
+    if (pids[r] < 0) { perror("fork"); return 1; }
+    if (pids[r] == 0) {                                   //  rank r
+      int rc = MB_OK;
+      if (r == 0) {
+        rc = mb_comm_unique_id(sh->id);
+        __sync_synchronize();
+        sh->idReady = (rc == MB_OK) ? 1 : -1;
+      } else {
+        while (sh->idReady == 0) sched_yield();
+        if (sh->idReady < 0) _exit(2);
+      }
+      mb_ctx *c = nullptr;
+      cfg.device = (int32_t)r;  cfg.rank = r;  cfg.worldSize = nGpus;
+      if (rc == MB_OK) rc = mb_create(&cfg, &c);
+      if (rc == MB_OK) rc = mb_comm_init(c, sh->id);
+      for (size_t i = 0; rc == MB_OK && i < inputs.size(); i++) rc = mb_add_file_shard(c, inputs[i], r, nGpus);
+      if (rc == MB_OK) rc = mb_count(c);
+      if (rc == MB_OK) rc = mb_write_db(c, outDir);
+      if (rc == MB_OK) rc = mb_get_stats(c, &sh->st[r]);
+      if (rc != MB_OK) { strncpy(sh->err[r], mb_last_error(), sizeof(sh->err[r]) - 1); _exit(1); }   //  (the peers will fail in their collectives)
+      mb_destroy(c);
+      _exit(0);
+    }
+  }
+  int bad = 0;
+  for (uint32_t r = 0; r < nGpus; r++) {
+    int status = 0;
+    if (waitpid(pids[r], &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+      if (!bad) fprintf(stderr, "ERROR: rank %u (GPU %u): %s\n", r, r, sh->err[r][0] ? sh->err[r] : "process ended abnormally");
+      bad = 1;
+      for (uint32_t q = 0; q < nGpus; q++) if (q != r && pids[q] > 0) kill(pids[q], SIGTERM);     //  do not leave the others waiting in a collective
+    }
+  }
+  if (!bad) {
+    *total = sh->st[0];
+    for (uint32_t r = 1; r < nGpus; r++) {
+      total->nKmers += sh->st[r].nKmers;  total->nDistinct += sh->st[r].nDistinct;  total->nUnique += sh->st[r].nUnique;
+      total->nBases += sh->st[r].nBases;  total->dbBytes += sh->st[r].dbBytes;
+      if (sh->st[r].msTotal > total->msTotal) total->msTotal = sh->st[r].msTotal;
+    }
+  }
+  munmap((void *)sh, sizeof(SharedPage));
+  return bad;
+}
+
 int main(int argc, char **argv) {
   for (int i = 1; i < argc; i++)
     if (setOpOf(argv[i]) >= 0) return unionSumMain(argc, argv);
 
-  uint32_t k = 0, mode = 0;
+  uint32_t k = 0, mode = 0, nGpus = 1;
   uint64_t nExpected = 0, memBytes = physicalMemory();
   bool haveOp = false, onlyConfig = false, quiet = false, compress = false;
   const char *outDir = nullptr;
@@ -121,6 +188,7 @@ int main(int argc, char **argv) {
     else if (!strncmp(w, "n=", 2))            { nExpected = strtoull(w + 2, 0, 10); }
     else if (!strncmp(w, "memory=", 7))       { memBytes = (uint64_t)(strtod(w + 7, 0) * 1024 * 1024 * 1024); }
     else if (!strncmp(w, "threads=", 8))      { }                         //  no CPU worker threads to size
+    else if (!strncmp(w, "gpus=", 5))         { nGpus = (uint32_t)strtoul(w + 5, 0, 10); }     //  (not a word of the reference)
     else if (isCountWord(w, &mode))           { haveOp = true; }
     else if (!strcmp(w, "compress"))          { compress = true; }           //  merylCommandBuilder.C:237-240 (here: all inputs)
     else if (!strcmp(w, "output")) {
@@ -149,6 +217,7 @@ int main(int argc, char **argv) {
   if (k == 0)                    { fprintf(stderr, "ERROR: Kmer size not supplied with modifier k=<kmer-size>.\n"); return 1; }
   if (!outDir && !onlyConfig)    { fprintf(stderr, "ERROR: No output specified for count operation.\n"); return 1; }
   if (inputs.empty())            { fprintf(stderr, "ERROR: No sequence inputs for count operation.\n"); return 1; }
+  if (nGpus == 0 || nGpus > 32 || 64 % nGpus) { fprintf(stderr, "ERROR: gpus=%u: the number of GPUs must divide 64 (1, 2, 4, 8, 16, 32).\n", nGpus); return 1; }
 
   if (nExpected == 0)
     for (const char *p : inputs) nExpected += mb_estimate_kmers_in_file(p);
@@ -176,7 +245,9 @@ int main(int argc, char **argv) {
   if (compress) cfg.flags |= MB_FLAG_COMPRESS;
 
   mb_stats st;
-  if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), outDir, &st) != MB_OK) {
+  if (nGpus > 1) {
+    if (multiGpuCount(nGpus, cfg, inputs, outDir, &st) != 0) return 1;
+  } else if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), outDir, &st) != MB_OK) {
     fprintf(stderr, "ERROR: %s\n", mb_last_error());
     return 1;
   }

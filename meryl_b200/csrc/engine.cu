@@ -451,6 +451,66 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
 }
 
 
+//  One of nShards pieces of a plain FASTA/FASTQ file (multi-GPU: rank r ingests shard r of every input; the reads are split
+//  evenly).  The file is cut at byte i * size / nShards, moved forward to the next line that starts a record
+//  of the file's kind (the kind of its first record: '>'; or '@' if the line after next starts with '+', since a quality
+//  line may start with '@' too).  Whether that guess was
+//  right shows at the END of the previous piece: its parser must stand at a record boundary there.  Shard 0 starts at the
+//  start of the file, so if every shard reports success every cut was a true record start (by induction) and the shards
+//  together are exactly the file; a shard whose end is not a boundary fails with MB_EFORMAT and the job must not be trusted.
+static size_t shardCut(const uint8_t *d, size_t n, uint32_t i, uint32_t nShards) {
+  if (i == 0) return 0;
+  if (i >= nShards) return n;
+  size_t p = (size_t)((unsigned __int128)n * i / nShards);
+  while (p < n) {
+    const uint8_t *lf = (const uint8_t *)memchr(d + p, '\n', n - p);
+    if (!lf || (size_t)(lf - d) + 1 >= n) return n;
+    p = (size_t)(lf - d) + 1;
+    if (d[p] == '>' && d[0] == '>') return p;              //  (in a FASTQ file a line that starts with '>' is a quality line)
+    if (d[p] == '@' && d[0] == '@') {
+      const uint8_t *l1 = (const uint8_t *)memchr(d + p, '\n', n - p);
+      const uint8_t *l2 = l1 ? (const uint8_t *)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - d)) : nullptr;
+      if (l2 && (size_t)(l2 + 1 - d) < n && l2[1] == '+') return p;
+    }
+  }
+  return n;
+}
+
+extern "C" int mb_add_file_shard(mb_ctx *c, const char *path, uint32_t shard, uint32_t nShards) {
+  mb_clear_error();
+  if (!c || !path || nShards == 0 || shard >= nShards)  return mb_fail(MB_EINVAL, "mb_add_file_shard: bad argument");
+  if (c->counted)   return mb_fail(MB_ESTATE, "mb_add_file_shard: already counted");
+  if (nShards == 1) return mb_add_file(c, path);
+  const size_t L = strlen(path);
+  if (!strcmp(path, "-") || (L > 3 && (!strcmp(path + L - 3, ".gz") || !strcmp(path + L - 3, ".xz"))) ||
+      (L > 4 && (!strcmp(path + L - 4, ".bz2") || !strcmp(path + L - 4, ".zst"))))
+    return mb_fail(MB_EINVAL, "'%s': only plain files can be split into shards (a compressed stream has no record index)", path);
+  const int fd = open(path, O_RDONLY);
+  struct stat stt;
+  if (fd < 0 || fstat(fd, &stt) != 0 || !S_ISREG(stt.st_mode)) { if (fd >= 0) close(fd); return mb_fail(MB_EIO, "cannot open '%s'", path); }
+  const size_t sz = (size_t)stt.st_size;
+  if (sz == 0) { close(fd); return MB_OK; }
+  void *m = mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return mb_fail(MB_EIO, "cannot map '%s'", path);
+  const uint8_t *d = (const uint8_t *)m;
+  int rc = MB_OK;
+  if (!SeqParser::sniff(d, sz < 65536 ? sz : 65536)) rc = mb_fail(MB_EFORMAT, "'%s' is not FASTA or FASTQ", path);
+  const size_t lo = shardCut(d, sz, shard, nShards), hi = shardCut(d, sz, shard + 1, nShards);
+  SeqParser ps(parserSink, c);
+  const size_t BLK = (size_t)256 << 20;
+  for (size_t at = lo; rc == MB_OK && at < hi; at += BLK) rc = mb_parse_parallel(parserSink, c, ps, d + at, std::min(BLK, hi - at));
+  if (rc == MB_OK && hi < sz) {                           //  the next shard starts here: is it a record boundary?
+    const SeqParser::State st = ps.state();
+    if (!(st == SeqParser::A || st == SeqParser::Q || st == SeqParser::G))
+      rc = mb_fail(MB_EFORMAT, "'%s': shard %u of %u does not end at a record boundary (multi-line FASTQ?); count this file on one GPU", path, shard, nShards);
+  }
+  munmap(m, sz);
+  if (rc != MB_OK) return rc;
+  return (lo < hi || shard == 0) ? ps.finish() : MB_OK;
+}
+
+
 //  ------------------------------------------------------------------------------------------
 //  counting
 //  ------------------------------------------------------------------------------------------

@@ -224,3 +224,71 @@ def test_sim_experimental_persistent_sweep(tmp_path, k, w_prefix):
         _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 3_000, 150, 0.004, 17 + k)}, k, w_prefix)
     finally:
         L.mb_dbg_sort_version(old)
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_sim_file_shards_are_the_file(tmp_path, n_shards):
+    """mb_add_file_shard (multi-GPU ingest: rank r takes shard r of every input): the shards, added one after the other to
+    one context, are exactly the file -- 4-line FASTQ with quality lines that start with '@' and '+', multi-line FASTA,
+    CRLF, a file shorter than the number of shards."""
+    rng = np.random.default_rng(n_shards)
+    fq = bytearray()
+    for i in range(900):
+        seq = synth.random_bases(int(rng.integers(40, 160)), rng).tobytes()
+        q = bytes([b"@+I>"[int(rng.integers(0, 4))]]) + b"I" * (len(seq) - 1)
+        fq += b"@r%d\n%s\n+\n%s\n" % (i, seq, q)
+    fa = bytearray()
+    for i in range(40):
+        seq = synth.random_bases(int(rng.integers(100, 3000)), rng).tobytes()
+        fa += b">s%d x\r\n" % i + b"\r\n".join(seq[j:j + 70] for j in range(0, len(seq), 70)) + b"\r\n"
+    files = {"a.fq": bytes(fq), "b.fa": bytes(fa), "tiny.fa": b">t\nACGTACGTACGTACGTACGTACGTAC\n"}
+    paths = []
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+        paths.append(str(tmp_path / name))
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=21", "wprefix=8", "count", *paths, "output", ora])
+    with mb.Counter(21, 8) as c:
+        for s in range(n_shards):
+            for p in paths:
+                c.add_file_shard(p, s, n_shards)
+        c.count()
+        c.write_db(out)
+    util.assert_same_db(ora, out)
+
+
+def test_sim_file_shard_exact_or_error(tmp_path):
+    """Compressed files cannot be split.  For files the cut heuristic was not made for (multi-line FASTQ, quality lines that
+    look like record starts, FASTA records inside a FASTQ file) the shards are still exactly the file -- or a shard reports
+    that it does not end at a record boundary; never a silently different db."""
+    gz = tmp_path / "r.fa.gz"
+    gz.write_bytes(b"\x1f\x8b")
+    with mb.Counter(21, 8) as c:
+        with pytest.raises(mb.MerylB200Error) as e:
+            c.add_file_shard(str(gz), 0, 2)
+        assert "plain files" in str(e.value)
+    rng = np.random.default_rng(9)
+    errors = exact = 0
+    for case in range(6):
+        lines = [b"@r0", b"ACGTACGTACGTACGTACGTACGTACGTACGT", b"+", b"IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII"]     # (the format sniff wants one good record)
+        for i in range(400):
+            kind = int(rng.integers(0, 6))
+            seq = synth.random_bases(int(rng.integers(30, 90)), rng).tobytes()
+            lines.append([b"@r%d" % i, seq, b"+", b"@" + seq[1:], b"+" + seq[1:], b">x%d" % i][kind])
+        f = tmp_path / ("soup%d.fq" % case)
+        f.write_bytes(b"\n".join(lines) + b"\n")
+        ora, out = str(tmp_path / ("ora%d.meryl" % case)), str(tmp_path / ("sim%d.meryl" % case))
+        util.run_oracle(["k=21", "wprefix=8", "count", str(f), "output", ora])
+        with mb.Counter(21, 8) as c:
+            try:
+                for s in range(5):
+                    c.add_file_shard(str(f), s, 5)
+            except mb.MerylB200Error as ex:
+                assert "record boundary" in str(ex)
+                errors += 1
+                continue
+            c.count()
+            c.write_db(out)
+        util.assert_same_db(ora, out)
+        exact += 1
+    assert errors + exact == 6

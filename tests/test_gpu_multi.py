@@ -125,3 +125,21 @@ def test_multi_gpu_p2p_scatter_db_bit_exact(tmp_path, world, k, cap, s32):
         os.remove(p)
         assert st[1] == n_reads * (L - k + 1) and st[3] == (4 if s32 else 8 if k <= 32 else 16) and (st[2] > 1) == bool(cap)
     util.assert_same_db(ora, out)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_cli_gpus_word(tmp_path, world):
+    """`meryl-b200 gpus=N count ...`: the CLI forks one process per GPU, rank r ingests shard r of every input file
+    (mb_add_file_shard), the NCCL id travels through shared memory; same directory as the oracle's."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import subprocess
+    fq, fa = tmp_path / "reads.fq", tmp_path / "contigs.fa"
+    fq.write_bytes(synth.reads_fastq_bytes(200_000, 40_000, 150, 0.003, 5))
+    fa.write_bytes(synth.fasta_bytes(5, 100_000, 9))
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "cli.meryl")
+    util.run_oracle(["k=21", "memory=2", "count", str(fq), str(fa), "output", ora])
+    p = subprocess.run([mb.CLI_PATH, "k=21", "memory=2", "gpus=%d" % world, "count", str(fq), str(fa), "output", out],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    util.assert_same_db(ora, out)

@@ -208,6 +208,10 @@ def test_cli_errors_like_the_reference(tmp_path):
     assert p.returncode == 1 and "is not a meryl database" in p.stderr
     p = _cli(["union-sum", "output", "z.meryl"])
     assert p.returncode == 1 and "needs at least one input database" in p.stderr
+    p = _cli(["k=21", "gpus=3", "count", str(fa), "output", str(tmp_path / "o.meryl")])     # (gpus= is ours: one process per GPU)
+    assert p.returncode == 1 and "must divide 64" in p.stderr
+    p = _cli(["k=21", "gpus=2", "count", str(fa), "output", str(tmp_path / "o.meryl")])     # no GPU here: every rank says so
+    assert p.returncode == 1 and "rank" in p.stderr and not (tmp_path / "o.meryl" / "merylIndex").exists()
 
 
 def test_cli_config_only_prints_the_canu_line(tmp_path):
