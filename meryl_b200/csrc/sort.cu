@@ -103,9 +103,10 @@ template <int KW>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
                  const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
-                 SortPassTable pt, u32 radix, u64 *__restrict__ ghist) {
+                 SortPassTable pt, u32 radix, u64 *__restrict__ ghist, u32 unrolled) {
   typedef typename KeyT<KW>::type Key;
   const int TILE = SORT_THREADS * SortShape<KW>::ITEMS;
+  const int HIST_UNROLL = 8;
   __shared__ u32 sh[HIST_WORDS];                      //  nPasses * radix <= HIST_WORDS (checked by the host)
 
   const u32 t = threadIdx.x;
@@ -136,6 +137,26 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
     u64 n = segStart[seg + 1] - begin;
     if (n > (u64)TILE) n = TILE;
 
+    //  HIST_UNROLL independent loads per thread are in flight before the first shared-memory atomic (one load at a time
+    //  left the kernel waiting on HBM latency: 1.3 TB/s measured).  MB_HIST_SIMPLE=1 keeps the one-load loop for A/B.
+    if (unrolled) {
+      const Key *kp = keys + begin;
+      u32 j = t;
+      for (; j + (HIST_UNROLL - 1) * SORT_THREADS < (u32)n; j += HIST_UNROLL * SORT_THREADS) {
+        Key k[HIST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < HIST_UNROLL; u++) k[u] = kp[j + u * SORT_THREADS];
+#pragma unroll
+        for (int u = 0; u < HIST_UNROLL; u++)
+          for (u32 p = 0; p < pt.nPasses; p++)
+            atomicAdd(&sh[p * radix + key_field(k[u], pt.shift[p], pt.bits[p])], 1u);
+      }
+      for (; j < (u32)n; j += SORT_THREADS) {
+        const Key key = kp[j];
+        for (u32 p = 0; p < pt.nPasses; p++)
+          atomicAdd(&sh[p * radix + key_field(key, pt.shift[p], pt.bits[p])], 1u);
+      }
+    } else
     for (u32 j = t; j < (u32)n; j += SORT_THREADS) {
       const Key key = keys[begin + j];
       for (u32 p = 0; p < pt.nPasses; p++)
@@ -978,7 +999,8 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     hg.total += 1u << hg.bitsAll[g];
   }
   if (histSingle || hg.total * 4 > 96 * 1024) {
-    sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist);
+    sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist,
+                                                                     getenv("MB_HIST_SIMPLE") ? 0u : 1u);
   } else {
     if ((e = cudaFuncSetAttribute(sort_hist2_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(hg.total * 4))) != cudaSuccess) return e;
     sort_hist2_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, hg.total * 4, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, hg, plan.nPasses, (u32)R, ghist);
