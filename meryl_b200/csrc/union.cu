@@ -768,7 +768,7 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
           need += in[i].fileKmers[f] * (W + 4) + 512;
           nk   += in[i].fileKmers[f];
         }
-      need += 2 * (nk * (W + 4) + 1024);                                    //  merge ping-pong
+      need += (nInputs > 2 ? 2 : 1) * (nk * (W + 4) + 1024);                //  merge output (ping-pong only when a fold has more than one step)
       need += nk * ((wS + 34 + 7) / 8 + 1) + nk / 64;                    //  encoded blocks (every block <= n(b+34) + headers) ...
       need += (size_t)(f1 - f0) * blocksPerFile * (E.streamMode ? 4096 : 512 + sizeof(MbBlockMeta) + 24 + 16);   //  ... headers, tables
       need += nk / MG_TILE * 16 + nk / MB_HIST_SMALL * 4 + 65536;
@@ -938,11 +938,12 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
       //  ---- fold the lists: ((A + B) + C) + ... ; a lone input is merged with an empty list (drops zero values) ----
       u64 total = 0;
       for (u32 i = 0; i < nInputs; i++) total += listN[i];
-      void *mk[2] = { g.take(total * W + 16), g.take(total * W + 16) };
-      u32  *mv[2] = { (u32 *)g.take(total * 4 + 16), (u32 *)g.take(total * 4 + 16) };
+      const bool pingPong = nInputs > 2;                     //  one fold step writes one buffer
+      void *mk[2] = { g.take(total * W + 16), pingPong ? g.take(total * W + 16) : nullptr };
+      u32  *mv[2] = { (u32 *)g.take(total * 4 + 16), pingPong ? (u32 *)g.take(total * 4 + 16) : nullptr };
       const u64 maxTiles = total / MG_TILE + 2;
       u64 *dStatus = (u64 *)g.take((maxTiles + 2) * 8);
-      if (!mk[0] || !mk[1] || !mv[0] || !mv[1] || !dStatus) { rc = mb_fail(MB_ENOMEM, "internal: union merge buffers do not fit"); goto done; }
+      if (!mk[0] || !mv[0] || (pingPong && (!mk[1] || !mv[1])) || !dStatus) { rc = mb_fail(MB_ENOMEM, "internal: union merge buffers do not fit"); goto done; }
 
       MB_UCUDA(cudaEventRecord(ev[0], s));
       const void *curK = lists[0].first;  const u32 *curV = lists[0].second;  u64 curN = listN[0];
