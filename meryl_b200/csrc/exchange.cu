@@ -265,21 +265,25 @@ int mb_comm_exchange_suffixes(MbComm *m, const void *sendBuf, void *recvBuf, u32
     });
   }
 #endif
-  MB_NCCL(g_nccl.GroupStart());
+  //  One group per data file (every rank walks the files in the same order): a group holds at most binsPerFile sends
+  //  and binsPerFile * world receives, instead of thousands of operations in one group.
   u64 recvAt = 0;
-  for (u32 b = binLo; b < binHi; b++) {
-    const u32 own = mb_file_owner(b / binsPerFile, world);
-    const u64 mine = Cb[(size_t)me * nBins + b];
-    if (mine) MB_NCCL(g_nccl.Send(sb + sendStart[b - binLo], mine * sizeof(u32), kNcclUint8, (int)own, m->comm, s));
-    if (own == me) {
-      for (u32 src = 0; src < world; src++) {
-        const u64 c = Cb[(size_t)src * nBins + b];
-        if (c) MB_NCCL(g_nccl.Recv(rb + recvAt, c * sizeof(u32), kNcclUint8, (int)src, m->comm, s));
-        recvAt += c;
+  for (u32 f = binLo / binsPerFile; f < binHi / binsPerFile; f++) {
+    const u32 own = mb_file_owner(f, world);
+    MB_NCCL(g_nccl.GroupStart());
+    for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) {
+      const u64 mine = Cb[(size_t)me * nBins + b];
+      if (mine) MB_NCCL(g_nccl.Send(sb + sendStart[b - binLo], mine * sizeof(u32), kNcclUint8, (int)own, m->comm, s));
+      if (own == me) {
+        for (u32 src = 0; src < world; src++) {
+          const u64 c = Cb[(size_t)src * nBins + b];
+          if (c) MB_NCCL(g_nccl.Recv(rb + recvAt, c * sizeof(u32), kNcclUint8, (int)src, m->comm, s));
+          recvAt += c;
+        }
       }
     }
+    MB_NCCL(g_nccl.GroupEnd());
   }
-  MB_NCCL(g_nccl.GroupEnd());
   return MB_OK;
 }
 
