@@ -240,6 +240,11 @@ int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, c
 #define MB_OP_MODULO               22
 int mb_value_operation(uint32_t op, uint64_t param, const char *inDir, const char *outDir, int32_t device,
                        uint64_t workspaceBytes, mb_union_stats *st);
+/*  The filters' threshold given as a share of the input (merylOperation::initializeThreshold, merylOp-nextMer.C:65-125;
+ *  words distinct= / d=, word-frequency= / f= of merylCommandBuilder.C:277-290): fracDistinct -> the smallest value v such
+ *  that at least fracDistinct * numDistinct k-mers have a value <= v; wordFrequency -> wordFrequency * numTotal (wins if both
+ *  are given); negative = not given.  Host only: reads the histogram in dbDir/merylIndex.  */
+int mb_db_threshold(const char *dbDir, double fracDistinct, double wordFrequency, uint64_t *threshold);
 
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 

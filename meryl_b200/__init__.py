@@ -335,3 +335,13 @@ def value_operation(op: str, param: int, inp, output: str, device: int = -1, wor
     _check(L.mb_value_operation(11 + VALUE_OPERATIONS.index(op), param, os.fsencode(os.fspath(inp)), os.fsencode(os.fspath(output)),
                                 device, workspace_bytes, ctypes.byref(st)))
     return st
+
+
+def db_threshold(db, distinct: float | None = None, word_frequency: float | None = None) -> int:
+    """The filters' threshold given as `distinct=` / `word-frequency=` (merylOperation::initializeThreshold): mb_db_threshold."""
+    L = lib()
+    L.mb_db_threshold.argtypes = [ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_uint64)]
+    t = ctypes.c_uint64()
+    _check(L.mb_db_threshold(os.fsencode(os.fspath(db)), -1.0 if distinct is None else distinct,
+                             -1.0 if word_frequency is None else word_frequency, ctypes.byref(t)))
+    return t.value

@@ -59,6 +59,7 @@ static int unionSumMain(int argc, char **argv) {
   int op = -1;
   bool haveParam = false;
   uint64_t param = 0;
+  double fracDistinct = -1, wordFrequency = -1;
   const char *outDir = nullptr;
   bool quiet = false;
   for (int i = 1; i < argc; i++) {
@@ -76,6 +77,10 @@ static int unionSumMain(int argc, char **argv) {
       param = strtoull(w, 0, 10);  haveParam = true;
       continue;
     }
+    //  thresholds of the filters: threshold= / t=, distinct= / d=, word-frequency= / f=  (merylCommandBuilder.C:277-296)
+    if (!strncmp(w, "threshold=", 10) || !strncmp(w, "t=", 2)) { param = strtoull(strchr(w, '=') + 1, 0, 10);  haveParam = true;  continue; }
+    if (!strncmp(w, "distinct=", 9) || !strncmp(w, "d=", 2))   { fracDistinct = strtod(strchr(w, '=') + 1, 0);  continue; }
+    if (!strncmp(w, "word-frequency=", 15) || !strncmp(w, "f=", 2)) { wordFrequency = strtod(strchr(w, '=') + 1, 0);  continue; }
     const std::string idx = std::string(w) + "/merylIndex";
     if (access(idx.c_str(), R_OK) != 0) { fprintf(stderr, "ERROR: '%s' is not a meryl database (no readable merylIndex).\n", w); return 1; }
     dbs.push_back(w);
@@ -85,8 +90,12 @@ static int unionSumMain(int argc, char **argv) {
   mb_union_stats st;
   int rc;
   if (op >= MB_OP_LESS_THAN) {
-    if (!haveParam)      { fprintf(stderr, "ERROR: %s needs a number (e.g. '%s 5').\n", kSetOps[op], kSetOps[op]); return 1; }
     if (dbs.size() != 1) { fprintf(stderr, "ERROR: %s takes exactly one input database.\n", kSetOps[op]); return 1; }
+    if ((fracDistinct >= 0 || wordFrequency >= 0) && op <= MB_OP_NOT_EQUAL_TO) {       //  merylOperation::initializeThreshold
+      if (mb_db_threshold(dbs[0], fracDistinct, wordFrequency, &param) != MB_OK) { fprintf(stderr, "ERROR: %s\n", mb_last_error()); return 1; }
+      haveParam = true;
+    }
+    if (!haveParam)      { fprintf(stderr, "ERROR: %s needs a number (e.g. '%s 5').\n", kSetOps[op], kSetOps[op]); return 1; }
     rc = mb_value_operation((uint32_t)op, param, dbs[0], outDir, -1, 0, &st);
   } else
     rc = mb_set_operation((uint32_t)op, dbs.data(), (uint32_t)dbs.size(), outDir, -1, 0, &st);

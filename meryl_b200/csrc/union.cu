@@ -690,6 +690,37 @@ struct Carve {
 }  //  namespace
 
 
+//  Threshold of a filter given as a share of the input's k-mers (merylOperation::initializeThreshold,
+//  src/meryl/merylOp-nextMer.C:65-125): fracDistinct (distinct= / d=) -> the smallest value v such that the k-mers with
+//  value <= v are at least fracDistinct * numDistinct; wordFrequency (word-frequency= / f=) -> wordFrequency * numTotal,
+//  and it wins if both are given.  A negative argument means "not given".  Reads the histogram of the master index only.
+extern "C" int mb_db_threshold(const char *dbDir, double fracDistinct, double wordFrequency, uint64_t *threshold) {
+  mb_clear_error();
+  if (!dbDir || !threshold) return mb_fail(MB_EINVAL, "mb_db_threshold: NULL argument");
+  std::vector<uint8_t> m;
+  MB_TRY(readWhole(std::string(dbDir) + "/merylIndex", m));
+  HostBits hb;
+  if (!hb.open(m.data(), m.size())) return mb_fail(MB_EFORMAT, "'%s/merylIndex' is not a meryl index", dbDir);
+  const u64 m1 = hb.get(64), m2 = hb.get(64);
+  if (m1 != 0x646e496c7972656dull || m2 != 0x33302e765f5f7865ull) return mb_fail(MB_EFORMAT, "'%s' is not a meryl v.03 database", dbDir);
+  for (int i = 0; i < 5; i++) hb.get(32);                   //  prefix, suffix, file bits, block bits, flags
+  hb.get(64);                                               //  numUnique
+  const u64 nDistinct = hb.get(64), nTotal = hb.get(64), nValues = hb.get(64);
+  u64 t = UINT64_MAX;                                       //  merylOp.H:251
+  if (fracDistinct >= 0) {
+    const u64 target = (u64)(fracDistinct * (double)nDistinct);
+    u64 seen = 0;
+    for (u64 i = 0; i < nValues; i++) {
+      const u64 value = hb.get(64), occ = hb.get(64);
+      seen += occ;
+      if (seen >= target) { t = value; break; }
+    }
+  }
+  if (wordFrequency >= 0) t = (u64)(wordFrequency * (double)nTotal);
+  *threshold = t;
+  return MB_OK;
+}
+
 extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                             uint64_t workspaceBytes, mb_union_stats *stOut) {
   return mb_set_operation(MB_OP_UNION_SUM, inDirs, nInputs, outDir, device, workspaceBytes, stOut);

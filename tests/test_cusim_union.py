@@ -61,3 +61,8 @@ def test_sim_union_small_ring(tmp_path, monkeypatch):
 @pytest.mark.parametrize("k,decoder", [(21, "warp"), (21, "thread"), (51, "warp"), (64, "thread"), (32, "warp"), (31, "auto")])
 def test_sim_union_long_blocks(tmp_path, monkeypatch, k, decoder):
     uc.case_long_blocks(str(tmp_path), monkeypatch, k, decoder)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+def test_sim_threshold_words_vs_reference(tmp_path):
+    uc.case_threshold_words(str(tmp_path))

@@ -91,3 +91,8 @@ def test_union_long_blocks(tmp_path, monkeypatch, k, decoder):
     if decoder != "thread" and not os.environ.get("MB_TEST_EXPERIMENTAL"):
         pytest.skip("decode_warp_kernel has not run on a GPU yet: MB_TEST_EXPERIMENTAL=1")
     uc.case_long_blocks(str(tmp_path), monkeypatch, k, decoder)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
+def test_threshold_words_vs_reference(tmp_path):
+    uc.case_threshold_words(str(tmp_path), n=60_000)

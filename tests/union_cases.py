@@ -124,3 +124,19 @@ def case_long_blocks(tmp, monkeypatch, k, decoder):
     st, out = check_union(tmp, [a, b], tag="long")
     assert st.nInputKmers > 50_000
     check_union(tmp, [out, a], tag="long2")                  # and the stream writer's own blocks (prefix 12) as input
+
+
+def case_threshold_words(tmp, n=12_000):
+    """`distinct=` / `word-frequency=` thresholds of the filters (merylOperation::initializeThreshold): the number our
+    mb_db_threshold derives from the input's histogram, fed to the filter, must give the reference binary's db."""
+    import subprocess
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(n // 4, n // 40, 150, 0.01, 77), 21)
+    for word, kw in (("distinct=0.5", dict(distinct=0.5)), ("distinct=0.98", dict(distinct=0.98)), ("d=0.0", dict(distinct=0.0)),
+                     ("word-frequency=0.00002", dict(word_frequency=0.00002)), ("f=0.0000001", dict(word_frequency=0.0000001))):
+        for op in ("greater-than", "at-most"):
+            t = mb.db_threshold(a, **kw)
+            ref, out = os.path.join(tmp, "ref_%s_%s.meryl" % (op, word)), os.path.join(tmp, "dev_%s_%s.meryl" % (op, word))
+            p = subprocess.run([util.REF_BIN, op, word, a, "output", ref], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr[-500:]
+            mb.value_operation(op, t, a, out)
+            util.assert_same_db(ref, out)
