@@ -19,9 +19,10 @@ MB_OVERLAP_D2H=1 timeout 420 python bench.py --steps 1 --warmup 1 --no-cpu-basel
 echo "== d. ncu: launch list of the default kernels (1 Gbp), then --set full with source of the sweep and the extraction";  date +%T
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_r2a.csv \
     python bench.py --gbp 1 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/ncu_launch_r2a.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"sortx_sweep|extract_kernel" -c 4 -o $OUT/full_r2a \
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"sortx_sweep|extract_kernel|sort_hist_kernel|count_suffix32_kernel" -c 6 -o $OUT/full_r2a \
     python bench.py --gbp 0.25 --workspace-gb 3 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/ncu_full_r2a.log 2>&1
 ls -la $OUT | tail -12
-echo "== e. union-sum next to the reference";  date +%T
+echo "== e. union-sum next to the reference (staging ring; then with the warp-per-block decoder)";  date +%T
 timeout 200 python tools/union_bench.py 0.5 2>&1 | tee $OUT/union_bench_r2a.json | cut -c1-900
+MB_DECODE=warp timeout 200 python tools/union_bench.py 0.5 2>&1 | tee $OUT/union_bench_r2a_warp.json | cut -c1-900
 date
