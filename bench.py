@@ -130,7 +130,7 @@ def reference_arm(args, world, rank):
         "impl": "reference", "metric": "kmers_per_sec_end_to_end_meryl_count", "value": val, "unit": "k-mers/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "meryl count k=21, synthetic 150 bp FASTQ (3 Gbp random genome, 0.1%% subst.), reference CPU binary on a %.2f Gbp prefix" % args.ref_gbp,
+        "config": {"workload": "meryl count k=%d, synthetic %d bp FASTQ (3 Gbp random genome, %.1f%% subst.), reference CPU binary on a %.2f Gbp prefix" % (K, READ_LEN, ERR * 100, args.ref_gbp),
                    "k": K, "read_len": READ_LEN, "sample_gbp": args.ref_gbp},
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": cores, "kind": "reference",
                          "sample": "first %d reads (%.2f Gbp) of the workload as a FASTQ file in /dev/shm, threads=%d memory=%d" % (n_reads, args.ref_gbp, cores, args.ref_memory_gb)},
@@ -151,7 +151,12 @@ def main():
     ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena per GPU (0 = all free memory); small values keep ncu replays fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    # the other BASELINE.json configs (parity-test cases, not the headline line): e.g. --k 31, or --k 51 --read-len 15000 --err 0.005 --gbp 50
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--read-len", type=int, default=READ_LEN)
+    ap.add_argument("--err", type=float, default=ERR)
     args = ap.parse_args()
+    globals().update(K=args.k, READ_LEN=args.read_len, ERR=args.err)
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -326,7 +331,8 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                              "--ref-gbp", str(args.ref_gbp), "--ref-memory-gb", str(args.ref_memory_gb)],
+                              "--ref-gbp", str(args.ref_gbp), "--ref-memory-gb", str(args.ref_memory_gb),
+                              "--k", str(K), "--read-len", str(READ_LEN), "--err", str(ERR)],
                              capture_output=True, text=True, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
         try:
             cpu = json.loads(sub.stdout.strip().splitlines()[-1]).get("cpu_baseline")
@@ -338,8 +344,8 @@ def main():
             "metric": "kmers_per_sec_end_to_end_meryl_count", "value": value, "unit": "k-mers/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "meryl count k=21 canonical, %.2f Gbp of synthetic 150 bp reads (3 Gbp uniform-random genome, both strands, 0.1%% substitutions)%s"
-                                   % (total_reads * READ_LEN / 1e9, "; " + reduced if reduced else ""),
+            "config": {"workload": "meryl count k=%d canonical, %.2f Gbp of synthetic %d bp reads (3 Gbp uniform-random genome, both strands, %.1f%% substitutions)%s"
+                                   % (K, total_reads * READ_LEN / 1e9, READ_LEN, ERR * 100, "; " + reduced if reduced else ""),
                        "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix, "key_bytes": stats.keyBytes,
                        "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
                        "l2": "inputs (%.1f GB store, %.1f GB keys per pass on rank 0) far exceed the 126 MB L2" % (stats.nBases * 0.375 / 1e9, stats.nKmers * 8 / max(1, stats.nPasses) / 1e9),
