@@ -207,7 +207,7 @@ int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir
  *    intersect*: only k-mers of ALL inputs, value = the first input's / min / max / sum;
  *    subtract: k-mers of the first input, its value minus the others' in turn, dropped as soon as it would not stay positive;
  *    difference: k-mers of the first input that no other input holds;
- *    symmetric-difference: k-mers of exactly one input (two inputs only here).                                       */
+ *    symmetric-difference: k-mers of exactly one input, with its value (more than two inputs: composed of three folds). */
 #define MB_OP_UNION                 0
 #define MB_OP_UNION_MIN             1
 #define MB_OP_UNION_MAX             2

@@ -731,10 +731,47 @@ static int setOperationImpl(uint32_t op, uint64_t param, const char *const *inDi
   return mb_merge_pipeline(op, param, inDirs, nInputs, outDir, device, workspaceBytes, stOut, nullptr);
 }
 
+static void removeDb(const std::string &dir) {              //  a database directory we made ourselves: 129 files
+  char path[4096];
+  for (u32 f = 0; f < 64; f++)
+    for (int isIdx = 0; isIdx < 2; isIdx++) { mb_file_name(path, sizeof(path), dir.c_str(), f, isIdx != 0); unlink(path); }
+  unlink((dir + "/merylIndex").c_str());
+  rmdir(dir.c_str());
+}
+
 extern "C" int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
                                 uint64_t workspaceBytes, mb_union_stats *stOut) {
   mb_clear_error();
   if (op > MB_OP_SYMMETRIC_DIFFERENCE) return mb_fail(MB_EINVAL, "mb_set_operation: unknown operation %u", op);
+  if (op == MB_OP_SYMMETRIC_DIFFERENCE && nInputs > 2 && inDirs && outDir) {
+    //  "the k-mers of exactly one input, with that input's value" (merylOp-nextMer.C:609-612) is not a left fold, but it is
+    //  a composition of folds:  intersect( union-sum(inputs), equal-to 1 ( union(inputs) ) )  -- union counts the inputs
+    //  that hold a k-mer, union-sum of a k-mer held by one input is that input's value, intersect keeps its first input's.
+    const std::string base = std::string(outDir) + ".tmp-symdiff-";
+    const std::string dCount = base + "count", dSum = base + "sum", dOne = base + "one";
+    mb_union_stats st1, st2, st3;
+    int rc = setOperationImpl(MB_OP_UNION, 0, inDirs, nInputs, dCount.c_str(), device, workspaceBytes, &st1);
+    if (rc == MB_OK) rc = setOperationImpl(MB_OP_UNION_SUM, 0, inDirs, nInputs, dSum.c_str(), device, workspaceBytes, &st2);
+    const char *one = dCount.c_str();
+    if (rc == MB_OK) rc = setOperationImpl(MB_OP_EQUAL_TO, 1, &one, 1, dOne.c_str(), device, workspaceBytes, &st3);
+    const char *two[2] = { dSum.c_str(), dOne.c_str() };
+    mb_union_stats st4;
+    if (rc == MB_OK) rc = setOperationImpl(MB_OP_INTERSECT, 0, two, 2, outDir, device, workspaceBytes, &st4);
+    char keep[1024];
+    strncpy(keep, mb_last_error(), sizeof(keep) - 1);  keep[sizeof(keep) - 1] = 0;
+    removeDb(dCount);  removeDb(dSum);  removeDb(dOne);
+    if (rc != MB_OK) return mb_fail(rc, "%s", keep);
+    if (stOut) {
+      *stOut = st4;
+      stOut->nInputs = nInputs;  stOut->nInputKmers = st2.nInputKmers;  stOut->inBytes = st2.inBytes;
+      stOut->nLaunches += st1.nLaunches + st2.nLaunches + st3.nLaunches;
+      stOut->msTotal += st1.msTotal + st2.msTotal + st3.msTotal;
+      stOut->msDecode += st1.msDecode + st2.msDecode + st3.msDecode;
+      stOut->msMerge += st1.msMerge + st2.msMerge + st3.msMerge;
+      stOut->msEncode += st1.msEncode + st2.msEncode + st3.msEncode;
+    }
+    return MB_OK;
+  }
   return setOperationImpl(op, 0, inDirs, nInputs, outDir, device, workspaceBytes, stOut);
 }
 
@@ -753,7 +790,7 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
   if (E.memInputs) nInputs = E.nMem;
   if ((!inDirs && !E.memInputs) || nInputs == 0 || (!outDir && !E.outImages)) return mb_fail(MB_EINVAL, "mb_set_operation: NULL argument");
   if (op == MB_OP_SYMMETRIC_DIFFERENCE && nInputs > 2)
-    return mb_fail(MB_EINVAL, "symmetric-difference of more than two databases is not implemented (it is not a left fold)");
+    return mb_fail(MB_EINVAL, "internal: symmetric-difference of more than two databases is a composition (mb_set_operation)");
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
     return mb_fail(MB_ENODEVICE, "mb_set_operation: no CUDA device (this library has no CPU path)");

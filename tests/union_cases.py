@@ -76,9 +76,7 @@ def case_set_operations(tmp, op, k=21, n=15_000):
     b = oracle_db(tmp, "b", common[: len(common) // 2] + synth.reads_fastq_bytes(n, n // 20, 150, 0.0, 3), k, op="count-forward")
     c = oracle_db(tmp, "c", common + common + synth.reads_fastq_bytes(n, n // 50, 150, 0.0, 2), k)
     e = oracle_db(tmp, "e", b">x\nACGT\n", k)
-    cases = [[a, b], [c, a], [a], [a, e], [e, a]]
-    if op != "symmetric-difference":
-        cases += [[a, b, c], [c, b, a, a]]
+    cases = [[a, b], [c, a], [a], [a, e], [e, a], [a, b, c], [c, b, a, a]]     # (symmetric-difference of > 2: a composition of folds)
     for i, ins in enumerate(cases):
         check_union(tmp, ins, "s%d" % i, op=op)
     a2 = oracle_db(tmp, "a2", synth.fasta_bytes(2, n // 2, 5), 40)
