@@ -177,7 +177,131 @@ static int multiGpuCount(uint32_t nGpus, mb_config cfg, const std::vector<const 
   return bad;
 }
 
+static int flatMain(int argc, char **argv);
+
+//  Operation trees (merylCommandBuilder.C:441-563: '[' opens an operation whose result is an input of the operation around
+//  it, ']' closes it).  The reference streams a sub-operation's k-mers into its parent; here every operation is one call on
+//  the device, so a sub-operation is run first, into its own `output` if it names one, else into a temporary database next
+//  to the root's output, and the parent reads that directory.  The result is the same function of the inputs.  k= is global
+//  as in the reference (kmerTiny::setSize); the other options of the outermost level are handed down to every operation.
+struct TreeNode {
+  std::vector<std::string> words;       //  this level's words in order; "\x01<i>" stands for sub-operation i
+  std::vector<TreeNode>    subs;
+};
+
+static bool parseTree(char **argv, int argc, int &i, TreeNode &node, bool inBracket) {
+  for (; i < argc; i++) {
+    if (!strcmp(argv[i], "[")) {
+      i++;
+      node.subs.emplace_back();
+      node.words.push_back(std::string("\x01") + std::to_string(node.subs.size() - 1));
+      if (!parseTree(argv, argc, i, node.subs.back(), true)) return false;
+    } else if (!strcmp(argv[i], "]")) {
+      if (!inBracket) { fprintf(stderr, "ERROR: ']' without a '['.\n"); return false; }
+      return true;
+    } else node.words.push_back(argv[i]);
+  }
+  if (inBracket) { fprintf(stderr, "ERROR: '[' without a ']'.\n"); return false; }
+  return true;
+}
+
+static bool isOptionWord(const std::string &w) {
+  static const char *opts[] = { "k=", "memory=", "threads=", "gpus=", "-V", "-Q", "-P" };
+  for (const char *o : opts) if (!strncmp(w.c_str(), o, strlen(o))) return true;
+  return false;
+}
+
+//  Runs the operation of `node` (after its sub-operations) and returns its database in `outDb`.
+static int runTree(const char *prog, TreeNode &node, const std::vector<std::string> &inherited, const std::string &tmpBase, int &tmpSeq,
+                   bool isRoot, std::string &outDb, std::vector<std::string> &temps) {
+  std::vector<std::string> subDb(node.subs.size());
+  for (size_t j = 0; j < node.subs.size(); j++)
+    if (runTree(prog, node.subs[j], inherited, tmpBase, tmpSeq, false, subDb[j], temps) != 0) return 1;
+  std::vector<std::string> cmd(1, prog);
+  for (const std::string &w : inherited) {                 //  an option of its own overrides the inherited one
+    const std::string key = w.substr(0, w.find('=') == std::string::npos ? w.size() : w.find('=') + 1);
+    bool own = false;
+    for (const std::string &x : node.words) if (!strncmp(x.c_str(), key.c_str(), key.size())) own = true;
+    if (!own) cmd.push_back(w);
+  }
+  bool haveOutput = false;
+  for (size_t j = 0; j < node.words.size(); j++) {
+    const std::string &w = node.words[j];
+    if (w[0] == '\x01') { cmd.push_back(subDb[(size_t)atoi(w.c_str() + 1)]); continue; }
+    if (w == "output" && j + 1 < node.words.size()) { haveOutput = true; outDb = node.words[j + 1]; }
+    cmd.push_back(w);
+  }
+  if (!haveOutput) {
+    if (isRoot) { fprintf(stderr, "ERROR: No output specified for the outermost operation.\n"); return 1; }
+    outDb = tmpBase + ".tmp-" + std::to_string(tmpSeq++);
+    temps.push_back(outDb);
+    cmd.push_back("output");  cmd.push_back(outDb);
+  }
+  if (getenv("MB_CLI_DRY")) {                              //  testing: print the flat command lines instead of running them
+    for (size_t j = 1; j < cmd.size(); j++) printf("%s%s", j > 1 ? " " : "", cmd[j].c_str());
+    printf("\n");
+    return 0;
+  }
+  std::vector<char *> av;
+  for (std::string &c : cmd) av.push_back(&c[0]);
+  av.push_back(nullptr);
+  return flatMain((int)cmd.size(), av.data());
+}
+
+static void removeTempDb(const std::string &dir) {
+  char name[64];
+  for (unsigned f = 0; f < 64; f++)
+    for (int isIdx = 0; isIdx < 2; isIdx++) {
+      char bits[7];
+      for (int b = 0; b < 6; b++) bits[b] = ((f >> (5 - b)) & 1) ? '1' : '0';
+      bits[6] = 0;
+      snprintf(name, sizeof(name), "/0x%s.%s", bits, isIdx ? "merylIndex" : "merylData");      //  constructBlockName, kmers.C:31-56
+      unlink((dir + name).c_str());
+    }
+  unlink((dir + "/merylIndex").c_str());
+  rmdir(dir.c_str());
+}
+
 int main(int argc, char **argv) {
+  bool tree = false;
+  for (int i = 1; i < argc; i++) if (!strcmp(argv[i], "[")) tree = true;
+  if (!tree) return flatMain(argc, argv);
+
+  TreeNode root;
+  int i = 1;
+  if (!parseTree(argv, argc, i, root, false)) return 1;
+  //  `meryl [ op ... ]`: the outermost level holds nothing but options and one bracket -- that bracket is the root
+  std::vector<std::string> inherited;
+  for (const std::string &w : root.words) if (isOptionWord(w)) inherited.push_back(w);
+  TreeNode *top = &root;
+  bool onlyOptions = root.subs.size() == 1;
+  for (const std::string &w : root.words) if (!isOptionWord(w) && w[0] != '\x01') onlyOptions = false;
+  if (onlyOptions) top = &root.subs[0];
+  else {                                                   //  the outermost level is itself an operation: its options stay with it
+    std::vector<std::string> keep;
+    for (const std::string &w : root.words) if (!isOptionWord(w)) keep.push_back(w);
+    root.words.swap(keep);
+  }
+  //  k= is global wherever it is written
+  std::vector<TreeNode *> stack(1, &root);
+  while (!stack.empty()) {
+    TreeNode *n = stack.back();  stack.pop_back();
+    for (const std::string &w : n->words)
+      if (!strncmp(w.c_str(), "k=", 2)) { bool have = false; for (const std::string &x : inherited) if (!strncmp(x.c_str(), "k=", 2)) have = true; if (!have) inherited.push_back(w); }
+    for (TreeNode &c : n->subs) stack.push_back(&c);
+  }
+  std::string rootOut;
+  for (size_t j = 0; j + 1 < top->words.size(); j++) if (top->words[j] == "output") rootOut = top->words[j + 1];
+  if (rootOut.empty()) { fprintf(stderr, "ERROR: No output specified for the outermost operation.\n"); return 1; }
+  int tmpSeq = 0;
+  std::vector<std::string> temps;
+  std::string outDb;
+  const int rc = runTree(argv[0], *top, inherited, rootOut, tmpSeq, true, outDb, temps);
+  for (const std::string &t : temps) removeTempDb(t);
+  return rc;
+}
+
+static int flatMain(int argc, char **argv) {
   for (int i = 1; i < argc; i++)
     if (setOpOf(argv[i]) >= 0) return unionSumMain(argc, argv);
 

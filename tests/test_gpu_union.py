@@ -96,3 +96,23 @@ def test_union_long_blocks(tmp_path, monkeypatch, k, decoder):
 @pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
 def test_threshold_words_vs_reference(tmp_path):
     uc.case_threshold_words(str(tmp_path), n=60_000)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
+def test_cli_operation_tree_vs_reference(tmp_path):
+    """`meryl-b200 union-sum [ count a ] [ greater-than 1 [ count b ] ] output x`: sub-operations run first into temporary
+    databases; the directory must be the one the reference writes for the same command line."""
+    a, b = tmp_path / "a.fa", tmp_path / "b.fq"
+    a.write_bytes(synth.fasta_bytes(3, 40_000, 5))
+    b.write_bytes(synth.reads_fastq_bytes(40_000, 3_000, 150, 0.002, 6))
+    def words(tag):                                            # (the reference wants an output for every count, in a tree too)
+        return ["k=21", "memory=2", "union-sum", "[", "count", str(a), "output", str(tmp_path / (tag + "_a.meryl")), "]",
+                "[", "greater-than", "1", "[", "count", str(b), "output", str(tmp_path / (tag + "_b.meryl")), "]", "]"]
+    ref, out = str(tmp_path / "ref.meryl"), str(tmp_path / "cli.meryl")
+    p = subprocess.run([util.REF_BIN] + words("ref") + ["output", ref], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    p = subprocess.run([mb.CLI_PATH] + words("cli") + ["output", out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    util.assert_same_db(ref, out)
+    util.assert_same_db(str(tmp_path / "ref_a.meryl"), str(tmp_path / "cli_a.meryl"))
+    assert not [n for n in os.listdir(str(tmp_path)) if ".tmp-" in n]          # the temporary databases are gone

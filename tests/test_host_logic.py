@@ -231,3 +231,24 @@ def test_cli_hands_other_operations_to_the_reference(tmp_path):
     p = _cli(["statistics", gold], env={"MERYL_REFERENCE": util.REF_BIN})
     q = subprocess.run([util.REF_BIN, "statistics", gold], capture_output=True, text=True)
     assert p.returncode == q.returncode == 0 and p.stdout == q.stdout and "unique" in p.stdout
+
+
+def test_cli_operation_trees_become_flat_commands(tmp_path):
+    """'[' ... ']' (merylCommandBuilder.C:441-563): a sub-operation runs first, into its own output or a temporary database next
+    to the root's output; k= is global, the outermost options are handed down.  MB_CLI_DRY=1 prints the flat command lines."""
+    env = dict(os.environ, MB_CLI_DRY="1")
+    def dry(words):
+        p = subprocess.run([mb.CLI_PATH] + words, capture_output=True, text=True, env=env, cwd=str(tmp_path))
+        return p.returncode, p.stdout.splitlines(), p.stderr
+    rc, out, _ = dry("k=21 threads=4 union-sum output u.meryl [ count a.fa output a.meryl ] [ count memory=2 b.fa ] c.meryl".split())
+    assert rc == 0 and out == ["k=21 threads=4 count a.fa output a.meryl",
+                               "k=21 threads=4 count memory=2 b.fa output u.meryl.tmp-0",
+                               "k=21 threads=4 union-sum output u.meryl a.meryl u.meryl.tmp-0 c.meryl"]
+    rc, out, _ = dry("[ difference [ greater-than 1 [ count k=15 x.fa ] ] y.meryl output d.meryl ]".split())
+    assert rc == 0 and out == ["count k=15 x.fa output d.meryl.tmp-0",
+                               "k=15 greater-than 1 d.meryl.tmp-0 output d.meryl.tmp-1",
+                               "k=15 difference d.meryl.tmp-1 y.meryl output d.meryl"]
+    rc, _, err = dry("union [ count k=9 a ]".split())
+    assert rc == 1 and "No output specified" in err
+    rc, _, err = dry("union [ count k=9 a output z".split())
+    assert rc == 1 and "without a ']'" in err
