@@ -240,6 +240,11 @@ int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, c
 #define MB_OP_MODULO               22
 int mb_value_operation(uint32_t op, uint64_t param, const char *inDir, const char *outDir, int32_t device,
                        uint64_t workspaceBytes, mb_union_stats *st);
+/*  `count-suffix=<bases>` (merylCommandBuilder.C:271-274, merylOp-countSimple.C:50-93, :172-199): keeps the k-mers of a count
+ *  database that end with the given bases and writes them with the geometry of the reference's simple counter (prefix width
+ *  6 + max(0, 2k - 2s - 26), a block for every prefix).  `meryl-b200 count count-suffix=ACG ...` = count, then this.  */
+int mb_keep_suffix(const char *inDir, const char *suffix, const char *outDir, int32_t device, uint64_t workspaceBytes,
+                   mb_union_stats *st);
 /*  The filters' threshold given as a share of the input (merylOperation::initializeThreshold, merylOp-nextMer.C:65-125;
  *  words distinct= / d=, word-frequency= / f= of merylCommandBuilder.C:277-290): fracDistinct -> the smallest value v such
  *  that at least fracDistinct * numDistinct k-mers have a value <= v; wordFrequency -> wordFrequency * numTotal (wins if both

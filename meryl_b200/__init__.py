@@ -345,3 +345,12 @@ def db_threshold(db, distinct: float | None = None, word_frequency: float | None
     _check(L.mb_db_threshold(os.fsencode(os.fspath(db)), -1.0 if distinct is None else distinct,
                              -1.0 if word_frequency is None else word_frequency, ctypes.byref(t)))
     return t.value
+
+
+def keep_suffix(inp, suffix: str, output: str, device: int = -1, workspace_bytes: int = 0) -> UnionStats:
+    """`count-suffix=<bases>`: the k-mers of a count db that end with `suffix`, in the simple counter's geometry (mb_keep_suffix)."""
+    L = lib()
+    L.mb_keep_suffix.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_uint64, ctypes.POINTER(UnionStats)]
+    st = UnionStats()
+    _check(L.mb_keep_suffix(os.fsencode(os.fspath(inp)), suffix.encode(), os.fsencode(os.fspath(output)), device, workspace_bytes, ctypes.byref(st)))
+    return st

@@ -308,7 +308,7 @@ static int flatMain(int argc, char **argv) {
   uint32_t k = 0, mode = 0, nGpus = 1;
   uint64_t nExpected = 0, memBytes = physicalMemory();
   bool haveOp = false, onlyConfig = false, quiet = false, compress = false;
-  const char *outDir = nullptr;
+  const char *outDir = nullptr, *countSuffix = nullptr;
   std::vector<const char *> inputs;
 
   for (int i = 1; i < argc; i++) {
@@ -324,6 +324,7 @@ static int flatMain(int argc, char **argv) {
     else if (!strncmp(w, "gpus=", 5))         { nGpus = (uint32_t)strtoul(w + 5, 0, 10); }     //  (not a word of the reference)
     else if (isCountWord(w, &mode))           { haveOp = true; }
     else if (!strcmp(w, "compress"))          { compress = true; }           //  merylCommandBuilder.C:237-240 (here: all inputs)
+    else if (!strncmp(w, "count-suffix=", 13)) { countSuffix = w + 13; }       //  merylCommandBuilder.C:271-274
     else if (!strcmp(w, "output")) {
       if (i + 1 >= argc) { fprintf(stderr, "ERROR: 'output' needs a database name.\n"); return 1; }
       outDir = argv[++i];
@@ -377,12 +378,23 @@ static int flatMain(int argc, char **argv) {
   cfg.k = k;  cfg.mode = mode;  cfg.wPrefix = wPrefix;  cfg.device = -1;
   if (compress) cfg.flags |= MB_FLAG_COMPRESS;
 
+  //  count-suffix=: the full count goes to a temporary database, mb_keep_suffix writes the wanted k-mers (csrc/union.cu)
+  const std::string finalDir = outDir;
+  const std::string countDir = countSuffix ? finalDir + ".tmp-count" : finalDir;
   mb_stats st;
   if (nGpus > 1) {
-    if (multiGpuCount(nGpus, cfg, inputs, outDir, &st) != 0) return 1;
-  } else if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), outDir, &st) != MB_OK) {
+    if (multiGpuCount(nGpus, cfg, inputs, countDir.c_str(), &st) != 0) return 1;
+  } else if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), countDir.c_str(), &st) != MB_OK) {
     fprintf(stderr, "ERROR: %s\n", mb_last_error());
     return 1;
+  }
+  if (countSuffix) {
+    mb_union_stats us;
+    const int rc = mb_keep_suffix(countDir.c_str(), countSuffix, finalDir.c_str(), -1, 0, &us);
+    if (rc != MB_OK) fprintf(stderr, "ERROR: %s\n", mb_last_error());
+    removeTempDb(countDir);
+    if (rc != MB_OK) return 1;
+    if (!quiet) fprintf(stderr, "Kept the %llu distinct %u-mers that end with '%s'.\n", (unsigned long long)us.nOutputKmers, k, countSuffix);
   }
   if (!quiet) {
     fprintf(stderr, "Counted %llu %u-mers (%llu distinct, %llu unique) in %u pass%s, %.1f ms on the device.\n",

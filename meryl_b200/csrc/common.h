@@ -100,6 +100,7 @@ void mb_file_name(char *out, size_t cap, const char *dir, u32 file, bool isIndex
 //  host memory, writes images, keeps the batches' prefix width and the block writer's rules (a block for every prefix),
 //  sums with saturation, and works inside the counting context's device arena.
 #define MB_OP_MERGE_BATCHES 100u          //  internal operator: saturating uint32 sum (kmers-writer-block.C:305-309)
+#define MB_OP_KEEP_SUFFIX   101u          //  internal one-input operator: keep the k-mers whose low bits equal a constant (count-suffix=)
 struct MbMergeEndpoints {
   const MbDbImages *const *memInputs = nullptr;      //  inputs in host memory instead of directories ...
   u32          nMem = 0, k = 0, wPrefix = 0;         //  ... all of this k and prefix width
@@ -109,6 +110,7 @@ struct MbMergeEndpoints {
   MbHistogram *outHist = nullptr;
   uint8_t     *arena = nullptr;                      //  device arena to work in (NULL: allocate one)
   size_t       arenaBytes = 0;
+  u64          param2 = 0;                           //  MB_OP_KEEP_SUFFIX: the mask (param is the value)
   u32          outPrefix = 12;                       //  kmers-writer.C:52-58: every non-count operation writes prefix 12
   u32          streamMode = 1;                       //  1: stream writer (blocks of present prefixes), 0: block writer (all prefixes)
 };

@@ -320,7 +320,7 @@ __device__ __forceinline__ u64 merge_path(const Key *a, u64 nA, const Key *b, u6
 //    difference            only A                                    symmetric-difference (two inputs)   only A or only B
 //  dropZero: values that are 0 are not written (only sums can wrap to 0; a wrapped intermediate sum of intersect-sum
 //  must survive to the next step, so the host sets dropZero in the last step only for that operator).
-struct MergeRule { u32 op, firstRaw, dropZero; u64 param; };
+struct MergeRule { u32 op, firstRaw, dropZero; u64 param, param2; };
 
 __device__ __forceinline__ double rint_half_away(double x) { return floor(x + 0.5); }      //  C round() for x >= 0
 
@@ -343,8 +343,12 @@ __device__ __forceinline__ u32 value_rule(u32 op, u64 param, u32 a) {
   }
 }
 
-__device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u32 &v) {
+__device__ __forceinline__ u64 key_low(u64 k)                { return k; }
+__device__ __forceinline__ u64 key_low(const ulonglong2 &k)  { return k.x; }
+
+__device__ __forceinline__ bool rule_only_a(const MergeRule &r, u32 va, u64 keyLo, u32 &v) {
   switch (r.op) {
+    case MB_OP_KEEP_SUFFIX:  v = va;  return (keyLo & r.param2) == r.param;      //  merylOp-countSimple.C:88-93
     case MB_OP_UNION:        v = r.firstRaw ? 1u : va;  return true;
     case MB_OP_UNION_MIN: case MB_OP_UNION_MAX: case MB_OP_UNION_SUM: case MB_OP_MERGE_BATCHES:
     case MB_OP_SUBTRACT:  case MB_OP_DIFFERENCE: case MB_OP_SYMMETRIC_DIFFERENCE:
@@ -420,7 +424,7 @@ merge_op_kernel(const typename KeyT<KW>::type *__restrict__ ka, const u32 *__res
       k = sa[ai];                                            //  k-mers are distinct within a database
       //  its partner in B, if any, is the next unconsumed element there (possibly the guard behind the window)
       if (bLo + bi < nB && key_eq(sb[bi], k)) keep = rule_both(rule, sva[ai], svb[bi], v);
-      else                                    keep = rule_only_a(rule, sva[ai], v);
+      else                                    keep = rule_only_a(rule, sva[ai], key_low(k), v);
       ai++;
     } else {
       k = sb[bi];
@@ -719,6 +723,35 @@ extern "C" int mb_db_threshold(const char *dbDir, double fracDistinct, double wo
   if (wordFrequency >= 0) t = (u64)(wordFrequency * (double)nTotal);
   *threshold = t;
   return MB_OK;
+}
+
+//  `count-suffix=ACG` (merylCommandBuilder.C:271-274; merylOp-countSimple.C:50-93, :172-199): only the k-mers whose counted
+//  form ends with the given bases are kept, and the database is written with the simple counter's geometry -- prefix width
+//  6 + max(0, 2k - 2s - 26), a block for every prefix.  The reference filters while it counts into a direct-indexed array of
+//  4^(k-s) entries (the option exists to split a count that does not fit memory into 4^s jobs); here the count is not
+//  memory-bound, so the full count is made first and this one-input operation keeps the wanted k-mers (same database).
+extern "C" int mb_keep_suffix(const char *inDir, const char *suffix, const char *outDir, int32_t device, uint64_t workspaceBytes,
+                              mb_union_stats *stOut) {
+  mb_clear_error();
+  if (!inDir || !suffix || !outDir) return mb_fail(MB_EINVAL, "mb_keep_suffix: NULL argument");
+  InputDb db;
+  MB_TRY(openDb(inDir, db));
+  const u32 s = (u32)strlen(suffix);
+  if (s == 0 || s > 32 || s >= db.k) return mb_fail(MB_EINVAL, "count-suffix '%s': 1..32 bases, shorter than k=%u", suffix, db.k);
+  if (2 * db.k - 2 * s > 42) return mb_fail(MB_EINVAL, "count-suffix '%s' with k=%u: not possible (the reference's simple mode needs 2k - 2s <= 42)", suffix, db.k);
+  if (2 * db.k - 2 * s < 6)  return mb_fail(MB_EINVAL, "count-suffix '%s' with k=%u leaves fewer than 3 bases", suffix, db.k);
+  u64 value = 0;
+  for (u32 i = 0; i < s; i++) {
+    const char c = suffix[i];
+    if (!strchr("ACGTacgt", c) || c == 0) return mb_fail(MB_EINVAL, "count-suffix '%s' is not made of ACGT", suffix);
+    value = (value << 2) | (u64)((c >> 1) & 3);            //  kmers-tiny.H:86: A=0 C=1 T=2 G=3
+  }
+  const u32 psbits = 2 * db.k - 2 * s - 6;
+  MbMergeEndpoints E;
+  E.param2     = s == 32 ? ~0ull : (((u64)1 << (2 * s)) - 1);
+  E.outPrefix  = 6 + (psbits > 20 ? psbits - 20 : 0);       //  merylOp-countSimple.C:172-175
+  E.streamMode = 0;
+  return mb_merge_pipeline(MB_OP_KEEP_SUFFIX, value, &inDir, 1, outDir, device, workspaceBytes, stOut, &E);
 }
 
 extern "C" int mb_union_sum(const char *const *inDirs, uint32_t nInputs, const char *outDir, int32_t device,
@@ -1025,6 +1058,7 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
         MergeRule rule;
         rule.op       = (nInputs == 1 && op != MB_OP_UNION && op <= MB_OP_SYMMETRIC_DIFFERENCE) ? (u32)MB_OP_UNION_SUM : op;
         rule.param    = param;
+        rule.param2   = E.param2;
         rule.firstRaw = (i == 1) ? 1 : 0;
         rule.dropZero = (op != MB_OP_INTERSECT_SUM || i + 1 >= nInputs) ? 1 : 0;
         const u64 tiles = (curN + bn + MG_TILE - 1) / MG_TILE;

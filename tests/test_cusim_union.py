@@ -66,3 +66,8 @@ def test_sim_union_long_blocks(tmp_path, monkeypatch, k, decoder):
 @pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
 def test_sim_threshold_words_vs_reference(tmp_path):
     uc.case_threshold_words(str(tmp_path))
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+def test_sim_count_suffix_vs_reference(tmp_path):
+    uc.case_count_suffix(str(tmp_path))

@@ -116,3 +116,21 @@ def test_cli_operation_tree_vs_reference(tmp_path):
     util.assert_same_db(ref, out)
     util.assert_same_db(str(tmp_path / "ref_a.meryl"), str(tmp_path / "cli_a.meryl"))
     assert not [n for n in os.listdir(str(tmp_path)) if ".tmp-" in n]          # the temporary databases are gone
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
+def test_count_suffix_vs_reference(tmp_path):
+    uc.case_count_suffix(str(tmp_path), n=30_000)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
+def test_cli_count_suffix(tmp_path):
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(30_000, 2_000, 150, 0.003, 8))
+    ref, out = str(tmp_path / "ref.meryl"), str(tmp_path / "cli.meryl")
+    words = ["k=14", "memory=2", "count-suffix=AC", "count", str(fq), "output"]
+    assert subprocess.run([util.REF_BIN] + words + [ref], capture_output=True).returncode == 0
+    p = subprocess.run([mb.CLI_PATH] + words + [out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-800:]
+    util.assert_same_db(ref, out)
+    assert not os.path.exists(out + ".tmp-count")
