@@ -251,6 +251,15 @@ int mb_keep_suffix(const char *inDir, const char *suffix, const char *outDir, in
  *  are given); negative = not given.  Host only: reads the histogram in dbDir/merylIndex.  */
 int mb_db_threshold(const char *dbDir, double fracDistinct, double wordFrequency, uint64_t *threshold);
 
+/*  merylExactLookup::value for many k-mers at once (src/utility/src/kmers-v1/kmers-lookup.H:139-146, kmers-exact.C;
+ *  SURVEY.md 8(f).4): values[i] = the value of k-mer i in the database, 0 if it is absent or its value lies outside
+ *  [minValue, maxValue] (the lookup table's load-time filter).  A k-mer is 2 bits per base, first base in the top bits,
+ *  A=0 C=1 T=2 G=3, in kmerLo[i] (and kmerHi[i] for k > 32; NULL otherwise); it is looked up as given -- pass the canonical
+ *  form for databases made by `count`, as meryl-lookup does.  The blocks are decoded on the device and every query is a
+ *  binary search in the list of its data file.  */
+int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const uint64_t *kmerLo, const uint64_t *kmerHi,
+              uint64_t nQueries, uint32_t *values, int32_t device, uint64_t workspaceBytes);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

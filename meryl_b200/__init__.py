@@ -354,3 +354,18 @@ def keep_suffix(inp, suffix: str, output: str, device: int = -1, workspace_bytes
     st = UnionStats()
     _check(L.mb_keep_suffix(os.fsencode(os.fspath(inp)), suffix.encode(), os.fsencode(os.fspath(output)), device, workspace_bytes, ctypes.byref(st)))
     return st
+
+
+def lookup(db, kmer_lo, kmer_hi=None, min_value: int = 0, max_value: int = 0xffffffff, device: int = -1, workspace_bytes: int = 0):
+    """merylExactLookup::value for an array of k-mers (mb_lookup): numpy uint64 arrays in (2 bits per base, first base in the
+    top bits, A=0 C=1 T=2 G=3; kmer_hi for k > 32), numpy uint32 values out (0 = absent)."""
+    import numpy as np
+    lo = np.ascontiguousarray(kmer_lo, dtype=np.uint64)
+    hi = None if kmer_hi is None else np.ascontiguousarray(kmer_hi, dtype=np.uint64)
+    out = np.zeros(lo.size, dtype=np.uint32)
+    L = lib()
+    L.mb_lookup.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                            ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64]
+    _check(L.mb_lookup(os.fsencode(os.fspath(db)), min_value, max_value, lo.ctypes.data, None if hi is None else hi.ctypes.data,
+                       lo.size, out.ctypes.data, device, workspace_bytes))
+    return out

@@ -294,6 +294,41 @@ decode_warp_kernel(const uint8_t *__restrict__ data, u64 dataBytes, const UnionB
 __device__ __forceinline__ bool key_less(u64 a, u64 b)                              { return a < b; }
 __device__ __forceinline__ bool key_less(const ulonglong2 &a, const ulonglong2 &b)  { return a.y < b.y || (a.y == b.y && a.x < b.x); }
 
+__device__ __forceinline__ void make_query(u64 &q, u32 &file, u64 lo, u64 hi, u32 k)        { (void)hi; q = lo; file = (u32)(lo >> (2 * k - 6)) & 63u; }
+__device__ __forceinline__ void make_query(ulonglong2 &q, u32 &file, u64 lo, u64 hi, u32 k) {
+  q.x = lo;  q.y = hi;
+  const u32 sh = 2 * k - 6;                                 //  > 58 here (k > 32)
+  file = (u32)(sh >= 64 ? (hi >> (sh - 64)) : ((hi << (64 - sh)) | (lo >> sh))) & 63u;
+}
+
+//  ---- K9: exact lookup ----------------------------------------------------------------------------------------
+//  merylExactLookup::value / exists (src/utility/src/kmers-v1/kmers-lookup.H:139-146, kmers-exact.C): the value of a k-mer in
+//  a database, 0 if it is not there (or its value lies outside [minValue, maxValue], the table's load-time filter).  The
+//  reference builds a prefix-indexed table in host memory; here the database's blocks are decoded on the device (K7) into
+//  their sorted (k-mer, value) lists, one list per data file, and every query is a binary search in the list of its file
+//  (top 6 bits).  One thread per query; queries whose file is not in the resident group are left alone.
+template <int KW>
+__global__ void __launch_bounds__(256)
+lookup_kernel(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__restrict__ vals, const u64 *__restrict__ fileStart /* [65] */,
+              u32 fileLo, u32 fileHi, u32 k, const u64 *__restrict__ qLo, const u64 *__restrict__ qHi, u64 nQueries,
+              u32 minValue, u32 maxValue, u32 *__restrict__ out) {
+  typedef typename KeyT<KW>::type Key;
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nQueries) return;
+  Key q;
+  u32 file;
+  make_query(q, file, qLo[i], KW == 2 ? qHi[i] : 0, k);
+  if (file < fileLo || file >= fileHi) return;
+  u64 lo = fileStart[file], hi = fileStart[file + 1];      //  first key >= q in [lo, hi)
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if (key_less(keys[mid], q)) lo = mid + 1; else hi = mid;
+  }
+  u32 v = 0;
+  if (lo < fileStart[file + 1] && key_eq(keys[lo], q)) { v = vals[lo]; if (v < minValue || v > maxValue) v = 0; }
+  out[i] = v;
+}
+
 const int MG_THREADS = 256;
 const int MG_ITEMS   = 8;
 const int MG_TILE    = MG_THREADS * MG_ITEMS;
@@ -723,6 +758,128 @@ extern "C" int mb_db_threshold(const char *dbDir, double fracDistinct, double wo
   if (wordFrequency >= 0) t = (u64)(wordFrequency * (double)nTotal);
   *threshold = t;
   return MB_OK;
+}
+
+//  merylExactLookup::value for many k-mers at once (kernel K9 above).  values[i] = the value of k-mer i (kmerLo[i], and
+//  kmerHi[i] for k > 32; first base in the top bits, as everywhere) in the database, 0 if absent or outside
+//  [minValue, maxValue].  The k-mers are looked up as given: the caller passes the canonical form for canonical databases,
+//  like merylExactLookup's callers do (meryl-lookup: existence.C).  The database is decoded group of files by group of files.
+extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const uint64_t *kmerLo, const uint64_t *kmerHi,
+                         uint64_t nQueries, uint32_t *values, int32_t device, uint64_t workspaceBytes) {
+  mb_clear_error();
+  if (!dbDir || (nQueries && (!kmerLo || !values))) return mb_fail(MB_EINVAL, "mb_lookup: NULL argument");
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return mb_fail(MB_ENODEVICE, "mb_lookup: no CUDA device (this library has no CPU path)");
+  InputDb db;
+  MB_TRY(openDb(dbDir, db));
+  const u32 k = db.k, kw = k <= 32 ? 1 : 2, W = 8 * kw;
+  if (kw == 2 && nQueries && !kmerHi) return mb_fail(MB_EINVAL, "mb_lookup: k=%u needs the high words of the k-mers", k);
+  if (nQueries == 0) return MB_OK;
+
+  int rc = MB_OK;
+  uint8_t *arena = nullptr;
+  cudaStream_t s = nullptr;
+  {
+    if (device >= 0) MB_UCUDA(cudaSetDevice(device));
+    size_t freeB = 0, totalB = 0;
+    MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
+    const size_t qBytes = (size_t)nQueries * (W + 4) + 4096;
+    auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
+      size_t need = (size_t)16 << 20;
+      for (u32 f = f0; f < f1; f++) need += db.fileBytes[f] + 256 + db.index[f].size() / 24 * sizeof(UnionBlock) + db.fileKmers[f] * (W + 4) + 1024;
+      return need;
+    };
+    size_t want = workspaceBytes ? (size_t)workspaceBytes : std::min(freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2,
+                                                                     qBytes + groupNeed(0, 64) + ((size_t)64 << 20));
+    if (want > freeB) want = freeB;
+    want = want / 256 * 256;
+    if (cudaMalloc((void **)&arena, want) != cudaSuccess) { cudaGetLastError(); arena = nullptr; rc = mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want); goto done; }
+    MB_UCUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+
+    Carve top(arena, want);
+    u64 *dQLo = (u64 *)top.take((size_t)nQueries * 8);
+    u64 *dQHi = kw == 2 ? (u64 *)top.take((size_t)nQueries * 8) : nullptr;
+    u32 *dOut = (u32 *)top.take((size_t)nQueries * 4);
+    u64 *dFileStart = (u64 *)top.take(65 * 8);
+    u32 *dErr = (u32 *)top.take(256);
+    if (!dQLo || (kw == 2 && !dQHi) || !dOut || !dFileStart || !dErr) { rc = mb_fail(MB_ENOMEM, "the %llu queries do not fit the device arena", (unsigned long long)nQueries); goto done; }
+    MB_UCUDA(cudaMemcpyAsync(dQLo, kmerLo, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
+    if (kw == 2) MB_UCUDA(cudaMemcpyAsync(dQHi, kmerHi, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
+    MB_UCUDA(cudaMemsetAsync(dOut, 0, (size_t)nQueries * 4, s));
+    MB_UCUDA(cudaMemsetAsync(dErr, 0, 256, s));
+    const size_t fixedOff = top.off;
+
+    HostBuf host;
+    u32 f0 = 0;
+    while (f0 < 64) {
+      u32 f1 = f0 + 1;
+      if (fixedOff + groupNeed(f0, f1) > want) { rc = mb_fail(MB_ENOMEM, "data file %u needs %zu bytes on the device, %zu available", f0, groupNeed(f0, f1), want - fixedOff); goto done; }
+      const u32 maxFiles = getenv("MB_UNION_MAX_FILES") ? (u32)strtoul(getenv("MB_UNION_MAX_FILES"), nullptr, 10) : 64;   //  testing knob
+      while (f1 < 64 && f1 - f0 < maxFiles && fixedOff + groupNeed(f0, f1 + 1) <= want) f1++;
+      Carve g(arena + fixedOff, want - fixedOff);
+
+      //  the group's bytes and block table
+      std::vector<size_t> off(f1 - f0 + 1, 0);
+      for (u32 f = f0; f < f1; f++) off[f - f0 + 1] = off[f - f0] + (db.fileBytes[f] + 7) / 8 * 8;
+      const size_t rawBytes = off[f1 - f0];
+      if (!host.need(rawBytes + 8)) { rc = mb_fail(MB_ENOMEM, "cannot allocate %zu bytes of host memory", rawBytes); goto done; }
+      std::atomic<int> bad(-1);
+      parallelFor(f1 - f0, [&](size_t fi) {
+        char path[4096];
+        mb_file_name(path, sizeof(path), db.dir.c_str(), f0 + (u32)fi, false);
+        const size_t n = (size_t)db.fileBytes[f0 + fi];
+        FILE *fp = fopen(path, "rb");
+        if (!fp || (n && fread(host.data() + off[fi], 1, n, fp) != n)) bad = (int)fi;
+        if (fp) fclose(fp);
+      });
+      if (bad >= 0) { rc = mb_fail(MB_EIO, "cannot read data file %u of '%s'", f0 + (u32)bad, dbDir); goto done; }
+      std::vector<UnionBlock> tab;
+      u64 fileStart[65], nk = 0;
+      for (u32 f = 0; f < 65; f++) {
+        fileStart[f] = nk;
+        if (f < f0 || f >= f1) continue;
+        const std::vector<uint8_t> &ix = db.index[f];
+        for (size_t e = 0; e + 24 <= ix.size(); e += 24) {
+          u64 at, n;
+          memcpy(&at, ix.data() + e + 8, 8);  memcpy(&n, ix.data() + e + 16, 8);
+          if (n == 0) continue;
+          if (at >= db.fileBytes[f]) { rc = mb_fail(MB_EFORMAT, "'%s': block index of data file %u points past the end of the file", dbDir, f); goto done; }
+          UnionBlock ub;  ub.byteOff = off[f - f0] + at;  ub.outIdx = nk;
+          tab.push_back(ub);
+          nk += n;
+        }
+      }
+      if (nk) {
+        uint8_t    *dRaw = (uint8_t *)g.take(rawBytes + 16);
+        UnionBlock *dTab = (UnionBlock *)g.take(tab.size() * sizeof(UnionBlock) + 16);
+        void       *dKey = g.take(nk * W + 16);
+        u32        *dVal = (u32 *)g.take(nk * 4 + 16);
+        if (!dRaw || !dTab || !dKey || !dVal) { rc = mb_fail(MB_ENOMEM, "internal: lookup group does not fit"); goto done; }
+        MB_UCUDA(cudaMemcpyAsync(dRaw, host.data(), rawBytes, cudaMemcpyHostToDevice, s));
+        MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
+        MB_UCUDA(cudaMemcpyAsync(dFileStart, fileStart, sizeof(fileStart), cudaMemcpyHostToDevice, s));
+        const unsigned dgrid = (unsigned)((tab.size() + 127) / 128);
+        if (kw == 1) decode_kernel<1><<<dgrid, 128, 0, s>>>(dRaw, rawBytes, dTab, tab.size(), db.wSuffix, (u64 *)dKey, dVal, nk, dErr);
+        else         decode_kernel<2><<<dgrid, 128, 0, s>>>(dRaw, rawBytes, dTab, tab.size(), db.wSuffix, (ulonglong2 *)dKey, dVal, nk, dErr);
+        MB_UCUDA(cudaGetLastError());
+        const unsigned qgrid = (unsigned)((nQueries + 255) / 256);
+        if (kw == 1) lookup_kernel<1><<<qgrid, 256, 0, s>>>((const u64 *)dKey, dVal, dFileStart, f0, f1, k, dQLo, dQHi, nQueries, minValue, maxValue, dOut);
+        else         lookup_kernel<2><<<qgrid, 256, 0, s>>>((const ulonglong2 *)dKey, dVal, dFileStart, f0, f1, k, dQLo, dQHi, nQueries, minValue, maxValue, dOut);
+        MB_UCUDA(cudaGetLastError());
+        u32 err = 0;
+        MB_UCUDA(cudaMemcpyAsync(&err, dErr, 4, cudaMemcpyDeviceToHost, s));
+        MB_UCUDA(cudaStreamSynchronize(s));                  //  (the host buffers are reused by the next group)
+        if (err) { rc = mb_fail(MB_EFORMAT, "corrupt block in '%s' (decoder flags 0x%x)", dbDir, err); goto done; }
+      }
+      f0 = f1;
+    }
+    MB_UCUDA(cudaMemcpyAsync(values, dOut, (size_t)nQueries * 4, cudaMemcpyDeviceToHost, s));
+    MB_UCUDA(cudaStreamSynchronize(s));
+  }
+done:
+  if (s) cudaStreamDestroy(s);
+  if (arena) cudaFree(arena);
+  return rc;
 }
 
 //  `count-suffix=ACG` (merylCommandBuilder.C:271-274; merylOp-countSimple.C:50-93, :172-199): only the k-mers whose counted

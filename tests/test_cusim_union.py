@@ -71,3 +71,9 @@ def test_sim_threshold_words_vs_reference(tmp_path):
 @pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
 def test_sim_count_suffix_vs_reference(tmp_path):
     uc.case_count_suffix(str(tmp_path))
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+@pytest.mark.parametrize("k", [21, 40, 9])
+def test_sim_lookup_vs_reference_print(tmp_path, monkeypatch, k):
+    uc.case_lookup(str(tmp_path), k, monkeypatch=monkeypatch)

@@ -134,3 +134,9 @@ def test_cli_count_suffix(tmp_path):
     assert p.returncode == 0, p.stderr[-800:]
     util.assert_same_db(ref, out)
     assert not os.path.exists(out + ".tmp-count")
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
+@pytest.mark.parametrize("k", [21, 40, 9])
+def test_lookup_vs_reference_print(tmp_path, monkeypatch, k):
+    uc.case_lookup(str(tmp_path), k, n=20_000, monkeypatch=monkeypatch)

@@ -158,3 +158,48 @@ def case_count_suffix(tmp, n=8_000):
         mb.count([fq], full, k, op, memory_gb=2)
         mb.keep_suffix(full, suffix, out)
         util.assert_same_db(ref, out)
+
+
+_CODE = {"A": 0, "C": 1, "T": 2, "G": 3}
+
+
+def _pack(kmer: str):
+    v = 0
+    for ch in kmer:
+        v = (v << 2) | _CODE[ch]
+    return v & 0xffffffffffffffff, v >> 64
+
+
+def case_lookup(tmp, k, n=6_000, monkeypatch=None):
+    """mb_lookup (merylExactLookup::value): every k-mer the reference binary prints for a database must come back with its
+    value, neighbours of present k-mers and random k-mers that are absent with 0, values outside [min, max] with 0 -- count
+    dbs (block writer, several prefix widths) and a union's output (stream writer, prefix 12); with the device arena cut down
+    so that the files are decoded in several groups."""
+    import subprocess
+    import numpy as np
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(n, n // 15, 150, 0.004, 40 + k), k)
+    b = oracle_db(tmp, "b", synth.fasta_bytes(2, n, k), k, wprefix=7)
+    _, u = check_union(tmp, [a, b], tag="lk")
+    rng = np.random.default_rng(k)
+    for db, ws in ((a, 0), (b, 0), (u, 0), (a, 40 << 20)):
+        if ws and monkeypatch is not None:
+            monkeypatch.setenv("MB_UNION_MAX_FILES", "7")      # ... in ten groups of files
+        p = subprocess.run([util.REF_BIN, "print", db], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-300:]
+        truth = {}
+        for line in p.stdout.split("\n"):
+            if line:
+                kmer, val = line.split()
+                truth[_pack(kmer)] = int(val)
+        assert truth
+        present = list(truth)
+        queries = present + [(lo ^ 1, hi) for lo, hi in present[:2000]] + \
+            [(int(rng.integers(0, 2 ** 63)) & ((1 << min(64, 2 * k)) - 1), int(rng.integers(0, 2 ** 62)) & ((1 << max(0, 2 * k - 64)) - 1)) for _ in range(2000)]
+        lo = np.array([q[0] for q in queries], dtype=np.uint64)
+        hi = np.array([q[1] for q in queries], dtype=np.uint64) if k > 32 else None
+        got = mb.lookup(db, lo, hi, workspace_bytes=ws)
+        want = np.array([truth.get(q, 0) for q in queries], dtype=np.uint32)
+        assert np.array_equal(got, want)
+        got = mb.lookup(db, lo, hi, min_value=2, max_value=3, workspace_bytes=ws)
+        want = np.array([truth.get(q, 0) if 2 <= truth.get(q, 0) <= 3 else 0 for q in queries], dtype=np.uint32)
+        assert np.array_equal(got, want)
