@@ -120,7 +120,7 @@ def test_cli_operation_tree_vs_reference(tmp_path):
 
 @pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
 def test_count_suffix_vs_reference(tmp_path):
-    uc.case_count_suffix(str(tmp_path), n=30_000)
+    uc.case_count_suffix(str(tmp_path), n=30_000, full=True)
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")

@@ -140,7 +140,7 @@ def case_threshold_words(tmp, n=12_000):
             util.assert_same_db(ref, out)
 
 
-def case_count_suffix(tmp, n=8_000):
+def case_count_suffix(tmp, n=8_000, full=False):
     """`count-suffix=`: the reference counts only the k-mers that end with the given bases (simple mode, its own db geometry);
     here: the full count, then mb_keep_suffix.  Same directory as the reference binary's, for canonical / forward / reverse
     counts, prefix widths 6 and above, and a suffix no k-mer has."""
@@ -149,8 +149,10 @@ def case_count_suffix(tmp, n=8_000):
     with open(fq, "wb") as fh:
         fh.write(synth.reads_fastq_bytes(n, n // 20, 150, 0.004, 31))
     # (the reference's simple counter allocates 2 * 4^(k-s) bytes: keep k - s small)
-    for k, suffix, op in ((12, "ACG", "count"), (15, "tg", "count-forward"), (14, "A", "count-reverse"), (21, "GATTACA", "count"),
-                          (9, "CCCCCC", "count")):
+    cases = [(12, "ACG", "count"), (13, "tg", "count-forward"), (12, "A", "count-reverse"), (9, "CCCCCC", "count")]
+    if full:
+        cases += [(21, "GATTACA", "count"), (15, "TG", "count")]
+    for k, suffix, op in cases:
         tag = "%d_%s" % (k, suffix)
         ref, full, out = (os.path.join(tmp, x + tag + ".meryl") for x in ("ref", "full", "dev"))
         p = subprocess.run([util.REF_BIN, "k=%d" % k, "memory=2", "count-suffix=" + suffix, op, fq, "output", ref], capture_output=True, text=True)
