@@ -154,11 +154,14 @@ def case_count_suffix(tmp, n=8_000, full=False):
         cases += [(21, "GATTACA", "count"), (15, "TG", "count")]
     for k, suffix, op in cases:
         tag = "%d_%s" % (k, suffix)
-        ref, full, out = (os.path.join(tmp, x + tag + ".meryl") for x in ("ref", "full", "dev"))
+        ref, full_db, out = (os.path.join(tmp, x + tag + ".meryl") for x in ("ref", "full", "dev"))
         p = subprocess.run([util.REF_BIN, "k=%d" % k, "memory=2", "count-suffix=" + suffix, op, fq, "output", ref], capture_output=True, text=True)
         assert p.returncode == 0, p.stderr[-500:]
-        mb.count([fq], full, k, op, memory_gb=2)
-        mb.keep_suffix(full, suffix, out)
+        with mb.Counter(k, 8, op) as c:                      # (the full count's own prefix width does not matter)
+            c.add_file(fq)
+            c.count()
+            c.write_db(full_db)
+        mb.keep_suffix(full_db, suffix, out)
         util.assert_same_db(ref, out)
 
 
