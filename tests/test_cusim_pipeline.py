@@ -174,8 +174,7 @@ def test_sim_parallel_parse_in_the_pipeline(tmp_path, monkeypatch):
 
 # ---- count batches (W6: merylBlockWriter::finishBatch / mergeBatches, kmers-writer-block.C:172-386) --------------------
 
-@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 10, "count", 190_000), (31, 9, "count-forward", 120_000),
-                                                       (51, 8, "count", 150_000), (8, 6, "count-reverse", 100_000)])
+@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 10, "count", 190_000), (51, 8, "count-forward", 150_000), (8, 6, "count-reverse", 100_000)])
 def test_sim_count_batches(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
     """Reads that outgrow the device are counted in batches cut at record breaks; the batches' blocks are decoded, merged
     (saturating sums) and encoded again with the block writer's rules.  MB_MAX_BATCH_BASES makes a small input take that
