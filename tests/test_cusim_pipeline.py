@@ -291,3 +291,31 @@ def test_sim_file_shard_exact_or_error(tmp_path):
         util.assert_same_db(ora, out)
         exact += 1
     assert errors + exact == 6
+
+
+def test_sim_count_batches_edges(tmp_path, monkeypatch):
+    """Batch cuts wait for a record break: a record longer than the batch limit stays whole; homopolymer compression
+    (MB_FLAG_COMPRESS) carries no state over a cut; N runs and lowercase as usual."""
+    monkeypatch.setenv("MB_MAX_BATCH_BASES", "30000")
+    rng = np.random.default_rng(3)
+    long_rec = synth.random_bases(100_000, rng).tobytes()                      # > 3 batch limits, no break inside
+    recs = [b">long\n" + long_rec + b"\n"]
+    for i in range(300):
+        s = bytearray(synth.random_bases(int(rng.integers(50, 300)), rng).tobytes())
+        if i % 7 == 0:
+            s[10:20] = b"N" * 10
+        if i % 5 == 0:
+            s = bytearray(bytes(s).lower())
+        recs.append(b">r%d\n" % i + bytes(s) + b"\n")
+    fa = tmp_path / "e.fa"
+    fa.write_bytes(b"".join(recs))
+    for flags, words in ((0, []), (mb.FLAG_COMPRESS, ["compress"])):
+        ora, out = str(tmp_path / ("ora%d.meryl" % flags)), str(tmp_path / ("sim%d.meryl" % flags))
+        util.run_oracle(["k=19", "wprefix=8"] + words + ["count", str(fa), "output", ora])
+        with mb.Counter(19, 8, flags=flags) as c:
+            c.add_file(str(fa))
+            c.count()
+            st = c.stats()
+            c.write_db(out)
+        util.assert_same_db(ora, out)
+        assert st.nBatches >= 3

@@ -9,6 +9,7 @@ import pytest
 import util
 import meryl_b200 as mb
 import union_cases as uc
+from meryl_b200 import synth
 
 SIM_DIR = os.path.join(util.ROOT, "tests", "cusim")
 SIM_LIB = os.path.join(SIM_DIR, "_build", "libmeryl_b200_sim.so")
@@ -77,3 +78,24 @@ def test_sim_count_suffix_vs_reference(tmp_path):
 @pytest.mark.parametrize("k", [21, 40, 9])
 def test_sim_lookup_vs_reference_print(tmp_path, monkeypatch, k):
     uc.case_lookup(str(tmp_path), k, monkeypatch=monkeypatch)
+
+
+def test_sim_new_entry_points_refuse_bad_arguments(tmp_path):
+    a = uc.oracle_db(str(tmp_path), "a", synth.fasta_bytes(1, 3_000, 4), 21)
+    out = str(tmp_path / "o.meryl")
+    for suffix, msg in (("ACGN", "not made of ACGT"), ("", "1..32 bases"), ("A" * 21, "shorter than k"), ("A" * 33, "1..32 bases")):
+        with pytest.raises(mb.MerylB200Error) as e:
+            mb.keep_suffix(a, suffix, out)
+        assert msg in str(e.value)
+    b = uc.oracle_db(str(tmp_path), "b", synth.fasta_bytes(1, 3_000, 4), 40)
+    with pytest.raises(mb.MerylB200Error) as e:
+        mb.keep_suffix(b, "ACG", out)                           # 2k - 2s = 74 > 42: the reference cannot do it either
+    assert "not possible" in str(e.value)
+    import numpy as np
+    with pytest.raises(mb.MerylB200Error) as e:
+        mb.lookup(b, np.zeros(3, dtype=np.uint64))                # k = 40 needs the high words
+    assert "high words" in str(e.value)
+    assert mb.lookup(a, np.zeros(0, dtype=np.uint64)).size == 0
+    e_db = uc.oracle_db(str(tmp_path), "e", b">x\nACGT\n", 21)     # a database without k-mers
+    assert mb.db_threshold(e_db, distinct=0.5) in (0, 2 ** 64 - 1)
+    assert list(mb.lookup(e_db, np.array([5, 6], dtype=np.uint64))) == [0, 0]
