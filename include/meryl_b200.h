@@ -240,6 +240,10 @@ int mb_set_operation(uint32_t op, const char *const *inDirs, uint32_t nInputs, c
 #define MB_OP_MODULO               22
 int mb_value_operation(uint32_t op, uint64_t param, const char *inDir, const char *outDir, int32_t device,
                        uint64_t workspaceBytes, mb_union_stats *st);
+/*  What `meryl histogram` / `meryl statistics` print (merylOp-histogram.C:20-100): k, the totals and the value histogram of
+ *  a database, read from its master index (host only).  values / occurrences may be NULL to ask for the length (*n) only.  */
+int mb_db_histogram(const char *dbDir, uint32_t *k, uint64_t *nUnique, uint64_t *nDistinct, uint64_t *nTotal,
+                    uint64_t *values, uint64_t *occurrences, uint64_t cap, uint64_t *n);
 /*  `count-suffix=<bases>` (merylCommandBuilder.C:271-274, merylOp-countSimple.C:50-93, :172-199): keeps the k-mers of a count
  *  database that end with the given bases and writes them with the geometry of the reference's simple counter (prefix width
  *  6 + max(0, 2k - 2s - 26), a block for every prefix).  `meryl-b200 count count-suffix=ACG ...` = count, then this.  */

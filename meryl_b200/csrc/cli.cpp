@@ -301,7 +301,52 @@ int main(int argc, char **argv) {
   return rc;
 }
 
+//  `meryl histogram <db>` and `meryl statistics <db>` (merylOp-histogram.C:20-100): printed from the master index.
+static int reportMain(int argc, char **argv, bool statistics) {
+  const char *db = nullptr;
+  for (int i = 1; i < argc; i++) {
+    const std::string idx = std::string(argv[i]) + "/merylIndex";
+    if (access(idx.c_str(), R_OK) == 0) {
+      if (db) { fprintf(stderr, "ERROR: told to dump a histogram for more than one input!\n"); return 1; }
+      db = argv[i];
+    }
+  }
+  if (!db) { fprintf(stderr, "ERROR: no meryl database given to %s.\n", statistics ? "statistics" : "histogram"); return 1; }
+  uint32_t k = 0;
+  uint64_t nUnique = 0, nDistinct = 0, nTotal = 0, n = 0;
+  if (mb_db_histogram(db, &k, &nUnique, &nDistinct, &nTotal, nullptr, nullptr, 0, &n) != MB_OK) { fprintf(stderr, "ERROR: %s\n", mb_last_error()); return 1; }
+  std::vector<uint64_t> val(n + 1), occ(n + 1);
+  if (mb_db_histogram(db, nullptr, nullptr, nullptr, nullptr, val.data(), occ.data(), n, &n) != MB_OK) { fprintf(stderr, "ERROR: %s\n", mb_last_error()); return 1; }
+  if (!statistics) {
+    for (uint64_t i = 0; i < n; i++) fprintf(stdout, "%llu\t%llu\n", (unsigned long long)val[i], (unsigned long long)occ[i]);
+    return 0;
+  }
+  const uint64_t nUniverse = (2 * k >= 64) ? 0 : ((uint64_t)1 << (2 * k));        //  buildLowBitMask<uint64>(2k) + 1, wraps for k >= 32
+  fprintf(stdout, "Number of %u-mers that are:\n", k);
+  fprintf(stdout, "  unique   %20llu  (exactly one instance of the kmer is in the input)\n", (unsigned long long)nUnique);
+  fprintf(stdout, "  distinct %20llu  (non-redundant kmer sequences in the input)\n", (unsigned long long)nDistinct);
+  fprintf(stdout, "  present  %20llu  (...)\n", (unsigned long long)nTotal);
+  fprintf(stdout, "  missing  %20llu  (non-redundant kmer sequences not in the input)\n", (unsigned long long)(nUniverse - nDistinct));
+  fprintf(stdout, "\n");
+  fprintf(stdout, "             number of   cumulative   cumulative     presence\n");
+  fprintf(stdout, "              distinct     fraction     fraction   in dataset\n");
+  fprintf(stdout, "frequency        kmers     distinct        total       (1e-6)\n");
+  fprintf(stdout, "--------- ------------ ------------ ------------ ------------\n");
+  uint64_t sDistinct = 0, sTotal = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    sDistinct += occ[i];
+    sTotal    += occ[i] * val[i];
+    fprintf(stdout, "%9llu %12llu %12.4f %12.4f %12.6f\n", (unsigned long long)val[i], (unsigned long long)occ[i],
+            (double)sDistinct / nDistinct, (double)sTotal / nTotal, (double)val[i] / nTotal * 1000000.0);
+  }
+  return 0;
+}
+
 static int flatMain(int argc, char **argv) {
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "histogram"))  return reportMain(argc, argv, false);
+    if (!strcmp(argv[i], "statistics")) return reportMain(argc, argv, true);
+  }
   for (int i = 1; i < argc; i++)
     if (setOpOf(argv[i]) >= 0) return unionSumMain(argc, argv);
 

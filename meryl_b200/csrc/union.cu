@@ -729,6 +729,34 @@ struct Carve {
 }  //  namespace
 
 
+//  The statistics of a database as its master index holds them (merylHistogram::load, kmers-histogram.C:97-130): what
+//  `meryl histogram` and `meryl statistics` print (merylOp-histogram.C:20-100).  values / occurrences may be NULL to ask for
+//  the length only; host only.
+extern "C" int mb_db_histogram(const char *dbDir, uint32_t *k, uint64_t *nUnique, uint64_t *nDistinct, uint64_t *nTotal,
+                               uint64_t *values, uint64_t *occurrences, uint64_t cap, uint64_t *n) {
+  mb_clear_error();
+  if (!dbDir || !n) return mb_fail(MB_EINVAL, "mb_db_histogram: NULL argument");
+  std::vector<uint8_t> m;
+  MB_TRY(readWhole(std::string(dbDir) + "/merylIndex", m));
+  HostBits hb;
+  if (!hb.open(m.data(), m.size())) return mb_fail(MB_EFORMAT, "'%s/merylIndex' is not a meryl index", dbDir);
+  const u64 m1 = hb.get(64), m2 = hb.get(64);
+  if (m1 != 0x646e496c7972656dull || m2 != 0x33302e765f5f7865ull) return mb_fail(MB_EFORMAT, "'%s' is not a meryl v.03 database", dbDir);
+  const u32 wP = (u32)hb.get(32), wS = (u32)hb.get(32);
+  hb.get(32);  hb.get(32);  hb.get(32);                     //  file bits, block bits, flags
+  const u64 nu = hb.get(64), nd = hb.get(64), nt = hb.get(64), nv = hb.get(64);
+  if (k) *k = (wP + wS) / 2;
+  if (nUnique) *nUnique = nu;
+  if (nDistinct) *nDistinct = nd;
+  if (nTotal) *nTotal = nt;
+  *n = nv;
+  if (values && occurrences) {
+    if (cap < nv) return mb_fail(MB_EINVAL, "mb_db_histogram: the histogram has %llu entries", (unsigned long long)nv);
+    for (u64 i = 0; i < nv; i++) { values[i] = hb.get(64); occurrences[i] = hb.get(64); }
+  }
+  return MB_OK;
+}
+
 //  Threshold of a filter given as a share of the input's k-mers (merylOperation::initializeThreshold,
 //  src/meryl/merylOp-nextMer.C:65-125): fracDistinct (distinct= / d=) -> the smallest value v such that the k-mers with
 //  value <= v are at least fracDistinct * numDistinct; wordFrequency (word-frequency= / f=) -> wordFrequency * numTotal,

@@ -252,3 +252,23 @@ def test_cli_operation_trees_become_flat_commands(tmp_path):
     assert rc == 1 and "No output specified" in err
     rc, _, err = dry("union [ count k=9 a output z".split())
     assert rc == 1 and "without a ']'" in err
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+def test_cli_histogram_and_statistics_print_what_the_reference_prints(tmp_path):
+    """`meryl histogram` / `meryl statistics` (merylOp-histogram.C:20-100) from the master index: no device involved.  On
+    every golden count db (k = 8 ... 64: the 'missing' line wraps for k >= 32 like the reference's) and a golden union."""
+    dbs = []
+    for name in util.golden_cases():
+        (tmp_path / name).mkdir()
+        dbs.append(util.load_golden(name, str(tmp_path / name))[1])
+    (tmp_path / "u").mkdir()
+    dbs.append(util.load_union_golden(util.union_golden_cases()[0], str(tmp_path / "u"))[1])
+    for db in dbs:
+        for word in ("histogram", "statistics"):
+            ours = _cli([word, db])
+            ref = subprocess.run([util.REF_BIN, word, db], capture_output=True, text=True)
+            assert ours.returncode == 0 and ref.returncode == 0, ours.stderr
+            assert ours.stdout == ref.stdout and ours.stdout
+    p = _cli(["histogram", str(tmp_path)])
+    assert p.returncode == 1 and "no meryl database" in p.stderr
