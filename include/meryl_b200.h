@@ -264,6 +264,12 @@ int mb_db_threshold(const char *dbDir, double fracDistinct, double wordFrequency
 int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const uint64_t *kmerLo, const uint64_t *kmerHi,
               uint64_t nQueries, uint32_t *values, int32_t device, uint64_t workspaceBytes);
 
+/*  Every k-mer of a database with its value, in ascending order (merylFileReader::nextMer, kmers-reader.C:456-531 -- the
+ *  loop behind `meryl print`): blocks decoded on the device, lists handed to the callback in pieces (kmerHi NULL for k <= 32).
+ *  A non-zero return of the callback stops the walk.  */
+typedef int (*mb_kmer_callback)(void *arg, uint32_t k, const uint64_t *kmerLo, const uint64_t *kmerHi, const uint32_t *values, uint64_t n);
+int mb_for_each_kmer(const char *dbDir, mb_kmer_callback cb, void *arg, int32_t device, uint64_t workspaceBytes);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

@@ -369,3 +369,24 @@ def lookup(db, kmer_lo, kmer_hi=None, min_value: int = 0, max_value: int = 0xfff
     _check(L.mb_lookup(os.fsencode(os.fspath(db)), min_value, max_value, lo.ctypes.data, None if hi is None else hi.ctypes.data,
                        lo.size, out.ctypes.data, device, workspace_bytes))
     return out
+
+
+def all_kmers(db, device: int = -1, workspace_bytes: int = 0):
+    """Every (k-mer lo, k-mer hi or None, value) of a database in ascending order (mb_for_each_kmer), as numpy arrays."""
+    import numpy as np
+    los, his, vals = [], [], []
+    CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                          ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint64)
+
+    def piece(_arg, _k, lo, hi, val, n):
+        los.append(np.ctypeslib.as_array(lo, shape=(n,)).copy())
+        if hi:
+            his.append(np.ctypeslib.as_array(hi, shape=(n,)).copy())
+        vals.append(np.ctypeslib.as_array(val, shape=(n,)).copy())
+        return 0
+
+    L = lib()
+    L.mb_for_each_kmer.argtypes = [ctypes.c_char_p, CB, ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64]
+    _check(L.mb_for_each_kmer(os.fsencode(os.fspath(db)), CB(piece), None, device, workspace_bytes))
+    cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
+    return cat(los, np.uint64), (cat(his, np.uint64) if his else None), cat(vals, np.uint32)

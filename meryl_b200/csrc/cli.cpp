@@ -8,8 +8,8 @@
 //                 count|count-forward|count-reverse [compress] <seq files...> output <db.meryl>
 //
 //  Words are order-free like the reference's.  Errors are a message on stderr and exit(1)
-//  (missing k: merylOp-count.C:311-312; missing output: :314-315).  `union-sum <dbs> output <db>` is the one
-//  set operation implemented (csrc/union.cu).  Any other operation (print, statistics, intersect, ...)
+//  (missing k: merylOp-count.C:311-312; missing output: :314-315).  The set operations and filters on databases
+//  (csrc/union.cu), `histogram`, `statistics` and `print <db>` are here too.  Any other word (compare, lookup tools, ...)
 //  is not part of this tool: if $MERYL_REFERENCE names the reference
 //  binary the whole command line is handed to it unchanged, otherwise it is an error.
 
@@ -342,10 +342,43 @@ static int reportMain(int argc, char **argv, bool statistics) {
   return 0;
 }
 
+//  `meryl print <db>` (merylOp-nextMer.C:646-667: "<k-mer>\t<value>" per line): the blocks are decoded on the device
+//  (mb_for_each_kmer), the text is made here.  Ascending k-mer order (the reference's order with threads=1).
+static int printPiece(void *arg, uint32_t k, const uint64_t *lo, const uint64_t *hi, const uint32_t *val, uint64_t n) {
+  FILE *out = (FILE *)arg;
+  static const char letter[4] = { 'A', 'C', 'T', 'G' };    //  kmers-tiny.H:86
+  char line[128];
+  for (uint64_t i = 0; i < n; i++) {
+    for (uint32_t b = 0; b < k; b++) {
+      const uint32_t sh = 2 * (k - 1 - b);
+      const uint64_t w = sh >= 64 ? hi[i] >> (sh - 64) : lo[i] >> sh;
+      line[b] = letter[w & 3];
+    }
+    const int m = snprintf(line + k, sizeof(line) - k, "\t%u\n", val[i]);
+    if (fwrite(line, 1, k + (size_t)m, out) != k + (size_t)m) return 1;
+  }
+  return 0;
+}
+
+static int printMain(int argc, char **argv) {
+  const char *db = nullptr;
+  for (int i = 1; i < argc; i++) {
+    const std::string idx = std::string(argv[i]) + "/merylIndex";
+    if (access(idx.c_str(), R_OK) == 0) {
+      if (db) { fprintf(stderr, "ERROR: print of more than one database: combine them with an operation first.\n"); return 1; }
+      db = argv[i];
+    }
+  }
+  if (!db) { fprintf(stderr, "ERROR: no meryl database given to print.\n"); return 1; }
+  if (mb_for_each_kmer(db, printPiece, stdout, -1, 0) != MB_OK) { fprintf(stderr, "ERROR: %s\n", mb_last_error()); return 1; }
+  return fflush(stdout) == 0 ? 0 : 1;
+}
+
 static int flatMain(int argc, char **argv) {
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "histogram"))  return reportMain(argc, argv, false);
     if (!strcmp(argv[i], "statistics")) return reportMain(argc, argv, true);
+    if (!strcmp(argv[i], "print"))      return printMain(argc, argv);
   }
   for (int i = 1; i < argc; i++)
     if (setOpOf(argv[i]) >= 0) return unionSumMain(argc, argv);

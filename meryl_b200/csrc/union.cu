@@ -788,21 +788,27 @@ extern "C" int mb_db_threshold(const char *dbDir, double fracDistinct, double wo
   return MB_OK;
 }
 
-//  merylExactLookup::value for many k-mers at once (kernel K9 above).  values[i] = the value of k-mer i (kmerLo[i], and
-//  kmerHi[i] for k > 32; first base in the top bits, as everywhere) in the database, 0 if absent or outside
-//  [minValue, maxValue].  The k-mers are looked up as given: the caller passes the canonical form for canonical databases,
-//  like merylExactLookup's callers do (meryl-lookup: existence.C).  The database is decoded group of files by group of files.
-extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const uint64_t *kmerLo, const uint64_t *kmerHi,
-                         uint64_t nQueries, uint32_t *values, int32_t device, uint64_t workspaceBytes) {
-  mb_clear_error();
-  if (!dbDir || (nQueries && (!kmerLo || !values))) return mb_fail(MB_EINVAL, "mb_lookup: NULL argument");
+//  A database decoded on the device, one group of consecutive data files at a time (the reader side of the set operations
+//  without the merge: merylFileReader's loop over blocks, kmers-reader.C:456-531).  setup(db, top, s) carves the caller's
+//  own buffers from the bottom of the arena; perGroup(db, g, s) works on a group's sorted (k-mer, value) lists while they are
+//  resident (the stream is synchronized after it returns); finish(s) runs after the last group.
+struct DecodedGroup {
+  const void *dKey = nullptr;           //  u64 or ulonglong2, all files of the group back to back
+  const u32  *dVal = nullptr;
+  u64         fileStart[65];            //  k-mers of the group before file f (files outside the group are empty ranges)
+  const u64  *dFileStart = nullptr;     //  the same on the device
+  u32         f0 = 0, f1 = 0;
+  u64         nKmers = 0;
+};
+
+template <typename Setup, typename PerGroup, typename Finish>
+static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspaceBytes, size_t fixedBytes,
+                            Setup setup, PerGroup perGroup, Finish finish) {
   int nDev = 0;
-  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return mb_fail(MB_ENODEVICE, "mb_lookup: no CUDA device (this library has no CPU path)");
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return mb_fail(MB_ENODEVICE, "no CUDA device (this library has no CPU path)");
   InputDb db;
   MB_TRY(openDb(dbDir, db));
-  const u32 k = db.k, kw = k <= 32 ? 1 : 2, W = 8 * kw;
-  if (kw == 2 && nQueries && !kmerHi) return mb_fail(MB_EINVAL, "mb_lookup: k=%u needs the high words of the k-mers", k);
-  if (nQueries == 0) return MB_OK;
+  const u32 kw = db.k <= 32 ? 1 : 2, W = 8 * kw;
 
   int rc = MB_OK;
   uint8_t *arena = nullptr;
@@ -811,30 +817,24 @@ extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue
     if (device >= 0) MB_UCUDA(cudaSetDevice(device));
     size_t freeB = 0, totalB = 0;
     MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
-    const size_t qBytes = (size_t)nQueries * (W + 4) + 4096;
     auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
       size_t need = (size_t)16 << 20;
       for (u32 f = f0; f < f1; f++) need += db.fileBytes[f] + 256 + db.index[f].size() / 24 * sizeof(UnionBlock) + db.fileKmers[f] * (W + 4) + 1024;
       return need;
     };
     size_t want = workspaceBytes ? (size_t)workspaceBytes : std::min(freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2,
-                                                                     qBytes + groupNeed(0, 64) + ((size_t)64 << 20));
+                                                                     fixedBytes + groupNeed(0, 64) + ((size_t)64 << 20));
     if (want > freeB) want = freeB;
     want = want / 256 * 256;
     if (cudaMalloc((void **)&arena, want) != cudaSuccess) { cudaGetLastError(); arena = nullptr; rc = mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want); goto done; }
     MB_UCUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
 
     Carve top(arena, want);
-    u64 *dQLo = (u64 *)top.take((size_t)nQueries * 8);
-    u64 *dQHi = kw == 2 ? (u64 *)top.take((size_t)nQueries * 8) : nullptr;
-    u32 *dOut = (u32 *)top.take((size_t)nQueries * 4);
     u64 *dFileStart = (u64 *)top.take(65 * 8);
     u32 *dErr = (u32 *)top.take(256);
-    if (!dQLo || (kw == 2 && !dQHi) || !dOut || !dFileStart || !dErr) { rc = mb_fail(MB_ENOMEM, "the %llu queries do not fit the device arena", (unsigned long long)nQueries); goto done; }
-    MB_UCUDA(cudaMemcpyAsync(dQLo, kmerLo, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
-    if (kw == 2) MB_UCUDA(cudaMemcpyAsync(dQHi, kmerHi, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
-    MB_UCUDA(cudaMemsetAsync(dOut, 0, (size_t)nQueries * 4, s));
+    if (!dFileStart || !dErr) { rc = mb_fail(MB_ENOMEM, "device arena too small"); goto done; }
     MB_UCUDA(cudaMemsetAsync(dErr, 0, 256, s));
+    MB_UTRY(setup(db, top, s));
     const size_t fixedOff = top.off;
 
     HostBuf host;
@@ -862,9 +862,11 @@ extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue
       });
       if (bad >= 0) { rc = mb_fail(MB_EIO, "cannot read data file %u of '%s'", f0 + (u32)bad, dbDir); goto done; }
       std::vector<UnionBlock> tab;
-      u64 fileStart[65], nk = 0;
+      DecodedGroup G;
+      G.f0 = f0;  G.f1 = f1;  G.dFileStart = dFileStart;
+      u64 nk = 0;
       for (u32 f = 0; f < 65; f++) {
-        fileStart[f] = nk;
+        G.fileStart[f] = nk;
         if (f < f0 || f >= f1) continue;
         const std::vector<uint8_t> &ix = db.index[f];
         for (size_t e = 0; e + 24 <= ix.size(); e += 24) {
@@ -877,23 +879,22 @@ extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue
           nk += n;
         }
       }
+      G.nKmers = nk;
       if (nk) {
         uint8_t    *dRaw = (uint8_t *)g.take(rawBytes + 16);
         UnionBlock *dTab = (UnionBlock *)g.take(tab.size() * sizeof(UnionBlock) + 16);
         void       *dKey = g.take(nk * W + 16);
         u32        *dVal = (u32 *)g.take(nk * 4 + 16);
-        if (!dRaw || !dTab || !dKey || !dVal) { rc = mb_fail(MB_ENOMEM, "internal: lookup group does not fit"); goto done; }
+        if (!dRaw || !dTab || !dKey || !dVal) { rc = mb_fail(MB_ENOMEM, "internal: decoded group does not fit"); goto done; }
         MB_UCUDA(cudaMemcpyAsync(dRaw, host.data(), rawBytes, cudaMemcpyHostToDevice, s));
         MB_UCUDA(cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(UnionBlock), cudaMemcpyHostToDevice, s));
-        MB_UCUDA(cudaMemcpyAsync(dFileStart, fileStart, sizeof(fileStart), cudaMemcpyHostToDevice, s));
+        MB_UCUDA(cudaMemcpyAsync(dFileStart, G.fileStart, sizeof(G.fileStart), cudaMemcpyHostToDevice, s));
         const unsigned dgrid = (unsigned)((tab.size() + 127) / 128);
         if (kw == 1) decode_kernel<1><<<dgrid, 128, 0, s>>>(dRaw, rawBytes, dTab, tab.size(), db.wSuffix, (u64 *)dKey, dVal, nk, dErr);
         else         decode_kernel<2><<<dgrid, 128, 0, s>>>(dRaw, rawBytes, dTab, tab.size(), db.wSuffix, (ulonglong2 *)dKey, dVal, nk, dErr);
         MB_UCUDA(cudaGetLastError());
-        const unsigned qgrid = (unsigned)((nQueries + 255) / 256);
-        if (kw == 1) lookup_kernel<1><<<qgrid, 256, 0, s>>>((const u64 *)dKey, dVal, dFileStart, f0, f1, k, dQLo, dQHi, nQueries, minValue, maxValue, dOut);
-        else         lookup_kernel<2><<<qgrid, 256, 0, s>>>((const ulonglong2 *)dKey, dVal, dFileStart, f0, f1, k, dQLo, dQHi, nQueries, minValue, maxValue, dOut);
-        MB_UCUDA(cudaGetLastError());
+        G.dKey = dKey;  G.dVal = dVal;
+        MB_UTRY(perGroup(db, G, s));
         u32 err = 0;
         MB_UCUDA(cudaMemcpyAsync(&err, dErr, 4, cudaMemcpyDeviceToHost, s));
         MB_UCUDA(cudaStreamSynchronize(s));                  //  (the host buffers are reused by the next group)
@@ -901,13 +902,86 @@ extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue
       }
       f0 = f1;
     }
-    MB_UCUDA(cudaMemcpyAsync(values, dOut, (size_t)nQueries * 4, cudaMemcpyDeviceToHost, s));
+    MB_UTRY(finish(s));
     MB_UCUDA(cudaStreamSynchronize(s));
   }
 done:
   if (s) cudaStreamDestroy(s);
   if (arena) cudaFree(arena);
   return rc;
+}
+
+//  merylExactLookup::value for many k-mers at once (kernel K9 above).  values[i] = the value of k-mer i (kmerLo[i], and
+//  kmerHi[i] for k > 32; first base in the top bits, as everywhere) in the database, 0 if absent or outside
+//  [minValue, maxValue].  The k-mers are looked up as given: the caller passes the canonical form for canonical databases,
+//  like merylExactLookup's callers do (meryl-lookup: existence.C).
+extern "C" int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const uint64_t *kmerLo, const uint64_t *kmerHi,
+                         uint64_t nQueries, uint32_t *values, int32_t device, uint64_t workspaceBytes) {
+  mb_clear_error();
+  if (!dbDir || (nQueries && (!kmerLo || !values))) return mb_fail(MB_EINVAL, "mb_lookup: NULL argument");
+  if (nQueries == 0) return MB_OK;
+  u64 *dQLo = nullptr, *dQHi = nullptr;
+  u32 *dOut = nullptr;
+  return decodeDbInGroups(dbDir, device, workspaceBytes, (size_t)nQueries * 20 + 4096,
+    [&](const InputDb &db, Carve &top, cudaStream_t s) -> int {
+      const bool wide = db.k > 32;
+      if (wide && !kmerHi) return mb_fail(MB_EINVAL, "mb_lookup: k=%u needs the high words of the k-mers", db.k);
+      dQLo = (u64 *)top.take((size_t)nQueries * 8);
+      dQHi = wide ? (u64 *)top.take((size_t)nQueries * 8) : nullptr;
+      dOut = (u32 *)top.take((size_t)nQueries * 4);
+      if (!dQLo || (wide && !dQHi) || !dOut) return mb_fail(MB_ENOMEM, "the %llu queries do not fit the device arena", (unsigned long long)nQueries);
+      MB_CUDA(cudaMemcpyAsync(dQLo, kmerLo, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
+      if (wide) MB_CUDA(cudaMemcpyAsync(dQHi, kmerHi, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
+      MB_CUDA(cudaMemsetAsync(dOut, 0, (size_t)nQueries * 4, s));
+      return MB_OK;
+    },
+    [&](const InputDb &db, const DecodedGroup &G, cudaStream_t s) -> int {
+      const unsigned qgrid = (unsigned)((nQueries + 255) / 256);
+      if (db.k <= 32) lookup_kernel<1><<<qgrid, 256, 0, s>>>((const u64 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dQLo, dQHi, nQueries, minValue, maxValue, dOut);
+      else            lookup_kernel<2><<<qgrid, 256, 0, s>>>((const ulonglong2 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dQLo, dQHi, nQueries, minValue, maxValue, dOut);
+      MB_CUDA(cudaGetLastError());
+      return MB_OK;
+    },
+    [&](cudaStream_t s) -> int {
+      MB_CUDA(cudaMemcpyAsync(values, dOut, (size_t)nQueries * 4, cudaMemcpyDeviceToHost, s));
+      return MB_OK;
+    });
+}
+
+//  Every k-mer of a database with its value, in order (merylFileReader::nextMer, kmers-reader.C:456-531; what `meryl print`
+//  walks): the blocks are decoded on the device, the lists come back to the host a group of files at a time and are handed
+//  to the callback in pieces.  kmerHi is NULL for k <= 32.  A non-zero return of the callback stops the walk (MB_EIO).
+extern "C" int mb_for_each_kmer(const char *dbDir, mb_kmer_callback cb, void *arg, int32_t device, uint64_t workspaceBytes) {
+  mb_clear_error();
+  if (!dbDir || !cb) return mb_fail(MB_EINVAL, "mb_for_each_kmer: NULL argument");
+  std::vector<u64> lo, hi, both;
+  std::vector<u32> val;
+  return decodeDbInGroups(dbDir, device, workspaceBytes, 4096,
+    [&](const InputDb &, Carve &, cudaStream_t) -> int { return MB_OK; },
+    [&](const InputDb &db, const DecodedGroup &G, cudaStream_t s) -> int {
+      const u64 n = G.nKmers;
+      const bool wide = db.k > 32;
+      val.resize(n);
+      MB_CUDA(cudaMemcpyAsync(val.data(), G.dVal, n * 4, cudaMemcpyDeviceToHost, s));
+      if (!wide) {
+        lo.resize(n);
+        MB_CUDA(cudaMemcpyAsync(lo.data(), G.dKey, n * 8, cudaMemcpyDeviceToHost, s));
+        MB_CUDA(cudaStreamSynchronize(s));
+      } else {
+        both.resize(2 * n);  lo.resize(n);  hi.resize(n);
+        MB_CUDA(cudaMemcpyAsync(both.data(), G.dKey, n * 16, cudaMemcpyDeviceToHost, s));
+        MB_CUDA(cudaStreamSynchronize(s));
+        for (u64 i = 0; i < n; i++) { lo[i] = both[2 * i]; hi[i] = both[2 * i + 1]; }
+      }
+      const u64 PIECE = (u64)1 << 20;
+      for (u64 at = 0; at < n; at += PIECE) {
+        const u64 m = std::min(PIECE, n - at);
+        if (cb(arg, db.k, (const uint64_t *)lo.data() + at, wide ? (const uint64_t *)hi.data() + at : nullptr, val.data() + at, m) != 0)
+          return mb_fail(MB_EIO, "mb_for_each_kmer: stopped by the callback");
+      }
+      return MB_OK;
+    },
+    [&](cudaStream_t) -> int { return MB_OK; });
 }
 
 //  `count-suffix=ACG` (merylCommandBuilder.C:271-274; merylOp-countSimple.C:50-93, :172-199): only the k-mers whose counted

@@ -99,3 +99,10 @@ def test_sim_new_entry_points_refuse_bad_arguments(tmp_path):
     e_db = uc.oracle_db(str(tmp_path), "e", b">x\nACGT\n", 21)     # a database without k-mers
     assert mb.db_threshold(e_db, distinct=0.5) in (0, 2 ** 64 - 1)
     assert list(mb.lookup(e_db, np.array([5, 6], dtype=np.uint64))) == [0, 0]
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+@pytest.mark.parametrize("k", [21, 40])
+def test_sim_cli_print_vs_reference(tmp_path, k):
+    """The command line tool with the emulated library in front of the CUDA one (LD_PRELOAD: same C ABI)."""
+    uc.case_cli_print(str(tmp_path), k, env=dict(os.environ, LD_PRELOAD=SIM_LIB))

@@ -140,3 +140,9 @@ def test_cli_count_suffix(tmp_path):
 @pytest.mark.parametrize("k", [21, 40, 9])
 def test_lookup_vs_reference_print(tmp_path, monkeypatch, k):
     uc.case_lookup(str(tmp_path), k, n=20_000, monkeypatch=monkeypatch)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not on this box")
+@pytest.mark.parametrize("k", [21, 40])
+def test_cli_print_vs_reference(tmp_path, k):
+    uc.case_cli_print(str(tmp_path), k, n=30_000)

@@ -201,6 +201,8 @@ def test_cli_errors_like_the_reference(tmp_path):
     p = _cli(["k=21", "count", str(fa)])
     assert p.returncode == 1 and "No output specified" in p.stderr             # merylOp-count.C:314-315
     p = _cli(["k=21", "print", "x.meryl"])
+    assert p.returncode == 1 and "no meryl database given to print" in p.stderr
+    p = _cli(["k=21", "compare", "x.meryl"])
     assert p.returncode == 1 and "not part of `meryl count`" in p.stderr
     p = _cli(["k=21", "intersect", "x.meryl", "y.meryl", "output", "z.meryl"])
     assert p.returncode == 1 and "is not a meryl database" in p.stderr

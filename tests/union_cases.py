@@ -205,6 +205,24 @@ def case_lookup(tmp, k, n=6_000, monkeypatch=None):
         got = mb.lookup(db, lo, hi, workspace_bytes=ws)
         want = np.array([truth.get(q, 0) for q in queries], dtype=np.uint32)
         assert np.array_equal(got, want)
+        # the whole database in order (mb_for_each_kmer, the walk behind `meryl print`) is the reference's print, sorted
+        alo, ahi, aval = mb.all_kmers(db, workspace_bytes=ws)
+        listed = [((int(alo[i]), int(ahi[i]) if ahi is not None else 0), int(aval[i])) for i in range(alo.size)]
+        assert listed == sorted(truth.items(), key=lambda kv: (kv[0][1], kv[0][0]))
         got = mb.lookup(db, lo, hi, min_value=2, max_value=3, workspace_bytes=ws)
         want = np.array([truth.get(q, 0) if 2 <= truth.get(q, 0) <= 3 else 0 for q in queries], dtype=np.uint32)
         assert np.array_equal(got, want)
+
+
+def case_cli_print(tmp, k, n=3_000, env=None):
+    """`meryl-b200 print db`: blocks decoded on the device, text made on the host; the reference's lines (its threads
+    interleave the files, so the reference side is compared sorted; ours is ascending in meryl's code A < C < T < G)."""
+    import subprocess
+    db = oracle_db(tmp, "a", synth.reads_fastq_bytes(n, max(200, n // 15), 150, 0.004, k), k)
+    ours = subprocess.run([mb.CLI_PATH, "print", db], capture_output=True, text=True, env=env)
+    ref = subprocess.run([util.REF_BIN, "print", db], capture_output=True, text=True)
+    assert ours.returncode == 0 and ref.returncode == 0, ours.stderr[-500:]
+    mine = ours.stdout.splitlines()
+    code = str.maketrans("ACTG", "0123")
+    assert mine and sorted(mine, key=lambda l: l.split("\t")[0].translate(code)) == mine
+    assert sorted(mine) == sorted(ref.stdout.splitlines())
