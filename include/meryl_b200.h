@@ -270,6 +270,15 @@ int mb_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const uin
 typedef int (*mb_kmer_callback)(void *arg, uint32_t k, const uint64_t *kmerLo, const uint64_t *kmerHi, const uint32_t *values, uint64_t n);
 int mb_for_each_kmer(const char *dbDir, mb_kmer_callback cb, void *arg, int32_t device, uint64_t workspaceBytes);
 
+/*  meryl-lookup's per-sequence numbers (src/meryl-lookup/existence.C:59-86 processSequence; include-exclude.C:62-97): sequence i is
+ *  bases[seqStart[i] .. seqStart[i+1]) (seqStart[0] = 0, nSeqs + 1 entries; letters as in the file, any case; a k-mer never spans
+ *  two sequences).  nTotal[i] = its k-mers (k consecutive ACGT letters); nFound[i] = those whose forward or reverse-complement form
+ *  is in the database with a value in [minValue, maxValue] (merylExactLookup::value > 0 after load(minV, maxV)); the k-mers that start
+ *  in the first skipFirst positions of a sequence are not looked up (-10x).  *nDbKmers (may be NULL) = merylExactLookup::nKmers.  */
+int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
+                 uint64_t nSeqs, uint32_t skipFirst, uint64_t *nTotal, uint64_t *nFound, uint64_t *nDbKmers,
+                 int32_t device, uint64_t workspaceBytes);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

@@ -390,3 +390,21 @@ def all_kmers(db, device: int = -1, workspace_bytes: int = 0):
     _check(L.mb_for_each_kmer(os.fsencode(os.fspath(db)), CB(piece), None, device, workspace_bytes))
     cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
     return cat(los, np.uint64), (cat(his, np.uint64) if his else None), cat(vals, np.uint32)
+
+
+def existence(db, sequences, min_value: int = 0, max_value: int = 0xffffffff, skip_first: int = 0, device: int = -1, workspace_bytes: int = 0):
+    """meryl-lookup -existence for a list of sequences (bytes): (nTotal[], nFound[], nDbKmers) (mb_existence)."""
+    import numpy as np
+    starts = np.zeros(len(sequences) + 1, dtype=np.uint64)
+    if sequences:
+        starts[1:] = np.cumsum([len(x) for x in sequences], dtype=np.uint64)
+    blob = b"".join(sequences)
+    tot = np.zeros(len(sequences), dtype=np.uint64)
+    fnd = np.zeros(len(sequences), dtype=np.uint64)
+    ndb = ctypes.c_uint64(0)
+    L = lib()
+    L.mb_existence.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint64,
+                               ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32, ctypes.c_uint64]
+    _check(L.mb_existence(os.fsencode(os.fspath(db)), min_value, max_value, blob, starts.ctypes.data, len(sequences), skip_first,
+                          tot.ctypes.data, fnd.ctypes.data, ctypes.byref(ndb), device, workspace_bytes))
+    return tot, fnd, ndb.value

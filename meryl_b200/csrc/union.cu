@@ -329,6 +329,109 @@ lookup_kernel(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__res
   out[i] = v;
 }
 
+//  ---- K10: existence of a sequence's k-mers ---------------------------------------------------------------------
+//  meryl-lookup -existence / -include / -exclude (src/meryl-lookup/existence.C:59-86, include-exclude.C:62-97): for every
+//  position of every sequence the k-mer that starts there (kmerIterator: k consecutive ACGTacgt letters, code (c >> 1) & 3,
+//  first base in the top bits; kmers-iterator.H:63-103) counts as found when the table holds its forward or its
+//  reverse-complement form with a value in [minValue, maxValue].  One thread per position: the sequence it lies in is a
+//  binary search in seqStart, both forms are built from the k letters, the smaller one is searched first (K9's search).
+//  flag[p]: bit 0 = a k-mer starts at p, bit 1 = found (in this or an earlier group of files), bit 2 = outside the
+//  positions that count for `found` (skipFirst: the 10x barcode rule, include-exclude.C:70).
+template <int KW>
+__device__ __forceinline__ bool list_holds(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__restrict__ vals,
+                                           const u64 *__restrict__ fileStart, u32 fileLo, u32 fileHi, u32 k,
+                                           u64 qlo, u64 qhi, u32 minValue, u32 maxValue) {
+  typename KeyT<KW>::type q;
+  u32 file;
+  make_query(q, file, qlo, qhi, k);
+  if (file < fileLo || file >= fileHi) return false;
+  u64 lo = fileStart[file], hi = fileStart[file + 1];
+  const u64 end = hi;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if (key_less(keys[mid], q)) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= end || !key_eq(keys[lo], q)) return false;
+  const u32 v = vals[lo];
+  return v > 0 && v >= minValue && v <= maxValue;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256)
+existence_kernel(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__restrict__ vals, const u64 *__restrict__ fileStart /* [65] */,
+                 u32 fileLo, u32 fileHi, u32 k, const unsigned char *__restrict__ bases, u64 nBases,
+                 const u64 *__restrict__ seqStart, u64 nSeqs, u32 skipFirst, u32 minValue, u32 maxValue, unsigned char *__restrict__ flag) {
+  const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nBases) return;
+  unsigned char fl = flag[p];
+  if (fl & 2) return;                                       //  found in an earlier group
+  u64 a = 0, b = nSeqs;                                     //  last sequence that starts at or before p
+  while (b - a > 1) { const u64 m = (a + b) >> 1; if (seqStart[m] <= p) a = m; else b = m; }
+  if (p + k > seqStart[a + 1]) return;
+  u64 flo = 0, fhi = 0, rlo = 0, rhi = 0;                   //  forward and reverse-complement k-mer, 2k bits each
+  bool ok = true;
+  for (u32 i = 0; i < k; i++) {
+    const unsigned char c = bases[p + i];
+    const unsigned char up = c & 0xdf;
+    ok = ok && (up == 'A' || up == 'C' || up == 'G' || up == 'T');
+    const u64 code = (c >> 1) & 3;
+    fhi = (fhi << 2) | (flo >> 62);  flo = (flo << 2) | code;                //  kmers-tiny.H:86 (addR)
+    rlo = (rlo >> 2) | (rhi << 62);  rhi >>= 2;                              //  kmers-tiny.H:87 (addL): complement = code ^ 2
+    const u32 sh = 2 * k - 2;
+    if (sh >= 64) rhi |= (code ^ 2) << (sh - 64); else rlo |= (code ^ 2) << sh;
+  }
+  if (!ok) return;
+  if (KW == 1) { fhi = 0; rhi = 0; }
+  else if (2 * k < 128) { fhi &= (~0ull) >> (128 - 2 * k); }
+  if (KW == 1 && 2 * k < 64) flo &= (~0ull) >> (64 - 2 * k);
+  fl |= 1;
+  if (p - seqStart[a] < skipFirst) fl |= 4;
+  else {
+    const bool fFirst = fhi < rhi || (fhi == rhi && flo <= rlo);
+    const u64 alo = fFirst ? flo : rlo, ahi = fFirst ? fhi : rhi, blo = fFirst ? rlo : flo, bhi = fFirst ? rhi : fhi;
+    bool found = list_holds<KW>(keys, vals, fileStart, fileLo, fileHi, k, alo, ahi, minValue, maxValue);
+    if (!found && !(alo == blo && ahi == bhi))
+      found = list_holds<KW>(keys, vals, fileStart, fileLo, fileHi, k, blo, bhi, minValue, maxValue);
+    if (found) fl |= 2;
+  }
+  flag[p] = fl;
+}
+
+//  Per-sequence sums of the flags: a warp whose 32 positions lie in one sequence adds once (ballot + popc), else per lane.
+__global__ void __launch_bounds__(256)
+existence_sum_kernel(const unsigned char *__restrict__ flag, u64 nBases, const u64 *__restrict__ seqStart, u64 nSeqs,
+                     u64 *__restrict__ nTotal, u64 *__restrict__ nFound) {
+  const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 lane = threadIdx.x & 31;
+  const unsigned char fl = p < nBases ? flag[p] : 0;
+  u64 a = 0, b = nSeqs;
+  if (p < nBases) while (b - a > 1) { const u64 m = (a + b) >> 1; if (seqStart[m] <= p) a = m; else b = m; }
+  const u64 a0 = __shfl_sync(0xffffffffu, a, 0);
+  const bool same = __all_sync(0xffffffffu, p >= nBases || a == a0);
+  const u32 tot = __ballot_sync(0xffffffffu, (fl & 1) != 0), fnd = __ballot_sync(0xffffffffu, (fl & 2) != 0);
+  if (same) {
+    if (lane == 0) {
+      if (tot) atomicAdd((unsigned long long *)&nTotal[a0], (unsigned long long)__popc(tot));
+      if (fnd) atomicAdd((unsigned long long *)&nFound[a0], (unsigned long long)__popc(fnd));
+    }
+  } else {
+    if (fl & 1) atomicAdd((unsigned long long *)&nTotal[a], 1ull);
+    if (fl & 2) atomicAdd((unsigned long long *)&nFound[a], 1ull);
+  }
+}
+
+//  merylExactLookup::nKmers (kmers-lookup.H:136): the k-mers of the database whose value lies in [minValue, maxValue].
+__global__ void __launch_bounds__(256)
+count_in_range_kernel(const u32 *__restrict__ vals, u64 n, u32 minValue, u32 maxValue, u64 *__restrict__ out) {
+  u64 mine = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u32 v = vals[i];
+    mine += (v >= minValue && v <= maxValue) ? 1 : 0;
+  }
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd((unsigned long long *)out, (unsigned long long)mine);
+}
+
 const int MG_THREADS = 256;
 const int MG_ITEMS   = 8;
 const int MG_TILE    = MG_THREADS * MG_ITEMS;
@@ -982,6 +1085,75 @@ extern "C" int mb_for_each_kmer(const char *dbDir, mb_kmer_callback cb, void *ar
       return MB_OK;
     },
     [&](cudaStream_t) -> int { return MB_OK; });
+}
+
+//  meryl-lookup's per-sequence numbers (existence.C:59-86): nTotal[i] = the k-mers of sequence i (bases[seqStart[i] ..
+//  seqStart[i+1])), nFound[i] = those whose forward or reverse-complement form is in the database with a value in
+//  [minValue, maxValue]; *nDbKmers = the database's k-mers in that range (merylExactLookup::nKmers).  The first skipFirst
+//  k-mer positions of every sequence do not count as found (-10x, include-exclude.C:70).  Kernel K10 above, group of
+//  files by group of files.
+extern "C" int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
+                            uint64_t nSeqs, uint32_t skipFirst, uint64_t *nTotal, uint64_t *nFound, uint64_t *nDbKmers,
+                            int32_t device, uint64_t workspaceBytes) {
+  mb_clear_error();
+  if (!dbDir || (nSeqs && (!seqStart || !nTotal || !nFound))) return mb_fail(MB_EINVAL, "mb_existence: NULL argument");
+  const u64 nBases = nSeqs ? seqStart[nSeqs] : 0;
+  if (nBases && !bases) return mb_fail(MB_EINVAL, "mb_existence: NULL argument");
+  for (u64 i = 0; i < nSeqs; i++) if (seqStart[i] > seqStart[i + 1]) return mb_fail(MB_EINVAL, "mb_existence: seqStart is not ascending");
+  if (nSeqs && seqStart[0] != 0) return mb_fail(MB_EINVAL, "mb_existence: seqStart[0] must be 0");
+  unsigned char *dBases = nullptr, *dFlag = nullptr;
+  u64 *dSeqStart = nullptr, *dTot = nullptr, *dFnd = nullptr, *dDbN = nullptr;
+  u32 kDb = 0;
+  bool ranGroup = false;
+  return decodeDbInGroups(dbDir, device, workspaceBytes, (size_t)nBases * 2 + (size_t)nSeqs * 24 + 8192,
+    [&](const InputDb &db, Carve &top, cudaStream_t s) -> int {
+      kDb = db.k;
+      dDbN = (u64 *)top.take(8);
+      if (!dDbN) return mb_fail(MB_ENOMEM, "device arena too small");
+      MB_CUDA(cudaMemsetAsync(dDbN, 0, 8, s));
+      if (!nSeqs) return MB_OK;
+      dBases    = (unsigned char *)top.take((size_t)nBases + 16);
+      dFlag     = (unsigned char *)top.take((size_t)nBases + 16);
+      dSeqStart = (u64 *)top.take((size_t)(nSeqs + 1) * 8);
+      dTot      = (u64 *)top.take((size_t)nSeqs * 8);
+      dFnd      = (u64 *)top.take((size_t)nSeqs * 8);
+      if (!dBases || !dFlag || !dSeqStart || !dTot || !dFnd)
+        return mb_fail(MB_ENOMEM, "the %llu bases of %llu sequences do not fit the device arena", (unsigned long long)nBases, (unsigned long long)nSeqs);
+      if (nBases) MB_CUDA(cudaMemcpyAsync(dBases, bases, (size_t)nBases, cudaMemcpyHostToDevice, s));
+      MB_CUDA(cudaMemcpyAsync(dSeqStart, seqStart, (size_t)(nSeqs + 1) * 8, cudaMemcpyHostToDevice, s));
+      MB_CUDA(cudaMemsetAsync(dFlag, 0, (size_t)nBases + 16, s));
+      MB_CUDA(cudaMemsetAsync(dTot, 0, (size_t)nSeqs * 8, s));
+      MB_CUDA(cudaMemsetAsync(dFnd, 0, (size_t)nSeqs * 8, s));
+      return MB_OK;
+    },
+    [&](const InputDb &db, const DecodedGroup &G, cudaStream_t s) -> int {
+      count_in_range_kernel<<<(unsigned)std::min<u64>((G.nKmers + 255) / 256, 148 * 8), 256, 0, s>>>(G.dVal, G.nKmers, minValue, maxValue, dDbN);
+      MB_CUDA(cudaGetLastError());
+      if (!nBases) return MB_OK;
+      ranGroup = true;
+      const unsigned grid = (unsigned)((nBases + 255) / 256);
+      if (db.k <= 32) existence_kernel<1><<<grid, 256, 0, s>>>((const u64 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
+      else            existence_kernel<2><<<grid, 256, 0, s>>>((const ulonglong2 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
+      MB_CUDA(cudaGetLastError());
+      return MB_OK;
+    },
+    [&](cudaStream_t s) -> int {
+      if (nDbKmers) MB_CUDA(cudaMemcpyAsync(nDbKmers, dDbN, 8, cudaMemcpyDeviceToHost, s));
+      if (!nSeqs) return MB_OK;
+      if (nBases) {
+        if (!ranGroup) {                                    //  a database without k-mers: the sequences' own k-mers still count
+          const unsigned grid = (unsigned)((nBases + 255) / 256);
+          if (kDb <= 32) existence_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, 0, 0, kDb, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
+          else           existence_kernel<2><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, 0, 0, kDb, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
+          MB_CUDA(cudaGetLastError());
+        }
+        existence_sum_kernel<<<(unsigned)((nBases + 255) / 256), 256, 0, s>>>(dFlag, nBases, dSeqStart, nSeqs, dTot, dFnd);
+        MB_CUDA(cudaGetLastError());
+      }
+      MB_CUDA(cudaMemcpyAsync(nTotal, dTot, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+      MB_CUDA(cudaMemcpyAsync(nFound, dFnd, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+      return MB_OK;
+    });
 }
 
 //  `count-suffix=ACG` (merylCommandBuilder.C:271-274; merylOp-countSimple.C:50-93, :172-199): only the k-mers whose counted

@@ -23,7 +23,7 @@ if [ ! -d "$SRC/meryl" ]; then
   echo "build_ref: $SRC not present; keeping prebuilt $OUT/meryl" >&2
   exit 0
 fi
-if [ -x "$OUT/meryl" ] && [ "$1" != "-f" ]; then
+if [ -x "$OUT/meryl" ] && [ -x "$OUT/meryl-lookup" ] && [ "$1" != "-f" ]; then
   exit 0
 fi
 
@@ -32,26 +32,35 @@ mkdir -p "$OUT/obj" "$OUT/gen"
 
 CXX="${REF_CXX:-/usr/bin/g++}"   #  not $CXX: this image exports a wrapper without libgomp
 FLAGS="-std=c++2a -fopenmp -pthread -O3 -DNOBACKTRACE -mxsave -w \
-  -I$OUT/gen -I$SRC -I$SRC/meryl -I$SRC/utility/src -I$SRC/utility/src/sequence"
+  -I$OUT/gen -I$SRC -I$SRC/meryl -I$SRC/meryl-lookup -I$SRC/utility/src -I$SRC/utility/src/sequence"
 
 FILES=""
 for d in bits datastructures files kmers-v1 math system; do
   FILES="$FILES $(ls $SRC/utility/src/$d/*.C)"
 done
 FILES="$FILES $SRC/utility/src/sequence/dnaSeq-v1.C $SRC/utility/src/sequence/bufSeqFile-v1.C $SRC/utility/src/sequence/sequence-v1.C"
-FILES="$FILES $(ls $SRC/meryl/*.C) $HERE/hts_stub.C"
+FILES="$FILES $HERE/hts_stub.C"
+NUTIL=$(echo $FILES | wc -w)
+#  the two programs: meryl (count / print / statistics / set operations) and meryl-lookup (existence / include / exclude)
+FILES="$FILES $(ls $SRC/meryl/*.C)"
+LOOKUP="$SRC/meryl-lookup/meryl-lookup.C $SRC/meryl-lookup/meryl-lookup-help.C $SRC/meryl-lookup/dump.C $SRC/meryl-lookup/existence.C $SRC/meryl-lookup/include-exclude.C"
+FILES="$FILES $LOOKUP"
 
 pids=()
 objs=""
+lobjs=""
 n=0
 for f in $FILES; do
   o="$OUT/obj/$(echo "$f" | sed -e 's#/#_#g' -e 's#\.C$#.o#')"
-  objs="$objs $o"
+  if [ $n -lt $NUTIL ]; then objs="$objs $o"; lobjs="$lobjs $o";
+  elif echo "$f" | grep -q "/meryl-lookup/"; then lobjs="$lobjs $o";
+  else objs="$objs $o"; fi
   $CXX $FLAGS -c "$f" -o "$o" &
   n=$((n+1))
   if [ $((n % $(nproc))) -eq 0 ]; then wait; fi
 done
 wait
 $CXX -fopenmp -pthread -O3 -o "$OUT/meryl" $objs -lm
+$CXX -fopenmp -pthread -O3 -o "$OUT/meryl-lookup" $lobjs -lm
 rm -rf "$OUT/obj"
-echo "build_ref: built $OUT/meryl" >&2
+echo "build_ref: built $OUT/meryl and $OUT/meryl-lookup" >&2

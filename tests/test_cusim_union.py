@@ -106,3 +106,9 @@ def test_sim_new_entry_points_refuse_bad_arguments(tmp_path):
 def test_sim_cli_print_vs_reference(tmp_path, k):
     """The command line tool with the emulated library in front of the CUDA one (LD_PRELOAD: same C ABI)."""
     uc.case_cli_print(str(tmp_path), k, env=dict(os.environ, LD_PRELOAD=SIM_LIB))
+
+
+@pytest.mark.skipif(not util.have_ref_lookup(), reason="reference meryl-lookup not built")
+@pytest.mark.parametrize("k", [21, 40, 9])
+def test_sim_existence_vs_reference_lookup(tmp_path, monkeypatch, k):
+    uc.case_existence(str(tmp_path), k, monkeypatch=monkeypatch)

@@ -226,3 +226,77 @@ def case_cli_print(tmp, k, n=3_000, env=None):
     code = str.maketrans("ACTG", "0123")
     assert mine and sorted(mine, key=lambda l: l.split("\t")[0].translate(code)) == mine
     assert sorted(mine) == sorted(ref.stdout.splitlines())
+
+
+def _existence_queries(k, n, seed):
+    """Sequences for meryl-lookup: reads of the database's genome (found), of another genome (not found), lower case, Ns,
+    shorter than k, exactly k, empty; names with flags after a blank or a tab."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    seqs = []
+    fq = synth.reads_fastq_bytes(n, 60, 150, 0.01, 40 + k).split(b"\n")            # same genome seed as the database below
+    seqs += [fq[i] for i in range(1, len(fq) - 1, 4)]
+    other = synth.reads_fastq_bytes(n, 20, 150, 0.0, 977).split(b"\n")
+    seqs += [other[i] for i in range(1, len(other) - 1, 4)]
+    seqs.append(seqs[0].lower())
+    seqs.append(seqs[1][:70] + b"N" + seqs[1][70:100] + b"nn" + seqs[1][100:])
+    seqs.append(seqs[2][:k - 1])
+    seqs.append(seqs[3][:k])
+    seqs.append(b"")
+    seqs.append(seqs[4][:k + 5] + b"R" + seqs[5][:k] + b"-" + seqs[6])
+    long_one = synth.fasta_bytes(1, 3_000, 40 + k).split(b"\n", 1)[1].replace(b"\n", b"")
+    seqs.append(long_one + seqs[7] + long_one[::-1])
+    seqs.append(b"")
+    names = []
+    for i in range(len(seqs)):
+        names.append(b"q%d" % i + (b"" if i % 3 == 0 else b" len=%d x" % len(seqs[i]) if i % 3 == 1 else b"\tflag"))
+    return names, seqs
+
+
+def _ref_existence(tmp, fa, dbs, extra=()):
+    import subprocess
+    out = os.path.join(tmp, "ref_existence.txt")
+    p = subprocess.run([util.REF_LOOKUP_BIN, "-existence", "-sequence", fa, "-mers", *dbs, "-output", out, "-threads", "4", *extra],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-500:]
+    with open(out) as fh:
+        return [line.rstrip("\n").split("\t") for line in fh]
+
+
+def case_existence(tmp, k, n=6_000, monkeypatch=None):
+    """mb_existence (meryl-lookup -existence, existence.C:59-86): per sequence the number of k-mers and the number found in the
+    database in either orientation, against the reference's meryl-lookup binary -- a canonical count db, a forward count db
+    (only one strand's form is stored: the reverse-complement lookup matters), a union's output; a value window (-min/-max);
+    the files decoded in several groups; an empty database."""
+    import numpy as np
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(n, n // 15, 150, 0.004, 40 + k), k)
+    f = oracle_db(tmp, "f", synth.reads_fastq_bytes(n, n // 30, 150, 0.004, 40 + k), k, op="count-forward")
+    e = oracle_db(tmp, "e", b">none\nACGT\n", k)
+    names, seqs = _existence_queries(k, n, k)
+    fa = os.path.join(tmp, "queries.fa")
+    with open(fa, "wb") as fh:
+        for i, (nm, sq) in enumerate(zip(names, seqs)):
+            if i % 2 == 0:
+                fh.write(b">" + nm + b"\n" + b"\n".join(sq[j:j + 60] for j in range(0, len(sq), 60)) + b"\n")
+            else:
+                fh.write(b">" + nm + b"\r\n" + sq + b"\r\n")
+    for dbs, ws, extra, window in (([a, f], 0, (), (0, 0xffffffff)), ([a], 40 << 20, ("-min", "2", "-max", "3"), (2, 3)), ([e], 0, (), (0, 0xffffffff))):
+        if ws and monkeypatch is not None:
+            monkeypatch.setenv("MB_UNION_MAX_FILES", "7")
+        ref = _ref_existence(tmp, fa, dbs, extra)
+        assert [r[0].encode() for r in ref] == [nm.split()[0] for nm in names]
+        for d, db in enumerate(dbs):
+            tot, fnd, ndb = mb.existence(db, seqs, min_value=window[0], max_value=window[1], workspace_bytes=ws)
+            assert [int(x) for x in tot] == [int(r[1]) for r in ref]
+            assert [int(x) for x in fnd] == [int(r[3 + 2 * d]) for r in ref]
+            assert ndb == int(ref[0][2 + 2 * d])
+        if dbs == [a, f]:
+            assert sum(int(r[3]) for r in ref) > 0 and sum(int(r[5]) for r in ref) > 0
+    # -10x: the k-mers that start in the first 23 positions are not looked up
+    tot0, fnd0, _ = mb.existence(a, seqs)
+    tot1, fnd1, _ = mb.existence(a, seqs, skip_first=23)
+    tot2, fnd2, _ = mb.existence(a, [s[23:] if len(s) >= 23 + k else b"" for s in seqs])
+    assert np.array_equal(tot0, tot1) and np.array_equal(fnd1, fnd2) and int(fnd1.sum()) < int(fnd0.sum())
+    # no sequences at all: only the database's size comes back
+    tot, fnd, ndb = mb.existence(a, [])
+    assert tot.size == 0 and ndb > 0

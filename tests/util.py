@@ -11,6 +11,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "meryl")
+REF_LOOKUP_BIN = os.path.join(ORACLE_DIR, "_ref", "meryl-lookup")
 ORACLE_BIN = os.path.join(ORACLE_DIR, "meryl_oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 
@@ -21,6 +22,10 @@ DB_FILES = (["merylIndex"]
 
 def have_ref() -> bool:
     return os.access(REF_BIN, os.X_OK)
+
+
+def have_ref_lookup() -> bool:
+    return os.access(REF_LOOKUP_BIN, os.X_OK)
 
 
 def run_ref(args: list[str], cwd: str | None = None, timeout: int = 600) -> str:
