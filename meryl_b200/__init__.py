@@ -19,6 +19,7 @@ from dataclasses import dataclass
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmeryl_b200.so")
 CLI_PATH = os.path.join(_HERE, "meryl-b200")
+LOOKUP_CLI_PATH = os.path.join(_HERE, "meryl-lookup-b200")
 
 MODE_CANONICAL, MODE_FORWARD, MODE_REVERSE = 0, 1, 2
 _MODES = {"count": MODE_CANONICAL, "count-forward": MODE_FORWARD, "count-reverse": MODE_REVERSE}

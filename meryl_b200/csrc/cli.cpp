@@ -262,7 +262,12 @@ static void removeTempDb(const std::string &dir) {
   rmdir(dir.c_str());
 }
 
+int mbLookupMain(int argc, char **argv);                 //  lookup_cli.cpp: meryl-lookup's -existence / -include / -exclude
+
 int main(int argc, char **argv) {
+  const char *self = strrchr(argv[0], '/');
+  self = self ? self + 1 : argv[0];
+  if (!strncmp(self, "meryl-lookup", 12) || (argc > 1 && !strcmp(argv[1], "lookup"))) return mbLookupMain(argc, argv);
   bool tree = false;
   for (int i = 1; i < argc; i++) if (!strcmp(argv[i], "[")) tree = true;
   if (!tree) return flatMain(argc, argv);

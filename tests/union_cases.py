@@ -300,3 +300,68 @@ def case_existence(tmp, k, n=6_000, monkeypatch=None):
     # no sequences at all: only the database's size comes back
     tot, fnd, ndb = mb.existence(a, [])
     assert tot.size == 0 and ndb > 0
+
+
+def case_cli_lookup(tmp, k, n=6_000, env=None):
+    """`meryl-lookup-b200` against the reference's meryl-lookup, file for file: -existence on a FASTA file with two databases;
+    -include / -exclude on FASTQ reads (single, paired, -10x, a value window) and on FASTA; usage errors."""
+    import subprocess
+    a = oracle_db(tmp, "a", synth.reads_fastq_bytes(n, n // 15, 150, 0.004, 40 + k), k)
+    f = oracle_db(tmp, "f", synth.reads_fastq_bytes(n, n // 30, 150, 0.004, 40 + k), k, op="count-forward")
+    names, seqs = _existence_queries(k, n, k)
+    fa = os.path.join(tmp, "queries.fa")
+    with open(fa, "wb") as fh:
+        for i, (nm, sq) in enumerate(zip(names, seqs)):
+            if sq or i % 2:                                  # (the reference's FASTA writer divides by the length: no empty sequences here)
+                fh.write(b">" + nm + b"\n" + b"\n".join(sq[j:j + 60] for j in range(0, len(sq), 60)) + b"\n")
+    fa_all = os.path.join(tmp, "queries_all.fa")
+    with open(fa_all, "wb") as fh:
+        for nm, sq in zip(names, seqs):
+            fh.write(b">" + nm + b"\n" + sq + b"\n")
+    # reads: half from the database's genome, half from another; as FASTQ (qualities starting above '!' and, for a few, with '!')
+    r1, r2 = os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")
+    own = synth.reads_fastq_bytes(n, 40, 100, 0.02, 40 + k).split(b"\n")
+    oth = synth.reads_fastq_bytes(n, 40, 100, 0.0, 4242).split(b"\n")
+    with open(r1, "wb") as f1, open(r2, "wb") as f2:
+        for i in range(40):
+            s1 = own[4 * i + 1] if i % 2 else oth[4 * i + 1]
+            s2 = oth[4 * i + 1][::-1] if i % 3 else own[4 * i + 1][:60]
+            q1 = (b"!" if i % 7 == 0 else b"I") + b"F" * (len(s1) - 1)
+            f1.write(b"@pair%d/1 extra words\n" % i + s1 + b"\n+\n" + q1 + b"\n")
+            f2.write(b"@pair%d/2\n" % i + s2 + b"\n+pair%d/2\n" % i + b"5" * len(s2) + b"\n")
+
+    def both(words, outs):
+        got = []
+        for exe, tag in ((util.REF_LOOKUP_BIN, "ref"), (mb.LOOKUP_CLI_PATH, "dev")):
+            names_ = [os.path.join(tmp, "%s_%s" % (tag, o)) for o in outs]
+            p = subprocess.run([exe] + words + ["-output"] + names_, capture_output=True, text=True, env=env if tag == "dev" else None)
+            assert p.returncode == 0, (tag, p.stderr[-500:])
+            got.append([open(x, "rb").read() for x in names_])
+        assert got[0] == got[1], words
+        return got[1]
+
+    out = both(["-existence", "-sequence", fa_all, "-mers", a, f], ["ex.txt"])
+    assert out[0].count(b"\n") == len(seqs)
+    both(["-existence", "-sequence", r1, "-mers", f, "-min", "2"], ["ex2.txt"])
+    inc = both(["-include", "-sequence", r1, "-mers", a], ["inc.fq"])
+    exc = both(["-exclude", "-sequence", r1, "-mers", a], ["exc.fq"])
+    assert inc[0].count(b"nKmers=") + exc[0].count(b"nKmers=") == 40 and inc[0].startswith(b"@pair1/1 nKmers=") and b">pair" in inc[0] + exc[0]
+    both(["-include", "-sequence", r1, r2, "-mers", a], ["inc1.fq", "inc2.fq"])
+    both(["-exclude", "-10x", "-sequence", r1, r2, "-mers", a, "-min", "2", "-max", "50"], ["exc1.fq", "exc2.fq"])
+    both(["-include", "-sequence", fa, "-mers", f], ["inc.fa"])
+    pr = subprocess.run([util.REF_LOOKUP_BIN, "-existence", "-sequence", fa, "-mers", a], capture_output=True)       # no -output: stdout
+    pd = subprocess.run([mb.LOOKUP_CLI_PATH, "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)
+    assert pr.returncode == pd.returncode == 0 and pr.stdout == pd.stdout and pd.stdout
+    pd = subprocess.run([mb.CLI_PATH, "lookup", "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)  # the same through `meryl-b200 lookup`
+    assert pd.returncode == 0 and pr.stdout == pd.stdout
+    both(["-exclude", "-sequence", fa, "-mers", f, "-threads", "2", "-memory", "4"], ["exc.fa"])
+    # usage errors (meryl-lookup.C:291-368): same sentences, exit code 1
+    for words in (["-sequence", fa, "-mers", a, "-output", "x"], ["-existence", "-mers", a, "-output", "x"],
+                  ["-existence", "-sequence", fa, "-output", "x"],
+                  ["-include", "-sequence", fa, "-mers", a, f, "-output", "x"], ["-existence", "-sequence", fa, fa, "-mers", a, "-output", "x"],
+                  ["-include", "-sequence", r1, r2, "-mers", a, "-output", "x"], ["-existence", "-frobnicate"]):
+        pr = subprocess.run([util.REF_LOOKUP_BIN] + words, capture_output=True, text=True, cwd=tmp)
+        pd = subprocess.run([mb.LOOKUP_CLI_PATH] + words, capture_output=True, text=True, cwd=tmp, env=env)
+        assert pr.returncode == pd.returncode == 1
+        sentences = [l for l in pr.stderr.splitlines() if l.startswith(("No ", "Only ", "Unknown ", "Labels "))]
+        assert sentences and all(l in pd.stderr for l in sentences), (words, pr.stderr[-300:], pd.stderr)
