@@ -79,7 +79,9 @@ void *dev_alloc(size_t bytes) {
   unsigned char *p = (unsigned char *)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
   if (p == MAP_FAILED) return nullptr;
   *(size_t *)p = total;
-  if (bytes <= ((size_t)64 << 20)) memset(p + 4096, 0xa5, bytes);
+  //  fresh device memory is not zero: poison it (large arenas only when CUSIM_POISON_ALL is set -- touching gigabytes is slow)
+  static const bool poisonAll = getenv("CUSIM_POISON_ALL") != nullptr;
+  if (poisonAll || bytes <= ((size_t)64 << 20)) memset(p + 4096, 0xa5, bytes);
   return p + 4096;
 }
 void dev_free(void *q) {
