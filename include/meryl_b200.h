@@ -279,6 +279,14 @@ int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxValue, const 
                  uint64_t nSeqs, uint32_t skipFirst, uint64_t *nTotal, uint64_t *nFound, uint64_t *nDbKmers,
                  int32_t device, uint64_t workspaceBytes);
 
+/*  The per-position form behind meryl-lookup -bed / -wig-count / -wig-depth (src/meryl-lookup/dump.C:86-157 processSequence): for
+ *  position p of the letters (same layout as mb_existence), flags[p] bit 0 = a k-mer starts at p, bit 1 = the database holds its
+ *  forward or reverse-complement form (exists(c) || exists(n)); values[p] (may be NULL) = value(fmer) + value(rmer), counted once
+ *  when the two forms are equal (dump.C:150-153).  As in the reference, value() is what the table stores: the k-mer's value less
+ *  (minValue - 1) when minValue > 1 (kmers-exact.C:57-62; mb_lookup, in contrast, returns the k-mer's own value).  */
+int mb_position_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
+                       uint64_t nSeqs, uint8_t *flags, uint32_t *values, int32_t device, uint64_t workspaceBytes);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

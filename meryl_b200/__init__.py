@@ -409,3 +409,21 @@ def existence(db, sequences, min_value: int = 0, max_value: int = 0xffffffff, sk
     _check(L.mb_existence(os.fsencode(os.fspath(db)), min_value, max_value, blob, starts.ctypes.data, len(sequences), skip_first,
                           tot.ctypes.data, fnd.ctypes.data, ctypes.byref(ndb), device, workspace_bytes))
     return tot, fnd, ndb.value
+
+
+def position_lookup(db, sequences, min_value: int = 0, max_value: int = 0xffffffff, values: bool = True, device: int = -1, workspace_bytes: int = 0):
+    """Per position of the concatenated sequences: flags (bit 0 a k-mer starts here, bit 1 found) and value(fmer) + value(rmer)
+    (mb_position_lookup; meryl-lookup -bed / -wig-count / -wig-depth)."""
+    import numpy as np
+    starts = np.zeros(len(sequences) + 1, dtype=np.uint64)
+    if sequences:
+        starts[1:] = np.cumsum([len(x) for x in sequences], dtype=np.uint64)
+    blob = b"".join(sequences)
+    flags = np.zeros(len(blob), dtype=np.uint8)
+    vals = np.zeros(len(blob), dtype=np.uint32) if values else None
+    L = lib()
+    L.mb_position_lookup.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint64,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64]
+    _check(L.mb_position_lookup(os.fsencode(os.fspath(db)), min_value, max_value, blob, starts.ctypes.data, len(sequences),
+                                flags.ctypes.data, None if vals is None else vals.ctypes.data, device, workspace_bytes))
+    return flags, vals

@@ -8,8 +8,8 @@
 //      -exclude     "<ident> nKmers=<found>"; the ones with none (include-exclude.C:62-134); -10x: the k-mers starting in the
 //                   first 23 positions of the first file's reads are not looked up
 //  with the reference's options -min / -max (value window of the table), -threads / -loadthreads / -memory / -V (accepted;
-//  they size host resources of the reference that do not exist here).  The per-position reports (-bed, -wig-count,
-//  -wig-depth: dump.C) are not rebuilt.  Option handling and the usage errors follow meryl-lookup.C:155-368.
+//  they size host resources of the reference that do not exist here).  The per-position reports (-bed, -bed-runs, -wig-count,
+//  -wig-depth: dump.C) are written from mb_position_lookup's per-position flags and values.  Option handling and the usage errors follow meryl-lookup.C:155-368.
 //
 //  The sequences are read on the host the way the reference's loader reads them (bufSeqFile::loadSequence / loadFASTA /
 //  loadFASTQ, src/utility/src/sequence/bufSeqFile-v1.C:291-549; names: dnaSeq::findNameAndFlags, dnaSeq-v1.C:89-101); the
@@ -138,10 +138,10 @@ void writeRecord(FILE *o, const Sequences &S, size_t i, uint64_t nFound) {
   }
 }
 
-enum Report { NONE, EXISTENCE, INCLUDE, EXCLUDE, UNSUPPORTED };
+enum Report { NONE, EXISTENCE, INCLUDE, EXCLUDE, BED, WIGCOUNT, WIGDEPTH, UNSUPPORTED };
 
 const char *reportName(Report r) {                       //  toString(lookupOp), meryl-lookup.H:38-50
-  switch (r) { case EXISTENCE: return "-existence"; case INCLUDE: return "-include"; case EXCLUDE: return "-exclude"; default: return "(not supplied)"; }
+  switch (r) { case BED: return "-bed"; case WIGCOUNT: return "-wig-count"; case WIGDEPTH: return "-wig-depth"; case EXISTENCE: return "-existence"; case INCLUDE: return "-include"; case EXCLUDE: return "-exclude"; default: return "(not supplied)"; }
 }
 
 }  //  namespace
@@ -152,7 +152,7 @@ int mbLookupMain(int argc, char **argv) {
   std::vector<const char *> dbs, labels;
   uint32_t minV = 0, maxV = 0xffffffffu;
   Report report = NONE;
-  bool is10x = false;
+  bool is10x = false, bedRuns = false;
   std::vector<std::string> err;
   for (int a = 1; a < argc; a++) {
     const char *w = argv[a];
@@ -168,7 +168,11 @@ int mbLookupMain(int argc, char **argv) {
     else if (!strcmp(w, "-existence")) { report = EXISTENCE; }
     else if (!strcmp(w, "-include"))   { report = INCLUDE; }
     else if (!strcmp(w, "-exclude"))   { report = EXCLUDE; }
-    else if (!strcmp(w, "-bed") || !strcmp(w, "-bed-runs") || !strcmp(w, "-wig-count") || !strcmp(w, "-wig-depth") || !strcmp(w, "-estimate")) { report = UNSUPPORTED; unsupported = w; }
+    else if (!strcmp(w, "-bed"))       { report = BED; }
+    else if (!strcmp(w, "-bed-runs"))  { report = BED; bedRuns = true; }
+    else if (!strcmp(w, "-wig-count")) { report = WIGCOUNT; }
+    else if (!strcmp(w, "-wig-depth")) { report = WIGDEPTH; }
+    else if (!strcmp(w, "-estimate"))  { report = UNSUPPORTED; unsupported = w; }
     else if (!strcmp(w, "-10x"))       { is10x = true; }
     else if (!strcmp(w, "-V"))         { }
     else err.push_back(std::string("Unknown option '") + w + "'.\n");
@@ -176,7 +180,7 @@ int mbLookupMain(int argc, char **argv) {
   if (report == UNSUPPORTED) {
     const char *ref = getenv("MERYL_LOOKUP_REFERENCE");
     if (ref) { execv(ref, argv); perror("execv"); return 1; }
-    fprintf(stderr, "ERROR: report '%s' is not rebuilt here (-existence, -include and -exclude are); set MERYL_LOOKUP_REFERENCE=<path to\n", unsupported);
+    fprintf(stderr, "ERROR: '%s' (the memory estimate of the reference's host table) has no meaning here; set MERYL_LOOKUP_REFERENCE=<path to\n", unsupported);
     fprintf(stderr, "       meryl-lookup> to have such command lines passed to the reference binary.\n");
     return 1;
   }
@@ -186,7 +190,7 @@ int mbLookupMain(int argc, char **argv) {
     if (!seq1)        err.push_back("No input sequences (-sequence) supplied.\n");
     if (dbs.empty())  err.push_back("No meryl database (-mers) supplied.\n");
     if (!out1)        err.push_back("No output file (-output) supplied.\n");
-    if (report == EXISTENCE) {
+    if (report != INCLUDE && report != EXCLUDE) {
       if (seq2) err.push_back(std::string("Only one input sequence (-sequence) supported for ") + reportName(report) + ".\n");
       if (out2) err.push_back(std::string("Only one output file (-output) supported for ") + reportName(report) + ".\n");
     } else {
@@ -194,7 +198,7 @@ int mbLookupMain(int argc, char **argv) {
       if (!seq2 && out2) err.push_back("No second input file (-input) supplied for second output (-output) file.\n");
       if (dbs.size() > 1) err.push_back(std::string("Only one meryl database (-mers) supported for ") + reportName(report) + ".\n");
     }
-    if (!labels.empty()) err.push_back(std::string("Labels (-labels) not supported for ") + reportName(report) + ".\n");
+    if (!labels.empty() && report != BED) err.push_back(std::string("Labels (-labels) not supported for ") + reportName(report) + ".\n");
   }
   if (!err.empty()) {
     fprintf(stderr, "usage: %s <report-type> -sequence <input1.fasta> [<input2.fasta>] -mers <input1.meryl> [<input2.meryl> ...] -output <output1> [<output2>]\n", argv[0]);
@@ -218,7 +222,70 @@ int mbLookupMain(int argc, char **argv) {
   FILE *o1 = openOut(out1, piped1), *o2 = out2 ? openOut(out2, piped2) : nullptr;
   if (!o1 || (out2 && !o2)) { fprintf(stderr, "ERROR: cannot open the output.\n"); return 1; }
 
-  if (report == EXISTENCE) {
+  if (report == BED || report == WIGCOUNT || report == WIGDEPTH) {
+    //  dump.C:86-240 (what is kept per position) and :249-412 (what is written), sequence by sequence
+    const size_t n = S1.size(), nBases = S1.bases.size();
+    const size_t nDb = (report == WIGDEPTH) ? 1 : dbs.size();           //  (the depth report looks at the first database only)
+    const bool   perDb = (report == BED) && !labels.empty();            //  with labels a BED line says which database; without, one line per k-mer
+    uint32_t k = 0;
+    uint64_t hu = 0, hd = 0, ht = 0, hn = 0;
+    if (mb_db_histogram(dbs[0], &k, &hu, &hd, &ht, nullptr, nullptr, 0, &hn) != MB_OK) { fprintf(stderr, "ERROR: %s\n", mb_last_error()); return 1; }
+    std::vector<std::vector<uint8_t>> found(perDb ? nDb : 1, std::vector<uint8_t>(nBases, 0));
+    std::vector<uint8_t>  flags(nBases, 0), valid(nBases, 0);
+    std::vector<uint32_t> count(report == WIGCOUNT ? nBases : 0, 0), vals(report == WIGCOUNT ? nBases : 0, 0);
+    for (size_t d = 0; d < nDb; d++) {
+      if (mb_position_lookup(dbs[d], minV, maxV, S1.bases.data(), S1.seqStart.data(), n, flags.data(), report == WIGCOUNT ? vals.data() : nullptr, -1, 0) != MB_OK) {
+        fprintf(stderr, "ERROR: %s\n", mb_last_error());
+        return 1;
+      }
+      std::vector<uint8_t> &f = found[perDb ? d : 0];
+      for (size_t p = 0; p < nBases; p++) { f[p] |= (flags[p] >> 1) & 1; valid[p] |= flags[p] & 1; }
+      if (report == WIGCOUNT) for (size_t p = 0; p < nBases; p++) count[p] += vals[p];
+    }
+    char num[64];
+    for (size_t i = 0; i < n; i++) {
+      const size_t b = (size_t)S1.seqStart[i], len = (size_t)S1.seqStart[i + 1] - b;
+      const char *id = S1.ident[i].c_str();
+      if (report == BED) {
+        size_t maxP = 0;                                              //  one past the last k-mer found in any database
+        for (size_t t = 0; t < found.size(); t++) for (size_t p = len; p > maxP; p--) if (found[t][b + p - 1]) { maxP = p; break; }
+        if (!bedRuns) {
+          for (size_t p = 0; p < maxP; p++)
+            for (size_t d = 0; d < found.size(); d++) {
+              if (!found[d][b + p]) continue;
+              fprintf(o1, "%s\t%zu\t%zu", id, p, p + k);
+              if (d < labels.size()) fprintf(o1, "\t%s", labels[d]);
+              fputc('\n', o1);
+            }
+        } else {
+          std::vector<size_t> bgn(found.size(), (size_t)-1);
+          for (size_t p = 0; p <= maxP; p++)
+            for (size_t d = 0; d < found.size(); d++) {
+              const bool bit = p < maxP && found[d][b + p];
+              if (bit) { if (bgn[d] == (size_t)-1) bgn[d] = p; continue; }
+              if (bgn[d] == (size_t)-1) continue;
+              fprintf(o1, "%s\t%zu\t%zu", id, bgn[d], p + k);         //  (dump.C:344: the end is written as p + k)
+              bgn[d] = (size_t)-1;
+              if (d < labels.size()) fprintf(o1, "\t%s", labels[d]);
+              fputc('\n', o1);
+            }
+        }
+      } else {
+        fprintf(o1, "variableStep chrom=%s\n", id);
+        if (report == WIGCOUNT) {
+          for (size_t p = 0; p < len; p++) if (valid[b + p] && count[b + p]) fprintf(o1, "%zu\t%u\n", p + 1, count[b + p]);
+        } else {
+          //  depth of the found k-mers over every base: +1 where one starts, -1 k bases on, running sum (dump.C:219-238)
+          std::vector<int32_t> diff(len + k + 1, 0);
+          size_t maxP = 0;
+          for (size_t p = 0; p < len; p++) if (found[0][b + p]) { diff[p]++; diff[p + k]--; maxP = p + k; }
+          int32_t dsum = 0;
+          for (size_t p = 0; p < maxP; p++) { dsum += diff[p]; if (dsum) fprintf(o1, "%zu\t%d\n", p + 1, dsum); }
+        }
+      }
+    }
+    (void)num;
+  } else if (report == EXISTENCE) {
     const size_t n = S1.size();
     std::vector<std::vector<uint64_t>> found(dbs.size(), std::vector<uint64_t>(n, 0));
     std::vector<uint64_t> total(n, 0), dbKmers(dbs.size(), 0);

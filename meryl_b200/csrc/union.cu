@@ -338,33 +338,34 @@ lookup_kernel(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__res
 //  flag[p]: bit 0 = a k-mer starts at p, bit 1 = found (in this or an earlier group of files), bit 2 = outside the
 //  positions that count for `found` (skipFirst: the 10x barcode rule, include-exclude.C:70).
 template <int KW>
-__device__ __forceinline__ bool list_holds(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__restrict__ vals,
-                                           const u64 *__restrict__ fileStart, u32 fileLo, u32 fileHi, u32 k,
-                                           u64 qlo, u64 qhi, u32 minValue, u32 maxValue) {
+__device__ __forceinline__ u32 list_value(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__restrict__ vals,
+                                          const u64 *__restrict__ fileStart, u32 fileLo, u32 fileHi, u32 k,
+                                          u64 qlo, u64 qhi, u32 minValue, u32 maxValue) {
   typename KeyT<KW>::type q;
   u32 file;
   make_query(q, file, qlo, qhi, k);
-  if (file < fileLo || file >= fileHi) return false;
+  if (file < fileLo || file >= fileHi) return 0;
   u64 lo = fileStart[file], hi = fileStart[file + 1];
   const u64 end = hi;
   while (lo < hi) {
     const u64 mid = (lo + hi) >> 1;
     if (key_less(keys[mid], q)) lo = mid + 1; else hi = mid;
   }
-  if (lo >= end || !key_eq(keys[lo], q)) return false;
+  if (lo >= end || !key_eq(keys[lo], q)) return 0;
   const u32 v = vals[lo];
-  return v > 0 && v >= minValue && v <= maxValue;
+  return (v >= minValue && v <= maxValue) ? v : 0;
 }
 
 template <int KW>
 __global__ void __launch_bounds__(256)
 existence_kernel(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__restrict__ vals, const u64 *__restrict__ fileStart /* [65] */,
                  u32 fileLo, u32 fileHi, u32 k, const unsigned char *__restrict__ bases, u64 nBases,
-                 const u64 *__restrict__ seqStart, u64 nSeqs, u32 skipFirst, u32 minValue, u32 maxValue, unsigned char *__restrict__ flag) {
+                 const u64 *__restrict__ seqStart, u64 nSeqs, u32 skipFirst, u32 minValue, u32 maxValue, unsigned char *__restrict__ flag,
+                 u32 *__restrict__ values /* NULL, or per position: value(fmer) + value(rmer), once for a palindrome (dump.C:139-157) */) {
   const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nBases) return;
   unsigned char fl = flag[p];
-  if (fl & 2) return;                                       //  found in an earlier group
+  if ((fl & 2) && !values) return;                          //  found in an earlier group
   u64 a = 0, b = nSeqs;                                     //  last sequence that starts at or before p
   while (b - a > 1) { const u64 m = (a + b) >> 1; if (seqStart[m] <= p) a = m; else b = m; }
   if (p + k > seqStart[a + 1]) return;
@@ -389,10 +390,16 @@ existence_kernel(const typename KeyT<KW>::type *__restrict__ keys, const u32 *__
   else {
     const bool fFirst = fhi < rhi || (fhi == rhi && flo <= rlo);
     const u64 alo = fFirst ? flo : rlo, ahi = fFirst ? fhi : rhi, blo = fFirst ? rlo : flo, bhi = fFirst ? rhi : fhi;
-    bool found = list_holds<KW>(keys, vals, fileStart, fileLo, fileHi, k, alo, ahi, minValue, maxValue);
-    if (!found && !(alo == blo && ahi == bhi))
-      found = list_holds<KW>(keys, vals, fileStart, fileLo, fileHi, k, blo, bhi, minValue, maxValue);
-    if (found) fl |= 2;
+    const bool palindrome = (alo == blo && ahi == bhi);
+    const u32 va = list_value<KW>(keys, vals, fileStart, fileLo, fileHi, k, alo, ahi, minValue, maxValue);
+    u32 vb = 0;
+    if (!palindrome && (values || va == 0)) vb = list_value<KW>(keys, vals, fileStart, fileLo, fileHi, k, blo, bhi, minValue, maxValue);
+    if (va | vb) fl |= 2;
+    //  merylExactLookup::value hands back what the table stores: the value less (minValue - 1) (kmers-exact.C:57-62,
+    //  kmers-lookup.H:405-449 -- value_value() would add it back, value() does not); -wig-count sums exactly that.
+    //  (The two forms may lie in different groups of files: the sum builds up.)
+    const u32 off = minValue > 1 ? minValue - 1 : 0;
+    if (values && (va | vb)) values[p] += (va ? va - off : 0) + (vb ? vb - off : 0);
   }
   flag[p] = fl;
 }
@@ -1092,20 +1099,21 @@ extern "C" int mb_for_each_kmer(const char *dbDir, mb_kmer_callback cb, void *ar
 //  [minValue, maxValue]; *nDbKmers = the database's k-mers in that range (merylExactLookup::nKmers).  The first skipFirst
 //  k-mer positions of every sequence do not count as found (-10x, include-exclude.C:70).  Kernel K10 above, group of
 //  files by group of files.
-extern "C" int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
-                            uint64_t nSeqs, uint32_t skipFirst, uint64_t *nTotal, uint64_t *nFound, uint64_t *nDbKmers,
-                            int32_t device, uint64_t workspaceBytes) {
+static int existenceRun(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
+                        uint64_t nSeqs, uint32_t skipFirst, uint64_t *nTotal, uint64_t *nFound, uint64_t *nDbKmers,
+                        uint8_t *flagsOut, uint32_t *valuesOut, int32_t device, uint64_t workspaceBytes) {
   mb_clear_error();
-  if (!dbDir || (nSeqs && (!seqStart || !nTotal || !nFound))) return mb_fail(MB_EINVAL, "mb_existence: NULL argument");
+  if (!dbDir || (nSeqs && !seqStart)) return mb_fail(MB_EINVAL, "mb_existence: NULL argument");
   const u64 nBases = nSeqs ? seqStart[nSeqs] : 0;
   if (nBases && !bases) return mb_fail(MB_EINVAL, "mb_existence: NULL argument");
   for (u64 i = 0; i < nSeqs; i++) if (seqStart[i] > seqStart[i + 1]) return mb_fail(MB_EINVAL, "mb_existence: seqStart is not ascending");
   if (nSeqs && seqStart[0] != 0) return mb_fail(MB_EINVAL, "mb_existence: seqStart[0] must be 0");
   unsigned char *dBases = nullptr, *dFlag = nullptr;
   u64 *dSeqStart = nullptr, *dTot = nullptr, *dFnd = nullptr, *dDbN = nullptr;
+  u32 *dValues = nullptr;
   u32 kDb = 0;
   bool ranGroup = false;
-  return decodeDbInGroups(dbDir, device, workspaceBytes, (size_t)nBases * 2 + (size_t)nSeqs * 24 + 8192,
+  return decodeDbInGroups(dbDir, device, workspaceBytes, (size_t)nBases * (valuesOut ? 6 : 2) + (size_t)nSeqs * 24 + 8192,
     [&](const InputDb &db, Carve &top, cudaStream_t s) -> int {
       kDb = db.k;
       dDbN = (u64 *)top.take(8);
@@ -1117,11 +1125,13 @@ extern "C" int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxVa
       dSeqStart = (u64 *)top.take((size_t)(nSeqs + 1) * 8);
       dTot      = (u64 *)top.take((size_t)nSeqs * 8);
       dFnd      = (u64 *)top.take((size_t)nSeqs * 8);
-      if (!dBases || !dFlag || !dSeqStart || !dTot || !dFnd)
+      if (valuesOut) dValues = (u32 *)top.take((size_t)nBases * 4 + 16);
+      if (!dBases || !dFlag || !dSeqStart || !dTot || !dFnd || (valuesOut && !dValues))
         return mb_fail(MB_ENOMEM, "the %llu bases of %llu sequences do not fit the device arena", (unsigned long long)nBases, (unsigned long long)nSeqs);
       if (nBases) MB_CUDA(cudaMemcpyAsync(dBases, bases, (size_t)nBases, cudaMemcpyHostToDevice, s));
       MB_CUDA(cudaMemcpyAsync(dSeqStart, seqStart, (size_t)(nSeqs + 1) * 8, cudaMemcpyHostToDevice, s));
       MB_CUDA(cudaMemsetAsync(dFlag, 0, (size_t)nBases + 16, s));
+      if (dValues) MB_CUDA(cudaMemsetAsync(dValues, 0, (size_t)nBases * 4 + 16, s));
       MB_CUDA(cudaMemsetAsync(dTot, 0, (size_t)nSeqs * 8, s));
       MB_CUDA(cudaMemsetAsync(dFnd, 0, (size_t)nSeqs * 8, s));
       return MB_OK;
@@ -1132,8 +1142,8 @@ extern "C" int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxVa
       if (!nBases) return MB_OK;
       ranGroup = true;
       const unsigned grid = (unsigned)((nBases + 255) / 256);
-      if (db.k <= 32) existence_kernel<1><<<grid, 256, 0, s>>>((const u64 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
-      else            existence_kernel<2><<<grid, 256, 0, s>>>((const ulonglong2 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
+      if (db.k <= 32) existence_kernel<1><<<grid, 256, 0, s>>>((const u64 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag, dValues);
+      else            existence_kernel<2><<<grid, 256, 0, s>>>((const ulonglong2 *)G.dKey, G.dVal, G.dFileStart, G.f0, G.f1, db.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag, dValues);
       MB_CUDA(cudaGetLastError());
       return MB_OK;
     },
@@ -1143,17 +1153,35 @@ extern "C" int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxVa
       if (nBases) {
         if (!ranGroup) {                                    //  a database without k-mers: the sequences' own k-mers still count
           const unsigned grid = (unsigned)((nBases + 255) / 256);
-          if (kDb <= 32) existence_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, 0, 0, kDb, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
-          else           existence_kernel<2><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, 0, 0, kDb, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag);
+          if (kDb <= 32) existence_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, 0, 0, kDb, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag, dValues);
+          else           existence_kernel<2><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, 0, 0, kDb, dBases, nBases, dSeqStart, nSeqs, skipFirst, minValue, maxValue, dFlag, dValues);
           MB_CUDA(cudaGetLastError());
         }
         existence_sum_kernel<<<(unsigned)((nBases + 255) / 256), 256, 0, s>>>(dFlag, nBases, dSeqStart, nSeqs, dTot, dFnd);
         MB_CUDA(cudaGetLastError());
       }
-      MB_CUDA(cudaMemcpyAsync(nTotal, dTot, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
-      MB_CUDA(cudaMemcpyAsync(nFound, dFnd, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+      if (nTotal) MB_CUDA(cudaMemcpyAsync(nTotal, dTot, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+      if (nFound) MB_CUDA(cudaMemcpyAsync(nFound, dFnd, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+      if (flagsOut && nBases)  MB_CUDA(cudaMemcpyAsync(flagsOut, dFlag, (size_t)nBases, cudaMemcpyDeviceToHost, s));
+      if (valuesOut && nBases) MB_CUDA(cudaMemcpyAsync(valuesOut, dValues, (size_t)nBases * 4, cudaMemcpyDeviceToHost, s));
       return MB_OK;
     });
+}
+
+extern "C" int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
+                            uint64_t nSeqs, uint32_t skipFirst, uint64_t *nTotal, uint64_t *nFound, uint64_t *nDbKmers,
+                            int32_t device, uint64_t workspaceBytes) {
+  if (nSeqs && (!nTotal || !nFound)) { mb_clear_error(); return mb_fail(MB_EINVAL, "mb_existence: NULL argument"); }
+  return existenceRun(dbDir, minValue, maxValue, bases, seqStart, nSeqs, skipFirst, nTotal, nFound, nDbKmers, nullptr, nullptr, device, workspaceBytes);
+}
+
+//  The per-position form behind meryl-lookup's -bed / -wig-count / -wig-depth (src/meryl-lookup/dump.C:86-157): for position p of
+//  the letters, flags[p] bit 0 = a k-mer starts here, bit 1 = the database holds its forward or reverse-complement form
+//  (exists(c) || exists(n)); values[p] (may be NULL) = value(fmer) + value(rmer), once when the two are equal.
+extern "C" int mb_position_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
+                                  uint64_t nSeqs, uint8_t *flags, uint32_t *values, int32_t device, uint64_t workspaceBytes) {
+  if (nSeqs && seqStart && seqStart[nSeqs] && !flags) { mb_clear_error(); return mb_fail(MB_EINVAL, "mb_position_lookup: NULL argument"); }
+  return existenceRun(dbDir, minValue, maxValue, bases, seqStart, nSeqs, 0, nullptr, nullptr, nullptr, flags, values, device, workspaceBytes);
 }
 
 //  `count-suffix=ACG` (merylCommandBuilder.C:271-274; merylOp-countSimple.C:50-93, :172-199): only the k-mers whose counted

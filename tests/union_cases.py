@@ -297,6 +297,12 @@ def case_existence(tmp, k, n=6_000, monkeypatch=None):
     tot1, fnd1, _ = mb.existence(a, seqs, skip_first=23)
     tot2, fnd2, _ = mb.existence(a, [s[23:] if len(s) >= 23 + k else b"" for s in seqs])
     assert np.array_equal(tot0, tot1) and np.array_equal(fnd1, fnd2) and int(fnd1.sum()) < int(fnd0.sum())
+    # the per-position form agrees with the per-sequence sums; a found position has a non-zero value sum
+    flags, vals = mb.position_lookup(a, seqs, workspace_bytes=40 << 20)
+    edges = np.cumsum([0] + [len(s) for s in seqs])
+    assert [int((flags[edges[i]:edges[i + 1]] & 1).sum()) for i in range(len(seqs))] == [int(x) for x in tot0]
+    assert [int(((flags[edges[i]:edges[i + 1]] >> 1) & 1).sum()) for i in range(len(seqs))] == [int(x) for x in fnd0]
+    assert np.array_equal(vals > 0, (flags & 2) > 0)
     # no sequences at all: only the database's size comes back
     tot, fnd, ndb = mb.existence(a, [])
     assert tot.size == 0 and ndb > 0
@@ -304,7 +310,8 @@ def case_existence(tmp, k, n=6_000, monkeypatch=None):
 
 def case_cli_lookup(tmp, k, n=6_000, env=None):
     """`meryl-lookup-b200` against the reference's meryl-lookup, file for file: -existence on a FASTA file with two databases;
-    -include / -exclude on FASTQ reads (single, paired, -10x, a value window) and on FASTA; usage errors."""
+    -include / -exclude on FASTQ reads (single, paired, -10x, a value window) and on FASTA; -bed / -bed-runs (with and without
+    labels) / -wig-count / -wig-depth; usage errors."""
     import subprocess
     a = oracle_db(tmp, "a", synth.reads_fastq_bytes(n, n // 15, 150, 0.004, 40 + k), k)
     f = oracle_db(tmp, "f", synth.reads_fastq_bytes(n, n // 30, 150, 0.004, 40 + k), k, op="count-forward")
@@ -349,6 +356,11 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
     both(["-include", "-sequence", r1, r2, "-mers", a], ["inc1.fq", "inc2.fq"])
     both(["-exclude", "-10x", "-sequence", r1, r2, "-mers", a, "-min", "2", "-max", "50"], ["exc1.fq", "exc2.fq"])
     both(["-include", "-sequence", fa, "-mers", f], ["inc.fa"])
+    # the per-position reports (dump.C), on sequences with hits, misses, Ns, lower case, and sequences shorter than k
+    for rep in (["-bed"], ["-bed-runs"], ["-wig-count"], ["-wig-depth"], ["-bed", "-labels", "A", "B"], ["-bed-runs", "-labels", "onlyA"]):
+        out = both(rep + ["-sequence", fa_all, "-mers", a, f], ["pos.txt"])
+        assert out[0]
+        both(rep + ["-sequence", r1, "-mers", f, a, "-min", "2", "-max", "40"], ["pos2.txt"])
     pr = subprocess.run([util.REF_LOOKUP_BIN, "-existence", "-sequence", fa, "-mers", a], capture_output=True)       # no -output: stdout
     pd = subprocess.run([mb.LOOKUP_CLI_PATH, "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)
     assert pr.returncode == pd.returncode == 0 and pr.stdout == pd.stdout and pd.stdout
@@ -359,7 +371,8 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
     for words in (["-sequence", fa, "-mers", a, "-output", "x"], ["-existence", "-mers", a, "-output", "x"],
                   ["-existence", "-sequence", fa, "-output", "x"],
                   ["-include", "-sequence", fa, "-mers", a, f, "-output", "x"], ["-existence", "-sequence", fa, fa, "-mers", a, "-output", "x"],
-                  ["-include", "-sequence", r1, r2, "-mers", a, "-output", "x"], ["-existence", "-frobnicate"]):
+                  ["-include", "-sequence", r1, r2, "-mers", a, "-output", "x"], ["-existence", "-frobnicate"],
+                  ["-wig-count", "-sequence", fa, "-mers", a, "-labels", "A", "-output", "x"], ["-bed", "-sequence", fa, fa, "-mers", a, "-output", "x", "y"]):
         pr = subprocess.run([util.REF_LOOKUP_BIN] + words, capture_output=True, text=True, cwd=tmp)
         pd = subprocess.run([mb.LOOKUP_CLI_PATH] + words, capture_output=True, text=True, cwd=tmp, env=env)
         assert pr.returncode == pd.returncode == 1
