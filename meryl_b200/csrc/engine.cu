@@ -368,12 +368,48 @@ extern "C" int mb_add_bases_device(mb_ctx *c, const char *dBases, uint64_t len) 
   return MB_OK;
 }
 
+//  Experimental (MB_DEVICE_PARSE=1, not the default until it has run on a GPU): the file's bytes go to the device as they
+//  are and the parser's state machine runs there (parse.cu); the base stream it emits is packed (K1) without leaving the
+//  device.  Not with homopolymer compression (a host-side filter of the stream), and a batch closes only between files.
+static int deviceStreamSink(void *arg, const char *dStream, size_t n) {
+  mb_ctx *c = (mb_ctx *)arg;
+  const u64 recs = (n + 31) / 32;
+  MB_TRY(storeReserve(c, recs));
+  if (!c->ingestStarted) { c->ingestStarted = true; MB_CUDA(cudaEventRecord(c->evIngest[0], c->stream)); }
+  MB_CUDA(mb_launch_pack((const uint8_t *)dStream, n, (u32 *)c->arena, c->nRecords, c->stream));
+  c->st.nLaunches++;
+  c->nRecords += recs;
+  return MB_OK;
+}
+
+static bool wantDeviceParse(const mb_ctx *c) {
+  return getenv("MB_DEVICE_PARSE") != nullptr && !(c->cfg.flags & MB_FLAG_COMPRESS);
+}
+
+static int addFileBytesOnDevice(mb_ctx *c, const uint8_t *data, uint64_t len) {
+  MB_TRY(ensureArena(c));
+  if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
+  MB_TRY(flushStage(c));                                   //  the stream is at a record boundary: padding is harmless
+  if (batchDue(c)) MB_TRY(closeBatch(c));
+  MB_CUDA(cudaSetDevice(c->device));
+  MbDeviceParser *P = nullptr;
+  MB_TRY(mb_dparse_create(&P, c->stream));
+  int rc = mb_dparse_feed(P, data, (size_t)len, deviceStreamSink, c);
+  if (rc == MB_OK) rc = mb_dparse_finish(P, deviceStreamSink, c);
+  if (rc == MB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = mb_fail(MB_ENODEVICE, "device parser: %s", cudaGetErrorString(cudaGetLastError()));
+  c->st.nLaunches += mb_dparse_launches(P);
+  c->st.h2dBytes  += len;
+  mb_dparse_destroy(P);
+  return rc;
+}
+
 extern "C" int mb_add_file_bytes(mb_ctx *c, const uint8_t *data, uint64_t len) {
   mb_clear_error();
   if (!c || (!data && len))  return mb_fail(MB_EINVAL, "mb_add_file_bytes: NULL argument");
   if (c->counted)            return mb_fail(MB_ESTATE, "mb_add_file_bytes: already counted");
   if (!SeqParser::sniff(data, len < 65536 ? len : 65536))
     return mb_fail(MB_EFORMAT, "input is not FASTA or FASTQ");
+  if (wantDeviceParse(c)) return addFileBytesOnDevice(c, data, len);
   SeqParser ps(parserSink, c);
   const size_t BLK = (size_t)256 << 20;
   for (uint64_t at = 0; at < len; at += BLK) MB_TRY(mb_parse_parallel(parserSink, c, ps, data + at, (size_t)std::min<uint64_t>(BLK, len - at)));
@@ -408,6 +444,11 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
         const uint8_t *d = (const uint8_t *)m;
         int rc = MB_OK;
         if (!SeqParser::sniff(d, sz < 65536 ? sz : 65536)) rc = mb_fail(MB_EFORMAT, "'%s' is not FASTA or FASTQ", path);
+        if (rc == MB_OK && wantDeviceParse(c)) {           //  experimental: the state machine on the device (parse.cu)
+          rc = addFileBytesOnDevice(c, d, sz);
+          munmap(m, sz);
+          return rc;
+        }
         SeqParser ps(parserSink, c);
         const size_t BLK = (size_t)256 << 20;
         for (size_t at = 0; rc == MB_OK && at < sz; at += BLK) rc = mb_parse_parallel(parserSink, c, ps, d + at, std::min(BLK, sz - at));
