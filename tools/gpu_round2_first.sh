@@ -25,4 +25,6 @@ ls -la $OUT | tail -12
 echo "== e. union-sum next to the reference (staging ring; then with the warp-per-block decoder)";  date +%T
 timeout 200 python tools/union_bench.py 0.5 2>&1 | tee $OUT/union_bench_r2a.json | cut -c1-900
 MB_DECODE=warp timeout 200 python tools/union_bench.py 0.5 2>&1 | tee $OUT/union_bench_r2a_warp.json | cut -c1-900
+echo "== f. meryl-lookup -existence next to the reference; ingest through the device parser next to the host parser";  date +%T
+timeout 300 python tools/lookup_bench.py 300 2>&1 | tee $OUT/lookup_bench_r2a.jsonl | cut -c1-400
 date
