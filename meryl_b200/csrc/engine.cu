@@ -462,7 +462,9 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
   FILE *f = nullptr;
   if (tool) {
     if (access(path, R_OK) != 0) return mb_fail(MB_EIO, "cannot read '%s'", path);
-    std::string cmd = std::string(tool) + " '" + path + "'";
+    std::string cmd = std::string(tool) + " '";             //  the path inside single quotes, a quote in it as '\''
+    for (const char *q = path; *q; q++) { if (*q == '\'') cmd += "'\\''"; else cmd += *q; }
+    cmd += "'";
     f = popen(cmd.c_str(), "r");
   } else if (!strcmp(path, "-")) {
     f = stdin;

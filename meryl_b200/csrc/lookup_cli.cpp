@@ -37,6 +37,12 @@ struct Sequences {                                      //  one input file
 inline bool isWhite(char c)   { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }   //  types-v1.H:258-263
 inline bool isVisible(char c) { return c >= '!' && c <= '~'; }
 
+std::string shellQuoted(const char *path) {              //  inside single quotes, a quote in it as '\''
+  std::string q = "'";
+  for (const char *c = path; *c; c++) { if (*c == '\'') q += "'\\''"; else q += *c; }
+  return q + "'";
+}
+
 bool readAll(const char *path, std::vector<char> &out) {
   const size_t L = strlen(path);
   const char *tool = nullptr;
@@ -46,7 +52,7 @@ bool readAll(const char *path, std::vector<char> &out) {
   FILE *f = nullptr;
   if (tool) {
     if (access(path, R_OK) != 0) return false;
-    std::string cmd = std::string(tool) + " '" + path + "'";
+    std::string cmd = std::string(tool) + " " + shellQuoted(path);
     f = popen(cmd.c_str(), "r");
   } else f = !strcmp(path, "-") ? stdin : fopen(path, "rb");
   if (!f) return false;
@@ -107,7 +113,7 @@ FILE *openOut(const char *name, bool &piped) {
   if (!strcmp(name, "-")) return stdout;
   const size_t L = strlen(name);
   if (L > 3 && !strcmp(name + L - 3, ".gz")) {
-    std::string cmd = std::string("gzip -1c > '") + name + "'";
+    std::string cmd = std::string("gzip -1c > ") + shellQuoted(name);
     piped = true;
     return popen(cmd.c_str(), "w");
   }

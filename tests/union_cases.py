@@ -367,6 +367,15 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
     pd = subprocess.run([mb.CLI_PATH, "lookup", "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)  # the same through `meryl-b200 lookup`
     assert pd.returncode == 0 and pr.stdout == pd.stdout
     both(["-exclude", "-sequence", fa, "-mers", f, "-threads", "2", "-memory", "4"], ["exc.fa"])
+    # a gzip-compressed input (read through `gzip -dc`), with a quote in its name; gzip-compressed output
+    import gzip
+    gz = os.path.join(tmp, "que'ries.fa.gz")
+    with gzip.open(gz, "wb") as fh:
+        fh.write(open(fa_all, "rb").read())
+    outgz = os.path.join(tmp, "ex'out.txt.gz")
+    pd = subprocess.run([mb.LOOKUP_CLI_PATH, "-existence", "-sequence", gz, "-mers", a, f, "-output", outgz], capture_output=True, env=env)
+    assert pd.returncode == 0, pd.stderr[-300:]
+    assert gzip.open(outgz, "rb").read() == open(os.path.join(tmp, "dev_ex.txt"), "rb").read()
     # usage errors (meryl-lookup.C:291-368): same sentences, exit code 1
     for words in (["-sequence", fa, "-mers", a, "-output", "x"], ["-existence", "-mers", a, "-output", "x"],
                   ["-existence", "-sequence", fa, "-output", "x"],
