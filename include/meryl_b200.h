@@ -287,6 +287,20 @@ int mb_existence(const char *dbDir, uint32_t minValue, uint32_t maxValue, const 
 int mb_position_lookup(const char *dbDir, uint32_t minValue, uint32_t maxValue, const char *bases, const uint64_t *seqStart,
                        uint64_t nSeqs, uint8_t *flags, uint32_t *values, int32_t device, uint64_t workspaceBytes);
 
+/*  The lookup table as an object (merylExactLookup: load() once, value() / exists() many times; kmers-lookup.H:83-146): the whole
+ *  database is decoded into device memory and stays there; the queries above run against it.  mb_table_open fails with MB_ENOMEM
+ *  when the decoded database does not fit the device (the one-shot calls, which work group of files by group, remain).
+ *  mb_table_query = mb_existence + mb_position_lookup in one (any output may be NULL); mb_table_values = mb_lookup;
+ *  mb_table_kmers = merylExactLookup::nKmers (the k-mers with a value in [minValue, maxValue]).  */
+typedef struct mb_table mb_table;
+int      mb_table_open(const char *dbDir, uint32_t minValue, uint32_t maxValue, int32_t device, uint64_t workspaceBytes, mb_table **out);
+void     mb_table_close(mb_table *t);
+uint32_t mb_table_k(const mb_table *t);
+uint64_t mb_table_kmers(const mb_table *t);
+int      mb_table_query(mb_table *t, const char *bases, const uint64_t *seqStart, uint64_t nSeqs, uint32_t skipFirst,
+                        uint64_t *nTotal, uint64_t *nFound, uint8_t *flags, uint32_t *values);
+int      mb_table_values(mb_table *t, const uint64_t *kmerLo, const uint64_t *kmerHi, uint64_t nQueries, uint32_t *values);
+
 /* ---- stage-level entry points used by the parity tests (tests/test_gpu_stages.py) ------------- */
 
 /*  K1+K2: host ASCII work-buffer -> all k-mers in stream order is not defined on the device (the

@@ -427,3 +427,64 @@ def position_lookup(db, sequences, min_value: int = 0, max_value: int = 0xffffff
     _check(L.mb_position_lookup(os.fsencode(os.fspath(db)), min_value, max_value, blob, starts.ctypes.data, len(sequences),
                                 flags.ctypes.data, None if vals is None else vals.ctypes.data, device, workspace_bytes))
     return flags, vals
+
+
+class Table:
+    """A database decoded into device memory once and asked many times (mb_table_*; merylExactLookup as an object)."""
+
+    def __init__(self, db, min_value: int = 0, max_value: int = 0xffffffff, device: int = -1, workspace_bytes: int = 0):
+        L = lib()
+        L.mb_table_open.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int32, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
+        L.mb_table_close.argtypes = [ctypes.c_void_p]
+        L.mb_table_close.restype = None
+        L.mb_table_k.argtypes = [ctypes.c_void_p]
+        L.mb_table_k.restype = ctypes.c_uint32
+        L.mb_table_kmers.argtypes = [ctypes.c_void_p]
+        L.mb_table_kmers.restype = ctypes.c_uint64
+        L.mb_table_query.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.mb_table_values.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        self._h = ctypes.c_void_p()
+        _check(L.mb_table_open(os.fsencode(os.fspath(db)), min_value, max_value, device, workspace_bytes, ctypes.byref(self._h)))
+        self.k = L.mb_table_k(self._h)
+        self.kmers = L.mb_table_kmers(self._h)
+
+    def close(self) -> None:
+        if self._h:
+            lib().mb_table_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query(self, sequences, skip_first: int = 0, positions: bool = False, values: bool = False):
+        """(nTotal[], nFound[], flags[] or None, values[] or None) for a list of sequences (bytes)."""
+        import numpy as np
+        starts = np.zeros(len(sequences) + 1, dtype=np.uint64)
+        if sequences:
+            starts[1:] = np.cumsum([len(x) for x in sequences], dtype=np.uint64)
+        blob = b"".join(sequences)
+        tot = np.zeros(len(sequences), dtype=np.uint64)
+        fnd = np.zeros(len(sequences), dtype=np.uint64)
+        flags = np.zeros(len(blob), dtype=np.uint8) if positions or values else None
+        vals = np.zeros(len(blob), dtype=np.uint32) if values else None
+        _check(lib().mb_table_query(self._h, blob, starts.ctypes.data, len(sequences), skip_first, tot.ctypes.data, fnd.ctypes.data,
+                                    None if flags is None else flags.ctypes.data, None if vals is None else vals.ctypes.data))
+        return tot, fnd, flags, vals
+
+    def values(self, kmer_lo, kmer_hi=None):
+        import numpy as np
+        lo = np.ascontiguousarray(kmer_lo, dtype=np.uint64)
+        hi = None if kmer_hi is None else np.ascontiguousarray(kmer_hi, dtype=np.uint64)
+        out = np.zeros(lo.size, dtype=np.uint32)
+        _check(lib().mb_table_values(self._h, lo.ctypes.data, None if hi is None else hi.ctypes.data, lo.size, out.ctypes.data))
+        return out

@@ -13,7 +13,8 @@
 //
 //  The sequences are read on the host the way the reference's loader reads them (bufSeqFile::loadSequence / loadFASTA /
 //  loadFASTQ, src/utility/src/sequence/bufSeqFile-v1.C:291-549; names: dnaSeq::findNameAndFlags, dnaSeq-v1.C:89-101); the
-//  counting is mb_existence (kernel K10, csrc/union.cu), one call per database.
+//  counting is kernel K10 (csrc/union.cu) against the database kept resident on the device (mb_table_open / mb_table_query),
+//  the sequences passing in batches.
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -144,6 +145,39 @@ void writeRecord(FILE *o, const Sequences &S, size_t i, uint64_t nFound) {
   }
 }
 
+//  One database against all sequences of a file: the database is decoded once and stays on the device (mb_table_open) while
+//  the sequences go by in batches of ~256 MB of letters (MB_LOOKUP_BATCH: testing knob); a database too large to stay
+//  resident falls back to the one-shot calls, which decode it group of files by group of files for every batch.
+int askDatabase(const char *db, uint32_t minV, uint32_t maxV, const Sequences &S, uint32_t skipFirst,
+                uint64_t *total, uint64_t *found, uint64_t *dbKmers, uint8_t *flags, uint32_t *values) {
+  size_t batch = (size_t)256 << 20;
+  if (getenv("MB_LOOKUP_BATCH")) batch = (size_t)strtoull(getenv("MB_LOOKUP_BATCH"), nullptr, 10);
+  mb_table *T = nullptr;
+  const int orc = getenv("MB_LOOKUP_NO_TABLE") ? MB_ENOMEM : mb_table_open(db, minV, maxV, -1, 0, &T);     //  (testing knob: the fallback)
+  if (orc != MB_OK && orc != MB_ENOMEM) return orc;
+  if (T && dbKmers) *dbKmers = mb_table_kmers(T);
+  int rc = MB_OK;
+  const size_t n = S.size();
+  std::vector<uint64_t> rel;
+  bool first = true;
+  for (size_t i0 = 0; (i0 < n || first) && rc == MB_OK; first = false) {
+    size_t i1 = i0;
+    while (i1 < n && (i1 == i0 || S.seqStart[i1 + 1] - S.seqStart[i0] <= batch)) i1++;
+    rel.assign(i1 - i0 + 1, 0);
+    for (size_t i = i0; i <= i1; i++) rel[i - i0] = S.seqStart[i] - S.seqStart[i0];
+    const char *b = S.bases.data() + S.seqStart[i0];
+    uint64_t *t = total ? total + i0 : nullptr, *f = found ? found + i0 : nullptr;
+    uint8_t  *fl = flags ? flags + S.seqStart[i0] : nullptr;
+    uint32_t *va = values ? values + S.seqStart[i0] : nullptr;
+    if (T) rc = mb_table_query(T, b, rel.data(), i1 - i0, skipFirst, t, f, fl, va);
+    else if (flags) rc = mb_position_lookup(db, minV, maxV, b, rel.data(), i1 - i0, fl, va, -1, 0);
+    else            rc = mb_existence(db, minV, maxV, b, rel.data(), i1 - i0, skipFirst, t, f, dbKmers, -1, 0);
+    i0 = i1;
+  }
+  mb_table_close(T);
+  return rc;
+}
+
 enum Report { NONE, EXISTENCE, INCLUDE, EXCLUDE, BED, WIGCOUNT, WIGDEPTH, UNSUPPORTED };
 
 const char *reportName(Report r) {                       //  toString(lookupOp), meryl-lookup.H:38-50
@@ -240,7 +274,7 @@ int mbLookupMain(int argc, char **argv) {
     std::vector<uint8_t>  flags(nBases, 0), valid(nBases, 0);
     std::vector<uint32_t> count(report == WIGCOUNT ? nBases : 0, 0), vals(report == WIGCOUNT ? nBases : 0, 0);
     for (size_t d = 0; d < nDb; d++) {
-      if (mb_position_lookup(dbs[d], minV, maxV, S1.bases.data(), S1.seqStart.data(), n, flags.data(), report == WIGCOUNT ? vals.data() : nullptr, -1, 0) != MB_OK) {
+      if (askDatabase(dbs[d], minV, maxV, S1, 0, nullptr, nullptr, nullptr, flags.data(), report == WIGCOUNT ? vals.data() : nullptr) != MB_OK) {
         fprintf(stderr, "ERROR: %s\n", mb_last_error());
         return 1;
       }
@@ -296,7 +330,7 @@ int mbLookupMain(int argc, char **argv) {
     std::vector<std::vector<uint64_t>> found(dbs.size(), std::vector<uint64_t>(n, 0));
     std::vector<uint64_t> total(n, 0), dbKmers(dbs.size(), 0);
     for (size_t d = 0; d < dbs.size(); d++)
-      if (mb_existence(dbs[d], minV, maxV, S1.bases.data(), S1.seqStart.data(), n, 0, total.data(), found[d].data(), &dbKmers[d], -1, 0) != MB_OK) {
+      if (askDatabase(dbs[d], minV, maxV, S1, 0, total.data(), found[d].data(), &dbKmers[d], nullptr, nullptr) != MB_OK) {
         fprintf(stderr, "ERROR: %s\n", mb_last_error());
         return 1;
       }
@@ -308,8 +342,8 @@ int mbLookupMain(int argc, char **argv) {
   } else {
     const size_t n1 = S1.size(), n2 = S2.size(), n = n1 > n2 ? n1 : n2;
     std::vector<uint64_t> t1(n1, 0), f1(n1, 0), t2(n2, 0), f2(n2, 0);
-    if (mb_existence(dbs[0], minV, maxV, S1.bases.data(), S1.seqStart.data(), n1, is10x ? 23 : 0, t1.data(), f1.data(), nullptr, -1, 0) != MB_OK ||
-        (seq2 && mb_existence(dbs[0], minV, maxV, S2.bases.data(), S2.seqStart.data(), n2, 0, t2.data(), f2.data(), nullptr, -1, 0) != MB_OK)) {
+    if (askDatabase(dbs[0], minV, maxV, S1, is10x ? 23 : 0, t1.data(), f1.data(), nullptr, nullptr, nullptr) != MB_OK ||
+        (seq2 && askDatabase(dbs[0], minV, maxV, S2, 0, t2.data(), f2.data(), nullptr, nullptr, nullptr) != MB_OK)) {
       fprintf(stderr, "ERROR: %s\n", mb_last_error());
       return 1;
     }

@@ -911,9 +911,13 @@ struct DecodedGroup {
   u64         nKmers = 0;
 };
 
+//  (hold: the whole database must decode as ONE group; its arena and stream are then handed to the caller instead of
+//  being released -- the resident table of mb_table_open)
+struct DecodeHold { uint8_t *arena = nullptr; cudaStream_t s = nullptr; DecodedGroup G; u32 k = 0; };
+
 template <typename Setup, typename PerGroup, typename Finish>
 static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspaceBytes, size_t fixedBytes,
-                            Setup setup, PerGroup perGroup, Finish finish) {
+                            Setup setup, PerGroup perGroup, Finish finish, DecodeHold *hold = nullptr) {
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return mb_fail(MB_ENODEVICE, "no CUDA device (this library has no CPU path)");
   InputDb db;
@@ -952,8 +956,9 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
     while (f0 < 64) {
       u32 f1 = f0 + 1;
       if (fixedOff + groupNeed(f0, f1) > want) { rc = mb_fail(MB_ENOMEM, "data file %u needs %zu bytes on the device, %zu available", f0, groupNeed(f0, f1), want - fixedOff); goto done; }
-      const u32 maxFiles = getenv("MB_UNION_MAX_FILES") ? (u32)strtoul(getenv("MB_UNION_MAX_FILES"), nullptr, 10) : 64;   //  testing knob
+      const u32 maxFiles = (!hold && getenv("MB_UNION_MAX_FILES")) ? (u32)strtoul(getenv("MB_UNION_MAX_FILES"), nullptr, 10) : 64;   //  testing knob
       while (f1 < 64 && f1 - f0 < maxFiles && fixedOff + groupNeed(f0, f1 + 1) <= want) f1++;
+      if (hold && f1 < 64) { rc = mb_fail(MB_ENOMEM, "the decoded database needs %zu bytes on the device, %zu available: it cannot stay resident", groupNeed(0, 64), want - fixedOff); goto done; }
       Carve g(arena + fixedOff, want - fixedOff);
 
       //  the group's bytes and block table
@@ -1004,6 +1009,7 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
         else         decode_kernel<2><<<dgrid, 128, 0, s>>>(dRaw, rawBytes, dTab, tab.size(), db.wSuffix, (ulonglong2 *)dKey, dVal, nk, dErr);
         MB_UCUDA(cudaGetLastError());
         G.dKey = dKey;  G.dVal = dVal;
+        if (hold) hold->G = G;
         MB_UTRY(perGroup(db, G, s));
         u32 err = 0;
         MB_UCUDA(cudaMemcpyAsync(&err, dErr, 4, cudaMemcpyDeviceToHost, s));
@@ -1014,6 +1020,15 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
     }
     MB_UTRY(finish(s));
     MB_UCUDA(cudaStreamSynchronize(s));
+    if (hold) {
+      if (!hold->G.dFileStart) {                              //  a database without k-mers: 64 empty lists
+        MB_UCUDA(cudaMemsetAsync(dFileStart, 0, 65 * 8, s));
+        MB_UCUDA(cudaStreamSynchronize(s));
+        hold->G.dFileStart = dFileStart;  hold->G.f0 = 0;  hold->G.f1 = 64;
+      }
+      hold->k = db.k;  hold->arena = arena;  hold->s = s;
+      arena = nullptr;  s = nullptr;
+    }
   }
 done:
   if (s) cudaStreamDestroy(s);
@@ -1182,6 +1197,128 @@ extern "C" int mb_position_lookup(const char *dbDir, uint32_t minValue, uint32_t
                                   uint64_t nSeqs, uint8_t *flags, uint32_t *values, int32_t device, uint64_t workspaceBytes) {
   if (nSeqs && seqStart && seqStart[nSeqs] && !flags) { mb_clear_error(); return mb_fail(MB_EINVAL, "mb_position_lookup: NULL argument"); }
   return existenceRun(dbDir, minValue, maxValue, bases, seqStart, nSeqs, 0, nullptr, nullptr, nullptr, flags, values, device, workspaceBytes);
+}
+
+//  ---- the resident table (merylExactLookup as an object: load once, ask many times; kmers-lookup.H:83-146) ----------------
+//  mb_table_open decodes the whole database into device memory and keeps it there (180 GB of HBM hold the decoded lists of a
+//  human-size read database); the queries are K9 / K10 launches against the resident lists, with a scratch allocation per
+//  call for the queries themselves.  A database that does not fit is MB_ENOMEM: the one-shot calls above (group by group)
+//  are the fallback.
+struct mb_table {
+  DecodeHold h;
+  int32_t    device = -1;
+  u32        minValue = 0, maxValue = 0xffffffffu;
+  u64        nInRange = 0;
+};
+
+extern "C" int mb_table_open(const char *dbDir, uint32_t minValue, uint32_t maxValue, int32_t device, uint64_t workspaceBytes, mb_table **out) {
+  mb_clear_error();
+  if (!dbDir || !out) return mb_fail(MB_EINVAL, "mb_table_open: NULL argument");
+  mb_table *T = new mb_table;
+  T->minValue = minValue;  T->maxValue = maxValue;
+  u64 *dN = nullptr;
+  const int rc = decodeDbInGroups(dbDir, device, workspaceBytes, 4096,
+    [&](const InputDb &, Carve &top, cudaStream_t s) -> int {
+      dN = (u64 *)top.take(8);
+      if (!dN) return mb_fail(MB_ENOMEM, "device arena too small");
+      MB_CUDA(cudaMemsetAsync(dN, 0, 8, s));
+      return MB_OK;
+    },
+    [&](const InputDb &, const DecodedGroup &G, cudaStream_t s) -> int {
+      count_in_range_kernel<<<(unsigned)std::min<u64>((G.nKmers + 255) / 256, 148 * 8), 256, 0, s>>>(G.dVal, G.nKmers, minValue, maxValue, dN);
+      MB_CUDA(cudaGetLastError());
+      return MB_OK;
+    },
+    [&](cudaStream_t s) -> int { MB_CUDA(cudaMemcpyAsync(&T->nInRange, dN, 8, cudaMemcpyDeviceToHost, s)); return MB_OK; },
+    &T->h);
+  if (rc != MB_OK) { delete T; return rc; }
+  if (cudaGetDevice(&T->device) != cudaSuccess) T->device = device;
+  *out = T;
+  return MB_OK;
+}
+
+extern "C" void mb_table_close(mb_table *T) {
+  if (!T) return;
+  if (T->device >= 0) cudaSetDevice(T->device);
+  if (T->h.s) { cudaStreamSynchronize(T->h.s); cudaStreamDestroy(T->h.s); }
+  if (T->h.arena) cudaFree(T->h.arena);
+  delete T;
+}
+
+extern "C" uint32_t mb_table_k(const mb_table *T)      { return T ? T->h.k : 0; }
+extern "C" uint64_t mb_table_kmers(const mb_table *T)  { return T ? T->nInRange : 0; }
+
+//  mb_existence / mb_position_lookup against the resident table (any of the outputs may be NULL).
+extern "C" int mb_table_query(mb_table *T, const char *bases, const uint64_t *seqStart, uint64_t nSeqs, uint32_t skipFirst,
+                              uint64_t *nTotal, uint64_t *nFound, uint8_t *flags, uint32_t *values) {
+  mb_clear_error();
+  if (!T || (nSeqs && !seqStart)) return mb_fail(MB_EINVAL, "mb_table_query: NULL argument");
+  if (nSeqs == 0) return MB_OK;
+  const u64 nBases = seqStart[nSeqs];
+  if (seqStart[0] != 0 || (nBases && !bases)) return mb_fail(MB_EINVAL, "mb_table_query: bad sequence offsets");
+  for (u64 i = 0; i < nSeqs; i++) if (seqStart[i] > seqStart[i + 1]) return mb_fail(MB_EINVAL, "mb_table_query: seqStart is not ascending");
+  MB_CUDA(cudaSetDevice(T->device));
+  const size_t bytes = ((size_t)nBases + 256) * 2 + (size_t)(nSeqs + 1) * 8 + 256 + (size_t)nSeqs * 16 + 512 + (values ? (size_t)nBases * 4 + 256 : 0) + 4096;
+  uint8_t *scratch = nullptr;
+  if (cudaMalloc((void **)&scratch, bytes) != cudaSuccess) { cudaGetLastError(); return mb_fail(MB_ENOMEM, "cannot allocate %zu bytes next to the resident table: ask in smaller batches", bytes); }
+  struct Free { uint8_t *p; ~Free() { cudaFree(p); } } freeIt{ scratch };
+  Carve top(scratch, bytes);
+  unsigned char *dBases = (unsigned char *)top.take((size_t)nBases + 16), *dFlag = (unsigned char *)top.take((size_t)nBases + 16);
+  u64 *dSeqStart = (u64 *)top.take((size_t)(nSeqs + 1) * 8), *dTot = (u64 *)top.take((size_t)nSeqs * 8), *dFnd = (u64 *)top.take((size_t)nSeqs * 8);
+  u32 *dValues = values ? (u32 *)top.take((size_t)nBases * 4 + 16) : nullptr;
+  if (!dBases || !dFlag || !dSeqStart || !dTot || !dFnd || (values && !dValues)) return mb_fail(MB_ENOMEM, "internal: query scratch too small");
+  cudaStream_t s = T->h.s;
+  const DecodedGroup &G = T->h.G;
+  if (nBases) MB_CUDA(cudaMemcpyAsync(dBases, bases, (size_t)nBases, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(dSeqStart, seqStart, (size_t)(nSeqs + 1) * 8, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemsetAsync(dFlag, 0, (size_t)nBases + 16, s));
+  MB_CUDA(cudaMemsetAsync(dTot, 0, (size_t)nSeqs * 8, s));
+  MB_CUDA(cudaMemsetAsync(dFnd, 0, (size_t)nSeqs * 8, s));
+  if (dValues) MB_CUDA(cudaMemsetAsync(dValues, 0, (size_t)nBases * 4 + 16, s));
+  if (nBases) {
+    const unsigned grid = (unsigned)((nBases + 255) / 256);
+    if (T->h.k <= 32) existence_kernel<1><<<grid, 256, 0, s>>>((const u64 *)G.dKey, G.dVal, G.dFileStart, 0, 64, T->h.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, T->minValue, T->maxValue, dFlag, dValues);
+    else              existence_kernel<2><<<grid, 256, 0, s>>>((const ulonglong2 *)G.dKey, G.dVal, G.dFileStart, 0, 64, T->h.k, dBases, nBases, dSeqStart, nSeqs, skipFirst, T->minValue, T->maxValue, dFlag, dValues);
+    MB_CUDA(cudaGetLastError());
+    existence_sum_kernel<<<grid, 256, 0, s>>>(dFlag, nBases, dSeqStart, nSeqs, dTot, dFnd);
+    MB_CUDA(cudaGetLastError());
+  }
+  if (nTotal) MB_CUDA(cudaMemcpyAsync(nTotal, dTot, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+  if (nFound) MB_CUDA(cudaMemcpyAsync(nFound, dFnd, (size_t)nSeqs * 8, cudaMemcpyDeviceToHost, s));
+  if (flags && nBases)  MB_CUDA(cudaMemcpyAsync(flags, dFlag, (size_t)nBases, cudaMemcpyDeviceToHost, s));
+  if (values && nBases) MB_CUDA(cudaMemcpyAsync(values, dValues, (size_t)nBases * 4, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  return MB_OK;
+}
+
+//  mb_lookup against the resident table.
+extern "C" int mb_table_values(mb_table *T, const uint64_t *kmerLo, const uint64_t *kmerHi, uint64_t nQueries, uint32_t *values) {
+  mb_clear_error();
+  if (!T || (nQueries && (!kmerLo || !values))) return mb_fail(MB_EINVAL, "mb_table_values: NULL argument");
+  if (nQueries == 0) return MB_OK;
+  const bool wide = T->h.k > 32;
+  if (wide && !kmerHi) return mb_fail(MB_EINVAL, "mb_table_values: k=%u needs the high words of the k-mers", T->h.k);
+  MB_CUDA(cudaSetDevice(T->device));
+  const size_t bytes = (size_t)nQueries * 20 + 4096;
+  uint8_t *scratch = nullptr;
+  if (cudaMalloc((void **)&scratch, bytes) != cudaSuccess) { cudaGetLastError(); return mb_fail(MB_ENOMEM, "cannot allocate %zu bytes next to the resident table: ask in smaller batches", bytes); }
+  struct Free { uint8_t *p; ~Free() { cudaFree(p); } } freeIt{ scratch };
+  Carve top(scratch, bytes);
+  u64 *dQLo = (u64 *)top.take((size_t)nQueries * 8), *dQHi = wide ? (u64 *)top.take((size_t)nQueries * 8) : nullptr;
+  u32 *dOut = (u32 *)top.take((size_t)nQueries * 4);
+  if (!dQLo || (wide && !dQHi) || !dOut) return mb_fail(MB_ENOMEM, "internal: query scratch too small");
+  cudaStream_t s = T->h.s;
+  const DecodedGroup &G = T->h.G;
+  MB_CUDA(cudaMemcpyAsync(dQLo, kmerLo, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
+  if (wide) MB_CUDA(cudaMemcpyAsync(dQHi, kmerHi, (size_t)nQueries * 8, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemsetAsync(dOut, 0, (size_t)nQueries * 4, s));
+  const unsigned qgrid = (unsigned)((nQueries + 255) / 256);
+  if (!wide) lookup_kernel<1><<<qgrid, 256, 0, s>>>((const u64 *)G.dKey, G.dVal, G.dFileStart, 0, 64, T->h.k, dQLo, dQHi, nQueries, T->minValue, T->maxValue, dOut);
+  else       lookup_kernel<2><<<qgrid, 256, 0, s>>>((const ulonglong2 *)G.dKey, G.dVal, G.dFileStart, 0, 64, T->h.k, dQLo, dQHi, nQueries, T->minValue, T->maxValue, dOut);
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaMemcpyAsync(values, dOut, (size_t)nQueries * 4, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  return MB_OK;
 }
 
 //  `count-suffix=ACG` (merylCommandBuilder.C:271-274; merylOp-countSimple.C:50-93, :172-199): only the k-mers whose counted

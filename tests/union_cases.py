@@ -2,6 +2,8 @@
 (tests/test_cusim_union.py) and against the CUDA library on the GPU (tests/test_gpu_union.py)."""
 import os
 
+import pytest
+
 import util
 import meryl_b200 as mb
 from meryl_b200 import synth
@@ -212,6 +214,9 @@ def case_lookup(tmp, k, n=6_000, monkeypatch=None):
         got = mb.lookup(db, lo, hi, min_value=2, max_value=3, workspace_bytes=ws)
         want = np.array([truth.get(q, 0) if 2 <= truth.get(q, 0) <= 3 else 0 for q in queries], dtype=np.uint32)
         assert np.array_equal(got, want)
+        if not ws:
+            with mb.Table(db, min_value=2, max_value=3) as t:                # the same from the resident table
+                assert np.array_equal(t.values(lo, hi), want)
 
 
 def case_cli_print(tmp, k, n=3_000, env=None):
@@ -303,6 +308,23 @@ def case_existence(tmp, k, n=6_000, monkeypatch=None):
     assert [int((flags[edges[i]:edges[i + 1]] & 1).sum()) for i in range(len(seqs))] == [int(x) for x in tot0]
     assert [int(((flags[edges[i]:edges[i + 1]] >> 1) & 1).sum()) for i in range(len(seqs))] == [int(x) for x in fnd0]
     assert np.array_equal(vals > 0, (flags & 2) > 0)
+    # the resident table (mb_table_*): the same answers, asked in several batches against one decoded copy
+    with mb.Table(a) as t:
+        assert t.k == k and t.kmers == mb.existence(a, [])[2]
+        half = len(seqs) // 2
+        t1, f1, fl1, v1 = t.query(seqs[:half], values=True)
+        t2, f2, fl2, v2 = t.query(seqs[half:], values=True)
+        assert np.array_equal(np.concatenate([t1, t2]), tot0) and np.array_equal(np.concatenate([f1, f2]), fnd0)
+        assert np.array_equal(np.concatenate([fl1, fl2]), flags) and np.array_equal(np.concatenate([v1, v2]), vals)
+        assert np.array_equal(t.query(seqs, skip_first=23)[1], fnd1)
+        assert t.query([])[0].size == 0
+    with mb.Table(a, min_value=2, max_value=3) as t:
+        w_tot, w_fnd, w_ndb = mb.existence(a, seqs, min_value=2, max_value=3)
+        assert t.kmers == w_ndb and np.array_equal(t.query(seqs)[1], w_fnd)
+    with mb.Table(e) as t:                                   # a database without k-mers
+        assert t.kmers == 0 and np.array_equal(t.query(seqs)[0], tot0) and int(t.query(seqs)[1].sum()) == 0
+    with pytest.raises(mb.MerylB200Error):                   # no room to keep it resident: the one-shot calls are the fallback
+        mb.Table(a, workspace_bytes=1 << 20)
     # no sequences at all: only the database's size comes back
     tot, fnd, ndb = mb.existence(a, [])
     assert tot.size == 0 and ndb > 0
@@ -367,6 +389,18 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
     pd = subprocess.run([mb.CLI_PATH, "lookup", "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)  # the same through `meryl-b200 lookup`
     assert pd.returncode == 0 and pr.stdout == pd.stdout
     both(["-exclude", "-sequence", fa, "-mers", f, "-threads", "2", "-memory", "4"], ["exc.fa"])
+    # the sequences in many small batches against the resident table, and the fallback without it (one-shot calls per batch)
+    for knobs in ({"MB_LOOKUP_BATCH": "2000"}, {"MB_LOOKUP_BATCH": "5000", "MB_LOOKUP_NO_TABLE": "1"}):
+        e2 = dict(env if env is not None else os.environ, **knobs)
+        for rep, ref_name in ((["-existence"], "dev_ex.txt"), (["-wig-count"], None), (["-bed-runs", "-labels", "A", "B"], None)):
+            o = os.path.join(tmp, "batched.txt")
+            pd = subprocess.run([mb.LOOKUP_CLI_PATH] + rep + ["-sequence", fa_all, "-mers", a, f, "-output", o], capture_output=True, env=e2)
+            assert pd.returncode == 0, pd.stderr[-300:]
+            if ref_name is None:
+                pr = subprocess.run([util.REF_LOOKUP_BIN] + rep + ["-sequence", fa_all, "-mers", a, f, "-output", o + ".ref"], capture_output=True)
+                assert pr.returncode == 0
+                ref_name = o + ".ref"
+            assert open(o, "rb").read() == open(os.path.join(tmp, ref_name), "rb").read(), (knobs, rep)
     # a gzip-compressed input (read through `gzip -dc`), with a quote in its name; gzip-compressed output
     import gzip
     gz = os.path.join(tmp, "que'ries.fa.gz")
