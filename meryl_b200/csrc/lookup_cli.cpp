@@ -215,6 +215,7 @@ int mbLookupMain(int argc, char **argv) {
     else if (!strcmp(w, "-estimate"))  { report = UNSUPPORTED; unsupported = w; }
     else if (!strcmp(w, "-10x"))       { is10x = true; }
     else if (!strcmp(w, "-V"))         { }
+    else if (!strcmp(w, "-help"))      { err.push_back(""); }               //  (usage and exit code 1, as the reference)
     else err.push_back(std::string("Unknown option '") + w + "'.\n");
   }
   if (report == UNSUPPORTED) {
