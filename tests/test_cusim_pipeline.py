@@ -335,3 +335,22 @@ def test_sim_device_parser_in_the_pipeline(tmp_path, monkeypatch, k, w_prefix, o
     monkeypatch.setenv("MB_DPARSE_BLOCK", "65536")
     st = _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(5_000, 900, 150, 0.01, 3), "g.fa": synth.fasta_bytes(7, 2_000, 4, width=60, eol=b"\r\n")}, k, w_prefix, op)
     assert st.nLaunches > 20
+
+
+def test_sim_compressed_input_with_a_quote_in_its_name(tmp_path):
+    """A .gz input arrives through `gzip -dc '<path>'`: the path is shell-quoted, a quote inside it included."""
+    import gzip
+    data = synth.reads_fastq_bytes(4_000, 300, 150, 0.01, 5)
+    plain, gz = tmp_path / "r.fq", tmp_path / "it's.fq.gz"
+    plain.write_bytes(data)
+    with gzip.open(gz, "wb") as fh:
+        fh.write(data)
+    outs = []
+    for p in (plain, gz):
+        out = str(tmp_path / (p.name + ".meryl"))
+        with mb.Counter(21, 8, "count") as c:
+            c.add_file(str(p))
+            c.count()
+            c.write_db(out)
+        outs.append(out)
+    util.assert_same_db(outs[0], outs[1])
