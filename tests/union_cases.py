@@ -363,7 +363,8 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
         got = []
         for exe, tag in ((util.REF_LOOKUP_BIN, "ref"), (mb.LOOKUP_CLI_PATH, "dev")):
             names_ = [os.path.join(tmp, "%s_%s" % (tag, o)) for o in outs]
-            p = subprocess.run([exe] + words + ["-output"] + names_, capture_output=True, text=True, env=env if tag == "dev" else None)
+            # (-threads: the reference sizes its load buffers at 512 MB per thread and refuses when that exceeds the memory limit)
+            p = subprocess.run([exe] + words + ["-threads", "4", "-output"] + names_, capture_output=True, text=True, env=env if tag == "dev" else None)
             assert p.returncode == 0, (tag, p.stderr[-500:])
             got.append([open(x, "rb").read() for x in names_])
         assert got[0] == got[1], words
@@ -383,8 +384,8 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
         out = both(rep + ["-sequence", fa_all, "-mers", a, f], ["pos.txt"])
         assert out[0]
         both(rep + ["-sequence", r1, "-mers", f, a, "-min", "2", "-max", "40"], ["pos2.txt"])
-    pr = subprocess.run([util.REF_LOOKUP_BIN, "-existence", "-sequence", fa, "-mers", a], capture_output=True)       # no -output: stdout
-    pd = subprocess.run([mb.LOOKUP_CLI_PATH, "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)
+    pr = subprocess.run([util.REF_LOOKUP_BIN, "-existence", "-sequence", fa, "-mers", a, "-threads", "4"], capture_output=True)   # no -output: stdout
+    pd = subprocess.run([mb.LOOKUP_CLI_PATH, "-existence", "-sequence", fa, "-mers", a, "-threads", "4"], capture_output=True, env=env)
     assert pr.returncode == pd.returncode == 0 and pr.stdout == pd.stdout and pd.stdout
     pd = subprocess.run([mb.CLI_PATH, "lookup", "-existence", "-sequence", fa, "-mers", a], capture_output=True, env=env)  # the same through `meryl-b200 lookup`
     assert pd.returncode == 0 and pr.stdout == pd.stdout
@@ -397,7 +398,7 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
             pd = subprocess.run([mb.LOOKUP_CLI_PATH] + rep + ["-sequence", fa_all, "-mers", a, f, "-output", o], capture_output=True, env=e2)
             assert pd.returncode == 0, pd.stderr[-300:]
             if ref_name is None:
-                pr = subprocess.run([util.REF_LOOKUP_BIN] + rep + ["-sequence", fa_all, "-mers", a, f, "-output", o + ".ref"], capture_output=True)
+                pr = subprocess.run([util.REF_LOOKUP_BIN] + rep + ["-sequence", fa_all, "-mers", a, f, "-threads", "4", "-output", o + ".ref"], capture_output=True)
                 assert pr.returncode == 0
                 ref_name = o + ".ref"
             assert open(o, "rb").read() == open(os.path.join(tmp, ref_name), "rb").read(), (knobs, rep)

@@ -56,7 +56,7 @@ def main():
             continue
         t0 = time.perf_counter()
         env = dict(os.environ, LD_PRELOAD=mb.LIB_PATH) if os.environ.get("MB_BENCH_SIM") and exe == mb.LOOKUP_CLI_PATH else None
-        p = subprocess.run([exe, "-existence", "-sequence", q, "-mers", db, "-output", os.path.join(tmp, tag.split()[0] + ".txt")], capture_output=True, text=True, env=env)
+        p = subprocess.run([exe, "-threads", "16", "-existence", "-sequence", q, "-mers", db, "-output", os.path.join(tmp, tag.split()[0] + ".txt")], capture_output=True, text=True, env=env)
         dt = time.perf_counter() - t0
         print(json.dumps({"what": tag + " -existence (whole command)", "rc": p.returncode, "query_bases": 150 * min(n_reads, 400_000), "seconds": dt}), flush=True)
     a = open(os.path.join(tmp, "meryl-lookup-b200.txt"), "rb").read() if os.path.exists(os.path.join(tmp, "meryl-lookup-b200.txt")) else b"a"
