@@ -86,29 +86,37 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+SYNTH_BIN = os.path.join(ROOT, "oracle", "synth_reads")
+METRIC = "kmers_per_sec_meryl_count"
+
+
+def cpu_reads_file(path, first, n_reads, fmt):
+    """The bench's synthetic reads written by the CPU twin of the device generator (oracle/synth_reads.c, same bytes):
+    the reference arm never loads CUDA or libmeryl_b200.so."""
+    if not os.access(SYNTH_BIN, os.X_OK):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "synth_reads"], check=True)
+    subprocess.run([SYNTH_BIN, path, str(first), str(n_reads), str(READ_LEN), str(GENOME_LEN), repr(ERR), str(SEED), str(fmt)], check=True)
+
+
+def workload_name(gbp):
+    return ("meryl count k=%d canonical, %.2f Gbp of synthetic %d bp reads (3 Gbp uniform-random genome, both strands, %.1f%% substitutions)"
+            % (K, gbp, READ_LEN, ERR * 100))
+
+
 def reference_arm(args, world, rank):
-    """The reference's own CPU implementation (oracle/_ref/meryl) on a bounded sample of the workload."""
+    """The reference's own CPU implementation (the unmodified binary oracle/_ref/meryl, all host threads) on a bounded
+    prefix of the workload's reads, FASTQ file in /dev/shm -> database directory in /dev/shm, wall clock of the process.
+    This function must not import torch, CUDA or meryl_b200: the arm is the reference alone."""
     if rank != 0:
         return
-    import torch
-    import meryl_b200 as mb
     cores = os.cpu_count() or 1
     if not os.access(REF_BIN, os.X_OK):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/meryl not built"}))
         return
     n_reads = int(args.ref_gbp * 1e9) // READ_LEN
-    rec = mb.synth_record_bytes(READ_LEN, 1)
     tmp = tempfile.mkdtemp(prefix="merylref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     fq = os.path.join(tmp, "sample.fq")
-    with open(fq, "wb") as fh:
-        chunk = 2_000_000
-        dev = torch.empty(chunk * rec, dtype=torch.uint8, device="cuda")
-        for first in range(0, n_reads, chunk):
-            m = min(chunk, n_reads - first)
-            mb.synth_reads_device(dev.data_ptr(), first, m, READ_LEN, GENOME_LEN, ERR, SEED, 1)
-            torch.cuda.synchronize()
-            fh.write(dev[: m * rec].cpu().numpy().tobytes())
-        del dev
+    cpu_reads_file(fq, 0, n_reads, 1)
     n_kmers = n_reads * (READ_LEN - K + 1)
     times = []
     for it in range(args.warmup + args.steps):
@@ -126,17 +134,61 @@ def reference_arm(args, world, rank):
     subprocess.run(["rm", "-rf", tmp])
     ms = 1000 * sum(times) / len(times)
     val = n_kmers / (ms / 1000)
+    total_gbp = args.gbp if args.gbp > 0 else 100.0
     print(json.dumps({
-        "impl": "reference", "metric": "kmers_per_sec_end_to_end_meryl_count", "value": val, "unit": "k-mers/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "k-mers/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "meryl count k=%d, synthetic %d bp FASTQ (3 Gbp random genome, %.1f%% subst.), reference CPU binary on a %.2f Gbp prefix" % (K, READ_LEN, ERR * 100, args.ref_gbp),
-                   "k": K, "read_len": READ_LEN, "sample_gbp": args.ref_gbp},
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(total_gbp), "k": K, "read_len": READ_LEN, "sample_gbp": args.ref_gbp,
+                   "sample": "each step counts the first %.2f Gbp of the workload's reads (FASTQ in /dev/shm) with the unmodified reference binary" % args.ref_gbp},
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": cores, "kind": "reference",
-                         "sample": "first %d reads (%.2f Gbp) of the workload as a FASTQ file in /dev/shm, threads=%d memory=%d" % (n_reads, args.ref_gbp, cores, args.ref_memory_gb)},
+                         "sample": "first %d reads (%.2f Gbp) of the workload as a FASTQ file in /dev/shm, threads=%d memory=%d, process start to exit" % (n_reads, args.ref_gbp, cores, args.ref_memory_gb)},
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def cli_leg(gbp, local):
+    """Both command line tools on the SAME FASTQ file in /dev/shm, wall clock from process start to exit: what a user
+    who swaps `meryl` for `meryl-b200` sees (FASTQ parsing and the 129-file write included)."""
+    cores = os.cpu_count() or 1
+    n_reads = int(gbp * 1e9) // READ_LEN
+    n_kmers = n_reads * (READ_LEN - K + 1)
+    tmp = tempfile.mkdtemp(prefix="merylcli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    res = {"gbp": gbp, "kmers": n_kmers, "unit": "k-mers/s", "cores": cores,
+           "what": "k=%d count <FASTQ in /dev/shm> output <dir in /dev/shm>, same words for both tools, wall clock of the process" % K}
+    try:
+        fq = os.path.join(tmp, "reads.fq")
+        cpu_reads_file(fq, 0, n_reads, 1)
+        res["fastq_bytes"] = os.path.getsize(fq)
+        words = ["k=%d" % K, "threads=%d" % cores, "memory=64", "count", fq, "output"]
+        cli = os.path.join(ROOT, "meryl_b200", "meryl-b200")
+        env = dict(os.environ)
+        best = None
+        for it in range(2):                                           # first run warms the page cache and the driver
+            subprocess.run(["rm", "-rf", os.path.join(tmp, "gpu.meryl")])
+            t0 = time.perf_counter()
+            p = subprocess.run([cli] + words + [os.path.join(tmp, "gpu.meryl")], capture_output=True, text=True, env=env)
+            dt = time.perf_counter() - t0
+            if p.returncode != 0:
+                res["error"] = "meryl-b200: " + p.stderr[-300:]
+                return res
+            best = dt if best is None else min(best, dt)
+        res["b200_seconds"], res["b200_value"] = best, n_kmers / best
+        if os.access(REF_BIN, os.X_OK):
+            t0 = time.perf_counter()
+            p = subprocess.run([REF_BIN] + words + [os.path.join(tmp, "ref.meryl")], capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if p.returncode == 0:
+                res["reference_seconds"], res["reference_value"] = dt, n_kmers / dt
+                res["speedup"] = dt / best
+                same = subprocess.run(["diff", "-rq", os.path.join(tmp, "gpu.meryl"), os.path.join(tmp, "ref.meryl")], capture_output=True, text=True)
+                res["db_identical"] = (same.returncode == 0)
+            else:
+                res["reference_error"] = p.stderr[-300:]
+    finally:
+        subprocess.run(["rm", "-rf", tmp])
+    return res
 
 
 def main():
@@ -151,6 +203,7 @@ def main():
     ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena per GPU (0 = all free memory); small values keep ncu replays fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cli-gbp", type=float, default=5.0, help="size of the FASTQ file both command line tools count (e2e_cli leg, one GPU only; 0 = skip)")
     # the other BASELINE.json configs (parity-test cases, not the headline line): e.g. --k 31, or --k 51 --read-len 15000 --err 0.005 --gbp 50
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--read-len", type=int, default=READ_LEN)
@@ -162,18 +215,17 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.ref_gbp <= 0:
-        # the reference counts ~15 M k-mers/s on this host: keep (steps + warmup) runs within ~2.5 minutes
+        # the reference binary counts 60-110 M k-mers/s on the boxes seen so far (16-32 host threads): at least 1 Gbp per
+        # run (below that its start-up and teardown dominate), more when few runs are asked for; all runs within ~6 minutes
         runs = (args.steps + args.warmup) if args.impl == "reference" else 1
-        args.ref_gbp = max(0.1, min(0.6, 2.6 / max(1, runs)))
+        args.ref_gbp = max(1.0, min(2.0, 28.0 / max(1, runs)))
+
+    if args.impl == "reference":                    # the reference alone: no torch, no CUDA, no libmeryl_b200.so in this process
+        reference_arm(args, world, rank)
+        return
 
     import torch
     import torch.distributed as dist
-
-    if args.impl == "reference":
-        if rank == 0:
-            torch.cuda.set_device(0)
-        reference_arm(args, world, rank)
-        return
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -339,20 +391,28 @@ def main():
         except Exception:
             cpu = {"value": None, "unit": "k-mers/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + sub.stderr[-200:]}
 
+    # ---- the command line tools side by side on one FASTQ file (rank 0, one GPU) -----------------
+    cli = None
+    if rank == 0 and world == 1 and args.cli_gbp > 0:
+        try:
+            cli = cli_leg(args.cli_gbp, local)
+        except Exception as ex:
+            cli = {"error": repr(ex)[:300]}
+
     if rank == 0:
         print(json.dumps({
-            "metric": "kmers_per_sec_end_to_end_meryl_count", "value": value, "unit": "k-mers/s",
+            "metric": METRIC, "value": value, "unit": "k-mers/s",
+            "value_kind": "device_resident: the whole count with the packed reads already in HBM; `e2e` is the same job from host buffers through the C ABI, `e2e_cli` the command line tools on a FASTQ file",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "meryl count k=%d canonical, %.2f Gbp of synthetic %d bp reads (3 Gbp uniform-random genome, both strands, %.1f%% substitutions)%s"
-                                   % (K, total_reads * READ_LEN / 1e9, READ_LEN, ERR * 100, "; " + reduced if reduced else ""),
+            "config": {"workload": workload_name(total_reads * READ_LEN / 1e9) + ("; " + reduced if reduced else ""),
                        "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix, "key_bytes": stats.keyBytes,
                        "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
                        "l2": "inputs (%.1f GB store, %.1f GB keys per pass on rank 0) far exceed the 126 MB L2" % (stats.nBases * 0.375 / 1e9, stats.nKmers * 8 / max(1, stats.nPasses) / 1e9),
                        "parallelism": "reads split over %d GPU(s); 64 data files sharded by owner(f)=min(f,63-f) mod N, one NCCL all-to-all per pass" % world},
             "stage_ms": {"histogram": stats.msHistogram, "extract": stats.msExtract, "sort_hist": stats.msSortHist,
                          "sort": stats.msSort, "count": stats.msCount, "encode": stats.msEncode, "exchange": stats.msExchange},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_cli": cli, "clocks": clocks,
             "gpu_launches": int(stats.nLaunches),
         }))
     if world > 1:

@@ -821,8 +821,9 @@ int openMem(const MbDbImages *img, u32 k, u32 wPrefix, InputDb &db) {
 struct Carve {
   uint8_t *base; size_t size, off = 0;
   Carve(uint8_t *b, size_t s) : base(b), size(s) {}
-  void *take(size_t bytes) {
-    const size_t o = (off + 255) / 256 * 256;
+  void *take(size_t bytes) {                            //  256-byte aligned as an ADDRESS (the base may be any pointer)
+    const size_t mis = (size_t)((uintptr_t)base & 255);
+    const size_t o = (off + mis + 255) / 256 * 256 - mis;
     if (o + bytes > size) return nullptr;
     off = o + bytes;
     return base + o;
@@ -949,7 +950,7 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
     if (!dFileStart || !dErr) { rc = mb_fail(MB_ENOMEM, "device arena too small"); goto done; }
     MB_UCUDA(cudaMemsetAsync(dErr, 0, 256, s));
     MB_UTRY(setup(db, top, s));
-    const size_t fixedOff = top.off;
+    const size_t fixedOff = (top.off + 255) / 256 * 256;   //  the group carve starts here: keep its base aligned
 
     HostBuf host;
     u32 f0 = 0;
@@ -1497,7 +1498,7 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
     MB_UCUDA(cudaMemsetAsync(dHistSmall, 0, (size_t)MB_HIST_SMALL * 8, s));
     MB_UCUDA(cudaMemsetAsync(dCtl, 0, 64 * 8, s));
     MB_UCUDA(cudaMemsetAsync(dFileBase, 0, 64 * 8, s));
-    const size_t fixedOff = top.off;
+    const size_t fixedOff = (top.off + 255) / 256 * 256;   //  the group carve starts here: keep its base aligned
 
     PinnedRing ring;
     MB_UTRY(ring.init());

@@ -28,7 +28,7 @@ if passes > 1:
 
 configs = [(1, 1), (1, 0), (2, 1), (2, 0)]
 if len(sys.argv) > 3 and sys.argv[3] == "sortonly":          # the sweep kernel shapes, filter on
-    configs = [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (7, 0)]
+    configs = [(int(v), 0) for v in os.environ.get("MB_AB_SHAPES", "1,2,3,4,5,6,7").split(",")]
 extra = [{}]
 if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel striped/blocked x histogram single/joint (default sweep)
     configs = [(L.mb_dbg_sort_version(0), 0)]
