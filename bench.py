@@ -267,7 +267,7 @@ def main():
             c.comm_init(mbd.broadcast_unique_id(mb.Counter.comm_unique_id, device="cuda"))
         return c
 
-    chunk_reads = 4_000_000
+    chunk_reads = max(1, min(4_000_000, (600 << 20) // rec0))     # ~600 MB of base stream per generator call (15 kb reads: 40 k reads)
     dev_chunk = torch.empty(chunk_reads * rec0, dtype=torch.uint8, device="cuda")
 
     def ingest_device(c):

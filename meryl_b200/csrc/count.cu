@@ -141,7 +141,7 @@ const int C32_HALF   = CNT_THREADS * C32_ITEMS;                          //  16 
 __global__ void __launch_bounds__(CNT_THREADS, 4)
 count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nHalves,
                       u64 endIndex, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart,
-                      u64 *__restrict__ numDistinct, u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
+                      u64 *__restrict__ numDistinct, u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 pfDist) {
   __shared__ u32 warpTot[CNT_WARPS];
   __shared__ u64 sTile, sExcl;
 
@@ -156,6 +156,18 @@ count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restr
   const u32  n       = ti.n > half * C32_HALF ? min(ti.n - half * C32_HALF, (u32)C32_HALF) : 0;
   const u32  seg     = ti.seg & 0x7fffffffu;
   const bool segHead = (ti.seg >> 31) != 0 && half == 0;     //  the segment's very first key always starts a run
+
+  //  the keys of the half-tile claimed pfDist claims from now: HBM -> L2 (the kernel is a chain of dependent round trips
+  //  per 16 KB of keys -- claim, descriptor, keys, look-back -- so the DRAM part of the key load is taken out of it)
+  if (pfDist && rel + pfDist < nHalves && t < 128) {
+    const u64 rn = rel + pfDist;
+    const CountTileInfo tn = info[tileLo + (rn >> 1)];
+    const u32 hn = (u32)(rn & 1);
+    if (tn.n > hn * C32_HALF) {
+      const u32 nn = min(tn.n - hn * C32_HALF, (u32)C32_HALF);
+      if (t * 32 < nn) prefetch_l2(keys + tn.begin + (u64)hn * C32_HALF + t * 32);
+    }
+  }
 
   u32 key[C32_ITEMS];
   u32 heads = 0;
@@ -406,7 +418,8 @@ cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u6
   const bool striped = getenv("MB_COUNT_BLOCKED") == nullptr;
   if (striped)
     count_suffix32_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
-                                                                  binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
+                                                                  binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter,
+                                                                  getenv("MB_COUNT_PREFETCH") ? (u32)strtoul(getenv("MB_COUNT_PREFETCH"), nullptr, 10) : 0u);
   else
     count_suffix32b_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
                                                                    binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);

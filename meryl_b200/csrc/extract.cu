@@ -584,6 +584,236 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   }
 }
 
+//  ---- dense form of a filtered pass (k <= 32) ----------------------------------------------------------------------
+//
+//  extract_kernel's filtered pass walks a thread's members in a divergent loop (a thread has 0..32 members among its 32
+//  positions, the warp runs as long as its busiest lane: about half the lanes idle) and does everything per member twice
+//  (rank in phase A, k-mer in phase B).  Here the bit-sliced membership test stays per thread, but the members of the
+//  whole tile are COMPACTED into a list of positions first (one block scan of the per-thread member counts), and then
+//  consecutive lanes take consecutive members: every member gets its k-mer by direct window extraction from the
+//  shared-memory records ONCE, its rank inside (tile, bin) from one returning shared-memory atomic issued by full warps, and
+//  keeps (stored key, bin, rank) in registers over the bin scan; placement in the bin-sorted stage buffer and the coalesced
+//  copy-out are as before.  ITEMS = members per thread and round (CAP = 256 ITEMS members per round; a tile with more
+//  members takes another round -- rare, the host sizes ITEMS for 1.3x the expected share).
+//  Per tile of 8192 positions at one fifth kept: ~830 warp instructions per thread row instead of ~1350.
+template <bool S32, int ITEMS>
+__global__ void __launch_bounds__(256, ITEMS <= 16 ? 3 : 2)
+extract_dense_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : 1>::type *__restrict__ out,
+                     const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 nTiles) {
+  typedef typename KeyT<S32 ? 0 : 1>::type Stored;
+  typedef ExtractSmem<1, S32>              S;
+  const int THREADS = 256, CAP = THREADS * ITEMS;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  u64            *bar    = (u64 *)(smem + S::OFF_BAR);
+  u32            *rec[2] = { (u32 *)(smem + S::OFF_REC0), (u32 *)(smem + S::OFF_REC1) };
+  const u32       nT     = p.binHi - p.binLo;
+  u32            *cnt    = (u32 *)(smem + S::OFF_TABLES);
+  u32            *binOff = cnt + nT;
+  u64            *gofs   = (u64 *)(smem + S::OFF_TABLES + (((size_t)nT * 8 + 7) / 8) * 8);
+  unsigned short *plist  = (unsigned short *)(smem + S::OFF_TABLES + S::tablesBytes(nT));   //  CAP member positions of this round ...
+  unsigned short *sbin   = plist;                                                          //  ... later the staged keys' bins (S32)
+  Stored         *stage  = (Stored *)(((uintptr_t)(plist + CAP) + 15) & ~(uintptr_t)15);
+  __shared__ u32 sWarpSum[THREADS / 32];
+
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const u32 perFile  = 1u << (p.binBits - 6);
+  const u32 fLo = p.binLo / perFile, fHi = p.binHi / perFile;
+  const u32 binShift = 2 * p.k - p.binBits;
+
+#ifdef MB_CUSIM
+  if (threadIdx.x == 0 && blockIdx.x == 0 && getenv("CUSIM_TRACE"))
+    fprintf(stderr, "cusim: extract bins [%u,%u) of %u: dense, %d members per thread and round\n", p.binLo, p.binHi, 1u << p.binBits, ITEMS);
+#endif
+  if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  for (u32 b = t; b < nT; b += THREADS) cnt[b] = 0;
+  __syncthreads();
+
+  const unsigned char *storeBytes = (const unsigned char *)p.store;
+  u64 tile = blockIdx.x;
+  if (t == 0 && tile < nTiles) {
+    mbar_expect_tx(&bar[0], S::REC_BYTES);
+    tma_bulk_g2s(rec[0], storeBytes + tile * (u64)(THREADS * MB_STORE_REC_WORDS * 4), S::REC_BYTES, &bar[0]);
+  }
+
+  for (u32 it = 0; tile < nTiles; it++, tile += gridDim.x) {
+    const u32 buf = it & 1;
+    const u64 next = tile + gridDim.x;
+    if (t == 0 && next < nTiles) {                      //  rec[buf ^ 1] was last read before the barrier that ended the previous tile
+      fence_proxy_async();
+      mbar_expect_tx(&bar[buf ^ 1], S::REC_BYTES);
+      tma_bulk_g2s(rec[buf ^ 1], storeBytes + next * (u64)(THREADS * MB_STORE_REC_WORDS * 4), S::REC_BYTES, &bar[buf ^ 1]);
+    }
+    while (!mbar_try_wait(&bar[buf], (it >> 1) & 1)) { }
+
+    //  members of this pass among my 32 positions, as a slot mask (slot q's top bit = bit 63 - 2q)
+    u64 cand = 0;
+    {
+      const u32 *r = rec[buf] + t * MB_STORE_REC_WORDS;
+      const u32 valid = windows_valid(r[2], r[5], r[8], p.k);
+      if (valid) {
+        Window w;
+        w.w0 = ((u64)r[0] << 32) | r[1];
+        w.w1 = ((u64)r[3] << 32) | r[4];
+        w.w2 = ((u64)r[6] << 32) | r[7];
+        u64 v = valid;                                  //  bit 31 - q  ->  bit 63 - 2q
+        v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+        v = (v | (v << 8))  & 0x00ff00ff00ff00ffull;
+        v = (v | (v << 4))  & 0x0f0f0f0f0f0f0f0full;
+        v = (v | (v << 2))  & 0x3333333333333333ull;
+        v = (v | (v << 1))  & 0x5555555555555555ull;
+        cand = file_range_slots(w, p.k, p.mode, fLo, fHi) & (v << 1);
+      }
+    }
+    const u32 mine = (u32)__popcll((long long)cand);
+    u32 incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32)o) incl += x;
+    }
+    if (lane == 31) sWarpSum[warp] = incl;
+    __syncthreads();
+    u32 base = incl - mine, total = 0;
+    for (u32 wi = 0; wi < THREADS / 32; wi++) { const u32 ws = sWarpSum[wi]; if (wi < warp) base += ws; total += ws; }
+
+    for (u32 round0 = 0; round0 < total; round0 += CAP) {          //  (uniform over the CTA; one round unless the tile is unusually full)
+      const u32 nR = min((u32)CAP, total - round0);
+      {                                                            //  my members whose place in the tile's list falls into this round
+        u32 idx = base;
+        for (u64 m = cand; m; idx++) {
+          const u32 b = __clzll((long long)m);
+          m &= ~(0x8000000000000000ull >> b);
+          if (idx - round0 < (u32)CAP) plist[idx - round0] = (unsigned short)(t * 32 + (b >> 1));   //  (unsigned: idx < round0 wraps)
+        }
+      }
+      __syncthreads();
+
+      //  dense: consecutive lanes, consecutive members
+      Stored sk[ITEMS];
+      u32    br[ITEMS];                                            //  bin (relative to the pass) << 16 | rank inside (tile, bin)
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++) {
+        const u32 j = (u32)i * THREADS + t;
+        if (j < nR) {
+          const u32 pos = plist[j];
+          const u32 *r  = rec[buf] + (pos >> 5) * MB_STORE_REC_WORDS;
+          const u32 q2  = 2 * (pos & 31);
+          const u64 a   = ((u64)r[0] << 32) | r[1], b = ((u64)r[3] << 32) | r[4];
+          const u64 f   = (q2 ? ((a << q2) | (b >> (64 - q2))) : a) >> (64 - 2 * p.k);              //  k bases from the position on
+          u64 key = f;
+          if (p.mode != MB_MODE_FORWARD) {
+            const u64 rc = revcomp64(f, p.k);
+            key = (p.mode == MB_MODE_REVERSE) ? rc : (f < rc ? f : rc);
+          }
+          const u32 bin = (u32)(key >> binShift) - p.binLo;
+          to_stored(key, sk[i]);
+          br[i] = (bin << 16) | atomicAdd(&cnt[bin], 1u);
+        }
+      }
+      __syncthreads();
+
+      //  the round's bin counts -> place of every bin's run in the stage buffer, and one global atomic per non-empty
+      //  bin reserves its run in the bin's segment
+      {
+        const u32 perThread = (nT + THREADS - 1) / THREADS;
+        const u32 b0 = t * perThread;
+        u32 mySum = 0;
+        for (u32 i = 0; i < perThread; i++) { const u32 b = b0 + i; if (b < nT) mySum += cnt[b]; }
+        u32 inc2 = mySum;
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 x = __shfl_up_sync(0xffffffffu, inc2, o);
+          if (lane >= (u32)o) inc2 += x;
+        }
+        __syncthreads();                                           //  (sWarpSum is read above by everybody)
+        if (lane == 31) sWarpSum[warp] = inc2;
+        __syncthreads();
+        u32 run = inc2 - mySum;
+        for (u32 wi = 0; wi < warp; wi++) run += sWarpSum[wi];
+        for (u32 i = 0; i < perThread; i++) {
+          const u32 b = b0 + i;
+          if (b < nT) {
+            const u32 c = cnt[b];
+            binOff[b] = run;
+            if (c) {
+              gofs[b] = binStart[p.binLo + b] + atomicAdd((unsigned long long *)&binCursor[p.binLo + b], (unsigned long long)c) - run;
+              cnt[b]  = 0;
+            }
+            run += c;
+          }
+        }
+      }
+      __syncthreads();
+
+      //  bin-sorted stage buffer (the list of positions is dead: its memory takes the staged keys' bins)
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++) {
+        const u32 j = (u32)i * THREADS + t;
+        if (j < nR) {
+          const u32 bin = br[i] >> 16;
+          const u32 pos = binOff[bin] + (br[i] & 0xffffu);
+          stage[pos] = sk[i];
+          if (S32) sbin[pos] = (unsigned short)bin;
+        }
+      }
+      __syncthreads();
+
+      //  copy-out: consecutive threads, consecutive staged keys -> every bin's run is written coalesced
+      for (u32 j = t; j < nR; j += THREADS) {
+        const Stored k2 = stage[j];
+        const u32 bin = S32 ? (u32)sbin[j] : (u32)(key_shr64(k2, binShift)) - p.binLo;
+        out[gofs[bin] + j] = k2;
+      }
+      __syncthreads();                                             //  stage / list / tables are reused by the next round or tile
+    }
+    __syncthreads();                                               //  (tiles without members: all reads of rec[buf] are done)
+  }
+}
+
+template <bool S32, int ITEMS>
+cudaError_t launch_dense(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, cudaStream_t s) {
+  typedef ExtractSmem<1, S32> S;
+  typedef typename KeyT<S32 ? 0 : 1>::type Stored;
+  const u32 nT = p.binHi - p.binLo;
+  const size_t smem = S::OFF_TABLES + S::tablesBytes(nT) + (size_t)256 * ITEMS * 2 + 16 + (size_t)256 * ITEMS * sizeof(Stored) + 16;
+  auto kern = extract_dense_kernel<S32, ITEMS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, perSm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 256, smem);
+  if (e != cudaSuccess) return e;
+  if (perSm < 1) perSm = 1;
+  const u64 nRecords = p.nPositions / 32;
+  const u64 nTiles   = (nRecords + 255) / 256;
+  if (nTiles == 0) return cudaSuccess;
+  u64 grid = (u64)sms * perSm;
+  if (grid > nTiles) grid = nTiles;
+  kern<<<(unsigned)grid, 256, smem, s>>>(p, (Stored *)out, binStart, binCursor, nTiles);
+  return cudaGetLastError();
+}
+
+//  Does this pass take the dense form?  k <= 32, file-aligned bins, a minority (or a small majority) of the k-mers kept.
+static bool dense_pass(const MbExtractParams &p) {
+  const bool off = getenv("MB_EXTRACT_DENSE") && getenv("MB_EXTRACT_DENSE")[0] == '0';      //  A/B: the divergent form of extract_kernel
+  if (off || p.k > 32 || p.k < 5 || p.binBits < 6 || p.binBits > 10 || p.noPrefilter || p.rankMatch || p.prof) return false;
+  const u32 perFile = 1u << (p.binBits - 6), nBins = 1u << p.binBits;
+  if ((p.binLo & (perFile - 1)) || (p.binHi & (perFile - 1)) || p.binHi - p.binLo >= nBins) return false;
+  const u32 kept = p.keptPerMille ? p.keptPerMille : (p.binHi - p.binLo) * 1000 / nBins;
+  return kept <= 600;
+}
+
+template <bool S32>
+cudaError_t launch_dense_sized(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, cudaStream_t s) {
+  const u32 kept = p.keptPerMille ? p.keptPerMille : (p.binHi - p.binLo) * 1000 / (1u << p.binBits);
+  u32 want = (u32)(8192ull * kept / 1000 * 13 / 10);                //  1.3 x the expected members of a tile (every position a k-mer)
+  if (getenv("MB_DENSE_ITEMS")) want = 256 * (u32)strtoul(getenv("MB_DENSE_ITEMS"), nullptr, 10);   //  testing knob: small values force several rounds per tile
+  if (want <= 256 * 8)  return launch_dense<S32, 8 >(p, out, binStart, binCursor, s);
+  if (want <= 256 * 12) return launch_dense<S32, 12>(p, out, binStart, binCursor, s);
+  if (want <= 256 * 16) return launch_dense<S32, 16>(p, out, binStart, binCursor, s);
+  return launch_dense<S32, 24>(p, out, binStart, binCursor, s);
+}
+
 template <int KW, bool COUNT_ONLY, bool S32, bool MATCH = false>
 cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, u64 *binCount, cudaStream_t s) {
   typedef ExtractSmem<KW, S32> S;
@@ -630,6 +860,13 @@ cudaError_t mb_launch_bin_histogram(const MbExtractParams &p, u64 *dBinCount, cu
 }
 
 cudaError_t mb_launch_extract(const MbExtractParams &p, void *dKeys, const u64 *dBinStart, u64 *dBinCursor, cudaStream_t s) {
+  if (dense_pass(p)) {
+    if (p.suffix32) {
+      if (2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;
+      return launch_dense_sized<true>(p, dKeys, dBinStart, dBinCursor, s);
+    }
+    return launch_dense_sized<false>(p, dKeys, dBinStart, dBinCursor, s);
+  }
   if (p.rankMatch) {                                     //  experimental ranking without returning atomics
     if (p.suffix32) {
       if (p.k > 32 || 2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;

@@ -97,6 +97,13 @@ __host__ __device__ __forceinline__ u64 key_shr64(const ulonglong2 &k, u32 shift
 #define MB_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
 #endif
 
+//  One 128-byte line on its way from HBM to L2 (no register, no wait): what a CTA does for the tile a LATER CTA will load.
+#ifdef MB_CUSIM
+__device__ __forceinline__ void prefetch_l2(const void *) { }
+#else
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+#endif
+
 #ifdef MB_CUSIM   //  host emulator used by the CPU tests (tests/cusim): a polling load lets the other fibers run
 __device__ __forceinline__ u64  ld_volatile_u64(const u64 *p)  { cusim::yield(); return *(const volatile u64 *)p; }
 __device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) { *(volatile u64 *)p = v; cusim::g_progress++; }

@@ -45,6 +45,9 @@ namespace {
 const int SORT_THREADS = 256;
 const int SORT_WARPS   = SORT_THREADS / 32;
 const int SORT_MAX_PASSES = 24;
+#ifndef MB_SWEEP_PREFETCH_DEFAULT
+#define MB_SWEEP_PREFETCH_DEFAULT 0      //  tiles ahead; measured A/B decides (MB_SWEEP_PREFETCH)
+#endif
 
 template <int KW> struct SortShape;
 //  MIN_CTAS: resident CTAs per SM the register budget is compiled for; ~68 KB of shared memory per CTA
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(SweepShape<VER>::THREADS, SweepShape<VER>::MIN
 sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                    const TileInfo *__restrict__ info,
                    const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, u32 wide,
-                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
+                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch, u64 nTiles, u32 pfDist) {
   typedef SweepX<KW, VER> S;
   extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
   __shared__ u32  binOff[S::RADIX + 1];
@@ -802,6 +805,13 @@ sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
 
   const u64 tile = sTile;
   const TileInfo ti = info[tile];
+  //  The keys of the tile that is claimed pfDist tiles from now start their way from HBM to L2 (one 128-byte line per
+  //  thread and round): the CTA that gets that tile then waits for L2, not for DRAM, in front of an otherwise idle tile.
+  if (pfDist && tile + pfDist < nTiles) {
+    const TileInfo tn = info[tile + pfDist];
+    const unsigned char *p0 = (const unsigned char *)(in + tn.begin);
+    for (u32 o = threadIdx.x * 128; o < tn.n * (u32)sizeof(typename KeyT<KW>::type); o += S::THREADS * 128) prefetch_l2(p0 + o);
+  }
   const u32  seg     = ti.seg & 0x7fffffffu;
   const bool isFirst = (ti.seg >> 31) != 0;
   SweepXShared sm;
@@ -1019,10 +1029,12 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 5>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 6>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortp_sweep_kernel<KW, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 7>::BYTES)) != cudaSuccess) return e;
+  //  MB_SWEEP_PREFETCH=<tiles>: L2 prefetch distance of the sweep kernel (0 = off)
+  const u32 pfDist = getenv("MB_SWEEP_PREFETCH") ? (u32)strtoul(getenv("MB_SWEEP_PREFETCH"), nullptr, 10) : MB_SWEEP_PREFETCH_DEFAULT;
   for (u32 p = 0; p < plan.nPasses; p++) {
 #define MB_SX_LAUNCH(V) do { typedef SweepX<KW, V> SX;                                                                                         \
       sortx_sweep_kernel<KW, V><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                       \
-                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1); } while (0)
+                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1, nTiles, pfDist); } while (0)
     if      (version == 2) MB_SX_LAUNCH(2);
     else if (version == 3) MB_SX_LAUNCH(3);
     else if (version == 4) MB_SX_LAUNCH(4);

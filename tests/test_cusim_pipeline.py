@@ -103,6 +103,15 @@ def test_sim_multi_pass_prefilter(tmp_path, monkeypatch, k, w_prefix, op):
     _vs_oracle(tmp_path, {"r.fq": reads, "odd.fa": odd + synth.fasta_bytes(2, 3_000, k)}, k, w_prefix, op=op, min_passes=3)
 
 
+@pytest.mark.parametrize("k,w_prefix,op", [(21, 12, "count"), (31, 9, "count-forward"), (18, 10, "count-reverse")])
+def test_sim_dense_extraction_rounds(tmp_path, monkeypatch, k, w_prefix, op):
+    """The dense form of a filtered pass (extract_dense_kernel) when a tile holds more members than one round takes:
+    two passes of about half the k-mers each, 8 members per thread and round -> two rounds per tile."""
+    monkeypatch.setenv("MB_MAX_PASS_KEYS", "300000")
+    monkeypatch.setenv("MB_DENSE_ITEMS", "1")
+    _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 177 + k)}, k, w_prefix, op=op, min_passes=2)
+
+
 def test_sim_multi_pass_rolling(tmp_path, monkeypatch):
     """The same kind of passes through the rolling path (filter switched off)."""
     monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")

@@ -36,8 +36,12 @@ if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel stri
 if len(sys.argv) > 3 and sys.argv[3] == "experiments":       # things written without a GPU at hand, to be measured
     configs = [(L.mb_dbg_sort_version(0), 0)]
     extra = [{}, {"MB_RANK_MATCH": "1"}]                     # (MB_OVERLAP_D2H needs host images: measure it with bench.py's e2e leg)
+if len(sys.argv) > 3 and sys.argv[3] == "env":               # any list of environments: MB_AB_ENVS='[{}, {"MB_X": "1"}, ...]' (default sweep)
+    configs = [(L.mb_dbg_sort_version(0), 0)]
+    extra = json.loads(os.environ.get("MB_AB_ENVS", "[{}]"))
+touched = set(k for e in extra for k in e) | {"MB_COUNT_BLOCKED", "MB_HIST_JOINT", "MB_RANK_MATCH"}
 for (sort_v, nofilter), env in [(c, e) for c in configs for e in extra]:
-    for k in ("MB_COUNT_BLOCKED", "MB_HIST_JOINT", "MB_RANK_MATCH"):
+    for k in touched:
         os.environ.pop(k, None)
     os.environ.update(env)
     L.mb_dbg_sort_version(sort_v)
