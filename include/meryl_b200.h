@@ -122,6 +122,12 @@ uint64_t mb_estimate_kmers_in_file(const char *path);
 int  mb_create(const mb_config *cfg, mb_ctx **ctx);
 void mb_destroy(mb_ctx *ctx);
 
+/*  A process keeps one device arena per GPU between contexts (a service counting job after job allocates its memory
+ *  once; with several GPUs the peers' mappings of an arena stay valid from job to job).  The reference frees its
+ *  buckets when countThreads returns (src/meryl/merylOp-countThreads.C:466-473); this is the explicit form of that for
+ *  a caller that wants the device memory back before the process ends.  MB_NO_ARENA_CACHE=1 disables the cache.  */
+void mb_release_device_memory(void);
+
 /*  Input.  All forms append to the same logical base stream ("record . record . ...",
  *  src/meryl/merylOp-countThreads.C:139-231); they may be mixed and called repeatedly.  */
 int mb_add_bases(mb_ctx *ctx, const char *bases, uint64_t len, int endOfSequence);  /*  host memory   */

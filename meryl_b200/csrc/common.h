@@ -116,3 +116,6 @@ struct MbMergeEndpoints {
 };
 int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir,
                       int32_t device, uint64_t workspaceBytes, mb_union_stats *st, const MbMergeEndpoints *ends);
+
+//  engine.cu: free the device arena a finished count context left behind (device < 0: on every device)
+void mb_arena_cache_release(int device);

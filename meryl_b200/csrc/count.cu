@@ -225,6 +225,106 @@ count_suffix32_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restr
   }
 }
 
+//  Grouped form (default; MB_COUNT_GROUP=1 keeps the kernel above for A/B).  ncu of the kernel above: 7.7 % of the issue slots
+//  busy, 53 % of the stall samples at the barrier behind the look-back and 26 % on the key loads -- a CTA is a chain of
+//  dependent round trips (claim, descriptor, keys, look-back, stores) for 16 KB of keys.  Here a CTA takes G consecutive
+//  half-tiles (64 KB of keys for G = 4) with ONE claim and ONE look-back: a first sweep over its keys counts the run heads
+//  per (half-tile, warp), the look-back resolves the CTA's exclusive distinct count, a second sweep -- the keys come from
+//  L2 now, every resident CTA's 64 KB together are far below its 126 MB -- writes the heads.  Twice the instructions per
+//  key (still far below what the memory system can feed), a quarter of the chains.
+template <int G, bool WRITE>
+__device__ __forceinline__ u32
+count32_half(const u32 *__restrict__ keys, const CountTileInfo &ti, u32 half, u32 lane, u32 warp,
+             u64 outBase, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart) {
+  const u64  begin   = ti.begin + (u64)half * C32_HALF;
+  const u32  n       = ti.n > half * C32_HALF ? min(ti.n - half * C32_HALF, (u32)C32_HALF) : 0;
+  const bool segHead = (ti.seg >> 31) != 0 && half == 0;     //  the segment's very first key always starts a run
+  const u32  wbase   = warp * 32 * C32_ITEMS;
+  if (wbase >= n) return 0;                                   //  (warp-uniform)
+  u32 key[C32_ITEMS];
+#pragma unroll
+  for (int i = 0; i < C32_ITEMS; i++) {
+    const u32 j = wbase + i * 32 + lane;
+    key[i] = j < n ? keys[begin + j] : 0;
+  }
+  u32 carry = 0;
+  if (lane == 0 && !(segHead && wbase == 0)) carry = keys[begin + wbase - 1];
+  const u64 hiBits = (u64)(binLo + (ti.seg & 0x7fffffffu)) << suffixBits;     //  (binLo may have wrapped below zero: 32-bit sum)
+  u32 wrun = 0;
+#pragma unroll
+  for (int i = 0; i < C32_ITEMS; i++) {
+    const u32 j = wbase + i * 32 + lane;
+    u32 prev = __shfl_up_sync(0xffffffffu, key[i], 1);
+    if (lane == 0) prev = carry;
+    const bool head = j < n && ((segHead && j == 0) || key[i] != prev);
+    const u32  b    = __ballot_sync(0xffffffffu, head);
+    if (WRITE && head) {
+      const u64 o = outBase + wrun + __popc(b & ((1u << lane) - 1));
+      uniq[o]     = hiBits | key[i];
+      runStart[o] = begin + j;
+    }
+    wrun += __popc(b);
+    carry = __shfl_sync(0xffffffffu, key[i], 31);
+  }
+  return wrun;
+}
+
+template <int G>
+__global__ void __launch_bounds__(CNT_THREADS, 4)
+count_suffix32g_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nHalves,
+                       u64 endIndex, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart,
+                       u64 *__restrict__ numDistinct, u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
+  __shared__ u32 warpTot[G][CNT_WARPS];
+  __shared__ u64 sTile, sExcl;
+  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
+  __syncthreads();
+  const u64 rel = sTile;                                     //  group of G half-tiles, in claim order
+  const u64 nGroups = (nHalves + G - 1) / G;
+  const u64 h0 = rel * G;
+  const u32 nH = (u32)min((u64)G, nHalves - h0);
+
+  CountTileInfo ti[G];
+#pragma unroll
+  for (int g = 0; g < G; g++) if ((u32)g < nH) ti[g] = info[tileLo + ((h0 + g) >> 1)];
+
+  //  first sweep: run heads per (half-tile, warp)
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    u32 c = 0;
+    if ((u32)g < nH) c = count32_half<G, false>(keys, ti[g], (u32)((h0 + g) & 1), lane, warp, 0, 0, suffixBits, uniq, runStart);
+    if (lane == 0) warpTot[g][warp] = c;
+  }
+  __syncthreads();
+
+  u32 myOff[G], tot = 0;                                      //  heads before my warp's share of half-tile g, inside this CTA
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+#pragma unroll
+    for (int w = 0; w < CNT_WARPS; w++) { if (w == (int)warp) myOff[g] = tot; tot += warpTot[g][w]; }
+  }
+
+  if (warp == 0) {
+    if (lane == 0) st_volatile_u64(status + rel, (rel == 0 ? MB_ST_INC : MB_ST_AGG) | tot);
+    const u64 excl = lookback_warp(status, rel, lane);
+    if (lane == 0) {
+      if (rel != 0) st_volatile_u64(status + rel, MB_ST_INC | (excl + tot));
+      sExcl = excl;
+      if (rel + 1 == nGroups) {                              //  last group: total and sentinel
+        *numDistinct = excl + tot;
+        runStart[excl + tot] = endIndex;
+      }
+    }
+  }
+  __syncthreads();
+
+  //  second sweep: the same walk, writing
+#pragma unroll
+  for (int g = 0; g < G; g++)
+    if ((u32)g < nH) count32_half<G, true>(keys, ti[g], (u32)((h0 + g) & 1), lane, warp, sExcl + myOff[g], binLo, suffixBits, uniq, runStart);
+}
+
 //  Second form of the same kernel (MB_COUNT_BLOCKED=1; NOT the default: measured 40 % slower on B200): blocked keys.
 //  The striped form above spends three warp collectives per 32 keys (shuffle for the predecessor, ballot, shuffle
 //  for the carry).  Here a warp transposes its rows through shared memory so that every thread owns 16 CONSECUTIVE
@@ -416,7 +516,12 @@ cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u6
   //  Measured on B200 (profiles/r1_ab_8gbp_countopts.jsonl): the striped form takes 36 ms per 6.9 G keys, the blocked form 50 ms
   //  (its transposition through shared memory costs more than the collectives it saves) -- striped is the default.
   const bool striped = getenv("MB_COUNT_BLOCKED") == nullptr;
-  if (striped)
+  const u32  group   = getenv("MB_COUNT_GROUP") ? (u32)strtoul(getenv("MB_COUNT_GROUP"), nullptr, 10) : 4u;
+  if (striped && group >= 2) {
+    if (group >= 8)      count_suffix32g_kernel<8><<<(unsigned)((nHalves + 7) / 8), CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
+    else if (group >= 4) count_suffix32g_kernel<4><<<(unsigned)((nHalves + 3) / 4), CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
+    else                 count_suffix32g_kernel<2><<<(unsigned)((nHalves + 1) / 2), CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
+  } else if (striped)
     count_suffix32_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
                                                                   binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter,
                                                                   getenv("MB_COUNT_PREFETCH") ? (u32)strtoul(getenv("MB_COUNT_PREFETCH"), nullptr, 10) : 0u);

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <thread>
@@ -155,17 +156,52 @@ extern "C" int mb_create(const mb_config *cfg, mb_ctx **out) {
 }
 
 
+//  A process keeps ONE arena per device between contexts (and its two page-locked staging buffers): a service that counts job
+//  after job allocates its ~170 GB once, and -- what made this necessary -- the peers' CUDA-IPC mappings of an arena stay valid
+//  from job to job (measured on two B200s: mapping and unmapping a 170 GB peer arena costs ~1.8 s per job, as much as the
+//  whole count).  mb_destroy hands the arena back here; mb_release_device_memory() (or MB_NO_ARENA_CACHE=1) frees it; the
+//  other entry points that size their own arenas from the free memory (set operations, lookup) release it first.
+namespace {
+struct ArenaSlot { uint8_t *arena = nullptr; size_t bytes = 0; char *hStage[2] = { nullptr, nullptr }; };
+std::mutex g_arenaMu;
+ArenaSlot  g_arenaSlot[64];
+bool arenaCacheOn(void) { return getenv("MB_NO_ARENA_CACHE") == nullptr; }
+void freeSlot(ArenaSlot &a) {
+  if (a.arena) cudaFree(a.arena);
+  for (int i = 0; i < 2; i++) if (a.hStage[i]) cudaFreeHost(a.hStage[i]);
+  a = ArenaSlot();
+}
+}  //  namespace
+
+void mb_arena_cache_release(int device) {                 //  device < 0: all
+  std::lock_guard<std::mutex> lk(g_arenaMu);
+  int cur = 0;  cudaGetDevice(&cur);
+  for (int d = 0; d < 64; d++)
+    if ((device < 0 || d == device) && g_arenaSlot[d].arena) { cudaSetDevice(d); freeSlot(g_arenaSlot[d]); }
+  cudaSetDevice(cur);
+}
+
+extern "C" void mb_release_device_memory(void) { mb_arena_cache_release(-1); }
+
 extern "C" void mb_destroy(mb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->comm) mb_comm_destroy(c->comm);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 2; i++) {
-    if (c->hStage[i]) cudaFreeHost(c->hStage[i]);
     if (c->evH2D[i])  cudaEventDestroy(c->evH2D[i]);
     if (c->evIngest[i]) cudaEventDestroy(c->evIngest[i]);
   }
-  if (c->arena)  cudaFree(c->arena);
+  {
+    ArenaSlot mine;
+    mine.arena = c->arena;  mine.bytes = c->arenaBytes;  mine.hStage[0] = c->hStage[0];  mine.hStage[1] = c->hStage[1];
+    std::lock_guard<std::mutex> lk(g_arenaMu);
+    if (c->arena && arenaCacheOn() && c->device >= 0 && c->device < 64 && cudaPeekAtLastError() == cudaSuccess) {
+      ArenaSlot &a = g_arenaSlot[c->device];
+      if (a.arena && a.bytes >= mine.bytes) freeSlot(mine);                //  keep the larger one
+      else { freeSlot(a); a = mine; }
+    } else freeSlot(mine);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -178,6 +214,18 @@ extern "C" void mb_destroy(mb_ctx *c) {
 static int ensureArena(mb_ctx *c) {
   if (c->arena) return MB_OK;
   MB_CUDA(cudaSetDevice(c->device));
+  if (c->device >= 0 && c->device < 64) {                  //  the arena the previous context on this device left behind
+    std::lock_guard<std::mutex> lk(g_arenaMu);
+    ArenaSlot &a = g_arenaSlot[c->device];
+    if (a.arena) {
+      const size_t wantB = c->cfg.workspaceBytes / kAlign * kAlign;
+      if (arenaCacheOn() && (c->cfg.workspaceBytes == 0 ? a.bytes >= ((size_t)8 << 30) : a.bytes == wantB)) {
+        c->arena = a.arena;  c->arenaBytes = a.bytes;
+        for (int i = 0; i < 2; i++) c->hStage[i] = a.hStage[i];
+        a = ArenaSlot();
+      } else freeSlot(a);
+    }
+  }
   size_t freeB = 0, totalB = 0;
   MB_CUDA(cudaMemGetInfo(&freeB, &totalB));
   const size_t margin = (size_t)(c->cfg.worldSize > 1 ? 4 : 2) << 30;
@@ -185,15 +233,17 @@ static int ensureArena(mb_ctx *c) {
   if (want == 0) want = freeB > margin + ((size_t)1 << 30) ? freeB - margin : freeB / 2;
   if (want > freeB) want = freeB;
   want = want / kAlign * kAlign;
-  if (want < ((size_t)256 << 20)) return mb_fail(MB_ENOMEM, "only %zu bytes of device memory free", freeB);
-  if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
-    cudaGetLastError();
-    c->arena = nullptr;
-    return mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want);
+  if (!c->arena) {
+    if (want < ((size_t)256 << 20)) return mb_fail(MB_ENOMEM, "only %zu bytes of device memory free", freeB);
+    if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
+      cudaGetLastError();
+      c->arena = nullptr;
+      return mb_fail(MB_ENOMEM, "cannot allocate a %zu byte device arena", want);
+    }
+    c->arenaBytes = want;
   }
-  c->arenaBytes = want;
   for (int i = 0; i < 2; i++) {
-    MB_CUDA(cudaMallocHost((void **)&c->hStage[i], kStageBytes));
+    if (!c->hStage[i]) MB_CUDA(cudaMallocHost((void **)&c->hStage[i], kStageBytes));
     c->dStage[i] = c->arena + c->arenaBytes - (size_t)(i + 1) * kStageBytes;
   }
   c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
@@ -684,22 +734,38 @@ static int runCount(mb_ctx *c) {
   //  Experimental (MB_MULTI_SUFFIX32=1, not the default until it has run on real GPUs): on several GPUs, too, a k-mer
   //  travels and is sorted as the 32 bits below its prefix bin when they fit a word (k <= 21).  Routing is then by bin,
   //  so everybody also learns everybody's per-bin counts.
-  const bool want32 = world > 1 && getenv("MB_MULTI_SUFFIX32") != nullptr && 2 * k - binBits <= 32 && !c->stopAfterSort;
+  auto envOff = [](const char *name) { const char *e = getenv(name); return e && e[0] == '0'; };
+  const bool want32 = world > 1 && !envOff("MB_MULTI_SUFFIX32") && 2 * k - binBits <= 32 && !c->stopAfterSort;
 
   //  Experimental (MB_P2P_SCATTER=1, not the default until it has run on real GPUs): extraction fused with the exchange.
   //  Every rank maps every other rank's arena (CUDA IPC) and the extraction kernel stores a kept k-mer straight into the
   //  receive segment of the GPU that owns its file -- the bin's "start" handed to the kernel is the peer address expressed
   //  as an index relative to the local key buffer, so the kernel itself does not change.  The k-mers cross NVLink tile by
   //  tile under the extraction; no send buffer is filled and no all-to-all follows.
-  const bool p2p = world > 1 && getenv("MB_P2P_SCATTER") != nullptr;
+  bool p2p = world > 1 && !envOff("MB_P2P_SCATTER");
   struct PeerMap {
     MbComm *comm = nullptr;  std::vector<uint8_t *> base;
     ~PeerMap() { if (comm) mb_comm_close_peer_arenas(comm, base.data()); }
   } peers;
   if (p2p) {
+    //  Every rank tries to map every other rank's arena; the ranks then agree: if one of them could not (no peer access
+    //  between two of the GPUs, a rank in another container), all of them route through the NCCL all-to-all instead.
     peers.base.assign(world, nullptr);
-    MB_TRY(mb_comm_open_peer_arenas(c->comm, c->arena, dCtl->allFileCount, peers.base.data(), s));
+    const int orc = mb_comm_open_peer_arenas(c->comm, c->arena, dCtl->allFileCount, peers.base.data(), s);
     peers.comm = c->comm;
+    const u64 mine = orc == MB_OK ? 1 : 0;
+    std::vector<u64> all(world, 0);
+    MB_CUDA(cudaMemcpyAsync(dCtl->fileCount, &mine, 8, cudaMemcpyHostToDevice, s));
+    MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 1, s));
+    MB_CUDA(cudaMemcpyAsync(all.data(), dCtl->allFileCount, (size_t)world * 8, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    for (u32 r = 0; r < world; r++) if (!all[r]) p2p = false;
+    if (!p2p) {
+      mb_comm_close_peer_arenas(c->comm, peers.base.data());
+      peers.comm = nullptr;
+      mb_clear_error();
+      if (getenv("MB_TRACE")) fprintf(stderr, "[meryl-b200] rank %u: no peer mapping on every rank, routing through NCCL\n", me);
+    }
   }
   std::vector<u64> Cb;                                  //  Cb[r][b]
   std::vector<u64> binTotal;

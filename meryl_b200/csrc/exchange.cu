@@ -71,6 +71,8 @@ int loadNccl(void) {
 struct MbComm {
   ncclComm_p comm = nullptr;
   u32 rank = 0, world = 1;
+  std::vector<unsigned char> peerHandle;                     //  world x 64 bytes: the CUDA-IPC handle behind peerPtr[r]
+  std::vector<void *>        peerPtr;                        //  rank r's arena in this process (nullptr: not mapped)
 };
 
 #ifdef MB_CUSIM
@@ -107,6 +109,9 @@ static MbComm *g_processComm = nullptr;
 
 void mb_comm_destroy(MbComm *m) {
   if (!m || m == g_processComm) return;                      //  the process-wide communicator lives until exit
+#ifndef MB_CUSIM
+  for (void *p : m->peerPtr) if (p) cudaIpcCloseMemHandle(p);
+#endif
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   delete m;
 }
@@ -311,16 +316,23 @@ int mb_comm_open_peer_arenas(MbComm *m, void *myArena, u64 *dScratch, uint8_t **
   MB_TRY(mb_comm_allgather_u64(m, dScratch, dScratch + 8, 8, s));
   MB_CUDA(cudaMemcpyAsync(all.data(), dScratch + 8, (size_t)world * 64, cudaMemcpyDeviceToHost, s));
   MB_CUDA(cudaStreamSynchronize(s));
+  //  A mapping outlives the job (measured: opening and closing a 170 GB peer arena costs ~1.8 s, per peer and job): the
+  //  ranks keep their arenas between contexts (engine.cu), so the same handle comes back and the mapping is reused; a
+  //  different handle (the peer allocated a new arena) replaces it.
+  if (m->peerHandle.size() != (size_t)world * 64) { m->peerHandle.assign((size_t)world * 64, 0); m->peerPtr.assign(world, nullptr); }
   for (u32 r = 0; r < world; r++) peerBase[r] = nullptr;
   for (u32 r = 0; r < world; r++) {
     if (r == me) { peerBase[r] = (uint8_t *)myArena; continue; }
+    if (m->peerPtr[r] && memcmp(&m->peerHandle[(size_t)r * 64], &all[r], 64) == 0) { peerBase[r] = (uint8_t *)m->peerPtr[r]; continue; }
+    if (m->peerPtr[r]) { cudaIpcCloseMemHandle(m->peerPtr[r]); m->peerPtr[r] = nullptr; }
     void *p = nullptr;
     const cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      mb_comm_close_peer_arenas(m, peerBase);
       return mb_fail(MB_ECOMM, "cannot map the arena of rank %u into rank %u: %s", r, me, cudaGetErrorString(e));
     }
+    m->peerPtr[r] = p;
+    memcpy(&m->peerHandle[(size_t)r * 64], &all[r], 64);
     peerBase[r] = (uint8_t *)p;
   }
   return MB_OK;
@@ -329,12 +341,8 @@ int mb_comm_open_peer_arenas(MbComm *m, void *myArena, u64 *dScratch, uint8_t **
 
 //  Unmap the peers' arenas (call after a collective that follows the last use, and before any rank frees its arena).
 int mb_comm_close_peer_arenas(MbComm *m, uint8_t **peerBase) {
-#ifndef MB_CUSIM
-  for (u32 r = 0; r < m->world; r++)
-    if (r != m->rank && peerBase[r]) { cudaIpcCloseMemHandle(peerBase[r]); peerBase[r] = nullptr; }
-#else
-  (void)m;  (void)peerBase;
-#endif
+  //  the mappings stay with the communicator (see above); a communicator that is destroyed closes them
+  for (u32 r = 0; r < m->world; r++) peerBase[r] = nullptr;
   return MB_OK;
 }
 

@@ -187,13 +187,14 @@ struct SortHistGroups {
   u32 total;                           //  entries of all tables
 };
 
-template <int KW>
+template <int KW, int NG>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_hist2_kernel(const typename KeyT<KW>::type *__restrict__ keys,
                   const u64 *__restrict__ segStart, const u64 *__restrict__ segTile, u32 nSegs, u64 nTiles,
                   SortHistGroups hg, u32 nPasses, u32 radix, u64 *__restrict__ ghist) {
   typedef typename KeyT<KW>::type Key;
   const int TILE = SORT_THREADS * SortShape<KW>::ITEMS;
+  const int UNROLL = 8;
   extern __shared__ __align__(16) unsigned char histSmem[];
   u32 *jt = (u32 *)histSmem;                           //  hg.total joint counters
   __shared__ u32 marg[HIST_WORDS];                     //  nPasses * radix marginal counters
@@ -201,6 +202,13 @@ sort_hist2_kernel(const typename KeyT<KW>::type *__restrict__ keys,
   const u32 t = threadIdx.x;
   for (u32 i = t; i < hg.total; i += SORT_THREADS) jt[i] = 0;
   __syncthreads();
+
+  //  the groups' fields, once, in registers (NG is a compile-time constant: the loops below unroll and the hot loop is
+  //  shift / mask / add / one shared-memory atomic per group -- ncu of the first form: 83 instructions per key, a
+  //  seventh of them constant-bank loads of these very numbers, and the atomics' queue (MIO) the top stall)
+  u32 gShift[NG], gBits[NG];  u32 *gTab[NG];
+#pragma unroll
+  for (int g = 0; g < NG; g++) { gShift[g] = hg.shift[g];  gBits[g] = hg.bitsAll[g];  gTab[g] = jt + hg.offset[g]; }
 
   const u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
   u64 tileEnd = tile0 + HIST_TILES_PER_CTA;
@@ -239,10 +247,21 @@ sort_hist2_kernel(const typename KeyT<KW>::type *__restrict__ keys,
     const u64 begin = segStart[seg] + (tile - segTile[seg]) * TILE;
     u64 n = segStart[seg + 1] - begin;
     if (n > (u64)TILE) n = TILE;
-    for (u32 j = t; j < (u32)n; j += SORT_THREADS) {
-      const Key key = keys[begin + j];
-      for (u32 g = 0; g < hg.nGroups; g++)
-        atomicAdd(&jt[hg.offset[g] + key_field(key, hg.shift[g], hg.bitsAll[g])], 1u);
+    const Key *kp = keys + begin;
+    u32 j = t;
+    for (; j + (UNROLL - 1) * SORT_THREADS < (u32)n; j += UNROLL * SORT_THREADS) {     //  UNROLL independent loads in flight
+      Key k[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) k[u] = kp[j + u * SORT_THREADS];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+        for (int g = 0; g < NG; g++) atomicAdd(gTab[g] + key_field(k[u], gShift[g], gBits[g]), 1u);
+    }
+    for (; j < (u32)n; j += SORT_THREADS) {
+      const Key key = kp[j];
+#pragma unroll
+      for (int g = 0; g < NG; g++) atomicAdd(gTab[g] + key_field(key, gShift[g], gBits[g]), 1u);
     }
   }
   flush(seg);
@@ -620,13 +639,17 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
   {
     const u32 wbase = warp * 32 * ITEMS;
     const u32 w0    = wbase + wbase / ITEMS + lane + (ITEMS >= 32 ? 0 : lane / ITEMS);
+    //  one base pointer per thread, the rows at constant offsets from it (ncu of the first form: two LEA per load for the
+    //  64-bit index arithmetic -- 178 of the load phase's 312 instructions per warp were address and predicate math)
+    const Key *pin = in + (begin + wbase + lane);
+    Key *px = xpose + w0;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
       const u32 j = wbase + i * 32 + lane;
       Key k;
       if (PRE) k = nx->key[i];
-      else if (FULL || j < n) k = in[begin + j]; else key_zero(k);
-      xpose[w0 + i * 32 + (i * 32) / ITEMS] = k;
+      else if (FULL || j < n) k = pin[i * 32]; else key_zero(k);
+      px[i * 32 + (i * 32) / ITEMS] = k;
     }
     if (PRE && t == 0) *nx->sNext = atomicAdd((unsigned long long *)nx->tileCounter, 1ull);     //  claim the next tile now, read it after the scan
     __syncwarp();
@@ -996,7 +1019,9 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   const u64 histGrid = (nTiles + HIST_TILES_PER_CTA - 1) / HIST_TILES_PER_CTA;
   //  Measured on B200 (profiles/r1_ab_8gbp_countopts.jsonl): the joint form is no faster (22.2 ms either way per 6.9 G keys:
   //  the kernel is not bound by the number of shared-memory atomics) -- the single form stays the default.
-  const bool histSingle = getenv("MB_HIST_JOINT") == nullptr;
+  //  Digit histograms: adjacent passes are counted jointly (one shared-memory atomic per PAIR of digits) while the joint
+  //  tables stay small; MB_HIST_SINGLE=1 keeps the one-atomic-per-digit kernel for A/B.
+  const bool histSingle = getenv("MB_HIST_SINGLE") != nullptr;
   SortHistGroups hg;
   memset(&hg, 0, sizeof(hg));
   for (u32 p = 0; p < plan.nPasses; ) {                 //  pair adjacent passes while the joint table stays small
@@ -1008,12 +1033,18 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
     } else p += 1;
     hg.total += 1u << hg.bitsAll[g];
   }
-  if (histSingle || hg.total * 4 > 96 * 1024) {
+  if (histSingle || hg.nGroups > 8 || hg.total * 4 > 96 * 1024) {
     sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist,
                                                                      getenv("MB_HIST_SIMPLE") ? 0u : 1u);
   } else {
-    if ((e = cudaFuncSetAttribute(sort_hist2_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(hg.total * 4))) != cudaSuccess) return e;
-    sort_hist2_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, hg.total * 4, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, hg, plan.nPasses, (u32)R, ghist);
+#define MB_HIST2(NG) do {                                                                                                                   \
+      if ((e = cudaFuncSetAttribute(sort_hist2_kernel<KW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(hg.total * 4))) != cudaSuccess) return e;  \
+      sort_hist2_kernel<KW, NG><<<(unsigned)histGrid, SORT_THREADS, hg.total * 4, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, hg, plan.nPasses, (u32)R, ghist); } while (0)
+    switch (hg.nGroups) {
+      case 1: MB_HIST2(1); break;  case 2: MB_HIST2(2); break;  case 3: MB_HIST2(3); break;  case 4: MB_HIST2(4); break;
+      case 5: MB_HIST2(5); break;  case 6: MB_HIST2(6); break;  case 7: MB_HIST2(7); break;  default: MB_HIST2(8); break;
+    }
+#undef MB_HIST2
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   sort_scan_kernel<<<dim3(nSegs, plan.nPasses), (unsigned)R, 0, s>>>(ghist, dSegStart, plan.nPasses);

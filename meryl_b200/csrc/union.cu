@@ -931,6 +931,7 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
   {
     if (device >= 0) MB_UCUDA(cudaSetDevice(device));
     size_t freeB = 0, totalB = 0;
+    mb_arena_cache_release(-1);                      //  (a count context's cached arena would otherwise hide most of the device)
     MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
     auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
       size_t need = (size_t)16 << 20;
@@ -1452,6 +1453,7 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
   {
     if (device >= 0) MB_UCUDA(cudaSetDevice(device));
     size_t freeB = 0, totalB = 0;
+    mb_arena_cache_release(-1);                      //  (a count context's cached arena would otherwise hide most of the device)
     MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
     if (E.arena) freeB = E.arenaBytes;
     //  what a group of files needs on the device (upper bound):

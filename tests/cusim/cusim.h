@@ -77,6 +77,7 @@ static inline cudaError_t cudaMemGetInfo(size_t *f, size_t *t)                  
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { memset(a, 0, sizeof(*a)); return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)         { memset(p, 0, sizeof(*p)); strcpy(p->name, "cusim"); p->major = 10; p->multiProcessorCount = 4; p->totalGlobalMem = (size_t)4 << 30; return cudaSuccess; }
 static inline cudaError_t cudaGetLastError(void)                                  { return cudaSuccess; }
+static inline cudaError_t cudaPeekAtLastError(void)                               { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t)                         { return "cusim"; }
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t)              { return cudaSuccess; }

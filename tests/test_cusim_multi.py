@@ -70,8 +70,11 @@ def test_sim_multi_rank_db_bit_exact(tmp_path, world, k):
 @pytest.mark.parametrize("world,k,cap", [(2, 21, 60_000), (4, 31, 40_000), (2, 51, 80_000)])
 def test_sim_multi_rank_multi_pass(tmp_path, monkeypatch, world, k, cap):
     """100 Gbp on 2 or 4 GPUs does not fit one pass (64-bit keys): passes over groups of file slots, one exchange per pass.
-    MB_MAX_PASS_KEYS caps what a rank may send or receive per pass, so a small input takes the same road."""
+    MB_MAX_PASS_KEYS caps what a rank may send or receive per pass, so a small input takes the same road.  The NCCL route
+    with full keys (both defaults of round 2 switched off)."""
     monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    monkeypatch.setenv("MB_MULTI_SUFFIX32", "0")
+    monkeypatch.setenv("MB_P2P_SCATTER", "0")
     n_reads, rl = 3_000, 150
     data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 5 + k)
     fq = tmp_path / "reads.fq"
@@ -86,10 +89,11 @@ def test_sim_multi_rank_multi_pass(tmp_path, monkeypatch, world, k, cap):
 
 @pytest.mark.parametrize("world,k,wp,cap", [(8, 21, 14, 0), (4, 15, 8, 0), (2, 21, 12, 60_000)])
 def test_sim_multi_rank_suffix32(tmp_path, monkeypatch, world, k, wp, cap):
-    """MB_MULTI_SUFFIX32=1 (experimental): on several GPUs, too, k <= 21 travels and is sorted as u32 suffixes below the
-    prefix bin; routing is by bin (one message per bin and peer), every owned bin is a sort segment, count groups are runs
-    of consecutive bins inside an owned file.  Same db bytes as the oracle; k-mers per rank as in the u64 form."""
+    """u32 suffix keys through the NCCL route (MB_P2P_SCATTER=0): on several GPUs, too, k <= 21 travels and is sorted as u32
+    suffixes below the prefix bin; routing is by bin (one message per bin and peer), every owned bin is a sort segment, count
+    groups are runs of consecutive bins inside an owned file.  Same db bytes as the oracle; k-mers per rank as in the u64 form."""
     monkeypatch.setenv("MB_MULTI_SUFFIX32", "1")
+    monkeypatch.setenv("MB_P2P_SCATTER", "0")
     if cap:
         monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
     n_reads, rl = 4_000, 150
@@ -121,13 +125,12 @@ def test_sim_multi_rank_suffix32_falls_back_for_long_kmers(tmp_path, monkeypatch
 @pytest.mark.parametrize("world,k,wp,cap,s32", [(4, 31, 12, 0, False), (8, 51, 10, 0, False), (2, 21, 12, 60_000, False),
                                                 (8, 21, 14, 0, True), (2, 19, 12, 50_000, True)])
 def test_sim_multi_rank_p2p_scatter(tmp_path, monkeypatch, world, k, wp, cap, s32):
-    """MB_P2P_SCATTER=1 (experimental): extraction fused with the exchange -- every rank maps the other ranks' arenas and
+    """The default route of round 2: extraction fused with the exchange -- every rank maps the other ranks' arenas and
     the extraction kernel stores each kept k-mer straight into the receive segment of the GPU that owns its file (in the
     emulator the ranks share one address space, so the 'mapping' is the pointer itself).  All key forms, with and without
     several passes, with and without the u32 suffix form; same db bytes as the oracle."""
     monkeypatch.setenv("MB_P2P_SCATTER", "1")
-    if s32:
-        monkeypatch.setenv("MB_MULTI_SUFFIX32", "1")
+    monkeypatch.setenv("MB_MULTI_SUFFIX32", "1" if s32 else "0")
     if cap:
         monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
     n_reads, rl = 3_000, 150

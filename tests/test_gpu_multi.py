@@ -45,7 +45,9 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("k", [21, 51])
-def test_multi_gpu_db_bit_exact(tmp_path, world, k):
+@pytest.mark.parametrize("route", ["default", "nccl-u64"])
+def test_multi_gpu_db_bit_exact(tmp_path, world, k, route):
+    """default: peer scatter (+ u32 suffix keys for k <= 21); nccl-u64: both switched off -- round 1's all-to-all of full keys."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
@@ -56,8 +58,9 @@ def test_multi_gpu_db_bit_exact(tmp_path, world, k):
     util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
     out = str(tmp_path / "gpu.meryl")
     os.makedirs(out)
-    port = 29600 + (os.getpid() + world * 7 + k) % 300
-    mp.spawn(_worker, args=(world, port, str(fq), out, k, 12), nprocs=world, join=True)
+    port = 29600 + (os.getpid() + world * 7 + k + len(route)) % 300
+    env = {"MB_P2P_SCATTER": "0", "MB_MULTI_SUFFIX32": "0"} if route == "nccl-u64" else None
+    mp.spawn(_worker, args=(world, port, str(fq), out, k, 12, env), nprocs=world, join=True)
     stats = []
     for r in range(world):
         p = os.path.join(out, "rank%d.txt" % r)
@@ -68,10 +71,9 @@ def test_multi_gpu_db_bit_exact(tmp_path, world, k):
     util.assert_same_db(ora, out)
 
 
-@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental path: MB_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("world,cap", [(2, 0), (2, 700_000), (8, 0)])
 def test_multi_gpu_suffix32_db_bit_exact(tmp_path, world, cap):
-    """MB_MULTI_SUFFIX32=1: u32 suffix keys routed by prefix bin (one NCCL message per bin and peer); emulator twin:
+    """u32 suffix keys through the NCCL route (MB_P2P_SCATTER=0), routed by prefix bin (one message per bin and peer); emulator twin:
     tests/test_cusim_multi.py::test_sim_multi_rank_suffix32."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
@@ -83,7 +85,7 @@ def test_multi_gpu_suffix32_db_bit_exact(tmp_path, world, cap):
     util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
     out = str(tmp_path / "gpu.meryl")
     os.makedirs(out)
-    env = {"MB_MULTI_SUFFIX32": "1"}
+    env = {"MB_MULTI_SUFFIX32": "1", "MB_P2P_SCATTER": "0"}
     if cap:
         env["MB_MAX_PASS_KEYS"] = str(cap)
     port = 29600 + (os.getpid() + world * 11 + cap) % 300
@@ -96,10 +98,9 @@ def test_multi_gpu_suffix32_db_bit_exact(tmp_path, world, cap):
     util.assert_same_db(ora, out)
 
 
-@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental path: MB_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("world,k,cap,s32", [(2, 21, 0, False), (2, 51, 0, False), (2, 21, 700_000, False), (2, 21, 0, True), (8, 21, 0, True), (8, 31, 0, False)])
 def test_multi_gpu_p2p_scatter_db_bit_exact(tmp_path, world, k, cap, s32):
-    """MB_P2P_SCATTER=1: the extraction kernel stores every kept k-mer straight into the owning GPU's receive segment
+    """The default route (MB_P2P_SCATTER, with and without u32 suffix keys): the extraction kernel stores every kept k-mer straight into the owning GPU's receive segment
     (peer arenas mapped with CUDA IPC, stores over NVLink); no all-to-all.  Emulator twin:
     tests/test_cusim_multi.py::test_sim_multi_rank_p2p_scatter."""
     if torch.cuda.device_count() < world:
@@ -112,9 +113,7 @@ def test_multi_gpu_p2p_scatter_db_bit_exact(tmp_path, world, k, cap, s32):
     util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
     out = str(tmp_path / "gpu.meryl")
     os.makedirs(out)
-    env = {"MB_P2P_SCATTER": "1"}
-    if s32:
-        env["MB_MULTI_SUFFIX32"] = "1"
+    env = {"MB_P2P_SCATTER": "1", "MB_MULTI_SUFFIX32": "1" if s32 else "0"}
     if cap:
         env["MB_MAX_PASS_KEYS"] = str(cap)
     port = 29600 + (os.getpid() + world * 13 + k + cap + int(s32)) % 300
