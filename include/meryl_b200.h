@@ -153,6 +153,12 @@ uint32_t mb_file_owner_of(uint32_t file, uint32_t worldSize);
  *  D * (2k - wPrefix + 36) / 8 + 2^wPrefix * 104 bytes).  */
 int mb_set_output_buffer(mb_ctx *ctx, void *hostBuf, uint64_t bytes);
 
+/*  Optional, before mb_count: the encoded data files go from the device straight into outDir while the count runs, one
+ *  host thread per file (the reference's writer has one OpenMP thread per file, merylOp-countThreads.C:452-459), instead
+ *  of staying in host memory; mb_write_db(ctx, outDir) then adds the 64 block indexes and merylIndex.  mb_get_image
+ *  refuses the streamed data files.  (A count that closed batches keeps its images in memory as before.)  */
+int mb_set_output_dir(mb_ctx *ctx, const char *outDir);
+
 /*  Count everything added so far.  After this the encoded db (this rank's files) is in host memory.  */
 int mb_count(mb_ctx *ctx);
 

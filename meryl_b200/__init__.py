@@ -97,6 +97,7 @@ def lib() -> ctypes.CDLL:
         L.mb_file_owner_of.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         L.mb_file_owner_of.restype = ctypes.c_uint32
         L.mb_set_output_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.mb_set_output_dir.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.mb_count.argtypes = [ctypes.c_void_p]
         L.mb_get_image.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), u64p]
         L.mb_write_db.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
@@ -214,6 +215,10 @@ class Counter:
         """Caller-owned (ideally pinned) host memory for the 64 data-file images."""
         _check(lib().mb_set_output_buffer(self._h, ctypes.c_void_p(host_ptr), n_bytes))
 
+    def set_output_dir(self, out_dir: str) -> None:
+        """Before count(): stream the data files into out_dir while counting (then write_db(out_dir) adds the indexes)."""
+        _check(lib().mb_set_output_dir(self._h, os.fsencode(out_dir)))
+
     def count(self) -> None:
         _check(lib().mb_count(self._h))
 
@@ -288,6 +293,7 @@ def count(inputs, output: str, k: int, operation: str = "count", memory_gb: floa
         memory_bytes = int(memory_gb * 1024 * 1024 * 1024)
     pl = plan(k, n, memory_bytes)
     with Counter(k, pl.w_prefix, operation, device) as c:
+        c.set_output_dir(os.fspath(output))
         for p in inputs:
             c.add_file(os.fspath(p))
         c.count()

@@ -24,6 +24,7 @@ extern "C" int mb_count_files(const mb_config *cfg, const char **paths, uint32_t
   mb_ctx *c = nullptr;
   int rc = mb_create(cfg, &c);
   if (rc != MB_OK) return rc;
+  if (rc == MB_OK) rc = mb_set_output_dir(c, outDir);       //  the data files are written while the count runs
   for (uint32_t i = 0; rc == MB_OK && i < nPaths; i++) rc = mb_add_file(c, paths[i]);
   if (rc == MB_OK) rc = mb_count(c);
   if (rc == MB_OK) rc = mb_write_db(c, outDir);

@@ -147,6 +147,7 @@ static int multiGpuCount(uint32_t nGpus, mb_config cfg, const std::vector<const 
       cfg.device = (int32_t)r;  cfg.rank = r;  cfg.worldSize = nGpus;
       if (rc == MB_OK) rc = mb_create(&cfg, &c);
       if (rc == MB_OK) rc = mb_comm_init(c, sh->id);
+      if (rc == MB_OK) rc = mb_set_output_dir(c, outDir);
       for (size_t i = 0; rc == MB_OK && i < inputs.size(); i++) rc = mb_add_file_shard(c, inputs[i], r, nGpus);
       if (rc == MB_OK) rc = mb_count(c);
       if (rc == MB_OK) rc = mb_write_db(c, outDir);

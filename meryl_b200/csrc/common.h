@@ -88,6 +88,7 @@ struct MbDbImages {
   std::vector<uint8_t> index[64];
   std::vector<uint8_t> master;
   bool owned[64];                         //  files this rank owns
+  bool streamed[64] = { false };          //  the data file is in the output directory already (mb_set_output_dir): only its length is known here
 };
 
 void mb_build_master_index(u32 k, u32 wPrefix, const MbHistogram &h, std::vector<uint8_t> &out);

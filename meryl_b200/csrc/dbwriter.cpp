@@ -110,7 +110,7 @@ int mb_write_db_dir(const MbDbImages &db, const char *dir, bool writeMaster) {
   for (u32 f = 0; f < 64; f++) {
     if (!db.owned[f]) continue;
     mb_file_name(path, sizeof(path), dir, f, false);
-    MB_TRY(writeWhole(path, db.dataPtr[f], db.dataLen[f]));
+    if (!db.streamed[f]) MB_TRY(writeWhole(path, db.dataPtr[f], db.dataLen[f]));
     mb_file_name(path, sizeof(path), dir, f, true);
     MB_TRY(writeWhole(path, db.index[f].data(), db.index[f].size()));
   }

@@ -316,6 +316,7 @@ extern "C" int mb_sim_multi_count(uint32_t world, uint32_t k, uint32_t mode, uin
     mb_ctx *c = nullptr;
     int rc = mb_create(&cfg, &c);
     if (rc == MB_OK) rc = mb_sim_comm_attach(c);
+    if (rc == MB_OK && (r & 1)) rc = mb_set_output_dir(c, outDir);          //  odd ranks stream their data files, even ranks keep images
     if (rc == MB_OK && lens[r]) rc = mb_add_file_bytes(c, data[r], lens[r]);
     if (rc == MB_OK) rc = mb_count(c);
     if (rc == MB_OK) rc = mb_write_db(c, outDir);

@@ -33,6 +33,7 @@
 #include "kernels.cuh"
 #include "engine.h"
 #include "exchange.h"
+#include "filesink.h"
 
 static u64 *g_extractProf = nullptr;                 //  debug: phase timing of the extract kernel
 
@@ -97,6 +98,7 @@ struct mb_ctx {
 
   uint8_t    *outBuf     = nullptr;                  //  caller-supplied host buffer for the data images
   size_t      outCap     = 0, outUsed = 0;
+  std::string outDir;                                //  mb_set_output_dir: the data files are streamed there while counting
 
   MbComm     *comm       = nullptr;                  //  multi-GPU (exchange.cu)
 
@@ -285,13 +287,25 @@ static int flushStage(mb_ctx *c) {
   return MB_OK;
 }
 
+//  The copy into the page-locked staging buffer was the serial part of the file ingest (one thread behind sixteen parsing
+//  threads): large pieces are copied by several threads.
+static void stageCopy(char *dst, const char *src, size_t n) {
+  static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  if (n < ((size_t)8 << 20) || hw < 2) { memcpy(dst, src, n); return; }
+  const size_t per = (n / hw + 4095) / 4096 * 4096;
+  std::vector<std::thread> th;
+  for (size_t at = per; at < n; at += per) th.emplace_back([=]() { memcpy(dst + at, src + at, std::min(per, n - at)); });
+  memcpy(dst, src, std::min(per, n));
+  for (auto &t : th) t.join();
+}
+
 static int appendRaw(mb_ctx *c, const char *p, size_t n) {
   MB_TRY(ensureArena(c));
   while (n) {
     size_t room = kStageBytes - c->fill;
     if (room == 0) { MB_TRY(flushStage(c)); room = kStageBytes; }
     const size_t m = n < room ? n : room;
-    memcpy(c->hStage[c->cur] + c->fill, p, m);
+    stageCopy(c->hStage[c->cur] + c->fill, p, m);
     c->fill += m;  p += m;  n -= m;
   }
   return MB_OK;
@@ -500,7 +514,7 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
           return rc;
         }
         SeqParser ps(parserSink, c);
-        const size_t BLK = (size_t)256 << 20;
+        const size_t BLK = (size_t)1 << 30;                  //  (16 threads x 64 MB: pieces large enough for the parallel staging copy)
         for (size_t at = 0; rc == MB_OK && at < sz; at += BLK) rc = mb_parse_parallel(parserSink, c, ps, d + at, std::min(BLK, sz - at));
         munmap(m, sz);
         if (rc != MB_OK) return rc;
@@ -1004,8 +1018,35 @@ static int runCount(mb_ctx *c) {
   c->st.sortPasses = plan.nPasses;
 
   //  host images
-  for (u32 f = 0; f < 64; f++) { c->db.dataVec[f].clear(); c->db.dataPtr[f] = nullptr; c->db.dataLen[f] = 0; c->db.index[f].clear(); }
+  for (u32 f = 0; f < 64; f++) { c->db.dataVec[f].clear(); c->db.dataPtr[f] = nullptr; c->db.dataLen[f] = 0; c->db.index[f].clear(); c->db.streamed[f] = false; }
   c->outUsed = 0;
+
+  //  mb_set_output_dir: the encoded data files do not stay in host memory, they go from the device to the directory
+  //  while the count runs, in parallel across files (filesink.h).  Only for a count that is a single batch.
+  struct Streamer {
+    MbFileSink *sink = nullptr;  int fd[64];  cudaEvent_t ready = nullptr;
+    Streamer() { for (int i = 0; i < 64; i++) fd[i] = -1; }
+    ~Streamer() {
+      if (sink) mb_filesink_drain(sink);
+      for (int i = 0; i < 64; i++) if (fd[i] >= 0) close(fd[i]);
+      if (ready) cudaEventDestroy(ready);
+    }
+  } stream;
+  const bool streaming = !c->outDir.empty() && !c->closing && c->batches.empty() && !c->stopAfterSort &&
+                         !(cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED));
+  if (streaming) {
+    if (mkdir(c->outDir.c_str(), 0777) != 0 && errno != EEXIST) return mb_fail(MB_EIO, "cannot create directory '%s': %s", c->outDir.c_str(), strerror(errno));
+    char path[4096];
+    for (u32 f = 0; f < 64; f++) {
+      if (!c->db.owned[f]) continue;
+      mb_file_name(path, sizeof(path), c->outDir.c_str(), f, false);
+      stream.fd[f] = open(path, O_CREAT | O_TRUNC | O_WRONLY, 0666);
+      if (stream.fd[f] < 0) return mb_fail(MB_EIO, "cannot create '%s': %s", path, strerror(errno));
+      c->db.streamed[f] = true;
+    }
+    stream.sink = mb_filesink_get();
+    MB_CUDA(cudaEventCreateWithFlags(&stream.ready, cudaEventDisableTiming));
+  }
   if (overlapD2H) for (u32 f = 0; f < 64; f++) c->db.index[f].reserve((size_t)blocksPerFile * 24);   //  no reallocation under a copy in flight
   std::vector<u64> fileBase(64, 0);
 
@@ -1312,7 +1353,24 @@ static int runCount(mb_ctx *c) {
           MB_CUDA(mb_launch_encode_write(ep, ch, dMeta, dCtl->encTotals, dSub, dOut, dIdx, dCtl->fileBase, s));
           c->st.nLaunches += D ? 2 : 1;
 
-          if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
+          if (streaming) {
+            MB_CUDA(cudaEventRecord(stream.ready, s));
+            for (u32 f = fi; f < fj; f++) {
+              const u32 file = fileLo + f;
+              const size_t fb = fm[f + 1].outByte - fm[f].outByte;
+              const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
+              std::vector<uint8_t> &iv = c->db.index[file];
+              mb_filesink_submit(stream.sink, c->device, stream.fd[file], c->db.dataLen[file],
+                                 dOut + (fm[f].outByte - ch.chunkByte0), fb, stream.ready);
+              c->db.dataLen[file] += fb;
+              const size_t i0 = iv.size();
+              iv.resize(i0 + ib);
+              MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
+              c->st.d2hBytes += fb + ib;
+            }
+            MB_CUDA(cudaStreamSynchronize(s));
+            MB_TRY(mb_filesink_drain(stream.sink));     //  (the encode region is reused by the next chunk)
+          } else if (!(cfg.flags & MB_FLAG_NO_IMAGES)) {
             for (u32 f = fi; f < fj; f++) {
               const u32 file = fileLo + f;
               const size_t fb = fm[f + 1].outByte - fm[f].outByte;
@@ -1447,6 +1505,14 @@ static int runCount(mb_ctx *c) {
 //  Debug: device buffer of 8 u64 receiving per-phase clock sums of the extract kernel (NULL = off).
 void mb_extract_set_profile_buffer(u64 *d) { g_extractProf = d; }
 
+extern "C" int mb_set_output_dir(mb_ctx *c, const char *outDir) {
+  mb_clear_error();
+  if (!c || !outDir || !outDir[0])  return mb_fail(MB_EINVAL, "mb_set_output_dir: NULL argument");
+  if (c->counted)                   return mb_fail(MB_ESTATE, "mb_set_output_dir: already counted");
+  c->outDir = outDir;
+  return MB_OK;
+}
+
 extern "C" int mb_set_output_buffer(mb_ctx *c, void *hostBuf, uint64_t bytes) {
   mb_clear_error();
   if (!c || (!hostBuf && bytes))  return mb_fail(MB_EINVAL, "mb_set_output_buffer: NULL argument");
@@ -1522,6 +1588,7 @@ extern "C" int mb_get_image(mb_ctx *c, uint32_t which, const uint8_t **ptr, uint
   mb_clear_error();
   if (!c || !ptr || !len || which > 128)  return mb_fail(MB_EINVAL, "mb_get_image: bad argument");
   if (!c->counted)                        return mb_fail(MB_ESTATE, "mb_get_image: call mb_count first");
+  if (which < 64 && c->db.streamed[which]) return mb_fail(MB_ESTATE, "mb_get_image: data file %u was streamed to '%s' (mb_set_output_dir)", which, c->outDir.c_str());
   if (which < 64) { *ptr = c->db.dataPtr[which]; *len = c->db.dataLen[which]; return MB_OK; }
   const std::vector<uint8_t> &v = which < 128 ? c->db.index[which - 64] : c->db.master;
   *ptr = v.data();
@@ -1534,6 +1601,9 @@ extern "C" int mb_write_db(mb_ctx *c, const char *outDir) {
   if (!c || !outDir)  return mb_fail(MB_EINVAL, "mb_write_db: NULL argument");
   if (!c->counted)    return mb_fail(MB_ESTATE, "mb_write_db: call mb_count first");
   if (c->cfg.flags & MB_FLAG_NO_IMAGES) return mb_fail(MB_ESTATE, "mb_write_db: context was created with MB_FLAG_NO_IMAGES");
+  for (u32 f = 0; f < 64; f++)
+    if (c->db.streamed[f] && c->outDir != outDir)
+      return mb_fail(MB_ESTATE, "mb_write_db: the data files were streamed to '%s' while counting (mb_set_output_dir); write the rest there", c->outDir.c_str());
   return mb_write_db_dir(c->db, outDir, c->cfg.rank == 0);
 }
 

@@ -225,8 +225,8 @@ int mb_parse_parallel(SeqParser::Sink out, void *outArg, SeqParser &ps, const ui
     if (ok) {
       if (pc[i].rc != MB_OK) return mb_fail(pc[i].rc, "%s", pc[i].err.c_str());
       //  hand the piece on in bounded slices (the sink copies into the pinned staging buffers)
-      for (size_t at = 0; at < pc[i].outp->size(); at += (size_t)8 << 20)
-        MB_TRY(out(outArg, pc[i].outp->data() + at, std::min<size_t>((size_t)8 << 20, pc[i].outp->size() - at)));
+      for (size_t at = 0; at < pc[i].outp->size(); at += (size_t)64 << 20)
+        MB_TRY(out(outArg, pc[i].outp->data() + at, std::min<size_t>((size_t)64 << 20, pc[i].outp->size() - at)));
       cur = pc[i].end;
     } else {                                                 //  the cut was not at a record start: sequentially from the true state
       SeqParser q(out, outArg);

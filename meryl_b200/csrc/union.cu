@@ -36,6 +36,7 @@
 
 #include "common.h"
 #include "kernels.cuh"
+#include "filesink.h"
 
 namespace {
 
@@ -1747,7 +1748,17 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
             if (fds[fi] < 0) wrc = mb_fail(MB_EIO, "cannot create '%s': %s", path, strerror(errno));
           }
         }
-        if (wrc == MB_OK)
+        if (wrc == MB_OK && !E.outImages) {
+          //  a directory: one job per data file, the files in parallel (filesink.h: several host threads on ONE file gain
+          //  nothing -- measured 3.4 GB/s for this step when the pieces of a 32 MB chunk were written by eight threads)
+          MbFileSink *sink = mb_filesink_get();
+          int dev = 0;  cudaGetDevice(&dev);
+          if (cudaStreamSynchronize(s) != cudaSuccess) wrc = mb_fail(MB_ENODEVICE, "%s", cudaGetErrorString(cudaGetLastError()));
+          for (u32 fi = 0; fi < nf && wrc == MB_OK; fi++)
+            mb_filesink_submit(sink, dev, fds[fi], 0, dOut + fileByte[fi], (size_t)(fileByte[fi + 1] - fileByte[fi]), nullptr);
+          const int drc = mb_filesink_drain(sink);
+          if (wrc == MB_OK) wrc = drc;
+        } else if (wrc == MB_OK)
           wrc = streamFromDevice(ring, dOut, (size_t)encTotals[0], s, [&](size_t off, size_t len, const uint8_t *src) -> int {
             //  pieces: (file, range) intersections of this chunk, at most 4 MB each
             struct Piece { u32 fi; size_t a0, a1; };

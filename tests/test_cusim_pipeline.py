@@ -112,6 +112,31 @@ def test_sim_dense_extraction_rounds(tmp_path, monkeypatch, k, w_prefix, op):
     _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 177 + k)}, k, w_prefix, op=op, min_passes=2)
 
 
+@pytest.mark.parametrize("cap", [0, 150_000])
+def test_sim_streamed_output_dir(tmp_path, monkeypatch, cap):
+    """mb_set_output_dir: the data files go from the device to the directory while the count runs (csrc/filesink.cpp, one
+    worker per file); write_db adds the block indexes and merylIndex.  Same 129 files as the oracle, one and several passes;
+    the streamed images are refused by mb_get_image; another directory is refused by write_db."""
+    if cap:
+        monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 31))
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=21", "wprefix=12", "count", str(fq), "output", ora])
+    with mb.Counter(21, 12) as c:
+        c.set_output_dir(out)
+        c.add_file(str(fq))
+        c.count()
+        assert (c.stats().nPasses > 1) == bool(cap)
+        with pytest.raises(mb.MerylB200Error):
+            c.image(0)
+        with pytest.raises(mb.MerylB200Error):
+            c.write_db(str(tmp_path / "elsewhere.meryl"))
+        c.write_db(out)
+        assert c.image(64) and c.image(128)
+    util.assert_same_db(ora, out)
+
+
 def test_sim_multi_pass_rolling(tmp_path, monkeypatch):
     """The same kind of passes through the rolling path (filter switched off)."""
     monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")

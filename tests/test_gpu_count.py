@@ -195,7 +195,7 @@ def test_multi_pass_equals_single_pass(tmp_path):
 
 
 @pytest.mark.parametrize("k,op", [(21, "count"), (21, "count-forward"), (22, "count-reverse"), (31, "count"), (51, "count"), (64, "count")])
-@pytest.mark.parametrize("sort_version", ["1", "2"])
+@pytest.mark.parametrize("sort_version", ["1", "3"])
 def test_multi_pass_file_aligned_prefilter(tmp_path, monkeypatch, k, op, sort_version):
     """Capped passes (MB_MAX_PASS_KEYS) exercise the file-aligned pass plan and the extraction kernel's bit-sliced
     pass-membership filter; run with both sweep kernels (MB_SORT is read when the first sort is planned, so each
@@ -210,6 +210,27 @@ def test_multi_pass_file_aligned_prefilter(tmp_path, monkeypatch, k, op, sort_ve
     assert p.returncode == 0, p.stderr
     import re
     assert int(re.search(r"in (\d+) pass", p.stderr).group(1)) >= 3, p.stderr
+    util.assert_same_db(ora, out)
+
+
+@pytest.mark.parametrize("cap", [0, 1_500_000])
+def test_streamed_output_dir(tmp_path, monkeypatch, cap):
+    """mb_set_output_dir: the data files go from the device to the directory while the count runs (csrc/filesink.cpp, one
+    worker and CUDA stream per file); write_db adds the block indexes and merylIndex.  Same 129 files as the oracle."""
+    if cap:
+        monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(300_000, 60_000, 150, 0.004, 31))
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "gpu.meryl")
+    util.run_oracle(["k=21", "wprefix=14", "count", str(fq), "output", ora])
+    with mb.Counter(21, 14) as c:
+        c.set_output_dir(out)
+        c.add_file(str(fq))
+        c.count()
+        assert (c.stats().nPasses > 1) == bool(cap)
+        with pytest.raises(mb.MerylB200Error):
+            c.image(0)
+        c.write_db(out)
     util.assert_same_db(ora, out)
 
 
