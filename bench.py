@@ -218,7 +218,7 @@ def main():
         # the reference binary counts 60-110 M k-mers/s on the boxes seen so far (16-32 host threads): at least 1 Gbp per
         # run (below that its start-up and teardown dominate), more when few runs are asked for; all runs within ~6 minutes
         runs = (args.steps + args.warmup) if args.impl == "reference" else 1
-        args.ref_gbp = max(1.0, min(2.0, 28.0 / max(1, runs)))
+        args.ref_gbp = max(1.0, min(2.0, 20.0 / max(1, runs)))
 
     if args.impl == "reference":                    # the reference alone: no torch, no CUDA, no libmeryl_b200.so in this process
         reference_arm(args, world, rank)
@@ -315,10 +315,7 @@ def main():
     sort_bytes = stats.sortLaunchKeys * 2 * stats.keyBytes
     achieved = sort_bytes / (stats.msSort / 1000) / 1e9 if stats.msSort > 0 else 0.0
     sweep_version = mb.lib().mb_dbg_sort_version(0)            # 0: query only
-    sweep_name = {1: "sort_sweep_kernel (256 threads, 6-bit digits)", 2: "sortx_sweep_kernel<128 threads, 8-bit digits>",
-                  3: "sortx_sweep_kernel<256 threads, 6-bit digits>", 4: "sortx_sweep_kernel<256 threads, 7-bit digits>",
-                  5: "sortx_sweep_kernel<512 threads, 6-bit digits>", 6: "sortx_sweep_kernel<256 threads, 6-bit digits, 2 CTAs/SM>",
-                  7: "sortp_sweep_kernel<256 threads, 6-bit digits, persistent>"}.get(sweep_version, "?")
+    sweep_name = {2: "sortx_sweep_kernel<128 threads, 8-bit digits>", 3: "sortx_sweep_kernel<256 threads, 6-bit digits>"}.get(sweep_version, "?")
     traffic = None                                              # DRAM bytes per launch, from the committed ncu capture of this kernel
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic_sweep.json")) as fh:
@@ -394,6 +391,8 @@ def main():
     # ---- the command line tools side by side on one FASTQ file (rank 0, one GPU) -----------------
     cli = None
     if rank == 0 and world == 1 and args.cli_gbp > 0:
+        torch.cuda.empty_cache()
+        mb.lib().mb_release_device_memory()         # the arena this process keeps between counts (another process is about to use the GPU)
         try:
             cli = cli_leg(args.cli_gbp, local)
         except Exception as ex:

@@ -323,9 +323,6 @@ int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *bases, uint64_t
 int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits);
 /*  K4 on u32 keys (the suffix-key form a pass uses when 2k - binBits <= 32).  */
 int mb_dbg_sort32(uint32_t *keys, uint64_t n, uint32_t bits);
-/*  Debug: per-phase clock sums of the sort sweep kernel (enable=1 starts collecting; out may be NULL).  */
-int mb_dbg_sort_profile(uint64_t out[8], int enable);
-int mb_dbg_extract_profile(uint64_t out[8], int enable);
 /*  K6 alone: encode one block like merylFileWriter::writeBlockToFile.  out must hold cap bytes.  */
 int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix, uint64_t n,
                         const uint64_t *sufLo, const uint64_t *sufHi, const uint32_t *values,

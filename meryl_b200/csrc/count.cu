@@ -325,94 +325,6 @@ count_suffix32g_kernel(const u32 *__restrict__ keys, const CountTileInfo *__rest
     if ((u32)g < nH) count32_half<G, true>(keys, ti[g], (u32)((h0 + g) & 1), lane, warp, sExcl + myOff[g], binLo, suffixBits, uniq, runStart);
 }
 
-//  Second form of the same kernel (MB_COUNT_BLOCKED=1; NOT the default: measured 40 % slower on B200): blocked keys.
-//  The striped form above spends three warp collectives per 32 keys (shuffle for the predecessor, ballot, shuffle
-//  for the carry).  Here a warp transposes its rows through shared memory so that every thread owns 16 CONSECUTIVE
-//  keys: run heads are plain compares against the previous register, and the only collectives left are one warp
-//  scan per thread and the block scan.
-__global__ void __launch_bounds__(CNT_THREADS, 4)
-count_suffix32b_kernel(const u32 *__restrict__ keys, const CountTileInfo *__restrict__ info, u64 tileLo, u64 nHalves,
-                       u64 endIndex, u32 binLo, u32 suffixBits, u64 *__restrict__ uniq, u64 *__restrict__ runStart,
-                       u64 *__restrict__ numDistinct, u64 *__restrict__ status, u64 *__restrict__ tileCounter) {
-  __shared__ u32 xpose[C32_HALF + CNT_THREADS];              //  key j at j + j / 16: conflict-free blocked reads
-  __shared__ u32 warpTot[CNT_WARPS];
-  __shared__ u64 sTile, sExcl;
-
-  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
-
-  if (t == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
-  __syncthreads();
-  const u64 rel  = sTile;                                    //  half-tile index inside the group
-  const u32 half = (u32)(rel & 1);
-  const CountTileInfo ti = info[tileLo + (rel >> 1)];
-  const u64  begin   = ti.begin + (u64)half * C32_HALF;
-  const u32  n       = ti.n > half * C32_HALF ? min(ti.n - half * C32_HALF, (u32)C32_HALF) : 0;
-  const u32  seg     = ti.seg & 0x7fffffffu;
-  const bool segHead = (ti.seg >> 31) != 0 && half == 0;     //  the segment's very first key always starts a run
-
-  //  coalesced rows -> shared memory (keys beyond n are never compared)
-  const u32 wbase = warp * 32 * C32_ITEMS;
-#pragma unroll
-  for (int i = 0; i < C32_ITEMS; i++) {
-    const u32 j = wbase + i * 32 + lane;
-    xpose[j + j / C32_ITEMS] = (j < n) ? keys[begin + j] : 0;
-  }
-  //  the key before my first one: the previous thread's last key, or (thread 0) the key before the half-tile
-  u32 prev = 0;
-  if (t == 0 && n > 0 && !segHead) prev = keys[begin - 1];
-  __syncthreads();
-  const u32 first = t * C32_ITEMS;
-  if (t > 0) prev = xpose[first - 1 + (first - 1) / C32_ITEMS];
-
-  u32 key[C32_ITEMS];
-  u32 heads = 0;
-#pragma unroll
-  for (int i = 0; i < C32_ITEMS; i++) {
-    key[i] = xpose[t * (C32_ITEMS + 1) + i];
-    const bool head = (first + i < n) && ((segHead && first + i == 0) || key[i] != prev);
-    if (head) heads |= 1u << i;
-    prev = key[i];
-  }
-
-  const u32 mine = __popc(heads);
-  u32 incl = mine;
-  for (int o = 1; o < 32; o <<= 1) {
-    const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (u32)o) incl += v;
-  }
-  if (lane == 31) warpTot[warp] = incl;
-  __syncthreads();
-
-  u32 wOff = 0, tileTot = 0;
-#pragma unroll
-  for (int w = 0; w < CNT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) wOff += c; tileTot += c; }
-
-  if (warp == 0) {
-    if (lane == 0) st_volatile_u64(status + rel, (rel == 0 ? MB_ST_INC : MB_ST_AGG) | tileTot);
-    const u64 excl = lookback_warp(status, rel, lane);
-    if (lane == 0) {
-      if (rel != 0) st_volatile_u64(status + rel, MB_ST_INC | (excl + tileTot));
-      sExcl = excl;
-      if (rel + 1 == nHalves) {                              //  last half-tile of the group: total and sentinel
-        *numDistinct = excl + tileTot;
-        runStart[excl + tileTot] = endIndex;
-      }
-    }
-  }
-  __syncthreads();
-
-  u64 o = sExcl + wOff + (incl - mine);
-  const u64 hiBits = (u64)(binLo + seg) << suffixBits;
-#pragma unroll
-  for (int i = 0; i < C32_ITEMS; i++) {
-    if (heads & (1u << i)) {
-      uniq[o]     = hiBits | key[i];
-      runStart[o] = begin + first + i;
-      o++;
-    }
-  }
-}
-
 //  ---- value histogram --------------------------------------------------------------------------
 
 const int VH_THREADS = 256;
@@ -513,21 +425,15 @@ cudaError_t mb_launch_count_suffix32(const u32 *dKeys, const void *dTileInfo, u6
   const u64 nHalves = 2 * (tileHi - tileLo);                 //  workspace: (2 + nHalves) u64
   if ((e = cudaMemsetAsync(dWorkspace, 0, (2 + nHalves) * sizeof(u64), s)) != cudaSuccess) return e;
   u64 *counter = (u64 *)dWorkspace, *status = counter + 2;
-  //  Measured on B200 (profiles/r1_ab_8gbp_countopts.jsonl): the striped form takes 36 ms per 6.9 G keys, the blocked form 50 ms
-  //  (its transposition through shared memory costs more than the collectives it saves) -- striped is the default.
-  const bool striped = getenv("MB_COUNT_BLOCKED") == nullptr;
-  const u32  group   = getenv("MB_COUNT_GROUP") ? (u32)strtoul(getenv("MB_COUNT_GROUP"), nullptr, 10) : 4u;
-  if (striped && group >= 2) {
-    if (group >= 8)      count_suffix32g_kernel<8><<<(unsigned)((nHalves + 7) / 8), CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
-    else if (group >= 4) count_suffix32g_kernel<4><<<(unsigned)((nHalves + 3) / 4), CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
-    else                 count_suffix32g_kernel<2><<<(unsigned)((nHalves + 1) / 2), CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
-  } else if (striped)
-    count_suffix32_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
-                                                                  binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter,
-                                                                  getenv("MB_COUNT_PREFETCH") ? (u32)strtoul(getenv("MB_COUNT_PREFETCH"), nullptr, 10) : 0u);
+  //  (A blocked-key form of this kernel, transposing through shared memory, measured 40 % slower in round 1 and is gone.)
+  //  MB_COUNT_GROUP=1: the one-half-tile-per-CTA kernel, for A/B (measured on B200, 6.9 G keys: 35.4 ms; two half-tiles per
+  //  CTA 28.1 ms; four 24.5 ms -- the default).
+  const bool grouped = !(getenv("MB_COUNT_GROUP") && getenv("MB_COUNT_GROUP")[0] == '1');
+  const CountTileInfo *ti = (const CountTileInfo *)dTileInfo;
+  if (grouped) count_suffix32g_kernel<4><<<(unsigned)((nHalves + 3) / 4), CNT_THREADS, 0, s>>>(dKeys, ti, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
   else
-    count_suffix32b_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, (const CountTileInfo *)dTileInfo, tileLo, nHalves, endIndex,
-                                                                   binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter);
+    count_suffix32_kernel<<<(unsigned)nHalves, CNT_THREADS, 0, s>>>(dKeys, ti, tileLo, nHalves, endIndex, binLo, suffixBits, dUniq, dRunStart, dNumDistinct, status, counter,
+                                                                  getenv("MB_COUNT_PREFETCH") ? (u32)strtoul(getenv("MB_COUNT_PREFETCH"), nullptr, 10) : 0u);
   return cudaGetLastError();
 }
 

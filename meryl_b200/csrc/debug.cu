@@ -95,48 +95,6 @@ extern "C" int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *base
   return rc;
 }
 
-void mb_sort_set_profile_buffer(u64 *dProf);
-void mb_extract_set_profile_buffer(u64 *dProf);
-
-//  Debug: phase timing of the extract (scatter) kernel.  out[0] = tiles, out[1..7] = summed clocks of:
-//  wait for the TMA tile, own phase A, CTA phase A, own reservations, CTA reservations, own phase B, CTA phase B.
-static u64 *g_dXProf = nullptr;
-extern "C" int mb_dbg_extract_profile(uint64_t out[8], int enable) {
-  mb_clear_error();
-  if (enable && !g_dXProf) {
-    MB_CUDA(cudaMalloc((void **)&g_dXProf, 8 * sizeof(u64)));
-    MB_CUDA(cudaMemset(g_dXProf, 0, 8 * sizeof(u64)));
-    mb_extract_set_profile_buffer(g_dXProf);
-  }
-  if (g_dXProf && out) {
-    MB_CUDA(cudaDeviceSynchronize());
-    MB_CUDA(cudaMemcpy(out, g_dXProf, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
-    MB_CUDA(cudaMemset(g_dXProf, 0, 8 * sizeof(u64)));
-  }
-  if (!enable && g_dXProf) { mb_extract_set_profile_buffer(nullptr); cudaFree(g_dXProf); g_dXProf = nullptr; }
-  return MB_OK;
-}
-
-//  Debug: turn the sweep kernel's phase timing on (returns 0) and read/reset it.
-//  out[0] = tiles, out[1..6] = summed clocks of: tile id, load+rank, scan+reorder, own look-back,
-//  wait for the CTA's look-back, copy-out.
-static u64 *g_dProf = nullptr;
-extern "C" int mb_dbg_sort_profile(uint64_t out[8], int enable) {
-  mb_clear_error();
-  if (enable && !g_dProf) {
-    MB_CUDA(cudaMalloc((void **)&g_dProf, 8 * sizeof(u64)));
-    MB_CUDA(cudaMemset(g_dProf, 0, 8 * sizeof(u64)));
-    mb_sort_set_profile_buffer(g_dProf);
-  }
-  if (g_dProf && out) {
-    MB_CUDA(cudaDeviceSynchronize());
-    MB_CUDA(cudaMemcpy(out, g_dProf, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
-    MB_CUDA(cudaMemset(g_dProf, 0, 8 * sizeof(u64)));
-  }
-  if (!enable && g_dProf) { mb_sort_set_profile_buffer(nullptr); cudaFree(g_dProf); g_dProf = nullptr; }
-  return MB_OK;
-}
-
 extern "C" int mb_dbg_sort(uint64_t *lo, uint64_t *hi, uint64_t n, uint32_t bits) {
   mb_clear_error();
   if (!lo && n) return mb_fail(MB_EINVAL, "mb_dbg_sort: NULL argument");
@@ -256,10 +214,10 @@ extern "C" int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix
   return rc;
 }
 
-//  Select the sweep kernel (1..6, see sort.cu) for the contexts created afterwards; returns the previous one.
+//  Select the sweep shape (2 or 3, see sort.cu) for the contexts created afterwards; returns the previous one.
 extern "C" int mb_dbg_sort_version(int v) {
   const int old = mb_sort_version();
-  if (v >= 1 && v <= 7) mb_sort_set_version(v);
+  if (v == 2 || v == 3) mb_sort_set_version(v);
   return old;
 }
 

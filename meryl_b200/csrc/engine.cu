@@ -35,7 +35,6 @@
 #include "exchange.h"
 #include "filesink.h"
 
-static u64 *g_extractProf = nullptr;                 //  debug: phase timing of the extract kernel
 
 namespace {
 
@@ -715,8 +714,6 @@ static int runCount(mb_ctx *c) {
   xp.k = k;  xp.mode = cfg.mode;  xp.binBits = binBits;  xp.binLo = 0;  xp.binHi = nBins;  xp.suffix32 = 0;
   xp.noPrefilter = getenv("MB_NO_PREFILTER") ? 1 : 0;
   xp.keptPerMille = 0;
-  xp.rankMatch = getenv("MB_RANK_MATCH") ? 1 : 0;
-  xp.prof = g_extractProf;
 
   tStage.start(s);
   MB_CUDA(mb_launch_bin_histogram(xp, dCtl->binCount, s));
@@ -804,31 +801,9 @@ static int runCount(mb_ctx *c) {
   u32 *dHistBig = (u32 *)top.take(histBigCap * sizeof(u32));
   if (!dHistBig) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
 
-  //  Experimental (MB_OVERLAP_D2H=1, not the default until it is measured): the device-to-host copy of a group's encoded
-  //  blocks runs on a second stream while the next group is counted and encoded.  Groups alternate between two halves
-  //  of the encode region; a half is reused only after its copy has finished.  Needs a caller-owned output buffer
-  //  (mb_set_output_buffer): the destination must not move while a copy is in flight.
-  const bool overlapD2H = getenv("MB_OVERLAP_D2H") != nullptr && c->outBuf != nullptr && !(cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED));
-  struct CopySide {                                     //  released on every way out of the function
-    cudaStream_t stream = nullptr;
-    cudaEvent_t  enc = nullptr, copied[2] = { nullptr, nullptr }, afterHist = nullptr;
-    ~CopySide() {
-      if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
-      if (enc) cudaEventDestroy(enc);
-      for (int i = 0; i < 2; i++) if (copied[i]) cudaEventDestroy(copied[i]);
-      if (afterHist) cudaEventDestroy(afterHist);
-    }
-  } side;
-  cudaStream_t &sCopy = side.stream;
-  cudaEvent_t  &evEnc = side.enc, (&evCopied)[2] = side.copied;
-  bool         copyPending[2] = { false, false };
-  u64          groupSeq = 0;
-  if (overlapD2H) {
-    MB_CUDA(cudaStreamCreateWithFlags(&sCopy, cudaStreamNonBlocking));
-    MB_CUDA(cudaEventCreateWithFlags(&evEnc, cudaEventDisableTiming));
-    for (int i = 0; i < 2; i++) MB_CUDA(cudaEventCreateWithFlags(&evCopied[i], cudaEventDisableTiming));
-  }
-
+  //  (Round 2 measured a second stream for the copy-back of a group's encoded blocks, alternating between two halves of
+  //  the encode region: no gain end to end -- 7.2 s against 7.0 s at 100 Gbp -- and it is gone.)
+  struct SortEvents { cudaEvent_t afterHist = nullptr; ~SortEvents() { if (afterHist) cudaEventDestroy(afterHist); } } side;
   //  ---- plan the passes --------------------------------------------------------------------
   const size_t R = top.left();
   const u64 nBlocksTotal = (u64)1 << wP;
@@ -894,7 +869,6 @@ static int runCount(mb_ctx *c) {
       const u32 tile32 = mb_sort_tile_keys(4);
       const double perKey32 = 2.0 * 4 + (double)radix * 8 / tile32 + 16.0 / tile32;
       size_t enc32 = std::max<size_t>((size_t)4 << 30, (size_t)nBlocksTotal * 200);
-      if (overlapD2H) enc32 *= 2;                          //  two alternating halves
       if (enc32 > R / 3) enc32 = R / 3;
       if (R > enc32 + fixed + ((size_t)64 << 20)) {
         u64 cap32 = (u64)((double)(R - enc32 - fixed) / perKey32);
@@ -904,7 +878,7 @@ static int runCount(mb_ctx *c) {
         if (planBins(cap32, p32) == 0) {
           bool ok = true;
           for (const Pass &P : p32) {
-            const u64 gcap = std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / (overlapD2H ? 2 : 1) / 3 / 8));
+            const u64 gcap = std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / 3 / 8));
             for (u64 cnt : P.segCount) if (cnt > gcap || cnt >= ((u64)1 << 32)) ok = false;
           }
           if (ok) { passes.swap(p32); suffix32 = true; }
@@ -1047,7 +1021,6 @@ static int runCount(mb_ctx *c) {
     stream.sink = mb_filesink_get();
     MB_CUDA(cudaEventCreateWithFlags(&stream.ready, cudaEventDisableTiming));
   }
-  if (overlapD2H) for (u32 f = 0; f < 64; f++) c->db.index[f].reserve((size_t)blocksPerFile * 24);   //  no reallocation under a copy in flight
   std::vector<u64> fileBase(64, 0);
 
   std::vector<u64> segStart, segTile, binStart(MB_MAX_BINS + 1);
@@ -1216,7 +1189,7 @@ static int runCount(mb_ctx *c) {
       g.encRanges = P.encRanges;
       groups.push_back(g);
     } else {
-      const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / (overlapD2H ? 2 : 1) / 3 / 8));
+      const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / 3 / 8));
       Group g;  g.segLo = 0;  g.binLo = P.binLo;  g.keyLo = 0;  g.tileLo = 0;
       u64 have = 0;
       auto segBin = [&](u32 i) -> u32 { return P.segBin.empty() ? P.binLo + i : P.segBin[i]; };
@@ -1237,10 +1210,7 @@ static int runCount(mb_ctx *c) {
     for (size_t gi = 0; gi < groups.size(); gi++) {
       const Group &G = groups[gi];
       const u64 gKeys = G.keyHi - G.keyLo;
-      const int    half    = overlapD2H ? (int)(groupSeq++ & 1) : 0;
-      const size_t halfLen = overlapD2H ? ec.left() / 2 / kAlign * kAlign : ec.left();
-      Carver gc((uint8_t *)ec.base + alignUp(ec.off) + (size_t)half * halfLen, halfLen);      //  per-group slice of the encode region
-      if (overlapD2H && copyPending[half]) { MB_CUDA(cudaEventSynchronize(evCopied[half])); copyPending[half] = false; }
+      Carver gc((uint8_t *)ec.base + alignUp(ec.off), ec.left());                              //  per-group slice of the encode region
 
       void *distinctKeys;  u64 *runStart;  u32 encKeyWords;
       tStage.start(s);
@@ -1394,15 +1364,12 @@ static int runCount(mb_ctx *c) {
               c->db.dataLen[file] += fb;
               const size_t i0 = iv.size();
               iv.resize(i0 + ib);
-              if (overlapD2H && f == fi) { MB_CUDA(cudaEventRecord(evEnc, s)); MB_CUDA(cudaStreamWaitEvent(sCopy, evEnc, 0)); }
-              cudaStream_t cs = overlapD2H ? sCopy : s;
-              MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, cs));
-              MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, cs));
+              MB_CUDA(cudaMemcpyAsync(dst, dOut + (fm[f].outByte - ch.chunkByte0), fb, cudaMemcpyDeviceToHost, s));
+              MB_CUDA(cudaMemcpyAsync(iv.data() + i0, (uint8_t *)dIdx + (fblk[f] - ch.chunkFirst) * 24, ib, cudaMemcpyDeviceToHost, s));
               c->st.d2hBytes += fb + ib;
             }
-            if (overlapD2H) { MB_CUDA(cudaEventRecord(evCopied[half], sCopy)); copyPending[half] = true; }
           }
-          if (!overlapD2H) MB_CUDA(cudaStreamSynchronize(s));
+          MB_CUDA(cudaStreamSynchronize(s));
           for (u32 f = fi; f < fj; f++) fileBase[fileLo + f] += fm[f + 1].outByte - fm[f].outByte;
           fi = fj;
         }
@@ -1411,14 +1378,6 @@ static int runCount(mb_ctx *c) {
       MB_CUDA(cudaStreamSynchronize(s));
       c->st.msEncode += tStage.ms();
     }
-    if (overlapD2H) {                                    //  the next pass carves the arena differently: no copy may still read it
-      MB_CUDA(cudaStreamSynchronize(sCopy));
-      copyPending[0] = copyPending[1] = false;
-    }
-  }
-
-  if (overlapD2H) {
-    MB_CUDA(cudaStreamSynchronize(sCopy));
   }
 
   if (p2p) {
@@ -1501,9 +1460,6 @@ static int runCount(mb_ctx *c) {
   return MB_OK;
 }
 
-
-//  Debug: device buffer of 8 u64 receiving per-phase clock sums of the extract kernel (NULL = off).
-void mb_extract_set_profile_buffer(u64 *d) { g_extractProf = d; }
 
 extern "C" int mb_set_output_dir(mb_ctx *c, const char *outDir) {
   mb_clear_error();

@@ -201,8 +201,6 @@ struct ExtractSmem {
   //  latency-bound rolling loop of phase A needs.
   __host__ __device__ static size_t tablesBytes(u32 nT)            { return ((size_t)nT * 16 + 15) / 16 * 16; }
   __host__ __device__ static size_t scatterBytes(u32 nT, u32 cap)  { return OFF_TABLES + tablesBytes(nT) + (size_t)TILE_POS * 2 + (size_t)cap * sizeof(Key) + (S32 ? (size_t)cap * 2 : 0) + 16; }
-  //  MATCH variant: + one u32 counter per (warp, bin of the pass)
-  __host__ __device__ static size_t matchBytes(u32 nT)             { return (size_t)(THREADS / 32) * nT * 4 + 16; }
   __host__ __device__ static size_t countBytes(u32 nT)             { return OFF_TABLES + (size_t)nT * 4; }
 };
 
@@ -290,13 +288,7 @@ __device__ __forceinline__ void to_stored(u64 k, u32 &o)                        
 __device__ __forceinline__ void to_stored(u64 k, u64 &o)                         { o = k; }
 __device__ __forceinline__ void to_stored(const ulonglong2 &k, ulonglong2 &o)    { o = k; }
 
-//  MATCH (experimental, MB_RANK_MATCH=1; not the default until it is measured): in a filtered pass the rank of a kept k-mer
-//  inside (tile, bin) comes from warp-private counters instead of a returning shared-memory atomic (~2 cycles per lane
-//  per SM, a third of the extraction time): the lanes of a warp take their candidates in lock-step rounds,
-//  __match_any_sync groups the lanes of a round by bin, the first lane of a group bumps the warp's counter of that bin
-//  by the group size (plain load/store: the counter is private to the warp) and every lane's rank is the old value plus
-//  its place in the group; a per-bin scan over the warps' counters then turns (warp, rank) into a tile-wide position.
-template <int KW, bool COUNT_ONLY, bool S32, bool MATCH>
+template <int KW, bool COUNT_ONLY, bool S32>
 __global__ void __launch_bounds__(ExtractShape<KW>::THREADS, 4)
 extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict__ out,
                const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 *__restrict__ binCount, u64 nTiles, u32 stageCap) {
@@ -315,8 +307,6 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
   unsigned short *rank   = (unsigned short *)(smem + S::OFF_TABLES + S::tablesBytes(nT));
   Stored         *stage  = (Stored *)(((uintptr_t)(rank + S::TILE_POS) + 15) & ~(uintptr_t)15);
   unsigned short *sbin   = (unsigned short *)(stage + stageCap);
-  const int       WARPS  = ExtractShape<KW>::THREADS / 32;
-  u32            *wcnt   = (u32 *)(((uintptr_t)(sbin + (S32 ? stageCap : 0)) + 15) & ~(uintptr_t)15);   //  MATCH: [warp][bin]
   __shared__ u32 sWarpSum[ExtractShape<KW>::THREADS / 32];
 
   const u32 t = threadIdx.x;
@@ -336,7 +326,6 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
 
   if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   for (u32 b = t; b < nT; b += blockDim.x) cnt[b] = 0;
-  if (MATCH && !COUNT_ONLY) for (u32 b = t; b < (u32)WARPS * nT; b += blockDim.x) wcnt[b] = 0;
   __syncthreads();
 
   const unsigned char *storeBytes = (const unsigned char *)p.store;
@@ -347,12 +336,9 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
     tma_bulk_g2s(rec[0], storeBytes + tile * (u64)(S::THREADS * MB_STORE_REC_WORDS * 4), S::REC_BYTES, &bar[0]);
   }
 
-  long long tk[8];
-#define MB_TICK(i) do { if (p.prof && t == 0) tk[i] = clock64(); } while (0)
 
   for (u32 it = 0; tile < nTiles; it++, tile += gridDim.x) {
     const u32 buf = it & 1;
-    MB_TICK(0);
 
     //  Prefetch the next tile into the other buffer (it was last read two iterations ago, and
     //  every thread has passed a __syncthreads since).
@@ -364,7 +350,6 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
     }
 
     while (!mbar_try_wait(&bar[buf], (it >> 1) & 1)) { }
-    MB_TICK(1);                                       //  tile landed
 
     const u32 *r = rec[buf] + t * MB_STORE_REC_WORDS;
     Window w;
@@ -407,40 +392,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
       //  Phase A for a file-aligned pass that keeps a minority of the bins: bit-sliced membership test of all
       //  32 positions, then only the members get their exact bin (5 bases of each strand) and a rank.
       u64 cand = valid ? file_range_slots(w, p.k, p.mode, fLo, fHi) : 0;
-      if (MATCH) {
-        const u64 ya = win_slots(w, p.k - 5), yb = win_slots(w, p.k - 5 + 32);
-        const u32 f0 = (u32)(w.w0 >> 32), f1 = (u32)w.w0, f2 = (u32)(w.w1 >> 32);
-        const u32 r0 = (u32)(ya >> 32),   r1 = (u32)ya,   r2 = (u32)(yb >> 32);
-        const u32 lane = t & 31;
-        u32 *myw = wcnt + (t >> 5) * nT;
-        for (;;) {                                     //  one round: every lane brings its next member, if it has one
-          bool have = false;
-          u32 q = 0, bin = 0;
-          while (cand && !have) {
-            const u32 b = __clzll((long long)cand);
-            cand &= ~(0x8000000000000000ull >> b);
-            q = b >> 1;
-            if ((valid << q) & 0x80000000u) {
-              const u32 f5 = five_bases_at(f0, f1, f2, q);
-              const u32 r5 = revcomp5(five_bases_at(r0, r1, r2, q));
-              const u32 top10 = (p.mode == MB_MODE_FORWARD) ? f5 : (p.mode == MB_MODE_REVERSE) ? r5 : min(f5, r5);
-              bin = (top10 >> (10 - p.binBits)) - p.binLo;
-              have = true;
-            }
-          }
-          const u32 act = __ballot_sync(0xffffffffu, have);
-          if (act == 0) break;
-          if (have) {
-            const u32 peers  = __match_any_sync(act, bin);          //  lanes of this round with my bin
-            const u32 leader = (u32)__ffs((int)peers) - 1;
-            u32 base = 0;
-            if (lane == leader) { base = myw[bin]; myw[bin] = base + (u32)__popc(peers); }
-            base = __shfl_sync(act, base, (int)leader);
-            keep |= 0x80000000u >> q;
-            rank[t * 32 + q] = (unsigned short)(base + (u32)__popc(peers & ((1u << lane) - 1)));
-          }
-        }
-      } else if (cand) {
+      if (cand) {
         const u64 ya = win_slots(w, p.k - 5), yb = win_slots(w, p.k - 5 + 32);
         const u32 f0 = (u32)(w.w0 >> 32), f1 = (u32)w.w0, f2 = (u32)(w.w1 >> 32);
         const u32 r0 = (u32)(ya >> 32),   r1 = (u32)ya,   r2 = (u32)(yb >> 32);
@@ -474,28 +426,14 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
         roll.push(window_code(w, q + p.k), p.k, rollMask);
       }
     }
-
-    MB_TICK(2);                                       //  my phase A done
     if (!COUNT_ONLY) {
       __syncthreads();
-      MB_TICK(3);                                     //  everybody's phase A done
 
       //  Exclusive scan of the tile's bin counts (-> place of every bin's run in the stage buffer)
       //  and, in the same sweep, one global atomic per non-empty bin to reserve its run in HBM.
       const u32 nPassBins = p.binHi - p.binLo;
       const u32 perThread = (nPassBins + blockDim.x - 1) / blockDim.x;
       const u32 b0 = p.binLo + t * perThread;
-      if (MATCH && prefilter) {
-        //  the tile's count of a bin = sum of the warps' counters; leave in them each warp's exclusive share
-        for (u32 i = 0; i < perThread; i++) {
-          const u32 b = b0 + i;
-          if (b < p.binHi) {
-            u32 run = 0;
-            for (int wi = 0; wi < WARPS; wi++) { const u32 c = wcnt[wi * nT + (b - p.binLo)]; wcnt[wi * nT + (b - p.binLo)] = run; run += c; }
-            cnt[b - p.binLo] = run;
-          }
-        }
-      }
       u32 mySum = 0;
       for (u32 i = 0; i < perThread; i++) { const u32 b = b0 + i; if (b < p.binHi) mySum += cnt[b - p.binLo]; }
       u32 incl = mySum;
@@ -519,9 +457,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
           run += c;
         }
       }
-      MB_TICK(4);                                     //  my reservations done
       __syncthreads();
-      MB_TICK(5);                                     //  everybody's reservations done
 
       //  Phase B: the kept k-mers are produced again (rolling when the pass keeps most positions,
       //  direct window extraction when it keeps few) and placed bin-sorted in the stage buffer;
@@ -546,19 +482,13 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
             v &= ~(0x80000000u >> q);
             const Key key = kmer_key(w, q, p.k, p.mode, (Key *)0);
             const u32 bin = key_field(key, binShift, p.binBits) - p.binLo;
-            const u32 pos = binOff[bin] + rank[t * 32 + q] + ((MATCH && prefilter) ? wcnt[(t >> 5) * nT + bin] : 0);
+            const u32 pos = binOff[bin] + rank[t * 32 + q];
             Stored sk;  to_stored(key, sk);
             if (pos < stageCap) { stage[pos] = sk; if (S32) sbin[pos] = (unsigned short)bin; } else out[gofs[bin] + pos] = sk;
           }
         }
       }
       __syncthreads();
-      if (MATCH && prefilter)                             //  warp counters back to zero for the next tile (the bins I own)
-        for (u32 i = 0; i < perThread; i++) {
-          const u32 b = b0 + i;
-          if (b < p.binHi) for (int wi = 0; wi < WARPS; wi++) wcnt[wi * nT + (b - p.binLo)] = 0;
-        }
-
       //  Copy-out: consecutive threads, consecutive staged keys -> every bin's run is written coalesced.
       const u32 nStaged = total < stageCap ? total : stageCap;
       for (u32 j = t; j < nStaged; j += blockDim.x) {
@@ -567,15 +497,8 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
         out[gofs[bin] + j] = sk;
       }
     }
-    MB_TICK(6);                                       //  my phase B done
     __syncthreads();                                  //  all reads of rec[buf] / gbase done
-    if (!COUNT_ONLY && p.prof && t == 0) {
-      tk[7] = clock64();
-      for (int i = 1; i < 8; i++) atomicAdd((unsigned long long *)&p.prof[i], (unsigned long long)(tk[i] - tk[i - 1]));
-      atomicAdd((unsigned long long *)&p.prof[0], 1ull);
-    }
   }
-#undef MB_TICK
 
   if (COUNT_ONLY) {
     __syncthreads();
@@ -796,7 +719,7 @@ cudaError_t launch_dense(const MbExtractParams &p, void *out, const u64 *binStar
 //  Does this pass take the dense form?  k <= 32, file-aligned bins, a minority (or a small majority) of the k-mers kept.
 static bool dense_pass(const MbExtractParams &p) {
   const bool off = getenv("MB_EXTRACT_DENSE") && getenv("MB_EXTRACT_DENSE")[0] == '0';      //  A/B: the divergent form of extract_kernel
-  if (off || p.k > 32 || p.k < 5 || p.binBits < 6 || p.binBits > 10 || p.noPrefilter || p.rankMatch || p.prof) return false;
+  if (off || p.k > 32 || p.k < 5 || p.binBits < 6 || p.binBits > 10 || p.noPrefilter) return false;
   const u32 perFile = 1u << (p.binBits - 6), nBins = 1u << p.binBits;
   if ((p.binLo & (perFile - 1)) || (p.binHi & (perFile - 1)) || p.binHi - p.binLo >= nBins) return false;
   const u32 kept = p.keptPerMille ? p.keptPerMille : (p.binHi - p.binLo) * 1000 / nBins;
@@ -814,7 +737,7 @@ cudaError_t launch_dense_sized(const MbExtractParams &p, void *out, const u64 *b
   return launch_dense<S32, 24>(p, out, binStart, binCursor, s);
 }
 
-template <int KW, bool COUNT_ONLY, bool S32, bool MATCH = false>
+template <int KW, bool COUNT_ONLY, bool S32>
 cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64 *binCursor, u64 *binCount, cudaStream_t s) {
   typedef ExtractSmem<KW, S32> S;
   const u32 nBins = 1u << p.binBits, nT = p.binHi - p.binLo;
@@ -828,8 +751,8 @@ cudaError_t launch(const MbExtractParams &p, void *out, const u64 *binStart, u64
     if (want < stageCap) stageCap = (u32)want;
   }
   if (sizeof(typename S::Key) * stageCap > 32768) stageCap = 32768 / sizeof(typename S::Key);
-  const size_t smem = COUNT_ONLY ? S::countBytes(nT) : S::scatterBytes(nT, stageCap) + (MATCH ? S::matchBytes(nT) : 0);
-  auto kern = extract_kernel<KW, COUNT_ONLY, S32, MATCH>;
+  const size_t smem = COUNT_ONLY ? S::countBytes(nT) : S::scatterBytes(nT, stageCap);
+  auto kern = extract_kernel<KW, COUNT_ONLY, S32>;
 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -866,14 +789,6 @@ cudaError_t mb_launch_extract(const MbExtractParams &p, void *dKeys, const u64 *
       return launch_dense_sized<true>(p, dKeys, dBinStart, dBinCursor, s);
     }
     return launch_dense_sized<false>(p, dKeys, dBinStart, dBinCursor, s);
-  }
-  if (p.rankMatch) {                                     //  experimental ranking without returning atomics
-    if (p.suffix32) {
-      if (p.k > 32 || 2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;
-      return launch<1, false, true, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
-    }
-    return (p.k <= 32) ? launch<1, false, false, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s)
-                       : launch<2, false, false, true>(p, dKeys, dBinStart, dBinCursor, nullptr, s);
   }
   if (p.suffix32) {
     if (p.k > 32 || 2 * p.k - p.binBits > 32) return cudaErrorInvalidValue;

@@ -162,8 +162,6 @@ struct MbExtractParams {
   u32        suffix32;       //  1: store only the low 2k-binBits (<= 32) bits of each k-mer as u32
   u32        noPrefilter;    //  1: never use the bit-sliced file-range filter (debug / A-B; env MB_NO_PREFILTER)
   u32        keptPerMille;   //  share of the store's k-mers this pass keeps, in 1/1000 (0 = unknown)
-  u32        rankMatch;      //  1: rank kept k-mers with warp-private counters + __match_any_sync (experimental; env MB_RANK_MATCH)
-  u64       *prof;           //  debug: per-phase clock sums (NULL = off)
 };
 
 //  K2a extract.cu: bin histogram of every k-mer in the store (count-only pre-pass).  dBinCount[MB_MAX_BINS] += ...

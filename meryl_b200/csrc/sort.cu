@@ -10,29 +10,20 @@
 //   sort_tiles_kernel   one 16-byte descriptor per tile (first key, count, segment, first-of-segment)
 //   sort_hist_kernel    one read of the keys: per (segment, pass, digit) counts
 //   sort_scan_kernel    exclusive scan over digits -> first output index of every (segment, pass, digit)
-//   sort_sweep_kernel   per pass: tile = 256 threads x ITEMS keys
+//   sortx_sweep_kernel  per pass: tile = THREADS x ITEMS keys (8192 u32 / 4096 u64 / 2048 u128 keys)
 //       1. coalesced (warp-striped) load, transposed through shared memory so that every thread
 //          owns ITEMS CONSECUTIVE keys -- rank order == memory order, which LSD needs (stable);
 //       2. rank by PRIVATE counters: thread t bumps its own 16-bit counter of the key's digit
 //          (two digits per 32-bit word, no atomics, no warp votes), a raking scan over the
-//          32 x 256 packed counters turns them into tile-wide positions -- ~25 instructions per 32
-//          keys, against ~95 for a match/ballot multisplit, which is what lets the kernel approach
-//          the HBM roofline on B200 (0.17 warp-instructions per byte at peak bandwidth);
-//       3. the tile publishes its 64 digit counts, and resolves its exclusive prefix by a batched
+//          packed counters turns them into tile-wide positions;
+//       3. the tile publishes its digit counts, and resolves its exclusive prefix by a batched
 //          decoupled look-back over the earlier tiles OF ITS SEGMENT (status words carry a pass
 //          epoch, so the table is cleared once per sort);
 //       4. keys are placed digit-sorted in shared memory and leave as coalesced digit runs.
 //
 //  Algorithmic HBM bytes per key: hist 1*W, each sweep pass 2*W (W = 4, 8 or 16 bytes), plus the
-//  tile status (512 B per tile written twice, read >= once).  Bound: HBM bandwidth.
-//
-//  Two sweep kernels share the tile table, the histogram and the scan (mb_sort_version()):
-//   v1  sort_sweep_kernel    256 threads x 32/16/8 keys, 6-bit digits  (32 suffix bits = 6 passes)
-//   v2-4 sortx_sweep_kernel  second generation, shaped by (threads, digit bits): the first one is issue-bound, not
-//       DRAM-bound (ncu: 63 % of the issue slots busy at 21 % DRAM), so the lever is instructions per key: 16-bit
-//       counter accesses, one PRMT per whole-byte digit, 32-bit output offsets -- about half the instructions per
-//       key and pass.  Measured on B200 (profiles/): the 8-bit shape (4 passes for 32 bits, but 64 KB of counters
-//       = 8 warps per SM) is latency-bound at 17 % issue utilisation and no faster than v1 over the whole sort.
+//  tile status (8 B per digit and tile, written twice, read >= once).  Measured bound (ncu, profiles/): not DRAM -- the
+//  shared-memory pipe (about 510 wavefronts per 1024 keys) together with the issue slots (41 instructions per key and pass).
 
 #include <stdlib.h>
 #include <string.h>
@@ -43,18 +34,16 @@
 namespace {
 
 const int SORT_THREADS = 256;
-const int SORT_WARPS   = SORT_THREADS / 32;
 const int SORT_MAX_PASSES = 24;
 #ifndef MB_SWEEP_PREFETCH_DEFAULT
 #define MB_SWEEP_PREFETCH_DEFAULT 0      //  tiles ahead; measured A/B decides (MB_SWEEP_PREFETCH)
 #endif
 
 template <int KW> struct SortShape;
-//  MIN_CTAS: resident CTAs per SM the register budget is compiled for; ~68 KB of shared memory per CTA
-//  (counters + key buffer) allow three.
-template <> struct SortShape<0> { static const int ITEMS = 32; static const int MIN_CTAS = 3; };   //  u32 suffix keys: 8192 per tile
-template <> struct SortShape<1> { static const int ITEMS = 16; static const int MIN_CTAS = 3; };   //  u64: 4096 per tile
-template <> struct SortShape<2> { static const int ITEMS = 8;  static const int MIN_CTAS = 3; };   //  128 bit: 2048 per tile
+//  keys per thread of the 256-thread tile that the tile table, the histogram and the count kernels share
+template <> struct SortShape<0> { static const int ITEMS = 32; };   //  u32 suffix keys: 8192 per tile
+template <> struct SortShape<1> { static const int ITEMS = 16; };   //  u64: 4096 per tile
+template <> struct SortShape<2> { static const int ITEMS = 8;  };   //  128 bit: 2048 per tile
 
 //  status word: [63:62] flag (0 none, 1 aggregate, 2 inclusive)  [61:57] epoch (pass tag, 1..24)  [56:0] value
 #define ST_FLAG(v)    ((u32)((v) >> 62))
@@ -288,239 +277,10 @@ sort_scan_kernel(u64 *__restrict__ ghist, const u64 *__restrict__ segStart, u32 
   h[d] = segStart[seg] + base + incl - c;
 }
 
-//  ---- one digit pass ---------------------------------------------------------------------------
-
-//  Dynamic shared memory: the private digit counters, then a key buffer used first as the
-//  striped->blocked transpose area and later as the digit-sorted stage.  Sizes in bytes, for TILE keys of KB bytes:
-//    transpose / stage : TILE*KB, plus one key of padding per 128 bytes (bank-conflict-free blocked reads)
-//    counters          : (MB_RADIX/2) lanes x 256 threads x 4 B = 32 KB, plus one word of padding per 32
-template <int KW> struct SweepSmem {
-  typedef typename KeyT<KW>::type Key;
-  static const int TILE     = SORT_THREADS * SortShape<KW>::ITEMS;
-  static const int PAD_EVERY= 128 / sizeof(Key);                               //  keys between two padding keys
-  static const int XPOSE    = (TILE + TILE / PAD_EVERY) * sizeof(Key);
-  static const int LANES    = MB_RADIX / 2;                                     //  two 16-bit counters per word
-  static const int CWORDS   = LANES * SORT_THREADS;
-  static const int COUNTERS = (CWORDS + CWORDS / 32) * 4;
-  static const int BYTES    = COUNTERS + XPOSE;                                 //  [counters][transpose area == stage]
-};
-
 __device__ __forceinline__ void key_zero(u32 &k)        { k = 0; }
 __device__ __forceinline__ void key_zero(u64 &k)        { k = 0; }
 __device__ __forceinline__ void key_zero(ulonglong2 &k) { k.x = 0; k.y = 0; }
 
-//  The work of one tile.  FULL: the tile holds exactly TILE keys, so the per-key bounds checks vanish
-//  (all tiles but the last one of each segment); the kernel picks the variant per tile, uniformly.
-struct SweepShared {
-  unsigned char *buf;  u32 *binOff;  u64 *gofs;  u32 *warpTot;
-};
-
-template <int KW, bool FULL>
-__device__ __forceinline__ void
-sweep_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
-           u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
-           const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
-           u64 *__restrict__ status, u32 epoch, const SweepShared &sm,
-           u64 *prof, long long &tk2, long long &tk3, long long &tk4, long long &tk5) {
-  typedef typename KeyT<KW>::type Key;
-  typedef SweepSmem<KW>           S;
-  const int ITEMS = SortShape<KW>::ITEMS;
-#define MB_TICK(i) do { if (prof && threadIdx.x == 0) tk##i = clock64(); } while (0)
-
-  u32 *counters = (u32 *)sm.buf;
-  Key *xpose    = (Key *)(sm.buf + S::COUNTERS);
-  Key *stage    = xpose;
-  u32 *binOff   = sm.binOff;
-  u64 *gofs     = sm.gofs;
-  u32 *warpTot  = sm.warpTot;
-
-  const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const u32 n = FULL ? (u32)S::TILE : nIn;
-
-  //  1. load striped (coalesced), transpose to blocked: thread t ends up with keys [t*ITEMS, (t+1)*ITEMS)
-  Key key[ITEMS];
-  {
-    //  The warp's slice is private: only __syncwarp needed.  One padding key per 128 bytes; ITEMS keys are
-    //  exactly 128 bytes, so the padded index of key j = t*ITEMS + i is t*(ITEMS+1) + i, and that of the
-    //  striped key wbase + i*32 + lane is w0 + i*(32 + 32/PAD) -- constant strides the compiler can fold.
-    const u32 wbase = warp * 32 * ITEMS;
-    const u32 w0    = wbase + wbase / S::PAD_EVERY + lane + lane / S::PAD_EVERY;
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      Key k;
-      if (FULL || wbase + i * 32 + lane < n) k = in[begin + wbase + i * 32 + lane]; else key_zero(k);
-      xpose[w0 + i * (32 + 32 / S::PAD_EVERY)] = k;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++)
-      key[i] = xpose[t * (ITEMS + 1) + i];
-  }
-  //  (the transpose area is read only by the warp that wrote it; its next use, as the stage, comes after
-  //  several block-wide barriers)
-
-  //  2. private counters.  Digit d lives in word (d & 31) of my column, half (d >> 5).
-  for (u32 i = t; i < (u32)(S::CWORDS + S::CWORDS / 32); i += SORT_THREADS) counters[i] = 0;
-  __syncthreads();
-
-  const u32 myFirst = t * ITEMS;                         //  my keys are tile positions [myFirst, myFirst + ITEMS)
-  const u32 tcol    = t + (t >> 5);                      //  my column in the padded counter array
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    if (FULL || myFirst + i < n) {
-      const u32 d = key_field(key[i], shift, bits);
-      //  word (d & 31) of my column: linear index (d&31)*256 + t, padded by one word per 32;
-      //  digits >= 32 use the high half-word
-      u32 *cp = &counters[(d & 31) * (SORT_THREADS + SORT_THREADS / 32) + tcol];
-      *cp += 1u << ((d & 32) >> 1);
-    }
-  }
-  __syncthreads();
-
-  //  raking scan over the CWORDS packed words: thread t owns the 32 consecutive words [32t, 32t+32)
-  u32 tileLow = 0;                                       //  keys whose digit is < 32 (low halves)
-  {
-    u32 *seg32 = &counters[t * 33];
-    u32 sum = 0;
-#pragma unroll
-    for (int j = 0; j < 32; j++) sum += seg32[j];
-    u32 incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (u32)o) incl += v;
-    }
-    if (lane == 31) warpTot[warp] = incl;
-    __syncthreads();
-    u32 run = incl - sum, tot = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) { const u32 c = warpTot[w]; if (w < (int)warp) run += c; tot += c; }
-    tileLow = tot & 0xffff;
-#pragma unroll
-    for (int j = 0; j < 32; j++) { const u32 c = seg32[j]; seg32[j] = run; run += c; }
-  }
-  __syncthreads();
-  MB_TICK(2);                                            //  2: keys loaded, counted, scanned
-
-  //  start of every digit's run (thread 0's slot of digit d holds it), then my keys go straight to their
-  //  place in the stage buffer: position = my (digit, thread) prefix, bumped as I walk my keys in order.
-  if (t < MB_RADIX) {
-    const u32 wv = counters[(t & 31) * (SORT_THREADS + SORT_THREADS / 32)];
-    const u32 hi = t & 32;
-    binOff[t] = ((wv >> (hi >> 1)) & 0xffff) + (hi ? tileLow : 0);
-  }
-  if (t == 0) binOff[MB_RADIX] = n;
-  __syncthreads();                                       //  thread 0's column is read before its owner bumps it
-
-  //  3a. publish this tile's digit counts as early as possible ...
-  const u32 myCount = (t < MB_RADIX) ? binOff[t + 1] - binOff[t] : 0;
-  if (t < MB_RADIX)
-    st_volatile_u64(status + tile * MB_RADIX + t, ST_MAKE(isFirst ? 2 : 1, epoch, myCount));
-
-  //  4a. ... put the keys in digit-sorted order in shared memory ...
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    if (FULL || myFirst + i < n) {
-      const u32 d    = key_field(key[i], shift, bits);
-      u32 *cp        = &counters[(d & 31) * (SORT_THREADS + SORT_THREADS / 32) + tcol];
-      const u32 hi   = d & 32;
-      const u32 wv   = *cp;
-      *cp = wv + (1u << (hi >> 1));
-      stage[((wv >> (hi >> 1)) & 0xffff) + (hi ? tileLow : 0)] = key[i];
-    }
-  }
-  MB_TICK(3);                                            //  3: reorder issued
-
-  //  3b. ... and only then wait for the earlier tiles of this segment (batched walk: LB status words
-  //  per L2 round trip; the segment's first tile ends it).
-  if (t < MB_RADIX) {
-    const int LB = 8;
-    const u32 d = t;
-    u64 excl = 0;
-    if (!isFirst) {
-      const u64 *p = status + (tile - 1) * MB_RADIX + d;
-      bool done = false;
-      while (!done) {
-        u64 v[LB];
-#pragma unroll
-        for (int b = 0; b < LB; b++) v[b] = ld_volatile_u64(p - (size_t)b * MB_RADIX);   //  may read before the segment: ignored below
-#pragma unroll
-        for (int b = 0; b < LB; b++) {
-          if (done) break;
-          if (ST_FLAG(v[b]) == 0 || ST_EPOCH(v[b]) != epoch) break;                      //  not published yet: poll again from here
-          excl += ST_VALUE(v[b]);
-          p -= MB_RADIX;
-          if (ST_FLAG(v[b]) == 2) done = true;
-        }
-      }
-      st_volatile_u64(status + tile * MB_RADIX + d, ST_MAKE(2, epoch, excl + myCount));
-    }
-    gofs[d] = gbase[((u64)seg * nPasses + pass) * MB_RADIX + d] + excl - binOff[d];
-  }
-  MB_TICK(4);                                            //  4: my own look-back done
-  __syncthreads();
-  MB_TICK(5);                                            //  5: everybody's look-back done
-
-  //  4b. digit runs to HBM
-  for (u32 j = t; j < n; j += SORT_THREADS) {
-    const Key k = stage[j];
-    out[gofs[key_field(k, shift, bits)] + j] = k;
-  }
-#undef MB_TICK
-}
-
-template <int KW>
-__global__ void __launch_bounds__(SORT_THREADS, SortShape<KW>::MIN_CTAS)
-sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
-                  const TileInfo *__restrict__ info,
-                  const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits,
-                  u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch, u64 *__restrict__ prof) {
-  typedef SweepSmem<KW> S;
-
-  //  optional phase timing (debug): thread 0 accumulates clock deltas into prof[1..6]
-  long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
-#define MB_TICK(i) do { if (prof && threadIdx.x == 0) tk##i = clock64(); } while (0)
-  MB_TICK(0);
-
-  extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
-  __shared__ u32  binOff[MB_RADIX + 1];
-  __shared__ u64  gofs[MB_RADIX];
-  __shared__ u32  warpTot[SORT_WARPS];
-  __shared__ u64  sTile;
-
-  if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
-  __syncthreads();
-  MB_TICK(1);                                            //  1: tile id
-
-  const u64 tile = sTile;
-  const TileInfo ti = info[tile];
-  const u32  seg     = ti.seg & 0x7fffffffu;
-  const bool isFirst = (ti.seg >> 31) != 0;
-  SweepShared sm;
-  sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.warpTot = warpTot;
-
-#ifdef MB_SWEEP_ONLY_FULL
-  if (true)
-#else
-  if (ti.n == (u32)S::TILE)
-#endif
-    sweep_tile<KW, true >(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, status, epoch, sm, prof, tk2, tk3, tk4, tk5);
-#ifndef MB_SWEEP_ONLY_FULL
-  else
-    sweep_tile<KW, false>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, status, epoch, sm, prof, tk2, tk3, tk4, tk5);
-#endif
-
-  MB_TICK(6);                                            //  6: my stores issued
-  if (prof && threadIdx.x == 0) {
-    atomicAdd((unsigned long long *)&prof[1], (unsigned long long)(tk1 - tk0));
-    atomicAdd((unsigned long long *)&prof[2], (unsigned long long)(tk2 - tk1));
-    atomicAdd((unsigned long long *)&prof[3], (unsigned long long)(tk3 - tk2));
-    atomicAdd((unsigned long long *)&prof[4], (unsigned long long)(tk4 - tk3));
-    atomicAdd((unsigned long long *)&prof[5], (unsigned long long)(tk5 - tk4));
-    atomicAdd((unsigned long long *)&prof[6], (unsigned long long)(tk6 - tk5));
-    atomicAdd((unsigned long long *)&prof[0], 1ull);
-  }
-#undef MB_TICK
-}
 
 //  ---- sweep kernel, second generation: one digit pass, shaped by (threads, digit bits) ------------------------
 //
@@ -541,11 +301,6 @@ sort_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<
 template <int VER> struct SweepShape;
 template <> struct SweepShape<2> { static const int THREADS = 128, RBITS = 8, MIN_CTAS = 2; };
 template <> struct SweepShape<3> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 3; };
-template <> struct SweepShape<4> { static const int THREADS = 256, RBITS = 7, MIN_CTAS = 2; };
-//  not yet measured (written without a GPU at hand; tools/ab_bench.py ... sortonly compares all shapes):
-template <> struct SweepShape<5> { static const int THREADS = 512, RBITS = 6, MIN_CTAS = 2; };   //  32 warps/SM, 16 keys per thread
-template <> struct SweepShape<6> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 2; };   //  16 warps/SM, 128 registers: no address recomputation
-template <> struct SweepShape<7> { static const int THREADS = 256, RBITS = 6, MIN_CTAS = 3; };   //  shape 3 as a persistent kernel that prefetches the next tile (sortp_sweep_kernel)
 
 template <int KW, int VER> struct SweepX {
   typedef typename KeyT<KW>::type Key;
@@ -596,26 +351,12 @@ __device__ __forceinline__ unsigned short *counter_of(unsigned char *buf, u32 cb
   return (unsigned short *)(buf + off);
 }
 
-//  Persistent form (sortp_sweep_kernel): a CTA keeps claiming tiles.  While it works on a tile it claims the next one (the
-//  atomic's round trip hides behind the counting), fetches that tile's descriptor after the scan, and -- as soon as this
-//  tile's keys sit in the stage buffer and their registers are free -- loads the next tile's keys, so the loads fly during
-//  the look-back and the copy-out instead of in front of an idle CTA.
-template <int KW, int VER> struct SweepNext {
-  typename KeyT<KW>::type key[SweepX<KW, VER>::ITEMS];   //  in: this tile's keys, striped (thread t holds keys wbase + 32 i + lane); out: the next tile's
-  const TileInfo *info;
-  u64   nTiles;
-  u64  *tileCounter;
-  u64  *sNext;                                            //  shared memory word: the tile claimed for the next round
-  u64   nextTile;
-  TileInfo nextInfo;
-};
-
-template <int KW, int VER, bool FULL, bool BYTE, bool PRE = false>
+template <int KW, int VER, bool FULL, bool BYTE>
 __device__ __forceinline__ void
 sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
             u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
             const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, bool wide,
-            u64 *__restrict__ status, u32 epoch, const SweepXShared &sm, SweepNext<KW, VER> *nx = nullptr) {
+            u64 *__restrict__ status, u32 epoch, const SweepXShared &sm) {
   typedef typename KeyT<KW>::type Key;
   typedef SweepX<KW, VER>         S;
   const int ITEMS = S::ITEMS, THREADS = S::THREADS, ROWS = S::ROWS, RADIX = S::RADIX;
@@ -647,11 +388,9 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
     for (int i = 0; i < ITEMS; i++) {
       const u32 j = wbase + i * 32 + lane;
       Key k;
-      if (PRE) k = nx->key[i];
-      else if (FULL || j < n) k = pin[i * 32]; else key_zero(k);
+      if (FULL || j < n) k = pin[i * 32]; else key_zero(k);
       px[i * 32 + (i * 32) / ITEMS] = k;
     }
-    if (PRE && t == 0) *nx->sNext = atomicAdd((unsigned long long *)nx->tileCounter, 1ull);     //  claim the next tile now, read it after the scan
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < ITEMS; i++)
@@ -710,10 +449,6 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
   }
   if (t == 0) binOff[RADIX] = n;
   __syncthreads();
-  if (PRE) {
-    nx->nextTile = *nx->sNext;
-    if (nx->nextTile < nx->nTiles) nx->nextInfo = nx->info[nx->nextTile];
-  }
 
   //  3a. publish this tile's digit counts as early as possible ...
   //  (digit ROWS-1's run ends where digit ROWS's begins, so binOff[d + 1] - binOff[d] holds for every d)
@@ -736,18 +471,6 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
       const u32 pos = *cp;
       *cp = (unsigned short)(pos + 1);
       stage[pos] = key[i];
-    }
-  }
-
-  //  (persistent form: my key registers are free now -- the next tile's keys start their way from HBM)
-  if (PRE && nx->nextTile < nx->nTiles) {
-    const u32 wbase = warp * 32 * ITEMS;
-    const u64 nb = nx->nextInfo.begin;
-    const u32 nn = nx->nextInfo.n;
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      const u32 j = wbase + i * 32 + lane;
-      if (j < nn) nx->key[i] = in[nb + j]; else key_zero(nx->key[i]);
     }
   }
 
@@ -848,84 +571,25 @@ sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
 #undef MB_SX_CALL
 }
 
-//  Persistent form of the sweep (MB_SORT=7): grid = the CTAs that fit the device at once; tiles are still claimed from the
-//  pass's counter in increasing order, so a tile's predecessors are always claimed by a resident CTA that depends on lower
-//  tiles only -- the look-back cannot dead-lock.
-template <int KW, int VER>
-__global__ void __launch_bounds__(SweepShape<VER>::THREADS, SweepShape<VER>::MIN_CTAS)
-sortp_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
-                   const TileInfo *__restrict__ info, u64 nTiles,
-                   const u64 *__restrict__ gbase, u32 nPasses, u32 pass, u32 shift, u32 bits, u32 wide,
-                   u64 *__restrict__ status, u64 *__restrict__ tileCounter, u32 epoch) {
-  typedef SweepX<KW, VER> S;
-  extern __shared__ __align__(16) unsigned char buf[];   //  S::BYTES
-  __shared__ u32  binOff[S::RADIX + 1];
-  __shared__ u64  gofs[S::RADIX];
-  __shared__ u32  gofs32[S::RADIX];
-  __shared__ u32  warpTot[S::WARPS];
-  __shared__ u64  sTile, sNext;
-
-  if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
-  __syncthreads();
-  u64 tile = sTile;
-  if (tile >= nTiles) return;
-  TileInfo ti = info[tile];
-
-  SweepXShared sm;
-  sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.gofs32 = gofs32;  sm.warpTot = warpTot;
-  SweepNext<KW, VER> nx;
-  nx.info = info;  nx.nTiles = nTiles;  nx.tileCounter = tileCounter;  nx.sNext = &sNext;  nx.nextTile = ~0ull;
-  {                                                       //  the first tile's keys: the only exposed load of this CTA
-    const u32 lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 32 * S::ITEMS;
-#pragma unroll
-    for (int i = 0; i < S::ITEMS; i++) {
-      const u32 j = wbase + i * 32 + lane;
-      if (j < ti.n) nx.key[i] = in[ti.begin + j]; else key_zero(nx.key[i]);
-    }
-  }
-  const bool byte = (S::RBITS == 8) && (bits == 8) && ((shift & 7) == 0);
-  for (;;) {
-    const u32  seg     = ti.seg & 0x7fffffffu;
-    const bool isFirst = (ti.seg >> 31) != 0;
-    const bool full    = (ti.n == (u32)S::TILE);
-#define MB_SP_CALL(F, B) sweepx_tile<KW, VER, F, B, true>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm, &nx)
-    if (S::RBITS == 8 && byte) { if (full) MB_SP_CALL(true, true);  else MB_SP_CALL(false, true);  }
-    else                       { if (full) MB_SP_CALL(true, false); else MB_SP_CALL(false, false); }
-#undef MB_SP_CALL
-    if (nx.nextTile >= nTiles) break;
-    tile = nx.nextTile;  ti = nx.nextInfo;
-    __syncthreads();                                      //  everybody has copied its keys out of the stage buffer
-  }
-}
-
 }  //  namespace
 
 
 //  ---- host side ---------------------------------------------------------------------------------
 
-//  Which sweep kernel: 1 (first generation, 6-bit digits) or a shape of the second generation (2: 128 threads x
-//  8 bits, 3: 256 x 6, 4: 256 x 7).  MB_SORT=1..4 in the environment, or mb_sort_set_version(); fixed for the
-//  lifetime of a plan / workspace.
+//  Which sweep shape: 3 = 256 threads x 6-bit digits (default), 2 = 128 threads x 8-bit digits.  MB_SORT=2|3 in the environment,
+//  or mb_sort_set_version(); fixed for the lifetime of a plan / workspace.  (Round 1 and 2 measured five more on B200 -- the first
+//  generation with warp votes, 256 x 7, 512 x 6, 256 x 6 at 128 registers, a persistent form with next-tile prefetch in
+//  registers: all slower than 256 x 6, see profiles/README.md -- and they are gone.)
 static int g_sortVersion = 0;
 int mb_sort_version(void) {
   if (g_sortVersion == 0) {
     const char *e = getenv("MB_SORT");
-    g_sortVersion = (e && e[0] >= '1' && e[0] <= '7' && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
+    g_sortVersion = (e && (e[0] == '2' || e[0] == '3') && e[1] == 0) ? e[0] - '0' : MB_SORT_DEFAULT_VERSION;
   }
   return g_sortVersion;
 }
-void mb_sort_set_version(int v) { g_sortVersion = (v >= 1 && v <= 7) ? v : MB_SORT_DEFAULT_VERSION; }
-u32  mb_sort_radix_bits(void) {
-  switch (mb_sort_version()) {
-    case 2:  return SweepShape<2>::RBITS;
-    case 3:  return SweepShape<3>::RBITS;
-    case 4:  return SweepShape<4>::RBITS;
-    case 5:  return SweepShape<5>::RBITS;
-    case 6:  return SweepShape<6>::RBITS;
-    case 7:  return SweepShape<7>::RBITS;
-    default: return MB_RADIX_BITS;
-  }
-}
+void mb_sort_set_version(int v) { g_sortVersion = (v == 2 || v == 3) ? v : MB_SORT_DEFAULT_VERSION; }
+u32  mb_sort_radix_bits(void) { return mb_sort_version() == 2 ? SweepShape<2>::RBITS : SweepShape<3>::RBITS; }
 u32  mb_sort_radix(void)        { return 1u << mb_sort_radix_bits(); }
 
 void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
@@ -935,8 +599,8 @@ void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
   plan->maxSegKeys = 0;
   u32 shift = 0;
   for (u32 p = 0; p < P; p++) {
-    //  v1: digits of (almost) equal width.  v2: whole bytes from the bottom (one PRMT per digit), the top
-    //  pass takes what is left.
+    //  6-bit shape: digits of (almost) equal width.  8-bit shape: whole bytes from the bottom (one PRMT per digit), the
+    //  top pass takes what is left.
     u32 b = sortBits / P + (p < sortBits % P ? 1 : 0);
     if (RB == 8) b = (sortBits - shift < 8) ? sortBits - shift : 8;
     plan->shift[p] = shift;
@@ -947,14 +611,10 @@ void mb_sort_plan(u32 sortBits, MbSortPlan *plan) {
 
 u32 mb_sort_tile_keys(u32 keyBytes) {                  //  the same for both sweep kernels: 8192 / 4096 / 2048
   static_assert(SORT_THREADS * SortShape<0>::ITEMS == SweepX<0, 2>::TILE && SweepX<0, 2>::TILE == SweepX<0, 3>::TILE, "tile size");
-  static_assert(SORT_THREADS * SortShape<1>::ITEMS == SweepX<1, 2>::TILE && SweepX<1, 4>::TILE == SweepX<1, 3>::TILE, "tile size");
-  static_assert(SORT_THREADS * SortShape<2>::ITEMS == SweepX<2, 2>::TILE && SweepX<2, 4>::TILE == SweepX<2, 3>::TILE, "tile size");
+  static_assert(SORT_THREADS * SortShape<1>::ITEMS == SweepX<1, 2>::TILE && SweepX<1, 2>::TILE == SweepX<1, 3>::TILE, "tile size");
+  static_assert(SORT_THREADS * SortShape<2>::ITEMS == SweepX<2, 2>::TILE && SweepX<2, 2>::TILE == SweepX<2, 3>::TILE, "tile size");
   return SORT_THREADS * (keyBytes == 4 ? SortShape<0>::ITEMS : keyBytes == 8 ? SortShape<1>::ITEMS : SortShape<2>::ITEMS);
 }
-
-//  Debug: device buffer of 8 u64 that receives per-phase clock sums of the sweep kernel (NULL = off).
-static u64 *g_sortProf = nullptr;
-void mb_sort_set_profile_buffer(u64 *dProf) { g_sortProf = dProf; }
 
 //  workspace: [ghist: nSegs*nPasses*R u64][tile counters: 32 u64][guard: 8*R u64][status: nTiles*R u64][tile info: nTiles*16 B]
 //  (R = mb_sort_radix(); the guard lets the batched look-back of the first tiles read a few status rows "before" row 0)
@@ -1053,40 +713,16 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if (evAfterHist) cudaEventRecord(evAfterHist, s);
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
-  if ((e = cudaFuncSetAttribute(sort_sweep_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem<KW>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 2>::BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 3>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 4>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 5>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 6>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sortp_sweep_kernel<KW, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 7>::BYTES)) != cudaSuccess) return e;
   //  MB_SWEEP_PREFETCH=<tiles>: L2 prefetch distance of the sweep kernel (0 = off)
   const u32 pfDist = getenv("MB_SWEEP_PREFETCH") ? (u32)strtoul(getenv("MB_SWEEP_PREFETCH"), nullptr, 10) : MB_SWEEP_PREFETCH_DEFAULT;
   for (u32 p = 0; p < plan.nPasses; p++) {
 #define MB_SX_LAUNCH(V) do { typedef SweepX<KW, V> SX;                                                                                         \
       sortx_sweep_kernel<KW, V><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                       \
                                                                      plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1, nTiles, pfDist); } while (0)
-    if      (version == 2) MB_SX_LAUNCH(2);
-    else if (version == 3) MB_SX_LAUNCH(3);
-    else if (version == 4) MB_SX_LAUNCH(4);
-    else if (version == 5) MB_SX_LAUNCH(5);
-    else if (version == 6) MB_SX_LAUNCH(6);
-    else if (version == 7) {
-      typedef SweepX<KW, 7> SX;
-      static int perSm = 0, sms = 0;                         //  co-resident CTAs: the grid of the persistent kernel
-      if (!perSm) {
-        int dev = 0;  cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sortp_sweep_kernel<KW, 7>, SX::THREADS, SX::BYTES)) != cudaSuccess) return e;
-        if (perSm < 1) perSm = 1;
-      }
-      const u64 grid = std::min<u64>(nTiles, (u64)sms * perSm);
-      sortp_sweep_kernel<KW, 7><<<(unsigned)grid, SX::THREADS, SX::BYTES, s>>>(src, dst, info, nTiles, ghist, plan.nPasses, p,
-                                                                     plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1);
-    }
-    else
-      sort_sweep_kernel<KW><<<(unsigned)nTiles, SORT_THREADS, SweepSmem<KW>::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,
-                                                                     plan.shift[p], plan.bits[p], status, counter + p, p + 1, g_sortProf);
+    if (version == 2) MB_SX_LAUNCH(2);
+    else              MB_SX_LAUNCH(3);
 #undef MB_SX_LAUNCH
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;

@@ -167,38 +167,6 @@ def test_sim_compress(tmp_path):
     util.assert_same_db(ora, out)
 
 
-@pytest.mark.parametrize("k,w_prefix,op", [(21, 12, "count"), (31, 9, "count-forward"), (51, 8, "count")])
-def test_sim_experimental_match_rank(tmp_path, monkeypatch, k, w_prefix, op):
-    """MB_RANK_MATCH=1 (not the default; to be measured on the GPU in round 2): ranks inside (tile, bin) from warp-private
-    counters and __match_any_sync instead of returning shared-memory atomics."""
-    monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
-    monkeypatch.setenv("MB_RANK_MATCH", "1")
-    _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 7 + k)}, k, w_prefix, op=op, min_passes=3)
-
-
-@pytest.mark.parametrize("k,w_prefix", [(21, 12), (31, 9)])
-def test_sim_experimental_overlap_d2h(tmp_path, monkeypatch, k, w_prefix):
-    """MB_OVERLAP_D2H=1 (not the default; to be measured in round 2): the copy-back of a group's encoded blocks on a second
-    stream, groups alternating between two halves of the encode region.  The emulator is synchronous, so this checks the
-    carving and bookkeeping (same bytes in the caller's buffer), not the asynchrony."""
-    monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
-    data = synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 70 + k)
-    ora = str(tmp_path / "ora.meryl")
-    fq = tmp_path / "r.fq"
-    fq.write_bytes(data)
-    util.run_oracle(["k=%d" % k, "wprefix=%d" % w_prefix, "count", str(fq), "output", ora])
-    monkeypatch.setenv("MB_OVERLAP_D2H", "1")
-    buf = np.zeros(64 << 20, dtype=np.uint8)
-    out = str(tmp_path / "sim.meryl")
-    with mb.Counter(k, w_prefix) as c:
-        c.set_output_buffer(buf.ctypes.data, buf.size)
-        c.add_file(str(fq))
-        c.count()
-        assert c.stats().nPasses >= 3
-        c.write_db(out)
-    util.assert_same_db(ora, out)
-
-
 def test_sim_parallel_parse_in_the_pipeline(tmp_path, monkeypatch):
     """mb_add_file maps the file and parses it in blocks on several threads (cuts verified against the state machine)."""
     monkeypatch.setenv("MB_PARSE_THREADS", "4")
@@ -242,21 +210,6 @@ def test_sim_count_batches_pushed_bases_and_output_buffer(tmp_path, monkeypatch)
         c.write_db(out)
     util.assert_same_db(ora, out)
     assert st.nBatches >= 3
-
-
-@pytest.mark.parametrize("k,w_prefix", [(21, 12), (31, 9), (51, 8)])
-def test_sim_experimental_persistent_sweep(tmp_path, k, w_prefix):
-    """MB_SORT=7 (not the default; to be measured in round 2): the sweep as a persistent kernel whose CTAs claim the next tile
-    and load its keys while the current tile waits for its predecessors and copies out -- whole pipeline, many segments,
-    full and ragged tiles, all three key widths."""
-    import ctypes
-    L = mb.lib()
-    L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
-    old = L.mb_dbg_sort_version(7)
-    try:
-        _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(20_000, 3_000, 150, 0.004, 17 + k)}, k, w_prefix)
-    finally:
-        L.mb_dbg_sort_version(old)
 
 
 @pytest.mark.parametrize("n_shards", [2, 3, 8])

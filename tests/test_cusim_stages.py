@@ -24,7 +24,7 @@ def sim_library():
     mb.LIB_PATH, mb._lib = saved
 
 
-@pytest.fixture(params=[1, 2, 3, 4, 5, 6, 7], ids=["sweep_v1", "sweep_128x8", "sweep_256x6", "sweep_256x7", "sweep_512x6", "sweep_256x6r", "sweep_persistent"])
+@pytest.fixture(params=[2, 3], ids=["sweep_128x8", "sweep_256x6"])
 def sort_version(request):
     L = mb.lib()
     L.mb_dbg_sort_version.argtypes = [ctypes.c_int]

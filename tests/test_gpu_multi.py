@@ -14,6 +14,15 @@ from meryl_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
+_ONLY_WORLDS = [int(x) for x in os.environ.get("MB_TEST_WORLDS", "").split(",") if x]     # e.g. MB_TEST_WORLDS=8 on an 8-GPU call (charged 8x)
+
+
+def _need(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    if _ONLY_WORLDS and world not in _ONLY_WORLDS:
+        pytest.skip("MB_TEST_WORLDS=%s" % os.environ["MB_TEST_WORLDS"])
+
 
 def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
     os.environ.update(env or {})
@@ -48,8 +57,7 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
 @pytest.mark.parametrize("route", ["default", "nccl-u64"])
 def test_multi_gpu_db_bit_exact(tmp_path, world, k, route):
     """default: peer scatter (+ u32 suffix keys for k <= 21); nccl-u64: both switched off -- round 1's all-to-all of full keys."""
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+    _need(world)
     import torch.multiprocessing as mp
     n_reads, L = 60_000, 150
     fq = tmp_path / "reads.fq"
@@ -75,8 +83,7 @@ def test_multi_gpu_db_bit_exact(tmp_path, world, k, route):
 def test_multi_gpu_suffix32_db_bit_exact(tmp_path, world, cap):
     """u32 suffix keys through the NCCL route (MB_P2P_SCATTER=0), routed by prefix bin (one message per bin and peer); emulator twin:
     tests/test_cusim_multi.py::test_sim_multi_rank_suffix32."""
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+    _need(world)
     import torch.multiprocessing as mp
     n_reads, L, k = 60_000, 150, 21
     fq = tmp_path / "reads.fq"
@@ -103,8 +110,7 @@ def test_multi_gpu_p2p_scatter_db_bit_exact(tmp_path, world, k, cap, s32):
     """The default route (MB_P2P_SCATTER, with and without u32 suffix keys): the extraction kernel stores every kept k-mer straight into the owning GPU's receive segment
     (peer arenas mapped with CUDA IPC, stores over NVLink); no all-to-all.  Emulator twin:
     tests/test_cusim_multi.py::test_sim_multi_rank_p2p_scatter."""
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+    _need(world)
     import torch.multiprocessing as mp
     n_reads, L = 60_000, 150
     fq = tmp_path / "reads.fq"
@@ -130,8 +136,7 @@ def test_multi_gpu_p2p_scatter_db_bit_exact(tmp_path, world, k, cap, s32):
 def test_cli_gpus_word(tmp_path, world):
     """`meryl-b200 gpus=N count ...`: the CLI forks one process per GPU, rank r ingests shard r of every input file
     (mb_add_file_shard), the NCCL id travels through shared memory; same directory as the oracle's."""
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+    _need(world)
     import subprocess
     fq, fa = tmp_path / "reads.fq", tmp_path / "contigs.fa"
     fq.write_bytes(synth.reads_fastq_bytes(200_000, 40_000, 150, 0.003, 5))

@@ -72,12 +72,12 @@ def test_extract_empty_and_no_kmers():
         assert len(glo) == 0
 
 
-_SHAPES = [1, 2, 3, 4] + ([5, 6, 7] if os.environ.get("MB_TEST_EXPERIMENTAL") else [])     # 5, 6, 7: not yet run on a GPU
+_SHAPES = [2, 3]
 
 
-@pytest.fixture(params=_SHAPES, ids=["sweep_v1", "sweep_128x8", "sweep_256x6", "sweep_256x7", "sweep_512x6", "sweep_256x6r", "sweep_persistent"][: len(_SHAPES)])
+@pytest.fixture(params=_SHAPES, ids=["sweep_128x8", "sweep_256x6"])
 def sort_version(request):
-    """Both sweep kernels (csrc/sort.cu): v1 = 6-bit digits, v2 = 8-bit digits."""
+    """Both sweep shapes (csrc/sort.cu): 128 threads x 8-bit digits, 256 threads x 6-bit digits."""
     L = mb.lib()
     L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
     old = L.mb_dbg_sort_version(request.param)

@@ -26,20 +26,14 @@ L.mb_dbg_sort_version.argtypes = [ctypes.c_int]
 if passes > 1:
     os.environ["MB_MAX_PASS_KEYS"] = str(int(n_kmers / passes * 1.02))
 
-configs = [(1, 1), (1, 0), (2, 1), (2, 0)]
+configs = [(3, 1), (3, 0), (2, 1), (2, 0)]
 if len(sys.argv) > 3 and sys.argv[3] == "sortonly":          # the sweep kernel shapes, filter on
-    configs = [(int(v), 0) for v in os.environ.get("MB_AB_SHAPES", "1,2,3,4,5,6,7").split(",")]
+    configs = [(int(v), 0) for v in os.environ.get("MB_AB_SHAPES", "2,3").split(",")]
 extra = [{}]
-if len(sys.argv) > 3 and sys.argv[3] == "countopts":         # count kernel striped/blocked x histogram single/joint (default sweep)
-    configs = [(L.mb_dbg_sort_version(0), 0)]
-    extra = [{}, {"MB_COUNT_BLOCKED": "1"}, {"MB_HIST_JOINT": "1"}, {"MB_COUNT_BLOCKED": "1", "MB_HIST_JOINT": "1"}]
-if len(sys.argv) > 3 and sys.argv[3] == "experiments":       # things written without a GPU at hand, to be measured
-    configs = [(L.mb_dbg_sort_version(0), 0)]
-    extra = [{}, {"MB_RANK_MATCH": "1"}]                     # (MB_OVERLAP_D2H needs host images: measure it with bench.py's e2e leg)
 if len(sys.argv) > 3 and sys.argv[3] == "env":               # any list of environments: MB_AB_ENVS='[{}, {"MB_X": "1"}, ...]' (default sweep)
     configs = [(L.mb_dbg_sort_version(0), 0)]
     extra = json.loads(os.environ.get("MB_AB_ENVS", "[{}]"))
-touched = set(k for e in extra for k in e) | {"MB_COUNT_BLOCKED", "MB_HIST_JOINT", "MB_RANK_MATCH"}
+touched = set(k for e in extra for k in e)
 for (sort_v, nofilter), env in [(c, e) for c in configs for e in extra]:
     for k in touched:
         os.environ.pop(k, None)
