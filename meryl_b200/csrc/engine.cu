@@ -778,9 +778,12 @@ static int runCount(mb_ctx *c) {
       if (getenv("MB_TRACE")) fprintf(stderr, "[meryl-b200] rank %u: no peer mapping on every rank, routing through NCCL\n", me);
     }
   }
+  //  With the peer scatter every key form is routed by BIN: an owned bin arrives as one sort segment, so the sort works on the
+  //  2k - binBits bits below the bin instead of the 2k - 6 below the file (k = 31: nine digit passes instead of ten).
+  const bool byBinFull = p2p;
   std::vector<u64> Cb;                                  //  Cb[r][b]
   std::vector<u64> binTotal;
-  if (want32) {
+  if (want32 || byBinFull) {
     u64 *dBinAll = (u64 *)top.take((size_t)(world + 1) * nBins * sizeof(u64));
     if (!dBinAll) return mb_fail(MB_ENOMEM, "device arena too small after the read store");
     Cb.assign((size_t)world * nBins, 0);
@@ -824,6 +827,9 @@ static int runCount(mb_ctx *c) {
   std::vector<Pass> passes;
   u32 sortBits;
   bool suffix32 = false;                                //  u32 suffix keys (k <= 21): half the bytes, twice the keys per pass
+  bool byBin    = false;                                //  several GPUs: the sort segments are the owned bins (else the owned files)
+  bool inPlace  = false;                                //  ... sorted in place group by group (one GPU)
+  u64  gcapKeys = 0;                                    //  ... keys per group
   if (world == 1) {
     //  consecutive bins, as many as fit; segments = bins, sorted on the bits below the bin
     sortBits = 2 * k - binBits;
@@ -864,24 +870,32 @@ static int runCount(mb_ctx *c) {
     };
 
     if (sortBits <= 32 && !c->stopAfterSort && !getenv("MB_NO_SUFFIX32")) {
-      //  u32 keys: 2 x 4 B per key + tile status; counted groups of a pass are expanded to u64 into the
-      //  spare key buffer (<= half a pass at a time) and the encode region.
+      //  u32 keys, sorted IN PLACE group by group: a pass holds its keys once (4 B per key); a group of consecutive bins
+      //  (<= gcapKeys keys) is sorted between its place in the pass and a scratch buffer T of 8 B per group key, which then
+      //  takes the group's distinct k-mers expanded to u64 for the encoder.  So a pass holds about twice the keys of the
+      //  ping-pong layout (100 Gbp / k=21 on one B200: 3 passes over the read store instead of 5).  MB_SORT_PINGPONG=1 keeps
+      //  the round-1 layout (two whole-pass buffers, one sort launch per digit and pass) for A/B.
+      const bool pingpong = getenv("MB_SORT_PINGPONG") != nullptr;
       const u32 tile32 = mb_sort_tile_keys(4);
-      const double perKey32 = 2.0 * 4 + (double)radix * 8 / tile32 + 16.0 / tile32;
+      const double perKey32 = pingpong ? 2.0 * 4 + (double)radix * 8 / tile32 + 16.0 / tile32 : 4.0;
+      u64 gKeys = std::min<u64>((u64)512 << 20, std::max<u64>(4096, R / 512));
+      if (getenv("MB_GROUP_KEYS")) gKeys = std::max<u64>(64, strtoull(getenv("MB_GROUP_KEYS"), nullptr, 10));   //  testing knob: many small groups
       size_t enc32 = std::max<size_t>((size_t)4 << 30, (size_t)nBlocksTotal * 200);
-      if (enc32 > R / 3) enc32 = R / 3;
-      if (R > enc32 + fixed + ((size_t)64 << 20)) {
-        u64 cap32 = (u64)((double)(R - enc32 - fixed) / perKey32);
+      if (!pingpong) enc32 = std::max<size_t>(enc32, (size_t)24 * gKeys);
+      if (enc32 > R / 3) { enc32 = R / 3; if (!pingpong) gKeys = std::min<u64>(gKeys, enc32 / 24); }
+      const size_t scratch = pingpong ? 0 : alignUp(8 * (size_t)gKeys + 64) + alignUp(mb_sort_workspace_bytes(gKeys / tile32 + nBins + 1, nBins, 6));
+      if (R > enc32 + fixed + scratch + ((size_t)64 << 20)) {
+        u64 cap32 = (u64)((double)(R - enc32 - fixed - scratch) / perKey32);
         cap32 = cap32 / 8192 * 8192;
         if (capLimit && cap32 > capLimit) cap32 = capLimit;
         std::vector<Pass> p32;
-        if (planBins(cap32, p32) == 0) {
+        if (cap32 > 0 && planBins(cap32, p32) == 0) {
           bool ok = true;
           for (const Pass &P : p32) {
-            const u64 gcap = std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / 3 / 8));
+            const u64 gcap = pingpong ? std::min<u64>(P.nKeys / 2 + 8, (u64)(enc32 / 3 / 8)) : gKeys;
             for (u64 cnt : P.segCount) if (cnt > gcap || cnt >= ((u64)1 << 32)) ok = false;
           }
-          if (ok) { passes.swap(p32); suffix32 = true; }
+          if (ok) { passes.swap(p32); suffix32 = true; inPlace = !pingpong; gcapKeys = gKeys; }
         }
       }
     }
@@ -963,7 +977,8 @@ static int runCount(mb_ctx *c) {
     if (want32 && cap32 > 0 && planSlots(cap32, true, ranges)) suffix32 = true;
     else if (!planSlots(capKeys, false, ranges))
       return mb_fail(MB_ENOMEM, "a single data file's k-mers do not fit one of the %u devices (capacity %llu keys); use more GPUs", world, (u64)capKeys);
-    sortBits = suffix32 ? 2 * k - binBits : 2 * k - 6;
+    byBin = suffix32 || byBinFull;
+    sortBits = byBin ? 2 * k - binBits : 2 * k - 6;
     for (const auto &rg : ranges) {
       Pass P;
       const u32 fLo = rg.first * world, fHi = rg.second * world;
@@ -972,12 +987,12 @@ static int runCount(mb_ctx *c) {
         P.nLocal += C[(size_t)me * 64 + f];
         if (!c->db.owned[f]) continue;
         P.nKeys += fileTotal[f];
-        if (suffix32) {
+        if (byBin) {
           for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) { P.segCount.push_back(binTotal[b]); P.segBin.push_back(b); }
         } else {
           P.segCount.push_back(fileTotal[f]);
-          P.encRanges.push_back(std::make_pair((u64)f * blocksPerFile, blocksPerFile));
         }
+        if (!suffix32) P.encRanges.push_back(std::make_pair((u64)f * blocksPerFile, blocksPerFile));
       }
       passes.push_back(P);
     }
@@ -1036,7 +1051,8 @@ static int runCount(mb_ctx *c) {
     //  ---- carve this pass ------------------------------------------------------------------
     Carver pc((uint8_t *)top.base + alignUp(top.off), top.left());
     void *bufA = pc.take((size_t)keyBytes * bufKeys + 64);
-    void *bufB = pc.take((size_t)keyBytes * bufKeys + 64);
+    void *bufB = inPlace ? pc.take(8 * (size_t)gcapKeys + 64)          //  scratch of one group: sort partner, then its distinct k-mers as u64
+                         : pc.take((size_t)keyBytes * bufKeys + 64);
 
     //  extraction layout: every bin of the pass is a contiguous run, bins ascending
     std::fill(binStart.begin(), binStart.end(), 0);
@@ -1060,7 +1076,43 @@ static int runCount(mb_ctx *c) {
       }
       segStart[nSegs] = at;  segTile[nSegs] = nTiles;
     }
-    const size_t sortWs = std::max(mb_sort_workspace_bytes(nTiles, nSegs ? nSegs : 1, plan.nPasses), mb_count_workspace_bytes(n));
+    //  K5 + K6 work on one group of whole segments at a time.  Full keys (8/16 B): a single group, counted in place.
+    //  u32 suffix keys: groups of consecutive bins whose distinct k-mers, expanded to u64, fit the scratch buffer
+    //  (in-place form: the group is also the unit of the sort).
+    struct Group { u32 segLo, segHi, binLo; u64 keyLo, keyHi, tileLo, tileHi; std::vector<std::pair<u64, u64>> encRanges; };
+    std::vector<Group> groups;
+    auto buildGroups = [&](u64 gcap) {
+      groups.clear();
+      if (!suffix32) {
+        Group g;  g.segLo = 0;  g.segHi = nSegs;  g.binLo = P.binLo;  g.keyLo = 0;  g.keyHi = n;  g.tileLo = 0;  g.tileHi = nTiles;
+        g.encRanges = P.encRanges;
+        groups.push_back(g);
+        return;
+      }
+      Group g;  g.segLo = 0;  g.binLo = P.binLo;  g.keyLo = 0;  g.tileLo = 0;
+      u64 have = 0;
+      auto segBin = [&](u32 i) -> u32 { return P.segBin.empty() ? P.binLo + i : P.segBin[i]; };
+      for (u32 i = 0; i <= nSegs; i++) {
+        //  a group is a run of consecutive bins (several GPUs: the owned files of a pass are not adjacent)
+        if (i == nSegs || (have > 0 && have + P.segCount[i] > gcap) || (i > g.segLo && segBin(i) != segBin(i - 1) + 1)) {
+          g.segHi = i;  g.keyHi = segStart[i];  g.tileHi = segTile[i];
+          //  the count kernel adds the segment index to binLo: pass-wide indexes (wraps), or -- in place -- the group's own
+          g.binLo = inPlace ? segBin(g.segLo) : segBin(g.segLo) - g.segLo;
+          g.encRanges.clear();
+          g.encRanges.push_back(std::make_pair((u64)segBin(g.segLo) * blocksPerBin, (u64)(g.segHi - g.segLo) * blocksPerBin));
+          groups.push_back(g);
+          g.segLo = i;  g.keyLo = segStart[i];  g.tileLo = segTile[i];  have = 0;
+        }
+        if (i < nSegs) have += P.segCount[i];
+      }
+    };
+    size_t sortWs = std::max(mb_sort_workspace_bytes(nTiles, nSegs ? nSegs : 1, plan.nPasses), mb_count_workspace_bytes(n));
+    if (inPlace) {                                        //  the sort's tables are per group
+      buildGroups(gcapKeys);
+      sortWs = 0;
+      for (const Group &G : groups)
+        sortWs = std::max(sortWs, std::max(mb_sort_workspace_bytes(G.tileHi - G.tileLo, std::max(1u, G.segHi - G.segLo), plan.nPasses), mb_count_workspace_bytes(G.keyHi - G.keyLo)));
+    }
     void *ws = pc.take(sortWs);
     if (!bufA || !bufB || !ws) return mb_fail(MB_ENOMEM, "internal: pass %zu does not fit the arena", pi);
 
@@ -1088,7 +1140,7 @@ static int runCount(mb_ctx *c) {
       };
       for (u32 f = P.binLo / binsPerFile; f < P.binHi / binsPerFile; f++) {
         const u32 d = mb_file_owner(f, world);
-        if (suffix32) {
+        if (byBin) {
           for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++) {
             u64 before = 0;
             for (u32 r = 0; r < me; r++) before += Cb[(size_t)r * nBins + b];
@@ -1149,19 +1201,28 @@ static int runCount(mb_ctx *c) {
     }
 
     //  ---- K4 ---------------------------------------------------------------------------------
-    int inSpare = 0;  u32 nl = 0;
     plan.maxSegKeys = 1;
     for (u64 cnt : P.segCount) if (cnt > plan.maxSegKeys) plan.maxSegKeys = cnt;
-    tSortHist.start(s);
-    MB_CUDA(mb_launch_sort(keyBytes, unsorted, spare, n, dCtl->segStart, dCtl->segTile, nSegs, nTiles, plan, ws, sortWs, &inSpare, &nl, s, evAfterHist));
-    tStage.stop(s);                                   //  [evAfterHist, tStage.b] = the sweep passes
-    MB_CUDA(cudaStreamSynchronize(s));
-    { float m = 0;  cudaEventElapsedTime(&m, tSortHist.a, evAfterHist);  c->st.msSortHist += m;
-      m = 0;        cudaEventElapsedTime(&m, evAfterHist, tStage.b);     c->st.msSort     += m; }
-    c->st.nLaunches += nl;
-    if (n) c->st.sortLaunchKeys += n * plan.nPasses;
-    void *sorted = inSpare ? spare : unsorted;
-    void *other  = inSpare ? unsorted : spare;
+    //  one sort of [lo, hi) segments between `from` and `partner` (both addressed with the pass's key indexes); times and counts it
+    auto sortSegments = [&](void *from, void *partner, u64 nk, u32 sLo, u32 sHi, u64 nt, int *inPartner) -> int {
+      u32 nl = 0;
+      tSortHist.start(s);
+      MB_CUDA(mb_launch_sort(keyBytes, from, partner, nk, dCtl->segStart + sLo, dCtl->segTile + sLo, sHi - sLo, nt, plan, ws, sortWs, inPartner, &nl, s, evAfterHist));
+      tStage.stop(s);                                 //  [evAfterHist, tStage.b] = the sweep passes
+      MB_CUDA(cudaStreamSynchronize(s));
+      { float m = 0;  cudaEventElapsedTime(&m, tSortHist.a, evAfterHist);  c->st.msSortHist += m;
+        m = 0;        cudaEventElapsedTime(&m, evAfterHist, tStage.b);     c->st.msSort     += m; }
+      c->st.nLaunches += nl;
+      if (nk) c->st.sortLaunchKeys += nk * plan.nPasses;
+      return MB_OK;
+    };
+    void *sorted = unsorted, *other = spare;
+    if (!inPlace) {
+      int inSpare = 0;
+      MB_TRY(sortSegments(unsorted, spare, n, 0, nSegs, nTiles, &inSpare));
+      sorted = inSpare ? spare : unsorted;
+      other  = inSpare ? unsorted : spare;
+    }
 
     if (c->stopAfterSort) {                           //  debug: hand back the sorted instances
       const size_t at = c->sortedLo.size();
@@ -1182,35 +1243,22 @@ static int runCount(mb_ctx *c) {
     //  ---- K5 + K6, one group of whole segments at a time ----------------------------------------------
     //  Full keys (8/16 B): a single group, counted in place.  u32 suffix keys: the pass is cut into
     //  groups of consecutive bins whose distinct k-mers, expanded to u64, fit the spare key buffer.
-    struct Group { u32 segLo, segHi, binLo; u64 keyLo, keyHi, tileLo, tileHi; std::vector<std::pair<u64, u64>> encRanges; };
-    std::vector<Group> groups;
-    if (!suffix32) {
-      Group g;  g.segLo = 0;  g.segHi = nSegs;  g.binLo = P.binLo;  g.keyLo = 0;  g.keyHi = n;  g.tileLo = 0;  g.tileHi = nTiles;
-      g.encRanges = P.encRanges;
-      groups.push_back(g);
-    } else {
-      const u64 gcap = std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / 3 / 8));
-      Group g;  g.segLo = 0;  g.binLo = P.binLo;  g.keyLo = 0;  g.tileLo = 0;
-      u64 have = 0;
-      auto segBin = [&](u32 i) -> u32 { return P.segBin.empty() ? P.binLo + i : P.segBin[i]; };
-      for (u32 i = 0; i <= nSegs; i++) {
-        //  a group is a run of consecutive bins (several GPUs: the owned files of a pass are not adjacent)
-        if (i == nSegs || (have > 0 && have + P.segCount[i] > gcap) || (i > g.segLo && segBin(i) != segBin(i - 1) + 1)) {
-          g.segHi = i;  g.keyHi = segStart[i];  g.tileHi = segTile[i];
-          g.binLo = segBin(g.segLo) - g.segLo;              //  (wraps; the kernel adds the segment index back)
-          g.encRanges.clear();
-          g.encRanges.push_back(std::make_pair((u64)segBin(g.segLo) * blocksPerBin, (u64)(g.segHi - g.segLo) * blocksPerBin));
-          groups.push_back(g);
-          g.segLo = i;  g.keyLo = segStart[i];  g.tileLo = segTile[i];  have = 0;
-        }
-        if (i < nSegs) have += P.segCount[i];
-      }
-    }
+    if (!inPlace) buildGroups(std::min<u64>(bufKeys / 2 + 8, (u64)(ec.left() / 3 / 8)));
 
     for (size_t gi = 0; gi < groups.size(); gi++) {
       const Group &G = groups[gi];
       const u64 gKeys = G.keyHi - G.keyLo;
       Carver gc((uint8_t *)ec.base + alignUp(ec.off), ec.left());                              //  per-group slice of the encode region
+
+      if (inPlace && gKeys) {
+        //  the group's segments between their place in the pass and the scratch buffer (addressed with the pass's key indexes:
+        //  the scratch's virtual base lies gKeyLo keys below it); an odd number of digit passes leaves them in the scratch
+        int inScratch = 0;
+        uint8_t *virt = (uint8_t *)bufB - (size_t)G.keyLo * 4;
+        MB_TRY(sortSegments(bufA, virt, gKeys, G.segLo, G.segHi, G.tileHi - G.tileLo, &inScratch));
+        if (inScratch) MB_CUDA(cudaMemcpyAsync((uint8_t *)bufA + (size_t)G.keyLo * 4, bufB, (size_t)gKeys * 4, cudaMemcpyDeviceToDevice, s));
+        sorted = bufA;  other = bufB;
+      }
 
       void *distinctKeys;  u64 *runStart;  u32 encKeyWords;
       tStage.start(s);
@@ -1219,13 +1267,18 @@ static int runCount(mb_ctx *c) {
         MB_CUDA(mb_launch_count(c->keyWords, sorted, n, runStart, &dCtl->numDistinct, ws, s));
       } else {
         distinctKeys = other;  encKeyWords = 1;
-        if (gKeys > bufKeys / 2 + 8) return mb_fail(MB_ENOMEM, "internal: group %zu of pass %zu (%llu k-mers) does not fit the spare key buffer", gi, pi, (u64)gKeys);
+        if (gKeys > (inPlace ? gcapKeys : bufKeys / 2 + 8)) return mb_fail(MB_ENOMEM, "internal: group %zu of pass %zu (%llu k-mers) does not fit the spare key buffer", gi, pi, (u64)gKeys);
         runStart = (u64 *)gc.take(8 * (size_t)(gKeys + 1));
         void *cws = gc.take(8 * (size_t)(2 * (G.tileHi - G.tileLo) + 2));   //  (the sort workspace still holds the tile table)
         if (!runStart || !cws) return mb_fail(MB_ENOMEM, "internal: no room for the run table of pass %zu group %zu", pi, gi);
-        MB_CUDA(mb_launch_count_suffix32((const u32 *)sorted, mb_sort_tile_info(ws, nTiles, nSegs ? nSegs : 1, plan.nPasses),
-                                         G.tileLo, G.tileHi, G.keyHi, G.binLo, 2 * k - binBits, (u64 *)other, runStart,
-                                         &dCtl->numDistinct, cws, s));
+        if (inPlace)
+          MB_CUDA(mb_launch_count_suffix32((const u32 *)sorted, mb_sort_tile_info(ws, G.tileHi - G.tileLo, std::max(1u, G.segHi - G.segLo), plan.nPasses),
+                                           0, G.tileHi - G.tileLo, G.keyHi, G.binLo, 2 * k - binBits, (u64 *)other, runStart,
+                                           &dCtl->numDistinct, cws, s));
+        else
+          MB_CUDA(mb_launch_count_suffix32((const u32 *)sorted, mb_sort_tile_info(ws, nTiles, nSegs ? nSegs : 1, plan.nPasses),
+                                           G.tileLo, G.tileHi, G.keyHi, G.binLo, 2 * k - binBits, (u64 *)other, runStart,
+                                           &dCtl->numDistinct, cws, s));
       }
       u64 D = 0;
       MB_CUDA(cudaMemcpyAsync(&D, &dCtl->numDistinct, sizeof(u64), cudaMemcpyDeviceToHost, s));

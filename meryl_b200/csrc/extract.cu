@@ -520,7 +520,7 @@ extract_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : KW>::type *__restrict_
 //  members takes another round -- rare, the host sizes ITEMS for 1.3x the expected share).
 //  Per tile of 8192 positions at one fifth kept: ~830 warp instructions per thread row instead of ~1350.
 template <bool S32, int ITEMS>
-__global__ void __launch_bounds__(256, ITEMS <= 16 ? 3 : 2)
+__global__ void __launch_bounds__(256, ITEMS <= 12 ? 4 : ITEMS <= 16 ? 3 : 2)
 extract_dense_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : 1>::type *__restrict__ out,
                      const u64 *__restrict__ binStart, u64 *__restrict__ binCursor, u64 nTiles) {
   typedef typename KeyT<S32 ? 0 : 1>::type Stored;
@@ -588,7 +588,17 @@ extract_dense_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : 1>::type *__rest
         cand = file_range_slots(w, p.k, p.mode, fLo, fHi) & (v << 1);
       }
     }
-    const u32 mine = (u32)__popcll((long long)cand);
+    //  the members as a 32-bit mask (bit 31 - q = position q): the loops below walk it with 32-bit instructions
+    u32 cand32;
+    {
+      u64 x = (cand >> 1) & 0x5555555555555555ull;       //  bit 2 (31 - q)
+      x = (x | (x >> 1))  & 0x3333333333333333ull;
+      x = (x | (x >> 2))  & 0x0f0f0f0f0f0f0f0full;
+      x = (x | (x >> 4))  & 0x00ff00ff00ff00ffull;
+      x = (x | (x >> 8))  & 0x0000ffff0000ffffull;
+      cand32 = (u32)(x | (x >> 16));
+    }
+    const u32 mine = (u32)__popc(cand32);
     u32 incl = mine;
     for (int o = 1; o < 32; o <<= 1) {
       const u32 x = __shfl_up_sync(0xffffffffu, incl, o);
@@ -602,11 +612,11 @@ extract_dense_kernel(MbExtractParams p, typename KeyT<S32 ? 0 : 1>::type *__rest
     for (u32 round0 = 0; round0 < total; round0 += CAP) {          //  (uniform over the CTA; one round unless the tile is unusually full)
       const u32 nR = min((u32)CAP, total - round0);
       {                                                            //  my members whose place in the tile's list falls into this round
-        u32 idx = base;
-        for (u64 m = cand; m; idx++) {
-          const u32 b = __clzll((long long)m);
-          m &= ~(0x8000000000000000ull >> b);
-          if (idx - round0 < (u32)CAP) plist[idx - round0] = (unsigned short)(t * 32 + (b >> 1));   //  (unsigned: idx < round0 wraps)
+        u32 idx = base - round0;                                   //  (unsigned: places before this round wrap far above CAP)
+        for (u32 m = cand32; m; idx++) {
+          const u32 q = __clz(m);
+          m &= ~(0x80000000u >> q);
+          if (idx < (u32)CAP) plist[idx] = (unsigned short)(t * 32 + q);
         }
       }
       __syncthreads();

@@ -76,13 +76,16 @@ sort_tiles_kernel(const u64 *__restrict__ segStart, const u64 *__restrict__ segT
                   u32 tileKeys, TileInfo *__restrict__ info) {
   const u64 tile = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= nTiles) return;
-  const u32 seg   = find_segment(segTile, nSegs, tile);
+  //  segTile[] may be a slice of a longer table (a group of a pass's segments sorted on its own): tiles are numbered
+  //  from the slice's first tile
+  const u64 ta    = tile + segTile[0];
+  const u32 seg   = find_segment(segTile, nSegs, ta);
   const u64 first = segTile[seg];
-  const u64 begin = segStart[seg] + (tile - first) * tileKeys;
+  const u64 begin = segStart[seg] + (ta - first) * tileKeys;
   u64 n = segStart[seg + 1] - begin;
   if (n > tileKeys) n = tileKeys;
   TileInfo t;
-  t.begin = begin;  t.n = (u32)n;  t.seg = seg | (tile == first ? 0x80000000u : 0u);
+  t.begin = begin;  t.n = (u32)n;  t.seg = seg | (ta == first ? 0x80000000u : 0u);
   info[tile] = t;
 }
 
@@ -105,9 +108,10 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
   for (u32 i = t; i < pt.nPasses * radix; i += SORT_THREADS) sh[i] = 0;
   __syncthreads();
 
-  const u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
+  u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
   u64 tileEnd = tile0 + HIST_TILES_PER_CTA;
   if (tileEnd > nTiles) tileEnd = nTiles;
+  tile0 += segTile[0];  tileEnd += segTile[0];             //  (segTile[] may be a slice of a longer table: absolute tile numbers from here on)
 
   u32 seg = find_segment(segTile, nSegs, tile0);
 
@@ -199,9 +203,10 @@ sort_hist2_kernel(const typename KeyT<KW>::type *__restrict__ keys,
 #pragma unroll
   for (int g = 0; g < NG; g++) { gShift[g] = hg.shift[g];  gBits[g] = hg.bitsAll[g];  gTab[g] = jt + hg.offset[g]; }
 
-  const u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
+  u64 tile0 = (u64)blockIdx.x * HIST_TILES_PER_CTA;
   u64 tileEnd = tile0 + HIST_TILES_PER_CTA;
   if (tileEnd > nTiles) tileEnd = nTiles;
+  tile0 += segTile[0];  tileEnd += segTile[0];             //  (segTile[] may be a slice of a longer table: absolute tile numbers from here on)
   u32 seg = find_segment(segTile, nSegs, tile0);
 
   auto flush = [&](u32 sg) {                           //  called by all threads

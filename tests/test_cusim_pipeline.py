@@ -137,6 +137,22 @@ def test_sim_streamed_output_dir(tmp_path, monkeypatch, cap):
     util.assert_same_db(ora, out)
 
 
+@pytest.mark.parametrize("k,w_prefix,op,cap", [(21, 12, "count", 0), (20, 12, "count", 0), (17, 10, "count-forward", 150_000), (21, 14, "count-reverse", 150_000)])
+def test_sim_in_place_group_sort(tmp_path, monkeypatch, k, w_prefix, op, cap):
+    """u32 suffix keys sorted in place, group of bins by group of bins, against a scratch buffer (engine.cu): many small groups
+    (MB_GROUP_KEYS), an even and an odd number of digit passes (k = 21: 32 bits, six passes, the group ends where it lay;
+    k = 20 / 17: five / four passes), one and several passes over the reads.  Same db as the oracle, and as the ping-pong layout."""
+    monkeypatch.setenv("MB_GROUP_KEYS", "3000")
+    if cap:
+        monkeypatch.setenv("MB_MAX_PASS_KEYS", str(cap))
+    files = {"r.fq": synth.reads_fastq_bytes(20_000, 4_000, 150, 0.004, 500 + k)}
+    st = _vs_oracle(tmp_path, files, k, w_prefix, op=op, expect_key_bytes=4, min_passes=2 if cap else 1)
+    monkeypatch.setenv("MB_SORT_PINGPONG", "1")
+    (tmp_path / "pp").mkdir()
+    st2 = _vs_oracle(tmp_path / "pp", files, k, w_prefix, op=op, expect_key_bytes=4)
+    assert st.nDistinct == st2.nDistinct and st.nLaunches > st2.nLaunches           # one sort per group, not per pass
+
+
 def test_sim_multi_pass_rolling(tmp_path, monkeypatch):
     """The same kind of passes through the rolling path (filter switched off)."""
     monkeypatch.setenv("MB_MAX_PASS_KEYS", "150000")
