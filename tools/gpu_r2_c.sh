@@ -11,8 +11,12 @@ date; nvidia-smi --query-gpu=name,memory.total --format=csv,noheader; nproc; fre
 echo "== a. the GPU suite, experimental tests included, no -x";  date +%T
 MB_TEST_EXPERIMENTAL=1 timeout 1800 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -12
 echo "== b. A/B at 8 Gbp in 5 passes (one process, same reads)";  date +%T
-MB_AB_ENVS='[{}, {"MB_SORT_PINGPONG": "1"}, {"MB_SWEEP_PREFETCH": "444"}, {"MB_SWEEP_PREFETCH": "1332"}, {"MB_COUNT_GROUP": "1"}, {"MB_EXTRACT_DENSE": "0"}]' \
+MB_AB_ENVS='[{}, {"MB_SWEEP_RUNS": "1"}, {"MB_SORT_PINGPONG": "1"}, {"MB_SWEEP_PREFETCH": "444"}, {"MB_SWEEP_PREFETCH": "1332"}, {"MB_SWEEP_RUNS": "1", "MB_SWEEP_PREFETCH": "444"}, {"MB_COUNT_GROUP": "1"}, {"MB_EXTRACT_DENSE": "0"}]' \
   timeout 400 python tools/ab_bench.py 8 5 env 2>&1 | tee $OUT/r2c_ab_8gbp_env.jsonl | cut -c1-420
+echo "== b2. parity with the copy-out by digit runs (MB_SWEEP_RUNS=1): sort stages + the headline plan";  date +%T
+MB_SWEEP_RUNS=1 timeout 900 python -m pytest tests/test_gpu_stages.py tests/test_gpu_headline.py -q -p no:cacheprovider 2>&1 | tail -3
+echo "== c0. bench 100 Gbp with MB_SWEEP_RUNS=1 (device-resident only)";  date +%T
+MB_SWEEP_RUNS=1 timeout 500 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --cli-gbp 0 > $OUT/r2c_bench_100gbp_runs.json 2> $OUT/r2c_bench_100gbp_runs.err; cut -c1-1700 $OUT/r2c_bench_100gbp_runs.json; tail -2 $OUT/r2c_bench_100gbp_runs.err
 echo "== c. bench 100 Gbp: the round-1 ping-pong layout (device-resident only), then the default with all legs";  date +%T
 MB_SORT_PINGPONG=1 timeout 500 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --cli-gbp 0 > $OUT/r2c_bench_100gbp_pingpong.json 2> $OUT/r2c_bench_100gbp_pingpong.err; cut -c1-1700 $OUT/r2c_bench_100gbp_pingpong.json; tail -2 $OUT/r2c_bench_100gbp_pingpong.err
 timeout 900 python bench.py --steps 3 --warmup 2 > $OUT/r2c_bench_100gbp.json 2> $OUT/r2c_bench_100gbp.err; cut -c1-3600 $OUT/r2c_bench_100gbp.json; tail -2 $OUT/r2c_bench_100gbp.err
