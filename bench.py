@@ -329,6 +329,30 @@ def main():
                 "algorithmic_bytes_per_launch": sort_bytes / max(1, stats.sortPasses * stats.nPasses),
                 "launches": stats.sortPasses * stats.nPasses}
 
+    # (The legs that start other processes come BEFORE the end-to-end leg: that one page-locks 130 GB of host memory, and a
+    #  196 GB box has no room for it next to the reference binary's buckets and two databases in /dev/shm.)
+    # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                              "--ref-gbp", str(args.ref_gbp), "--ref-memory-gb", str(args.ref_memory_gb),
+                              "--k", str(K), "--read-len", str(READ_LEN), "--err", str(ERR)],
+                             capture_output=True, text=True, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
+        try:
+            cpu = json.loads(sub.stdout.strip().splitlines()[-1]).get("cpu_baseline")
+        except Exception:
+            cpu = {"value": None, "unit": "k-mers/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + sub.stderr[-200:]}
+
+    # ---- the command line tools side by side on one FASTQ file (rank 0, one GPU) -----------------
+    cli = None
+    if rank == 0 and world == 1 and args.cli_gbp > 0:
+        torch.cuda.empty_cache()
+        mb.lib().mb_release_device_memory()         # the arena this process keeps between counts (another process is about to use the GPU)
+        try:
+            cli = cli_leg(args.cli_gbp, local)
+        except Exception as ex:
+            cli = {"error": repr(ex)[:300]}
+
     # ---- e2e: host buffer -> C ABI -> host images ----------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -370,33 +394,13 @@ def main():
                    "d2h_bytes_per_step": int(est.d2hBytes), "seconds_per_step": dt,
                    "input": "pinned host buffer of the base stream (1 B/base + '.' per read), output: 129 db images in (pinned) host memory"}
             del host, out_host
+            if hasattr(torch._C, "_host_emptyCache"):
+                torch._C._host_emptyCache()             # torch keeps freed page-locked blocks: 130 GB that the host may need back
         except Exception as ex:                 # the device-resident line above stands; say why there is no end-to-end number
             if world > 1:
                 raise                           # (a rank that drops out of the collectives would hang the others)
             e2e = {"value": None, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:300]}
     del dev_chunk
-
-    # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                              "--ref-gbp", str(args.ref_gbp), "--ref-memory-gb", str(args.ref_memory_gb),
-                              "--k", str(K), "--read-len", str(READ_LEN), "--err", str(ERR)],
-                             capture_output=True, text=True, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
-        try:
-            cpu = json.loads(sub.stdout.strip().splitlines()[-1]).get("cpu_baseline")
-        except Exception:
-            cpu = {"value": None, "unit": "k-mers/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + sub.stderr[-200:]}
-
-    # ---- the command line tools side by side on one FASTQ file (rank 0, one GPU) -----------------
-    cli = None
-    if rank == 0 and world == 1 and args.cli_gbp > 0:
-        torch.cuda.empty_cache()
-        mb.lib().mb_release_device_memory()         # the arena this process keeps between counts (another process is about to use the GPU)
-        try:
-            cli = cli_leg(args.cli_gbp, local)
-        except Exception as ex:
-            cli = {"error": repr(ex)[:300]}
 
     if rank == 0:
         print(json.dumps({

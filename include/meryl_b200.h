@@ -329,8 +329,6 @@ int mb_dbg_encode_block(uint32_t k, uint32_t wPrefix, uint64_t prefix, uint64_t 
                         uint8_t *out, uint64_t cap, uint64_t *outLen);
 /*  P1/P2 alone (host parser): file image -> base stream in work-buffer format.  */
 int mb_dbg_parse(const uint8_t *data, uint64_t len, char *out, uint64_t cap, uint64_t *outLen);
-/*  the same stream from the device parser (csrc/parse.cu, kernels K11a-c)  */
-int mb_dbg_parse_device(const uint8_t *data, uint64_t len, char *out, uint64_t cap, uint64_t *outLen);
 /*  The same through the multi-threaded block parser the file inputs use (cuts at guessed record starts, verified).  */
 int mb_dbg_parse_parallel(const uint8_t *data, uint64_t len, uint64_t block, char *out, uint64_t cap, uint64_t *outLen);
 /*  Select the sort sweep kernel (1: 6-bit digits, 2: 8-bit digits) for contexts created afterwards; returns the previous one.  */

@@ -114,6 +114,7 @@ struct MbMergeEndpoints {
   u64          param2 = 0;                           //  MB_OP_KEEP_SUFFIX: the mask (param is the value)
   u32          outPrefix = 12;                       //  kmers-writer.C:52-58: every non-count operation writes prefix 12
   u32          streamMode = 1;                       //  1: stream writer (blocks of present prefixes), 0: block writer (all prefixes)
+  const bool  *onlyFiles = nullptr;                  //  64 flags: the data files to produce (several GPUs: the files this rank owns); NULL = all
 };
 int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, uint32_t nInputs, const char *outDir,
                       int32_t device, uint64_t workspaceBytes, mb_union_stats *st, const MbMergeEndpoints *ends);

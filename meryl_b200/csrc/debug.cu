@@ -31,38 +31,6 @@ extern "C" int mb_dbg_parse(const uint8_t *data, uint64_t len, char *out, uint64
   return MB_OK;
 }
 
-//  The device parser's stream for a file's bytes, back on the host (parity with mb_dbg_parse; tests only).
-extern "C" int mb_dbg_parse_device(const uint8_t *data, uint64_t len, char *out, uint64_t cap, uint64_t *outLen) {
-  mb_clear_error();
-  if (!outLen) return mb_fail(MB_EINVAL, "mb_dbg_parse_device: NULL argument");
-  if (!SeqParser::sniff(data, len < 65536 ? len : 65536)) return mb_fail(MB_EFORMAT, "input is not FASTA or FASTQ");
-  int nDev = 0;
-  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return mb_fail(MB_ENODEVICE, "no CUDA device (this library has no CPU path)");
-  struct Acc { std::string s; cudaStream_t st; } acc;
-  MB_CUDA(cudaStreamCreateWithFlags(&acc.st, cudaStreamNonBlocking));
-  MbDeviceParser *P = nullptr;
-  int rc = mb_dparse_create(&P, acc.st);
-  auto sink = [](void *a, const char *d, size_t n) -> int {
-    Acc *A = (Acc *)a;
-    const size_t at = A->s.size();
-    A->s.resize(at + n);
-    if (cudaMemcpyAsync(&A->s[at], d, n, cudaMemcpyDeviceToHost, A->st) != cudaSuccess || cudaStreamSynchronize(A->st) != cudaSuccess)
-      return mb_fail(MB_ENODEVICE, "mb_dbg_parse_device: copy failed");
-    return MB_OK;
-  };
-  if (rc == MB_OK) rc = mb_dparse_feed(P, data, (size_t)len, sink, &acc);
-  if (rc == MB_OK) rc = mb_dparse_finish(P, sink, &acc);
-  mb_dparse_destroy(P);
-  cudaStreamDestroy(acc.st);
-  if (rc != MB_OK) return rc;
-  *outLen = acc.s.size();
-  if (out) {
-    if (acc.s.size() > cap) return mb_fail(MB_EINVAL, "mb_dbg_parse_device: output needs %zu bytes", acc.s.size());
-    memcpy(out, acc.s.data(), acc.s.size());
-  }
-  return MB_OK;
-}
-
 extern "C" int mb_dbg_extract_sorted(uint32_t k, uint32_t mode, const char *bases, uint64_t len,
                                      uint64_t *kmerLo, uint64_t *kmerHi, uint64_t cap, uint64_t *n) {
   mb_clear_error();

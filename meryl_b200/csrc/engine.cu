@@ -107,6 +107,10 @@ struct mb_ctx {
   std::vector<std::unique_ptr<MbDbImages>> batches;
   u64         batchLimit = 0;                        //  records; 0 = never
   bool        closing    = false;
+  //  several GPUs: every rank takes part in every batch (runCount is collective).  A round's first all-gather carries two flags:
+  //  "I count this as a batch" and "nothing follows this round on my side" (mb_count); the answers:
+  bool        finalRound = false;                    //  set by mb_count
+  bool        roundAnyBatch = false, roundAllFinal = true;
 };
 
 
@@ -248,9 +252,9 @@ static int ensureArena(mb_ctx *c) {
     c->dStage[i] = c->arena + c->arenaBytes - (size_t)(i + 1) * kStageBytes;
   }
   c->storeLimit = c->arenaBytes - 2 * kStageBytes - ((size_t)64 << 20);
-  //  One batch = as many reads as leave half of the arena to the key buffers of a pass.  Not with several GPUs (every
-  //  rank would have to close its batches together) and not for the kernel-only / debugging forms that keep no images.
-  if (c->cfg.worldSize <= 1 && !(c->cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED)) && !c->stopAfterSort) {
+  //  One batch = as many reads as leave half of the arena to the key buffers of a pass.  (With several GPUs a batch is closed
+  //  by all ranks together, see mb_count.)  Not for the kernel-only / debugging forms that keep no images.
+  if (!(c->cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED)) && !c->stopAfterSort) {
     c->batchLimit = c->storeLimit / 2 / (MB_STORE_REC_WORDS * 4);
     if (getenv("MB_MAX_BATCH_BASES")) c->batchLimit = std::max<u64>(1, strtoull(getenv("MB_MAX_BATCH_BASES"), nullptr, 10) / 32);   //  testing knob
   }
@@ -431,48 +435,12 @@ extern "C" int mb_add_bases_device(mb_ctx *c, const char *dBases, uint64_t len) 
   return MB_OK;
 }
 
-//  Experimental (MB_DEVICE_PARSE=1, not the default until it has run on a GPU): the file's bytes go to the device as they
-//  are and the parser's state machine runs there (parse.cu); the base stream it emits is packed (K1) without leaving the
-//  device.  Not with homopolymer compression (a host-side filter of the stream), and a batch closes only between files.
-static int deviceStreamSink(void *arg, const char *dStream, size_t n) {
-  mb_ctx *c = (mb_ctx *)arg;
-  const u64 recs = (n + 31) / 32;
-  MB_TRY(storeReserve(c, recs));
-  if (!c->ingestStarted) { c->ingestStarted = true; MB_CUDA(cudaEventRecord(c->evIngest[0], c->stream)); }
-  MB_CUDA(mb_launch_pack((const uint8_t *)dStream, n, (u32 *)c->arena, c->nRecords, c->stream));
-  c->st.nLaunches++;
-  c->nRecords += recs;
-  return MB_OK;
-}
-
-static bool wantDeviceParse(const mb_ctx *c) {
-  return getenv("MB_DEVICE_PARSE") != nullptr && !(c->cfg.flags & MB_FLAG_COMPRESS);
-}
-
-static int addFileBytesOnDevice(mb_ctx *c, const uint8_t *data, uint64_t len) {
-  MB_TRY(ensureArena(c));
-  if (c->inRecord) { const char dot = '.'; MB_TRY(appendHost(c, &dot, 1)); c->inRecord = false; }
-  MB_TRY(flushStage(c));                                   //  the stream is at a record boundary: padding is harmless
-  if (batchDue(c)) MB_TRY(closeBatch(c));
-  MB_CUDA(cudaSetDevice(c->device));
-  MbDeviceParser *P = nullptr;
-  MB_TRY(mb_dparse_create(&P, c->stream));
-  int rc = mb_dparse_feed(P, data, (size_t)len, deviceStreamSink, c);
-  if (rc == MB_OK) rc = mb_dparse_finish(P, deviceStreamSink, c);
-  if (rc == MB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = mb_fail(MB_ENODEVICE, "device parser: %s", cudaGetErrorString(cudaGetLastError()));
-  c->st.nLaunches += mb_dparse_launches(P);
-  c->st.h2dBytes  += len;
-  mb_dparse_destroy(P);
-  return rc;
-}
-
 extern "C" int mb_add_file_bytes(mb_ctx *c, const uint8_t *data, uint64_t len) {
   mb_clear_error();
   if (!c || (!data && len))  return mb_fail(MB_EINVAL, "mb_add_file_bytes: NULL argument");
   if (c->counted)            return mb_fail(MB_ESTATE, "mb_add_file_bytes: already counted");
   if (!SeqParser::sniff(data, len < 65536 ? len : 65536))
     return mb_fail(MB_EFORMAT, "input is not FASTA or FASTQ");
-  if (wantDeviceParse(c)) return addFileBytesOnDevice(c, data, len);
   SeqParser ps(parserSink, c);
   const size_t BLK = (size_t)256 << 20;
   for (uint64_t at = 0; at < len; at += BLK) MB_TRY(mb_parse_parallel(parserSink, c, ps, data + at, (size_t)std::min<uint64_t>(BLK, len - at)));
@@ -507,11 +475,6 @@ extern "C" int mb_add_file(mb_ctx *c, const char *path) {
         const uint8_t *d = (const uint8_t *)m;
         int rc = MB_OK;
         if (!SeqParser::sniff(d, sz < 65536 ? sz : 65536)) rc = mb_fail(MB_EFORMAT, "'%s' is not FASTA or FASTQ", path);
-        if (rc == MB_OK && wantDeviceParse(c)) {           //  experimental: the state machine on the device (parse.cu)
-          rc = addFileBytesOnDevice(c, d, sz);
-          munmap(m, sz);
-          return rc;
-        }
         SeqParser ps(parserSink, c);
         const size_t BLK = (size_t)1 << 30;                  //  (16 threads x 64 MB: pieces large enough for the parallel staging copy)
         for (size_t at = 0; rc == MB_OK && at < sz; at += BLK) rc = mb_parse_parallel(parserSink, c, ps, d + at, std::min(BLK, sz - at));
@@ -642,8 +605,8 @@ struct Control {                                      //  small device-side tabl
   u64 segStart [MB_MAX_BINS + 1];
   u64 segTile  [MB_MAX_BINS + 1];
   u64 fileBase [64];
-  u64 fileCount[64];                                  //  multi-GPU: this rank's k-mers per file
-  u64 allFileCount[32 * 64];                          //  multi-GPU: every rank's
+  u64 fileCount[72];                                  //  multi-GPU: this rank's k-mers per file (+ the round's flags, see runCount)
+  u64 allFileCount[32 * 72];                          //  multi-GPU: every rank's
   u64 numDistinct;
   u64 encTotals[4];
   u64 histTotals[3];
@@ -662,6 +625,49 @@ struct Pass {
 
 }  //  namespace
 
+
+//  Several GPUs: rank 0 collects the other ranks' value histograms for the master index (collective: every rank calls it).
+//  dScratch: device memory for the exchange.
+static int gatherHistograms(mb_ctx *c, uint8_t *dScratch, size_t scratchBytes) {
+  const u32 world = mb_comm_world(c->comm), me = mb_comm_rank(c->comm);
+  cudaStream_t s = c->stream;
+  {
+      const u64 myWords = 2 * (u64)c->hist.values.size();
+      std::vector<u64> cnt(world, 0);
+      Carver hc(dScratch, scratchBytes);
+      u64 *dCnt = (u64 *)hc.take(8 * (size_t)(world + 1));
+      if (!dCnt) return mb_fail(MB_ENOMEM, "internal: no room for the histogram exchange");
+      MB_CUDA(cudaMemcpyAsync(dCnt, &myWords, 8, cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCnt, dCnt + 1, 1, s));
+      MB_CUDA(cudaMemcpyAsync(cnt.data(), dCnt + 1, 8 * (size_t)world, cudaMemcpyDeviceToHost, s));
+      MB_CUDA(cudaStreamSynchronize(s));
+      u64 others = 0;
+      for (u32 r = 1; r < world; r++) others += cnt[r];
+      std::vector<u64> mine(myWords);
+      for (size_t i = 0; i < c->hist.values.size(); i++) { mine[2 * i] = c->hist.values[i]; mine[2 * i + 1] = c->hist.occ[i]; }
+      u64 *dSend = (u64 *)hc.take(8 * (size_t)(myWords + 1));
+      u64 *dRecv = (u64 *)hc.take(8 * (size_t)(others + 1));
+      if (!dSend || !dRecv) return mb_fail(MB_ENOMEM, "internal: no room for the histogram exchange");
+      if (myWords) MB_CUDA(cudaMemcpyAsync(dSend, mine.data(), 8 * (size_t)myWords, cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_gather_u64(c->comm, dSend, myWords, dRecv, cnt.data(), s));
+      MB_CUDA(cudaStreamSynchronize(s));
+      if (me == 0 && others) {
+        std::vector<u64> got(others);
+        MB_CUDA(cudaMemcpy(got.data(), dRecv, 8 * (size_t)others, cudaMemcpyDeviceToHost));
+        std::map<u64, u64> m;
+        for (size_t i = 0; i < c->hist.values.size(); i++) m[c->hist.values[i]] += c->hist.occ[i];
+        for (u64 i = 0; i < others; i += 2) {
+          m[got[i]] += got[i + 1];
+          if (got[i] == 1) c->hist.nUnique += got[i + 1];
+          c->hist.nDistinct += got[i + 1];
+          c->hist.nTotal    += got[i] * got[i + 1];
+        }
+        c->hist.values.clear();  c->hist.occ.clear();
+        for (auto &kv : m) { c->hist.values.push_back(kv.first); c->hist.occ.push_back(kv.second); }
+      }
+    }
+  return MB_OK;
+}
 
 static int runCount(mb_ctx *c) {
   const mb_config &cfg = c->cfg;
@@ -733,12 +739,26 @@ static int runCount(mb_ctx *c) {
   {
     for (u32 b = 0; b < nBins; b++) C[(size_t)me * 64 + b / binsPerFile] += binCount[b];
     if (world > 1) {
-      MB_CUDA(cudaMemcpyAsync(dCtl->fileCount, &C[(size_t)me * 64], 64 * sizeof(u64), cudaMemcpyHostToDevice, s));
-      MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 64, s));
-      MB_CUDA(cudaMemcpyAsync(C.data(), dCtl->allFileCount, (size_t)world * 64 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+      //  65 words per rank: the 64 counts and the round's flags (bit 0: this rank counts the round as a batch -- it is closing
+      //  one, or has closed one before; bit 1: this rank is in mb_count, no more reads follow)
+      std::vector<u64> mine(65), all((size_t)world * 65);
+      for (u32 f = 0; f < 64; f++) mine[f] = C[(size_t)me * 64 + f];
+      mine[64] = ((c->closing || !c->batches.empty()) ? 1 : 0) | (c->finalRound ? 2 : 0);
+      MB_CUDA(cudaMemcpyAsync(dCtl->fileCount, mine.data(), 65 * sizeof(u64), cudaMemcpyHostToDevice, s));
+      MB_TRY(mb_comm_allgather_u64(c->comm, dCtl->fileCount, dCtl->allFileCount, 65, s));
+      MB_CUDA(cudaMemcpyAsync(all.data(), dCtl->allFileCount, all.size() * sizeof(u64), cudaMemcpyDeviceToHost, s));
       MB_CUDA(cudaStreamSynchronize(s));
-    }
+      c->roundAnyBatch = false;  c->roundAllFinal = true;
+      for (u32 r = 0; r < world; r++) {
+        for (u32 f = 0; f < 64; f++) C[(size_t)r * 64 + f] = all[(size_t)r * 65 + f];
+        if (all[(size_t)r * 65 + 64] & 1)    c->roundAnyBatch = true;
+        if (!(all[(size_t)r * 65 + 64] & 2)) c->roundAllFinal = false;
+      }
+    } else { c->roundAnyBatch = c->closing;  c->roundAllFinal = true; }
   }
+  //  One rank's batch is everybody's batch: the images of this round stay in host memory and are merged at the end.
+  const bool asBatch = c->closing || c->roundAnyBatch;
+  uint8_t *const outBuf = asBatch ? nullptr : c->outBuf;
   std::vector<u64> fileTotal(64, 0);
   for (u32 r = 0; r < world; r++) for (u32 f = 0; f < 64; f++) fileTotal[f] += C[(size_t)r * 64 + f];
 
@@ -1021,7 +1041,7 @@ static int runCount(mb_ctx *c) {
       if (ready) cudaEventDestroy(ready);
     }
   } stream;
-  const bool streaming = !c->outDir.empty() && !c->closing && c->batches.empty() && !c->stopAfterSort &&
+  const bool streaming = !c->outDir.empty() && !asBatch && c->batches.empty() && !c->stopAfterSort &&
                          !(cfg.flags & (MB_FLAG_NO_IMAGES | MB_FLAG_KEEP_COUNTED));
   if (streaming) {
     if (mkdir(c->outDir.c_str(), 0777) != 0 && errno != EEXIST) return mb_fail(MB_EIO, "cannot create directory '%s': %s", c->outDir.c_str(), strerror(errno));
@@ -1400,13 +1420,13 @@ static int runCount(mb_ctx *c) {
               const size_t ib = (size_t)(fblk[f + 1] - fblk[f]) * 24;
               std::vector<uint8_t> &iv = c->db.index[file];
               uint8_t *dst;
-              if (c->outBuf) {                          //  append to the caller's buffer: a file's pieces arrive back to back
+              if (outBuf) {                             //  append to the caller's buffer: a file's pieces arrive back to back
                 if (c->outUsed + fb > c->outCap)
                   return mb_fail(MB_ENOMEM, "output buffer too small: data file %u needs %zu more bytes, %zu of %zu used", file, fb, c->outUsed, c->outCap);
-                if (c->db.dataLen[file] == 0) c->db.dataPtr[file] = c->outBuf + c->outUsed;
-                else if (c->db.dataPtr[file] + c->db.dataLen[file] != c->outBuf + c->outUsed)
+                if (c->db.dataLen[file] == 0) c->db.dataPtr[file] = outBuf + c->outUsed;
+                else if (c->db.dataPtr[file] + c->db.dataLen[file] != outBuf + c->outUsed)
                   return mb_fail(MB_ESTATE, "internal: data file %u is not contiguous in the output buffer", file);
-                dst = c->outBuf + c->outUsed;
+                dst = outBuf + c->outUsed;
                 c->outUsed += fb;
               } else {
                 std::vector<uint8_t> &dv = c->db.dataVec[file];
@@ -1462,47 +1482,13 @@ static int runCount(mb_ctx *c) {
     c->hist.nUnique = totals[0];  c->hist.nDistinct = totals[1];  c->hist.nTotal = totals[2];
     c->st.nUnique = totals[0];  c->st.nDistinct = totals[1];  c->st.nTotal = totals[2];
 
-    //  multi-GPU: rank 0 collects the other ranks' histograms for the master index
-    if (world > 1) {
-      const u64 myWords = 2 * (u64)c->hist.values.size();
-      std::vector<u64> cnt(world, 0);
-      Carver hc((uint8_t *)top.base + alignUp(top.off), top.left());
-      u64 *dCnt = (u64 *)hc.take(8 * (size_t)(world + 1));
-      if (!dCnt) return mb_fail(MB_ENOMEM, "internal: no room for the histogram exchange");
-      MB_CUDA(cudaMemcpyAsync(dCnt, &myWords, 8, cudaMemcpyHostToDevice, s));
-      MB_TRY(mb_comm_allgather_u64(c->comm, dCnt, dCnt + 1, 1, s));
-      MB_CUDA(cudaMemcpyAsync(cnt.data(), dCnt + 1, 8 * (size_t)world, cudaMemcpyDeviceToHost, s));
-      MB_CUDA(cudaStreamSynchronize(s));
-      u64 others = 0;
-      for (u32 r = 1; r < world; r++) others += cnt[r];
-      std::vector<u64> mine(myWords);
-      for (size_t i = 0; i < c->hist.values.size(); i++) { mine[2 * i] = c->hist.values[i]; mine[2 * i + 1] = c->hist.occ[i]; }
-      u64 *dSend = (u64 *)hc.take(8 * (size_t)(myWords + 1));
-      u64 *dRecv = (u64 *)hc.take(8 * (size_t)(others + 1));
-      if (!dSend || !dRecv) return mb_fail(MB_ENOMEM, "internal: no room for the histogram exchange");
-      if (myWords) MB_CUDA(cudaMemcpyAsync(dSend, mine.data(), 8 * (size_t)myWords, cudaMemcpyHostToDevice, s));
-      MB_TRY(mb_comm_gather_u64(c->comm, dSend, myWords, dRecv, cnt.data(), s));
-      MB_CUDA(cudaStreamSynchronize(s));
-      if (me == 0 && others) {
-        std::vector<u64> got(others);
-        MB_CUDA(cudaMemcpy(got.data(), dRecv, 8 * (size_t)others, cudaMemcpyDeviceToHost));
-        std::map<u64, u64> m;
-        for (size_t i = 0; i < c->hist.values.size(); i++) m[c->hist.values[i]] += c->hist.occ[i];
-        for (u64 i = 0; i < others; i += 2) {
-          m[got[i]] += got[i + 1];
-          if (got[i] == 1) c->hist.nUnique += got[i + 1];
-          c->hist.nDistinct += got[i + 1];
-          c->hist.nTotal    += got[i] * got[i + 1];
-        }
-        c->hist.values.clear();  c->hist.occ.clear();
-        for (auto &kv : m) { c->hist.values.push_back(kv.first); c->hist.occ.push_back(kv.second); }
-      }
-    }
+    //  multi-GPU: rank 0 collects the other ranks' histograms for the master index (after the merge when this round is a batch)
+    if (world > 1 && !asBatch) MB_TRY(gatherHistograms(c, (uint8_t *)top.base + alignUp(top.off), top.left()));
 
     mb_build_master_index(k, wP, c->hist, c->db.master);
     c->st.dbBytes = (me == 0) ? c->db.master.size() : 0;
     for (u32 f = 0; f < 64; f++) {
-      if (!c->outBuf) c->db.dataPtr[f] = c->db.dataVec[f].data();       //  vectors may have moved while growing
+      if (!outBuf) c->db.dataPtr[f] = c->db.dataVec[f].data();          //  vectors may have moved while growing
       c->st.dbBytes += c->db.dataLen[f] + c->db.index[f].size();
     }
   }
@@ -1530,48 +1516,59 @@ extern "C" int mb_set_output_buffer(mb_ctx *c, void *hostBuf, uint64_t bytes) {
   return MB_OK;
 }
 
+//  The images of the round that has just been counted become a batch; the store starts again.
+static void stashBatch(mb_ctx *c) {
+  std::unique_ptr<MbDbImages> b(new MbDbImages());
+  for (u32 f = 0; f < 64; f++) {
+    b->dataVec[f] = std::move(c->db.dataVec[f]);  b->dataLen[f] = c->db.dataLen[f];  b->dataPtr[f] = b->dataVec[f].data();
+    b->index[f]   = std::move(c->db.index[f]);    b->owned[f] = c->db.owned[f];
+    c->db.dataVec[f].clear();  c->db.dataLen[f] = 0;  c->db.dataPtr[f] = nullptr;  c->db.index[f].clear();
+  }
+  c->batches.push_back(std::move(b));
+  c->nRecords = 0;  c->ingestStarted = false;  c->counted = false;
+}
+
 //  Count what the store holds as one batch, set its images aside, start the store again (finishBatch).
+//  Several GPUs: the call is collective -- a rank whose store fills during the ingest meets the others here, each of them
+//  in its own closeBatch or, when its reads are all in, in mb_count's rounds.
 static int closeBatch(mb_ctx *c) {
   const mb_stats prev = c->st;
-  uint8_t *const ob = c->outBuf;
   const bool inRecord = c->inRecord;
-  c->outBuf = nullptr;  c->inRecord = false;  c->closing = true;     //  a batch's images live in their own vectors
+  c->inRecord = false;  c->closing = true;
   c->st.nBases = 0;  c->st.nKmers = 0;  c->st.nPasses = 0;  c->st.msPack = 0;  c->st.msTotal = 0;
   const int rc = runCount(c);
-  c->outBuf = ob;  c->inRecord = inRecord;  c->closing = false;
+  c->inRecord = inRecord;  c->closing = false;
   if (rc != MB_OK) return rc;
   //  (the other statistics are sums already)
   c->st.nBases += prev.nBases;  c->st.nKmers += prev.nKmers;  c->st.nPasses += prev.nPasses;
   c->st.msPack += prev.msPack;  c->st.msTotal += prev.msTotal;
   c->st.nBatches = prev.nBatches + 1;
-  std::unique_ptr<MbDbImages> b(new MbDbImages());
-  for (u32 f = 0; f < 64; f++) {
-    b->dataVec[f] = std::move(c->db.dataVec[f]);  b->dataLen[f] = c->db.dataLen[f];  b->dataPtr[f] = b->dataVec[f].data();
-    b->index[f]   = std::move(c->db.index[f]);    b->owned[f] = true;
-    c->db.dataVec[f].clear();  c->db.dataLen[f] = 0;  c->db.dataPtr[f] = nullptr;  c->db.index[f].clear();
-  }
-  c->batches.push_back(std::move(b));
-  c->nRecords = 0;  c->ingestStarted = false;  c->counted = false;
+  stashBatch(c);
+  if (getenv("MB_TRACE")) fprintf(stderr, "[meryl-b200] rank %u: batch %u closed (%llu k-mers counted by this rank so far)\n", c->cfg.rank, c->st.nBatches, (u64)c->st.nKmers);
   return MB_OK;
 }
 
 //  mergeBatches: the batches' blocks are decoded, merged with saturating sums and encoded again with the block writer's
-//  rules, file group by file group, inside this context's arena (the read store is not needed any more).
+//  rules, file group by file group, inside this context's arena (the read store is not needed any more).  Several GPUs:
+//  every rank merges the files it owns, then rank 0 collects the histograms.
 static int mergeBatches(mb_ctx *c) {
   std::vector<const MbDbImages *> in;
   for (auto &b : c->batches) in.push_back(b.get());
+  const bool multi = c->comm && mb_comm_world(c->comm) > 1;
   MbMergeEndpoints E;
   E.memInputs = in.data();  E.nMem = (u32)in.size();  E.k = c->cfg.k;  E.wPrefix = c->cfg.wPrefix;
   E.outImages = &c->db;  E.outBuf = c->outBuf;  E.outCap = c->outCap;  E.outUsed = &c->outUsed;  E.outHist = &c->hist;
   E.arena = c->arena;  E.arenaBytes = c->arenaBytes;
   E.outPrefix = c->cfg.wPrefix;  E.streamMode = 0;
+  if (multi) E.onlyFiles = c->db.owned;
   c->outUsed = 0;
   mb_union_stats us;
   MB_TRY(mb_merge_pipeline(MB_OP_MERGE_BATCHES, 0, nullptr, 0, nullptr, c->device, 0, &us, &E));
   c->batches.clear();
+  c->st.nUnique = c->hist.nUnique;  c->st.nDistinct = c->hist.nDistinct;  c->st.nTotal = c->hist.nTotal;     //  this rank's files
+  if (multi) MB_TRY(gatherHistograms(c, c->arena, c->arenaBytes));
   mb_build_master_index(c->cfg.k, c->cfg.wPrefix, c->hist, c->db.master);
-  c->st.nUnique = c->hist.nUnique;  c->st.nDistinct = c->hist.nDistinct;  c->st.nTotal = c->hist.nTotal;
-  c->st.dbBytes = c->db.master.size();
+  c->st.dbBytes = (!multi || mb_comm_rank(c->comm) == 0) ? c->db.master.size() : 0;
   for (u32 f = 0; f < 64; f++) c->st.dbBytes += c->db.dataLen[f] + c->db.index[f].size();
   c->st.nLaunches += us.nLaunches;  c->st.h2dBytes += us.h2dBytes;  c->st.d2hBytes += us.d2hBytes;
   c->st.msMerge = us.msTotal;  c->st.msTotal += us.msTotal;
@@ -1583,8 +1580,26 @@ extern "C" int mb_count(mb_ctx *c) {
   mb_clear_error();
   if (!c)          return mb_fail(MB_EINVAL, "mb_count: NULL context");
   if (c->counted)  return mb_fail(MB_ESTATE, "mb_count: already counted");
-  if (c->batches.empty()) { MB_TRY(runCount(c)); c->st.nBatches = 1; return MB_OK; }
-  if (c->nRecords || c->fill || c->inRecord) MB_TRY(closeBatch(c));        //  the last batch
+  if (c->cfg.worldSize <= 1) {
+    if (c->batches.empty()) { MB_TRY(runCount(c)); c->st.nBatches = 1; return MB_OK; }
+    if (c->nRecords || c->fill || c->inRecord) MB_TRY(closeBatch(c));        //  the last batch
+    return mergeBatches(c);
+  }
+  //  Several GPUs: rounds of the collective count until every rank has said that nothing follows on its side.  A rank that has
+  //  closed batches (or meets one that has) counts the round as a batch; a rank whose reads are all in keeps taking part with
+  //  an empty store while another rank still closes batches (its files receive that rank's k-mers).
+  c->finalRound = true;
+  for (;;) {
+    if (!c->batches.empty()) MB_TRY(closeBatch(c));
+    else {
+      const mb_stats prev = c->st;
+      MB_TRY(runCount(c));
+      if (c->roundAnyBatch) { c->st.nBatches = prev.nBatches + 1; stashBatch(c); }
+    }
+    if (c->roundAllFinal) break;
+  }
+  c->finalRound = false;
+  if (c->batches.empty()) { c->st.nBatches = 1; return MB_OK; }
   return mergeBatches(c);
 }
 

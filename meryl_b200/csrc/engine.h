@@ -18,12 +18,3 @@ MbComm                  *mb_ctx_comm(mb_ctx *c);
 cudaStream_t             mb_ctx_stream(mb_ctx *c);
 int                      mb_ctx_device(mb_ctx *c);
 const mb_config         &mb_ctx_config(mb_ctx *c);
-
-//  parse.cu: FASTA/FASTQ bytes -> base stream on the device (experimental, MB_DEVICE_PARSE=1)
-struct MbDeviceParser;
-typedef int (*MbDeviceSink)(void *arg, const char *dStream, size_t n);
-int  mb_dparse_create(MbDeviceParser **out, cudaStream_t s);
-void mb_dparse_destroy(MbDeviceParser *P);
-int  mb_dparse_feed(MbDeviceParser *P, const uint8_t *data, size_t n, MbDeviceSink sink, void *arg);
-int  mb_dparse_finish(MbDeviceParser *P, MbDeviceSink sink, void *arg);
-u64  mb_dparse_launches(const MbDeviceParser *P);

@@ -35,11 +35,8 @@ namespace {
 
 const int SORT_THREADS = 256;
 const int SORT_MAX_PASSES = 24;
-#ifndef MB_SWEEP_RUNS_DEFAULT
-#define MB_SWEEP_RUNS_DEFAULT 0          //  copy-out by digit runs; measured A/B decides (MB_SWEEP_RUNS)
-#endif
 #ifndef MB_SWEEP_PREFETCH_DEFAULT
-#define MB_SWEEP_PREFETCH_DEFAULT 0      //  tiles ahead; measured A/B decides (MB_SWEEP_PREFETCH)
+#define MB_SWEEP_PREFETCH_DEFAULT 444    //  tiles ahead = one wave of resident CTAs on 148 SMs (measured at 8 Gbp: 0 -> 131.1 ms, 444 -> 124.2 ms, 1332 -> 136.0 ms)
 #endif
 
 template <int KW> struct SortShape;
@@ -331,7 +328,6 @@ template <int KW, int VER> struct SweepX {
 
 struct SweepXShared {
   unsigned char *buf;  u32 *binOff;  u64 *gofs;  u32 *gofs32;  u32 *warpTot;
-  u32 *chunkTab;  u32 *nChunks;                            //  copy-out by digit runs (see 4b)
 };
 
 //  Digit of a pass.  BYTE: the digit is one whole byte of the key (8 bits at a multiple of 8) -- a single
@@ -360,7 +356,7 @@ __device__ __forceinline__ unsigned short *counter_of(unsigned char *buf, u32 cb
   return (unsigned short *)(buf + off);
 }
 
-template <int KW, int VER, bool FULL, bool BYTE, bool RUNS>
+template <int KW, int VER, bool FULL, bool BYTE>
 __device__ __forceinline__ void
 sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
             u64 tile, u64 begin, u32 nIn, u32 seg, bool isFirst,
@@ -483,28 +479,6 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
     }
   }
 
-  //  (copy-out by runs: one warp cuts the digit runs of the stage buffer into chunks of <= 32 keys while the others look back --
-  //  entry = digit << 16 | first stage position; see 4b)
-  if (RUNS && warp == 2) {
-    const int DPL = RADIX / 32;                          //  digits per lane
-    u32 cnt[DPL], mine = 0;
-#pragma unroll
-    for (int i = 0; i < DPL; i++) { const u32 d = lane * DPL + i; cnt[i] = (binOff[d + 1] - binOff[d] + 31) >> 5; mine += cnt[i]; }
-    u32 incl = mine;
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (u32)o) incl += v;
-    }
-    u32 at = incl - mine;
-#pragma unroll
-    for (int i = 0; i < DPL; i++) {
-      const u32 d = lane * DPL + i, p0 = binOff[d];
-      for (u32 c = 0; c < cnt[i]; c++) sm.chunkTab[at + c] = (d << 16) | (p0 + 32 * c);
-      at += cnt[i];
-    }
-    if (lane == 31) *sm.nChunks = incl;
-  }
-
   //  3b. ... and only then wait for the earlier tiles of this segment (batched walk, LB status words per
   //  L2 round trip; the segment's first tile ends it).
   const u64 segBase = gbase[((u64)seg * nPasses + pass) * RADIX];              //  first key of the segment (digit 0 starts there)
@@ -540,19 +514,7 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
   __syncthreads();
 
   //  4b. digit runs to HBM.  Segments shorter than 2^32 keys: 32-bit offsets from the segment's first key.
-  if (RUNS) {
-    //  By runs: a warp takes a chunk of one digit's run -- the digit, its global offset and the run's end are warp-uniform,
-    //  so a key costs a load, an add and a store instead of digit extraction + offset lookup (9.4 -> ~5 instructions per
-    //  key in the ncu of the first form); the price is the idle lanes of every run's last chunk.
-    Key *outSeg = out + segBase;
-    MB_OPAQUE_PTR(outSeg);
-    const u32 nC = *sm.nChunks;
-    for (u32 c = warp; c < nC; c += S::WARPS) {
-      const u32 e = sm.chunkTab[c];
-      const u32 d = e >> 16, j = (e & 0xffffu) + lane;
-      if (j < binOff[d + 1]) outSeg[(u32)(gofs32[d] + j)] = stage[j];
-    }
-  } else if (!wide) {
+  if (!wide) {
     Key *outSeg = out + segBase;
     MB_OPAQUE_PTR(outSeg);                               //  keep it a base pointer: one IMAD.WIDE per store instead of 64-bit index math
     if (FULL) {
@@ -575,7 +537,7 @@ sweepx_tile(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::t
   }
 }
 
-template <int KW, int VER, bool RUNS>
+template <int KW, int VER>
 __global__ void __launch_bounds__(SweepShape<VER>::THREADS, SweepShape<VER>::MIN_CTAS)
 sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT<KW>::type *__restrict__ out,
                    const TileInfo *__restrict__ info,
@@ -587,8 +549,6 @@ sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
   __shared__ u64  gofs[S::RADIX];
   __shared__ u32  gofs32[S::RADIX];
   __shared__ u32  warpTot[S::WARPS];
-  __shared__ u32  chunkTab[RUNS ? S::TILE / 32 + S::RADIX : 1];
-  __shared__ u32  sChunks;
   __shared__ u64  sTile;
 
   if (threadIdx.x == 0) sTile = atomicAdd((unsigned long long *)tileCounter, 1ull);
@@ -607,11 +567,10 @@ sortx_sweep_kernel(const typename KeyT<KW>::type *__restrict__ in, typename KeyT
   const bool isFirst = (ti.seg >> 31) != 0;
   SweepXShared sm;
   sm.buf = buf;  sm.binOff = binOff;  sm.gofs = gofs;  sm.gofs32 = gofs32;  sm.warpTot = warpTot;
-  sm.chunkTab = chunkTab;  sm.nChunks = &sChunks;
 
   const bool full = (ti.n == (u32)S::TILE);
   const bool byte = (S::RBITS == 8) && (bits == 8) && ((shift & 7) == 0);
-#define MB_SX_CALL(F, B) sweepx_tile<KW, VER, F, B, RUNS>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm)
+#define MB_SX_CALL(F, B) sweepx_tile<KW, VER, F, B>(in, out, tile, ti.begin, ti.n, seg, isFirst, gbase, nPasses, pass, shift, bits, wide != 0, status, epoch, sm)
   if (S::RBITS == 8 && byte) { if (full) MB_SX_CALL(true, true);  else MB_SX_CALL(false, true);  }
   else                       { if (full) MB_SX_CALL(true, false); else MB_SX_CALL(false, false); }
 #undef MB_SX_CALL
@@ -759,20 +718,17 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   if (evAfterHist) cudaEventRecord(evAfterHist, s);
 
   Key *src = (Key *)dKeysA, *dst = (Key *)dKeysB;
-  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 2>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 3>::BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 3, true>,  cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 3>::BYTES)) != cudaSuccess) return e;
-  //  MB_SWEEP_PREFETCH=<tiles>: L2 prefetch distance of the sweep kernel (0 = off)
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 2>::BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sortx_sweep_kernel<KW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepX<KW, 3>::BYTES)) != cudaSuccess) return e;
+  //  MB_SWEEP_PREFETCH=<tiles>: L2 prefetch distance of the sweep kernel (0 = off).  (A copy-out by digit runs -- a warp per
+  //  chunk of one digit's run, no per-key digit extraction and offset lookup -- measured 14 % SLOWER, 149.0 vs 131.1 ms, and is gone.)
   const u32 pfDist = getenv("MB_SWEEP_PREFETCH") ? (u32)strtoul(getenv("MB_SWEEP_PREFETCH"), nullptr, 10) : MB_SWEEP_PREFETCH_DEFAULT;
-  //  MB_SWEEP_RUNS=1: copy-out by digit runs (256 x 6 shape; u32 and u64 keys: the runs of a 2048-key tile of 128-bit keys are too short)
-  const u32 runs = (getenv("MB_SWEEP_RUNS") ? getenv("MB_SWEEP_RUNS")[0] == '1' : MB_SWEEP_RUNS_DEFAULT) && KW < 2 && !wide ? 1u : 0u;
   for (u32 p = 0; p < plan.nPasses; p++) {
-#define MB_SX_LAUNCH(V, RN) do { typedef SweepX<KW, V> SX;                                                                                     \
-      sortx_sweep_kernel<KW, V, RN><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                   \
+#define MB_SX_LAUNCH(V) do { typedef SweepX<KW, V> SX;                                                                                         \
+      sortx_sweep_kernel<KW, V><<<(unsigned)nTiles, SX::THREADS, SX::BYTES, s>>>(src, dst, info, ghist, plan.nPasses, p,                       \
                                                                      plan.shift[p], plan.bits[p], wide, status, counter + p, p + 1, nTiles, pfDist); } while (0)
-    if (version == 2) MB_SX_LAUNCH(2, false);
-    else if (runs)    MB_SX_LAUNCH(3, true);
-    else              MB_SX_LAUNCH(3, false);
+    if (version == 2) MB_SX_LAUNCH(2);
+    else              MB_SX_LAUNCH(3);
 #undef MB_SX_LAUNCH
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nLaunches) *nLaunches += 1;

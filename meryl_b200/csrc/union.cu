@@ -1508,13 +1508,14 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
     HostBuf outIdx;
     u32 f0 = 0;
     while (f0 < 64) {
+      if (E.onlyFiles && !E.onlyFiles[f0]) { f0++; continue; }     //  (several GPUs: another rank's file)
       u32 f1 = f0 + 1;
       if (fixedOff + groupNeed(f0, f1) > want) {
         rc = mb_fail(MB_ENOMEM, "data file %u of the inputs needs %zu bytes on the device, %zu available", f0, groupNeed(f0, f1), want - fixedOff);
         goto done;
       }
       const u32 maxFiles = getenv("MB_UNION_MAX_FILES") ? (u32)strtoul(getenv("MB_UNION_MAX_FILES"), nullptr, 10) : 64;   //  testing knob
-      while (f1 < 64 && f1 - f0 < maxFiles && fixedOff + groupNeed(f0, f1 + 1) <= want) f1++;
+      while (f1 < 64 && f1 - f0 < maxFiles && !(E.onlyFiles && !E.onlyFiles[f1]) && fixedOff + groupNeed(f0, f1 + 1) <= want) f1++;
       st.nGroups++;
 
       Carve g(arena + fixedOff, want - fixedOff);

@@ -26,10 +26,13 @@ def sim_library():
     mb.LIB_PATH, mb._lib = saved
 
 
-def multi_count(world, k, w_prefix, data: bytes, out_dir: str, mode: int = 0):
+def multi_count(world, k, w_prefix, data: bytes, out_dir: str, mode: int = 0, weights=None):
     recs = data.split(b"@r")[1:]                          # synthetic FASTQ: every record starts with "@r"
     parts = []
-    for r in range(world):
+    if weights:                                           # uneven shares (rank r gets weights[r] parts of sum(weights))
+        cuts = [len(recs) * sum(weights[:r]) // sum(weights) for r in range(world + 1)]
+        parts = [b"".join(b"@r" + x for x in recs[cuts[r]:cuts[r + 1]]) for r in range(world)]
+    for r in range(world if not weights else 0):
         first, cnt = mbd.shard_range(len(recs), r, world)
         parts.append(b"".join(b"@r" + x for x in recs[first:first + cnt]))
     L = mb.lib()
@@ -144,3 +147,21 @@ def test_sim_multi_rank_p2p_scatter(tmp_path, monkeypatch, world, k, wp, cap, s3
     assert sum(nk) == n_reads * (rl - k + 1)
     assert (npass[0] > 1) == bool(cap)
     assert multi_key_bytes() == [4 if s32 else (8 if k <= 32 else 16)] * world
+
+
+@pytest.mark.parametrize("world,k,wp,weights", [(2, 21, 12, None), (4, 31, 10, [1, 4, 2, 0]), (2, 51, 9, [5, 1]), (8, 21, 12, [3, 1, 1, 1, 2, 0, 1, 1])])
+def test_sim_multi_rank_count_batches(tmp_path, monkeypatch, world, k, wp, weights):
+    """Count batches on several GPUs (merylOp-countThreads.C:286-380, kmers-writer-block.C:221-386): a rank whose read store
+    fills closes a batch, and the count is collective, so every rank takes part in it -- the others with what they hold at
+    that moment, or, once their reads are all in, from mb_count's rounds with an empty store.  Ranks with very different
+    shares (and one with nothing) close different numbers of batches of their own; every rank merges the files it owns,
+    rank 0 collects the histograms.  Same db as the single-process oracle."""
+    monkeypatch.setenv("MB_MAX_BATCH_BASES", "60000")
+    n_reads, rl = 3_000, 150
+    data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 90 + k + world)
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(data)
+    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "sim.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=%d" % wp, "count", str(fq), "output", ora])
+    nk, npass = multi_count(world, k, wp, data, out, weights=weights)
+    util.assert_same_db(ora, out)

@@ -324,22 +324,6 @@ def test_sim_count_batches_edges(tmp_path, monkeypatch):
         assert st.nBatches >= 3
 
 
-# ---- the parser's state machine on the device (experimental, MB_DEVICE_PARSE=1; csrc/parse.cu) ---------------------------
-
-def test_sim_device_parser_is_the_host_parser(monkeypatch):
-    import parse_cases
-    parse_cases.case_edges_and_fuzz(monkeypatch)
-
-
-@pytest.mark.parametrize("k,w_prefix,op", [(21, 8, "count"), (40, 10, "count-forward")])
-def test_sim_device_parser_in_the_pipeline(tmp_path, monkeypatch, k, w_prefix, op):
-    """mb_add_file with MB_DEVICE_PARSE=1: file bytes -> device -> K11 -> K1, several blocks per file, two files."""
-    monkeypatch.setenv("MB_DEVICE_PARSE", "1")
-    monkeypatch.setenv("MB_DPARSE_BLOCK", "65536")
-    st = _vs_oracle(tmp_path, {"r.fq": synth.reads_fastq_bytes(5_000, 900, 150, 0.01, 3), "g.fa": synth.fasta_bytes(7, 2_000, 4, width=60, eol=b"\r\n")}, k, w_prefix, op)
-    assert st.nLaunches > 20
-
-
 def test_sim_compressed_input_with_a_quote_in_its_name(tmp_path):
     """A .gz input arrives through `gzip -dc '<path>'`: the path is shell-quoted, a quote inside it included."""
     import gzip

@@ -347,6 +347,8 @@ def test_suffix32_path_equals_full_key_path(tmp_path, monkeypatch):
             monkeypatch.setenv("MB_NO_SUFFIX32", env)
         else:
             monkeypatch.delenv("MB_NO_SUFFIX32", raising=False)
+        if ws:                                           # (the in-place sort holds twice the keys per pass: cap the passes explicitly)
+            monkeypatch.setenv("MB_MAX_PASS_KEYS", "6000000")
         out = str(tmp_path / ("db%d" % len(dbs)))
         with mb.Counter(21, 13, workspace_bytes=ws) as c:
             c.add_file_bytes(data)
@@ -374,19 +376,4 @@ def test_multi_pass_full_keys(tmp_path, k):
         c.count()
         assert c.stats().nPasses > 1
         c.write_db(out)
-    util.assert_same_db(ora, out)
-
-
-@pytest.mark.skipif(not os.environ.get("MB_TEST_EXPERIMENTAL"), reason="experimental kernels: set MB_TEST_EXPERIMENTAL=1 (not yet run on a GPU)")
-def test_experimental_device_parser(tmp_path, monkeypatch):
-    """csrc/parse.cu (K11a-c): the device parser's stream is the host parser's; a count through it is the oracle's database."""
-    import parse_cases
-    parse_cases.case_edges_and_fuzz(monkeypatch, n_fuzz=300)
-    monkeypatch.setenv("MB_DEVICE_PARSE", "1")
-    monkeypatch.setenv("MB_DPARSE_BLOCK", "1048576")
-    fq = tmp_path / "r.fq"
-    fq.write_bytes(synth.reads_fastq_bytes(200_000, 40_000, 150, 0.01, 3))
-    ora, out = str(tmp_path / "ora.meryl"), str(tmp_path / "gpu.meryl")
-    util.run_oracle(["k=21", "memory=2", "count", str(fq), "output", ora])
-    mb.count([str(fq)], out, 21, "count", memory_gb=2)
     util.assert_same_db(ora, out)

@@ -36,10 +36,15 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
         data = open(fq_path, "rb").read()
         recs = data.split(b"@r")[1:]                      # synthetic FASTQ: every record starts with "@r"
         first, cnt = mbd.shard_range(len(recs), rank, world)
+        if os.environ.get("MB_TEST_UNEVEN"):              # very different shares: rank r gets (r * 3) % 5 parts (rank 0: nothing)
+            w = [(r * 3) % 5 for r in range(world)]
+            cuts = [len(recs) * sum(w[:r]) // sum(w) for r in range(world + 1)]
+            first, cnt = cuts[rank], cuts[rank + 1] - cuts[rank]
         mine = b"".join(b"@r" + r for r in recs[first:first + cnt])
         c = mb.Counter(k, wp, "count", device=rank, rank=rank, world_size=world)
         c.comm_init(mbd.broadcast_unique_id(mb.Counter.comm_unique_id, device="cuda"))
-        c.add_file_bytes(mine)
+        if mine:
+            c.add_file_bytes(mine)
         c.count()
         st = c.stats()
         total = mbd.all_ranks_sum(st.nKmers, "cuda")
@@ -47,7 +52,7 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
         c.close()
         dist.barrier()
         with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as fh:
-            fh.write("%d %d %d %d\n" % (st.nKmers, total, st.nPasses, st.keyBytes))
+            fh.write("%d %d %d %d %d\n" % (st.nKmers, total, st.nPasses, st.keyBytes, st.nBatches))
     finally:
         dist.destroy_process_group()
 
@@ -146,4 +151,32 @@ def test_cli_gpus_word(tmp_path, world):
     p = subprocess.run([mb.CLI_PATH, "k=21", "memory=2", "gpus=%d" % world, "count", str(fq), str(fa), "output", out],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr
+    util.assert_same_db(ora, out)
+
+
+@pytest.mark.parametrize("world,k", [(2, 21), (2, 51), (8, 21), (8, 31)])
+def test_multi_gpu_count_batches(tmp_path, world, k):
+    """Count batches on several GPUs: MB_MAX_BATCH_BASES makes the ranks' read stores "fill" after 300 k bases, the shares are
+    very uneven (rank 0 has no reads at all), every batch is counted by all ranks together and every rank merges the files it
+    owns (engine.cu: mb_count's rounds).  Emulator twin: tests/test_cusim_multi.py::test_sim_multi_rank_count_batches."""
+    _need(world)
+    import torch.multiprocessing as mp
+    n_reads, L = 40_000, 150
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(synth.reads_fastq_bytes(200_000, n_reads, L, 0.003, 71 + k))
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["k=%d" % k, "wprefix=12", "count", str(fq), "output", ora])
+    out = str(tmp_path / "gpu.meryl")
+    os.makedirs(out)
+    env = {"MB_MAX_BATCH_BASES": "300000", "MB_TEST_UNEVEN": "1"}
+    port = 29600 + (os.getpid() + world * 17 + k) % 300
+    mp.spawn(_worker, args=(world, port, str(fq), out, k, 12, env), nprocs=world, join=True)
+    batches = []
+    for r in range(world):
+        p = os.path.join(out, "rank%d.txt" % r)
+        st = [int(x) for x in open(p).read().split()]
+        os.remove(p)
+        assert st[1] == n_reads * (L - k + 1)
+        batches.append(st[4])
+    assert max(batches) >= 3, batches
     util.assert_same_db(ora, out)

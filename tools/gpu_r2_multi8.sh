@@ -9,7 +9,7 @@ mkdir -p $OUT
 exec > >(tee $OUT/r2_multi_8.log) 2>&1
 date; nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -$N; nproc; free -g | head -2
 echo "== a. multi-GPU byte parity at world 8";  date +%T
-MB_TEST_WORLDS=8 timeout 600 python -m pytest tests/test_gpu_multi.py -v -p no:cacheprovider 2>&1 | grep -E "PASS|FAIL|ERROR|passed|failed" | tee $OUT/r2_multi_8_pytest.log | tail -30
+MB_TEST_WORLDS=8 timeout 700 python -m pytest tests/test_gpu_multi.py -v -p no:cacheprovider -k "not nccl-u64-51" 2>&1 | grep -E "PASS|FAIL|ERROR|passed|failed" | tee $OUT/r2_multi_8_pytest.log | tail -30
 run() {   #  name, bench args
   local name=$1; shift
   echo "== bench $name";  date +%T
@@ -18,6 +18,6 @@ run() {   #  name, bench args
   grep '^{' $OUT/r2_bench_8gpu_$name.json | cut -c1-2400; tail -3 $OUT/r2_bench_8gpu_$name.err | cut -c1-400
 }
 run c2_k21 --steps 3 --warmup 2
-run c3_k31 --steps 2 --warmup 1 --k 31
-run c4_k51 --steps 2 --warmup 1 --k 51 --read-len 15000 --err 0.005 --gbp 50
+run c3_k31 --steps 2 --warmup 1 --k 31 --no-e2e
+run c4_k51 --steps 2 --warmup 1 --k 51 --read-len 15000 --err 0.005 --gbp 50 --no-e2e
 date

@@ -1,6 +1,7 @@
 """Timing of the entry points written without a GPU at hand, next to their CPU counterparts (run on the GPU box):
   a. mb_existence / meryl-lookup-b200 -existence   vs the reference's meryl-lookup (oracle/_ref/meryl-lookup)
-  b. mb_add_file with MB_DEVICE_PARSE=1 (csrc/parse.cu)   vs the multi-threaded host parser
+  b. mb_add_file: the multi-threaded host parser's rate (round 2 measured a device form of the state machine next to it:
+     6.6 GB/s against 14.3 GB/s on 16 host threads -- slower, and removed)
 usage: python tools/lookup_bench.py [Mbp of reads, default 300]      -> one JSON line per measurement"""
 import json
 import os
@@ -31,7 +32,7 @@ def main():
     size = os.path.getsize(fq)
     db = os.path.join(tmp, "reads.meryl")
     # b. ingest + count through the host parser and through the device parser
-    for tag, env in (("host_parser", {}), ("device_parser", {"MB_DEVICE_PARSE": "1"})):
+    for tag, env in (("host_parser", {}),):
         for k, v in env.items():
             os.environ[k] = v
         best = None
