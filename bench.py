@@ -317,17 +317,20 @@ def main():
     sweep_version = mb.lib().mb_dbg_sort_version(0)            # 0: query only
     sweep_name = {2: "sortx_sweep_kernel<128 threads, 8-bit digits>", 3: "sortx_sweep_kernel<256 threads, 6-bit digits>"}.get(sweep_version, "?")
     traffic = None                                              # DRAM bytes per launch, from the committed ncu capture of this kernel
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic_sweep.json")) as fh:
-            tr = json.load(fh)
-        if sweep_version == 3 and stats.keyBytes == 4:
-            traffic = tr["dram_bytes_per_key"] * stats.sortLaunchKeys / max(1, stats.sortPasses * stats.nPasses)
-    except Exception:
-        pass
+    for name in ("r2_traffic_sweep.json", "r1_traffic_sweep.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                tr = json.load(fh)
+            if sweep_version == 3 and stats.keyBytes == 4:
+                traffic = tr["dram_bytes_per_key"] * stats.sortLaunchKeys / max(1, stats.sortPasses * stats.nPasses)
+            break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": sweep_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                "algorithmic_bytes_per_launch": sort_bytes / max(1, stats.sortPasses * stats.nPasses),
-                "launches": stats.sortPasses * stats.nPasses}
+                "per": "one sweep (digit pass) over all keys of a pass over the reads; on one GPU it is issued as one launch per group of bins",
+                "algorithmic_bytes_per_sweep": sort_bytes / max(1, stats.sortPasses * stats.nPasses),
+                "sweeps": stats.sortPasses * stats.nPasses}
 
     # (The legs that start other processes come BEFORE the end-to-end leg: that one page-locks 130 GB of host memory, and a
     #  196 GB box has no room for it next to the reference binary's buckets and two databases in /dev/shm.)
@@ -412,7 +415,7 @@ def main():
                        "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix, "key_bytes": stats.keyBytes,
                        "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
                        "l2": "inputs (%.1f GB store, %.1f GB keys per pass on rank 0) far exceed the 126 MB L2" % (stats.nBases * 0.375 / 1e9, stats.nKmers * 8 / max(1, stats.nPasses) / 1e9),
-                       "parallelism": "reads split over %d GPU(s); 64 data files sharded by owner(f)=min(f,63-f) mod N, one NCCL all-to-all per pass" % world},
+                       "parallelism": ("one GPU" if world == 1 else "reads split over %d GPUs; 64 data files sharded by owner(f)=min(f,63-f) mod N; the extraction kernel stores every k-mer into its owner's HBM over NVLink (peer memory), NCCL for the small collectives" % world)},
             "stage_ms": {"histogram": stats.msHistogram, "extract": stats.msExtract, "sort_hist": stats.msSortHist,
                          "sort": stats.msSort, "count": stats.msCount, "encode": stats.msEncode, "exchange": stats.msExchange},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_cli": cli, "clocks": clocks,
