@@ -41,7 +41,10 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
             cuts = [len(recs) * sum(w[:r]) // sum(w) for r in range(world + 1)]
             first, cnt = cuts[rank], cuts[rank + 1] - cuts[rank]
         mine = b"".join(b"@r" + r for r in recs[first:first + cnt])
-        c = mb.Counter(k, wp, "count", device=rank, rank=rank, world_size=world)
+        # a 4 GB arena per rank: allocating the whole device and mapping seven 170 GB peer arenas costs every test of a
+        # world-8 run about a minute (measured: 9 tests in 643 s); the emulator's twins run with 384 MB arenas
+        c = mb.Counter(k, wp, "count", device=rank, rank=rank, world_size=world,
+                       workspace_bytes=0 if os.environ.get("MB_TEST_FULL_ARENA") else (4 << 30))
         c.comm_init(mbd.broadcast_unique_id(mb.Counter.comm_unique_id, device="cuda"))
         if mine:
             c.add_file_bytes(mine)
