@@ -1,7 +1,9 @@
 #!/bin/bash
-#  Round 2, last GPU call (one B200, ~22 min): the state that is committed -- the whole GPU suite, the bench with all its
-#  legs as the driver runs it, the reference arm, smoke(), the launch list and the DRAM traffic of the default sweep kernel.
-#  usage (from the repo root):  gpurun --timeout 2400 -- 'bash tools/gpu_r2_final.sh'
+#  The call round 2 had planned last and could not afford (its GPU minutes ended inside the 8-GPU call): the committed state on one
+#  B200, ~22 min -- the whole GPU suite, the bench with all its legs as the driver runs it, the reference arm, smoke(), the launch
+#  list and the DRAM traffic of the default sweep kernel, the A/Bs of the prefetch distance and of the dense extraction's members
+#  per thread.  First call of the next round.
+#  usage (from the repo root):  gpurun --timeout 2400 -- 'bash tools/gpu_next_first.sh'
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
