@@ -153,6 +153,11 @@ uint32_t mb_file_owner_of(uint32_t file, uint32_t worldSize);
  *  D * (2k - wPrefix + 36) / 8 + 2^wPrefix * 104 bytes).  */
 int mb_set_output_buffer(mb_ctx *ctx, void *hostBuf, uint64_t bytes);
 
+/*  Homopolymer compression for the inputs added from now on (the reference's `compress` word applies to the inputs that
+ *  follow it: merylCommandBuilder.C:237-240, :546; merylInput.C:258-262).  MB_FLAG_COMPRESS in mb_config = on from the start.
+ *  Only between records.  */
+int mb_set_input_compression(mb_ctx *ctx, int on);
+
 /*  Optional, before mb_count: the encoded data files go from the device straight into outDir while the count runs, one
  *  host thread per file (the reference's writer has one OpenMP thread per file, merylOp-countThreads.C:452-459), instead
  *  of staying in host memory; mb_write_db(ctx, outDir) then adds the 64 block indexes and merylIndex.  mb_get_image

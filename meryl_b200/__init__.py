@@ -98,6 +98,7 @@ def lib() -> ctypes.CDLL:
         L.mb_file_owner_of.restype = ctypes.c_uint32
         L.mb_set_output_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
         L.mb_set_output_dir.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.mb_set_input_compression.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.mb_count.argtypes = [ctypes.c_void_p]
         L.mb_get_image.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), u64p]
         L.mb_write_db.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
@@ -214,6 +215,10 @@ class Counter:
     def set_output_buffer(self, host_ptr: int, n_bytes: int) -> None:
         """Caller-owned (ideally pinned) host memory for the 64 data-file images."""
         _check(lib().mb_set_output_buffer(self._h, ctypes.c_void_p(host_ptr), n_bytes))
+
+    def set_input_compression(self, on: bool) -> None:
+        """Homopolymer compression for the inputs added from now on (the CLI's `compress` word)."""
+        _check(lib().mb_set_input_compression(self._h, 1 if on else 0))
 
     def set_output_dir(self, out_dir: str) -> None:
         """Before count(): stream the data files into out_dir while counting (then write_db(out_dir) adds the indexes)."""

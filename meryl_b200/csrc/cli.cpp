@@ -125,7 +125,7 @@ struct SharedPage {
   char         err[32][512];
 };
 
-static int multiGpuCount(uint32_t nGpus, mb_config cfg, const std::vector<const char *> &inputs, const char *outDir, mb_stats *total) {
+static int multiGpuCount(uint32_t nGpus, mb_config cfg, const std::vector<const char *> &inputs, const std::vector<char> &inputCompress, const char *outDir, mb_stats *total) {
   SharedPage *sh = (SharedPage *)mmap(nullptr, sizeof(SharedPage), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
   if (sh == MAP_FAILED) { perror("mmap"); return 1; }
   memset((void *)sh, 0, sizeof(SharedPage));
@@ -148,7 +148,10 @@ static int multiGpuCount(uint32_t nGpus, mb_config cfg, const std::vector<const 
       if (rc == MB_OK) rc = mb_create(&cfg, &c);
       if (rc == MB_OK) rc = mb_comm_init(c, sh->id);
       if (rc == MB_OK) rc = mb_set_output_dir(c, outDir);
-      for (size_t i = 0; rc == MB_OK && i < inputs.size(); i++) rc = mb_add_file_shard(c, inputs[i], r, nGpus);
+      for (size_t i = 0; rc == MB_OK && i < inputs.size(); i++) {
+        rc = mb_set_input_compression(c, inputCompress[i]);
+        if (rc == MB_OK) rc = mb_add_file_shard(c, inputs[i], r, nGpus);
+      }
       if (rc == MB_OK) rc = mb_count(c);
       if (rc == MB_OK) rc = mb_write_db(c, outDir);
       if (rc == MB_OK) rc = mb_get_stats(c, &sh->st[r]);
@@ -394,6 +397,7 @@ static int flatMain(int argc, char **argv) {
   bool haveOp = false, onlyConfig = false, quiet = false, compress = false;
   const char *outDir = nullptr, *countSuffix = nullptr;
   std::vector<const char *> inputs;
+  std::vector<char> inputCompress;                     //  per input: was `compress` in force when it was named?
 
   for (int i = 1; i < argc; i++) {
     const char *w = argv[i];
@@ -407,14 +411,14 @@ static int flatMain(int argc, char **argv) {
     else if (!strncmp(w, "threads=", 8))      { }                         //  no CPU worker threads to size
     else if (!strncmp(w, "gpus=", 5))         { nGpus = (uint32_t)strtoul(w + 5, 0, 10); }     //  (not a word of the reference)
     else if (isCountWord(w, &mode))           { haveOp = true; }
-    else if (!strcmp(w, "compress"))          { compress = true; }           //  merylCommandBuilder.C:237-240 (here: all inputs)
+    else if (!strcmp(w, "compress"))          { compress = true; }           //  merylCommandBuilder.C:237-240: for the inputs that follow
     else if (!strncmp(w, "count-suffix=", 13)) { countSuffix = w + 13; }       //  merylCommandBuilder.C:271-274
     else if (!strcmp(w, "output")) {
       if (i + 1 >= argc) { fprintf(stderr, "ERROR: 'output' needs a database name.\n"); return 1; }
       outDir = argv[++i];
     }
     else if (!strcmp(w, "[") || !strcmp(w, "]")) { }
-    else if (access(w, R_OK) == 0 || !strcmp(w, "-")) { inputs.push_back(w); }
+    else if (access(w, R_OK) == 0 || !strcmp(w, "-")) { inputs.push_back(w); inputCompress.push_back(compress ? 1 : 0); }
     else {
       //  not a count command line: the reference handles everything else
       const char *ref = getenv("MERYL_REFERENCE");
@@ -460,17 +464,28 @@ static int flatMain(int argc, char **argv) {
   mb_config cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.k = k;  cfg.mode = mode;  cfg.wPrefix = wPrefix;  cfg.device = -1;
-  if (compress) cfg.flags |= MB_FLAG_COMPRESS;
+  //  (`compress` holds for the inputs named after it: every input carries its own flag)
 
   //  count-suffix=: the full count goes to a temporary database, mb_keep_suffix writes the wanted k-mers (csrc/union.cu)
   const std::string finalDir = outDir;
   const std::string countDir = countSuffix ? finalDir + ".tmp-count" : finalDir;
   mb_stats st;
   if (nGpus > 1) {
-    if (multiGpuCount(nGpus, cfg, inputs, countDir.c_str(), &st) != 0) return 1;
-  } else if (mb_count_files(&cfg, inputs.data(), (uint32_t)inputs.size(), countDir.c_str(), &st) != MB_OK) {
-    fprintf(stderr, "ERROR: %s\n", mb_last_error());
-    return 1;
+    if (multiGpuCount(nGpus, cfg, inputs, inputCompress, countDir.c_str(), &st) != 0) return 1;
+  } else {
+    //  what mb_count_files does, with the per-input compression flag
+    mb_ctx *c = nullptr;
+    int rc = mb_create(&cfg, &c);
+    if (rc == MB_OK) rc = mb_set_output_dir(c, countDir.c_str());
+    for (size_t i = 0; rc == MB_OK && i < inputs.size(); i++) {
+      rc = mb_set_input_compression(c, inputCompress[i]);
+      if (rc == MB_OK) rc = mb_add_file(c, inputs[i]);
+    }
+    if (rc == MB_OK) rc = mb_count(c);
+    if (rc == MB_OK) rc = mb_write_db(c, countDir.c_str());
+    if (rc == MB_OK) rc = mb_get_stats(c, &st);
+    if (rc != MB_OK) { fprintf(stderr, "ERROR: %s\n", mb_last_error()); if (c) mb_destroy(c); return 1; }
+    mb_destroy(c);
   }
   if (countSuffix) {
     mb_union_stats us;

@@ -1500,6 +1500,16 @@ static int runCount(mb_ctx *c) {
 }
 
 
+extern "C" int mb_set_input_compression(mb_ctx *c, int on) {
+  mb_clear_error();
+  if (!c)          return mb_fail(MB_EINVAL, "mb_set_input_compression: NULL context");
+  if (c->counted)  return mb_fail(MB_ESTATE, "mb_set_input_compression: already counted");
+  if (c->inRecord) return mb_fail(MB_ESTATE, "mb_set_input_compression: inside a record (end it with endOfSequence first)");
+  if (on) c->cfg.flags |= MB_FLAG_COMPRESS; else c->cfg.flags &= ~(uint32_t)MB_FLAG_COMPRESS;
+  c->hpLast = 0;
+  return MB_OK;
+}
+
 extern "C" int mb_set_output_dir(mb_ctx *c, const char *outDir) {
   mb_clear_error();
   if (!c || !outDir || !outDir[0])  return mb_fail(MB_EINVAL, "mb_set_output_dir: NULL argument");

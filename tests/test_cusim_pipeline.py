@@ -341,3 +341,27 @@ def test_sim_compressed_input_with_a_quote_in_its_name(tmp_path):
             c.write_db(out)
         outs.append(out)
     util.assert_same_db(outs[0], outs[1])
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/meryl not built")
+def test_sim_cli_compress_holds_for_the_inputs_that_follow(tmp_path):
+    """`meryl k=K count a.fa compress b.fa output d`: the reference compresses homopolymer runs of the inputs named AFTER the
+    word only (merylCommandBuilder.C:237-240, :546).  The command line tool (emulated library in front of it) writes the
+    reference binary's directory, for the word in front of, between and behind the inputs."""
+    rng = np.random.default_rng(21)
+
+    def runs(n, seed_letters=b"ACGT"):
+        out = bytearray()
+        for _ in range(n):
+            out += bytes([seed_letters[int(rng.integers(0, 4))]]) * int(rng.integers(1, 5))
+        return bytes(out)
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa"
+    a.write_bytes(b">a\n" + runs(4000) + b"\n>a2\n" + runs(500) + b"\n")
+    b.write_bytes(b">b\n" + runs(3000) + b"\n")
+    env = dict(os.environ, LD_PRELOAD=SIM_LIB)
+    for i, words in enumerate((["compress", str(a), str(b)], [str(a), "compress", str(b)], [str(a), str(b), "compress"])):
+        ref, out = str(tmp_path / ("ref%d.meryl" % i)), str(tmp_path / ("cli%d.meryl" % i))
+        util.run_ref(["k=15", "memory=2", "threads=4", "count"] + words + ["output", ref])
+        p = subprocess.run([mb.CLI_PATH, "k=15", "memory=2", "count"] + words + ["output", out], capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr
+        util.assert_same_db(ref, out)
