@@ -235,7 +235,9 @@ static int runTree(const char *prog, TreeNode &node, const std::vector<std::stri
     if (w == "output" && j + 1 < node.words.size()) { haveOutput = true; outDb = node.words[j + 1]; }
     cmd.push_back(w);
   }
-  if (!haveOutput) {
+  bool report = false;                                     //  print: the result is text, not a database
+  for (const std::string &w : node.words) if (w == "print") report = true;
+  if (!haveOutput && !(isRoot && report)) {
     if (isRoot) { fprintf(stderr, "ERROR: No output specified for the outermost operation.\n"); return 1; }
     outDb = tmpBase + ".tmp-" + std::to_string(tmpSeq++);
     temps.push_back(outDb);
@@ -301,6 +303,13 @@ int main(int argc, char **argv) {
   }
   std::string rootOut;
   for (size_t j = 0; j + 1 < top->words.size(); j++) if (top->words[j] == "output") rootOut = top->words[j + 1];
+  bool rootReports = false;                                //  `print [ ... ]`: the sub-operation runs into a temporary database and is printed
+  for (const std::string &w : top->words)                  //  from that (`histogram` / `statistics` of a tree: the reference refuses, and so does this)
+    if (w == "print") rootReports = true;
+  if (rootOut.empty() && rootReports) {
+    const char *td = getenv("TMPDIR");
+    rootOut = std::string(td && td[0] ? td : "/tmp") + "/meryl-b200-" + std::to_string((long)getpid());
+  }
   if (rootOut.empty()) { fprintf(stderr, "ERROR: No output specified for the outermost operation.\n"); return 1; }
   int tmpSeq = 0;
   std::vector<std::string> temps;

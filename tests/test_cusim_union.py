@@ -118,3 +118,31 @@ def test_sim_existence_vs_reference_lookup(tmp_path, monkeypatch, k):
 @pytest.mark.parametrize("k", [21])
 def test_sim_cli_lookup_vs_reference(tmp_path, k):
     uc.case_cli_lookup(str(tmp_path), k, env=dict(os.environ, LD_PRELOAD=SIM_LIB))
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/meryl not built")
+def test_sim_cli_print_of_an_operation_tree(tmp_path):
+    """`meryl print [ union-sum a b ]` (merylCommandBuilder.C:441-563): the sub-operation runs into a temporary database and is
+    printed from that -- the reference binary's lines (its order depends on its threads).  `histogram` / `statistics` of a
+    tree: the reference refuses ("can only accept databases"), and so does the tool."""
+    import subprocess
+    from meryl_b200 import synth
+    env = dict(os.environ, LD_PRELOAD=SIM_LIB, TMPDIR=str(tmp_path))
+    dbs = []
+    for i in range(2):
+        fq = tmp_path / ("r%d.fq" % i)
+        fq.write_bytes(synth.reads_fastq_bytes(3_000, 400, 120, 0.01, 40 + i))
+        db = str(tmp_path / ("d%d.meryl" % i))
+        util.run_ref(["k=17", "memory=2", "threads=4", "count", str(fq), "output", db])
+        dbs.append(db)
+    cli = os.path.join(util.ROOT, "meryl_b200", "meryl-b200")
+    tree = ["print", "[", "union-sum", dbs[0], dbs[1], "]"]
+    ref = subprocess.run([util.REF_BIN, "threads=4"] + tree, capture_output=True, text=True)
+    got = subprocess.run([cli] + tree, capture_output=True, text=True, env=env)
+    assert ref.returncode == 0 and got.returncode == 0, (ref.stderr[-500:], got.stderr[-500:])
+    assert sorted(ref.stdout.splitlines()) == sorted(got.stdout.splitlines()) and got.stdout
+    assert not [f for f in os.listdir(tmp_path) if f.startswith("meryl-b200-")], "the temporary database is removed"
+    for word in ("histogram", "statistics"):
+        tree = [word, "[", "union-sum", dbs[0], dbs[1], "]"]
+        assert subprocess.run([util.REF_BIN, "threads=4"] + tree, capture_output=True).returncode != 0
+        assert subprocess.run([cli] + tree, capture_output=True, env=env).returncode != 0
