@@ -75,19 +75,26 @@ void *dyn_smem(void) { return g_dynSmem; }
 //  "Device" allocations: anonymous mappings (large arenas stay untouched until used); small ones are
 //  filled with garbage, like fresh device memory, so a kernel cannot rely on zeroed buffers.
 void *dev_alloc(size_t bytes) {
-  const size_t total = ((bytes ? bytes : 1) + 4096 + 4095) / 4096 * 4096;
+  //  [ header page | the allocation, its END (rounded up to 256 bytes) on a page boundary | inaccessible page ]: running over
+  //  the end of a device allocation stops the process here, like the smaller ones compute-sanitizer would report
+  const size_t body  = ((bytes ? bytes : 1) + 4095) / 4096 * 4096;
+  const size_t total = 4096 + body + 4096;
   unsigned char *p = (unsigned char *)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
   if (p == MAP_FAILED) return nullptr;
-  *(size_t *)p = total;
+  if (mprotect(p + 4096 + body, 4096, PROT_NONE) != 0) { munmap(p, total); return nullptr; }
+  const size_t rounded = ((bytes ? bytes : 1) + 255) / 256 * 256;
+  unsigned char *q = p + 4096 + body - rounded;
+  ((size_t *)p)[0] = total;
   //  fresh device memory is not zero: poison it (large arenas only when CUSIM_POISON_ALL is set -- touching gigabytes is slow)
   static const bool poisonAll = getenv("CUSIM_POISON_ALL") != nullptr;
-  if (poisonAll || bytes <= ((size_t)64 << 20)) memset(p + 4096, 0xa5, bytes);
-  return p + 4096;
+  if (poisonAll || bytes <= ((size_t)64 << 20)) memset(q, 0xa5, bytes);
+  ((void **)(q - 8))[0] = p;                              //  (the slack in front of q: where dev_free finds the mapping)
+  return q;
 }
 void dev_free(void *q) {
   if (!q) return;
-  unsigned char *p = (unsigned char *)q - 4096;
-  munmap(p, *(size_t *)p);
+  unsigned char *p = (unsigned char *)((void **)((unsigned char *)q - 8))[0];
+  munmap(p, ((size_t *)p)[0]);
 }
 unsigned long long launches(void) { return g_launches; }
 
@@ -123,8 +130,21 @@ void launch(dim3 grid, dim3 block, size_t dynSmem, const std::function<void()> &
     g_stacks = (unsigned char *)mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (g_stacks == MAP_FAILED) { perror("cusim: mmap"); abort(); }
   }
-  if (dynSmem > g_dynCap) { free(g_dynSmem); g_dynSmem = (unsigned char *)aligned_alloc(128, (dynSmem + 127) / 128 * 128); g_dynCap = dynSmem; }
   if (dynSmem > (size_t)227 << 10) { fprintf(stderr, "cusim: %zu bytes of dynamic shared memory exceed the 227 KB of an SM\n", dynSmem); abort(); }
+  //  Dynamic shared memory ends at an inaccessible page: a kernel that runs over the size it was launched with (rounded up
+  //  to 128 bytes, the alignment the sources declare) stops here instead of scribbling over whatever a real SM has there.
+  {
+    static unsigned char *region = nullptr;               //  256 KB + one guard page, mapped once
+    const size_t cap = (size_t)256 << 10;
+    if (!region) {
+      region = (unsigned char *)mmap(nullptr, cap + 4096, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+      if (region == MAP_FAILED) { perror("cusim: mmap"); abort(); }
+      if (mprotect(region + cap, 4096, PROT_NONE) != 0) { perror("cusim: mprotect"); abort(); }
+    }
+    const size_t rounded = (dynSmem + 127) / 128 * 128;
+    g_dynSmem = region + cap - rounded;
+    g_dynCap  = rounded;
+  }
   g_launches++;
   g_body = &body;
   static const bool trace = getenv("CUSIM_TRACE") != nullptr;
