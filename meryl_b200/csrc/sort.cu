@@ -134,7 +134,7 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
     if (n > (u64)TILE) n = TILE;
 
     //  HIST_UNROLL independent loads per thread are in flight before the first shared-memory atomic (one load at a time
-    //  left the kernel waiting on HBM latency: 1.3 TB/s measured).  MB_HIST_SIMPLE=1 keeps the one-load loop for A/B.
+    //  left the kernel waiting on HBM latency: 1.3 TB/s measured).  (unrolled == 0: the one-load loop, kept for reference.)
     if (unrolled) {
       const Key *kp = keys + begin;
       u32 j = t;
@@ -167,7 +167,7 @@ sort_hist_kernel(const typename KeyT<KW>::type *__restrict__ keys,
   }
 }
 
-//  Joint form (MB_HIST_JOINT=1; not the default: measured equal): adjacent passes are histogrammed together (one
+//  Joint form (the default since round 2; MB_HIST_SINGLE=1 for the kernel above): adjacent passes are histogrammed together (one
 //  shared-memory atomic per PAIR of digits into a 2^(b1+b2)-entry table) and split into the two marginal histograms
 //  only when a CTA flushes.
 struct SortHistGroups {
@@ -700,7 +700,7 @@ static cudaError_t sort_impl(void *dKeysA, void *dKeysB, u64 nKeys,
   }
   if (histSingle || hg.nGroups > 8 || hg.total * 4 > 96 * 1024) {
     sort_hist_kernel<KW><<<(unsigned)histGrid, SORT_THREADS, 0, s>>>((const Key *)dKeysA, dSegStart, dSegTile, nSegs, nTiles, pt, (u32)R, ghist,
-                                                                     getenv("MB_HIST_SIMPLE") ? 0u : 1u);
+                                                                     1u);
   } else {
 #define MB_HIST2(NG) do {                                                                                                                   \
       if ((e = cudaFuncSetAttribute(sort_hist2_kernel<KW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(hg.total * 4))) != cudaSuccess) return e;  \
