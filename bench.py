@@ -103,6 +103,16 @@ def workload_name(gbp):
             % (K, gbp, READ_LEN, ERR * 100))
 
 
+def shared_config(total_reads, world, reduced=None):
+    """`config` of the JSON line: the workload and nothing else, so that both arms print the same object for the same job."""
+    gbp = total_reads * READ_LEN / 1e9
+    kmers = total_reads * (READ_LEN - K + 1)
+    return {"workload": workload_name(gbp) + ("; " + reduced if reduced else ""),
+            "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": kmers,
+            "l2": "no flush between steps: one step reads %.1f GB of packed reads and moves %.1f G k-mers through the sort, far beyond the 126 MB L2" % (total_reads * (READ_LEN + 1) * 0.375 / 1e9, kmers / 1e9),
+            "parallelism": "strong scaling: the one workload split evenly over %d GPU(s)" % world}
+
+
 def reference_arm(args, world, rank):
     """The reference's own CPU implementation (the unmodified binary oracle/_ref/meryl, all host threads) on a bounded
     prefix of the workload's reads, FASTQ file in /dev/shm -> database directory in /dev/shm, wall clock of the process.
@@ -139,8 +149,9 @@ def reference_arm(args, world, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "k-mers/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(total_gbp), "k": K, "read_len": READ_LEN, "sample_gbp": args.ref_gbp,
-                   "sample": "each step counts the first %.2f Gbp of the workload's reads (FASTQ in /dev/shm) with the unmodified reference binary" % args.ref_gbp},
+        "config": shared_config(int(total_gbp * 1e9) // READ_LEN, world),
+        "sample_gbp": args.ref_gbp,
+        "sample": "each step counts the first %.2f Gbp of the workload's reads (FASTQ in /dev/shm) with the unmodified reference binary" % args.ref_gbp,
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": cores, "kind": "reference",
                          "sample": "first %d reads (%.2f Gbp) of the workload as a FASTQ file in /dev/shm, threads=%d memory=%d, process start to exit" % (n_reads, args.ref_gbp, cores, args.ref_memory_gb)},
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -411,11 +422,10 @@ def main():
             "value_kind": "device_resident: the whole count with the packed reads already in HBM; `e2e` is the same job from host buffers through the C ABI, `e2e_cli` the command line tools on a FASTQ file",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(total_reads * READ_LEN / 1e9) + ("; " + reduced if reduced else ""),
-                       "k": K, "read_len": READ_LEN, "reads": total_reads, "kmers": total_kmers, "w_prefix": pl.w_prefix, "key_bytes": stats.keyBytes,
-                       "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
-                       "l2": "inputs (%.1f GB store, %.1f GB keys per pass on rank 0) far exceed the 126 MB L2" % (stats.nBases * 0.375 / 1e9, stats.nKmers * 8 / max(1, stats.nPasses) / 1e9),
-                       "parallelism": ("one GPU" if world == 1 else "reads split over %d GPUs; 64 data files sharded by owner(f)=min(f,63-f) mod N; the extraction kernel stores every k-mer into its owner's HBM over NVLink (peer memory), NCCL for the small collectives" % world)},
+            "config": shared_config(total_reads, world, reduced),
+            "plan": {"w_prefix": pl.w_prefix, "key_bytes": stats.keyBytes, "passes": stats.nPasses, "sort_digit_passes": stats.sortPasses,
+                     "per_rank": "%.1f GB packed read store, %.1f GB of keys per pass over the reads on rank 0" % (stats.nBases * 0.375 / 1e9, stats.nKmers * stats.keyBytes / max(1, stats.nPasses) / 1e9),
+                     "routing": ("one GPU" if world == 1 else "reads split over %d GPUs; 64 data files sharded by owner(f)=min(f,63-f) mod N; the extraction kernel stores every k-mer into its owner's HBM over NVLink (peer memory), NCCL for the small collectives" % world)},
             "stage_ms": {"histogram": stats.msHistogram, "extract": stats.msExtract, "sort_hist": stats.msSortHist,
                          "sort": stats.msSort, "count": stats.msCount, "encode": stats.msEncode, "exchange": stats.msExchange},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_cli": cli, "clocks": clocks,
