@@ -20,6 +20,18 @@ def _build_oracle():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_override():
+    """MB_TEST_LIB=<path>: run the tests against another build of the C-ABI library (e.g. the `-m gpu` files against
+    tests/cusim/_build/libmeryl_b200_sim.so in a container without a GPU, as far as they go through the binding)."""
+    path = os.environ.get("MB_TEST_LIB")
+    if path:
+        import meryl_b200 as mb
+        mb.LIB_PATH, mb._lib = path, None
+        os.environ["LD_PRELOAD"] = path          # the command line tools of the tests bind the same symbols
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     """A GPU test that hangs (a spinning kernel) must end the process, not sit on the box until the outer limit."""
     if not config.pluginmanager.hasplugin("timeout"):
