@@ -27,6 +27,10 @@
 //             fields_kernel   thread per distinct k-mer: its unary bit, binary bits and count,
 //                             OR-ed into the zeroed output with 64-bit atomics
 //
+//  Stream-writer mode (set operations): a prefix without k-mers writes nothing, and a prefix with more than 16 Mi k-mers is
+//  written as consecutive blocks (parts) of 16 Mi k-mers under one index entry, like merylStreamWriter::addMer
+//  (kmers-writer-stream.C:127-141): each part is laid out as a block of its own, MbSplitPart keeps its place.
+//
 //  Bytes: reads (W+8) per distinct k-mer (+ the chain's O(log n) probes), writes ~(b+34)/8.
 
 #include "kernels.cuh"
@@ -118,6 +122,9 @@ __device__ __forceinline__ u64 lower_bound_prefix(const Key *keys, u64 D, u32 wS
   return lo;
 }
 
+//  A stream-writer prefix that is written as several blocks (MbEncodeParams::streamBlockMax).
+__device__ __forceinline__ bool is_split(const MbEncodeParams &p, u64 n) { return p.streamMode && n > p.streamBlockMax; }
+
 //  ---- layout ---------------------------------------------------------------------------------
 
 template <int KW>
@@ -138,15 +145,31 @@ layout_kernel(MbEncodeParams p, MbBlockMeta *__restrict__ meta, u64 *__restrict_
   u64 words = 0;
   u32 nSub  = 0;
   const bool skip = p.streamMode && n == 0;                 //  the stream writer never writes a block without k-mers
-  if (!skip) nSub = walk_subblocks(keys, first, n, s, [&](u32, u64, u64 len) { words += (len + 63) >> 6; });
-  if (p.streamMode && n > ((u64)16 << 20)) totals[4] = 1;   //  would be split by merylStreamWriter::addMer
+  u64 bytes = 0;
+  if (is_split(p, n)) {
+    //  merylStreamWriter::addMer dumps the batch when it holds streamBlockMax k-mers and goes on with the same prefix:
+    //  every part is a block of its own (own shape, own sub-block chain); the parts follow each other in the file
+    MbSplitPart *part = p.parts + 2 * (first / p.streamBlockMax);
+    for (u64 at = 0; at < n; at += p.streamBlockMax, part++) {
+      const u64 np = (n - at < p.streamBlockMax) ? n - at : p.streamBlockMax;
+      const BlockShape sp = block_shape(np, wSuffix);
+      u64 w = 0;
+      const u32 ns = walk_subblocks(keys, first + at, np, sp, [&](u32, u64, u64 len) { w += (len + 63) >> 6; });
+      part->relByte = bytes;  part->relSub = nSub;  part->nSub = ns;
+      bytes += 16 + 16 * (u64)ns + 8 * w;
+      nSub  += ns;
+    }
+  } else if (!skip) {
+    nSub  = walk_subblocks(keys, first, n, s, [&](u32, u64, u64 len) { words += (len + 63) >> 6; });
+    bytes = 16 + 16 * (u64)nSub + 8 * words;
+  }
 
   MbBlockMeta m;
   m.first    = first;
   m.outByte  = 0;
   m.nSub     = nSub;
   m.subFirst = 0;
-  m.bytes    = skip ? 0 : 16 + 16 * (u64)nSub + 8 * words;
+  m.bytes    = bytes;
   meta[blk]  = m;
 
   if (blk == 0)             totals[2] = first;             //  the chunk's distinct k-mers are [totals[2], totals[3])
@@ -245,6 +268,34 @@ __device__ __forceinline__ void or_bits(u64 *words, u64 pos, u32 width, u64 valu
   }
 }
 
+//  Container header, sub-block tables and the 528-bit block header of one serialised block of n k-mers (keys[first ...]).
+template <typename Key>
+__device__ void write_block_head(const Key *keys, u64 first, u64 n, const BlockShape &s, u64 prefix, u32 nSub, u64 *o, u32 *sw) {
+  u64 *bgn  = o + 2;
+  u64 *len  = bgn + nSub;
+  u64 *data = len + nSub;
+
+  o[0] = s.maxBits;
+  o[1] = (u64)nSub | ((u64)(32 * ((nSub - 1) / 32 + 1)) << 32);
+
+  u32 wordBase = 0;
+  walk_subblocks(keys, first, n, s, [&](u32 j, u64 b0, u64 l) {
+    bgn[j] = b0;
+    len[j] = l;
+    sw[j]  = wordBase;
+    wordBase += (u32)((l + 63) >> 6);
+  });
+
+  //  the 528 header bits live at the start of sub-block 0 (maxBits >= 1024)
+  atomicOr((unsigned long long *)&data[0], 0x7461446c7972656dull);
+  atomicOr((unsigned long long *)&data[1], 0x0a3030656c694661ull);
+  atomicOr((unsigned long long *)&data[2], (unsigned long long)prefix);
+  atomicOr((unsigned long long *)&data[3], (unsigned long long)n);
+  atomicOr((unsigned long long *)&data[4], (1ull << 56) | ((u64)s.u << 24) | ((u64)s.b >> 8));
+  atomicOr((unsigned long long *)&data[5], ((u64)s.b & 0xff) << 56);
+  atomicOr((unsigned long long *)&data[6], 1ull << 48);
+}
+
 //  ---- per-block headers ------------------------------------------------------------------------
 
 template <int KW>
@@ -271,31 +322,15 @@ header_kernel(MbEncodeParams p, MbEncodeChunk c, const MbBlockMeta *__restrict__
     return;
   }
 
-  u64 *o    = (u64 *)(out + (m.outByte - c.chunkByte0));
-  u64 *bgn  = o + 2;
-  u64 *len  = bgn + m.nSub;
-  u64 *data = len + m.nSub;
-  u32 *sw   = subWord + (m.subFirst - c.chunkSub0);
-
-  o[0] = s.maxBits;
-  o[1] = (u64)m.nSub | ((u64)(32 * ((m.nSub - 1) / 32 + 1)) << 32);
-
-  u32 wordBase = 0;
-  walk_subblocks(keys, m.first, n, s, [&](u32 j, u64 b0, u64 l) {
-    bgn[j] = b0;
-    len[j] = l;
-    sw[j]  = wordBase;
-    wordBase += (u32)((l + 63) >> 6);
-  });
-
-  //  the 528 header bits live at the start of sub-block 0 (maxBits >= 1024)
-  atomicOr((unsigned long long *)&data[0], 0x7461446c7972656dull);
-  atomicOr((unsigned long long *)&data[1], 0x0a3030656c694661ull);
-  atomicOr((unsigned long long *)&data[2], (unsigned long long)prefix);
-  atomicOr((unsigned long long *)&data[3], (unsigned long long)n);
-  atomicOr((unsigned long long *)&data[4], (1ull << 56) | ((u64)s.u << 24) | ((u64)s.b >> 8));
-  atomicOr((unsigned long long *)&data[5], ((u64)s.b & 0xff) << 56);
-  atomicOr((unsigned long long *)&data[6], 1ull << 48);
+  if (is_split(p, n)) {
+    const MbSplitPart *part = p.parts + 2 * (m.first / p.streamBlockMax);
+    for (u64 at = 0; at < n; at += p.streamBlockMax, part++) {
+      const u64 np = (n - at < p.streamBlockMax) ? n - at : p.streamBlockMax;
+      write_block_head(keys, m.first + at, np, block_shape(np, wSuffix), prefix, part->nSub,
+                       (u64 *)(out + (m.outByte + part->relByte - c.chunkByte0)), subWord + (m.subFirst + part->relSub - c.chunkSub0));
+    }
+  } else
+    write_block_head(keys, m.first, n, s, prefix, m.nSub, (u64 *)(out + (m.outByte - c.chunkByte0)), subWord + (m.subFirst - c.chunkSub0));
 
   //  index entry: {prefix, byte position in its data file, nKmers}
   const u32 blockBits   = p.wPrefix - 6;
@@ -324,9 +359,18 @@ fields_kernel(MbEncodeParams p, MbEncodeChunk c, const MbBlockMeta *__restrict__
   const u32  wSuffix = 2 * p.k - p.wPrefix;
   const Key  key     = keys[g];
   const u64  blk     = key_shr64(key, wSuffix) - p.blockLo;
-  const MbBlockMeta m = meta[blk];
+  MbBlockMeta m = meta[blk];
   const u64  end     = (blk + 1 < p.nBlocks) ? meta[blk + 1].first : passEnd;
-  const u64  n       = end - m.first;
+  u64        n       = end - m.first;
+  if (is_split(p, n)) {                                      //  the k-mer's part of an over-full prefix is its block
+    const u64 q = (g - m.first) / p.streamBlockMax;
+    const MbSplitPart part = p.parts[2 * (m.first / p.streamBlockMax) + q];
+    n          = (n - q * p.streamBlockMax < p.streamBlockMax) ? n - q * p.streamBlockMax : p.streamBlockMax;
+    m.first   += q * p.streamBlockMax;
+    m.outByte += part.relByte;
+    m.subFirst += part.relSub;
+    m.nSub     = part.nSub;
+  }
   const u64  i       = g - m.first;
   const BlockShape s = block_shape(n, wSuffix);
 

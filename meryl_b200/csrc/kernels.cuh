@@ -225,6 +225,11 @@ struct MbBlockMeta {           //  one per block of the pass, written by the lay
   u32 subFirst;                //  index of its first entry in the sub-block word table
   u64 bytes;                   //  serialised size
 };
+struct MbSplitPart {           //  one of the consecutive blocks an over-full stream-writer prefix is written as
+  u64 relByte;                 //  its place after the first part's, in bytes ...
+  u32 relSub;                  //  ... and in the sub-block word table
+  u32 nSub;
+};
 struct MbEncodeParams {
   const void *keys;            //  distinct keys of the pass (sorted)
   const u64  *runStart;
@@ -235,8 +240,14 @@ struct MbEncodeParams {
   u64         nBlocks;         //  number of consecutive block prefixes in the pass
   const u32  *counts;          //  NULL: value j = runStart[j+1] - runStart[j];  else value j = counts[j] (set operations)
   u32         streamMode;      //  1: merylStreamWriter rules (kmers-writer-stream.C:89-157): a prefix without k-mers writes
-                               //     no block and leaves its index entry {0, UINT64_MAX, 0}; dTotals[4] is set if a block
-                               //     holds more than 16 Mi k-mers (the stream writer would split it; not implemented)
+                               //     no block and leaves its index entry {0, UINT64_MAX, 0}; a prefix with more than
+                               //     streamBlockMax k-mers is written as consecutive blocks of streamBlockMax k-mers (the last
+                               //     one shorter) under ONE index entry {prefix, place of the first, total k-mers}
+                               //     (merylStreamWriter::addMer :131-141, merylFileIndex::set, kmers-files.H:116-128)
+  u64         streamBlockMax = 0;      //  16 Mi in the reference (_batchMaxKmers)
+  MbSplitPart *parts = nullptr;        //  streamMode: 2 * (nDistinct / streamBlockMax) + 4 slots; part q of the block whose first
+                                       //     k-mer is `first` lives in slot 2 * (first / streamBlockMax) + q  (two over-full
+                                       //     blocks are more than streamBlockMax k-mers apart, so their slots never meet)
 };
 //  E0+E1 for the whole pass: per-block extent and layout size into dMeta[nBlocks]; an exclusive scan
 //  then fills outByte/subFirst (relative to the pass).  dTotals[0] = total bytes, dTotals[1] = total

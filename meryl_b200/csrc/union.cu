@@ -756,6 +756,42 @@ int streamFromDevice(PinnedRing &R, const uint8_t *dSrc, size_t total, cudaStrea
   return MB_OK;
 }
 
+//  merylStreamWriter keeps at most this many k-mers in a block (_batchMaxKmers, kmers-writer-stream.C:127): a prefix with
+//  more is written as consecutive blocks under one index entry.  MB_STREAM_BLOCK_MAX is a testing knob (16 Mi k-mers of
+//  one prefix are too many for most emulator runs); the reader side must be told the same value.
+u64 streamBlockMax(void) {
+  const char *e = getenv("MB_STREAM_BLOCK_MAX");
+  const u64 v = e ? strtoull(e, nullptr, 10) : 0;
+  return v ? v : ((u64)16 << 20);
+}
+
+//  The serialised blocks behind one entry {prefix, place, nKmers} of a block index: one -- or, when the entry counts more
+//  k-mers than the stream writer puts in a block, the consecutive blocks of that prefix (merylFileIndex::set adds their
+//  k-mers up, kmers-files.H:116-128; the reference's reader just reads block after block, kmers-reader.C).  Their places
+//  follow from the container headers: {maxBits, nSub | ..., bgn[nSub], len[nSub], data...}, data word 3 = the block's
+//  k-mer count.  fetch(pos, dst, len) reads bytes of the data file.
+template <typename Fetch>
+int blocksOfEntry(Fetch fetch, u64 at, u64 nEntry, u64 fileBytes, u64 &nk, std::vector<UnionBlock> &tab) {
+  UnionBlock ub;
+  if (nEntry <= streamBlockMax()) { ub.byteOff = at;  ub.outIdx = nk;  tab.push_back(ub);  nk += nEntry;  return MB_OK; }
+  std::vector<u64> len;
+  for (u64 left = nEntry; left; ) {
+    u64 head[2], nBlock = 0;
+    if (at + 16 > fileBytes || !fetch(at, head, 16)) return MB_EFORMAT;
+    const u64 nSub = head[1] & 0xffffffffull;
+    if (nSub == 0 || nSub > (fileBytes - at) / 16 || at + 16 + 16 * nSub + 32 > fileBytes) return MB_EFORMAT;
+    len.resize(nSub);
+    if (!fetch(at + 16 + 8 * nSub, len.data(), 8 * nSub) || !fetch(at + 16 + 16 * nSub + 24, &nBlock, 8)) return MB_EFORMAT;
+    u64 words = 0;
+    for (u64 l : len) words += (l + 63) >> 6;
+    if (nBlock == 0 || nBlock > left) return MB_EFORMAT;
+    ub.byteOff = at;  ub.outIdx = nk;  tab.push_back(ub);
+    nk += nBlock;  left -= nBlock;
+    at += 16 + 16 * nSub + 8 * words;
+  }
+  return MB_OK;
+}
+
 struct FileJob {                                            //  one input data file of the group
   u32 input = 0, file = 0;
   int fd = -1;
@@ -936,7 +972,7 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
     MB_UCUDA(cudaMemGetInfo(&freeB, &totalB));
     auto groupNeed = [&](u32 f0, u32 f1) -> size_t {
       size_t need = (size_t)16 << 20;
-      for (u32 f = f0; f < f1; f++) need += db.fileBytes[f] + 256 + db.index[f].size() / 24 * sizeof(UnionBlock) + db.fileKmers[f] * (W + 4) + 1024;
+      for (u32 f = f0; f < f1; f++) need += db.fileBytes[f] + 256 + (db.index[f].size() / 24 + db.fileKmers[f] / streamBlockMax()) * sizeof(UnionBlock) + db.fileKmers[f] * (W + 4) + 1024;
       return need;
     };
     size_t want = workspaceBytes ? (size_t)workspaceBytes : std::min(freeB > ((size_t)3 << 30) ? freeB - ((size_t)2 << 30) : freeB / 2,
@@ -992,9 +1028,12 @@ static int decodeDbInGroups(const char *dbDir, int32_t device, uint64_t workspac
           memcpy(&at, ix.data() + e + 8, 8);  memcpy(&n, ix.data() + e + 16, 8);
           if (n == 0) continue;
           if (at >= db.fileBytes[f]) { rc = mb_fail(MB_EFORMAT, "'%s': block index of data file %u points past the end of the file", dbDir, f); goto done; }
-          UnionBlock ub;  ub.byteOff = off[f - f0] + at;  ub.outIdx = nk;
-          tab.push_back(ub);
-          nk += n;
+          const uint8_t *bytes = host.data() + off[f - f0];
+          const size_t t0 = tab.size();
+          if (blocksOfEntry([&](u64 pos, void *dst, size_t len) { memcpy(dst, bytes + pos, len); return true; }, at, n, db.fileBytes[f], nk, tab) != MB_OK) {
+            rc = mb_fail(MB_EFORMAT, "'%s': block index and block headers of data file %u disagree", dbDir, f);  goto done;
+          }
+          for (size_t t = t0; t < tab.size(); t++) tab[t].byteOff += off[f - f0];
         }
       }
       G.nKmers = nk;
@@ -1473,6 +1512,7 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
       need += nk * ((wS + 34 + 7) / 8 + 1) + nk / 64;                    //  encoded blocks (every block <= n(b+34) + headers) ...
       need += (size_t)(f1 - f0) * blocksPerFile * (E.streamMode ? 4096 : 512 + sizeof(MbBlockMeta) + 24 + 16);   //  ... headers, tables
       need += nk / MG_TILE * 16 + nk / MB_HIST_SMALL * 4 + 65536;
+      if (E.streamMode) need += (nk / streamBlockMax() + 2) * (2 * sizeof(MbSplitPart) + 256);   //  parts of over-full prefixes: table + containers
       return need;
     };
 
@@ -1537,23 +1577,28 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
         for (u32 f = f0; f < f1; f++) {
           FileJob j;  j.input = i;  j.file = f;  j.off = inBytes[i];  j.bytes = (size_t)in[i].fileBytes[f];
           inBytes[i] += (j.bytes + 7) / 8 * 8;
-          const std::vector<uint8_t> &ix = in[i].indexOf(f);
-          for (size_t e = 0; e + 24 <= ix.size(); e += 24) {
-            u64 at, nkB;
-            memcpy(&at, ix.data() + e + 8, 8);  memcpy(&nkB, ix.data() + e + 16, 8);
-            if (nkB == 0) continue;                         //  an empty block (block writer) or an absent one (stream writer)
-            if (at >= j.bytes) { rc = mb_fail(MB_EFORMAT, "'%s': block index of data file %u points past the end of the file", in[i].dir.c_str(), f); goto done; }
-            UnionBlock ub;  ub.byteOff = at;  ub.outIdx = j.nk;
-            j.tab.push_back(ub);
-            j.nk += nkB;
-          }
           if (!in[i].mem && j.bytes) {
             char path[4096];
             mb_file_name(path, sizeof(path), in[i].dir.c_str(), f, false);
             j.fd = open(path, O_RDONLY);
             if (j.fd < 0) { rc = mb_fail(MB_EIO, "cannot open '%s': %s", path, strerror(errno)); jobs.push_back(std::move(j)); goto done; }
           }
+          const std::vector<uint8_t> &ix = in[i].indexOf(f);
+          const uint8_t *memBytes = in[i].mem ? in[i].mem->dataPtr[f] : nullptr;
+          const int fd = j.fd;
+          for (size_t e = 0; e + 24 <= ix.size() && rc == MB_OK; e += 24) {
+            u64 at, nkB;
+            memcpy(&at, ix.data() + e + 8, 8);  memcpy(&nkB, ix.data() + e + 16, 8);
+            if (nkB == 0) continue;                         //  an empty block (block writer) or an absent one (stream writer)
+            if (at >= j.bytes) rc = mb_fail(MB_EFORMAT, "'%s': block index of data file %u points past the end of the file", in[i].dir.c_str(), f);
+            else if (blocksOfEntry([&](u64 pos, void *dst, size_t len) {
+                       if (memBytes) { memcpy(dst, memBytes + pos, len); return true; }
+                       return pread(fd, dst, len, (off_t)pos) == (ssize_t)len;
+                     }, at, nkB, j.bytes, j.nk, j.tab) != MB_OK)
+              rc = mb_fail(MB_EFORMAT, "'%s': block index and block headers of data file %u disagree", in[i].dir.c_str(), f);
+          }
           jobs.push_back(std::move(j));
+          if (rc != MB_OK) goto done;
         }
 
       std::vector<std::vector<UnionBlock>> tabs(nInputs);    //  alive until the stream has consumed them
@@ -1699,6 +1744,11 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
       MbEncodeParams ep;
       ep.keys = curK;  ep.runStart = nullptr;  ep.nDistinct = D;  ep.keyWords = kw;  ep.k = k;  ep.wPrefix = wP;
       ep.blockLo = (u64)f0 * blocksPerFile;  ep.nBlocks = nBlocks;  ep.counts = curV;  ep.streamMode = E.streamMode;
+      if (E.streamMode) {                                      //  prefixes of more than 16 Mi k-mers are written as several blocks
+        ep.streamBlockMax = streamBlockMax();
+        ep.parts = (MbSplitPart *)g.take((2 * (D / ep.streamBlockMax) + 4) * sizeof(MbSplitPart));
+        if (!ep.parts) { rc = mb_fail(MB_ENOMEM, "internal: union encode tables do not fit"); goto done; }
+      }
       MB_UCUDA(cudaMemsetAsync(dCtl, 0, 8 * 8, s));
       MB_UCUDA(mb_launch_encode_layout(ep, dMeta, dCtl, dScanTmp, s));
       u64 encTotals[8];
@@ -1708,7 +1758,6 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
         MB_UCUDA(cudaMemcpyAsync(&meta[f - f0], dMeta + (u64)(f - f0) * blocksPerFile, sizeof(MbBlockMeta), cudaMemcpyDeviceToHost, s));
       MB_UCUDA(cudaStreamSynchronize(s));
       st.nLaunches += 6;
-      if (encTotals[4]) { rc = mb_fail(MB_ENOMEM, "a 12-bit prefix holds more than 16 Mi k-mers; splitting such blocks (kmers-writer-stream.C:131-141) is not implemented"); goto done; }
 
       uint8_t *dOut = (uint8_t *)g.take(encTotals[0] + 16);
       u32     *dSub = (u32 *)g.take(encTotals[1] * 4 + 16);

@@ -64,6 +64,16 @@ def test_sim_union_long_blocks(tmp_path, monkeypatch, k, decoder):
     uc.case_long_blocks(str(tmp_path), monkeypatch, k, decoder)
 
 
+@pytest.mark.parametrize("k,limit", [(21, 30), (40, 33), (32, 50)])
+def test_sim_stream_block_split(tmp_path, monkeypatch, k, limit):
+    uc.case_stream_block_split(str(tmp_path), monkeypatch, k, limit)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
+def test_sim_stream_block_real_limit_vs_reference(tmp_path):
+    uc.case_stream_block_real_limit(tmp_path)
+
+
 @pytest.mark.skipif(not util.have_ref(), reason="reference binary not built")
 def test_sim_threshold_words_vs_reference(tmp_path):
     uc.case_threshold_words(str(tmp_path))

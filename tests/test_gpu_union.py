@@ -86,6 +86,11 @@ def test_union_small_ring(tmp_path, monkeypatch):
     uc.case_small_ring(str(tmp_path), monkeypatch)
 
 
+@pytest.mark.parametrize("k,limit", [(21, 30), (40, 33), (32, 50)])
+def test_stream_block_split(tmp_path, monkeypatch, k, limit):
+    uc.case_stream_block_split(str(tmp_path), monkeypatch, k, limit)
+
+
 @pytest.mark.parametrize("k,decoder", [(21, "warp"), (21, "thread"), (51, "warp"), (64, "thread"), (32, "warp"), (31, "auto")])
 def test_union_long_blocks(tmp_path, monkeypatch, k, decoder):
     if decoder != "thread" and not os.environ.get("MB_TEST_EXPERIMENTAL"):

@@ -422,3 +422,81 @@ def case_cli_lookup(tmp, k, n=6_000, env=None):
         assert pr.returncode == pd.returncode == 1
         sentences = [l for l in pr.stderr.splitlines() if l.startswith(("No ", "Only ", "Unknown ", "Labels "))]
         assert sentences and all(l in pd.stderr for l in sentences), (words, pr.stderr[-300:], pd.stderr)
+
+
+def case_stream_block_split(tmp, monkeypatch, k, limit):
+    """A prefix with more k-mers than the stream writer keeps in a block (16 Mi in the reference,
+    kmers-writer-stream.C:127-141) is written as consecutive blocks of the same prefix under one index entry.  The limit
+    is lowered on both sides (MB_STREAM_BLOCK_MAX / ORA_STREAM_BATCH_MAX) so that most of the 4096 prefixes are cut in
+    two to five parts, one of them into parts of exactly the limit; tests/test_gpu_zzzz_stream_split.py holds the real limit
+    against the reference binary.  Written (encoder) and read back (block tables from the container headers): as the input
+    of another operation, by the database walk, by the exact lookup."""
+    import numpy as np
+    monkeypatch.setenv("MB_STREAM_BLOCK_MAX", str(limit))
+    monkeypatch.setenv("ORA_STREAM_BATCH_MAX", str(limit))
+    def index_of(db):
+        return np.concatenate([np.fromfile(os.path.join(db, n), dtype=np.uint64) for n in sorted(os.listdir(db)) if n.endswith(".merylIndex")]).reshape(-1, 3)
+    fa, fb = synth.fasta_bytes(2, 150_000, 40 + k), synth.fasta_bytes(1, 150_000, 41 + k) + synth.fasta_bytes(1, 150_000, 40 + k)
+    b = oracle_db(tmp, "b", fb, k, op="count-forward")
+    # one prefix (GATTAC = 0xca1) is filled up to a multiple of the limit: its last part is a full one
+    _, u0 = check_union(tmp, [oracle_db(tmp, "a0", fa, k, op="count-forward"), b], "before")
+    ix = index_of(u0)
+    n0 = int(ix[ix[:, 0] == 0xca1, 2].sum())
+    fill = (n0 // limit + 2) * limit - n0
+    tails = np.random.default_rng(limit + k).choice(4 ** 9, size=fill, replace=False)
+    extra = b"".join(b">e\n" + b"GATTAC" + bytes(b"ACGT"[(int(t) >> (2 * j)) & 3] for j in range(9)) + b"C" * (k - 15) + b"\n" for t in tails)
+    a = oracle_db(tmp, "a", fa + extra, k, op="count-forward")
+    st, u = check_union(tmp, [a, b], "split")
+    assert st.nOutputKmers > 4096 * limit                  # the average prefix is over the limit
+    ix = index_of(u)
+    assert (ix[:, 2] > limit).sum() > 1000 and (ix[:, 2] > 3 * limit).any()
+    assert int(ix[ix[:, 0] == 0xca1, 2][0]) == n0 + fill and (n0 + fill) % limit == 0
+    _, u2 = check_union(tmp, [u, a], "again")              # split blocks as input (+ written again)
+    check_union(tmp, [u2, u, b], "three", op="intersect-sum")
+    lo, hi, val = mb.all_kmers(u)
+    assert lo.size == st.nOutputKmers and int(val.sum(dtype=np.uint64)) == st.nTotal
+    key = lo if hi is None else hi.astype(object) * (1 << 64) + lo.astype(object)
+    assert all(key[i] < key[i + 1] for i in range(0, key.size - 1, max(1, key.size // 5000)))
+    pick = np.arange(0, lo.size, max(1, lo.size // 3000))
+    got = mb.lookup(u, lo[pick], None if hi is None else hi[pick])
+    assert (got == val[pick]).all()
+
+
+def case_stream_block_real_limit(tmp_path):
+    """16 Mi + 300 000 distinct 19-mers that share their first six bases (one 12-bit prefix of a set operation's output) are
+    written as a block of 16 Mi k-mers followed by a block of 300 000 under one index entry (merylStreamWriter::addMer,
+    kmers-writer-stream.C:127-141; merylFileIndex::set, kmers-files.H:116-128) -- byte for byte what the reference binary
+    writes -- and such a database is read back."""
+    import numpy as np
+    k, n = 19, (16 << 20) + 300_000
+    rec = np.empty((n, 23), dtype=np.uint8)
+    rec[:, :3] = np.frombuffer(b">s\n", dtype=np.uint8)
+    rec[:, 3:9] = np.frombuffer(b"GATTAC", dtype=np.uint8)
+    i = np.arange(n, dtype=np.uint32)
+    for j in range(13):                                     # the tail spells the record's number: all k-mers distinct
+        rec[:, 9 + j] = np.frombuffer(b"ACTG", dtype=np.uint8)[(i >> (2 * (12 - j))) & 3]      # meryl: A 0, C 1, T 2, G 3
+    rec[:, 22] = ord("\n")
+    fa = str(tmp_path / "one_prefix.fa")
+    with open(fa, "wb") as fh:
+        fh.write(b">other\nTTGACCATGGCATTACGGATCAGGCATTTAGC\n")
+        rec.tofile(fh)
+    del rec
+    a, ref = str(tmp_path / "a.meryl"), str(tmp_path / "ref.meryl")
+    util.run_ref(["k=%d" % k, "memory=8", "threads=4", "count-forward", fa, "output", a], timeout=1800)
+    util.run_ref(["union-sum", a, "output", ref], timeout=1800)
+    ix = np.fromfile(os.path.join(ref, "0x110010.merylIndex"), dtype=np.uint64).reshape(-1, 3)     # GATTAC = 110010 100001
+    assert ix[0b100001, 2] == n                             # one index entry for the whole prefix
+
+    ora = str(tmp_path / "ora.meryl")
+    util.run_oracle(["union-sum", ref, "output", ora])      # the oracle's restatement of the limit, read and written
+    util.assert_same_db(ref, ora)
+
+    out = str(tmp_path / "dev.meryl")
+    st = mb.union_sum([a], out)                             # written: two blocks of one prefix
+    assert st.nOutputKmers == n + 14
+    util.assert_same_db(ref, out)
+    again = str(tmp_path / "dev2.meryl")
+    mb.union_sum([ref], again)                              # read: block places from the container headers
+    util.assert_same_db(ref, again)
+    lo = np.array([0b110010100001 << 26, (0b110010100001 << 26) + n - 1, (0b110010100001 << 26) + n], dtype=np.uint64)
+    assert mb.lookup(ref, lo).tolist() == [1, 1, 0]
