@@ -762,13 +762,13 @@ static int runCount(mb_ctx *c) {
   std::vector<u64> fileTotal(64, 0);
   for (u32 r = 0; r < world; r++) for (u32 f = 0; f < 64; f++) fileTotal[f] += C[(size_t)r * 64 + f];
 
-  //  Experimental (MB_MULTI_SUFFIX32=1, not the default until it has run on real GPUs): on several GPUs, too, a k-mer
-  //  travels and is sorted as the 32 bits below its prefix bin when they fit a word (k <= 21).  Routing is then by bin,
+  //  On several GPUs, too, a k-mer travels and is sorted as the 32 bits below its prefix bin when they fit a word
+  //  (k <= 21; MB_MULTI_SUFFIX32=0 turns it off: measured at 2 and 8 B200s).  Routing is then by bin,
   //  so everybody also learns everybody's per-bin counts.
   auto envOff = [](const char *name) { const char *e = getenv(name); return e && e[0] == '0'; };
   const bool want32 = world > 1 && !envOff("MB_MULTI_SUFFIX32") && 2 * k - binBits <= 32 && !c->stopAfterSort;
 
-  //  Experimental (MB_P2P_SCATTER=1, not the default until it has run on real GPUs): extraction fused with the exchange.
+  //  Extraction fused with the exchange (the default since it ran on 2 and 8 B200s; MB_P2P_SCATTER=0: NCCL all-to-all).
   //  Every rank maps every other rank's arena (CUDA IPC) and the extraction kernel stores a kept k-mer straight into the
   //  receive segment of the GPU that owns its file -- the bin's "start" handed to the kernel is the peer address expressed
   //  as an index relative to the local key buffer, so the kernel itself does not change.  The k-mers cross NVLink tile by

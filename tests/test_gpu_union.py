@@ -93,8 +93,6 @@ def test_stream_block_split(tmp_path, monkeypatch, k, limit):
 
 @pytest.mark.parametrize("k,decoder", [(21, "warp"), (21, "thread"), (51, "warp"), (64, "thread"), (32, "warp"), (31, "auto")])
 def test_union_long_blocks(tmp_path, monkeypatch, k, decoder):
-    if decoder != "thread" and not os.environ.get("MB_TEST_EXPERIMENTAL"):
-        pytest.skip("decode_warp_kernel has not run on a GPU yet: MB_TEST_EXPERIMENTAL=1")
     uc.case_long_blocks(str(tmp_path), monkeypatch, k, decoder)
 
 
