@@ -239,7 +239,10 @@ static int ensureArena(mb_ctx *c) {
   if (want > freeB) want = freeB;
   want = want / kAlign * kAlign;
   if (!c->arena) {
-    if (want < ((size_t)256 << 20)) return mb_fail(MB_ENOMEM, "only %zu bytes of device memory free", freeB);
+    if (want < ((size_t)256 << 20))
+      return c->cfg.workspaceBytes && c->cfg.workspaceBytes <= freeB
+               ? mb_fail(MB_EINVAL, "workspaceBytes = %llu: the device arena needs at least 256 MB", (unsigned long long)c->cfg.workspaceBytes)
+               : mb_fail(MB_ENOMEM, "only %zu bytes of device memory free", freeB);
     if (cudaMalloc((void **)&c->arena, want) != cudaSuccess) {
       cudaGetLastError();
       c->arena = nullptr;

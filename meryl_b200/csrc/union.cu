@@ -1475,7 +1475,9 @@ int mb_merge_pipeline(uint32_t op, uint64_t param, const char *const *inDirs, ui
   }
   const u32 k = in[0].k, kw = k <= 32 ? 1 : 2, W = 8 * kw;
   const u32 wP = E.outPrefix, wS = 2 * k - wP;
-  if (2 * k < wP + 1) return mb_fail(MB_EINVAL, "set operations need k >= 7 (the stream writer's 12-bit prefix)");
+  //  (no suffix bits at all is fine: k = 6 under the stream writer's 12-bit prefix -- the reference binary writes such
+  //   databases, and fails an assertion for k = 5 --, k = 3 in a merge of count batches, which keeps the count's geometry)
+  if (2 * k < wP) return mb_fail(MB_EINVAL, "set operations need k >= 6 (the stream writer's 12-bit prefix)");
   const u64 blocksPerFile = (u64)1 << (wP - 6);
 
   mb_union_stats st;

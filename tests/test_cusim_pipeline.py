@@ -192,7 +192,8 @@ def test_sim_parallel_parse_in_the_pipeline(tmp_path, monkeypatch):
 
 # ---- count batches (W6: merylBlockWriter::finishBatch / mergeBatches, kmers-writer-block.C:172-386) --------------------
 
-@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 10, "count", 190_000), (51, 8, "count-forward", 150_000), (8, 6, "count-reverse", 100_000)])
+@pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 10, "count", 190_000), (51, 8, "count-forward", 150_000), (8, 6, "count-reverse", 100_000),
+                                                       (3, 6, "count", 100_000)])          # (k = 3: prefix 6 is the whole k-mer)
 def test_sim_count_batches(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
     """Reads that outgrow the device are counted in batches cut at record breaks; the batches' blocks are decoded, merged
     (saturating sums) and encoded again with the block writer's rules.  MB_MAX_BATCH_BASES makes a small input take that

@@ -29,7 +29,7 @@ def test_sim_union_golden(tmp_path, name):
     uc.case_golden(str(tmp_path), name)
 
 
-@pytest.mark.parametrize("k", [7, 8, 21, 31, 32, 33, 51, 64])
+@pytest.mark.parametrize("k", [6, 7, 8, 21, 31, 32, 33, 51, 64])       # (k = 6: the stream writer's 12-bit prefix is the whole k-mer)
 def test_sim_union_k_sweep(tmp_path, k):
     uc.case_k_sweep(str(tmp_path), k, n=8_000)
 

@@ -19,7 +19,7 @@ def test_union_golden(tmp_path, name):
     uc.case_golden(str(tmp_path), name)
 
 
-@pytest.mark.parametrize("k", [7, 8, 15, 21, 31, 32, 33, 51, 64])
+@pytest.mark.parametrize("k", [6, 7, 8, 15, 21, 31, 32, 33, 51, 64])
 def test_union_k_sweep(tmp_path, k):
     uc.case_k_sweep(str(tmp_path), k, n=60_000)
 

@@ -34,7 +34,7 @@ def test_c1_shape_small(tmp_path):
     _both(tmp_path, {"a.fa": synth.fasta_bytes(4, 100_000, 42)}, 21)
 
 
-@pytest.mark.parametrize("k", [6, 15, 16, 21, 22, 31, 32, 33, 51, 64])
+@pytest.mark.parametrize("k", [3, 4, 6, 15, 16, 21, 22, 31, 32, 33, 51, 64])       # (k = 3: simple mode with prefix 6 and no suffix bits)
 def test_k_sweep(tmp_path, k):
     _both(tmp_path, {"a.fa": synth.fasta_bytes(2, 30_000, 100 + k)}, k)
 

@@ -30,7 +30,7 @@ needs_ref = pytest.mark.skipif(not util.have_ref(), reason="reference binary ora
 
 
 @needs_ref
-@pytest.mark.parametrize("k", [8, 21, 33, 64])
+@pytest.mark.parametrize("k", [6, 8, 21, 33, 64])        # (k = 6: no suffix bits under the 12-bit prefix; the reference asserts for k = 5)
 def test_oracle_union_sum_vs_reference(tmp_path, k):
     a = _count_ref(tmp_path, "a", synth.fasta_bytes(2, 40_000, 10 + k), k)
     b = _count_ref(tmp_path, "b", synth.fasta_bytes(1, 40_000, 10 + k) + synth.fasta_bytes(2, 30_000, 99 + k), k)

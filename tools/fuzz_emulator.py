@@ -1,0 +1,247 @@
+#!/usr/bin/env python
+"""Randomised soak of the count path (and, with --what union, of chains of set / value operations) in the emulator (tests/cusim) against the C oracle: random k, operation, prefix width,
+inputs with every oddity of the parser's grammar, and random settings of the testing knobs (passes, groups, batches, sweep
+shape, dense extraction, key width).  Every case must give the oracle's 129 files byte for byte.  TEST INFRASTRUCTURE -- it
+proves logic in a container without a GPU; `MB_TEST_LIB=... pytest -m gpu` and this script are the two checks used for
+host-side changes made when no GPU minutes are left.
+
+    python tools/fuzz_emulator.py --seconds 600 --jobs 6 [--seed 1]
+
+A failing case is kept under --keep (inputs, both databases, the environment) and reported; exit code 1."""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+SIM_DIR = os.path.join(ROOT, "tests", "cusim")
+SIM_LIB = os.path.join(SIM_DIR, "_build", "libmeryl_b200_sim.so")
+KNOBS = ("MB_MAX_PASS_KEYS", "MB_GROUP_KEYS", "MB_DENSE_ITEMS", "MB_SORT", "MB_MAX_BATCH_BASES", "MB_EXTRACT_DENSE", "MB_SORT_PINGPONG",
+         "MB_COUNT_GROUP", "MB_HIST_SINGLE", "MB_NO_SUFFIX32", "MB_NO_PREFILTER", "MB_PARSE_MIN_PIECE", "MB_PARSE_THREADS")
+
+
+def make_input(rng, k):
+    """One sequence file: FASTA or FASTQ with the oddities bufSeqFile::loadBases accepts."""
+    import numpy as np
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    eol = b"\r\n" if rng.random() < 0.15 else b"\n"
+    fastq = rng.random() < 0.5
+    out = []
+    nrec = int(rng.integers(1, 40))
+    scale = int(rng.choice([30, 200, 2000, 20000]))
+    genome = acgt[rng.integers(0, 4, size=scale * 4 + 200, dtype=np.uint8)]
+    for r in range(nrec):
+        n = int(rng.integers(0, scale))
+        if rng.random() < 0.1:
+            n = int(rng.integers(max(0, k - 2), k + 3))                 # around k: zero, one, two k-mers
+        at = int(rng.integers(0, genome.size - n)) if rng.random() < 0.7 else 0      # repeats between the records: counts > 1
+        s = genome[at: at + n].copy()
+        if rng.random() < 0.3 and n:
+            s[rng.random(n) < 0.02] = ord("N")
+        if rng.random() < 0.2 and n:
+            low = rng.random(n) < 0.3
+            s[low] = s[low] | 0x20
+        if rng.random() < 0.1 and n > 40:
+            p = int(rng.integers(0, n - 30))
+            s[p: p + 30] = s[p]                                          # a homopolymer run
+        s = s.tobytes()
+        if fastq:
+            out += [b"@r%d some text" % r + eol, s + eol, b"+" + (b"r%d" % r if rng.random() < 0.3 else b"") + eol,
+                    (b"@" if rng.random() < 0.2 else b"I") + b"I" * max(0, n - 1) + eol]
+        else:
+            out.append(b">s%d" % r + eol)
+            w = int(rng.choice([60, 80, 7, 100000]))
+            for p in range(0, n, w):
+                out.append(s[p: p + w] + eol)
+            if rng.random() < 0.1:
+                out.append(eol)
+    if rng.random() < 0.1 and out:
+        out[-1] = out[-1].rstrip(b"\r\n")                                # no end of line at the end of the file
+    return b"".join(out), (".fq" if fastq else ".fa")
+
+
+def one_case(seed, keep):
+    import numpy as np
+    import util
+    import meryl_b200 as mb
+    mb.LIB_PATH, mb._lib = SIM_LIB, None
+    rng = np.random.default_rng(seed)
+    k = int(rng.choice([3, 4, 8, 11, 15, 16, 17, 19, 20, 21, 22, 23, 27, 31, 32, 33, 40, 48, 51, 63, 64]))
+    op = str(rng.choice(["count", "count", "count-forward", "count-reverse"]))
+    # 64 files: at least six prefix bits; the reference's planner stops at 2k - 2 (merylOp-count.C:197), its simple mode
+    # uses 6 for k <= 13 (k = 3: no suffix bits at all)
+    wp = int(rng.integers(6, max(6, min(2 * k - 2, 17)) + 1))
+    env = {}
+    if rng.random() < 0.5: env["MB_MAX_PASS_KEYS"] = str(int(rng.choice([4096, 20000, 100000, 1000000])))
+    if rng.random() < 0.4: env["MB_GROUP_KEYS"] = str(int(rng.choice([4096, 8192, 65536])))
+    if rng.random() < 0.4: env["MB_DENSE_ITEMS"] = str(int(rng.choice([8, 12, 16, 24])))
+    if rng.random() < 0.3: env["MB_SORT"] = "2"
+    if rng.random() < 0.25: env["MB_MAX_BATCH_BASES"] = str(int(rng.choice([300, 5000, 60000])))
+    if rng.random() < 0.15: env["MB_EXTRACT_DENSE"] = "0"
+    if rng.random() < 0.2: env["MB_SORT_PINGPONG"] = "1"
+    if rng.random() < 0.15: env["MB_COUNT_GROUP"] = "1"
+    if rng.random() < 0.15: env["MB_HIST_SINGLE"] = "1"
+    if rng.random() < 0.15: env["MB_NO_SUFFIX32"] = "1"
+    if rng.random() < 0.1: env["MB_NO_PREFILTER"] = "1"
+    if rng.random() < 0.3: env["MB_PARSE_MIN_PIECE"] = str(int(rng.choice([64, 1000])))
+    for name in KNOBS:
+        os.environ.pop(name, None)
+    os.environ.update(env)
+    tmp = tempfile.mkdtemp(prefix="mbfuzz_")
+    what = {"seed": seed, "k": k, "op": op, "wprefix": wp, "env": env}
+    try:
+        paths = []
+        for i in range(int(rng.integers(1, 4))):
+            data, ext = make_input(rng, k)
+            p = os.path.join(tmp, "in%d%s" % (i, ext))
+            with open(p, "wb") as fh:
+                fh.write(data)
+            paths.append(p)
+        what["bytes"] = sum(os.path.getsize(p) for p in paths)
+        ora, out = os.path.join(tmp, "ora.meryl"), os.path.join(tmp, "sim.meryl")
+        o = subprocess.run([util.ORACLE_BIN, "k=%d" % k, "wprefix=%d" % wp, op, *paths, "output", ora], capture_output=True, text=True)
+        if o.returncode != 0:                    # (an input the reference rejects, a prefix width it cannot have)
+            what["skipped"] = o.stderr[-200:]
+            return what
+        try:
+            with mb.Counter(k, wp, op, workspace_bytes=int(rng.choice([0, 0, 1 << 28]))) as c:
+                for p in paths:
+                    c.add_file(p)
+                c.count()
+                st = c.stats()
+                c.write_db(out)
+            what["kmers"], what["passes"], what["batches"] = int(st.nKmers), int(st.nPasses), int(st.nBatches)
+            util.assert_same_db(ora, out)
+        except Exception as ex:
+            if isinstance(ex, mb.MerylB200Error) and ex.code == -3 and "MB_MAX_PASS_KEYS" in env:
+                what["skipped"] = "one prefix bin holds more k-mers than the pass limit drawn for this case"
+                return what
+            what["failed"] = repr(ex)[:500]
+            if keep:
+                os.makedirs(keep, exist_ok=True)
+                dst = os.path.join(keep, "case_%d" % seed)
+                shutil.rmtree(dst, ignore_errors=True)
+                shutil.copytree(tmp, dst)
+                with open(os.path.join(dst, "case.json"), "w") as fh:
+                    json.dump(what, fh)
+        return what
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+SET_OPS = ["union", "union-min", "union-max", "union-sum", "intersect", "intersect-min", "intersect-max", "intersect-sum",
+           "subtract", "difference", "symmetric-difference"]
+VALUE_OPS = [("less-than", 3), ("greater-than", 1), ("at-least", 2), ("at-most", 1), ("equal-to", 2), ("not-equal-to", 1),
+             ("increase", 5), ("decrease", 1), ("multiply", 3), ("divide", 2), ("divide-round", 2), ("modulo", 2)]
+UNION_KNOBS = ("MB_UNION_MAX_FILES", "MB_RING_BYTES", "MB_STREAM_BLOCK_MAX", "ORA_STREAM_BATCH_MAX", "MB_DECODE")
+
+
+def one_union_case(seed, keep):
+    """A short chain of set / value operations on count databases (and on its own outputs) against the oracle's."""
+    import numpy as np
+    import util
+    import meryl_b200 as mb
+    mb.LIB_PATH, mb._lib = SIM_LIB, None
+    rng = np.random.default_rng(seed)
+    k = int(rng.choice([6, 8, 12, 16, 19, 21, 22, 31, 32, 33, 40, 51, 64]))
+    env = {}
+    if rng.random() < 0.4: env["MB_UNION_MAX_FILES"] = str(int(rng.choice([1, 3, 7, 20])))
+    if rng.random() < 0.3: env["MB_RING_BYTES"] = str(int(rng.choice([4096, 65536])))
+    if rng.random() < 0.4:
+        env["MB_STREAM_BLOCK_MAX"] = env["ORA_STREAM_BATCH_MAX"] = str(int(rng.choice([1, 2, 7, 64, 500])))
+    if rng.random() < 0.5: env["MB_DECODE"] = str(rng.choice(["warp", "auto", "thread"]))
+    for name in KNOBS + UNION_KNOBS:
+        os.environ.pop(name, None)
+    os.environ.update(env)
+    tmp = tempfile.mkdtemp(prefix="mbfuzz_")
+    what = {"seed": seed, "k": k, "env": env, "steps": []}
+    try:
+        dbs = []
+        shared, _ = make_input(rng, k)
+        for i in range(int(rng.integers(1, 4))):
+            data, ext = make_input(rng, k)
+            p = os.path.join(tmp, "in%d%s" % (i, ext))
+            with open(p, "wb") as fh:
+                fh.write(data + (b"\n" + shared if rng.random() < 0.6 and ext == ".fa" and shared[:1] == b">" else b""))
+            db = os.path.join(tmp, "c%d.meryl" % i)
+            o = subprocess.run([util.ORACLE_BIN, "k=%d" % k, "memory=1", str(rng.choice(["count", "count-forward"])), p, "output", db],
+                               capture_output=True, text=True)
+            if o.returncode != 0:
+                what["skipped"] = o.stderr[-200:]
+                return what
+            dbs.append(db)
+        try:
+            for step in range(int(rng.integers(1, 4))):
+                ora, out = os.path.join(tmp, "o%d.meryl" % step), os.path.join(tmp, "d%d.meryl" % step)
+                if rng.random() < 0.7:
+                    op = str(rng.choice(SET_OPS))
+                    ins = [dbs[int(j)] for j in rng.integers(0, len(dbs), size=int(rng.integers(1, 4)))]
+                    what["steps"].append([op, [os.path.basename(x) for x in ins]])
+                    util.run_oracle([op, *ins, "output", ora])
+                    st = mb.set_operation(op, ins, out)
+                else:
+                    op, param = VALUE_OPS[int(rng.integers(0, len(VALUE_OPS)))]
+                    inp = dbs[int(rng.integers(0, len(dbs)))]
+                    what["steps"].append([op, param, os.path.basename(inp)])
+                    util.run_oracle([op, str(param), inp, "output", ora])
+                    st = mb.value_operation(op, param, inp, out)
+                util.assert_same_db(ora, out)
+                what["kmers"] = what.get("kmers", 0) + int(st.nInputKmers)
+                dbs.append(out)                             # a later step may read this step's output (stream-written blocks)
+        except Exception as ex:
+            what["failed"] = repr(ex)[:500]
+            if keep:
+                os.makedirs(keep, exist_ok=True)
+                dst = os.path.join(keep, "union_case_%d" % seed)
+                shutil.rmtree(dst, ignore_errors=True)
+                shutil.copytree(tmp, dst)
+                with open(os.path.join(dst, "case.json"), "w") as fh:
+                    json.dump(what, fh)
+        return what
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def worker(args):
+    first, step, seconds, keep, what = args
+    t0, seed, res = time.time(), first, []
+    while time.time() - t0 < seconds:
+        res.append(one_union_case(seed, keep) if what == "union" else one_case(seed, keep))
+        seed += step
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=300)
+    ap.add_argument("--jobs", type=int, default=4)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--what", default="count", choices=["count", "union"])
+    ap.add_argument("--keep", default=os.path.join(tempfile.gettempdir(), "mbfuzz_failures"))
+    a = ap.parse_args()
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    subprocess.run(["make", "-s", "-j8", "-C", SIM_DIR], check=True)
+    with mp.get_context("spawn").Pool(a.jobs) as pool:
+        parts = pool.map(worker, [(a.seed + j, a.jobs, a.seconds, a.keep, a.what) for j in range(a.jobs)])
+    res = [r for p in parts for r in p]
+    bad = [r for r in res if "failed" in r]
+    ran = [r for r in res if "failed" not in r and "skipped" not in r]
+    print(json.dumps({"cases": len(res), "compared": len(ran), "skipped": len(res) - len(ran) - len(bad), "failed": len(bad),
+                      "kmers": sum(r.get("kmers", 0) for r in ran), "multi_pass": sum(1 for r in ran if r.get("passes", 0) > 1),
+                      "multi_batch": sum(1 for r in ran if r.get("batches", 0) > 1)}))
+    for r in bad:
+        print(json.dumps(r))
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
