@@ -954,7 +954,7 @@ static int runCount(mb_ctx *c) {
         enc32   = (size_t)std::min<u64>(enc32, all[(size_t)r * 3 + 2]);
       }
     }
-    const u32 slots = 64 / world;
+    const u32 slots = (64 + world - 1) / world;          //  (the last slot is short when the world size does not divide 64)
     //  Greedy: a pass takes consecutive slots while every rank still fits what it sends and what it receives.  (Canonical
     //  k-mers are skewed towards the low files, so the passes get longer towards the end.)  Every rank knows the whole count
     //  matrix and the agreed capacities, so every rank cuts at the same slots.
@@ -963,7 +963,7 @@ static int runCount(mb_ctx *c) {
       out.clear();
       std::vector<u64> snd(world), rcv(world);
       auto add = [&](u32 slot, std::vector<u64> &sn, std::vector<u64> &rc) {
-        for (u32 f = slot * world; f < (slot + 1) * world; f++) {
+        for (u32 f = slot * world; f < std::min(64u, (slot + 1) * world); f++) {
           for (u32 r = 0; r < world; r++) sn[r] += C[(size_t)r * 64 + f];
           rc[mb_file_owner(f, world)] += fileTotal[f];
         }
@@ -985,7 +985,7 @@ static int runCount(mb_ctx *c) {
           snd.swap(sn);  rcv.swap(rc);  p1++;
         }
         if (s32)                                            //  every owned bin must fit a count group (see the groups below)
-          for (u32 f = p0 * world; f < p1 * world; f++) {
+          for (u32 f = p0 * world; f < std::min(64u, p1 * world); f++) {
             const u32 r = mb_file_owner(f, world);
             const u64 gcap = std::min<u64>(std::max(snd[r], rcv[r]) / 2 + 8, (u64)(enc32 / 3 / 8));
             for (u32 b = f * binsPerFile; b < (f + 1) * binsPerFile; b++)
@@ -1004,7 +1004,7 @@ static int runCount(mb_ctx *c) {
     sortBits = byBin ? 2 * k - binBits : 2 * k - 6;
     for (const auto &rg : ranges) {
       Pass P;
-      const u32 fLo = rg.first * world, fHi = rg.second * world;
+      const u32 fLo = rg.first * world, fHi = std::min(64u, rg.second * world);
       P.binLo = fLo * binsPerFile;  P.binHi = fHi * binsPerFile;
       for (u32 f = fLo; f < fHi; f++) {
         P.nLocal += C[(size_t)me * 64 + f];

@@ -56,7 +56,7 @@ def multi_key_bytes():
     return [L.mb_sim_last_key_bytes(r) for r in range(multi_key_bytes.world)]
 
 
-@pytest.mark.parametrize("world,k", [(2, 21), (4, 21), (8, 31), (2, 51)])
+@pytest.mark.parametrize("world,k", [(2, 21), (4, 21), (8, 31), (2, 51), (3, 21), (5, 31), (6, 21), (7, 51)])   # (3, 5, 6, 7 do not divide 64: a short last slot)
 def test_sim_multi_rank_db_bit_exact(tmp_path, world, k):
     n_reads, rl = 6_000, 150
     data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 17 + k)
@@ -149,7 +149,7 @@ def test_sim_multi_rank_p2p_scatter(tmp_path, monkeypatch, world, k, wp, cap, s3
     assert multi_key_bytes() == [4 if s32 else (8 if k <= 32 else 16)] * world
 
 
-@pytest.mark.parametrize("world,k,wp,weights", [(2, 21, 12, None), (4, 31, 10, [1, 4, 2, 0]), (2, 51, 9, [5, 1]), (8, 21, 12, [3, 1, 1, 1, 2, 0, 1, 1])])
+@pytest.mark.parametrize("world,k,wp,weights", [(2, 21, 12, None), (4, 31, 10, [1, 4, 2, 0]), (2, 51, 9, [5, 1]), (8, 21, 12, [3, 1, 1, 1, 2, 0, 1, 1]), (3, 21, 12, [0, 2, 5])])
 def test_sim_multi_rank_count_batches(tmp_path, monkeypatch, world, k, wp, weights):
     """Count batches on several GPUs (merylOp-countThreads.C:286-380, kmers-writer-block.C:221-386): a rank whose read store
     fills closes a batch, and the count is collective, so every rank takes part in it -- the others with what they hold at

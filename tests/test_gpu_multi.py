@@ -60,7 +60,7 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("k", [21, 51])
 @pytest.mark.parametrize("route", ["default", "nccl-u64"])
 def test_multi_gpu_db_bit_exact(tmp_path, world, k, route):

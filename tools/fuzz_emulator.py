@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Randomised soak of the count path (and, with --what union, of chains of set / value operations) in the emulator (tests/cusim) against the C oracle: random k, operation, prefix width,
+"""Randomised soak of the count path (with --what union: of chains of set / value operations; with --what multi: of the collective count of 2-8 emulated ranks) in the emulator (tests/cusim) against the C oracle: random k, operation, prefix width,
 inputs with every oddity of the parser's grammar, and random settings of the testing knobs (passes, groups, batches, sweep
 shape, dense extraction, key width).  Every case must give the oracle's 129 files byte for byte.  TEST INFRASTRUCTURE -- it
 proves logic in a container without a GPU; `MB_TEST_LIB=... pytest -m gpu` and this script are the two checks used for
@@ -211,11 +211,88 @@ def one_union_case(seed, keep):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+MULTI_KNOBS = ("MB_MULTI_SUFFIX32", "MB_P2P_SCATTER")
+
+
+def one_multi_case(seed, keep):
+    """The collective count of several ranks (fibers of one emulator process, rendezvous copies for NCCL, peer stores for the
+    fused exchange) with uneven shares, batches and both routes against the single-process oracle."""
+    import ctypes
+    import numpy as np
+    import util
+    import meryl_b200 as mb
+    from meryl_b200 import synth
+    mb.LIB_PATH, mb._lib = SIM_LIB, None
+    rng = np.random.default_rng(seed)
+    world = int(rng.choice([2, 2, 3, 4, 5, 7, 8]))
+    k = int(rng.choice([8, 15, 16, 19, 21, 22, 31, 32, 33, 51, 64]))
+    mode = int(rng.integers(0, 3))
+    wp = int(rng.integers(6, max(6, min(2 * k - 2, 15)) + 1))
+    env = {}
+    if rng.random() < 0.4: env["MB_MAX_BATCH_BASES"] = str(int(rng.choice([20000, 60000, 150000])))
+    if rng.random() < 0.4: env["MB_MAX_PASS_KEYS"] = str(int(rng.choice([20000, 100000])))
+    if rng.random() < 0.3: env["MB_MULTI_SUFFIX32"] = "0"
+    if rng.random() < 0.3: env["MB_P2P_SCATTER"] = "0"
+    if rng.random() < 0.3: env["MB_GROUP_KEYS"] = str(int(rng.choice([4096, 65536])))
+    if rng.random() < 0.2: env["MB_SORT"] = "2"
+    if rng.random() < 0.2: env["MB_EXTRACT_DENSE"] = "0"
+    for name in KNOBS + UNION_KNOBS + MULTI_KNOBS:
+        os.environ.pop(name, None)
+    os.environ.update(env)
+    tmp = tempfile.mkdtemp(prefix="mbfuzz_")
+    weights = [int(x) for x in rng.integers(0, 5, size=world)]
+    if sum(weights) == 0:
+        weights[int(rng.integers(0, world))] = 1
+    what = {"seed": seed, "world": world, "k": k, "mode": mode, "wprefix": wp, "weights": weights, "env": env}
+    try:
+        rl = int(rng.choice([max(k + 1, 40), 150, 600]))
+        n_reads = int(rng.choice([300, 2000, 6000])) * 150 // rl + 1
+        data = synth.reads_fastq_bytes(int(rng.choice([3000, 30000])) + rl, n_reads, rl, float(rng.choice([0.0, 0.004])), seed)
+        fq = os.path.join(tmp, "reads.fq")
+        with open(fq, "wb") as fh:
+            fh.write(data)
+        ora, out = os.path.join(tmp, "ora.meryl"), os.path.join(tmp, "sim.meryl")
+        util.run_oracle(["k=%d" % k, "wprefix=%d" % wp, ["count", "count-forward", "count-reverse"][mode], fq, "output", ora])
+        try:
+            recs = data.split(b"@r")[1:]
+            cuts = [len(recs) * sum(weights[:r]) // sum(weights) for r in range(world + 1)]
+            parts = [b"".join(b"@r" + x for x in recs[cuts[r]:cuts[r + 1]]) for r in range(world)]
+            L = mb.lib()
+            L.mb_sim_multi_count.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p),
+                                             ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
+            arr = (ctypes.c_char_p * world)(*parts)
+            lens = (ctypes.c_uint64 * world)(*[len(p) for p in parts])
+            nk, npass = (ctypes.c_uint64 * world)(), (ctypes.c_uint32 * world)()
+            os.makedirs(out, exist_ok=True)
+            rc = L.mb_sim_multi_count(world, k, mode, wp, arr, lens, out.encode(), nk, npass)
+            if rc != 0:
+                msg = L.mb_last_error().decode()
+                if rc == -3 and "MB_MAX_PASS_KEYS" in env:
+                    what["skipped"] = msg[:200]
+                    return what
+                raise RuntimeError("rc %d: %s" % (rc, msg))
+            what["kmers"], what["passes"] = int(sum(nk)), int(max(npass))
+            what["batches"] = 2 if "MB_MAX_BATCH_BASES" in env else 1
+            util.assert_same_db(ora, out)
+        except Exception as ex:
+            what["failed"] = repr(ex)[:500]
+            if keep:
+                os.makedirs(keep, exist_ok=True)
+                dst = os.path.join(keep, "multi_case_%d" % seed)
+                shutil.rmtree(dst, ignore_errors=True)
+                shutil.copytree(tmp, dst)
+                with open(os.path.join(dst, "case.json"), "w") as fh:
+                    json.dump(what, fh)
+        return what
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def worker(args):
     first, step, seconds, keep, what = args
     t0, seed, res = time.time(), first, []
     while time.time() - t0 < seconds:
-        res.append(one_union_case(seed, keep) if what == "union" else one_case(seed, keep))
+        res.append({"union": one_union_case, "multi": one_multi_case, "count": one_case}[what](seed, keep))
         seed += step
     return res
 
@@ -225,7 +302,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--jobs", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--what", default="count", choices=["count", "union"])
+    ap.add_argument("--what", default="count", choices=["count", "union", "multi"])
     ap.add_argument("--keep", default=os.path.join(tempfile.gettempdir(), "mbfuzz_failures"))
     a = ap.parse_args()
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
