@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Randomised soak of the count path (with --what union: of chains of set / value operations; with --what multi: of the collective count of 2-8 emulated ranks) in the emulator (tests/cusim) against the C oracle: random k, operation, prefix width,
+"""Randomised soak of the count path (with --what union: of chains of set / value operations; with --what multi: of the collective count of 2-8 emulated ranks; with --what cli / lookup: of the command line tools next to the reference's binaries) in the emulator (tests/cusim) against the C oracle: random k, operation, prefix width,
 inputs with every oddity of the parser's grammar, and random settings of the testing knobs (passes, groups, batches, sweep
 shape, dense extraction, key width).  Every case must give the oracle's 129 files byte for byte.  TEST INFRASTRUCTURE -- it
 proves logic in a container without a GPU; `MB_TEST_LIB=... pytest -m gpu` and this script are the two checks used for
@@ -214,6 +214,129 @@ def one_union_case(seed, keep):
 MULTI_KNOBS = ("MB_MULTI_SUFFIX32", "MB_P2P_SCATTER")
 
 
+def one_lookup_case(seed, keep):
+    """`meryl-lookup-b200` (emulated library preloaded) next to the reference's meryl-lookup: -existence and the per-position
+    reports on query files with the parser's oddities, one or two databases, value windows; the output files byte for byte."""
+    import numpy as np
+    import util
+    import meryl_b200 as mb
+    if not util.have_ref_lookup():
+        return {"seed": seed, "skipped": "no reference meryl-lookup"}
+    rng = np.random.default_rng(seed)
+    for name in KNOBS + UNION_KNOBS + MULTI_KNOBS + ("MB_LOOKUP_BATCH", "MB_LOOKUP_NO_TABLE"):
+        os.environ.pop(name, None)
+    k = int(rng.choice([8, 13, 16, 21, 22, 31, 32, 33, 51, 64]))
+    rep = [["-existence"], ["-bed"], ["-bed-runs"], ["-wig-count"], ["-wig-depth"]][int(rng.integers(0, 5))]
+    env = dict(os.environ, LD_PRELOAD=SIM_LIB)
+    if rng.random() < 0.4: env["MB_LOOKUP_BATCH"] = str(int(rng.choice([300, 5000])))
+    if rng.random() < 0.2: env["MB_LOOKUP_NO_TABLE"] = "1"
+    if rng.random() < 0.3: env["MB_UNION_MAX_FILES"] = str(int(rng.choice([3, 20])))
+    tmp = tempfile.mkdtemp(prefix="mbfuzz_")
+    what = {"seed": seed, "k": k, "words": rep, "env": {n: env[n] for n in ("MB_LOOKUP_BATCH", "MB_LOOKUP_NO_TABLE", "MB_UNION_MAX_FILES") if n in env}}
+    try:
+        dbs, texts = [], []
+        for i in range(int(rng.integers(1, 3))):
+            data, ext = make_input(rng, k)
+            texts.append((data, ext))
+            p = os.path.join(tmp, "in%d%s" % (i, ext))
+            with open(p, "wb") as fh:
+                fh.write(data)
+            db = os.path.join(tmp, "c%d.meryl" % i)
+            o = subprocess.run([util.ORACLE_BIN, "k=%d" % k, "memory=1", str(rng.choice(["count", "count-forward"])), p, "output", db], capture_output=True, text=True)
+            if o.returncode != 0:
+                what["skipped"] = o.stderr[-200:]
+                return what
+            dbs.append(db)
+        q, ext = (make_input(rng, k) if rng.random() < 0.5 else texts[0])      # other sequences, or the database's own (every k-mer found)
+        qf = os.path.join(tmp, "query" + ext)
+        with open(qf, "wb") as fh:
+            fh.write(q)
+        words = rep + ["-sequence", qf, "-mers"] + dbs
+        if rng.random() < 0.3: words += ["-min", str(int(rng.integers(1, 4)))]
+        if rng.random() < 0.3: words += ["-max", str(int(rng.integers(3, 60)))]
+        what["words"] = [os.path.basename(w) for w in words]
+        r = subprocess.run([util.REF_LOOKUP_BIN] + words + ["-threads", "2", "-output", os.path.join(tmp, "ref.txt")], capture_output=True, text=True)
+        if r.returncode != 0:
+            what["skipped"] = "the reference fails: " + r.stderr[-150:]
+            return what
+        o = subprocess.run([mb.LOOKUP_CLI_PATH] + words + ["-output", os.path.join(tmp, "dev.txt")], capture_output=True, text=True, env=env)
+        try:
+            assert o.returncode == 0, o.stderr[-400:]
+            assert open(os.path.join(tmp, "ref.txt"), "rb").read() == open(os.path.join(tmp, "dev.txt"), "rb").read(), "outputs differ"
+            what["kmers"] = 1
+        except Exception as ex:
+            what["failed"] = repr(ex)[:600]
+            if keep:
+                os.makedirs(keep, exist_ok=True)
+                dst = os.path.join(keep, "lookup_case_%d" % seed)
+                shutil.rmtree(dst, ignore_errors=True)
+                shutil.copytree(tmp, dst)
+                with open(os.path.join(dst, "case.json"), "w") as fh:
+                    json.dump(what, fh)
+        return what
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def one_cli_case(seed, keep):
+    """`meryl-b200 <words>` (the emulated library preloaded) next to the reference binary on the same words: option words in
+    any order, memory= / n= through the planner (the prefix width decides the bytes), compress, several inputs, gz."""
+    import gzip
+    import numpy as np
+    import util
+    import meryl_b200 as mb
+    if not util.have_ref():
+        return {"seed": seed, "skipped": "no reference binary"}
+    rng = np.random.default_rng(seed)
+    for name in KNOBS + UNION_KNOBS + MULTI_KNOBS:
+        os.environ.pop(name, None)
+    k = int(rng.choice([4, 6, 8, 13, 15, 16, 17, 20, 21, 22, 25, 31, 32, 33, 51, 64]))
+    op = str(rng.choice(["count", "count", "count-forward", "count-reverse"]))
+    opts = ["k=%d" % k, "threads=%d" % int(rng.integers(1, 5))]
+    if rng.random() < 0.8: opts.append("memory=%s" % str(rng.choice(["0.5", "1", "2", "4", "8", "0.05"])))
+    if rng.random() < 0.4: opts.append("n=%d" % int(rng.choice([1000, 100000, 10000000, 5000000000])))
+    opts = [opts[int(i)] for i in rng.permutation(len(opts))]
+    tmp = tempfile.mkdtemp(prefix="mbfuzz_")
+    what = {"seed": seed, "k": k, "words": opts + [op]}
+    try:
+        ins = []
+        for i in range(int(rng.integers(1, 4))):
+            data, ext = make_input(rng, k)
+            p = os.path.join(tmp, "in%d%s" % (i, ext))
+            if rng.random() < 0.25:
+                p += ".gz"
+                data = gzip.compress(data)
+            with open(p, "wb") as fh:
+                fh.write(data)
+            if rng.random() < 0.2:
+                ins.append("compress")
+                what["words"].append("compress")
+            ins.append(p)
+        ref, out = os.path.join(tmp, "ref.meryl"), os.path.join(tmp, "cli.meryl")
+        r = subprocess.run([util.REF_BIN] + opts + [op] + ins + ["output", ref], capture_output=True, text=True)
+        o = subprocess.run([mb.CLI_PATH] + opts + [op] + ins + ["output", out], capture_output=True, text=True, env=dict(os.environ, LD_PRELOAD=SIM_LIB))
+        try:
+            if r.returncode != 0:
+                assert o.returncode != 0, "the reference fails (%s) and meryl-b200 does not" % r.stderr[-150:]
+                what["skipped"] = "both refuse"
+                return what
+            assert o.returncode == 0, o.stderr[-400:]
+            util.assert_same_db(ref, out)
+            what["kmers"] = 1
+        except Exception as ex:
+            what["failed"] = repr(ex)[:600]
+            if keep:
+                os.makedirs(keep, exist_ok=True)
+                dst = os.path.join(keep, "cli_case_%d" % seed)
+                shutil.rmtree(dst, ignore_errors=True)
+                shutil.copytree(tmp, dst)
+                with open(os.path.join(dst, "case.json"), "w") as fh:
+                    json.dump(what, fh)
+        return what
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def one_multi_case(seed, keep):
     """The collective count of several ranks (fibers of one emulator process, rendezvous copies for NCCL, peer stores for the
     fused exchange) with uneven shares, batches and both routes against the single-process oracle."""
@@ -292,7 +415,7 @@ def worker(args):
     first, step, seconds, keep, what = args
     t0, seed, res = time.time(), first, []
     while time.time() - t0 < seconds:
-        res.append({"union": one_union_case, "multi": one_multi_case, "count": one_case}[what](seed, keep))
+        res.append({"union": one_union_case, "multi": one_multi_case, "count": one_case, "cli": one_cli_case, "lookup": one_lookup_case}[what](seed, keep))
         seed += step
     return res
 
@@ -302,7 +425,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--jobs", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--what", default="count", choices=["count", "union", "multi"])
+    ap.add_argument("--what", default="count", choices=["count", "union", "multi", "cli", "lookup"])
     ap.add_argument("--keep", default=os.path.join(tempfile.gettempdir(), "mbfuzz_failures"))
     a = ap.parse_args()
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
