@@ -323,6 +323,39 @@ def one_cli_case(seed, keep):
             assert o.returncode == 0, o.stderr[-400:]
             util.assert_same_db(ref, out)
             what["kmers"] = 1
+            # a second command on the database(s): the readers and the operators' words, outputs compared with the reference's
+            sim_env = dict(os.environ, LD_PRELOAD=SIM_LIB)
+            for rnd in range(2):
+                pick = int(rng.integers(0, 7))
+                if pick <= 2:
+                    words = [["histogram", ref], ["statistics", ref], ["print", ref]][pick]
+                    a = subprocess.run([util.REF_BIN] + words, capture_output=True, text=True)
+                    b = subprocess.run([mb.CLI_PATH] + words, capture_output=True, text=True, env=sim_env)
+                    what["second"] = words[0]
+                    assert a.returncode == b.returncode == 0, b.stderr[-300:]
+                    assert (sorted(a.stdout.splitlines()) == sorted(b.stdout.splitlines())) if pick == 2 else (a.stdout == b.stdout), words[0] + " differs"
+                    continue
+                if k < 6:
+                    continue                                  # (the reference's stream writer asserts below k = 6)
+                r2, o2 = os.path.join(tmp, "ref2_%d.meryl" % rnd), os.path.join(tmp, "cli2_%d.meryl" % rnd)
+                if pick == 3:
+                    words = [str(rng.choice(SET_OPS)), ref, ref]
+                elif pick == 4:
+                    opn, par = VALUE_OPS[int(rng.integers(0, len(VALUE_OPS)))]
+                    words = [opn, str(par), ref]
+                elif pick == 5:
+                    words = [str(rng.choice(["less-than", "greater-than", "at-least", "at-most"])),
+                             str(rng.choice(["distinct=0.5", "distinct=0.9", "word-frequency=0.0001", "d=0.2", "f=0.01"])), ref]
+                else:
+                    words = ["union-sum", "[", "greater-than", "1", ref, "]", "[", "at-most", "3", ref, "]"]
+                what["second"] = words[:2]
+                a = subprocess.run([util.REF_BIN] + words + ["output", r2], capture_output=True, text=True)
+                b = subprocess.run([mb.CLI_PATH] + words + ["output", o2], capture_output=True, text=True, env=sim_env)
+                if a.returncode != 0:
+                    assert b.returncode != 0, "the reference fails (%s) and meryl-b200 does not" % a.stderr[-150:]
+                    continue
+                assert b.returncode == 0, b.stderr[-400:]
+                util.assert_same_db(r2, o2)
         except Exception as ex:
             what["failed"] = repr(ex)[:600]
             if keep:
