@@ -77,7 +77,7 @@ def test_c1_config_10mb_fasta_k21(tmp_path):
         util.assert_same_db(ref, out)
 
 
-@pytest.mark.parametrize("k", [3, 4, 6, 13, 14, 15, 16, 22, 31, 32, 33, 51, 64])
+@pytest.mark.parametrize("k", [4, 6, 13, 14, 15, 16, 22, 31, 32, 33, 51, 64])       # (k = 3: tests/test_gpu_zzzz_late.py)
 def test_k_sweep(tmp_path, k):
     _vs_oracle(tmp_path, {"a.fa": synth.fasta_bytes(2, 30_000, 100 + k)}, k)
 

@@ -60,11 +60,15 @@ def _worker(rank, world, port, fq_path, out_dir, k, wp, env=None):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("k", [21, 51])
 @pytest.mark.parametrize("route", ["default", "nccl-u64"])
 def test_multi_gpu_db_bit_exact(tmp_path, world, k, route):
     """default: peer scatter (+ u32 suffix keys for k <= 21); nccl-u64: both switched off -- round 1's all-to-all of full keys."""
+    _db_bit_exact(tmp_path, world, k, route)
+
+
+def _db_bit_exact(tmp_path, world, k, route):
     _need(world)
     import torch.multiprocessing as mp
     n_reads, L = 60_000, 150
@@ -183,3 +187,11 @@ def test_multi_gpu_count_batches(tmp_path, world, k):
         batches.append(st[4])
     assert max(batches) >= 3, batches
     util.assert_same_db(ora, out)
+
+
+@pytest.mark.parametrize("world,k,route", [(3, 21, "default"), (3, 51, "nccl-u64"), (6, 31, "default")])
+def test_multi_gpu_world_not_dividing_64(tmp_path, world, k, route):
+    """A world size that does not divide the 64 data files: the pass plan's last slot is a short one (files 63 / 60..63 were
+    dropped before the emulator soak found it; emulator twin: test_sim_multi_rank_db_bit_exact[3|5|6|7]).  Added after round 2's
+    last multi-GPU call, so it comes last."""
+    _db_bit_exact(tmp_path, world, k, route)

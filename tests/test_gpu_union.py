@@ -19,7 +19,7 @@ def test_union_golden(tmp_path, name):
     uc.case_golden(str(tmp_path), name)
 
 
-@pytest.mark.parametrize("k", [6, 7, 8, 15, 21, 31, 32, 33, 51, 64])
+@pytest.mark.parametrize("k", [7, 8, 15, 21, 31, 32, 33, 51, 64])                # (k = 6: tests/test_gpu_zzzz_late.py)
 def test_union_k_sweep(tmp_path, k):
     uc.case_k_sweep(str(tmp_path), k, n=60_000)
 
@@ -84,11 +84,6 @@ def test_value_operations(tmp_path):
 
 def test_union_small_ring(tmp_path, monkeypatch):
     uc.case_small_ring(str(tmp_path), monkeypatch)
-
-
-@pytest.mark.parametrize("k,limit", [(21, 30), (40, 33), (32, 50)])
-def test_stream_block_split(tmp_path, monkeypatch, k, limit):
-    uc.case_stream_block_split(str(tmp_path), monkeypatch, k, limit)
 
 
 @pytest.mark.parametrize("k,decoder", [(21, "warp"), (21, "thread"), (51, "warp"), (64, "thread"), (32, "warp"), (31, "auto")])

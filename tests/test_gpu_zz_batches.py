@@ -36,8 +36,7 @@ def _count_vs_oracle(tmp_path, files, k, w_prefix, op="count"):
 
 
 @pytest.mark.parametrize("k,w_prefix,op,batch_bases", [(21, 14, "count", 2_000_000), (31, 12, "count-forward", 1_500_000),
-                                                       (51, 10, "count", 3_000_000), (9, 6, "count-reverse", 1_000_000),
-                                                       (3, 6, "count", 1_000_000)])
+                                                       (51, 10, "count", 3_000_000), (9, 6, "count-reverse", 1_000_000)])
 def test_count_batches_db_bit_exact(tmp_path, monkeypatch, k, w_prefix, op, batch_bases):
     monkeypatch.setenv("MB_MAX_BATCH_BASES", str(batch_bases))
     reads = synth.reads_fastq_bytes(300_000, 50_000, 150, 0.004, 7 + k)

@@ -428,7 +428,7 @@ def case_stream_block_split(tmp, monkeypatch, k, limit):
     """A prefix with more k-mers than the stream writer keeps in a block (16 Mi in the reference,
     kmers-writer-stream.C:127-141) is written as consecutive blocks of the same prefix under one index entry.  The limit
     is lowered on both sides (MB_STREAM_BLOCK_MAX / ORA_STREAM_BATCH_MAX) so that most of the 4096 prefixes are cut in
-    two to five parts, one of them into parts of exactly the limit; tests/test_gpu_zzzz_stream_split.py holds the real limit
+    two to five parts, one of them into parts of exactly the limit; tests/test_gpu_zzzz_late.py holds the real limit
     against the reference binary.  Written (encoder) and read back (block tables from the container headers): as the input
     of another operation, by the database walk, by the exact lookup."""
     import numpy as np
