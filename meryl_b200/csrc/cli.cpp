@@ -405,6 +405,7 @@ static int flatMain(int argc, char **argv) {
   uint64_t nExpected = 0, memBytes = physicalMemory();
   bool haveOp = false, onlyConfig = false, quiet = false, compress = false;
   const char *outDir = nullptr, *countSuffix = nullptr;
+  std::string countSuffixWord;
   std::vector<const char *> inputs;
   std::vector<char> inputCompress;                     //  per input: was `compress` in force when it was named?
 
@@ -421,7 +422,18 @@ static int flatMain(int argc, char **argv) {
     else if (!strncmp(w, "gpus=", 5))         { nGpus = (uint32_t)strtoul(w + 5, 0, 10); }     //  (not a word of the reference)
     else if (isCountWord(w, &mode))           { haveOp = true; }
     else if (!strcmp(w, "compress"))          { compress = true; }           //  merylCommandBuilder.C:237-240: for the inputs that follow
-    else if (!strncmp(w, "count-suffix=", 13)) { countSuffix = w + 13; }       //  merylCommandBuilder.C:271-274
+    else if (!strncmp(w, "count-suffix=", 13)) {                               //  merylCommandBuilder.C:271-274
+      //  The reference builds the suffix with kmerTiny::addR at this point of the command line (merylOp.H:139-147); in front
+      //  of `k=` the k-mer masks are still zero and every addR drops what came before: only the last base survives, the test
+      //  becomes "ends with A...A<last base>".  Reproduced (the databases are compared byte for byte), and said aloud.
+      countSuffixWord = w + 13;
+      if (k == 0 && countSuffixWord.size() > 1) {
+        countSuffixWord = std::string(countSuffixWord.size() - 1, 'A') + countSuffixWord.back();
+        fprintf(stderr, "NOTE: count-suffix= in front of k=: like the reference, only its last base counts -- keeping the k-mers that end with '%s'.\n",
+                countSuffixWord.c_str());
+      }
+      countSuffix = countSuffixWord.c_str();
+    }
     else if (!strcmp(w, "output")) {
       if (i + 1 >= argc) { fprintf(stderr, "ERROR: 'output' needs a database name.\n"); return 1; }
       outDir = argv[++i];

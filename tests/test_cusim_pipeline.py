@@ -366,3 +366,23 @@ def test_sim_cli_compress_holds_for_the_inputs_that_follow(tmp_path):
         p = subprocess.run([mb.CLI_PATH, "k=15", "memory=2", "count"] + words + ["output", out], capture_output=True, text=True, env=env)
         assert p.returncode == 0, p.stderr
         util.assert_same_db(ref, out)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/meryl not built")
+def test_sim_cli_count_suffix_in_front_of_k(tmp_path):
+    """`count-suffix=GCG` named BEFORE `k=`: the reference builds the suffix while its k-mer masks are still zero
+    (merylOp.H:139-147, kmers-tiny.H:86), only the last base survives and it keeps the k-mers that end with AAG.  The command
+    line tool writes the same directory (and says so); behind `k=` the word means what it says.  Found by
+    tools/fuzz_emulator.py --what cli."""
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(synth.fasta_bytes(1, 20_000, 5))
+    env = dict(os.environ, LD_PRELOAD=SIM_LIB)
+    kept = []
+    for i, words in enumerate((["count-suffix=GCG", "k=12"], ["k=12", "count-suffix=GCG"], ["count-suffix=gct", "k=12"], ["count-suffix=T", "k=12"])):
+        ref, out = str(tmp_path / ("ref%d.meryl" % i)), str(tmp_path / ("cli%d.meryl" % i))
+        util.run_ref(words + ["memory=2", "threads=4", "count-forward", str(fa), "output", ref])
+        p = subprocess.run([mb.CLI_PATH] + words + ["memory=2", "count-forward", str(fa), "output", out], capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr
+        util.assert_same_db(ref, out)
+        kept.append(("NOTE: count-suffix= in front of k=" in p.stderr, {l.split()[0][-3:] for l in util.run_ref_stdout(["print", out]).splitlines()}))
+    assert kept[0] == (True, {"AAG"}) and kept[1] == (False, {"GCG"}) and kept[2] == (True, {"AAT"}) and kept[3][0] is False

@@ -35,6 +35,13 @@ def run_ref(args: list[str], cwd: str | None = None, timeout: int = 600) -> str:
     return p.stderr
 
 
+def run_ref_stdout(args: list[str], timeout: int = 600) -> str:
+    """Run the unmodified reference meryl; returns its stdout (print, histogram, statistics)."""
+    p = subprocess.run([REF_BIN] + args, capture_output=True, text=True, timeout=timeout)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
 def run_oracle(args: list[str], cwd: str | None = None, timeout: int = 600) -> str:
     p = subprocess.run([ORACLE_BIN] + args, cwd=cwd, capture_output=True, text=True, timeout=timeout)
     assert p.returncode == 0, p.stderr[-2000:]

@@ -295,6 +295,10 @@ def one_cli_case(seed, keep):
     opts = ["k=%d" % k, "threads=%d" % int(rng.integers(1, 5))]
     if rng.random() < 0.8: opts.append("memory=%s" % str(rng.choice(["0.5", "1", "2", "4", "8", "0.05"])))
     if rng.random() < 0.4: opts.append("n=%d" % int(rng.choice([1000, 100000, 10000000, 5000000000])))
+    if 8 <= k <= 17 and rng.random() < 0.25:                  # (the reference's simple counter allocates 2 * 4^(k-s) bytes: k - s stays small)
+        s_len = int(rng.integers(max(1, k - 12), min(k - 6, 7) + 1)) if k - 6 >= max(1, k - 12) else 0
+        if s_len:
+            opts.append("count-suffix=" + "".join(str(rng.choice(list("ACGTacgt"))) for _ in range(s_len)))
     opts = [opts[int(i)] for i in rng.permutation(len(opts))]
     tmp = tempfile.mkdtemp(prefix="mbfuzz_")
     what = {"seed": seed, "k": k, "words": opts + [op]}
