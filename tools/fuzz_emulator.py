@@ -317,8 +317,19 @@ def one_cli_case(seed, keep):
                 what["words"].append("compress")
             ins.append(p)
         ref, out = os.path.join(tmp, "ref.meryl"), os.path.join(tmp, "cli.meryl")
-        r = subprocess.run([util.REF_BIN] + opts + [op] + ins + ["output", ref], capture_output=True, text=True)
-        o = subprocess.run([mb.CLI_PATH] + opts + [op] + ins + ["output", out], capture_output=True, text=True, env=dict(os.environ, LD_PRELOAD=SIM_LIB))
+
+        def line(out_dir):
+            if not scramble:
+                return opts + [op] + ins + ["output", out_dir]
+            # the words are order-free (merylCommandBuilder.C:188-549): options between the inputs, the output in front ...
+            words = [[w] for w in [op] + ins] + [["output", out_dir]]
+            for w, at in zip(opts, places):
+                words.insert(int(at * (len(words) + 1)), [w])
+            return [x for w in words for x in w]
+        scramble, places = rng.random() < 0.5, rng.random(len(opts))
+        what["line"] = [os.path.basename(w) for w in line("OUT")]
+        r = subprocess.run([util.REF_BIN] + line(ref), capture_output=True, text=True)
+        o = subprocess.run([mb.CLI_PATH] + line(out), capture_output=True, text=True, env=dict(os.environ, LD_PRELOAD=SIM_LIB))
         try:
             if r.returncode != 0:
                 assert o.returncode != 0, "the reference fails (%s) and meryl-b200 does not" % r.stderr[-150:]
