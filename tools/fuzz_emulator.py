@@ -56,7 +56,7 @@ def make_input(rng, k):
         s = s.tobytes()
         if fastq:
             out += [b"@r%d some text" % r + eol, s + eol, b"+" + (b"r%d" % r if rng.random() < 0.3 else b"") + eol,
-                    (b"@" if rng.random() < 0.2 else b"I") + b"I" * max(0, n - 1) + eol]
+                    ((b"@" if rng.random() < 0.2 else b"I") + b"I" * (n - 1) if n else b"") + eol]
         else:
             out.append(b">s%d" % r + eol)
             w = int(rng.choice([60, 80, 7, 100000]))
@@ -226,7 +226,7 @@ def one_lookup_case(seed, keep):
     for name in KNOBS + UNION_KNOBS + MULTI_KNOBS + ("MB_LOOKUP_BATCH", "MB_LOOKUP_NO_TABLE"):
         os.environ.pop(name, None)
     k = int(rng.choice([8, 13, 16, 21, 22, 31, 32, 33, 51, 64]))
-    rep = [["-existence"], ["-bed"], ["-bed-runs"], ["-wig-count"], ["-wig-depth"]][int(rng.integers(0, 5))]
+    rep = [["-existence"], ["-bed"], ["-bed-runs"], ["-wig-count"], ["-wig-depth"], ["-include"], ["-exclude"]][int(rng.integers(0, 7))]
     env = dict(os.environ, LD_PRELOAD=SIM_LIB)
     if rng.random() < 0.4: env["MB_LOOKUP_BATCH"] = str(int(rng.choice([300, 5000])))
     if rng.random() < 0.2: env["MB_LOOKUP_NO_TABLE"] = "1"
@@ -235,7 +235,7 @@ def one_lookup_case(seed, keep):
     what = {"seed": seed, "k": k, "words": rep, "env": {n: env[n] for n in ("MB_LOOKUP_BATCH", "MB_LOOKUP_NO_TABLE", "MB_UNION_MAX_FILES") if n in env}}
     try:
         dbs, texts = [], []
-        for i in range(int(rng.integers(1, 3))):
+        for i in range(1 if rep[0] in ("-include", "-exclude") else int(rng.integers(1, 3))):     # (the filters take one database)
             data, ext = make_input(rng, k)
             texts.append((data, ext))
             p = os.path.join(tmp, "in%d%s" % (i, ext))
