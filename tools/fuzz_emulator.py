@@ -113,9 +113,19 @@ def one_case(seed, keep):
             what["skipped"] = o.stderr[-200:]
             return what
         try:
+            push = rng.random() < 0.3                       # the merylInput::loadBases seam: the records' bases pushed in pieces
+            what["push"] = bool(push)
             with mb.Counter(k, wp, op, workspace_bytes=int(rng.choice([0, 0, 1 << 28]))) as c:
                 for p in paths:
-                    c.add_file(p)
+                    if not push:
+                        c.add_file(p)
+                        continue
+                    for rec in util.oracle_parse(open(p, "rb").read()).split(b"."):
+                        cuts = sorted(set(int(x) for x in rng.integers(0, len(rec) + 1, size=int(rng.integers(0, 4))))) + [len(rec)]
+                        at = 0
+                        for cut in cuts:
+                            c.add_bases(rec[at:cut], end_of_sequence=(cut == len(rec)))
+                            at = cut
                 c.count()
                 st = c.stats()
                 c.write_db(out)
