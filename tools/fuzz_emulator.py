@@ -114,9 +114,13 @@ def one_case(seed, keep):
             return what
         try:
             push = rng.random() < 0.3                       # the merylInput::loadBases seam: the records' bases pushed in pieces
-            what["push"] = bool(push)
+            shards = int(rng.choice([2, 3, 8])) if (not push and rng.random() < 0.25) else 0      # the gpus=N ingest: every shard of every file
+            what["push"], what["shards"] = bool(push), shards
             with mb.Counter(k, wp, op, workspace_bytes=int(rng.choice([0, 0, 1 << 28]))) as c:
-                for p in paths:
+                for sh in range(shards):
+                    for p in paths:
+                        c.add_file_shard(p, sh, shards)
+                for p in ([] if shards else paths):
                     if not push:
                         c.add_file(p)
                         continue
