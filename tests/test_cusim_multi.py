@@ -157,7 +157,7 @@ def test_sim_multi_rank_count_batches(tmp_path, monkeypatch, world, k, wp, weigh
     shares (and one with nothing) close different numbers of batches of their own; every rank merges the files it owns,
     rank 0 collects the histograms.  Same db as the single-process oracle."""
     monkeypatch.setenv("MB_MAX_BATCH_BASES", "60000")
-    n_reads, rl = 3_000, 150
+    n_reads, rl = (3_000 if world == 2 and k == 21 else 1_800), 150
     data = synth.reads_fastq_bytes(20_000, n_reads, rl, 0.003, 90 + k + world)
     fq = tmp_path / "reads.fq"
     fq.write_bytes(data)

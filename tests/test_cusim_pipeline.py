@@ -378,7 +378,7 @@ def test_sim_cli_count_suffix_in_front_of_k(tmp_path):
     fa.write_bytes(synth.fasta_bytes(1, 20_000, 5))
     env = dict(os.environ, LD_PRELOAD=SIM_LIB)
     kept = []
-    for i, words in enumerate((["count-suffix=GCG", "k=12"], ["k=12", "count-suffix=GCG"], ["count-suffix=gct", "k=12"], ["count-suffix=T", "k=12"])):
+    for i, words in enumerate((["count-suffix=GCG", "k=10"], ["k=10", "count-suffix=GCG"], ["count-suffix=gct", "k=10"], ["count-suffix=T", "k=10"])):
         ref, out = str(tmp_path / ("ref%d.meryl" % i)), str(tmp_path / ("cli%d.meryl" % i))
         util.run_ref(words + ["memory=2", "threads=4", "count-forward", str(fa), "output", ref])
         p = subprocess.run([mb.CLI_PATH] + words + ["memory=2", "count-forward", str(fa), "output", out], capture_output=True, text=True, env=env)
