@@ -538,7 +538,15 @@ static size_t shardCut(const uint8_t *d, size_t n, uint32_t i, uint32_t nShards)
     const uint8_t *lf = (const uint8_t *)memchr(d + p, '\n', n - p);
     if (!lf || (size_t)(lf - d) + 1 >= n) return n;
     p = (size_t)(lf - d) + 1;
-    if (d[p] == '>' && d[0] == '>') return p;              //  (in a FASTQ file a line that starts with '>' is a quality line)
+    if (d[p] == '>' && d[0] == '>') {                      //  (in a FASTQ file a line that starts with '>' is a quality line)
+      //  ... unless the last non-blank line in front of it is a header too: after the header of a record without bases the
+      //  reference's grammar reads the next line as sequence whatever it starts with -- not a record start, try the next one
+      size_t q = p;
+      while (q > 0 && (d[q - 1] == '\n' || d[q - 1] == '\r')) q--;            //  end of the last non-blank line
+      while (q > 0 && d[q - 1] != '\n') q--;                                   //  its start
+      if (d[q] != '>' || q == p) return p;
+      continue;
+    }
     if (d[p] == '@' && d[0] == '@') {
       const uint8_t *l1 = (const uint8_t *)memchr(d + p, '\n', n - p);
       const uint8_t *l2 = l1 ? (const uint8_t *)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - d)) : nullptr;
